@@ -1,0 +1,327 @@
+"""ctypes bindings for the CPU oracle (oracle/libtb_oracle.so, oracle/_ref/libtb_ref.so).
+
+TEST INFRASTRUCTURE ONLY — see oracle/tb_oracle.h.  May be imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.  The product package
+(trackingbench_slam_b200) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'),
+                     ('response', '<f4'), ('octave', '<i4'), ('class_id', '<i4')])
+MATCH_DTYPE = np.dtype([('queryIdx', '<i4'), ('trainIdx', '<i4'), ('imgIdx', '<i4'), ('distance', '<f4')])
+
+
+class MatcherParams(C.Structure):
+    _fields_ = [('TH_LOW', C.c_int), ('TH_HIGH', C.c_int), ('HISTO_LENGTH', C.c_int),
+                ('checkOrientation', C.c_int), ('nRatio', C.c_float)]
+
+
+class Pinhole(C.Structure):
+    _fields_ = [('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
+                ('width', C.c_int), ('height', C.c_int), ('d', C.c_float * 5)]
+
+
+def build(force=False):
+    """Compile the C restatement (always) and oracle/_ref (only where /root/reference exists)."""
+    so = os.path.join(_HERE, 'libtb_oracle.so')
+    src_newer = (not os.path.exists(so)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
+        for f in ('tb_oracle.c', 'tb_oracle.h', 'orb_pattern.inc'))
+    if force or src_newer or (os.path.exists('/root/reference/src/extractors/ORBextractor.cpp')
+                              and not os.path.exists(os.path.join(_HERE, '_ref', 'libtb_ref.so'))):
+        subprocess.check_call(['make', '-C', _HERE, '-s'] + (['-B'] if force else []))
+
+
+_lib = None
+_ref = {}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(os.path.join(_HERE, 'libtb_oracle.so'))
+        _lib.tbo_fast_atan2.restype = C.c_float
+        _lib.tbo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.tbo_ic_angle.restype = C.c_float
+        _lib.tbo_shi_tomasi.restype = C.c_float
+        _lib.tbo_grid_build.restype = C.c_void_p
+    return _lib
+
+
+def ref_available(unpinned=False):
+    name = 'libtb_ref_unpinned.so' if unpinned else 'libtb_ref.so'
+    return os.path.exists(os.path.join(_HERE, '_ref', name))
+
+
+def ref_lib(unpinned=False):
+    name = 'libtb_ref_unpinned.so' if unpinned else 'libtb_ref.so'
+    if name not in _ref:
+        build()
+        L = C.CDLL(os.path.join(_HERE, '_ref', name))
+        L.tbref_extractor_new.restype = C.c_void_p
+        L.tbref_extractor_delete.argtypes = [C.c_void_p]
+        _ref[name] = L
+    return _ref[name]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+# ---------------------------------------------------------------- pyramid
+def scale_factors(n_levels, scale):
+    sf = np.zeros(n_levels, np.float32)
+    lib().tbo_scale_factors(n_levels, C.c_float(scale), _p(sf))
+    return sf
+
+
+def level_sizes(w0, h0, sf):
+    out = []
+    for s in sf:
+        w, h = C.c_int(), C.c_int()
+        lib().tbo_level_size(w0, h0, C.c_float(float(s)), C.byref(w), C.byref(h))
+        out.append((w.value, h.value))
+    return out
+
+
+def resize_linear(src, dw, dh):
+    src = _u8(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().tbo_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def pyramid(img, n_levels, scale):
+    """Frame::ComputePyramid: level i = resize(level i-1 -> int(cols*sf[i]) x int(rows*sf[i]))."""
+    img = _u8(img)
+    sf = scale_factors(n_levels, scale)
+    sizes = level_sizes(img.shape[1], img.shape[0], sf)
+    levels = [img]
+    for i in range(1, n_levels):
+        levels.append(resize_linear(levels[-1], sizes[i][0], sizes[i][1]))
+    return levels, sf
+
+
+# ---------------------------------------------------------------- primitives
+def fast9(img, T, nonmax=True):
+    img = _u8(img)
+    cap = img.size // 2 + 16
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().tbo_fast9(_p(img), img.strides[0], img.shape[1], img.shape[0], int(T), int(nonmax), _p(out), cap)
+    return out[:n]
+
+
+def gauss7x7(img):
+    img = _u8(img)
+    dst = np.empty_like(img)
+    lib().tbo_gauss7x7(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().tbo_fast_atan2(float(y), float(x))
+
+
+def ic_angle(img, cx, cy):
+    img = _u8(img)
+    return lib().tbo_ic_angle(_p(img), img.strides[0], int(cx), int(cy))
+
+
+def rbrief(blur, cx, cy, angle_deg):
+    blur = _u8(blur)
+    d = np.zeros(32, np.uint8)
+    lib().tbo_rbrief(_p(blur), blur.strides[0], int(cx), int(cy), C.c_float(angle_deg), _p(d))
+    return d
+
+
+def shi_tomasi(img, u, v):
+    img = _u8(img)
+    return lib().tbo_shi_tomasi(_p(img), img.shape[1], img.shape[0], img.strides[0], int(u), int(v))
+
+
+# ---------------------------------------------------------------- extractor
+def orb_budget(n_levels, factor, target):
+    b = np.zeros(n_levels, np.int32)
+    lib().tbo_orb_budget(n_levels, C.c_float(float(factor)), int(target), _p(b))
+    return b
+
+
+def cell_candidates(img, initTh, minTh):
+    img = _u8(img)
+    cap = img.size // 4 + 16
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().tbo_cell_candidates(_p(img), img.shape[1], img.shape[0], img.strides[0],
+                                  C.c_float(initTh), C.c_float(minTh), _p(out), cap)
+    return out[:n]
+
+
+def distribute_octree(cand, exit_kps, minX, maxX, minY, maxY, N):
+    cand = np.ascontiguousarray(cand, KP_DTYPE)
+    ex = np.ascontiguousarray(exit_kps if exit_kps is not None else np.zeros(0, KP_DTYPE), KP_DTYPE)
+    out = np.zeros(len(cand) + 8, KP_DTYPE)
+    n = lib().tbo_distribute_octree(_p(cand), len(cand), _p(ex), len(ex), minX, maxX, minY, maxY, int(N),
+                                    _p(out), len(out))
+    return out[:n]
+
+
+def _level_args(levels):
+    levels = [_u8(l) for l in levels]
+    n = len(levels)
+    ptrs = (C.c_void_p * n)(*[l.ctypes.data for l in levels])
+    w = (C.c_int * n)(*[l.shape[1] for l in levels])
+    h = (C.c_int * n)(*[l.shape[0] for l in levels])
+    s = (C.c_int * n)(*[l.strides[0] for l in levels])
+    return levels, ptrs, w, h, s
+
+
+def orb_extract(levels, sf, target, initTh, minTh, exit_kps=None, budget=None, cap=None):
+    """ORBExtractor::operator() (budget None) or AddPoints (budget = previous per-level budget)."""
+    levels, ptrs, w, h, s = _level_args(levels)
+    n = len(levels)
+    sf = np.ascontiguousarray(sf, np.float32)
+    cap = cap or (4 * target + 256)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    npl = np.zeros(n, np.int32)
+    ex = np.ascontiguousarray(exit_kps if exit_kps is not None else np.zeros(0, KP_DTYPE), KP_DTYPE)
+    bud = None if budget is None else np.ascontiguousarray(budget, np.int32)
+    cnt = lib().tbo_orb_extract(ptrs, w, h, s, n, _p(sf), int(target), C.c_float(initTh), C.c_float(minTh),
+                                _p(ex), len(ex), None if bud is None else _p(bud), _p(kps), _p(desc), cap, _p(npl))
+    assert cnt <= cap, (cnt, cap)
+    return kps[:cnt].copy(), desc[:cnt].copy(), npl
+
+
+class RefExtractor:
+    """The reference's own ORBExtractor (oracle/_ref, compiled from /root/reference unmodified)."""
+
+    def __init__(self, unpinned=False):
+        self.L = ref_lib(unpinned)
+        self.h = C.c_void_p(self.L.tbref_extractor_new())
+
+    def __del__(self):
+        try:
+            self.L.tbref_extractor_delete(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, levels, sf, target, initTh, minTh, cap=None):
+        levels, ptrs, w, h, s = _level_args(levels)
+        sf = np.ascontiguousarray(sf, np.float32)
+        cap = cap or (4 * target + 256)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.tbref_extract(self.h, ptrs, w, h, s, len(levels), _p(sf), int(target), C.c_float(initTh),
+                                 C.c_float(minTh), _p(kps), _p(desc), cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def add_points(self, levels, sf, target, initTh, minTh, exit_kps, cap=None):
+        levels, ptrs, w, h, s = _level_args(levels)
+        sf = np.ascontiguousarray(sf, np.float32)
+        ex = np.ascontiguousarray(exit_kps, KP_DTYPE)
+        cap = cap or (4 * target + 256)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.tbref_add_points(self.h, ptrs, w, h, s, len(levels), _p(sf), int(target), C.c_float(initTh),
+                                    C.c_float(minTh), _p(ex), len(ex), _p(kps), _p(desc), cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+
+# ---------------------------------------------------------------- matchers
+def hamming256(a, b):
+    a, b = _u8(a), _u8(b)
+    return lib().tbo_hamming256(_p(a), _p(b))
+
+
+def knn2(q, t):
+    q, t = _u8(q), _u8(t)
+    idx = np.zeros(len(q), np.int32)
+    best = np.zeros(len(q), np.int32)
+    second = np.zeros(len(q), np.int32)
+    lib().tbo_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(best), _p(second))
+    return idx, best, second
+
+
+def bf_cross(d1, d2):
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(max(len(d1), 1), MATCH_DTYPE)
+    n = lib().tbo_bf_cross(_p(d1), len(d1), _p(d2), len(d2), _p(out))
+    return out[:n].copy()
+
+
+def search_by_bf(d1, d2, ratio, minTh):
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(max(len(d1), 1), MATCH_DTYPE)
+    n = lib().tbo_search_by_bf(_p(d1), len(d1), _p(d2), len(d2), C.c_float(ratio), C.c_float(minTh), _p(out))
+    return out[:n].copy()
+
+
+def features_in_area(kps, cols, rows, x, y, r, minLevel=-1, maxLevel=-1):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    g = C.c_void_p(lib().tbo_grid_build(_p(kps), len(kps), cols, rows))
+    out = np.zeros(len(kps) + 1, np.int32)
+    n = lib().tbo_features_in_area(g, C.c_float(x), C.c_float(y), C.c_float(r), minLevel, maxLevel, _p(out), len(out))
+    lib().tbo_grid_free(g)
+    return out[:n].copy()
+
+
+def search_by_violence(params, k1, d1, k2, d2, cols2, rows2, min_level=0, max_level=1, search_r=10.0):
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(len(k1) + 1, MATCH_DTYPE)
+    n = lib().tbo_search_by_violence(C.byref(params), _p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2),
+                                     cols2, rows2, min_level, max_level, C.c_float(search_r), _p(out))
+    return out[:n].copy()
+
+
+def search_by_projection(params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1, k2, mp_valid, mp_xyz, mp_desc):
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, mp_desc = _u8(d1), _u8(mp_desc)
+    Tcw1 = np.ascontiguousarray(Tcw1, np.float32)
+    sf1 = np.ascontiguousarray(sf1, np.float32)
+    mp_valid = _u8(mp_valid)
+    mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+    fm = None if f1_matched is None else _u8(f1_matched)
+    out = np.zeros(len(k2) + 1, MATCH_DTYPE)
+    n = lib().tbo_search_by_projection(C.byref(params), C.byref(cam), _p(Tcw1), _p(k1), _p(d1), len(k1),
+                                       None if fm is None else _p(fm), _p(sf1), len(sf1), cols1, rows1,
+                                       _p(k2), len(k2), _p(mp_valid), _p(mp_xyz), _p(mp_desc), _p(out))
+    return out[:n].copy()
+
+
+def search_by_projection_map(params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1,
+                             mp_bad, mp_xyz, mp_normal, mp_desc, radio):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE)
+    d1, mp_desc = _u8(d1), _u8(mp_desc)
+    Tcw1 = np.ascontiguousarray(Tcw1, np.float32)
+    sf1 = np.ascontiguousarray(sf1, np.float32)
+    mp_bad = _u8(mp_bad)
+    mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+    mp_normal = np.ascontiguousarray(mp_normal, np.float32)
+    fm = None if f1_matched is None else _u8(f1_matched)
+    out = np.zeros(len(mp_bad) + 1, MATCH_DTYPE)
+    n = lib().tbo_search_by_projection_map(C.byref(params), C.byref(cam), _p(Tcw1), _p(k1), _p(d1), len(k1),
+                                           None if fm is None else _p(fm), _p(sf1), cols1, rows1,
+                                           len(mp_bad), _p(mp_bad), _p(mp_xyz), _p(mp_normal), _p(mp_desc),
+                                           C.c_float(radio), _p(out))
+    return out[:n].copy()
+
+
+def three_maxima(hist_sizes):
+    hs = np.ascontiguousarray(hist_sizes, np.int32)
+    a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    lib().tbo_three_maxima(_p(hs), len(hs), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value

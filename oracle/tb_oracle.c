@@ -1,0 +1,967 @@
+/* tb_oracle.c — CPU ORACLE (test infrastructure, see tb_oracle.h header comment).
+ *
+ * Plain-C restatement of the reference feature-tracking front end.  Written for clarity and
+ * exactness, not speed.  Build: gcc -std=c99 -O2 -ffp-contract=off -fPIC -shared (see Makefile);
+ * -ffp-contract=off because the reference is built without optimisation flags
+ * (CMakeLists.txt:4-6 commented out) so no FMA contraction happens in its float math.
+ */
+#include "tb_oracle.h"
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint8_t u8;
+
+/* cvRound: round-half-to-even (SSE cvtsd2si / cvtss2si under the default rounding mode). */
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_floor_f(float v) { int i = (int)v; return i - (v < (float)i); }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* ------------------------------------------------------------------------------------------
+ * Frame scale tables — src/types/Frame.cpp:18-29:  sf[i] = sf[i-1] * scale  (float32 chain)
+ * ------------------------------------------------------------------------------------------ */
+void tbo_scale_factors(int n_levels, float scale, float *sf)
+{
+    for (int i = 0; i < n_levels; i++) sf[i] = 1.f;
+    for (int i = 1; i < n_levels; i++) sf[i] = sf[i - 1] * scale;
+}
+
+/* Level size — src/types/Frame.cpp:424: cv::Size(image.cols * scale, image.rows * scale):
+ * int * float -> float, truncated to int. */
+void tbo_level_size(int w0, int h0, float sf_level, int *w, int *h)
+{
+    *w = (int)((float)w0 * sf_level);
+    *h = (int)((float)h0 * sf_level);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cv::resize(src, dst, dsize) default INTER_LINEAR, 8UC1 — call site src/types/Frame.cpp:423.
+ * OpenCV (imgproc/resize.cpp) fixed-point path: 11-bit coefficients (INTER_RESIZE_COEF_SCALE =
+ * 2048), horizontal pass into int32, vertical pass ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2)>>2.
+ * When both scale factors are exactly 2 OpenCV silently switches to INTER_AREA (2x2 mean).
+ * ------------------------------------------------------------------------------------------ */
+void tbo_resize_linear_u8(const u8 *src, int sw, int sh, int sstride, u8 *dst, int dw, int dh, int dstride)
+{
+    double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+    double scale_x = 1. / inv_scale_x, scale_y = 1. / inv_scale_y;
+    int iscale_x = (int)lrint(scale_x), iscale_y = (int)lrint(scale_y);
+    int is_area_fast = fabs(scale_x - iscale_x) < DBL_EPSILON && fabs(scale_y - iscale_y) < DBL_EPSILON;
+    if (is_area_fast && iscale_x == 2 && iscale_y == 2) {
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++) {
+                const u8 *s = src + (size_t)(2 * y) * sstride + 2 * x;
+                dst[(size_t)y * dstride + x] = (u8)((s[0] + s[1] + s[sstride] + s[sstride + 1] + 2) >> 2);
+            }
+        return;
+    }
+    int *xofs = (int *)malloc(sizeof(int) * dw);
+    short *ialpha = (short *)malloc(sizeof(short) * 2 * dw);
+    int *rows = (int *)malloc(sizeof(int) * 2 * dw);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor_f(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        ialpha[2 * dx] = (short)cv_round_f((1.f - fx) * 2048.f);
+        ialpha[2 * dx + 1] = (short)cv_round_f(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor_f(fy);
+        fy -= sy;
+        short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
+        int sy0 = imin(imax(sy, 0), sh - 1), sy1 = imin(imax(sy + 1, 0), sh - 1);
+        const u8 *r0 = src + (size_t)sy0 * sstride, *r1 = src + (size_t)sy1 * sstride;
+        for (int dx = 0; dx < dw; dx++) {
+            int sx = xofs[dx], sx1 = imin(sx + 1, sw - 1);
+            rows[dx] = r0[sx] * ialpha[2 * dx] + r0[sx1] * ialpha[2 * dx + 1];
+            rows[dw + dx] = r1[sx] * ialpha[2 * dx] + r1[sx1] * ialpha[2 * dx + 1];
+        }
+        for (int dx = 0; dx < dw; dx++) {
+            int v = (((b0 * (rows[dx] >> 4)) >> 16) + ((b1 * (rows[dw + dx] >> 4)) >> 16) + 2) >> 2;
+            dst[(size_t)dy * dstride + dx] = (u8)v;
+        }
+    }
+    free(xofs); free(ialpha); free(rows);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cv::FAST(img, kps, T, nonmax) TYPE_9_16 — call sites src/extractors/ORBextractor.cpp:785,790.
+ * OpenCV features2d/fast.cpp + fast_score.cpp: a pixel is a corner iff 9 contiguous ring pixels
+ * are all > v+T or all < v-T; score = cornerScore<16> = max(A,B)-1 where A = max over arcs of the
+ * min of d_k = v - ring_k, B the same for -d_k; 3-px border never tested; non-max suppression
+ * keeps strict maxima of the score buffer (non-corners hold 0) over the 8-neighbourhood;
+ * output row-major; KeyPoint(x, y, 7.f, -1, score).
+ * ------------------------------------------------------------------------------------------ */
+static const int RING_DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int RING_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+/* m = max(A,B): corner at T iff m > T; score = m - 1 (threshold independent). */
+static int fast9_m(const u8 *p, int stride)
+{
+    int d[25];
+    int v = p[0];
+    for (int k = 0; k < 16; k++) d[k] = v - p[RING_DY[k] * stride + RING_DX[k]];
+    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
+    int A = INT_MIN, B = INT_MIN;
+    for (int s = 0; s < 16; s++) {
+        int mn = INT_MAX, mx = INT_MIN;
+        for (int k = s; k < s + 9; k++) { mn = imin(mn, d[k]); mx = imax(mx, d[k]); }
+        A = imax(A, mn);
+        B = imax(B, -mx);
+    }
+    return imax(A, B);
+}
+
+int tbo_fast9(const u8 *img, int stride, int w, int h, int T, int nonmax, tbo_kp *out, int cap)
+{
+    if (w < 7 || h < 7) return 0;
+    int *score = (int *)calloc((size_t)w * h, sizeof(int)); /* 0 for non-corners, as OpenCV's row buffers */
+    u8 *corner = (u8 *)calloc((size_t)w * h, 1);
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            int m = fast9_m(img + (size_t)y * stride + x, stride);
+            if (m > T) { score[(size_t)y * w + x] = m - 1; corner[(size_t)y * w + x] = 1; }
+        }
+    int n = 0;
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            if (!corner[(size_t)y * w + x]) continue;
+            int s = score[(size_t)y * w + x];
+            int keep = 1;
+            if (nonmax) {
+                for (int dy = -1; dy <= 1 && keep; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        if (!dx && !dy) continue;
+                        if (!(s > score[(size_t)(y + dy) * w + x + dx])) { keep = 0; break; }
+                    }
+            }
+            if (!keep) continue;
+            if (n < cap) {
+                tbo_kp k = {(float)x, (float)y, 7.f, -1.f, (float)s, 0, -1};
+                out[n] = k;
+            }
+            n++;
+        }
+    free(score); free(corner);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cv::GaussianBlur(img, img, Size(7,7), 2, 2, BORDER_REFLECT_101) on CV_8U — call sites
+ * src/extractors/ORBextractor.cpp:884,960.  OpenCV >= 3.4.2 uses the bit-exact fixed-point path
+ * (imgproc/smooth.dispatch.cpp, ufixedpoint16): kernel {18,34,48,56,48,34,18}/256, horizontal
+ * pass in 8.8, vertical pass in 16.16, one final rounding (v + 32768) >> 16.
+ * ------------------------------------------------------------------------------------------ */
+static inline int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    }
+    return p;
+}
+
+void tbo_gauss7x7(const u8 *src, int w, int h, int sstride, u8 *dst, int dstride)
+{
+    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    uint16_t *tmp = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * h);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = 0; i < 7; i++) s += K[i] * src[(size_t)y * sstride + reflect101(x + i - 3, w)];
+            tmp[(size_t)y * w + x] = (uint16_t)s;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint32_t s = 0;
+            for (int j = 0; j < 7; j++) s += (uint32_t)K[j] * tmp[(size_t)reflect101(y + j - 3, h) * w + x];
+            dst[(size_t)y * dstride + x] = (u8)((s + 32768u) >> 16);
+        }
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cv::fastAtan2(y, x) — call site src/extractors/ORBextractor.cpp:43.  OpenCV core/mathfuncs_core
+ * scalar path: 7th-order odd polynomial, constants are float x float products, no FMA.
+ * ------------------------------------------------------------------------------------------ */
+float tbo_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * ORBExtractor — src/extractors/ORBextractor.cpp
+ * ------------------------------------------------------------------------------------------ */
+#define HALF_PATCH 15
+#define EDGE_THRESHOLD 19
+
+static const int8_t ORB_PATTERN[256 * 4] = {
+#include "orb_pattern.inc"
+};
+
+/* umax table — ORBextractor.cpp:389-404 */
+static void make_umax(int *umax)
+{
+    int v, v0, vmax = cv_floor_f(HALF_PATCH * sqrtf(2.f) / 2 + 1);
+    int vmin = (int)ceil(HALF_PATCH * sqrt(2.f) / 2);
+    const double hp2 = HALF_PATCH * HALF_PATCH;
+    for (v = 0; v <= vmax; ++v) umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+}
+
+/* IC_Angle — ORBextractor.cpp:17-44 (on the un-blurred level image) */
+float tbo_ic_angle(const u8 *img, int stride, int cx, int cy)
+{
+    int umax[HALF_PATCH + 2];
+    make_umax(umax);
+    int m_01 = 0, m_10 = 0;
+    const u8 *center = img + (size_t)cy * stride + cx;
+    for (int u = -HALF_PATCH; u <= HALF_PATCH; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH; ++v) {
+        int v_sum = 0, d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int val_plus = center[u + v * stride], val_minus = center[u - v * stride];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+    }
+    return tbo_fast_atan2((float)m_01, (float)m_10);
+}
+
+/* computeOrbDescriptor — ORBextractor.cpp:46-87 (on the blurred level image).
+ * cos/sin resolve to the float overloads (using namespace std) = glibc cosf/sinf. */
+void tbo_rbrief(const u8 *blur, int stride, int cx, int cy, float angle_deg, u8 *desc)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float angle = angle_deg * factorPI;
+    float a = cosf(angle), b = sinf(angle);
+    const u8 *center = blur + (size_t)cy * stride + cx;
+    const int8_t *pat = ORB_PATTERN;
+    for (int i = 0; i < 32; ++i, pat += 32) {
+        int val = 0;
+        for (int k = 0; k < 8; k++) {
+            const int8_t *q = pat + 4 * k;
+            int t0 = center[cv_round_f(q[0] * b + q[1] * a) * stride + cv_round_f(q[0] * a - q[1] * b)];
+            int t1 = center[cv_round_f(q[2] * b + q[3] * a) * stride + cv_round_f(q[2] * a - q[3] * b)];
+            val |= (t0 < t1) << k;
+        }
+        desc[i] = (u8)val;
+    }
+}
+
+/* Per-level feature budget — ORBextractor.cpp:919-930 */
+void tbo_orb_budget(int n_levels, float factor, int target, int *per_level)
+{
+    float nDesired = target * (1 - factor) / (1 - (float)pow((double)factor, (double)n_levels));
+    int sum = 0;
+    for (int level = 0; level < n_levels - 1; level++) {
+        per_level[level] = cv_round_f(nDesired);
+        sum += per_level[level];
+        nDesired *= factor;
+    }
+    per_level[n_levels - 1] = imax(target - sum, 0);
+}
+
+/* Cell loop of ComputeKeyPointsOctTree — ORBextractor.cpp:743-804.  Output coordinates are
+ * relative to (minBorderX, minBorderY) = (16,16) exactly as vToDistributeKeys holds them. */
+int tbo_cell_candidates(const u8 *img, int w, int h, int stride, float initTh, float minTh, tbo_kp *out, int cap)
+{
+    const float W = 30;
+    const int minBorderX = EDGE_THRESHOLD - 3, minBorderY = minBorderX;
+    const int maxBorderX = w - EDGE_THRESHOLD + 3, maxBorderY = h - EDGE_THRESHOLD + 3;
+    const float width = (float)(maxBorderX - minBorderX), height = (float)(maxBorderY - minBorderY);
+    const int nCols = (int)(width / W), nRows = (int)(height / W);
+    if (nCols <= 0 || nRows <= 0) return 0;
+    const int wCell = (int)ceilf(width / (float)nCols), hCell = (int)ceilf(height / (float)nRows);
+    int n = 0;
+    int cell_cap = (wCell + 6) * (hCell + 6);
+    tbo_kp *cell = (tbo_kp *)malloc(sizeof(tbo_kp) * (size_t)cell_cap);
+    for (int i = 0; i < nRows; i++) {
+        const float iniY = (float)minBorderY + (float)i * (float)hCell;
+        float maxY = iniY + (float)hCell + 6.f;
+        if (iniY >= (float)maxBorderY - 3.f) continue;
+        if (maxY > (float)maxBorderY) maxY = (float)maxBorderY;
+        for (int j = 0; j < nCols; j++) {
+            const float iniX = minBorderX + (float)(j * wCell);
+            float maxX = iniX + (float)wCell + 6.f;
+            if (iniX >= (float)maxBorderX - 6.f) continue;
+            if (maxX > (float)maxBorderX) maxX = (float)maxBorderX;
+            int x0 = (int)iniX, x1 = (int)maxX, y0 = (int)iniY, y1 = (int)maxY;
+            const u8 *roi = img + (size_t)y0 * stride + x0;
+            int nc = tbo_fast9(roi, stride, x1 - x0, y1 - y0, (int)initTh, 1, cell, cell_cap);
+            if (nc == 0) nc = tbo_fast9(roi, stride, x1 - x0, y1 - y0, (int)minTh, 1, cell, cell_cap);
+            for (int k = 0; k < nc; k++) {
+                cell[k].x += (float)j * (float)wCell;
+                cell[k].y += (float)i * (float)hCell;
+                if (n < cap) out[n] = cell[k];
+                n++;
+            }
+        }
+    }
+    free(cell);
+    return n;
+}
+
+/* ---- DistributeOctTree — ORBextractor.cpp:494-733, ExtractorNode::DivideNode :416-491 ---- */
+typedef struct {
+    int ulx, urx, uly, bry; /* UL.x, UR.x, UL.y, BR.y (BL/BR.x are redundant) */
+    int *keys, nkeys;       /* indices into cand, in vKeys order */
+    int *ekeys, nekeys;     /* indices into exit keys */
+    int no_more;
+    int prev, next;         /* std::list links (-1 = end) */
+} onode;
+
+typedef struct {
+    onode *n;
+    int count, cap;
+    int head, tail, size;
+} olist;
+
+static int ol_new(olist *L)
+{
+    if (L->count == L->cap) {
+        L->cap = L->cap ? L->cap * 2 : 256;
+        L->n = (onode *)realloc(L->n, sizeof(onode) * (size_t)L->cap);
+    }
+    memset(&L->n[L->count], 0, sizeof(onode));
+    L->n[L->count].prev = L->n[L->count].next = -1;
+    return L->count++;
+}
+static void ol_push_front(olist *L, int id)
+{
+    L->n[id].prev = -1;
+    L->n[id].next = L->head;
+    if (L->head >= 0) L->n[L->head].prev = id; else L->tail = id;
+    L->head = id;
+    L->size++;
+}
+static void ol_push_back(olist *L, int id)
+{
+    L->n[id].next = -1;
+    L->n[id].prev = L->tail;
+    if (L->tail >= 0) L->n[L->tail].next = id; else L->head = id;
+    L->tail = id;
+    L->size++;
+}
+static int ol_erase(olist *L, int id) /* returns next */
+{
+    int p = L->n[id].prev, nx = L->n[id].next;
+    if (p >= 0) L->n[p].next = nx; else L->head = nx;
+    if (nx >= 0) L->n[nx].prev = p; else L->tail = p;
+    L->size--;
+    free(L->n[id].keys); free(L->n[id].ekeys);
+    L->n[id].keys = L->n[id].ekeys = NULL;
+    return nx;
+}
+
+/* DivideNode: children ids written to c[4] (n1..n4). */
+static void divide_node(olist *L, int id, const tbo_kp *cand, const tbo_kp *ex, int c[4])
+{
+    for (int k = 0; k < 4; k++) c[k] = ol_new(L);
+    onode *P = &L->n[id]; /* taken after the reallocs above */
+    const int halfX = (int)ceilf((float)(P->urx - P->ulx) / 2);
+    const int halfY = (int)ceilf((float)(P->bry - P->uly) / 2);
+    onode *n1 = &L->n[c[0]], *n2 = &L->n[c[1]], *n3 = &L->n[c[2]], *n4 = &L->n[c[3]];
+    n1->ulx = P->ulx; n1->urx = P->ulx + halfX; n1->uly = P->uly; n1->bry = P->uly + halfY;
+    n2->ulx = n1->urx; n2->urx = P->urx; n2->uly = P->uly; n2->bry = P->uly + halfY;
+    n3->ulx = P->ulx; n3->urx = n1->urx; n3->uly = n1->bry; n3->bry = P->bry;
+    n4->ulx = n1->urx; n4->urx = P->urx; n4->uly = n1->bry; n4->bry = P->bry;
+    for (int k = 0; k < 4; k++) {
+        L->n[c[k]].keys = (int *)malloc(sizeof(int) * (size_t)(P->nkeys + 1));
+        L->n[c[k]].ekeys = (int *)malloc(sizeof(int) * (size_t)(P->nekeys + 1));
+    }
+    const float mx = (float)n1->urx, my = (float)n1->bry;
+    for (int k = 0; k < P->nkeys; k++) {
+        const tbo_kp *kp = &cand[P->keys[k]];
+        onode *d = kp->x < mx ? (kp->y < my ? n1 : n3) : (kp->y < my ? n2 : n4);
+        d->keys[d->nkeys++] = P->keys[k];
+    }
+    for (int k = 0; k < P->nekeys; k++) {
+        const tbo_kp *kp = &ex[P->ekeys[k]];
+        onode *d = kp->x < mx ? (kp->y < my ? n1 : n3) : (kp->y < my ? n2 : n4);
+        d->ekeys[d->nekeys++] = P->ekeys[k];
+    }
+    for (int k = 0; k < 4; k++)
+        if (L->n[c[k]].nkeys == 1) L->n[c[k]].no_more = 1;
+}
+
+typedef struct { int size, id, ulx, uly; } sz_node;
+/* PINNED comparator: the reference sorts pair<int, ExtractorNode*> (ORBextractor.cpp:643), i.e.
+ * ties on size are broken by heap address — not reproducible run to run.  The oracle (and
+ * oracle/_ref) pin ties by (UL.x, UL.y) ascending; consumed from the back as the reference does. */
+static int sz_cmp(const void *a, const void *b)
+{
+    const sz_node *p = (const sz_node *)a, *q = (const sz_node *)b;
+    if (p->size != q->size) return p->size < q->size ? -1 : 1;
+    if (p->ulx != q->ulx) return p->ulx < q->ulx ? -1 : 1;
+    if (p->uly != q->uly) return p->uly < q->uly ? -1 : 1;
+    return p->id < q->id ? -1 : (p->id > q->id);
+}
+
+/* split node `id`, push non-empty children to the front (n1..n4 order), collect expandable */
+static void split_push(olist *L, int id, const tbo_kp *cand, const tbo_kp *ex, sz_node *exp, int *nexp)
+{
+    int c[4];
+    divide_node(L, id, cand, ex, c);
+    for (int k = 0; k < 4; k++) {
+        onode *ch = &L->n[c[k]];
+        if (ch->nkeys > 0) {
+            ol_push_front(L, c[k]);
+            if (ch->nkeys > 1) {
+                sz_node s = {ch->nkeys, c[k], ch->ulx, ch->uly};
+                exp[(*nexp)++] = s;
+            }
+        } else {
+            free(ch->keys); free(ch->ekeys);
+            ch->keys = ch->ekeys = NULL;
+        }
+    }
+}
+
+int tbo_distribute_octree(const tbo_kp *cand, int n_cand, const tbo_kp *ex, int n_exit,
+                          int minX, int maxX, int minY, int maxY, int N, tbo_kp *out, int cap)
+{
+    const int nIni = (int)roundf((float)(maxX - minX) / (maxY - minY));
+    const float hX = (float)(maxX - minX) / nIni;
+    olist L = {0};
+    L.head = L.tail = -1;
+    if (nIni <= 0) return 0;
+    for (int i = 0; i < nIni; i++) {
+        int id = ol_new(&L);
+        onode *ni = &L.n[id];
+        ni->ulx = (int)(hX * (float)i);
+        ni->urx = (int)(hX * (float)(i + 1));
+        ni->uly = 0;
+        ni->bry = maxY - minY;
+        ni->keys = (int *)malloc(sizeof(int) * (size_t)(n_cand + 1));
+        ni->ekeys = (int *)malloc(sizeof(int) * (size_t)(n_exit + 1));
+        ol_push_back(&L, id);
+    }
+    for (int k = 0; k < n_cand; k++) {
+        onode *d = &L.n[(size_t)(cand[k].x / hX)];
+        d->keys[d->nkeys++] = k;
+    }
+    for (int k = 0; k < n_exit; k++) L.n[0].ekeys[L.n[0].nekeys++] = k;
+    for (int it = L.head; it >= 0;) {
+        if (L.n[it].nkeys == 1) { L.n[it].no_more = 1; it = L.n[it].next; }
+        else if (L.n[it].nkeys == 0) it = ol_erase(&L, it);
+        else it = L.n[it].next;
+    }
+    int finish = 0;
+    size_t exp_cap = (size_t)(4 * (n_cand + 8));
+    sz_node *exp = (sz_node *)malloc(sizeof(sz_node) * exp_cap);
+    sz_node *prev = (sz_node *)malloc(sizeof(sz_node) * exp_cap);
+    while (!finish) {
+        int prevSize = L.size, nexp = 0;
+        for (int it = L.head; it >= 0;) {
+            if (L.n[it].no_more) { it = L.n[it].next; continue; }
+            split_push(&L, it, cand, ex, exp, &nexp);
+            it = ol_erase(&L, it);
+        }
+        if (L.size >= N || L.size == prevSize) finish = 1;
+        else if (L.size + nexp * 3 > N) {
+            while (!finish) {
+                prevSize = L.size;
+                int nprev = nexp;
+                memcpy(prev, exp, sizeof(sz_node) * (size_t)nexp);
+                nexp = 0;
+                qsort(prev, (size_t)nprev, sizeof(sz_node), sz_cmp);
+                for (int j = nprev - 1; j >= 0; j--) {
+                    split_push(&L, prev[j].id, cand, ex, exp, &nexp);
+                    ol_erase(&L, prev[j].id);
+                    if (L.size >= N) break;
+                }
+                if (L.size >= N || L.size == prevSize) finish = 1;
+            }
+        }
+    }
+    int n = 0;
+    for (int it = L.head; it >= 0; it = L.n[it].next) {
+        onode *nd = &L.n[it];
+        int best = nd->keys[0];
+        float maxResponse = cand[best].response;
+        for (int k = 1; k < nd->nkeys; k++)
+            if (cand[nd->keys[k]].response > maxResponse) { best = nd->keys[k]; maxResponse = cand[best].response; }
+        int accept = 1;
+        for (int k = 0; k < nd->nekeys; k++) {
+            const tbo_kp *e = &ex[nd->ekeys[k]];
+            float dx = e->x - cand[best].x, dy = e->y - cand[best].y;
+            if (dx * dx + dy * dy < 400) accept = 0;
+        }
+        if (accept) {
+            if (n < cap) out[n] = cand[best];
+            n++;
+        }
+    }
+    for (int i = 0; i < L.count; i++) { free(L.n[i].keys); free(L.n[i].ekeys); }
+    free(L.n); free(exp); free(prev);
+    return n;
+}
+
+/* operator() / AddPoints — ORBextractor.cpp:906-978 / 840-904 with ComputeKeyPointsOctTree :735-828 */
+int tbo_orb_extract(const u8 *const *levels, const int *w, const int *h, const int *stride, int n_levels,
+                    const float *sf, int target, float initTh, float minTh,
+                    const tbo_kp *exit_kps, int n_exit, const int *budget_in,
+                    tbo_kp *kps, u8 *desc, int cap, int *n_per_level)
+{
+    if (n_levels <= 0 || !levels[0] || w[0] <= 0 || h[0] <= 0) return 0;
+    int budget[64];
+    if (budget_in) memcpy(budget, budget_in, sizeof(int) * (size_t)n_levels);
+    else tbo_orb_budget(n_levels, sf[1], target, budget);
+    int n_out = 0;
+    for (int level = 0; level < n_levels; level++) {
+        const int W = w[level], H = h[level], S = stride[level];
+        const u8 *img = levels[level];
+        const int minB = EDGE_THRESHOLD - 3, maxBX = W - EDGE_THRESHOLD + 3, maxBY = H - EDGE_THRESHOLD + 3;
+        int ccap = imax((W * H) / 4, 16);
+        tbo_kp *cand = (tbo_kp *)malloc(sizeof(tbo_kp) * (size_t)ccap);
+        int nc = tbo_cell_candidates(img, W, H, S, initTh, minTh, cand, ccap);
+        int kcap = nc + 8;
+        tbo_kp *kept = (tbo_kp *)malloc(sizeof(tbo_kp) * (size_t)kcap);
+        int nk = tbo_distribute_octree(cand, nc, exit_kps, n_exit, minB, maxBX, minB, maxBY, budget[level], kept, kcap);
+        const int scaledPatchSize = (int)(31 * sf[level]);
+        u8 *blur = NULL;
+        if (nk > 0) {
+            blur = (u8 *)malloc((size_t)W * H);
+            tbo_gauss7x7(img, W, H, S, blur, W);
+        }
+        for (int i = 0; i < nk; i++) {
+            tbo_kp k = kept[i];
+            k.x += minB; k.y += minB;
+            k.octave = level;
+            k.size = (float)scaledPatchSize;
+            int cx = cv_round_f(k.x), cy = cv_round_f(k.y);
+            k.angle = tbo_ic_angle(img, S, cx, cy);
+            if (n_out < cap) {
+                tbo_rbrief(blur, W, cx, cy, k.angle, desc + (size_t)32 * n_out);
+                if (level != 0) { k.x *= sf[level]; k.y *= sf[level]; } /* :969-974 (multiplies; replicated) */
+                kps[n_out] = k;
+            }
+            n_out++;
+        }
+        if (n_per_level) n_per_level[level] = nk;
+        free(blur); free(kept); free(cand);
+    }
+    return n_out;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matcher — src/matchers/matcher.cpp
+ * ------------------------------------------------------------------------------------------ */
+/* DescriptorDistance — matcher.cpp:793-808 (8 x 32-bit SWAR popcount) */
+int tbo_hamming256(const u8 *a, const u8 *b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb;
+        memcpy(&pa, a + 4 * i, 4);
+        memcpy(&pb, b + 4 * i, 4);
+        uint32_t v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+static inline int ham_fast(const u8 *a, const u8 *b)
+{
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32); memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) +
+           __builtin_popcountll(x[2] ^ y[2]) + __builtin_popcountll(x[3] ^ y[3]);
+}
+
+void tbo_knn2(const u8 *q, int nq, const u8 *t, int nt, int32_t *idx, int32_t *best, int32_t *second)
+{
+    for (int i = 0; i < nq; i++) {
+        int b = INT_MAX, s = INT_MAX, bi = -1;
+        for (int j = 0; j < nt; j++) {
+            int d = ham_fast(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (d < b) { s = b; b = d; bi = j; }
+            else if (d < s) s = d;
+        }
+        idx[i] = bi; best[i] = b; second[i] = s;
+    }
+}
+
+/* cv::BFMatcher(NORM_HAMMING, crossCheck=true).match(d1,d2) — matcher.cpp:20,207.  OpenCV
+ * features2d/matchers.cpp: knnMatch k=1 both ways (batchDistance keeps the first minimum = lowest
+ * index), emit (i, nn12[i]) for ascending i iff nn21[nn12[i]] == i. */
+int tbo_bf_cross(const u8 *d1, int n1, const u8 *d2, int n2, tbo_match *out)
+{
+    if (n1 <= 0 || n2 <= 0) return 0;
+    int *nn12 = (int *)malloc(sizeof(int) * (size_t)n1), *d12 = (int *)malloc(sizeof(int) * (size_t)n1);
+    int *nn21 = (int *)malloc(sizeof(int) * (size_t)n2), *d21 = (int *)malloc(sizeof(int) * (size_t)n2);
+    for (int i = 0; i < n1; i++) d12[i] = INT_MAX;
+    for (int j = 0; j < n2; j++) d21[j] = INT_MAX;
+    for (int i = 0; i < n1; i++)
+        for (int j = 0; j < n2; j++) {
+            int d = ham_fast(d1 + 32 * (size_t)i, d2 + 32 * (size_t)j);
+            if (d < d12[i]) { d12[i] = d; nn12[i] = j; }
+            if (d < d21[j]) { d21[j] = d; nn21[j] = i; }
+        }
+    int n = 0;
+    for (int i = 0; i < n1; i++)
+        if (nn21[nn12[i]] == i) {
+            tbo_match m = {i, nn12[i], 0, (float)d12[i]};
+            out[n++] = m;
+        }
+    free(nn12); free(d12); free(nn21); free(d21);
+    return n;
+}
+
+/* searchByBF, all-levels branch — matcher.cpp:168-228 */
+int tbo_search_by_bf(const u8 *d1, int n1, const u8 *d2, int n2, float ratio, float minTh, tbo_match *out)
+{
+    tbo_match *all = (tbo_match *)malloc(sizeof(tbo_match) * (size_t)(n1 > 0 ? n1 : 1));
+    int na = tbo_bf_cross(d1, n1, d2, n2, all);
+    int n = 0;
+    if (na > 0) { /* the reference dereferences min_element of an empty vector otherwise (UB) */
+        float min_distance = all[0].distance;
+        for (int i = 1; i < na; i++) if (all[i].distance < min_distance) min_distance = all[i].distance;
+        for (int i = 0; i < na; i++)
+            if (all[i].distance < fminf(ratio * min_distance, minTh)) out[n++] = all[i];
+    }
+    free(all);
+    return n;
+}
+
+/* ---- Frame grid — src/types/Frame.cpp:30-31 (scale members), 187-200, 202-255, 257-265 ---- */
+#define GRID_ROWS 36
+#define GRID_COLS 120
+struct tbo_grid {
+    float wInv, hInv; /* mfGridElementWidthInv = 36/rows, mfGridElementHeightInv = 120/cols (sic) */
+    int *cell_start;  /* [GRID_COLS*GRID_ROWS + 1], cell (ix,iy) at ix*GRID_ROWS+iy */
+    int *items;
+    const tbo_kp *kps;
+    int n;
+};
+
+static int pos_in_grid(const tbo_grid *g, const tbo_kp *kp, int *px, int *py)
+{
+    *px = (int)roundf(kp->x * g->wInv);
+    *py = (int)roundf(kp->y * g->hInv);
+    return !(*px < 0 || *px >= GRID_COLS || *py < 0 || *py >= GRID_ROWS);
+}
+
+tbo_grid *tbo_grid_build(const tbo_kp *kps, int n, int img_cols, int img_rows)
+{
+    tbo_grid *g = (tbo_grid *)calloc(1, sizeof(tbo_grid));
+    g->hInv = (float)GRID_COLS / (float)img_cols;
+    g->wInv = (float)GRID_ROWS / (float)img_rows;
+    g->kps = kps; g->n = n;
+    int ncell = GRID_COLS * GRID_ROWS;
+    g->cell_start = (int *)calloc((size_t)ncell + 1, sizeof(int));
+    g->items = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int *cnt = (int *)calloc((size_t)ncell, sizeof(int));
+    for (int i = 0; i < n; i++) { int x, y; if (pos_in_grid(g, &kps[i], &x, &y)) cnt[x * GRID_ROWS + y]++; }
+    for (int c = 0; c < ncell; c++) g->cell_start[c + 1] = g->cell_start[c] + cnt[c];
+    memset(cnt, 0, sizeof(int) * (size_t)ncell);
+    for (int i = 0; i < n; i++) {
+        int x, y;
+        if (pos_in_grid(g, &kps[i], &x, &y)) { int c = x * GRID_ROWS + y; g->items[g->cell_start[c] + cnt[c]++] = i; }
+    }
+    free(cnt);
+    return g;
+}
+void tbo_grid_free(tbo_grid *g) { if (g) { free(g->cell_start); free(g->items); free(g); } }
+
+int tbo_features_in_area(const tbo_grid *g, float x, float y, float r, int minLevel, int maxLevel, int32_t *out, int cap)
+{
+    int n = 0;
+    const int nMinCellX = imax(0, (int)floorf((x - r) * g->wInv));
+    if (nMinCellX >= GRID_COLS) return 0;
+    const int nMaxCellX = imin(GRID_COLS - 1, (int)ceilf((x + r) * g->wInv));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = imax(0, (int)floorf((y - r) * g->hInv));
+    if (nMinCellY >= GRID_ROWS) return 0;
+    const int nMaxCellY = imin(GRID_ROWS - 1, (int)ceilf((y + r) * g->hInv));
+    if (nMaxCellY < 0) return 0;
+    const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            int c = ix * GRID_ROWS + iy;
+            for (int k = g->cell_start[c]; k < g->cell_start[c + 1]; k++) {
+                int j = g->items[k];
+                const tbo_kp *kp = &g->kps[j];
+                if (bCheckLevels) {
+                    if (kp->octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                }
+                const float distx = kp->x - x, disty = kp->y - y;
+                if (fabsf(distx) < r && fabsf(disty) < r) { if (n < cap) out[n] = j; n++; }
+            }
+        }
+    return n;
+}
+
+/* ComputeThreeMaxima — matcher.cpp:810-851 */
+void tbo_three_maxima(const int *hs, int L, int *ind1, int *ind2, int *ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = hs[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+/* rotation-histogram regrouping shared by searchByViolence (:359-393) and searchByProjection
+ * (:493-529): bins[i] = histogram bin of raw match i; output = matches grouped by bin ascending,
+ * only the three maxima bins. */
+static int rot_hist_filter(const tbo_match *raw, const int *bins, int n, int L, tbo_match *out)
+{
+    int *hs = (int *)calloc((size_t)L, sizeof(int));
+    for (int i = 0; i < n; i++) hs[bins[i]]++;
+    int ind[3] = {-1, -1, -1};
+    tbo_three_maxima(hs, L, &ind[0], &ind[1], &ind[2]);
+    int m = 0;
+    for (int b = 0; b < L; b++)
+        if (b == ind[0] || b == ind[1] || b == ind[2])
+            for (int i = 0; i < n; i++) if (bins[i] == b) out[m++] = raw[i];
+    free(hs);
+    return m;
+}
+
+/* searchByViolence — matcher.cpp:299-395 (MapPointOnly == false) */
+int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const u8 *d1, int n1,
+                           const tbo_kp *k2, const u8 *d2, int n2, int cols2, int rows2,
+                           int min_level, int max_level, float search_r, tbo_match *out)
+{
+    tbo_grid *g = tbo_grid_build(k2, n2, cols2, rows2);
+    int32_t *ind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 + 1));
+    tbo_match *raw = (tbo_match *)malloc(sizeof(tbo_match) * (size_t)(n1 + 1));
+    int *bins = (int *)malloc(sizeof(int) * (size_t)(n1 + 1));
+    const float factor = 1.f / (float)p->HISTO_LENGTH;
+    int n = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        int nc = tbo_features_in_area(g, k1[i1].x, k1[i1].y, search_r, min_level, max_level, ind, n2);
+        if (nc == 0) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            int dist = tbo_hamming256(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)ind[c]);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = ind[c]; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= p->TH_LOW && (float)bestDist < (float)bestDist2 * p->nRatio) {
+            tbo_match m = {i1, bestIdx2, 0, (float)bestDist};
+            raw[n] = m;
+            if (p->checkOrientation) {
+                float rot = k1[i1].angle - k2[bestIdx2].angle;
+                if (rot < 0) rot += 360.f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == p->HISTO_LENGTH) bin = 0;
+                bins[n] = bin;
+            }
+            n++;
+        }
+    }
+    int m;
+    if (p->checkOrientation) m = rot_hist_filter(raw, bins, n, p->HISTO_LENGTH, out);
+    else { memcpy(out, raw, sizeof(tbo_match) * (size_t)n); m = n; }
+    free(ind); free(raw); free(bins);
+    tbo_grid_free(g);
+    return m;
+}
+
+/* PinholeCamera::World2Cam without distortion — CameraModel.cpp:63-74; IsInFrame on truncated
+ * ints — CameraModel.h:33-39 (boundary 0, scale 1). */
+static void world2cam(const tbo_pinhole *c, const float *xyz, float *u, float *v)
+{
+    float x = xyz[0] / xyz[2], y = xyz[1] / xyz[2];
+    if (!(fabs(c->d[0]) > 0.0000001)) { /* mbDistortion — CameraModel.cpp:9 */
+        *u = c->fx * x + c->cx;
+        *v = c->fy * y + c->cy;
+    } else { /* radtan — CameraModel.cpp:75-92 */
+        float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+        float a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+        float cdist = 1 + c->d[0] * r2 + c->d[1] * r4 + c->d[4] * r6;
+        float xd = x * cdist + c->d[2] * a1 + c->d[3] * a2;
+        float yd = y * cdist + c->d[2] * a3 + c->d[3] * a1;
+        *u = xd * c->fx + c->cx;
+        *v = yd * c->fy + c->cy;
+    }
+}
+static int is_in_frame(const tbo_pinhole *c, float u, float v)
+{
+    int iu = (int)u, iv = (int)v;
+    return iu >= 0 && iu < (int)((float)c->width * 1.f) && iv >= 0 && iv < (int)((float)c->height * 1.f);
+}
+/* Eigen evaluates a fixed-size 3-term dot product with its non-vectorised redux unroller
+ * (Eigen/src/Core/Redux.h, HalfLength = 3/2 = 1): x0 + (x1 + x2).  Eigen is an un-vendored
+ * dependency of the reference; this order is restated here and mirrored by the CUDA path. */
+static inline float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return a0 * b0 + (a1 * b1 + a2 * b2);
+}
+static void transform_pt(const float *T, const float *X, float *out) /* Rcw*Xw + tcw */
+{
+    for (int r = 0; r < 3; r++)
+        out[r] = dot3(T[4 * r + 0], X[0], T[4 * r + 1], X[1], T[4 * r + 2], X[2]) + T[4 * r + 3];
+}
+
+/* searchByProjection(F1,F2) — matcher.cpp:405-531 */
+int tbo_search_by_projection(const tbo_matcher_params *p, const tbo_pinhole *cam, const float *Tcw1,
+                             const tbo_kp *k1, const u8 *d1, int n1, const u8 *f1_matched,
+                             const float *sf1, int n_levels1, int cols1, int rows1,
+                             const tbo_kp *k2, int n2, const u8 *mp_valid, const float *mp_xyz,
+                             const u8 *mp_desc, tbo_match *out)
+{
+    (void)n_levels1;
+    tbo_grid *g = tbo_grid_build(k1, n1, cols1, rows1);
+    int32_t *ind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n1 + 1));
+    tbo_match *raw = (tbo_match *)malloc(sizeof(tbo_match) * (size_t)(n2 + 1));
+    int *bins = (int *)malloc(sizeof(int) * (size_t)(n2 + 1));
+    const float factor = 1.0f / (float)p->HISTO_LENGTH;
+    int n = 0;
+    for (int i2 = 0; i2 < n2; i2++) {
+        if (!mp_valid[i2]) continue;
+        float xc[3];
+        transform_pt(Tcw1, mp_xyz + 3 * (size_t)i2, xc);
+        const float invzc = 1.0f / xc[2];
+        if (invzc < 0) continue;
+        float u, v;
+        world2cam(cam, xc, &u, &v);
+        if (!is_in_frame(cam, u, v)) continue;
+        int nLastOctave = k2[i2].octave;
+        float radius = p->nRatio * sf1[nLastOctave];
+        int nc = tbo_features_in_area(g, u, v, radius, nLastOctave - 1, nLastOctave + 1, ind, n1);
+        if (nc == 0) continue;
+        int bestDist = 256, bestIdx1 = -1;
+        for (int c = 0; c < nc; c++) {
+            int i1 = ind[c];
+            if (f1_matched && f1_matched[i1]) continue;
+            int dist = tbo_hamming256(mp_desc + 32 * (size_t)i2, d1 + 32 * (size_t)i1);
+            if (dist < bestDist) { bestDist = dist; bestIdx1 = i1; }
+        }
+        if (bestDist <= p->TH_HIGH) {
+            tbo_match m = {bestIdx1, i2, 0, (float)bestDist};
+            raw[n] = m;
+            if (p->checkOrientation) {
+                float rot = k2[i2].angle - k1[bestIdx1].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)round(rot * factor);
+                if (bin == p->HISTO_LENGTH) bin = 0;
+                bins[n] = bin;
+            }
+            n++;
+        }
+    }
+    int m;
+    if (p->checkOrientation) m = rot_hist_filter(raw, bins, n, p->HISTO_LENGTH, out);
+    else { memcpy(out, raw, sizeof(tbo_match) * (size_t)n); m = n; }
+    free(ind); free(raw); free(bins);
+    tbo_grid_free(g);
+    return m;
+}
+
+/* searchByProjection(map,F1,radio) — matcher.cpp:539-617; Frame::IsInFrustum — Frame.cpp:370-412 */
+int tbo_search_by_projection_map(const tbo_matcher_params *p, const tbo_pinhole *cam, const float *Tcw1,
+                                 const tbo_kp *k1, const u8 *d1, int n1, const u8 *f1_matched,
+                                 const float *sf1, int cols1, int rows1,
+                                 int n_mp, const u8 *mp_bad, const float *mp_xyz, const float *mp_normal,
+                                 const u8 *mp_desc, float radio, tbo_match *out)
+{
+    tbo_grid *g = tbo_grid_build(k1, n1, cols1, rows1);
+    int32_t *ind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n1 + 1));
+    const int bFactor = p->nRatio != 1.0;
+    /* camera centre mOw = -Rcw^T tcw — Frame.cpp:57 */
+    float Ow[3];
+    for (int c = 0; c < 3; c++)
+        Ow[c] = dot3(-Tcw1[0 + c], Tcw1[3], -Tcw1[4 + c], Tcw1[7], -Tcw1[8 + c], Tcw1[11]);
+    int n = 0, cnt = 0;
+    for (int im = 0; im < n_mp; im++) {
+        cnt++;
+        if (mp_bad[im]) continue;
+        const float *P = mp_xyz + 3 * (size_t)im;
+        float Pc[3];
+        transform_pt(Tcw1, P, Pc);
+        if (Pc[2] < 0.0f) continue;
+        float u, v;
+        world2cam(cam, Pc, &u, &v);
+        if (!is_in_frame(cam, u, v)) continue;
+        const float maxDistance = 1000.f, minDistance = 1.f; /* MapPoint.cpp:207-217 */
+        float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist3 = sqrtf(dot3(PO[0], PO[0], PO[1], PO[1], PO[2], PO[2]));
+        if (dist3 < minDistance || dist3 > maxDistance) continue;
+        const float *Pn = mp_normal + 3 * (size_t)im;
+        const float viewCos = dot3(PO[0], Pn[0], PO[1], Pn[1], PO[2], Pn[2]) / dist3;
+        if (viewCos < 0.5f) continue;
+        const int nPredictedLevel = 0;
+        float r = 4.f;
+        if (viewCos > 0.998) r = 2.5;
+        if (bFactor) r *= p->nRatio;
+        int nc = tbo_features_in_area(g, u, v, r * sf1[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, ind, n1);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            int idx = ind[c];
+            if (f1_matched && f1_matched[idx]) continue;
+            const int dist = tbo_hamming256(mp_desc + 32 * (size_t)im, d1 + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                bestLevel = k1[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) { bestLevel2 = k1[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= p->TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > radio * bestDist2) continue;
+            tbo_match m = {bestIdx, cnt - 1, 0, (float)bestDist};
+            out[n++] = m;
+        }
+    }
+    free(ind);
+    tbo_grid_free(g);
+    return n;
+}
+
+/* FASTExtractor::shiTomasiScore — src/extractors/FASTextractor.cpp:87-127 */
+float tbo_shi_tomasi(const u8 *img, int w, int h, int stride, int u, int v)
+{
+    float dXX = 0.0, dYY = 0.0, dXY = 0.0;
+    const int halfbox_size = 4, box_size = 2 * halfbox_size, box_area = box_size * box_size;
+    const int x_min = u - halfbox_size, x_max = u + halfbox_size;
+    const int y_min = v - halfbox_size, y_max = v + halfbox_size;
+    if (x_min < 1 || x_max >= w - 1 || y_min < 1 || y_max >= h - 1) return 0.0;
+    for (int y = y_min; y < y_max; ++y) {
+        const u8 *pl = img + (size_t)stride * y + x_min - 1, *pr = img + (size_t)stride * y + x_min + 1;
+        const u8 *pt = img + (size_t)stride * (y - 1) + x_min, *pb = img + (size_t)stride * (y + 1) + x_min;
+        for (int x = 0; x < box_size; ++x, ++pl, ++pr, ++pt, ++pb) {
+            float dx = (float)*pr - (float)*pl, dy = (float)*pb - (float)*pt;
+            dXX += dx * dx; dYY += dy * dy; dXY += dx * dy;
+        }
+    }
+    dXX = dXX / (2.f * box_area); dYY = dYY / (2.f * box_area); dXY = dXY / (2.f * box_area);
+    return 0.5f * (dXX + dYY - sqrtf((dXX + dYY) * (dXX + dYY) - 4 * (dXX * dYY - dXY * dXY)));
+}

@@ -1,0 +1,132 @@
+/* tb_oracle.h — CPU ORACLE for the trackingBench-SLAM feature-tracking front end.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load it, and
+ * only as the checker (or the timed CPU baseline), never as the thing shipped or measured as
+ * "ours".  The product (trackingbench_slam_b200/csrc, include/) never links or calls this.
+ *
+ * It is a plain-C restatement of the reference algorithm (file:line cited per function, all
+ * paths relative to the reference repo root) plus restatements of the OpenCV primitives the
+ * reference calls (cv::resize, cv::FAST, cv::GaussianBlur, cv::fastAtan2, cv::BFMatcher) — those
+ * live in an un-vendored dependency (OpenCV; the reference's prebuilt libDBoW2.so was linked
+ * against 3.3, the only OpenCV available here is cv2 4.13.0).
+ *
+ * PARITY PINNING: the reference's own tests hold no golden vectors (they are imshow demos), so
+ * the oracle is pinned by (a) tests/test_oracle_cv2.py: every primitive bit-exact against cv2
+ * 4.13.0 on images and random data; (b) tests/test_oracle_ref.py: the extractor restatement
+ * bit-exact against oracle/_ref = the reference's own ORBextractor.cpp compiled unmodified here
+ * (sort comparator pinned, see oracle/ref_build.cpp); (c) committed golden vectors in
+ * tests/golden made by scripts/make_golden.py from (b).
+ */
+#ifndef TB_ORACLE_H
+#define TB_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cv::KeyPoint-shaped POD (7 x 4 bytes). */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} tbo_kp;
+
+/* cv::DMatch-shaped POD. */
+typedef struct {
+    int32_t queryIdx, trainIdx, imgIdx;
+    float distance;
+} tbo_match;
+
+/* ---- Frame: scale tables + pyramid (src/types/Frame.cpp:18-29, 414-427) ---- */
+void tbo_scale_factors(int n_levels, float scale, float *sf);
+void tbo_level_size(int w0, int h0, float sf_level, int *w, int *h);
+void tbo_resize_linear_u8(const uint8_t *src, int sw, int sh, int sstride,
+                          uint8_t *dst, int dw, int dh, int dstride);
+
+/* ---- OpenCV primitives used by ORBextractor.cpp ---- */
+/* cv::FAST(img, kps, T, nonmax) TYPE_9_16 on a w x h ROI; returns count (writes at most cap). */
+int tbo_fast9(const uint8_t *img, int stride, int w, int h, int T, int nonmax, tbo_kp *out, int cap);
+/* cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on 8U (OpenCV >= 3.4.2 fixed-point path). */
+void tbo_gauss7x7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride);
+float tbo_fast_atan2(float y, float x);
+
+/* ---- ORBExtractor (src/extractors/ORBextractor.cpp) ---- */
+void tbo_orb_budget(int n_levels, float factor, int target, int *per_level); /* :919-930 */
+/* operator() (:906-978) when budget_in == NULL; AddPoints (:840-904) when budget_in != NULL
+ * (the reference reuses mnFeaturesPerLevel from the previous operator() call).
+ * levels[l] is a w[l] x h[l] u8 image with row stride stride[l]. Returns n keypoints (may exceed
+ * cap; only cap are written). desc is n x 32. n_per_level (optional) receives per-level counts. */
+int tbo_orb_extract(const uint8_t *const *levels, const int *w, const int *h, const int *stride,
+                    int n_levels, const float *sf, int target, float initTh, float minTh,
+                    const tbo_kp *exit_kps, int n_exit, const int *budget_in,
+                    tbo_kp *kps, uint8_t *desc, int cap, int *n_per_level);
+/* Intermediate stages, exposed for stage-by-stage parity tests. */
+int tbo_cell_candidates(const uint8_t *img, int w, int h, int stride, float initTh, float minTh,
+                        tbo_kp *out, int cap); /* :743-804, coords relative to (16,16) */
+int tbo_distribute_octree(const tbo_kp *cand, int n_cand, const tbo_kp *exit_kps, int n_exit,
+                          int minX, int maxX, int minY, int maxY, int N,
+                          tbo_kp *out, int cap); /* :494-733 */
+float tbo_ic_angle(const uint8_t *img, int stride, int cx, int cy); /* :17-44 */
+void tbo_rbrief(const uint8_t *blur, int stride, int cx, int cy, float angle_deg, uint8_t *desc32); /* :48-87 */
+
+/* ---- Matcher (src/matchers/matcher.cpp) ---- */
+int tbo_hamming256(const uint8_t *a, const uint8_t *b); /* :793-808 */
+/* BFMatcher(NORM_HAMMING, crossCheck=true).match (ctor :20, call :207): returns count. */
+int tbo_bf_cross(const uint8_t *d1, int n1, const uint8_t *d2, int n2, tbo_match *out);
+/* best / second-best / argbest per query row (lowest index on ties). */
+void tbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *idx, int32_t *best, int32_t *second);
+/* searchByBF all-levels branch (:168-228). */
+int tbo_search_by_bf(const uint8_t *d1, int n1, const uint8_t *d2, int n2, float ratio, float minTh, tbo_match *out);
+
+/* Frame search grid (src/types/Frame.cpp:30-31,187-265). Opaque handle. */
+typedef struct tbo_grid tbo_grid;
+tbo_grid *tbo_grid_build(const tbo_kp *kps, int n, int img_cols, int img_rows);
+void tbo_grid_free(tbo_grid *g);
+int tbo_features_in_area(const tbo_grid *g, float x, float y, float r, int minLevel, int maxLevel,
+                         int32_t *out, int cap);
+
+typedef struct {
+    int TH_LOW, TH_HIGH, HISTO_LENGTH, checkOrientation;
+    float nRatio;
+} tbo_matcher_params; /* matcher.h:23-27 */
+
+/* searchByViolence (:299-395): F1 keys/desc vs grid of F2. */
+int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const uint8_t *d1, int n1,
+                           const tbo_kp *k2, const uint8_t *d2, int n2, int cols2, int rows2,
+                           int min_level, int max_level, float search_r, tbo_match *out);
+
+typedef struct {
+    float fx, fy, cx, cy;
+    int width, height;
+    float d[5]; /* radtan distortion, used iff |d[0]| > 1e-7 */
+} tbo_pinhole; /* CameraModel.cpp:63-94; CameraModel.h:33-39 */
+
+/* searchByProjection(F1,F2) (:405-531). Map points of F2 flattened: mp_valid[i2] (non-null &&
+ * !isBad), mp_xyz[3*i2], mp_desc[32*i2]. f1_matched[i1] != 0 means F1's map point i1 has
+ * Observations()>0 (skipped). Tcw1 = row-major 4x4 pose of F1. sf1 = F1 scale factors. */
+int tbo_search_by_projection(const tbo_matcher_params *p, const tbo_pinhole *cam, const float *Tcw1,
+                             const tbo_kp *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                             const float *sf1, int n_levels1, int cols1, int rows1,
+                             const tbo_kp *k2, int n2, const uint8_t *mp_valid, const float *mp_xyz,
+                             const uint8_t *mp_desc, tbo_match *out);
+
+/* searchByProjection(map,F1,r) (:539-617) with Frame::IsInFrustum (Frame.cpp:370-412). Map points
+ * given in iteration order (the reference iterates a std::set<shared_ptr> = pointer order; the
+ * oracle defines the order as the array order). normals: 3 floats each; min/max distance per
+ * MapPoint.cpp:207-217 are constants 1 / 1000. */
+int tbo_search_by_projection_map(const tbo_matcher_params *p, const tbo_pinhole *cam, const float *Tcw1,
+                                 const tbo_kp *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                                 const float *sf1, int cols1, int rows1,
+                                 int n_mp, const uint8_t *mp_bad, const float *mp_xyz, const float *mp_normal,
+                                 const uint8_t *mp_desc, float radio, tbo_match *out);
+
+void tbo_three_maxima(const int *hist_sizes, int L, int *ind1, int *ind2, int *ind3); /* :810-851 */
+
+/* FASTExtractor::shiTomasiScore (src/extractors/FASTextractor.cpp:87-127). */
+float tbo_shi_tomasi(const uint8_t *img, int w, int h, int stride, int u, int v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
