@@ -1,0 +1,201 @@
+/* tb_capi.h — C ABI of libtb_b200.so, the B200 (sm_100a) implementation of the
+ * trackingBench-SLAM feature-tracking front end (pyramid -> FAST/ORB extract -> Hamming match).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and POD structs; no C++/torch types; no
+ * exceptions cross it.  Everything above it (the C++ facade classes in include/types,
+ * include/extractors, include/matchers that keep the reference's names, and the Python ctypes
+ * mirror in trackingbench_slam_b200/) only converts cv::Mat / cv::KeyPoint / cv::DMatch to these
+ * PODs.  Each entry point cites the reference interface (file:line, relative to the reference
+ * repo) whose body it replaces.
+ *
+ * Conventions
+ *  - every function returns tb_status (0 = ok, negative = error); tb_last_error(ctx) gives text.
+ *  - one tb_ctx = one CUDA device + one stream; NOT thread-safe; use one host thread per ctx.
+ *    Calls are stream-ordered; functions with host outputs synchronise before returning,
+ *    *_device functions do not (call tb_sync or consume on the same stream).
+ *  - outputs go to caller-allocated buffers with a capacity; the true count is always reported;
+ *    count > capacity => TB_E_CAPACITY (the first `capacity` items are valid).
+ *  - "dptr" arguments are raw CUDA device pointers valid on the ctx's device (e.g. a torch
+ *    tensor's data_ptr()); ownership stays with the caller.
+ *  - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef TB_CAPI_H
+#define TB_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TB_OK = 0,
+    TB_E_INVALID = -1,     /* bad argument */
+    TB_E_CUDA = -2,        /* CUDA runtime error (text in tb_last_error) */
+    TB_E_CAPACITY = -3,    /* an output or internal buffer was too small; counts are still valid */
+    TB_E_UNSUPPORTED = -4, /* shape outside what the kernels support (documented per call) */
+    TB_E_NOMEM = -5
+} tb_status;
+
+#define TB_MAX_LEVELS 16
+#define TB_DESC_BYTES 32
+
+/* cv::KeyPoint layout (7 x 4 bytes): pt.x pt.y size angle response octave class_id */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} tb_keypoint;
+
+/* cv::DMatch layout */
+typedef struct {
+    int32_t queryIdx, trainIdx, imgIdx;
+    float distance;
+} tb_match;
+
+/* Matcher public parameters — include/matchers/matcher.h:23-27 */
+typedef struct {
+    int32_t TH_LOW, TH_HIGH, HISTO_LENGTH, checkOrientation;
+    float nRatio;
+} tb_matcher_params;
+
+/* PinholeCamera — include/camera/CameraModel.h:43-87 (World2Cam src/camera/CameraModel.cpp:63-94) */
+typedef struct {
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float d[5]; /* radtan; used iff |d[0]| > 1e-7 (CameraModel.cpp:9) */
+} tb_pinhole;
+
+typedef struct tb_ctx tb_ctx;
+typedef struct tb_frontend tb_frontend;
+
+/* ------------------------------------------------------------------ context */
+/* stream: a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
+ * create an owned non-blocking stream. */
+int tb_ctx_create(int device, void *stream, tb_ctx **out);
+void tb_ctx_destroy(tb_ctx *ctx);
+int tb_sync(tb_ctx *ctx);
+const char *tb_last_error(const tb_ctx *ctx);
+const char *tb_version(void);
+/* number of kernel launches issued through this ctx since creation (bench.py's gpu_launches) */
+int64_t tb_launch_count(const tb_ctx *ctx);
+
+/* ------------------------------------------------------------------ pyramid geometry (host, pure)
+ * Frame::Frame scale tables (src/types/Frame.cpp:18-29) and the level sizes of
+ * Frame::ComputePyramid (src/types/Frame.cpp:414-427): sf[i] = sf[i-1]*scale (float32 chain),
+ * size_i = (int(cols*sf[i]), int(rows*sf[i])) with the product taken in float32. */
+int tb_pyramid_geometry(int width, int height, int n_levels, float scale,
+                        float *sf /*[n_levels]*/, int32_t *level_w, int32_t *level_h);
+
+/* ------------------------------------------------------------------ front end object
+ * Owns the device buffers for a batch of up to max_batch equally-sized frames: the image pyramid,
+ * the blurred pyramid, FAST candidates, octree workspace and the keypoint/descriptor outputs.
+ * Level sizes are given explicitly so that pyramids built elsewhere (any vector<cv::Mat> handed
+ * to ORBExtractor::operator()) can be processed too. max_target bounds `target` of later extract
+ * calls (outputs hold up to tb_frontend_kp_capacity() keypoints per frame). */
+int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *level_w, const int32_t *level_h,
+                       int max_batch, int max_target, tb_frontend **out);
+void tb_frontend_destroy(tb_frontend *fe);
+int tb_frontend_kp_capacity(const tb_frontend *fe);
+
+/* Device layout of level `level`: frame f starts at base + f*frame_stride, rows are `pitch` apart. */
+int tb_frontend_level_layout(const tb_frontend *fe, int level, int blurred, void **base_dptr,
+                             size_t *pitch, size_t *frame_stride);
+/* H2D / D2H of one level of one frame (host row stride in bytes). */
+int tb_frontend_upload_level(tb_frontend *fe, int frame, int level, const uint8_t *host, size_t host_stride);
+int tb_frontend_download_level(tb_frontend *fe, int frame, int level, int blurred, uint8_t *host, size_t host_stride);
+/* H2D of level 0 of n_frames frames packed back to back (frame stride = host_stride*height). */
+int tb_frontend_upload_frames(tb_frontend *fe, int first_frame, int n_frames, const uint8_t *host, size_t host_stride);
+
+/* Frame::ComputePyramid (src/types/Frame.cpp:414-427): levels 1.. from level 0 by chained
+ * cv::resize INTER_LINEAR (OpenCV fixed-point semantics incl. the exact-2x INTER_AREA switch). */
+int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames);
+
+/* ORBExtractor::operator() (src/extractors/ORBextractor.cpp:906-978) on frames [0,n_frames) whose
+ * pyramid levels are resident in the frontend (uploaded or built). sf = the scale factors the
+ * reference caller passes (Frame::GetScaleFactors). Results stay on the device.
+ * ORBExtractor::AddPoints (src/extractors/ORBextractor.cpp:840-904) when exit_kps != NULL
+ * (host array, shared by all frames of the call) — it reuses the per-level budget of the previous
+ * tb_frontend_extract call on this frontend, as the reference reuses mnFeaturesPerLevel. */
+int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
+                        const tb_keypoint *exit_kps, int n_exit);
+
+/* Results of the last extract. Device views: keypoints of frame f at kps + f*kp_capacity,
+ * descriptors at desc + f*kp_capacity*32, counts[f]. */
+int tb_frontend_results_device(const tb_frontend *fe, void **kps_dptr, void **desc_dptr, void **counts_dptr);
+/* D2H of one frame's results; *n = true count. Synchronises. */
+int tb_frontend_get_results(tb_frontend *fe, int frame, tb_keypoint *kps, uint8_t *desc, int capacity, int *n);
+/* D2H of all counts + packed results of frames [0,n_frames): kps/desc hold n_frames*capacity slots. */
+int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts);
+/* Stage outputs for stage-by-stage parity tests: FAST candidates of (frame, level) as keypoints
+ * relative to the (16,16) border in the reference's vToDistributeKeys order (ORBextractor.cpp:743-804). */
+int tb_frontend_get_candidates(tb_frontend *fe, int frame, int level, tb_keypoint *out, int capacity, int *n);
+int tb_frontend_get_level_counts(tb_frontend *fe, int frame, int32_t *n_per_level /*[n_levels]*/);
+
+/* One-call host convenience used by the C++ facade ORBExtractor::operator()/AddPoints: pyramid
+ * levels in host memory (as vector<cv::Mat>), results to host. */
+int tb_orb_extract_host(tb_frontend *fe, const uint8_t *const *levels, const size_t *host_strides,
+                        const float *sf, int target, float initTh, float minTh,
+                        const tb_keypoint *exit_kps, int n_exit,
+                        tb_keypoint *kps, uint8_t *desc, int capacity, int *n);
+
+/* ------------------------------------------------------------------ matching (device-resident inputs)
+ * Descriptors are rows of 32 bytes. */
+
+/* Matcher::DescriptorDistance (src/matchers/matcher.cpp:793-808), elementwise over n pairs. */
+int tb_hamming_pairs_device(tb_ctx *ctx, const void *a_dptr, const void *b_dptr, int n, void *dist_i32_dptr);
+
+/* best / second-best / argbest (lowest index on ties) of every query row against all train rows:
+ * the kernel shared by BFMatcher::match and the best/second loops (matcher.cpp:333-350,582-605). */
+int tb_knn2_device(tb_ctx *ctx, const void *q_dptr, int nq, const void *t_dptr, int nt,
+                   void *idx_i32_dptr, void *best_i32_dptr, void *second_i32_dptr);
+
+/* cv::BFMatcher(NORM_HAMMING, crossCheck=true).match (matcher.cpp:20,207): ascending queryIdx. */
+int tb_match_bf_cross_device(tb_ctx *ctx, const void *d1_dptr, int n1, const void *d2_dptr, int n2,
+                             tb_match *out_host, int capacity, int *n);
+
+/* Matcher::searchByBF all-levels branch (matcher.cpp:168-228): cross-check then
+ * dist < fmin(ratio*min_dist, minTh). */
+int tb_search_by_bf_device(tb_ctx *ctx, const void *d1_dptr, int n1, const void *d2_dptr, int n2,
+                           float ratio, float minTh, tb_match *out_host, int capacity, int *n);
+
+/* Batched searchByBF over frame pairs of one frontend's last extract: pair p matches frame
+ * q_frames[p] (query/F1) against t_frames[p] (train/F2). Outputs on the device:
+ * matches_dptr[p*capacity + i], counts_dptr[p]. No host synchronisation. */
+int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int32_t *q_frames, const int32_t *t_frames,
+                             float ratio, float minTh, void *matches_dptr, int capacity, void *counts_i32_dptr);
+
+/* Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/types/Frame.cpp:187-265) as a query:
+ * indices in the reference's traversal order. kps on the host. */
+int tb_features_in_area(tb_ctx *ctx, const tb_keypoint *kps, int n, int img_cols, int img_rows,
+                        float x, float y, float r, int minLevel, int maxLevel, int32_t *out, int capacity, int *n_out);
+
+/* Matcher::searchByViolence (matcher.cpp:299-395), MapPointOnly=false. Host in/out. */
+int tb_search_by_violence(tb_ctx *ctx, const tb_matcher_params *p,
+                          const tb_keypoint *k1, const uint8_t *d1, int n1,
+                          const tb_keypoint *k2, const uint8_t *d2, int n2, int cols2, int rows2,
+                          int min_level, int max_level, float search_r,
+                          tb_match *out, int capacity, int *n);
+
+/* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
+ * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
+ * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */
+int tb_search_by_projection(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, const float *Tcw1,
+                            const tb_keypoint *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                            const float *sf1, int n_levels1, int cols1, int rows1,
+                            const tb_keypoint *k2, int n2, const uint8_t *mp_valid, const float *mp_xyz,
+                            const uint8_t *mp_desc, tb_match *out, int capacity, int *n);
+
+/* Matcher::searchByProjection(map,F1,radio) (matcher.cpp:539-617) + Frame::IsInFrustum
+ * (src/types/Frame.cpp:370-412). Map points in the caller's iteration order. */
+int tb_search_by_projection_map(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, const float *Tcw1,
+                                const tb_keypoint *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                                const float *sf1, int cols1, int rows1,
+                                int n_mp, const uint8_t *mp_bad, const float *mp_xyz, const float *mp_normal,
+                                const uint8_t *mp_desc, float radio, tb_match *out, int capacity, int *n);
+
+/* Matcher::ComputeThreeMaxima (matcher.cpp:810-851) — host helper kept for API completeness. */
+void tb_three_maxima(const int32_t *hist_sizes, int L, int *ind1, int *ind2, int *ind3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB_CAPI_H */

@@ -1,0 +1,295 @@
+"""ctypes binding of libtb_b200.so — exactly the C ABI declared in include/tb_capi.h.
+
+This module is plumbing: it loads the CUDA library (failing loudly if it is missing — there is no
+CPU fallback) and converts numpy arrays / raw device pointers to the POD arguments.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtb_b200.so')
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'),
+                     ('response', '<f4'), ('octave', '<i4'), ('class_id', '<i4')])
+MATCH_DTYPE = np.dtype([('queryIdx', '<i4'), ('trainIdx', '<i4'), ('imgIdx', '<i4'), ('distance', '<f4')])
+
+TB_OK, TB_E_INVALID, TB_E_CUDA, TB_E_CAPACITY, TB_E_UNSUPPORTED, TB_E_NOMEM = 0, -1, -2, -3, -4, -5
+TB_MAX_LEVELS = 16
+
+# every symbol include/tb_capi.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    'tb_ctx_create', 'tb_ctx_destroy', 'tb_sync', 'tb_last_error', 'tb_version', 'tb_launch_count',
+    'tb_pyramid_geometry',
+    'tb_frontend_create', 'tb_frontend_destroy', 'tb_frontend_kp_capacity', 'tb_frontend_level_layout',
+    'tb_frontend_upload_level', 'tb_frontend_download_level', 'tb_frontend_upload_frames',
+    'tb_frontend_build_pyramid', 'tb_frontend_extract', 'tb_frontend_results_device',
+    'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_candidates',
+    'tb_frontend_get_level_counts', 'tb_orb_extract_host',
+    'tb_hamming_pairs_device', 'tb_knn2_device', 'tb_match_bf_cross_device', 'tb_search_by_bf_device',
+    'tb_frontend_search_by_bf', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
+    'tb_search_by_projection_map', 'tb_three_maxima',
+]
+
+
+class MatcherParams(C.Structure):
+    _fields_ = [('TH_LOW', C.c_int32), ('TH_HIGH', C.c_int32), ('HISTO_LENGTH', C.c_int32),
+                ('checkOrientation', C.c_int32), ('nRatio', C.c_float)]
+
+
+class Pinhole(C.Structure):
+    _fields_ = [('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
+                ('width', C.c_int32), ('height', C.c_int32), ('d', C.c_float * 5)]
+
+
+class TbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('tb error %d: %s' % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libtb_b200.so. Raises if the CUDA extension has not been built — never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError('%s is missing: run `python -m trackingbench_slam_b200.build` '
+                              '(there is no CPU fallback)' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.tb_last_error.restype = C.c_char_p
+        L.tb_version.restype = C.c_char_p
+        L.tb_launch_count.restype = C.c_int64
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def pyramid_geometry(width, height, n_levels, scale):
+    sf = np.zeros(n_levels, np.float32)
+    lw = np.zeros(n_levels, np.int32)
+    lh = np.zeros(n_levels, np.int32)
+    rc = lib().tb_pyramid_geometry(width, height, n_levels, C.c_float(scale), _vp(sf), _vp(lw), _vp(lh))
+    if rc:
+        raise TbError(rc, 'tb_pyramid_geometry')
+    return sf, lw, lh
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        rc = lib().tb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc:
+            raise TbError(rc, 'tb_ctx_create failed (no usable CUDA device?)')
+
+    def check(self, rc, allow=()):
+        if rc and rc not in allow:
+            raise TbError(rc, lib().tb_last_error(self.h).decode())
+        return rc
+
+    def sync(self):
+        self.check(lib().tb_sync(self.h))
+
+    def launch_count(self):
+        return lib().tb_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().tb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # ---- matching on device pointers (ints) or numpy arrays uploaded by the caller elsewhere
+    def hamming_pairs_device(self, a_dptr, b_dptr, n, out_dptr):
+        self.check(lib().tb_hamming_pairs_device(self.h, _vp(a_dptr), _vp(b_dptr), int(n), _vp(out_dptr)))
+
+    def knn2_device(self, q_dptr, nq, t_dptr, nt, idx_dptr, best_dptr, second_dptr):
+        self.check(lib().tb_knn2_device(self.h, _vp(q_dptr), int(nq), _vp(t_dptr), int(nt),
+                                        _vp(idx_dptr), _vp(best_dptr), _vp(second_dptr)))
+
+    def match_bf_cross_device(self, d1_dptr, n1, d2_dptr, n2):
+        out = np.zeros(max(int(n1), 1), MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_match_bf_cross_device(self.h, _vp(d1_dptr), int(n1), _vp(d2_dptr), int(n2),
+                                                  _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def search_by_bf_device(self, d1_dptr, n1, d2_dptr, n2, ratio, minTh):
+        out = np.zeros(max(int(n1), 1), MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_search_by_bf_device(self.h, _vp(d1_dptr), int(n1), _vp(d2_dptr), int(n2),
+                                                C.c_float(ratio), C.c_float(minTh), _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- windowed matchers (host in / host out)
+    def features_in_area(self, kps, cols, rows, x, y, r, minLevel=-1, maxLevel=-1):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        out = np.zeros(len(kps) + 1, np.int32)
+        n = C.c_int()
+        self.check(lib().tb_features_in_area(self.h, _vp(kps), len(kps), int(cols), int(rows), C.c_float(x), C.c_float(y),
+                                             C.c_float(r), int(minLevel), int(maxLevel), _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def search_by_violence(self, params, k1, d1, k2, d2, cols2, rows2, min_level=0, max_level=1, search_r=10.0):
+        k1 = np.ascontiguousarray(k1, KP_DTYPE)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8)
+        d2 = np.ascontiguousarray(d2, np.uint8)
+        out = np.zeros(len(k1) + 1, MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_search_by_violence(self.h, C.byref(params), _vp(k1), _vp(d1), len(k1), _vp(k2), _vp(d2), len(k2),
+                                               int(cols2), int(rows2), int(min_level), int(max_level), C.c_float(search_r),
+                                               _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def search_by_projection(self, params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1, k2, mp_valid, mp_xyz, mp_desc):
+        k1 = np.ascontiguousarray(k1, KP_DTYPE)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        Tcw1 = np.ascontiguousarray(Tcw1, np.float32)
+        sf1 = np.ascontiguousarray(sf1, np.float32)
+        mp_valid = np.ascontiguousarray(mp_valid, np.uint8)
+        mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+        fm = None if f1_matched is None else np.ascontiguousarray(f1_matched, np.uint8)
+        out = np.zeros(len(k2) + 1, MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_search_by_projection(self.h, C.byref(params), C.byref(cam), _vp(Tcw1), _vp(k1), _vp(d1), len(k1),
+                                                 _vp(fm), _vp(sf1), len(sf1), int(cols1), int(rows1), _vp(k2), len(k2),
+                                                 _vp(mp_valid), _vp(mp_xyz), _vp(mp_desc), _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def search_by_projection_map(self, params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1,
+                                 mp_bad, mp_xyz, mp_normal, mp_desc, radio):
+        k1 = np.ascontiguousarray(k1, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        Tcw1 = np.ascontiguousarray(Tcw1, np.float32)
+        sf1 = np.ascontiguousarray(sf1, np.float32)
+        mp_bad = np.ascontiguousarray(mp_bad, np.uint8)
+        mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+        mp_normal = np.ascontiguousarray(mp_normal, np.float32)
+        fm = None if f1_matched is None else np.ascontiguousarray(f1_matched, np.uint8)
+        out = np.zeros(len(mp_bad) + 1, MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_search_by_projection_map(self.h, C.byref(params), C.byref(cam), _vp(Tcw1), _vp(k1), _vp(d1), len(k1),
+                                                     _vp(fm), _vp(sf1), int(cols1), int(rows1), len(mp_bad), _vp(mp_bad),
+                                                     _vp(mp_xyz), _vp(mp_normal), _vp(mp_desc), C.c_float(radio),
+                                                     _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
+class Frontend:
+    """tb_frontend: device-resident batch of equally sized frames."""
+
+    def __init__(self, ctx, level_w, level_h, max_batch=1, max_target=2000):
+        self.ctx = ctx
+        self.level_w = np.ascontiguousarray(level_w, np.int32)
+        self.level_h = np.ascontiguousarray(level_h, np.int32)
+        self.n_levels = len(self.level_w)
+        self.max_batch = max_batch
+        self.h = C.c_void_p()
+        ctx.check(lib().tb_frontend_create(ctx.h, self.n_levels, _vp(self.level_w), _vp(self.level_h),
+                                           int(max_batch), int(max_target), C.byref(self.h)))
+        self.kp_cap = lib().tb_frontend_kp_capacity(self.h)
+
+    def close(self):
+        if self.h:
+            lib().tb_frontend_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def level_layout(self, level, blurred=False):
+        base, pitch, fs = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self.ctx.check(lib().tb_frontend_level_layout(self.h, level, int(blurred), C.byref(base), C.byref(pitch), C.byref(fs)))
+        return base.value, pitch.value, fs.value
+
+    def upload_level(self, frame, level, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.level_h[level], self.level_w[level]), (img.shape, level)
+        self.ctx.check(lib().tb_frontend_upload_level(self.h, frame, level, _vp(img), img.strides[0]))
+        self.ctx.sync()
+
+    def upload_frames(self, first, frames):
+        """frames: (n, H, W) u8 contiguous numpy array or a host pointer tuple (ptr, n)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.shape[1:] == (self.level_h[0], self.level_w[0])
+        self.ctx.check(lib().tb_frontend_upload_frames(self.h, first, frames.shape[0], _vp(frames), frames.strides[1]))
+
+    def upload_frames_ptr(self, first, n, host_ptr, host_stride):
+        self.ctx.check(lib().tb_frontend_upload_frames(self.h, first, n, C.c_void_p(host_ptr), host_stride))
+
+    def download_level(self, frame, level, blurred=False):
+        out = np.empty((self.level_h[level], self.level_w[level]), np.uint8)
+        self.ctx.check(lib().tb_frontend_download_level(self.h, frame, level, int(blurred), _vp(out), out.strides[0]))
+        return out
+
+    def build_pyramid(self, n_frames):
+        self.ctx.check(lib().tb_frontend_build_pyramid(self.h, n_frames))
+
+    def extract(self, n_frames, sf, target, initTh, minTh, exit_kps=None):
+        sf = np.ascontiguousarray(sf, np.float32)
+        ex = None if exit_kps is None else np.ascontiguousarray(exit_kps, KP_DTYPE)
+        self.ctx.check(lib().tb_frontend_extract(self.h, n_frames, _vp(sf), int(target), C.c_float(initTh), C.c_float(minTh),
+                                                 _vp(ex), 0 if ex is None else len(ex)))
+
+    def results_device(self):
+        k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().tb_frontend_results_device(self.h, C.byref(k), C.byref(d), C.byref(c)))
+        return k.value, d.value, c.value
+
+    def get_results(self, frame):
+        kps = np.zeros(self.kp_cap, KP_DTYPE)
+        desc = np.zeros((self.kp_cap, 32), np.uint8)
+        n = C.c_int()
+        self.ctx.check(lib().tb_frontend_get_results(self.h, frame, _vp(kps), _vp(desc), self.kp_cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def get_results_batch(self, n_frames, kps=None, desc=None, counts=None):
+        kps = np.zeros((n_frames, self.kp_cap), KP_DTYPE) if kps is None else kps
+        desc = np.zeros((n_frames, self.kp_cap, 32), np.uint8) if desc is None else desc
+        counts = np.zeros(n_frames, np.int32) if counts is None else counts
+        self.ctx.check(lib().tb_frontend_get_results_batch(self.h, n_frames, _vp(kps), _vp(desc), self.kp_cap, _vp(counts)))
+        return kps, desc, counts
+
+    def get_candidates(self, frame, level):
+        cap = int(self.level_w[level]) * int(self.level_h[level]) // 4 + 64
+        out = np.zeros(cap, KP_DTYPE)
+        n = C.c_int()
+        self.ctx.check(lib().tb_frontend_get_candidates(self.h, frame, level, _vp(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def get_level_counts(self, frame):
+        out = np.zeros(self.n_levels, np.int32)
+        self.ctx.check(lib().tb_frontend_get_level_counts(self.h, frame, _vp(out)))
+        return out
+
+    def orb_extract_host(self, levels, sf, target, initTh, minTh, exit_kps=None):
+        levels = [np.ascontiguousarray(l, np.uint8) for l in levels]
+        n = len(levels)
+        ptrs = (C.c_void_p * n)(*[l.ctypes.data for l in levels])
+        strides = (C.c_size_t * n)(*[l.strides[0] for l in levels])
+        sf = np.ascontiguousarray(sf, np.float32)
+        ex = None if exit_kps is None else np.ascontiguousarray(exit_kps, KP_DTYPE)
+        kps = np.zeros(self.kp_cap, KP_DTYPE)
+        desc = np.zeros((self.kp_cap, 32), np.uint8)
+        cnt = C.c_int()
+        self.ctx.check(lib().tb_orb_extract_host(self.h, ptrs, strides, _vp(sf), int(target), C.c_float(initTh), C.c_float(minTh),
+                                                 _vp(ex), 0 if ex is None else len(ex), _vp(kps), _vp(desc), self.kp_cap, C.byref(cnt)))
+        return kps[:cnt.value].copy(), desc[:cnt.value].copy()
+
+    def search_by_bf(self, q_frames, t_frames, ratio, minTh, matches_dptr, capacity, counts_dptr):
+        q = np.ascontiguousarray(q_frames, np.int32)
+        t = np.ascontiguousarray(t_frames, np.int32)
+        self.ctx.check(lib().tb_frontend_search_by_bf(self.h, len(q), _vp(q), _vp(t), C.c_float(ratio), C.c_float(minTh),
+                                                      _vp(matches_dptr), int(capacity), _vp(counts_dptr)))

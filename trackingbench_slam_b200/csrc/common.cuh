@@ -1,0 +1,68 @@
+// common.cuh — shared declarations for libtb_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/tb_capi.h"
+
+#ifndef __CUDA_ARCH__
+#define TB_HOST_ONLY 1
+#endif
+
+struct tb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    int64_t launches = 0;
+    std::string err;
+    struct MatchWs *mws = nullptr;   // lazily grown matching workspace (match.cu)
+};
+void tb_match_ws_free(tb_ctx *ctx);
+
+static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define TB_CUDA(ctx, expr)                                                                    \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) return tb_fail((ctx), TB_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define TB_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) return tb_fail((ctx), TB_E_CUDA, "kernel launch: %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Packed FAST candidate: y:12 | x:12 | m:8, coordinates relative to the (16,16) border.
+// m = max(A,B) of the FAST-9 arcs; response = m - 1.
+__host__ __device__ static inline uint32_t cand_pack(int x, int y, int m) { return ((uint32_t)y << 20) | ((uint32_t)x << 8) | (uint32_t)m; }
+__host__ __device__ static inline int cand_x(uint32_t c) { return (c >> 8) & 0xFFF; }
+__host__ __device__ static inline int cand_y(uint32_t c) { return c >> 20; }
+__host__ __device__ static inline int cand_m(uint32_t c) { return c & 0xFF; }
+
+// Per-level geometry of the ORB cell grid (ORBextractor.cpp:743-763), computed on the host.
+struct LevelGeom {
+    int w, h;           // level size
+    int pitch;          // row pitch in bytes
+    size_t frame_stride;
+    int nCols, nRows, wCell, hCell;
+    int nColsRun, nRowsRun; // cells not skipped by the iniX/iniY tests (:770,:779)
+    int maxBX, maxBY;   // w-16, h-16
+    int cand_cap;       // candidate slots per (frame, level)
+    int nIni;           // initial octree nodes (:498)
+    float hX;           // (:500)
+};

@@ -1,0 +1,439 @@
+// frontend.cu — context + tb_frontend: owns the device-resident batch (pyramid, blurred pyramid,
+// FAST candidates, octree scratch, keypoints/descriptors) and sequences the kernels.
+// Host code here is bookkeeping only (sizes, budgets, launches); all image / descriptor
+// arithmetic runs in the CUDA kernels of pyramid.cu, fast.cu, octree.cu, describe.cu, match.cu.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <cmath>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------ ctx
+extern "C" const char *tb_version(void) { return "trackingbench_slam_b200 0.1 (sm_100a)"; }
+
+extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
+{
+    if (!out) return TB_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TB_E_CUDA; // no CPU fallback: fail loudly
+    if (device < 0 || device >= ndev) return TB_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return TB_E_CUDA;
+    tb_ctx *c = new tb_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return TB_E_CUDA; }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return TB_OK;
+}
+extern "C" void tb_ctx_destroy(tb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    tb_match_ws_free(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int tb_sync(tb_ctx *ctx)
+{
+    if (!ctx) return TB_E_INVALID;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
+}
+extern "C" const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" int64_t tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// Frame::Frame scale tables + ComputePyramid sizes (reference src/types/Frame.cpp:18-29, :424)
+extern "C" int tb_pyramid_geometry(int width, int height, int n_levels, float scale, float *sf, int32_t *lw, int32_t *lh)
+{
+    if (n_levels <= 0 || n_levels > TB_MAX_LEVELS || width <= 0 || height <= 0) return TB_E_INVALID;
+    std::vector<float> s(n_levels, 1.f);
+    for (int i = 1; i < n_levels; i++) {
+        volatile float v = s[i - 1] * scale; // float32 chain
+        s[i] = v;
+    }
+    for (int i = 0; i < n_levels; i++) {
+        if (sf) sf[i] = s[i];
+        volatile float fw = (float)width * s[i], fh = (float)height * s[i];
+        if (lw) lw[i] = i == 0 ? width : (int)fw;
+        if (lh) lh[i] = i == 0 ? height : (int)fh;
+    }
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ frontend
+struct tb_frontend {
+    tb_ctx *ctx = nullptr;
+    int L = 0, B = 0, max_target = 0, kp_cap = 0, kept_cap = 0;
+    LevelGeom g[TB_MAX_LEVELS];
+    uint8_t *pyr[TB_MAX_LEVELS] = {}, *blur[TB_MAX_LEVELS] = {};
+    int4 *xtab[TB_MAX_LEVELS] = {}, *ytab[TB_MAX_LEVELS] = {};
+    bool area2[TB_MAX_LEVELS] = {};
+    uint32_t *cand[TB_MAX_LEVELS] = {}, *kept[TB_MAX_LEVELS] = {};
+    uint16_t *nid[TB_MAX_LEVELS] = {};
+    int *n_cand = nullptr, *n_kept = nullptr, *n_kp = nullptr, *overflow = nullptr;
+    tb_keypoint *kps = nullptr;
+    uint8_t *desc = nullptr;
+    float2 *exit_xy = nullptr; int16_t *enid = nullptr; int exit_cap = 0;
+    int budget[TB_MAX_LEVELS] = {};
+    bool has_budget = false;
+    std::vector<void *> allocs;
+};
+
+template <typename T> static int dev_alloc(tb_frontend *fe, T **p, size_t count)
+{
+    void *q = nullptr;
+    if (cudaMalloc(&q, count * sizeof(T) + 256) != cudaSuccess) return tb_fail(fe->ctx, TB_E_NOMEM, "cudaMalloc failed");
+    fe->allocs.push_back(q);
+    *p = (T *)q;
+    return TB_OK;
+}
+
+static void level_geometry(LevelGeom &g, int w, int h, int B)
+{
+    // ORBextractor.cpp:743-763 (cell grid) and :498-500 (initial octree nodes)
+    g.w = w; g.h = h;
+    g.pitch = (int)align_up((size_t)w, 64);
+    g.frame_stride = (size_t)g.pitch * h;
+    const int minB = 16;
+    g.maxBX = w - 16; g.maxBY = h - 16;
+    const float width = (float)(g.maxBX - minB), height = (float)(g.maxBY - minB);
+    g.nCols = (int)(width / 30.f); g.nRows = (int)(height / 30.f);
+    if (g.nCols <= 0 || g.nRows <= 0) { g.nCols = g.nRows = 0; g.wCell = g.hCell = 1; g.nColsRun = g.nRowsRun = 0; g.cand_cap = 64; g.nIni = 0; g.hX = 1.f; return; }
+    g.wCell = (int)ceil(width / (float)g.nCols); g.hCell = (int)ceil(height / (float)g.nRows);
+    g.nColsRun = 0; for (int j = 0; j < g.nCols; j++) if ((float)(minB + j * g.wCell) < (float)g.maxBX - 6.f) g.nColsRun++;
+    g.nRowsRun = 0; for (int i = 0; i < g.nRows; i++) if ((float)minB + (float)i * (float)g.hCell < (float)g.maxBY - 3.f) g.nRowsRun++;
+    int wi = w - 38 > 0 ? w - 38 : 0, hi = h - 38 > 0 ? h - 38 : 0;
+    g.cand_cap = ((wi + g.nCols + 1) / 2) * ((hi + g.nRows + 1) / 2) + 64; // NMS survivors can never exceed this
+    g.nIni = (int)roundf((float)(g.maxBX - minB) / (g.maxBY - minB));
+    volatile float hx = (float)(g.maxBX - minB) / g.nIni;
+    g.hX = g.nIni > 0 ? hx : 1.f;
+    (void)B;
+}
+
+extern "C" void tb_frontend_destroy(tb_frontend *fe)
+{
+    if (!fe) return;
+    cudaSetDevice(fe->ctx->device);
+    cudaStreamSynchronize(fe->ctx->stream);
+    for (void *p : fe->allocs) cudaFree(p);
+    delete fe;
+}
+
+extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, const int32_t *lh, int max_batch, int max_target, tb_frontend **out)
+{
+    if (!ctx || !out || !lw || !lh || n_levels <= 0 || n_levels > TB_MAX_LEVELS || max_batch <= 0 || max_target <= 0) return TB_E_INVALID;
+    *out = nullptr;
+    for (int l = 0; l < n_levels; l++) {
+        if (lw[l] <= 0 || lh[l] <= 0) return tb_fail(ctx, TB_E_INVALID, "level size must be positive");
+        if (lw[l] > 4096 || lh[l] > 4096) return tb_fail(ctx, TB_E_UNSUPPORTED, "level dimensions above 4096 are not supported (12-bit packed coordinates)");
+    }
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    tb_frontend *fe = new tb_frontend();
+    fe->ctx = ctx; fe->L = n_levels; fe->B = max_batch; fe->max_target = max_target;
+    fe->kept_cap = max_target + 8;
+    fe->kp_cap = max_target + 4 * n_levels + 16;
+    int rc = TB_OK;
+    const size_t B = (size_t)max_batch;
+    for (int l = 0; l < n_levels && !rc; l++) {
+        LevelGeom &g = fe->g[l];
+        level_geometry(g, lw[l], lh[l], max_batch);
+        if ((rc = dev_alloc(fe, &fe->pyr[l], g.frame_stride * B))) break;
+        if ((rc = dev_alloc(fe, &fe->blur[l], g.frame_stride * B))) break;
+        if ((rc = dev_alloc(fe, &fe->cand[l], (size_t)g.cand_cap * B))) break;
+        if ((rc = dev_alloc(fe, &fe->nid[l], (size_t)g.cand_cap * B))) break;
+        if ((rc = dev_alloc(fe, &fe->kept[l], (size_t)fe->kept_cap * B))) break;
+        // padding bytes of every row must be defined (4-byte loads may touch them)
+        cudaMemsetAsync(fe->pyr[l], 0, g.frame_stride * B, ctx->stream);
+        if (l > 0) {
+            fe->area2[l] = tb_resize_is_area2(lw[l - 1], lh[l - 1], lw[l], lh[l]);
+            std::vector<ResizeTab> tx, ty; std::vector<int32_t> x1, y1;
+            tb_build_resize_tab(lw[l - 1], lw[l], true, tx, x1);
+            tb_build_resize_tab(lh[l - 1], lh[l], false, ty, y1);
+            std::vector<int4> hx(lw[l]), hy(lh[l]);
+            for (int i = 0; i < lw[l]; i++) hx[i] = make_int4(tx[i].ofs, x1[i], tx[i].c0, tx[i].c1);
+            for (int i = 0; i < lh[l]; i++) hy[i] = make_int4(ty[i].ofs, y1[i], ty[i].c0, ty[i].c1);
+            if ((rc = dev_alloc(fe, &fe->xtab[l], hx.size()))) break;
+            if ((rc = dev_alloc(fe, &fe->ytab[l], hy.size()))) break;
+            cudaMemcpy(fe->xtab[l], hx.data(), hx.size() * sizeof(int4), cudaMemcpyHostToDevice);
+            cudaMemcpy(fe->ytab[l], hy.data(), hy.size() * sizeof(int4), cudaMemcpyHostToDevice);
+        }
+    }
+    if (!rc) rc = dev_alloc(fe, &fe->n_cand, B * n_levels);
+    if (!rc) rc = dev_alloc(fe, &fe->n_kept, B * n_levels);
+    if (!rc) rc = dev_alloc(fe, &fe->n_kp, B);
+    if (!rc) rc = dev_alloc(fe, &fe->overflow, 4);
+    if (!rc) rc = dev_alloc(fe, &fe->kps, B * fe->kp_cap);
+    if (!rc) rc = dev_alloc(fe, &fe->desc, B * fe->kp_cap * 32);
+    if (!rc) {
+        cudaMemsetAsync(fe->n_kp, 0, sizeof(int) * B, ctx->stream);
+        cudaMemsetAsync(fe->n_kept, 0, sizeof(int) * B * n_levels, ctx->stream);
+        cudaMemsetAsync(fe->n_cand, 0, sizeof(int) * B * n_levels, ctx->stream);
+        cudaMemsetAsync(fe->overflow, 0, sizeof(int) * 4, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = tb_fail(ctx, TB_E_CUDA, "frontend init failed");
+    }
+    if (rc) { tb_frontend_destroy(fe); return rc; }
+    *out = fe;
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_kp_capacity(const tb_frontend *fe) { return fe ? fe->kp_cap : 0; }
+
+extern "C" int tb_frontend_level_layout(const tb_frontend *fe, int level, int blurred, void **base, size_t *pitch, size_t *frame_stride)
+{
+    if (!fe || level < 0 || level >= fe->L) return TB_E_INVALID;
+    if (base) *base = blurred ? fe->blur[level] : fe->pyr[level];
+    if (pitch) *pitch = fe->g[level].pitch;
+    if (frame_stride) *frame_stride = fe->g[level].frame_stride;
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_upload_level(tb_frontend *fe, int frame, int level, const uint8_t *host, size_t host_stride)
+{
+    if (!fe || !host || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L) return TB_E_INVALID;
+    const LevelGeom &g = fe->g[level];
+    TB_CUDA(fe->ctx, cudaMemcpy2DAsync(fe->pyr[level] + (size_t)frame * g.frame_stride, g.pitch, host, host_stride, g.w, g.h,
+                                       cudaMemcpyHostToDevice, fe->ctx->stream));
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_upload_frames(tb_frontend *fe, int first, int n, const uint8_t *host, size_t host_stride)
+{
+    if (!fe || !host || first < 0 || n < 0 || first + n > fe->B) return TB_E_INVALID;
+    const LevelGeom &g = fe->g[0];
+    // frames are back to back on the host and at frame_stride on the device: one strided copy
+    TB_CUDA(fe->ctx, cudaMemcpy2DAsync(fe->pyr[0] + (size_t)first * g.frame_stride, g.pitch, host, host_stride, g.w, (size_t)g.h * n,
+                                       cudaMemcpyHostToDevice, fe->ctx->stream));
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_download_level(tb_frontend *fe, int frame, int level, int blurred, uint8_t *host, size_t host_stride)
+{
+    if (!fe || !host || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L) return TB_E_INVALID;
+    const LevelGeom &g = fe->g[level];
+    const uint8_t *src = (blurred ? fe->blur[level] : fe->pyr[level]) + (size_t)frame * g.frame_stride;
+    TB_CUDA(fe->ctx, cudaMemcpy2DAsync(host, host_stride, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, fe->ctx->stream));
+    TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
+{
+    if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
+    if (n_frames == 0) return TB_OK;
+    for (int l = 1; l < fe->L; l++) {
+        const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
+        int rc = tb_launch_resize(fe->ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
+                                  d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames);
+        if (rc) return rc;
+    }
+    return TB_OK;
+}
+
+// ORBextractor.cpp:919-930
+static void orb_budget(int L, float factor, int target, int *per_level)
+{
+    volatile float denom = 1 - (float)pow((double)factor, (double)L);
+    volatile float numer = target * (1 - factor);
+    volatile float nDesired = numer / denom;
+    int sum = 0;
+    for (int level = 0; level < L - 1; level++) {
+        per_level[level] = (int)lrintf(nDesired);
+        sum += per_level[level];
+        nDesired = nDesired * factor;
+    }
+    per_level[L - 1] = target - sum > 0 ? target - sum : 0;
+}
+
+extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
+                                   const tb_keypoint *exit_kps, int n_exit)
+{
+    if (!fe || !sf || n_frames < 0 || n_frames > fe->B || target <= 0 || n_exit < 0) return TB_E_INVALID;
+    tb_ctx *ctx = fe->ctx;
+    if (target > fe->max_target) return tb_fail(ctx, TB_E_INVALID, "target exceeds the frontend's max_target");
+    if (n_frames == 0) return TB_OK;
+    const int L = fe->L;
+    const bool add_points = exit_kps != nullptr;
+    if (add_points) {
+        if (!fe->has_budget) return tb_fail(ctx, TB_E_INVALID, "AddPoints before operator(): the reference reads an unset mnFeaturesPerLevel here");
+    } else {
+        if (L < 2) { fe->budget[0] = target; } // (the reference indexes mvScaleFactor[1]; single level => all features)
+        else orb_budget(L, sf[1], target, fe->budget);
+        fe->has_budget = true;
+    }
+    if (add_points && n_exit > 0) {
+        if (n_exit > fe->exit_cap) {
+            int rc = dev_alloc(fe, &fe->exit_xy, (size_t)n_exit);
+            if (!rc) rc = dev_alloc(fe, &fe->enid, (size_t)n_exit * fe->B);
+            if (rc) return rc;
+            fe->exit_cap = n_exit;
+        }
+        std::vector<float2> xy(n_exit);
+        for (int i = 0; i < n_exit; i++) xy[i] = make_float2(exit_kps[i].x, exit_kps[i].y);
+        TB_CUDA(ctx, cudaMemcpyAsync(fe->exit_xy, xy.data(), sizeof(float2) * n_exit, cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    TB_CUDA(ctx, cudaMemsetAsync(fe->n_cand, 0, sizeof(int) * (size_t)n_frames * L, ctx->stream));
+    TB_CUDA(ctx, cudaMemsetAsync(fe->n_kept, 0, sizeof(int) * (size_t)n_frames * L, ctx->stream));
+    TB_CUDA(ctx, cudaMemsetAsync(fe->overflow, 0, sizeof(int) * 4, ctx->stream));
+
+    int max_budget = 0;
+    for (int l = 0; l < L; l++) {
+        const LevelGeom &g = fe->g[l];
+        if (g.nColsRun > 0 && g.nRowsRun > 0) {
+            FastArgs a;
+            a.img = fe->pyr[l]; a.pitch = g.pitch; a.frame_stride = g.frame_stride; a.w = g.w; a.h = g.h;
+            a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
+            a.G = 256 / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
+            a.scw = a.G * g.wCell;
+            a.tpitch = ((3 + a.scw + 6 + 3) & ~3) + 4;
+            a.initTh = (int)initTh; a.minTh = (int)minTh;
+            a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
+            a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
+            a.overflow = fe->overflow;
+            size_t smem = (size_t)(g.hCell + 6) * a.tpitch + (size_t)((g.hCell * a.scw + 3) & ~3) + 2 * (size_t)g.hCell * a.scw + 16;
+            int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
+            if (rc) return rc;
+        }
+        OctArgs o;
+        o.cand = fe->cand[l]; o.cand_cap = g.cand_cap; o.n_cand = fe->n_cand + l; o.n_stride = L;
+        o.nid = fe->nid[l]; o.N = fe->budget[l];
+        o.W = g.maxBX - 16; o.H = g.maxBY - 16; o.nIni = g.nIni; o.hX = g.hX; o.wCell = g.wCell; o.hCell = g.hCell;
+        o.exit_xy = fe->exit_xy; o.n_exit = add_points ? n_exit : 0; o.enid = fe->enid;
+        o.kept = fe->kept[l]; o.kept_cap = fe->kept_cap; o.n_kept = fe->n_kept + l; o.overflow = fe->overflow;
+        o.node_cap = fe->budget[l] + 4 * (g.nIni > 0 ? g.nIni : 1) + 8;
+        int rc = tb_launch_octree(ctx, o, n_frames);
+        if (rc) return rc;
+        if (fe->budget[l] > max_budget) max_budget = fe->budget[l];
+    }
+    for (int l = 0; l < L; l++) {
+        const LevelGeom &g = fe->g[l];
+        int rc = tb_launch_gauss(ctx, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
+        if (rc) return rc;
+    }
+    DescArgs d;
+    memset(&d, 0, sizeof d);
+    d.n_levels = L; d.n_kept = fe->n_kept; d.kps = fe->kps; d.desc = fe->desc; d.kp_cap = fe->kp_cap; d.n_kp = fe->n_kp;
+    d.overflow = fe->overflow;
+    for (int l = 0; l < L; l++) {
+        const LevelGeom &g = fe->g[l];
+        d.lv[l].raw = fe->pyr[l]; d.lv[l].blur = fe->blur[l]; d.lv[l].pitch = g.pitch; d.lv[l].frame_stride = g.frame_stride;
+        d.lv[l].kept = fe->kept[l]; d.lv[l].kept_cap = fe->kept_cap;
+        d.lv[l].sf = sf[l];
+        volatile float ps = 31 * sf[l];
+        d.lv[l].size = (float)(int)ps; // (int)(PATCH_SIZE*mvScaleFactor[level]) :812
+    }
+    return tb_launch_describe(ctx, d, max_budget + 4, n_frames);
+}
+
+static int check_overflow(tb_frontend *fe)
+{
+    int ov[4] = {0, 0, 0, 0};
+    TB_CUDA(fe->ctx, cudaMemcpyAsync(ov, fe->overflow, sizeof ov, cudaMemcpyDeviceToHost, fe->ctx->stream));
+    TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
+    if (ov[0]) return tb_fail(fe->ctx, TB_E_CAPACITY, "internal buffer overflow during extract (candidates / octree nodes / keypoints)");
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_results_device(const tb_frontend *fe, void **kps, void **desc, void **counts)
+{
+    if (!fe) return TB_E_INVALID;
+    if (kps) *kps = fe->kps;
+    if (desc) *desc = fe->desc;
+    if (counts) *counts = fe->n_kp;
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_get_results(tb_frontend *fe, int frame, tb_keypoint *kps, uint8_t *desc, int capacity, int *n)
+{
+    if (!fe || frame < 0 || frame >= fe->B || !n || capacity < 0) return TB_E_INVALID;
+    tb_ctx *ctx = fe->ctx;
+    int rc = check_overflow(fe);
+    if (rc) return rc;
+    int cnt = 0;
+    TB_CUDA(ctx, cudaMemcpy(&cnt, fe->n_kp + frame, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    int m = cnt < capacity ? cnt : capacity;
+    if (m > 0 && kps) TB_CUDA(ctx, cudaMemcpy(kps, fe->kps + (size_t)frame * fe->kp_cap, sizeof(tb_keypoint) * m, cudaMemcpyDeviceToHost));
+    if (m > 0 && desc) TB_CUDA(ctx, cudaMemcpy(desc, fe->desc + (size_t)frame * fe->kp_cap * 32, (size_t)32 * m, cudaMemcpyDeviceToHost));
+    return cnt > capacity ? tb_fail(ctx, TB_E_CAPACITY, "keypoint output capacity too small") : TB_OK;
+}
+
+extern "C" int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
+{
+    if (!fe || n_frames < 0 || n_frames > fe->B || !counts || capacity < 0) return TB_E_INVALID;
+    tb_ctx *ctx = fe->ctx;
+    if (n_frames == 0) return TB_OK;
+    const int m = capacity < fe->kp_cap ? capacity : fe->kp_cap;
+    TB_CUDA(ctx, cudaMemcpyAsync(counts, fe->n_kp, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kps) TB_CUDA(ctx, cudaMemcpy2DAsync(kps, sizeof(tb_keypoint) * capacity, fe->kps, sizeof(tb_keypoint) * fe->kp_cap,
+                                            sizeof(tb_keypoint) * m, n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) TB_CUDA(ctx, cudaMemcpy2DAsync(desc, (size_t)32 * capacity, fe->desc, (size_t)32 * fe->kp_cap, (size_t)32 * m, n_frames,
+                                             cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = check_overflow(fe);
+    if (rc) return rc;
+    for (int f = 0; f < n_frames; f++) if (counts[f] > capacity) return tb_fail(ctx, TB_E_CAPACITY, "keypoint output capacity too small");
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_get_level_counts(tb_frontend *fe, int frame, int32_t *n_per_level)
+{
+    if (!fe || frame < 0 || frame >= fe->B || !n_per_level) return TB_E_INVALID;
+    TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
+    TB_CUDA(fe->ctx, cudaMemcpy(n_per_level, fe->n_kept + (size_t)frame * fe->L, sizeof(int) * fe->L, cudaMemcpyDeviceToHost));
+    return TB_OK;
+}
+
+// Candidates are stored unordered; the reference order is (cell row, cell col, y, x). Sort on the
+// host for the stage test only (this accessor is test plumbing, not part of the data path).
+extern "C" int tb_frontend_get_candidates(tb_frontend *fe, int frame, int level, tb_keypoint *out, int capacity, int *n)
+{
+    if (!fe || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L || !n) return TB_E_INVALID;
+    tb_ctx *ctx = fe->ctx;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int cnt = 0;
+    TB_CUDA(ctx, cudaMemcpy(&cnt, fe->n_cand + (size_t)frame * fe->L + level, sizeof(int), cudaMemcpyDeviceToHost));
+    const LevelGeom &g = fe->g[level];
+    if (cnt > g.cand_cap) cnt = g.cand_cap;
+    std::vector<uint32_t> c(cnt);
+    if (cnt) TB_CUDA(ctx, cudaMemcpy(c.data(), fe->cand[level] + (size_t)frame * g.cand_cap, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> key(cnt);
+    for (int i = 0; i < cnt; i++) {
+        uint64_t x = cand_x(c[i]), y = cand_y(c[i]);
+        key[i] = (((y - 3) / g.hCell) << 52) | (((x - 3) / g.wCell) << 40) | (y << 28) | (x << 16) | (uint64_t)cand_m(c[i]);
+    }
+    std::sort(key.begin(), key.end());
+    *n = cnt;
+    for (int i = 0; i < cnt && i < capacity; i++) {
+        tb_keypoint k = {(float)((key[i] >> 16) & 0xFFF), (float)((key[i] >> 28) & 0xFFF), 7.f, -1.f, (float)((int)(key[i] & 0xFF) - 1), 0, -1};
+        out[i] = k;
+    }
+    return cnt > capacity ? TB_E_CAPACITY : TB_OK;
+}
+
+extern "C" int tb_orb_extract_host(tb_frontend *fe, const uint8_t *const *levels, const size_t *host_strides, const float *sf,
+                                   int target, float initTh, float minTh, const tb_keypoint *exit_kps, int n_exit,
+                                   tb_keypoint *kps, uint8_t *desc, int capacity, int *n)
+{
+    if (!fe || !levels || !host_strides || !n) return TB_E_INVALID;
+    for (int l = 0; l < fe->L; l++) {
+        int rc = tb_frontend_upload_level(fe, 0, l, levels[l], host_strides[l]);
+        if (rc) return rc;
+    }
+    int rc = tb_frontend_extract(fe, 1, sf, target, initTh, minTh, exit_kps, n_exit);
+    if (rc) return rc;
+    return tb_frontend_get_results(fe, 0, kps, desc, capacity, n);
+}
+
+extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int32_t *q_frames, const int32_t *t_frames,
+                                        float ratio, float minTh, void *matches, int capacity, void *counts)
+{
+    if (!fe || n_pairs < 0 || !q_frames || !t_frames || !matches || !counts) return TB_E_INVALID;
+    for (int p = 0; p < n_pairs; p++)
+        if (q_frames[p] < 0 || q_frames[p] >= fe->B || t_frames[p] < 0 || t_frames[p] >= fe->B) return TB_E_INVALID;
+    return tb_match_bf_batched(fe->ctx, n_pairs, q_frames, t_frames, fe->desc, (size_t)fe->kp_cap * 32, fe->n_kp, fe->kp_cap,
+                               ratio, minTh, (tb_match *)matches, capacity, (int *)counts);
+}

@@ -1,0 +1,57 @@
+// kernels.cuh — argument structs and host launchers shared between the kernel files and frontend.cu.
+#pragma once
+#include "common.cuh"
+
+struct ResizeTab { int32_t ofs; int16_t c0, c1; };
+void tb_build_resize_tab(int sn, int dn, bool is_x, std::vector<ResizeTab> &tab, std::vector<int32_t> &ofs1);
+bool tb_resize_is_area2(int sw, int sh, int dw, int dh);
+int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
+                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames);
+struct FastArgs {
+    const uint8_t *img; int pitch; size_t frame_stride;
+    int w, h;
+    int nCols, nRows, wCell, hCell, maxBX, maxBY;
+    int G, tpitch, scw;
+    int initTh, minTh;
+    uint32_t *cand; int cand_cap;
+    int *n_cand; int n_cand_stride;
+    int *overflow;
+};
+int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem);
+struct OctArgs {
+    const uint32_t *cand; int cand_cap;
+    const int *n_cand; int n_stride;
+    uint16_t *nid;
+    int N;
+    int W, H;
+    int nIni; float hX;
+    int wCell, hCell;
+    const float2 *exit_xy; int n_exit;
+    int16_t *enid;
+    uint32_t *kept; int kept_cap;
+    int *n_kept;
+    int *overflow;
+    int node_cap;
+};
+size_t tb_octree_smem_bytes(int node_cap);
+int tb_launch_octree(tb_ctx *ctx, const OctArgs &a, int n_frames);
+int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames);
+struct DescLevel {
+    const uint8_t *raw, *blur;
+    int pitch; size_t frame_stride;
+    const uint32_t *kept; int kept_cap;
+    float sf; float size;
+};
+struct DescArgs {
+    DescLevel lv[TB_MAX_LEVELS];
+    int n_levels;
+    const int *n_kept;
+    tb_keypoint *kps; uint8_t *desc; int kp_cap;
+    int *n_kp;
+    int *overflow;
+};
+int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames);
+int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host,
+                        const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,
+                        float ratio, float minTh, tb_match *matches, int capacity, int *out_counts);
+

@@ -1,0 +1,554 @@
+// window.cu — K9/K10: search grid, windowed / projection-guided Hamming matching and the
+// rotation-histogram consistency filter.  Replaces, in the reference:
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/types/Frame.cpp:187-265 (+ :30-31)
+//   Matcher::searchByViolence                                     src/matchers/matcher.cpp:299-395
+//   Matcher::searchByProjection(F1,F2)                            src/matchers/matcher.cpp:405-531
+//   Matcher::searchByProjection(map,F1,r) + Frame::IsInFrustum    src/matchers/matcher.cpp:539-617, Frame.cpp:370-412
+//   rotation histogram + ComputeThreeMaxima                       src/matchers/matcher.cpp:359-393, :493-529, :810-851
+//   PinholeCamera::World2Cam / CameraModel::IsInFrame             src/camera/CameraModel.cpp:63-94, CameraModel.h:33-39
+//
+// Grid = CSR over the reference's 120x36 cells (cell (ix,iy) at ix*36+iy, items in insertion order),
+// so the candidates of one ix column and iy range are ONE contiguous item range, already in the
+// reference's traversal order.  One warp per query: lanes take consecutive candidates, keep their
+// two smallest (distance, traversal position) keys, and a shuffle tree merges the 32 pairs — this
+// reproduces "first strict minimum in traversal order" and the reference's second-best exactly.
+// All parity-critical float math uses explicit round-to-nearest intrinsics (no FMA contraction),
+// mirroring the reference's unoptimised build.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define GRID_COLS 120
+#define GRID_ROWS 36
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+
+struct GridDev {
+    const int *cell_start; // [GRID_CELLS+1]
+    const int *items;
+    const tb_keypoint *kps;
+    float wInv, hInv;      // mfGridElementWidthInv = 36/rows, mfGridElementHeightInv = 120/cols (sic, Frame.cpp:30-31)
+};
+
+// ---- grid build
+__global__ void grid_cell_ids(const tb_keypoint *kps, int n, float wInv, float hInv, int *cellid, int *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int px = (int)roundf(__fmul_rn(kps[i].x, wInv)), py = (int)roundf(__fmul_rn(kps[i].y, hInv)); // Frame.cpp:259-260
+    int c = -1;
+    if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) { c = px * GRID_ROWS + py; atomicAdd(&count[c], 1); }
+    cellid[i] = c;
+}
+__global__ void __launch_bounds__(1024) grid_scan(const int *count, int *cell_start)
+{
+    __shared__ int s[1024];
+    const int tid = threadIdx.x;
+    const int ipt = (GRID_CELLS + 1023) / 1024;
+    int b0 = min(tid * ipt, GRID_CELLS), b1 = min(b0 + ipt, GRID_CELLS);
+    int sum = 0;
+    for (int i = b0; i < b1; i++) sum += count[i];
+    s[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { int v = tid >= o ? s[tid - o] : 0; __syncthreads(); s[tid] += v; __syncthreads(); }
+    int run = s[tid] - sum;
+    for (int i = b0; i < b1; i++) { cell_start[i] = run; run += count[i]; }
+    if (tid == 1023) cell_start[GRID_CELLS] = s[1023];
+}
+__global__ void grid_fill(const int *cellid, int n, const int *count, const int *cell_start, int *items)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= GRID_CELLS || count[c] == 0) return;
+    int pos = cell_start[c];
+    for (int i = 0; i < n; i++) if (cellid[i] == c) items[pos++] = i; // insertion (index) order
+}
+
+// ---- candidate walk
+struct Top2 { uint32_t k1, k2; int i1, i2; }; // keys = dist<<20 | traversal position; 0xFFFFFFFF = none
+__device__ __forceinline__ void top2_push(Top2 &t, uint32_t key, int idx)
+{
+    if (key < t.k1) { t.k2 = t.k1; t.i2 = t.i1; t.k1 = key; t.i1 = idx; }
+    else if (key < t.k2) { t.k2 = key; t.i2 = idx; }
+}
+__device__ __forceinline__ Top2 top2_warp_merge(Top2 t)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        uint32_t ok1 = __shfl_xor_sync(0xffffffffu, t.k1, o), ok2 = __shfl_xor_sync(0xffffffffu, t.k2, o);
+        int oi1 = __shfl_xor_sync(0xffffffffu, t.i1, o), oi2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+        top2_push(t, ok1, oi1);
+        top2_push(t, ok2, oi2);
+    }
+    return t;
+}
+__device__ __forceinline__ int ham256_g(const uint32_t q[8], const uint8_t *d)
+{
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(d)), b = __ldg(reinterpret_cast<const uint4 *>(d) + 1);
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+// GetFeaturesInArea + distance scan for one warp. skip[j] != 0 excludes candidate j (may be null).
+// If out_idx != null the surviving candidate indices are also written in traversal order (lane-
+// cooperative, used by tb_features_in_area) and *out_n receives their number.
+__device__ Top2 window_scan(const GridDev &g, float x, float y, float r, int minLevel, int maxLevel,
+                            const uint32_t q[8], const uint8_t *desc, const uint8_t *skip, int *out_idx, int *out_n)
+{
+    const int lane = threadIdx.x & 31;
+    Top2 t = {0xFFFFFFFFu, 0xFFFFFFFFu, -1, -1};
+    int nout = 0;
+    const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(x, r), g.wInv)));
+    const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(x, r), g.wInv)));
+    const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(y, r), g.hInv)));
+    const int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), g.hInv)));
+    if (x0 >= GRID_COLS || x1 < 0 || y0 >= GRID_ROWS || y1 < 0) { if (out_n) *out_n = 0; return t; }
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    int tpos = 0;
+    for (int ix = x0; ix <= x1; ix++) {
+        const int s = g.cell_start[ix * GRID_ROWS + y0], e = g.cell_start[ix * GRID_ROWS + y1 + 1];
+        for (int k0 = s; k0 < e; k0 += 32) {
+            const int k = k0 + lane;
+            bool pass = false;
+            int j = -1;
+            if (k < e) {
+                j = g.items[k];
+                const tb_keypoint kp = g.kps[j];
+                pass = true;
+                if (check) {
+                    if (kp.octave < minLevel) pass = false;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) pass = false;
+                }
+                const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+                if (!(fabsf(dx) < r && fabsf(dy) < r)) pass = false;
+            }
+            if (out_idx) {
+                unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) out_idx[nout + __popc(bal & ((1u << lane) - 1))] = j;
+                nout += __popc(bal);
+            }
+            if (pass && desc && !(skip && skip[j])) {
+                const int d = ham256_g(q, desc + (size_t)32 * j);
+                top2_push(t, ((uint32_t)d << 20) | (uint32_t)(tpos + (k - k0)), j);
+            }
+            tpos += 32;
+        }
+    }
+    if (out_n) *out_n = nout;
+    return top2_warp_merge(t);
+}
+
+__device__ __forceinline__ void load_desc(uint32_t q[8], const uint8_t *d)
+{
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(d)), b = __ldg(reinterpret_cast<const uint4 *>(d) + 1);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+}
+
+// per-query result record
+struct QRes { int ok, q, t, dist, bin; };
+
+__device__ __forceinline__ int rot_bin(float a_from, float a_to, int histo)
+{
+    float rot = __fsub_rn(a_from, a_to);
+    if (rot < 0) rot = __fadd_rn(rot, 360.f);
+    const float factor = __fdiv_rn(1.f, (float)histo);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == histo) bin = 0;
+    return bin;
+}
+
+// searchByViolence inner loop: one warp per F1 keypoint
+__global__ void __launch_bounds__(256)
+violence_query(GridDev g2, const uint8_t *d2, const tb_keypoint *k1, const uint8_t *d1, int n1,
+               int min_level, int max_level, float search_r, tb_matcher_params p, QRes *res)
+{
+    const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i1 >= n1) return;
+    uint32_t q[8];
+    load_desc(q, d1 + (size_t)32 * i1);
+    const tb_keypoint kp = k1[i1];
+    Top2 t = window_scan(g2, kp.x, kp.y, search_r, min_level, max_level, q, d2, nullptr, nullptr, nullptr);
+    if ((threadIdx.x & 31) == 0) {
+        QRes r = {0, i1, -1, 0, 0};
+        if (t.i1 >= 0) {
+            const int bestDist = (int)(t.k1 >> 20);
+            const int bestDist2 = t.i2 >= 0 ? (int)(t.k2 >> 20) : 0x7fffffff;
+            if (bestDist <= p.TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, p.nRatio)) {
+                r.ok = 1; r.t = t.i1; r.dist = bestDist;
+                if (p.checkOrientation) r.bin = rot_bin(kp.angle, g2.kps[t.i1].angle, p.HISTO_LENGTH);
+            }
+        }
+        res[i1] = r;
+    }
+}
+
+// Eigen's fixed-size 3-term reduction order: x0 + (x1 + x2)  (see oracle/tb_oracle.c:dot3)
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return __fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2)));
+}
+struct Pose { float T[16]; };
+__device__ __forceinline__ void transform_pt(const Pose &P, const float *X, float *o)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        o[r] = __fadd_rn(dot3(P.T[4 * r], X[0], P.T[4 * r + 1], X[1], P.T[4 * r + 2], X[2]), P.T[4 * r + 3]);
+}
+__device__ __forceinline__ void world2cam(const tb_pinhole &c, const float *xyz, float &u, float &v)
+{
+    const float x = __fdiv_rn(xyz[0], xyz[2]), y = __fdiv_rn(xyz[1], xyz[2]);
+    if (!(fabs((double)c.d[0]) > 0.0000001)) {
+        u = __fadd_rn(__fmul_rn(c.fx, x), c.cx);
+        v = __fadd_rn(__fmul_rn(c.fy, y), c.cy);
+    } else {
+        const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), r4 = __fmul_rn(r2, r2), r6 = __fmul_rn(r4, r2);
+        const float a1 = __fmul_rn(__fmul_rn(2.f, x), y);
+        const float a2 = __fadd_rn(r2, __fmul_rn(__fmul_rn(2.f, x), x)), a3 = __fadd_rn(r2, __fmul_rn(__fmul_rn(2.f, y), y));
+        const float cdist = __fadd_rn(__fadd_rn(__fadd_rn(1.f, __fmul_rn(c.d[0], r2)), __fmul_rn(c.d[1], r4)), __fmul_rn(c.d[4], r6));
+        const float xd = __fadd_rn(__fadd_rn(__fmul_rn(x, cdist), __fmul_rn(c.d[2], a1)), __fmul_rn(c.d[3], a2));
+        const float yd = __fadd_rn(__fadd_rn(__fmul_rn(y, cdist), __fmul_rn(c.d[2], a3)), __fmul_rn(c.d[3], a1));
+        u = __fadd_rn(__fmul_rn(xd, c.fx), c.cx);
+        v = __fadd_rn(__fmul_rn(yd, c.fy), c.cy);
+    }
+}
+__device__ __forceinline__ bool is_in_frame(const tb_pinhole &c, float u, float v)
+{
+    const int iu = (int)u, iv = (int)v;
+    return iu >= 0 && iu < (int)((float)c.width * 1.f) && iv >= 0 && iv < (int)((float)c.height * 1.f);
+}
+
+// searchByProjection(F1,F2) inner loop: one warp per F2 keypoint carrying a map point
+struct SfTab { float sf[TB_MAX_LEVELS]; };
+__global__ void __launch_bounds__(256)
+projection_query(GridDev g1, const uint8_t *d1, const uint8_t *f1_matched, SfTab sf1, tb_pinhole cam, Pose T,
+                 const tb_keypoint *k2, int n2, const uint8_t *mp_valid, const float *mp_xyz, const uint8_t *mp_desc,
+                 tb_matcher_params p, QRes *res)
+{
+    const int i2 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i2 >= n2) return;
+    QRes r = {0, -1, i2, 0, 0};
+    bool go = mp_valid[i2] != 0;
+    float u = 0, v = 0;
+    if (go) {
+        float xc[3];
+        transform_pt(T, mp_xyz + 3 * (size_t)i2, xc);
+        const float invzc = __fdiv_rn(1.0f, xc[2]);
+        if (invzc < 0) go = false;
+        else {
+            world2cam(cam, xc, u, v);
+            if (!is_in_frame(cam, u, v)) go = false;
+        }
+    }
+    if (go) {
+        const tb_keypoint kp2 = k2[i2];
+        const int oct = kp2.octave;
+        const float radius = __fmul_rn(p.nRatio, sf1.sf[oct]);
+        uint32_t q[8];
+        load_desc(q, mp_desc + (size_t)32 * i2);
+        Top2 t = window_scan(g1, u, v, radius, oct - 1, oct + 1, q, d1, f1_matched, nullptr, nullptr);
+        if (t.i1 >= 0) {
+            const int bestDist = (int)(t.k1 >> 20);
+            if (bestDist <= p.TH_HIGH) { // bestDist starts at 256 in the reference: a candidate at 256 cannot win
+                if (bestDist < 256) {
+                    r.ok = 1; r.q = t.i1; r.dist = bestDist;
+                    if (p.checkOrientation) r.bin = rot_bin(kp2.angle, g1.kps[t.i1].angle, p.HISTO_LENGTH);
+                }
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0) res[i2] = r;
+}
+
+// searchByProjection(map,F1,radio) inner loop: one warp per map point
+__global__ void __launch_bounds__(256)
+projection_map_query(GridDev g1, const uint8_t *d1, const uint8_t *f1_matched, float sf0, tb_pinhole cam, Pose T,
+                     int n_mp, const uint8_t *mp_bad, const float *mp_xyz, const float *mp_normal, const uint8_t *mp_desc,
+                     tb_matcher_params p, float radio, QRes *res)
+{
+    const int im = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (im >= n_mp) return;
+    QRes r = {0, -1, im, 0, 0};
+    bool go = mp_bad[im] == 0;
+    float u = 0, v = 0, viewCos = 0;
+    if (go) {
+        const float *P = mp_xyz + 3 * (size_t)im;
+        float Pc[3];
+        transform_pt(T, P, Pc);
+        if (Pc[2] < 0.0f) go = false;
+        else {
+            world2cam(cam, Pc, u, v);
+            if (!is_in_frame(cam, u, v)) go = false;
+        }
+        if (go) {
+            float Ow[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Ow[c] = dot3(-T.T[0 + c], T.T[3], -T.T[4 + c], T.T[7], -T.T[8 + c], T.T[11]); // Frame.cpp:57
+            const float PO[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
+            const float dist3 = __fsqrt_rn(dot3(PO[0], PO[0], PO[1], PO[1], PO[2], PO[2]));
+            if (dist3 < 1.f || dist3 > 1000.f) go = false; // MapPoint.cpp:207-217
+            else {
+                const float *Pn = mp_normal + 3 * (size_t)im;
+                viewCos = __fdiv_rn(dot3(PO[0], Pn[0], PO[1], Pn[1], PO[2], Pn[2]), dist3);
+                if (viewCos < 0.5f) go = false;
+            }
+        }
+    }
+    if (go) {
+        float rr = 4.f;
+        if ((double)viewCos > 0.998) rr = 2.5f;
+        if ((double)p.nRatio != 1.0) rr = __fmul_rn(rr, p.nRatio);
+        uint32_t q[8];
+        load_desc(q, mp_desc + (size_t)32 * im);
+        Top2 t = window_scan(g1, u, v, __fmul_rn(rr, sf0), -1, 0, q, d1, f1_matched, nullptr, nullptr);
+        if (t.i1 >= 0) {
+            const int bestDist = (int)(t.k1 >> 20);
+            if (bestDist < 256 && bestDist <= p.TH_HIGH) {
+                const int bestLevel = g1.kps[t.i1].octave;
+                int bestLevel2 = -1, bestDist2 = 256;
+                if (t.i2 >= 0 && (int)(t.k2 >> 20) < 256) { bestLevel2 = g1.kps[t.i2].octave; bestDist2 = (int)(t.k2 >> 20); }
+                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(radio, (float)bestDist2))) {
+                    r.ok = 1; r.q = t.i1; r.dist = bestDist;
+                }
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0) res[im] = r;
+}
+
+__global__ void __launch_bounds__(32)
+area_query(GridDev g, float x, float y, float r, int minLevel, int maxLevel, int *out, int *out_n)
+{
+    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 0;
+    window_scan(g, x, y, r, minLevel, maxLevel, q, nullptr, nullptr, out, &n);
+    if (threadIdx.x == 0) *out_n = n;
+}
+
+// ---- emission: ordered compaction of per-query results, optional rotation-histogram regrouping.
+__device__ int scan256w(int *a, int n)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int ipt = (n + 255) / 256;
+    const int b0 = min(tid * ipt, n), b1 = min(b0 + ipt, n);
+    int sum = 0;
+    for (int i = b0; i < b1; i++) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    if (tid == 0) { int r = 0; for (int w = 0; w < 8; w++) { int v = s_warp[w]; s_warp[w] = r; r += v; } s_total = r; }
+    __syncthreads();
+    int run = s_warp[tid >> 5] + inc - sum;
+    for (int i = b0; i < b1; i++) { int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+    return s_total;
+}
+
+// One CTA. With check_orientation: output = raw matches of the (up to) three maximal bins,
+// grouped by bin ascending, raw order inside a bin (matcher.cpp:377-392). Else raw order.
+__global__ void __launch_bounds__(256)
+emit_matches(const QRes *res, int n, int check_orientation, int histo, tb_match *out, int capacity, int *out_n)
+{
+    __shared__ int s_hist[256];
+    __shared__ int s_sel[3], s_nsel;
+    __shared__ int s_chunk[2048];
+    __shared__ int s_run;
+    const int tid = threadIdx.x;
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    if (check_orientation) {
+        for (int i = tid; i < n; i += 256) if (res[i].ok) atomicAdd(&s_hist[res[i].bin], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0; // ComputeThreeMaxima :810-851
+            for (int i = 0; i < histo; i++) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            int ns = 0;
+            for (int b = 0; b < histo; b++) if (b == ind1 || b == ind2 || b == ind3) s_sel[ns++] = b;
+            s_nsel = ns;
+        }
+    } else if (tid == 0) { s_nsel = 1; s_sel[0] = -1; }
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int sidx = 0; sidx < s_nsel; sidx++) {
+        const int bsel = s_sel[sidx];
+        for (int base = 0; base < n; base += 2048) {
+            const int m = min(2048, n - base);
+            for (int i = tid; i < m; i += 256) {
+                const QRes r = res[base + i];
+                s_chunk[i] = (r.ok && (bsel < 0 || r.bin == bsel)) ? 1 : 0;
+            }
+            __syncthreads();
+            // remember flags before the scan overwrites them
+            int mine[8]; int nm = 0;
+            for (int i = tid; i < m; i += 256) mine[nm++] = s_chunk[i];
+            __syncthreads();
+            const int tot = scan256w(s_chunk, m);
+            const int run = s_run;
+            nm = 0;
+            for (int i = tid; i < m; i += 256) {
+                if (mine[nm++]) {
+                    const int pos = run + s_chunk[i];
+                    if (pos < capacity) {
+                        const QRes r = res[base + i];
+                        tb_match mt = {r.q, r.t, 0, (float)r.dist};
+                        out[pos] = mt;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_run = run + tot;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) *out_n = s_run;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct DevBuf {
+    std::vector<void *> ptrs;
+    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> T *alloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, (n ? n : 1) * sizeof(T) + 64) != cudaSuccess) return nullptr; ptrs.push_back(p); return (T *)p; }
+    template <typename T> T *upload(const T *h, size_t n, cudaStream_t s)
+    {
+        T *d = alloc<T>(n);
+        if (d && n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
+        return d;
+    }
+};
+
+static int build_grid(tb_ctx *ctx, DevBuf &buf, const tb_keypoint *d_kps, int n, int cols, int rows, GridDev &g)
+{
+    int *cellid = buf.alloc<int>(n), *count = buf.alloc<int>(GRID_CELLS), *start = buf.alloc<int>(GRID_CELLS + 1), *items = buf.alloc<int>(n);
+    if (!cellid || !count || !start || !items) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    volatile float hInv = (float)GRID_COLS / (float)cols, wInv = (float)GRID_ROWS / (float)rows; // Frame.cpp:30-31
+    g.wInv = wInv; g.hInv = hInv; g.kps = d_kps; g.cell_start = start; g.items = items;
+    TB_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * GRID_CELLS, ctx->stream));
+    if (n > 0) { grid_cell_ids<<<div_up(n, 256), 256, 0, ctx->stream>>>(d_kps, n, g.wInv, g.hInv, cellid, count); TB_LAUNCH_CHECK(ctx); }
+    grid_scan<<<1, 1024, 0, ctx->stream>>>(count, start); TB_LAUNCH_CHECK(ctx);
+    if (n > 0) { grid_fill<<<div_up(GRID_CELLS, 128), 128, 0, ctx->stream>>>(cellid, n, count, start, items); TB_LAUNCH_CHECK(ctx); }
+    return TB_OK;
+}
+
+static int emit_and_download(tb_ctx *ctx, DevBuf &buf, const QRes *res, int nq, int check, int histo, tb_match *out, int capacity, int *n)
+{
+    if (histo > 256 || histo < 1) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    tb_match *d_out = buf.alloc<tb_match>(nq);
+    int *d_n = buf.alloc<int>(1);
+    if (!d_out || !d_n) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    emit_matches<<<1, 256, 0, ctx->stream>>>(res, nq, check, histo, d_out, nq, d_n);
+    TB_LAUNCH_CHECK(ctx);
+    int cnt = 0;
+    TB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = cnt;
+    int m = cnt < capacity ? cnt : capacity;
+    if (m > 0) TB_CUDA(ctx, cudaMemcpy(out, d_out, sizeof(tb_match) * m, cudaMemcpyDeviceToHost));
+    return cnt > capacity ? tb_fail(ctx, TB_E_CAPACITY, "match output capacity too small") : TB_OK;
+}
+
+extern "C" int tb_features_in_area(tb_ctx *ctx, const tb_keypoint *kps, int n, int cols, int rows, float x, float y, float r,
+                                   int minLevel, int maxLevel, int32_t *out, int capacity, int *n_out)
+{
+    if (!ctx || n < 0 || !n_out || cols <= 0 || rows <= 0) return TB_E_INVALID;
+    DevBuf buf;
+    tb_keypoint *dk = buf.upload(kps, n, ctx->stream);
+    int *d_out = buf.alloc<int>(n + 32), *d_n = buf.alloc<int>(1);
+    if (!dk || !d_out || !d_n) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    GridDev g;
+    int rc = build_grid(ctx, buf, dk, n, cols, rows, g);
+    if (rc) return rc;
+    area_query<<<1, 32, 0, ctx->stream>>>(g, x, y, r, minLevel, maxLevel, d_out, d_n);
+    TB_LAUNCH_CHECK(ctx);
+    int cnt = 0;
+    TB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = cnt;
+    int m = cnt < capacity ? cnt : capacity;
+    if (m > 0) TB_CUDA(ctx, cudaMemcpy(out, d_out, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    return cnt > capacity ? TB_E_CAPACITY : TB_OK;
+}
+
+extern "C" int tb_search_by_violence(tb_ctx *ctx, const tb_matcher_params *p, const tb_keypoint *k1, const uint8_t *d1, int n1,
+                                     const tb_keypoint *k2, const uint8_t *d2, int n2, int cols2, int rows2,
+                                     int min_level, int max_level, float search_r, tb_match *out, int capacity, int *n)
+{
+    if (!ctx || !p || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
+    *n = 0;
+    if (n1 == 0) return TB_OK;
+    DevBuf buf;
+    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream), *dd2 = buf.upload(d2, (size_t)32 * n2, ctx->stream);
+    QRes *res = buf.alloc<QRes>(n1);
+    if (!dk1 || !dk2 || !dd1 || !dd2 || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    GridDev g;
+    int rc = build_grid(ctx, buf, dk2, n2, cols2, rows2, g);
+    if (rc) return rc;
+    violence_query<<<div_up(n1, 8), 256, 0, ctx->stream>>>(g, dd2, dk1, dd1, n1, min_level, max_level, search_r, *p, res);
+    TB_LAUNCH_CHECK(ctx);
+    return emit_and_download(ctx, buf, res, n1, p->checkOrientation, p->HISTO_LENGTH, out, capacity, n);
+}
+
+extern "C" int tb_search_by_projection(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, const float *Tcw1,
+                                       const tb_keypoint *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                                       const float *sf1, int n_levels1, int cols1, int rows1,
+                                       const tb_keypoint *k2, int n2, const uint8_t *mp_valid, const float *mp_xyz,
+                                       const uint8_t *mp_desc, tb_match *out, int capacity, int *n)
+{
+    if (!ctx || !p || !cam || !Tcw1 || !sf1 || n1 < 0 || n2 < 0 || !n || n_levels1 <= 0 || n_levels1 > TB_MAX_LEVELS) return TB_E_INVALID;
+    *n = 0;
+    if (n2 == 0) return TB_OK;
+    for (int i = 0; i < n2; i++) if (k2[i].octave < 0 || k2[i].octave >= n_levels1) return tb_fail(ctx, TB_E_INVALID, "octave outside the scale table");
+    DevBuf buf;
+    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream);
+    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1, ctx->stream) : nullptr;
+    uint8_t *dval = buf.upload(mp_valid, (size_t)n2, ctx->stream);
+    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n2, ctx->stream);
+    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n2, ctx->stream);
+    QRes *res = buf.alloc<QRes>(n2);
+    if (!dk1 || !dk2 || !dd1 || !dval || !dxyz || !dmd || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    GridDev g;
+    int rc = build_grid(ctx, buf, dk1, n1, cols1, rows1, g);
+    if (rc) return rc;
+    SfTab sf; memset(&sf, 0, sizeof sf);
+    for (int i = 0; i < n_levels1; i++) sf.sf[i] = sf1[i];
+    Pose T; memcpy(T.T, Tcw1, sizeof T.T);
+    projection_query<<<div_up(n2, 8), 256, 0, ctx->stream>>>(g, dd1, dfm, sf, *cam, T, dk2, n2, dval, dxyz, dmd, *p, res);
+    TB_LAUNCH_CHECK(ctx);
+    return emit_and_download(ctx, buf, res, n2, p->checkOrientation, p->HISTO_LENGTH, out, capacity, n);
+}
+
+extern "C" int tb_search_by_projection_map(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, const float *Tcw1,
+                                           const tb_keypoint *k1, const uint8_t *d1, int n1, const uint8_t *f1_matched,
+                                           const float *sf1, int cols1, int rows1,
+                                           int n_mp, const uint8_t *mp_bad, const float *mp_xyz, const float *mp_normal,
+                                           const uint8_t *mp_desc, float radio, tb_match *out, int capacity, int *n)
+{
+    if (!ctx || !p || !cam || !Tcw1 || !sf1 || n1 < 0 || n_mp < 0 || !n) return TB_E_INVALID;
+    *n = 0;
+    if (n_mp == 0) return TB_OK;
+    DevBuf buf;
+    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream);
+    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1, ctx->stream) : nullptr;
+    uint8_t *dbad = buf.upload(mp_bad, (size_t)n_mp, ctx->stream);
+    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n_mp, ctx->stream), *dnrm = buf.upload(mp_normal, (size_t)3 * n_mp, ctx->stream);
+    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n_mp, ctx->stream);
+    QRes *res = buf.alloc<QRes>(n_mp);
+    if (!dk1 || !dd1 || !dbad || !dxyz || !dnrm || !dmd || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    GridDev g;
+    int rc = build_grid(ctx, buf, dk1, n1, cols1, rows1, g);
+    if (rc) return rc;
+    Pose T; memcpy(T.T, Tcw1, sizeof T.T);
+    projection_map_query<<<div_up(n_mp, 8), 256, 0, ctx->stream>>>(g, dd1, dfm, sf1[0], *cam, T, n_mp, dbad, dxyz, dnrm, dmd, *p, radio, res);
+    TB_LAUNCH_CHECK(ctx);
+    // no orientation check in this overload (matcher.cpp:539-617)
+    return emit_and_download(ctx, buf, res, n_mp, 0, p->HISTO_LENGTH > 0 ? p->HISTO_LENGTH : 1, out, capacity, n);
+}
