@@ -77,6 +77,10 @@ const char *tb_last_error(const tb_ctx *ctx);
 const char *tb_version(void);
 /* number of kernel launches issued through this ctx since creation (bench.py's gpu_launches) */
 int64_t tb_launch_count(const tb_ctx *ctx);
+/* Per-kernel timing for the roofline report: when enabled every kernel launch is bracketed by CUDA
+ * events on the ctx stream; tb_profile_report synchronises and writes "name launches total_ms" lines. */
+int tb_profile_enable(tb_ctx *ctx, int on);
+int tb_profile_report(tb_ctx *ctx, char *buf, size_t cap);
 
 /* ------------------------------------------------------------------ pyramid geometry (host, pure)
  * Frame::Frame scale tables (src/types/Frame.cpp:18-29) and the level sizes of

@@ -126,7 +126,16 @@ int tbo_fast9(const u8 *img, int stride, int w, int h, int T, int nonmax, tbo_kp
     u8 *corner = (u8 *)calloc((size_t)w * h, 1);
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
-            int m = fast9_m(img + (size_t)y * stride + x, stride);
+            const u8 *p = img + (size_t)y * stride + x;
+            /* exact early reject (as OpenCV's scalar path does with its threshold table): every
+             * 9-arc contains one pixel of each antipodal pair, so a corner needs one pixel of
+             * (0,8) and one of (4,12) outside [v-T, v+T]. */
+            int v = p[0], lo = v - T, hi = v + T;
+            int a0 = p[3 * stride], a8 = p[-3 * stride];
+            if (a0 >= lo && a0 <= hi && a8 >= lo && a8 <= hi) continue;
+            int a4 = p[3], a12 = p[-3];
+            if (a4 >= lo && a4 <= hi && a12 >= lo && a12 <= hi) continue;
+            int m = fast9_m(p, stride);
             if (m > T) { score[(size_t)y * w + x] = m - 1; corner[(size_t)y * w + x] = 1; }
         }
     int n = 0;
@@ -173,18 +182,24 @@ void tbo_gauss7x7(const u8 *src, int w, int h, int sstride, u8 *dst, int dstride
 {
     static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
     uint16_t *tmp = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)w * h);
-    for (int y = 0; y < h; y++)
+    for (int y = 0; y < h; y++) {
+        const u8 *r = src + (size_t)y * sstride;
         for (int x = 0; x < w; x++) {
             int s = 0;
-            for (int i = 0; i < 7; i++) s += K[i] * src[(size_t)y * sstride + reflect101(x + i - 3, w)];
+            if (x >= 3 && x + 3 < w) for (int i = 0; i < 7; i++) s += K[i] * r[x + i - 3];
+            else for (int i = 0; i < 7; i++) s += K[i] * r[reflect101(x + i - 3, w)];
             tmp[(size_t)y * w + x] = (uint16_t)s;
         }
-    for (int y = 0; y < h; y++)
+    }
+    for (int y = 0; y < h; y++) {
+        const uint16_t *rows[7];
+        for (int j = 0; j < 7; j++) rows[j] = tmp + (size_t)reflect101(y + j - 3, h) * w;
         for (int x = 0; x < w; x++) {
             uint32_t s = 0;
-            for (int j = 0; j < 7; j++) s += (uint32_t)K[j] * tmp[(size_t)reflect101(y + j - 3, h) * w + x];
+            for (int j = 0; j < 7; j++) s += (uint32_t)K[j] * rows[j][x];
             dst[(size_t)y * dstride + x] = (u8)((s + 32768u) >> 16);
         }
+    }
     free(tmp);
 }
 

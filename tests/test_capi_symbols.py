@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/tb_capi.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from .conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'tb_capi.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(tb_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol(tb):
+    L = tb.capi.lib()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(tb.capi.EXPORTS) == names
+
+
+def test_no_cpu_fallback_without_cuda(tb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    h = ctypes.c_void_p()
+    rc = tb.capi.lib().tb_ctx_create(0, None, ctypes.byref(h))
+    assert rc == tb.capi.TB_E_CUDA and not h.value
+    with pytest.raises(tb.TbError):
+        tb.Context(0)
+
+
+def test_host_geometry_matches_oracle(tb, oracle):
+    for (w, h, nl, sc) in ((1241, 376, 8, 1 / 1.2), (1920, 1080, 8, 1 / 1.2), (3840, 2160, 8, 1 / 1.2), (1241, 376, 5, 0.8), (752, 480, 5, 0.6)):
+        sf, lw, lh = tb.pyramid_geometry(w, h, nl, sc)
+        sfo = oracle.scale_factors(nl, sc)
+        assert np.array_equal(sf, sfo)
+        assert list(zip(lw.tolist(), lh.tolist())) == oracle.level_sizes(w, h, sfo)
+
+
+def test_three_maxima_matches_oracle(tb, oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        hs = rng.integers(0, 12, 30).astype(np.int32)
+        a, b, c = ctypes.c_int(-1), ctypes.c_int(-1), ctypes.c_int(-1)
+        tb.capi.lib().tb_three_maxima(hs.ctypes.data_as(ctypes.c_void_p), 30, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        assert (a.value, b.value, c.value) == oracle.three_maxima(hs)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'trackingbench_slam_b200')
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, f)).read()
+                assert 'import oracle' not in txt and 'tb_oracle.h' not in txt and 'libtb_oracle' not in txt, f
+    for f in os.listdir(os.path.join(ROOT, 'include')):
+        assert 'tb_oracle' not in open(os.path.join(ROOT, 'include', f)).read()

@@ -1,0 +1,164 @@
+"""GPU parity tests (through the C ABI): pyramid, FAST candidates, blur, octree, orientation,
+descriptors vs the oracle and the committed golden vectors.  Bit-exact for pixels, coordinates,
+octaves, responses and descriptors; angles are compared as float32 bit patterns too (the CUDA
+fastAtan2 follows OpenCV's float polynomial without FMA) — see DESIGN.md for the sin/cos note."""
+import os
+
+import numpy as np
+import pytest
+
+from .conftest import GOLDEN, PARAM_SETS, kp_bytes_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _frontend(tb, ctx, img_shape, nl, sc, batch, target):
+    sf, lw, lh = tb.pyramid_geometry(img_shape[1], img_shape[0], nl, sc)
+    return tb.Frontend(ctx, lw, lh, max_batch=batch, max_target=target), sf
+
+
+def _report_desc_flips(dg, do):
+    rows = int((dg != do).any(1).sum())
+    return rows, rows / max(len(do), 1)
+
+
+@pytest.mark.parametrize('pname', list(PARAM_SETS))
+@pytest.mark.parametrize('iname', ['left', 'right'])
+def test_extract_matches_golden_and_oracle(tb, ctx, oracle, images, iname, pname):
+    nl, sc, tgt, a, b = PARAM_SETS[pname]
+    img = images[iname]
+    g = np.load(os.path.join(GOLDEN, 'extract_%s_%s.npz' % (iname, pname)))
+    fe, sf = _frontend(tb, ctx, img.shape, nl, sc, 1, tgt)
+    try:
+        fe.upload_frames(0, img[None])
+        fe.build_pyramid(1)
+        lv, sfo = oracle.pyramid(img, nl, sc)
+        assert np.array_equal(sf, sfo)
+        for l in range(nl):
+            assert np.array_equal(fe.download_level(0, l), lv[l]), 'pyramid level %d' % l
+        fe.extract(1, sf, tgt, a, b)
+        for l in range(nl):
+            co, cg = oracle.cell_candidates(lv[l], a, b), fe.get_candidates(0, l)
+            assert len(co) == len(cg) and np.array_equal(co['x'], cg['x']) and np.array_equal(co['y'], cg['y']) \
+                and np.array_equal(co['response'], cg['response']), 'FAST candidates level %d' % l
+            assert np.array_equal(fe.download_level(0, l, blurred=True), oracle.gauss7x7(lv[l])), 'blur level %d' % l
+        k, d = fe.get_results(0)
+        ko, do, npl = oracle.orb_extract(lv, sf, tgt, a, b)
+        assert np.array_equal(fe.get_level_counts(0), npl)
+        assert kp_bytes_equal(k, ko)
+        assert kp_bytes_equal(k, g['kps'])                      # = the reference's own code (oracle/_ref)
+        rows, frac = _report_desc_flips(d, g['desc'])
+        assert rows == 0, 'descriptor rows differing: %d (%.4f%%)' % (rows, 100 * frac)
+    finally:
+        fe.close()
+
+
+def test_orb_extract_host_entry_point(tb, ctx, oracle, images):
+    """tb_orb_extract_host = what the C++ facade ORBExtractor::operator() calls (pyramid given by the caller)."""
+    nl, sc, tgt, a, b = PARAM_SETS['A1000']
+    lv, sf = oracle.pyramid(images['left'], nl, sc)
+    fe = tb.Frontend(ctx, [l.shape[1] for l in lv], [l.shape[0] for l in lv], 1, tgt)
+    try:
+        k, d = fe.orb_extract_host(lv, sf, tgt, a, b)
+        ko, do, _ = oracle.orb_extract(lv, sf, tgt, a, b)
+        assert kp_bytes_equal(k, ko) and np.array_equal(d, do)
+        # AddPoints (test_frame.cpp:36 flow): every 5th keypoint is "existing"
+        ex = ko[::5]
+        k2, d2 = fe.orb_extract_host(lv, sf, tgt, a, b, exit_kps=ex)
+        ko2, do2, _ = oracle.orb_extract(lv, sf, tgt, a, b, exit_kps=ex, budget=oracle.orb_budget(nl, sf[1], tgt))
+        assert len(ko2) < len(ko)
+        assert kp_bytes_equal(k2, ko2) and np.array_equal(d2, do2)
+    finally:
+        fe.close()
+
+
+def test_batch_slots_and_ragged_batch(tb, ctx, oracle, images):
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    L, R = images['left'], images['right']
+    fe, sf = _frontend(tb, ctx, L.shape, nl, sc, 5, tgt)
+    try:
+        fe.upload_frames(0, np.stack([L, R, L]))          # 3 of 5 slots used
+        fe.build_pyramid(3)
+        fe.extract(3, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(3)
+        ref = {}
+        for name, img in (('L', L), ('R', R)):
+            lv, _ = oracle.pyramid(img, nl, sc)
+            ref[name] = oracle.orb_extract(lv, sf, tgt, a, b)
+        for f, name in enumerate('LRL'):
+            ko, do, _ = ref[name]
+            assert counts[f] == len(ko)
+            assert kp_bytes_equal(kps[f, :counts[f]], ko) and np.array_equal(desc[f, :counts[f]], do)
+        # idempotence: running again gives the same bytes
+        fe.extract(3, sf, tgt, a, b)
+        kps2, desc2, counts2 = fe.get_results_batch(3)
+        assert np.array_equal(counts, counts2) and kps2.tobytes() == kps.tobytes() and np.array_equal(desc, desc2)
+    finally:
+        fe.close()
+
+
+def test_synthetic_1080p_frame(tb, ctx, oracle):
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = PARAM_SETS['B2000']
+    img = synth_frame(3, 1920, 1080)
+    fe, sf = _frontend(tb, ctx, img.shape, nl, sc, 1, tgt)
+    try:
+        fe.upload_frames(0, img[None])
+        fe.build_pyramid(1)
+        fe.extract(1, sf, tgt, a, b)
+        k, d = fe.get_results(0)
+        lv, _ = oracle.pyramid(img, nl, sc)
+        for l in range(nl):
+            assert np.array_equal(fe.download_level(0, l), lv[l])
+        ko, do, _ = oracle.orb_extract(lv, sf, tgt, a, b)
+        assert kp_bytes_equal(k, ko)
+        rows, frac = _report_desc_flips(d, do)
+        assert frac < 0.001, 'descriptor flips %d' % rows   # north_star bound; observed 0
+        assert rows == 0
+    finally:
+        fe.close()
+
+
+@pytest.mark.parametrize('shape', [(40, 50), (70, 70), (97, 161), (376, 1241)])
+def test_edge_shapes_and_flat_images(tb, ctx, oracle, shape):
+    rng = np.random.default_rng(shape[0])
+    for img in (rng.integers(0, 256, shape, dtype=np.uint8), np.full(shape, 128, np.uint8)):
+        nl, sc, tgt, a, b = 3, 0.8, 300, 20.0, 7.0
+        fe, sf = _frontend(tb, ctx, img.shape, nl, sc, 1, tgt)
+        try:
+            fe.upload_frames(0, img[None])
+            fe.build_pyramid(1)
+            fe.extract(1, sf, tgt, a, b)
+            k, d = fe.get_results(0)
+            lv, _ = oracle.pyramid(img, nl, sc)
+            ko, do, _ = oracle.orb_extract(lv, sf, tgt, a, b)
+            assert kp_bytes_equal(k, ko) and np.array_equal(d, do)
+        finally:
+            fe.close()
+
+
+def test_pyramid_exact_half_scale(tb, ctx, oracle):
+    """Frame(...,4,0.5) (test_projection.cpp:723): OpenCV switches to INTER_AREA on exact 2x."""
+    img = np.random.default_rng(11).integers(0, 256, (480, 640), dtype=np.uint8)
+    fe, sf = _frontend(tb, ctx, img.shape, 4, 0.5, 1, 100)
+    try:
+        fe.upload_frames(0, img[None])
+        fe.build_pyramid(1)
+        lv, _ = oracle.pyramid(img, 4, 0.5)
+        for l in range(4):
+            assert np.array_equal(fe.download_level(0, l), lv[l])
+    finally:
+        fe.close()
+
+
+def test_invalid_arguments_fail_loudly(tb, ctx):
+    with pytest.raises(tb.TbError):
+        tb.Frontend(ctx, [5000], [100], 1, 100)      # above the 12-bit coordinate packing
+    fe = tb.Frontend(ctx, [200, 160], [100, 80], 1, 100)
+    try:
+        with pytest.raises(tb.TbError):
+            fe.extract(1, np.array([1, 0.8], np.float32), 500, 20, 7)   # target > max_target
+        with pytest.raises(tb.TbError):
+            fe.extract(1, np.array([1, 0.8], np.float32), 50, 20, 7, exit_kps=np.zeros(1, tb.KP_DTYPE))  # AddPoints before operator()
+    finally:
+        fe.close()

@@ -21,6 +21,7 @@ TB_MAX_LEVELS = 16
 # every symbol include/tb_capi.h declares (tests check that the library exports all of them)
 EXPORTS = [
     'tb_ctx_create', 'tb_ctx_destroy', 'tb_sync', 'tb_last_error', 'tb_version', 'tb_launch_count',
+    'tb_profile_enable', 'tb_profile_report',
     'tb_pyramid_geometry',
     'tb_frontend_create', 'tb_frontend_destroy', 'tb_frontend_kp_capacity', 'tb_frontend_level_layout',
     'tb_frontend_upload_level', 'tb_frontend_download_level', 'tb_frontend_upload_frames',
@@ -104,6 +105,19 @@ class Context:
 
     def launch_count(self):
         return lib().tb_launch_count(self.h)
+
+    def profile_enable(self, on=True):
+        self.check(lib().tb_profile_enable(self.h, int(on)))
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since the last report."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(lib().tb_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self.h:

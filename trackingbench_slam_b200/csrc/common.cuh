@@ -20,6 +20,24 @@ struct tb_ctx {
     int64_t launches = 0;
     std::string err;
     struct MatchWs *mws = nullptr;   // lazily grown matching workspace (match.cu)
+    // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
+    bool profiling = false;
+    struct ProfEvt { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfEvt> prof;
+};
+// RAII: records an event pair around the launches issued in its scope when profiling is on.
+struct ProfScope {
+    tb_ctx *c; int idx;
+    ProfScope(tb_ctx *ctx, const char *name) : c(ctx), idx(-1)
+    {
+        if (!c->profiling) return;
+        tb_ctx::ProfEvt e; e.name = name;
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, c->stream);
+        idx = (int)c->prof.size();
+        c->prof.push_back(e);
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream); }
 };
 void tb_match_ws_free(tb_ctx *ctx);
 

@@ -92,6 +92,7 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
 
 int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
 {
+    ProfScope prof__(ctx, "gauss7x7_u8");
     dim3 grid(div_up(w, GB_TW), div_up(h, GB_TH), n_frames);
     gauss7x7_u8<<<grid, 256, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
     TB_LAUNCH_CHECK(ctx);
@@ -214,6 +215,7 @@ orb_describe(DescArgs a)
 
 int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames)
 {
+    ProfScope prof__(ctx, "orb_describe");
     dim3 grid(div_up(max_kept_per_level, 8), a.n_levels, n_frames);
     orb_describe<<<grid, 256, 0, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);

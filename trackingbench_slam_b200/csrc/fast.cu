@@ -226,6 +226,7 @@ int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, i
         cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
+    ProfScope prof__(ctx, "fast9_cells");
     dim3 grid(div_up(nColsRun, a.G), nRowsRun, n_frames);
     fast9_cells<<<grid, 256, smem, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);

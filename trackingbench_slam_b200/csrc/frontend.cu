@@ -46,6 +46,35 @@ extern "C" int tb_sync(tb_ctx *ctx)
 extern "C" const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int64_t tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int tb_profile_enable(tb_ctx *ctx, int on)
+{
+    if (!ctx) return TB_E_INVALID;
+    ctx->profiling = on != 0;
+    return TB_OK;
+}
+// Synchronises, then writes one line per kernel name: "name launches total_ms\n"; clears the log.
+extern "C" int tb_profile_report(tb_ctx *ctx, char *buf, size_t cap)
+{
+    if (!ctx || !buf || cap == 0) return TB_E_INVALID;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names; std::vector<int> cnt; std::vector<double> ms;
+    for (auto &e : ctx->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+        size_t k = 0;
+        for (; k < names.size(); k++) if (names[k] == e.name) break;
+        if (k == names.size()) { names.push_back(e.name); cnt.push_back(0); ms.push_back(0); }
+        cnt[k]++; ms[k] += t;
+    }
+    ctx->prof.clear();
+    std::string out;
+    char line[256];
+    for (size_t k = 0; k < names.size(); k++) { snprintf(line, sizeof line, "%s %d %.6f\n", names[k].c_str(), cnt[k], ms[k]); out += line; }
+    snprintf(buf, cap, "%s", out.c_str());
+    return TB_OK;
+}
+
 // Frame::Frame scale tables + ComputePyramid sizes (reference src/types/Frame.cpp:18-29, :424)
 extern "C" int tb_pyramid_geometry(int width, int height, int n_levels, float scale, float *sf, int32_t *lw, int32_t *lh)
 {

@@ -304,8 +304,12 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
     build_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w.pairs, n_pairs, w.frames, w.frames + n_pairs, desc, frame_stride, counts);
     TB_LAUNCH_CHECK(ctx);
     dim3 grid(div_up(kp_cap, KNN_THREADS), 2 * n_pairs);
-    hamming_knn<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, kp_cap, w.best_idx, w.best_dist, nullptr);
+    {
+        ProfScope prof__(ctx, "hamming_knn");
+        hamming_knn<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, kp_cap, w.best_idx, w.best_dist, nullptr);
+    }
     TB_LAUNCH_CHECK(ctx);
+    ProfScope prof2__(ctx, "bf_cross_filter");
     bf_cross_filter<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, n_pairs, kp_cap, w.best_idx, w.best_dist, w.scratch, 1, ratio, minTh,
                                                       matches, capacity, out_counts);
     TB_LAUNCH_CHECK(ctx);

@@ -367,6 +367,7 @@ int tb_launch_octree(tb_ctx *ctx, const OctArgs &a, int n_frames)
         cudaFuncSetAttribute(octree_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
+    ProfScope prof__(ctx, "octree_distribute");
     octree_distribute<<<n_frames, OCT_THREADS, smem, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;

@@ -99,6 +99,7 @@ pyr_resize_area2_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
                      size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames)
 {
+    ProfScope prof__(ctx, "pyr_resize");
     if (area2) {
         dim3 grid(div_up(dw, 64), div_up(dh, 4), n_frames), block(64, 4);
         pyr_resize_area2_u8<<<grid, block, 0, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh);
