@@ -12,10 +12,10 @@
 //  * Cell ROIs are [ini, ini+cell+6) with a 3-px untested border, so cell INTERIORS tile the level
 //    exactly with period (wCell, hCell); a cell is self-contained: tile = interior + 3-px ring halo.
 //  * A cell uses initTh if any NMS survivor has m > initTh, else minTh.
-// One CTA handles FAST_G consecutive cells of one cell row: the u8 tile (+halo) is staged once in
-// shared memory with 4-byte coalesced loads; corners are compacted to a shared work list so the
-// expensive score runs on dense lanes; survivors are appended to the (frame, level) candidate
-// array with one global atomic per CTA.  Candidate ORDER in memory is arbitrary: every consumer
+// One CTA handles G consecutive cells of one cell row: the u8 tile (+halo) is staged once in
+// shared memory with 8-byte coalesced loads; a byte-SIMD prefilter and two exact tests thin the
+// pixels through compacted shared work lists so every expensive stage runs on dense lanes;
+// survivors are appended to the (frame, level) candidate array with one global atomic per CTA.  Candidate ORDER in memory is arbitrary: every consumer
 // derives the reference's order (cell row, cell col, y, x) from the coordinates themselves.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -24,10 +24,8 @@
 __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3i(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-// ring offsets (dx,dy) k = 0..15, same order as OpenCV's makeOffsets(pixel, step, 16)
-__device__ __constant__ int8_t c_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-__device__ __constant__ int8_t c_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-
+// ring pixel k = 0..15 at (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+// (same order as OpenCV's makeOffsets(pixel, step, 16))
 #define RING_LOAD(p, tp) { \
     r[0] = (p)[3 * (tp)];       r[1] = (p)[3 * (tp) + 1];   r[2] = (p)[2 * (tp) + 2];   r[3] = (p)[(tp) + 3];      \
     r[4] = (p)[3];              r[5] = (p)[-(tp) + 3];      r[6] = (p)[-2 * (tp) + 2];  r[7] = (p)[-3 * (tp) + 1]; \
@@ -69,6 +67,56 @@ __device__ __forceinline__ int fast9_score_m(const uint8_t *p, int tp)
 
 extern __shared__ __align__(16) uint8_t fast_smem[];
 
+// |ring - centre| > T per byte, result in bit 7 of each byte (T <= 127; K = (127-T)*0x01010101)
+__device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t c, uint32_t K)
+{
+    const uint32_t ad = __vabsdiffu4(ring, c);
+    return ((ad & 0x7f7f7f7fu) + K) | ad;
+}
+
+// i / n for small i via multiply-high; magic = 2^32/n rounded up (n == 1 has no 32-bit magic)
+__device__ __forceinline__ uint32_t div_magic(int n) { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; }
+__device__ __forceinline__ int fast_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
+
+// warp-aggregated append of `cnt` (0..8) items per lane: returns this lane's first slot
+__device__ __forceinline__ int warp_reserve(int cnt, int *counter)
+{
+    const int lane = threadIdx.x & 31;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (total) {
+        if (lane == 31) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    return base + inc - cnt;
+}
+
+__device__ __forceinline__ int warp_append1(bool pred, int *counter)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    int base = 0;
+    if (bal) {
+        if (lane == 0) base = atomicAdd(counter, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+    }
+    return base + __popc(bal & ((1u << lane) - 1));
+}
+
+// Pipeline of one CTA (G cells of one cell row), every stage on dense lanes:
+//   0  stage the u8 tile (+3-px halo) with 8-byte loads
+//   1  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
+//      (N,E,S,W at radius 3) with |d| > T  ->  (aN|aS) & (aE|aW); VABSDIFF4 + 3 ops per 4 px
+//   2  signed compass test on the survivors (both brighter or both darker)
+//   3  full 16-pixel ring masks + 9-contiguous-arc test           -> corners at minTh
+//   4  score m of the corners                                     -> m map
+//   5  NMS inside the cell interior, per-cell threshold decision, emission
 __global__ void __launch_bounds__(256)
 fast9_cells(FastArgs a)
 {
@@ -78,99 +126,158 @@ fast9_cells(FastArgs a)
     const int cj0 = blockIdx.x * a.G;   // first cell column
     const int y0 = 16 + ci * a.hCell;   // ROI origin (iniY)
     const int x0 = 16 + cj0 * a.wCell;  // ROI origin (iniX of first cell)
-    // interior extents handled by this CTA
-    const int hEff = min(a.hCell, a.maxBY - 3 - (y0 + 3));
-    const int wEff = min(a.scw, a.maxBX - 3 - (x0 + 3));
+    const int hEff = min(a.hCell, a.maxBY - 3 - (y0 + 3));   // interior rows of this CTA
+    const int wEff = min(a.scw, a.maxBX - 3 - (x0 + 3));     // interior columns of this CTA
     if (hEff <= 0 || wEff <= 0) return;
-    const int xa = x0 & ~3;             // aligned tile origin
+    const int xa = x0 & ~7;             // 8-byte aligned tile origin
     const int ox = x0 - xa;
+    const int cs = ox + 3, ce = cs + wEff;   // interior byte range inside a tile row
     const int rows = hEff + 6;
     const int tp = a.tpitch;
+    const int cap = a.hCell * a.scw;
 
-    uint8_t *tile = fast_smem;                                   // (hCell+6) * tp
-    uint8_t *sc = tile + (size_t)(a.hCell + 6) * tp;             // hCell * scw  (m map, 0 = not a corner)
-    uint16_t *list = reinterpret_cast<uint16_t *>(sc + (size_t)((a.hCell * a.scw + 3) & ~3)); // hCell*scw
-    __shared__ int s_n, s_emit, s_base;
+    uint8_t *tile = fast_smem;                                      // (hCell+6) * tp
+    uint8_t *sc = tile + (size_t)(a.hCell + 6) * tp;                // hCell * scw : m map (0 = not a corner)
+    uint8_t *cellOf = sc + ((cap + 15) & ~15);                      // scw : cell index of an interior column
+    uint16_t *listA = reinterpret_cast<uint16_t *>(cellOf + ((a.scw + 15) & ~15));
+    uint16_t *listB = listA + ((cap + 7) & ~7);
+    __shared__ int s_nA, s_nB, s_nC, s_emit, s_base;
     __shared__ int s_has_init[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
-    // ---- stage tile: 4-byte loads, rows [y0, y0+rows), bytes [xa, x0+wEff+6)
-    const int words = (ox + wEff + 6 + 3) >> 2;
-    for (int i = tid; i < rows * words; i += 256) {
-        int rr = i / words, ww = i - rr * words;
-        uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
-        *reinterpret_cast<uint32_t *>(tile + rr * tp + 4 * ww) = v;
+    // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 8-byte words
+    const int w8 = (ox + wEff + 6 + 7) >> 3;
+    const uint32_t magic8 = div_magic(w8);
+    for (int i = tid; i < rows * w8; i += 256) {
+        const int rr = fast_div(i, magic8), ww = i - rr * w8;
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
+        *reinterpret_cast<uint2 *>(tile + rr * tp + 8 * ww) = v;
     }
-    for (int i = tid; i < (a.hCell * a.scw + 3) / 4; i += 256) reinterpret_cast<uint32_t *>(sc)[i] = 0;
-    if (tid == 0) { s_n = 0; s_emit = 0; }
+    for (int i = tid; i < (cap + 3) / 4; i += 256) reinterpret_cast<uint32_t *>(sc)[i] = 0;
+    for (int i = tid; i < a.scw; i += 256) cellOf[i] = (uint8_t)(i / a.wCell);
+    if (tid == 0) { s_nA = 0; s_nB = 0; s_nC = 0; s_emit = 0; }
     if (tid < 64) s_has_init[tid] = 0;
     __syncthreads();
 
-    // ---- phase 1a: corner test at minTh, compact corners to the work list
-    const int npx = hEff * wEff;
     const int T = a.minTh;
-    for (int base = 0; base < npx; base += 256) {
-        int i = base + tid;
-        bool corner = false;
-        int rr = 0, cc = 0;
-        if (i < npx) {
-            rr = i / wEff; cc = i - rr * wEff;
-            const uint8_t *p = tile + (rr + 3) * tp + (cc + 3 + ox);
-            const int v = p[0], lo = v - T, hi = v + T;
-            // antipodal pairs: every 9-arc contains one pixel of each pair
-            int p0 = p[3 * tp], p8 = p[-3 * tp];
-            if ((p0 < lo || p0 > hi || p8 < lo || p8 > hi)) {
-                int p4 = p[3], p12 = p[-3];
-                if ((p4 < lo || p4 > hi || p12 < lo || p12 > hi)) {
-                    int r[16];
-                    RING_LOAD(p, tp);
-                    uint32_t mb = 0, md = 0;
+    // ---- stage 1: SWAR compass prefilter
+    if (T <= 127) {
+        const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
+        const int g0 = cs >> 3, nG = ((ce + 7) >> 3) - g0;
+        const uint32_t magic = div_magic(nG);
+        const int items = hEff * nG;
+        for (int base = 0; base < items; base += 256) {
+            const int it = base + tid;
+            uint32_t c0 = 0, c1 = 0;
+            int r = 0, o = 0;
+            if (it < items) {
+                r = fast_div(it, magic);
+                o = 8 * (it - r * nG + g0);
+                const uint8_t *row = tile + (r + 3) * tp + o;
+                const uint2 cen = *reinterpret_cast<const uint2 *>(row);
+                const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
+                const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
+                const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
+                const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
+                const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
+                const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
+                c0 = (absdiff_gt(up.x, cen.x, K) | absdiff_gt(dn.x, cen.x, K)) & (absdiff_gt(lw0, cen.x, K) | absdiff_gt(rw0, cen.x, K)) & 0x80808080u;
+                c1 = (absdiff_gt(up.y, cen.y, K) | absdiff_gt(dn.y, cen.y, K)) & (absdiff_gt(lw1, cen.y, K) | absdiff_gt(rw1, cen.y, K)) & 0x80808080u;
+                if (o < cs || o + 8 > ce) {   // edge groups: drop bytes outside the interior
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        mb |= (r[k] > hi ? 1u : 0u) << k;   // ring brighter  (d < -T)
-                        md |= (r[k] < lo ? 1u : 0u) << k;   // ring darker    (d >  T)
+                    for (int b = 0; b < 4; b++) {
+                        if (o + b < cs || o + b >= ce) c0 &= ~(0x80u << (8 * b));
+                        if (o + 4 + b < cs || o + 4 + b >= ce) c1 &= ~(0x80u << (8 * b));
                     }
-                    corner = arc9(mb) || arc9(md);
                 }
             }
+            const int cnt = __popc(c0) + __popc(c1);
+            int pos = warp_reserve(cnt, &s_nA);
+            if (cnt) {
+                const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that the edge mask dropped
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + b);
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + 4 + b);
+            }
         }
-        unsigned bal = __ballot_sync(0xffffffffu, corner);
-        if (bal) {
-            int lane = tid & 31, wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_n, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (corner) list[wbase + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(rr * a.scw + cc);
-        }
+    } else {
+        // thresholds above 127 do not fit the SWAR compare: every interior pixel goes to stage 2
+        for (int i = tid; i < hEff * wEff; i += 256) { int rr = i / wEff; listA[i] = (uint16_t)((rr << 10) | (i - rr * wEff)); }
+        if (tid == 0) s_nA = hEff * wEff;
     }
     __syncthreads();
-    const int nc = s_n;
-    // ---- phase 1b: score of the corners (dense lanes)
-    for (int i = tid; i < nc; i += 256) {
-        int idx = list[i];
-        int rr = idx / a.scw, cc = idx - rr * a.scw;
-        const uint8_t *p = tile + (rr + 3) * tp + (cc + 3 + ox);
-        sc[idx] = (uint8_t)fast9_score_m(p, tp);
+    // ---- stage 2: signed compass test (two adjacent compass pixels both brighter or both darker)
+    const int nA = s_nA;
+    for (int base = 0; base < nA; base += 256) {
+        const int i = base + tid;
+        bool pass = false;
+        int e = 0;
+        if (i < nA) {
+            e = listA[i];
+            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
+            const int v = p[0], lo = v - T, hi = v + T;
+            const int pN = p[3 * tp], pE = p[3], pS = p[-3 * tp], pW = p[-3];
+            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
+            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
+            pass = ((bN | bS) & (bE | bW)) | ((dN | dS) & (dE | dW));
+        }
+        const int pos = warp_append1(pass, &s_nB);
+        if (pass) listB[pos] = (uint16_t)e;
     }
     __syncthreads();
-    // ---- phase 2: NMS inside the cell interior; per-cell "has a survivor above initTh"
+    // ---- stage 3: full ring test at minTh
+    const int nB = s_nB;
+    for (int base = 0; base < nB; base += 256) {
+        const int i = base + tid;
+        bool corner = false;
+        int e = 0;
+        if (i < nB) {
+            e = listB[i];
+            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
+            const int v = p[0], lo = v - T, hi = v + T;
+            int r[16];
+            RING_LOAD(p, tp);
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
+                md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
+            }
+            corner = arc9(mb) || arc9(md);
+        }
+        const int pos = warp_append1(corner, &s_nC);
+        if (corner) listA[pos] = (uint16_t)e;
+    }
+    __syncthreads();
+    // ---- stage 4: score of the corners
+    const int nc = s_nC;
+    uint16_t *list = listA;
     for (int i = tid; i < nc; i += 256) {
-        int idx = list[i];
-        int rr = idx / a.scw, cc = idx - rr * a.scw;
-        int m = sc[idx];
-        int cell = cc / a.wCell;
-        int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
+        const int e = list[i];
+        const int rr = e >> 10, cc = e & 1023;
+        sc[rr * a.scw + cc] = (uint8_t)fast9_score_m(tile + (rr + 3) * tp + cs + cc, tp);
+    }
+    __syncthreads();
+    // ---- stage 5a: NMS inside the cell interior; per-cell "has a survivor above initTh"
+    for (int i = tid; i < nc; i += 256) {
+        const int e = list[i];
+        const int rr = e >> 10, cc = e & 1023;
+        const int m = sc[rr * a.scw + cc];
+        const int cell = cellOf[cc];
+        const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
         bool keep = true;
 #pragma unroll
         for (int dr = -1; dr <= 1; dr++) {
-            int r2 = rr + dr;
+            const int r2 = rr + dr;
             if (r2 < 0 || r2 >= hEff) continue;
 #pragma unroll
             for (int dc = -1; dc <= 1; dc++) {
                 if (!dr && !dc) continue;
-                int c2 = cc + dc;
+                const int c2 = cc + dc;
                 if (c2 < cl || c2 >= chi) continue;
-                int m2 = sc[r2 * a.scw + c2];
-                // compare scores (m-1), non-corners are 0 in OpenCV's buffer: m-1 > max(m2-1, 0)
+                const int m2 = sc[r2 * a.scw + c2];
+                // scores are m-1, non-corners hold 0 in OpenCV's buffer: keep iff m-1 > max(m2-1, 0)
                 if (!(m - 1 > max(m2 - 1, 0))) keep = false;
             }
         }
@@ -181,32 +288,26 @@ fast9_cells(FastArgs a)
         }
     }
     __syncthreads();
-    // ---- phase 3: apply the cell threshold; stage survivors in shared memory (the tile is dead now),
+    // ---- stage 5b: apply the cell threshold; stage survivors in shared memory (the tile is dead now),
     //      reserve space in the (frame, level) candidate array with ONE global atomic, copy out.
     uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
     for (int base = 0; base < nc; base += 256) {
-        int i = base + tid;
+        const int i = base + tid;
         bool emit = false;
         uint32_t val = 0;
         if (i < nc && list[i] != 0xFFFF) {
-            int idx = list[i];
-            int rr = idx / a.scw, cc = idx - rr * a.scw;
-            int m = sc[idx];
-            int cell = cc / a.wCell;
-            int Tc = s_has_init[cell] ? a.initTh : a.minTh;
+            const int e = list[i];
+            const int rr = e >> 10, cc = e & 1023;
+            const int m = sc[rr * a.scw + cc];
+            const int Tc = s_has_init[cellOf[cc]] ? a.initTh : a.minTh;
             if (m > Tc) {
                 emit = true;
                 // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
                 val = cand_pack(cj0 * a.wCell + cc + 3, ci * a.hCell + rr + 3, m);
             }
         }
-        unsigned bal = __ballot_sync(0xffffffffu, emit);
-        if (bal) {
-            int lane = tid & 31, wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_emit, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (emit) stage[wbase + __popc(bal & ((1u << lane) - 1))] = val;
-        }
+        const int pos = warp_append1(emit, &s_emit);
+        if (emit) stage[pos] = val;
     }
     __syncthreads();
     const int cnt = s_emit;
@@ -219,11 +320,17 @@ fast9_cells(FastArgs a)
         if (gbase + i < a.cand_cap) a.cand[(size_t)f * a.cand_cap + gbase + i] = stage[i];
 }
 
+size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
+{
+    const int cap = hCell * scw;
+    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + 2 * sizeof(uint16_t) * ((cap + 7) & ~7) + 64;
+}
+
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     ProfScope prof__(ctx, "fast9_cells");

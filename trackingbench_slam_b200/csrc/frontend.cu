@@ -318,12 +318,12 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
             a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
             a.G = 256 / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
             a.scw = a.G * g.wCell;
-            a.tpitch = ((3 + a.scw + 6 + 3) & ~3) + 4;
+            a.tpitch = ((7 + a.scw + 6 + 7) & ~7) + 8;   // 8-byte aligned origin + halo + one spare word for the E-side read
             a.initTh = (int)initTh; a.minTh = (int)minTh;
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
             a.overflow = fe->overflow;
-            size_t smem = (size_t)(g.hCell + 6) * a.tpitch + (size_t)((g.hCell * a.scw + 3) & ~3) + 2 * (size_t)g.hCell * a.scw + 16;
+            size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch);
             int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
             if (rc) return rc;
         }

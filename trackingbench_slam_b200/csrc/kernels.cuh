@@ -17,6 +17,7 @@ struct FastArgs {
     int *n_cand; int n_cand_stride;
     int *overflow;
 };
+size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch);
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem);
 struct OctArgs {
     const uint32_t *cand; int cand_cap;
