@@ -111,12 +111,176 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 
 // Pipeline of one CTA (G cells of one cell row), every stage on dense lanes:
 //   0  stage the u8 tile (+3-px halo) with 8-byte loads
+//   then, at T = initTh for every cell and again at T = minTh only for the cells that produced no
+//   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792):
 //   1  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
 //      (N,E,S,W at radius 3) with |d| > T  ->  (aN|aS) & (aE|aW); VABSDIFF4 + 3 ops per 4 px
 //   2  signed compass test on the survivors (both brighter or both darker)
-//   3  full 16-pixel ring masks + 9-contiguous-arc test           -> corners at minTh
+//   3  full 16-pixel ring masks + 9-contiguous-arc test           -> corners at T
 //   4  score m of the corners                                     -> m map
-//   5  NMS inside the cell interior, per-cell threshold decision, emission
+//   5  NMS inside the cell interior, emission with one global atomic per pass
+struct FastSmem {
+    uint8_t *tile, *sc, *cellOf, *need;
+    uint16_t *listA, *listB;
+};
+
+__device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
+                                          const int hEff, const int wEff, const int cs, const int ce, const int tp,
+                                          const int cand_x0, const int cand_y0, int *s_cnt, int *s_has, int *s_base)
+{
+    const int tid = threadIdx.x;
+    uint8_t *tile = S.tile, *sc = S.sc;
+    uint16_t *listA = S.listA, *listB = S.listB;
+    // ---- stage 1: SWAR compass prefilter (need[] holds 0x80 for the bytes this pass must test)
+    if (T <= 127) {
+        const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
+        const int g0 = cs >> 3, nG = ((ce + 7) >> 3) - g0;
+        const uint32_t magic = div_magic(nG);
+        const int items = hEff * nG;
+        for (int base = 0; base < items; base += 256) {
+            const int it = base + tid;
+            uint32_t c0 = 0, c1 = 0;
+            int r = 0, o = 0;
+            if (it < items) {
+                r = fast_div(it, magic);
+                o = 8 * (it - r * nG + g0);
+                const uint2 nd = *reinterpret_cast<const uint2 *>(S.need + o);
+                if (nd.x | nd.y) {
+                    const uint8_t *row = tile + (r + 3) * tp + o;
+                    const uint2 cen = *reinterpret_cast<const uint2 *>(row);
+                    const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
+                    const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
+                    const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
+                    const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
+                    const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
+                    const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
+                    c0 = (absdiff_gt(up.x, cen.x, K) | absdiff_gt(dn.x, cen.x, K)) & (absdiff_gt(lw0, cen.x, K) | absdiff_gt(rw0, cen.x, K)) & nd.x;
+                    c1 = (absdiff_gt(up.y, cen.y, K) | absdiff_gt(dn.y, cen.y, K)) & (absdiff_gt(lw1, cen.y, K) | absdiff_gt(rw1, cen.y, K)) & nd.y;
+                }
+            }
+            const int cnt = __popc(c0) + __popc(c1);
+            int pos = warp_reserve(cnt, &s_cnt[0]);
+            if (cnt) {
+                const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + b);
+#pragma unroll
+                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + 4 + b);
+            }
+        }
+    } else {
+        // thresholds above 127 do not fit the SWAR compare: every needed interior pixel goes to stage 2
+        for (int base = 0; base < hEff * wEff; base += 256) {
+            const int i = base + tid;
+            bool ok = false;
+            int rr = 0, cc = 0;
+            if (i < hEff * wEff) { rr = i / wEff; cc = i - rr * wEff; ok = S.need[cs + cc] != 0; }
+            const int pos = warp_append1(ok, &s_cnt[0]);
+            if (ok) listA[pos] = (uint16_t)((rr << 10) | cc);
+        }
+    }
+    __syncthreads();
+    // ---- stage 2: signed compass test (two adjacent compass pixels both brighter or both darker)
+    const int nA = s_cnt[0];
+    for (int base = 0; base < nA; base += 256) {
+        const int i = base + tid;
+        bool pass = false;
+        int e = 0;
+        if (i < nA) {
+            e = listA[i];
+            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
+            const int v = p[0], lo = v - T, hi = v + T;
+            const int pN = p[3 * tp], pE = p[3], pS = p[-3 * tp], pW = p[-3];
+            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
+            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
+            pass = ((bN | bS) & (bE | bW)) | ((dN | dS) & (dE | dW));
+        }
+        const int pos = warp_append1(pass, &s_cnt[1]);
+        if (pass) listB[pos] = (uint16_t)e;
+    }
+    __syncthreads();
+    // ---- stage 3: full ring test at T
+    const int nB = s_cnt[1];
+    for (int base = 0; base < nB; base += 256) {
+        const int i = base + tid;
+        bool corner = false;
+        int e = 0;
+        if (i < nB) {
+            e = listB[i];
+            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
+            const int v = p[0], lo = v - T, hi = v + T;
+            int r[16];
+            RING_LOAD(p, tp);
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
+                md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
+            }
+            corner = arc9(mb) || arc9(md);
+        }
+        const int pos = warp_append1(corner, &s_cnt[2]);
+        if (corner) listA[pos] = (uint16_t)e;
+    }
+    __syncthreads();
+    // ---- stage 4: score of the corners
+    const int nc = s_cnt[2];
+    for (int i = tid; i < nc; i += 256) {
+        const int e = listA[i];
+        const int rr = e >> 10, cc = e & 1023;
+        sc[rr * a.scw + cc] = (uint8_t)fast9_score_m(tile + (rr + 3) * tp + cs + cc, tp);
+    }
+    __syncthreads();
+    // ---- stage 5: NMS inside the cell interior; survivors are staged in listB (free now)
+    uint32_t *stage = reinterpret_cast<uint32_t *>(listB);
+    for (int base = 0; base < nc; base += 256) {
+        const int i = base + tid;
+        bool keep = false;
+        uint32_t val = 0;
+        if (i < nc) {
+            const int e = listA[i];
+            const int rr = e >> 10, cc = e & 1023;
+            const int m = sc[rr * a.scw + cc];
+            const int cell = S.cellOf[cc];
+            const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
+            keep = true;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++) {
+                const int r2 = rr + dr;
+                if (r2 < 0 || r2 >= hEff) continue;
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (!dr && !dc) continue;
+                    const int c2 = cc + dc;
+                    if (c2 < cl || c2 >= chi) continue;
+                    const int m2 = sc[r2 * a.scw + c2];
+                    // scores are m-1, non-corners hold 0 in OpenCV's buffer: keep iff m-1 > max(m2-1, 0)
+                    if (!(m - 1 > max(m2 - 1, 0))) keep = false;
+                }
+            }
+            if (keep) {
+                s_has[cell] = 1;
+                // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
+                val = cand_pack(cand_x0 + cc + 3, cand_y0 + rr + 3, m);
+            }
+        }
+        const int pos = warp_append1(keep, &s_cnt[3]);
+        if (keep) stage[pos] = val;
+    }
+    __syncthreads();
+    // ---- emission: one global atomic for this pass
+    const int cnt = s_cnt[3];
+    if (cnt) {
+        if (tid == 0) *s_base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], cnt);
+        __syncthreads();
+        const int gbase = *s_base;
+        if (gbase + cnt > a.cand_cap) { if (tid == 0) atomicExch(a.overflow, 1); }
+        for (int i = tid; i < cnt; i += 256)
+            if (gbase + i < a.cand_cap) a.cand[(size_t)f * a.cand_cap + gbase + i] = stage[i];
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 fast9_cells(FastArgs a)
 {
@@ -136,13 +300,15 @@ fast9_cells(FastArgs a)
     const int tp = a.tpitch;
     const int cap = a.hCell * a.scw;
 
-    uint8_t *tile = fast_smem;                                      // (hCell+6) * tp
-    uint8_t *sc = tile + (size_t)(a.hCell + 6) * tp;                // hCell * scw : m map (0 = not a corner)
-    uint8_t *cellOf = sc + ((cap + 15) & ~15);                      // scw : cell index of an interior column
-    uint16_t *listA = reinterpret_cast<uint16_t *>(cellOf + ((a.scw + 15) & ~15));
-    uint16_t *listB = listA + ((cap + 7) & ~7);
-    __shared__ int s_nA, s_nB, s_nC, s_emit, s_base;
-    __shared__ int s_has_init[64];
+    FastSmem S;
+    S.tile = fast_smem;                                              // (hCell+6) * tp
+    S.sc = S.tile + (size_t)(a.hCell + 6) * tp;                      // hCell * scw : m map (0 = not a corner)
+    S.cellOf = S.sc + ((cap + 15) & ~15);                            // scw : cell index of an interior column
+    S.need = S.cellOf + ((a.scw + 15) & ~15);                        // tp : 0x80 where this pass tests the byte column
+    S.listA = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
+    S.listB = S.listA + ((cap + 7) & ~7);
+    __shared__ int s_cnt[4], s_base, s_again;
+    __shared__ int s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
     // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 8-byte words
@@ -151,179 +317,36 @@ fast9_cells(FastArgs a)
     for (int i = tid; i < rows * w8; i += 256) {
         const int rr = fast_div(i, magic8), ww = i - rr * w8;
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
-        *reinterpret_cast<uint2 *>(tile + rr * tp + 8 * ww) = v;
+        *reinterpret_cast<uint2 *>(S.tile + rr * tp + 8 * ww) = v;
     }
-    for (int i = tid; i < (cap + 3) / 4; i += 256) reinterpret_cast<uint32_t *>(sc)[i] = 0;
-    for (int i = tid; i < a.scw; i += 256) cellOf[i] = (uint8_t)(i / a.wCell);
-    if (tid == 0) { s_nA = 0; s_nB = 0; s_nC = 0; s_emit = 0; }
-    if (tid < 64) s_has_init[tid] = 0;
+    for (int i = tid; i < (cap + 3) / 4; i += 256) reinterpret_cast<uint32_t *>(S.sc)[i] = 0;
+    for (int i = tid; i < a.scw; i += 256) S.cellOf[i] = (uint8_t)(i / a.wCell);
+    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
+    if (tid < 4) s_cnt[tid] = 0;
+    if (tid < 64) s_has[tid] = 0;
     __syncthreads();
 
-    const int T = a.minTh;
-    // ---- stage 1: SWAR compass prefilter
-    if (T <= 127) {
-        const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
-        const int g0 = cs >> 3, nG = ((ce + 7) >> 3) - g0;
-        const uint32_t magic = div_magic(nG);
-        const int items = hEff * nG;
-        for (int base = 0; base < items; base += 256) {
-            const int it = base + tid;
-            uint32_t c0 = 0, c1 = 0;
-            int r = 0, o = 0;
-            if (it < items) {
-                r = fast_div(it, magic);
-                o = 8 * (it - r * nG + g0);
-                const uint8_t *row = tile + (r + 3) * tp + o;
-                const uint2 cen = *reinterpret_cast<const uint2 *>(row);
-                const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
-                const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
-                const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
-                const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
-                const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
-                const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
-                c0 = (absdiff_gt(up.x, cen.x, K) | absdiff_gt(dn.x, cen.x, K)) & (absdiff_gt(lw0, cen.x, K) | absdiff_gt(rw0, cen.x, K)) & 0x80808080u;
-                c1 = (absdiff_gt(up.y, cen.y, K) | absdiff_gt(dn.y, cen.y, K)) & (absdiff_gt(lw1, cen.y, K) | absdiff_gt(rw1, cen.y, K)) & 0x80808080u;
-                if (o < cs || o + 8 > ce) {   // edge groups: drop bytes outside the interior
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        if (o + b < cs || o + b >= ce) c0 &= ~(0x80u << (8 * b));
-                        if (o + 4 + b < cs || o + 4 + b >= ce) c1 &= ~(0x80u << (8 * b));
-                    }
-                }
-            }
-            const int cnt = __popc(c0) + __popc(c1);
-            int pos = warp_reserve(cnt, &s_nA);
-            if (cnt) {
-                const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that the edge mask dropped
-#pragma unroll
-                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + b);
-#pragma unroll
-                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + 4 + b);
-            }
-        }
-    } else {
-        // thresholds above 127 do not fit the SWAR compare: every interior pixel goes to stage 2
-        for (int i = tid; i < hEff * wEff; i += 256) { int rr = i / wEff; listA[i] = (uint16_t)((rr << 10) | (i - rr * wEff)); }
-        if (tid == 0) s_nA = hEff * wEff;
+    // pass 1: every cell at initTh (ORBextractor.cpp:785)
+    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base);
+    // pass 2: cells without a keypoint again at minTh (:788-792)
+    const int nCells = (wEff + a.wCell - 1) / a.wCell;
+    if (tid == 0) {
+        int again = 0;
+        for (int c = 0; c < nCells; c++) again |= !s_has[c];
+        s_again = again && (a.minTh != a.initTh);
     }
+    if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
-    // ---- stage 2: signed compass test (two adjacent compass pixels both brighter or both darker)
-    const int nA = s_nA;
-    for (int base = 0; base < nA; base += 256) {
-        const int i = base + tid;
-        bool pass = false;
-        int e = 0;
-        if (i < nA) {
-            e = listA[i];
-            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
-            const int v = p[0], lo = v - T, hi = v + T;
-            const int pN = p[3 * tp], pE = p[3], pS = p[-3 * tp], pW = p[-3];
-            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
-            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
-            pass = ((bN | bS) & (bE | bW)) | ((dN | dS) & (dE | dW));
-        }
-        const int pos = warp_append1(pass, &s_nB);
-        if (pass) listB[pos] = (uint16_t)e;
-    }
+    if (!s_again) return;
+    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce && !s_has[S.cellOf[i - cs]]) ? 0x80 : 0;
     __syncthreads();
-    // ---- stage 3: full ring test at minTh
-    const int nB = s_nB;
-    for (int base = 0; base < nB; base += 256) {
-        const int i = base + tid;
-        bool corner = false;
-        int e = 0;
-        if (i < nB) {
-            e = listB[i];
-            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
-            const int v = p[0], lo = v - T, hi = v + T;
-            int r[16];
-            RING_LOAD(p, tp);
-            uint32_t mb = 0, md = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
-                md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
-            }
-            corner = arc9(mb) || arc9(md);
-        }
-        const int pos = warp_append1(corner, &s_nC);
-        if (corner) listA[pos] = (uint16_t)e;
-    }
-    __syncthreads();
-    // ---- stage 4: score of the corners
-    const int nc = s_nC;
-    uint16_t *list = listA;
-    for (int i = tid; i < nc; i += 256) {
-        const int e = list[i];
-        const int rr = e >> 10, cc = e & 1023;
-        sc[rr * a.scw + cc] = (uint8_t)fast9_score_m(tile + (rr + 3) * tp + cs + cc, tp);
-    }
-    __syncthreads();
-    // ---- stage 5a: NMS inside the cell interior; per-cell "has a survivor above initTh"
-    for (int i = tid; i < nc; i += 256) {
-        const int e = list[i];
-        const int rr = e >> 10, cc = e & 1023;
-        const int m = sc[rr * a.scw + cc];
-        const int cell = cellOf[cc];
-        const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
-        bool keep = true;
-#pragma unroll
-        for (int dr = -1; dr <= 1; dr++) {
-            const int r2 = rr + dr;
-            if (r2 < 0 || r2 >= hEff) continue;
-#pragma unroll
-            for (int dc = -1; dc <= 1; dc++) {
-                if (!dr && !dc) continue;
-                const int c2 = cc + dc;
-                if (c2 < cl || c2 >= chi) continue;
-                const int m2 = sc[r2 * a.scw + c2];
-                // scores are m-1, non-corners hold 0 in OpenCV's buffer: keep iff m-1 > max(m2-1, 0)
-                if (!(m - 1 > max(m2 - 1, 0))) keep = false;
-            }
-        }
-        if (keep) {
-            if (m > a.initTh) s_has_init[cell] = 1;
-        } else {
-            list[i] = 0xFFFF;
-        }
-    }
-    __syncthreads();
-    // ---- stage 5b: apply the cell threshold; stage survivors in shared memory (the tile is dead now),
-    //      reserve space in the (frame, level) candidate array with ONE global atomic, copy out.
-    uint32_t *stage = reinterpret_cast<uint32_t *>(tile);
-    for (int base = 0; base < nc; base += 256) {
-        const int i = base + tid;
-        bool emit = false;
-        uint32_t val = 0;
-        if (i < nc && list[i] != 0xFFFF) {
-            const int e = list[i];
-            const int rr = e >> 10, cc = e & 1023;
-            const int m = sc[rr * a.scw + cc];
-            const int Tc = s_has_init[cellOf[cc]] ? a.initTh : a.minTh;
-            if (m > Tc) {
-                emit = true;
-                // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
-                val = cand_pack(cj0 * a.wCell + cc + 3, ci * a.hCell + rr + 3, m);
-            }
-        }
-        const int pos = warp_append1(emit, &s_emit);
-        if (emit) stage[pos] = val;
-    }
-    __syncthreads();
-    const int cnt = s_emit;
-    if (cnt == 0) return;
-    if (tid == 0) s_base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], cnt);
-    __syncthreads();
-    const int gbase = s_base;
-    if (gbase + cnt > a.cand_cap) { if (tid == 0) atomicExch(a.overflow, 1); }
-    for (int i = tid; i < cnt; i += 256)
-        if (gbase + i < a.cand_cap) a.cand[(size_t)f * a.cand_cap + gbase + i] = stage[i];
+    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base);
 }
 
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
 {
     const int cap = hCell * scw;
-    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + 2 * sizeof(uint16_t) * ((cap + 7) & ~7) + 64;
+    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) + 2 * sizeof(uint16_t) * ((cap + 7) & ~7) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
