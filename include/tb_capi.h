@@ -161,6 +161,14 @@ int tb_match_bf_cross_device(tb_ctx *ctx, const void *d1_dptr, int n1, const voi
 int tb_search_by_bf_device(tb_ctx *ctx, const void *d1_dptr, int n1, const void *d2_dptr, int n2,
                            float ratio, float minTh, tb_match *out_host, int capacity, int *n);
 
+/* Host-buffer variants used by the C++ facade (Matcher::searchByBF / DescriptorDistance): stage the
+ * descriptors to the device, run the same kernels, copy the result back. */
+int tb_match_bf_cross_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+                           tb_match *out, int capacity, int *n);
+int tb_search_by_bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+                         float ratio, float minTh, tb_match *out, int capacity, int *n);
+int tb_hamming_pairs_host(tb_ctx *ctx, const uint8_t *a, const uint8_t *b, int n, int32_t *dist);
+
 /* Batched searchByBF over frame pairs of one frontend's last extract: pair p matches frame
  * q_frames[p] (query/F1) against t_frames[p] (train/F2). Outputs on the device:
  * matches_dptr[p*capacity + i], counts_dptr[p]. No host synchronisation. */

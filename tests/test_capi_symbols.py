@@ -59,5 +59,6 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dp, f)).read()
                 assert 'import oracle' not in txt and 'tb_oracle.h' not in txt and 'libtb_oracle' not in txt, f
-    for f in os.listdir(os.path.join(ROOT, 'include')):
-        assert 'tb_oracle' not in open(os.path.join(ROOT, 'include', f)).read()
+    for dp, _, fs in os.walk(os.path.join(ROOT, 'include')):
+        for f in fs:
+            assert 'tb_oracle' not in open(os.path.join(dp, f)).read(), f

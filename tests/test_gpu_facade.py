@@ -1,0 +1,70 @@
+"""The C++ facade (include/extractors, include/matchers, include/types keep the reference's class
+names) driven by a headless restatement of test/test_matcher.cpp, compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from .conftest import ROOT, PARAM_SETS
+
+pytestmark = pytest.mark.gpu
+
+
+def _fnv(b, h=1469598103934665603):
+    for x in b:
+        h ^= x
+        h = (h * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _digest(m):
+    h = 1469598103934665603
+    for r in m:
+        h = _fnv(np.array([r['queryIdx'], r['trainIdx']], np.int32).tobytes(), h)
+        h = _fnv(np.float32(r['distance']).tobytes(), h)
+    return h
+
+
+def test_headless_test_matcher(tmp_path, oracle, images):
+    exe = str(tmp_path / 'test_matcher_headless')
+    libdir = os.path.join(ROOT, 'trackingbench_slam_b200')
+    subprocess.check_call(['g++', '-std=c++14', '-O2', '-I' + os.path.join(ROOT, 'include'), '-o', exe,
+                           os.path.join(ROOT, 'examples', 'test_matcher_headless.cpp'), '-L' + libdir, '-ltb_b200',
+                           '-Wl,-rpath,' + libdir])
+    paths = []
+    for n in ('left', 'right', 'disparity'):
+        p = str(tmp_path / (n + '.pgm'))
+        im = images[n]
+        with open(p, 'wb') as f:
+            f.write(b'P5\n%d %d\n255\n' % (im.shape[1], im.shape[0]))
+            f.write(im.tobytes())
+        paths.append(p)
+    out = subprocess.check_output([exe] + paths).decode().split('\n')
+    got = {l.split()[0]: l.split()[1:] for l in out if l.strip()}
+    nl, sc, tgt, a, b = PARAM_SETS['A1000']
+    ext = []
+    for n in ('left', 'right'):
+        lv, sf = oracle.pyramid(images[n], nl, sc)
+        ext.append(oracle.orb_extract(lv, sf, tgt, a, b))
+    (k1, d1, _), (k2, d2, _) = ext
+    assert got['kps'] == [str(len(k1)), str(len(k2))]
+    assert got['kps_digest'] == ['%x' % _fnv(k1.tobytes()), '%x' % _fnv(k2.tobytes())]
+    assert got['desc_digest'] == ['%x' % _fnv(d1.tobytes()), '%x' % _fnv(d2.tobytes())]
+    bf = oracle.search_by_bf(d1, d2, 10.0, 30.0)
+    assert got['bf'] == [str(len(bf)), '%x' % _digest(bf)]
+    H, W = images['left'].shape
+    vio = oracle.search_by_violence(oracle.MatcherParams(30, 100, 30, 1, 5.0), k1, d1, k2, d2, W, H, 0, 5, 50.0)
+    assert got['violence'] == [str(len(vio)), '%x' % _digest(vio)]
+    fx, fy, cx, cy, base = np.float32(718.856), np.float32(718.856), np.float32(607.1928), np.float32(185.2157), np.float32(0.573)
+    disp = images['disparity'][k1['y'].astype(np.int32), k1['x'].astype(np.int32)].astype(np.float32)
+    valid = (disp > 0).astype(np.uint8)
+    depth = np.where(disp > 0, (base * fx) / np.maximum(disp, 1), 0).astype(np.float32)
+    xyz = np.stack([(k1['x'] - cx) / fx * depth, (k1['y'] - cy) / fy * depth, depth], 1).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    T[0, 3] = -base
+    cam = oracle.Pinhole(718.856, 718.856, 607.1928, 185.2157, W, H, (oracle.C.c_float * 5)(0, 0, 0, 0, 0))
+    sf = oracle.scale_factors(nl, sc)
+    proj = oracle.search_by_projection(oracle.MatcherParams(30, 50, 30, 1, 30.0), cam, T, k2, d2, None, sf, W, H, k1, valid, xyz, d1)
+    assert got['projection'] == [str(len(proj)), '%x' % _digest(proj)]
+    assert got['dist01'] == [str(oracle.hamming256(d1[0], d1[1]))]

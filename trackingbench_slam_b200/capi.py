@@ -29,6 +29,7 @@ EXPORTS = [
     'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_candidates',
     'tb_frontend_get_level_counts', 'tb_orb_extract_host',
     'tb_hamming_pairs_device', 'tb_knn2_device', 'tb_match_bf_cross_device', 'tb_search_by_bf_device',
+    'tb_match_bf_cross_host', 'tb_search_by_bf_host', 'tb_hamming_pairs_host',
     'tb_frontend_search_by_bf', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
     'tb_search_by_projection_map', 'tb_three_maxima',
 ]

@@ -284,6 +284,47 @@ extern "C" int tb_search_by_bf_device(tb_ctx *ctx, const void *d1, int n1, const
     return bf_single(ctx, d1, n1, d2, n2, 1, ratio, minTh, out, capacity, n);
 }
 
+static int bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int filter, float ratio, float minTh,
+                   tb_match *out, int capacity, int *n)
+{
+    if (!ctx || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
+    *n = 0;
+    if (n1 == 0 || n2 == 0) return TB_OK;
+    uint8_t *dd1 = nullptr, *dd2 = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&dd1, (size_t)32 * n1));
+    if (cudaMalloc(&dd2, (size_t)32 * n2) != cudaSuccess) { cudaFree(dd1); return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed"); }
+    cudaMemcpyAsync(dd1, d1, (size_t)32 * n1, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dd2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = bf_single(ctx, dd1, n1, dd2, n2, filter, ratio, minTh, out, capacity, n);
+    cudaFree(dd1); cudaFree(dd2);
+    return rc;
+}
+extern "C" int tb_match_bf_cross_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, tb_match *out, int capacity, int *n)
+{
+    return bf_host(ctx, d1, n1, d2, n2, 0, 0.f, 0.f, out, capacity, n);
+}
+extern "C" int tb_search_by_bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, float ratio, float minTh,
+                                    tb_match *out, int capacity, int *n)
+{
+    return bf_host(ctx, d1, n1, d2, n2, 1, ratio, minTh, out, capacity, n);
+}
+extern "C" int tb_hamming_pairs_host(tb_ctx *ctx, const uint8_t *a, const uint8_t *b, int n, int32_t *dist)
+{
+    if (!ctx || n < 0 || !dist) return TB_E_INVALID;
+    if (n == 0) return TB_OK;
+    uint8_t *da = nullptr, *db = nullptr; int *dd = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&da, (size_t)32 * n));
+    TB_CUDA(ctx, cudaMalloc(&db, (size_t)32 * n));
+    TB_CUDA(ctx, cudaMalloc(&dd, sizeof(int) * (size_t)n));
+    cudaMemcpyAsync(da, a, (size_t)32 * n, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(db, b, (size_t)32 * n, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = tb_hamming_pairs_device(ctx, da, db, n, dd);
+    if (!rc && cudaMemcpyAsync(dist, dd, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = TB_E_CUDA;
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = TB_E_CUDA;
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return rc;
+}
+
 // Batched searchByBF over frames of one extract result (called by frontend.cu).
 int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host,
                         const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,

@@ -1,0 +1,55 @@
+"""Multi-GPU partitioning of the path: one process per GPU.
+
+* frame streams / batches shard by FRAME with no data-path collective (extract + frame-to-frame or
+  projection matching are independent per frame pair);
+* large brute-force matching (BASELINE config 4) shards QUERY ROWS, the train set is replicated and the
+  per-row (argbest, best, second) triples are assembled with one all_gather — the only collective.
+Works with any torch.distributed backend: nccl on GPUs, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [lo, hi) of n items for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def frame_shards(n_frames, world):
+    return [shard_range(n_frames, r, world) for r in range(world)]
+
+
+def gather_rows(local, n_total, group=None):
+    """all_gather of row-sharded tensors (shard_range layout) into the full [n_total, ...] tensor."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [hi - lo for lo, hi in (shard_range(n_total, r, world) for r in range(world))]
+    assert local.shape[0] == sizes[rank], (local.shape, sizes, rank)
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+
+
+def sharded_knn2(ctx, q_dev, t_dev, group=None):
+    """Config 4 on GPUs: every rank holds the full Q and T on its device, computes best / second /
+    argbest for its query rows with the CUDA kernel and gathers. Returns full (idx, best, second)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = q_dev.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    m = hi - lo
+    idx = torch.empty(m, dtype=torch.int32, device=q_dev.device)
+    best = torch.empty_like(idx)
+    second = torch.empty_like(idx)
+    if m:
+        ctx.knn2_device(q_dev[lo:hi].data_ptr(), m, t_dev.data_ptr(), t_dev.shape[0], idx.data_ptr(), best.data_ptr(), second.data_ptr())
+    if world == 1:
+        return idx, best, second
+    packed = torch.stack([idx, best, second], 1)
+    full = gather_rows(packed, n, group)
+    return full[:, 0].contiguous(), full[:, 1].contiguous(), full[:, 2].contiguous()
