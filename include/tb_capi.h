@@ -129,6 +129,12 @@ int tb_frontend_results_device(const tb_frontend *fe, void **kps_dptr, void **de
 int tb_frontend_get_results(tb_frontend *fe, int frame, tb_keypoint *kps, uint8_t *desc, int capacity, int *n);
 /* D2H of all counts + packed results of frames [0,n_frames): kps/desc hold n_frames*capacity slots. */
 int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts);
+/* Pipelined variant: only enqueues the D2H copies on the ctx stream (use pinned host buffers) and
+ * returns at once; call tb_frontend_status (or tb_sync) before reading them. Lets one host thread keep
+ * two ctx/frontend pairs busy so that H2D of batch k+1 overlaps the kernels of batch k. */
+int tb_frontend_get_results_batch_async(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts);
+/* Synchronises the ctx stream and reports TB_E_CAPACITY if the last extract overflowed an internal buffer. */
+int tb_frontend_status(tb_frontend *fe);
 /* Stage outputs for stage-by-stage parity tests: FAST candidates of (frame, level) as keypoints
  * relative to the (16,16) border in the reference's vToDistributeKeys order (ORBextractor.cpp:743-804). */
 int tb_frontend_get_candidates(tb_frontend *fe, int frame, int level, tb_keypoint *out, int capacity, int *n);

@@ -26,7 +26,8 @@ EXPORTS = [
     'tb_frontend_create', 'tb_frontend_destroy', 'tb_frontend_kp_capacity', 'tb_frontend_level_layout',
     'tb_frontend_upload_level', 'tb_frontend_download_level', 'tb_frontend_upload_frames',
     'tb_frontend_build_pyramid', 'tb_frontend_extract', 'tb_frontend_results_device',
-    'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_candidates',
+    'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_results_batch_async',
+    'tb_frontend_status', 'tb_frontend_get_candidates',
     'tb_frontend_get_level_counts', 'tb_orb_extract_host',
     'tb_hamming_pairs_device', 'tb_knn2_device', 'tb_match_bf_cross_device', 'tb_search_by_bf_device',
     'tb_match_bf_cross_host', 'tb_search_by_bf_host', 'tb_hamming_pairs_host',
@@ -276,6 +277,13 @@ class Frontend:
         counts = np.zeros(n_frames, np.int32) if counts is None else counts
         self.ctx.check(lib().tb_frontend_get_results_batch(self.h, n_frames, _vp(kps), _vp(desc), self.kp_cap, _vp(counts)))
         return kps, desc, counts
+
+    def get_results_batch_async(self, n_frames, kps, desc, counts):
+        """Enqueue the D2H copies only (pinned numpy views); call status() before reading."""
+        self.ctx.check(lib().tb_frontend_get_results_batch_async(self.h, n_frames, _vp(kps), _vp(desc), self.kp_cap, _vp(counts)))
+
+    def status(self):
+        self.ctx.check(lib().tb_frontend_status(self.h))
 
     def get_candidates(self, frame, level):
         cap = int(self.level_w[level]) * int(self.level_h[level]) // 4 + 64

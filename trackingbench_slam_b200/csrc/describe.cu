@@ -10,15 +10,12 @@
 // ------------------------------------------------------------------------------------------
 // K5: cv::GaussianBlur 7x7 sigma=2 on 8U = OpenCV's fixed-point kernel {18,34,48,56,48,34,18}/256:
 // horizontal pass in 8.8 (u16, no rounding), vertical pass in 16.16, one rounding (v+32768)>>16,
-// BORDER_REFLECT_101.  Tile = 128x32 outputs per CTA; the (128+8)x(32+6) u8 source box is staged
-// in shared memory with 4-byte loads, the horizontal pass writes 4xu16 (8-byte) groups, the
-// vertical pass reads 7 such groups per 4 outputs and stores 4 bytes.  HBM traffic = 1 read +
-// 1 write per pixel (+ halo re-reads served by L2).
+// BORDER_REFLECT_101.  No shared memory: a thread owns one 4-pixel column group and walks GB_ROWS
+// output rows.  Per input row it loads its word and both neighbours (coalesced, L1 serves the overlap),
+// forms the 4 horizontal sums with byte permutes + two DP4A each, and keeps the last 7 rows of sums in
+// registers for the vertical pass.  HBM traffic = 1 read + 1 write per pixel (+ 6/GB_ROWS halo rows).
 // ------------------------------------------------------------------------------------------
-#define GB_TW 128
-#define GB_TH 32
-#define GB_INW (GB_TW + 8)   // bytes per staged row: [x0-4, x0+132)
-#define GB_INH (GB_TH + 6)
+#define GB_ROWS 64
 
 __device__ __forceinline__ int reflect101(int p, int len)
 {
@@ -27,74 +24,86 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
-__global__ void __launch_bounds__(256)
+struct W3 { uint32_t wm, w0, wp; };
+
+// the word holding pixels 4xw..4xw+3 of `row` and its two neighbours (reflected at the image border)
+__device__ __forceinline__ W3 gauss_load3(const uint8_t *__restrict__ row, int xw, int w)
+{
+    W3 r;
+    const int x = 4 * xw;
+    if (x >= 4 && x + 8 <= w) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
+        r.wm = __ldg(p - 1); r.w0 = __ldg(p); r.wp = __ldg(p + 1);
+    } else {
+        r.wm = r.w0 = r.wp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            r.wm |= (uint32_t)row[reflect101(x - 4 + k, w)] << (8 * k);
+            r.w0 |= (uint32_t)row[reflect101(x + k, w)] << (8 * k);
+            r.wp |= (uint32_t)row[reflect101(x + 4 + k, w)] << (8 * k);
+        }
+    }
+    return r;
+}
+
+// horizontal 7-tap sums of the 4 pixels of the middle word (u16 range, exact)
+__device__ __forceinline__ void gauss_hrow(const W3 a, uint32_t h[4])
+{
+    const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps -3..0
+    const uint32_t KB = 48u | (34u << 8) | (18u << 16);                 // taps +1..+3
+    h[0] = __dp4a(__byte_perm(a.wm, a.w0, 0x4321), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x4321), KB, 0u));
+    h[1] = __dp4a(__byte_perm(a.wm, a.w0, 0x5432), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x5432), KB, 0u));
+    h[2] = __dp4a(__byte_perm(a.wm, a.w0, 0x6543), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x6543), KB, 0u));
+    h[3] = __dp4a(a.w0, KA, __dp4a(a.wp, KB, 0u));
+}
+
+__global__ void __launch_bounds__(128)
 gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride)
 {
-    __shared__ __align__(16) uint8_t in[GB_INH][GB_INW];
-    __shared__ __align__(16) uint16_t hs[GB_INH][GB_TW];
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * GB_TW, y0 = blockIdx.y * GB_TH;
+    const int xw = blockIdx.x * 128 + threadIdx.x;
+    if (4 * xw >= w) return;
+    const int y0 = blockIdx.y * GB_ROWS;
+    const int ny = min(GB_ROWS, h - y0);
     const uint8_t *s = src + (size_t)blockIdx.z * frame_stride;
     uint8_t *d = dst + (size_t)blockIdx.z * frame_stride;
-
-    // stage: word ww of row rr covers x in [x0-4+4ww, x0+4ww)
-    for (int i = tid; i < GB_INH * (GB_INW / 4); i += 256) {
-        int rr = i / (GB_INW / 4), ww = i - rr * (GB_INW / 4);
-        int sy = reflect101(y0 - 3 + rr, h);
-        int xs = x0 - 4 + 4 * ww;
-        uint32_t v;
-        if (xs >= 0 && xs + 3 < w) {
-            v = __ldg(reinterpret_cast<const uint32_t *>(s + (size_t)sy * pitch + xs));
-        } else {
-            v = 0;
+    uint32_t win[7][4];
+    // input rows y0-3 .. y0+ny+2; output row (r-6) is ready once input row r is in the window.
+    // Each chunk first issues the loads of its 7 rows (21 independent requests per thread), then computes.
+    for (int base = 0; base < ny + 6; base += 7) {
+        W3 in[7];
 #pragma unroll
-            for (int k = 0; k < 4; k++) v |= (uint32_t)s[(size_t)sy * pitch + reflect101(xs + k, w)] << (8 * k);
+        for (int k = 0; k < 7; k++) {
+            const int r = min(base + k, ny + 5);
+            in[k] = gauss_load3(s + (size_t)reflect101(y0 - 3 + r, h) * pitch, xw, w);
         }
-        *reinterpret_cast<uint32_t *>(&in[rr][4 * ww]) = v;
-    }
-    __syncthreads();
-    // horizontal: item = (row rr, group g of 4 outputs); output x0+4g+k needs bytes 4g+1+k .. 4g+7+k
-    for (int i = tid; i < GB_INH * (GB_TW / 4); i += 256) {
-        int rr = i / (GB_TW / 4), g = i - rr * (GB_TW / 4);
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(&in[rr][4 * g]);
-        uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        int b[12];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xFF; b[4 + k] = (w1 >> (8 * k)) & 0xFF; b[8 + k] = (w2 >> (8 * k)) & 0xFF; }
-        uint32_t o[4];
+        for (int k = 0; k < 7; k++) {
+            const int r = base + k;
+            if (r < ny + 6) {
+                gauss_hrow(in[k], win[k]);
+                if (r >= 6) {
+                    // window rows oldest..newest = win[(k+1)%7] .. win[k]
+                    uint32_t out = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            o[k] = 18 * (b[k + 1] + b[k + 7]) + 34 * (b[k + 2] + b[k + 6]) + 48 * (b[k + 3] + b[k + 5]) + 56 * b[k + 4];
-        uint2 pk = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-        *reinterpret_cast<uint2 *>(&hs[rr][4 * g]) = pk;
-    }
-    __syncthreads();
-    // vertical
-    for (int i = tid; i < GB_TH * (GB_TW / 4); i += 256) {
-        int yy = i / (GB_TW / 4), g = i - yy * (GB_TW / 4);
-        int x = x0 + 4 * g, y = y0 + yy;
-        if (x >= w || y >= h) continue;
-        uint32_t acc[4] = {0, 0, 0, 0};
-        const int K[7] = {18, 34, 48, 56, 48, 34, 18};
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            uint2 v = *reinterpret_cast<const uint2 *>(&hs[yy + j][4 * g]);
-            acc[0] += K[j] * (v.x & 0xFFFF); acc[1] += K[j] * (v.x >> 16);
-            acc[2] += K[j] * (v.y & 0xFFFF); acc[3] += K[j] * (v.y >> 16);
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t v = 18u * (win[(k + 1) % 7][j] + win[k][j]) + 34u * (win[(k + 2) % 7][j] + win[(k + 6) % 7][j]) +
+                                           48u * (win[(k + 3) % 7][j] + win[(k + 5) % 7][j]) + 56u * win[(k + 4) % 7][j];
+                        out |= ((v + 32768u) >> 16) << (8 * j);
+                    }
+                    const int y = y0 + r - 6, x = 4 * xw;
+                    if (x + 3 < w) *reinterpret_cast<uint32_t *>(d + (size_t)y * pitch + x) = out;
+                    else for (int j = 0; j < 4 && x + j < w; j++) d[(size_t)y * pitch + x + j] = (uint8_t)(out >> (8 * j));
+                }
+            }
         }
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) out |= ((acc[k] + 32768u) >> 16) << (8 * k);
-        if (x + 3 < w) *reinterpret_cast<uint32_t *>(d + (size_t)y * pitch + x) = out;
-        else for (int k = 0; k < 4 && x + k < w; k++) d[(size_t)y * pitch + x + k] = (uint8_t)(out >> (8 * k));
     }
 }
 
 int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
 {
     ProfScope prof__(ctx, "gauss7x7_u8");
-    dim3 grid(div_up(w, GB_TW), div_up(h, GB_TH), n_frames);
-    gauss7x7_u8<<<grid, 256, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
+    dim3 grid(div_up(div_up(w, 4), 128), div_up(h, GB_ROWS), n_frames);
+    gauss7x7_u8<<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }

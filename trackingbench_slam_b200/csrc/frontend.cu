@@ -101,6 +101,7 @@ struct tb_frontend {
     uint8_t *pyr[TB_MAX_LEVELS] = {}, *blur[TB_MAX_LEVELS] = {};
     int4 *xtab[TB_MAX_LEVELS] = {}, *ytab[TB_MAX_LEVELS] = {};
     bool area2[TB_MAX_LEVELS] = {};
+    int box_pitch[TB_MAX_LEVELS] = {}, box_rows[TB_MAX_LEVELS] = {};   // K1 shared-memory source box
     uint32_t *cand[TB_MAX_LEVELS] = {}, *kept[TB_MAX_LEVELS] = {};
     uint16_t *nid[TB_MAX_LEVELS] = {};
     int *n_cand = nullptr, *n_kept = nullptr, *n_kp = nullptr, *overflow = nullptr;
@@ -182,6 +183,7 @@ extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, 
             std::vector<ResizeTab> tx, ty; std::vector<int32_t> x1, y1;
             tb_build_resize_tab(lw[l - 1], lw[l], true, tx, x1);
             tb_build_resize_tab(lh[l - 1], lh[l], false, ty, y1);
+            tb_resize_box(tx, x1, ty, y1, &fe->box_pitch[l], &fe->box_rows[l]);
             std::vector<int4> hx(lw[l]), hy(lh[l]);
             for (int i = 0; i < lw[l]; i++) hx[i] = make_int4(tx[i].ofs, x1[i], tx[i].c0, tx[i].c1);
             for (int i = 0; i < lh[l]; i++) hy[i] = make_int4(ty[i].ofs, y1[i], ty[i].c0, ty[i].c1);
@@ -256,7 +258,7 @@ extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
     for (int l = 1; l < fe->L; l++) {
         const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
         int rc = tb_launch_resize(fe->ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
-                                  d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames);
+                                  d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames, fe->box_pitch[l], fe->box_rows[l]);
         if (rc) return rc;
     }
     return TB_OK;
@@ -406,6 +408,26 @@ extern "C" int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_k
     if (rc) return rc;
     for (int f = 0; f < n_frames; f++) if (counts[f] > capacity) return tb_fail(ctx, TB_E_CAPACITY, "keypoint output capacity too small");
     return TB_OK;
+}
+
+extern "C" int tb_frontend_get_results_batch_async(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
+{
+    if (!fe || n_frames < 0 || n_frames > fe->B || !counts || capacity < 0) return TB_E_INVALID;
+    tb_ctx *ctx = fe->ctx;
+    if (n_frames == 0) return TB_OK;
+    const int m = capacity < fe->kp_cap ? capacity : fe->kp_cap;
+    TB_CUDA(ctx, cudaMemcpyAsync(counts, fe->n_kp, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kps) TB_CUDA(ctx, cudaMemcpy2DAsync(kps, sizeof(tb_keypoint) * capacity, fe->kps, sizeof(tb_keypoint) * fe->kp_cap,
+                                            sizeof(tb_keypoint) * m, n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) TB_CUDA(ctx, cudaMemcpy2DAsync(desc, (size_t)32 * capacity, fe->desc, (size_t)32 * fe->kp_cap, (size_t)32 * m, n_frames,
+                                             cudaMemcpyDeviceToHost, ctx->stream));
+    return TB_OK;
+}
+
+extern "C" int tb_frontend_status(tb_frontend *fe)
+{
+    if (!fe) return TB_E_INVALID;
+    return check_overflow(fe);
 }
 
 extern "C" int tb_frontend_get_level_counts(tb_frontend *fe, int frame, int32_t *n_per_level)

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 
 
 static inline int cv_floor_f(float v) { int i = (int)v; return i - (v < (float)i); }
@@ -51,36 +52,85 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh)
 }
 
 // xtab: int4 per output column {ofs0, ofs1, c0, c1}; ytab likewise.
+// One CTA produces a PYR_TW x PYR_TH output tile.  The source box it needs (rows ytab[first].x ..
+// ytab[last].y, columns xtab[first].x .. xtab[last].y) is staged in shared memory with 16-byte loads
+// that are all issued before any arithmetic (memory-level parallelism: the kernel is HBM-latency bound
+// otherwise); a thread then owns 4 output columns x 4 consecutive output rows, keeps its 4 column
+// entries in registers and reuses the horizontal interpolation of a source row shared by two
+// consecutive output rows.  Every source byte is read from HBM once, every output byte written once.
+#define PYR_TW 256
+#define PYR_TH 16
+extern __shared__ __align__(16) uint8_t pyr_smem[];
+
 __global__ void __launch_bounds__(256)
 pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
                      uint8_t *__restrict__ dst, int dpitch, size_t dframe,
-                     int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
+                     int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bp)
 {
-    const int dx0 = (blockIdx.x * 64 + threadIdx.x) * 4;
-    const int dy = blockIdx.y * 4 + threadIdx.y;
-    if (dx0 >= dw || dy >= dh) return;
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+    const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
     const uint8_t *s = src + (size_t)blockIdx.z * sframe;
     uint8_t *d = dst + (size_t)blockIdx.z * dframe;
-    const int4 yt = __ldg(&ytab[dy]);
-    const uint8_t *r0 = s + (size_t)yt.x * spitch;
-    const uint8_t *r1 = s + (size_t)yt.y * spitch;
-    uint32_t out = 0;
+    // source box (tables are monotone)
+    const int sx_lo = __ldg(&xtab[tx0]).x & ~15, sx_hi = __ldg(&xtab[tx1]).y;
+    const int sy_lo = __ldg(&ytab[ty0]).x, sy_hi = __ldg(&ytab[ty1]).y;
+    const int bw16 = (sx_hi - sx_lo + 16) >> 4, bh = sy_hi - sy_lo + 1;
+    for (int i = tid; i < bw16 * bh; i += 256) {
+        const int r = i / bw16, c = i - r * bw16;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(sy_lo + r) * spitch + sx_lo) + c);
+        *reinterpret_cast<uint4 *>(pyr_smem + r * bp + 16 * c) = v;
+    }
+    __syncthreads();
+    const int dx0 = tx0 + threadIdx.x * 4;
+    const int dy0 = ty0 + threadIdx.y * 4;
+    if (dx0 > tx1 || dy0 > ty1) return;
+    int4 xt[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int dx = dx0 + k;
-        if (dx < dw) {
-            const int4 xt = __ldg(&xtab[dx]);
-            int h0 = (int)r0[xt.x] * xt.z + (int)r0[xt.y] * xt.w;
-            int h1 = (int)r1[xt.x] * xt.z + (int)r1[xt.y] * xt.w;
-            int v = (((yt.z * (h0 >> 4)) >> 16) + ((yt.w * (h1 >> 4)) >> 16) + 2) >> 2;
+    for (int k = 0; k < 4; k++) { xt[k] = __ldg(&xtab[min(dx0 + k, dw - 1)]); xt[k].x -= sx_lo; xt[k].y -= sx_lo; }
+    int prev_row = -1;
+    int hprev[4] = {0, 0, 0, 0};
+    const int dy1 = min(dy0 + 4, dh);
+    for (int dy = dy0; dy < dy1; dy++) {
+        const int4 yt = __ldg(&ytab[dy]);
+        int h0[4], h1[4];
+        if (yt.x == prev_row) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) h0[k] = hprev[k];
+        } else {
+            const uint8_t *r0 = pyr_smem + (yt.x - sy_lo) * bp;
+#pragma unroll
+            for (int k = 0; k < 4; k++) h0[k] = (int)r0[xt[k].x] * xt[k].z + (int)r0[xt[k].y] * xt[k].w;
+        }
+        const uint8_t *r1 = pyr_smem + (yt.y - sy_lo) * bp;
+#pragma unroll
+        for (int k = 0; k < 4; k++) h1[k] = (int)r1[xt[k].x] * xt[k].z + (int)r1[xt[k].y] * xt[k].w;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int v = (((yt.z * (h0[k] >> 4)) >> 16) + ((yt.w * (h1[k] >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 0xFF) << (8 * k);
+            hprev[k] = h1[k];
+        }
+        prev_row = yt.y;
+        if (dx0 + 3 < dw) {
+            *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
+        } else {
+            for (int k = 0; k < 4 && dx0 + k < dw; k++) d[(size_t)dy * dpitch + dx0 + k] = (uint8_t)(out >> (8 * k));
         }
     }
-    if (dx0 + 3 < dw) {
-        *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
-    } else {
-        for (int k = 0; k < 4 && dx0 + k < dw; k++) d[(size_t)dy * dpitch + dx0 + k] = (uint8_t)(out >> (8 * k));
-    }
+}
+
+// Host: shared-memory box (pitch, rows) needed by the worst tile of a level.
+void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
+                   const std::vector<int32_t> &y1, int *bp, int *bh)
+{
+    int mw = 0, mh = 0;
+    const int dw = (int)tx.size(), dh = (int)ty.size();
+    for (int a = 0; a < dw; a += PYR_TW) { int b = std::min(a + PYR_TW, dw) - 1; mw = std::max(mw, x1[b] - (tx[a].ofs & ~15) + 16); }
+    for (int a = 0; a < dh; a += PYR_TH) { int b = std::min(a + PYR_TH, dh) - 1; mh = std::max(mh, y1[b] - ty[a].ofs + 1); }
+    *bp = ((mw + 15) & ~15) + 16;
+    *bh = mh;
 }
 
 // Exact 2x: OpenCV switches INTER_LINEAR to INTER_AREA (2x2 mean with rounding).
@@ -97,15 +147,19 @@ pyr_resize_area2_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 }
 
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
-                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames)
+                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh)
 {
     ProfScope prof__(ctx, "pyr_resize");
     if (area2) {
         dim3 grid(div_up(dw, 64), div_up(dh, 4), n_frames), block(64, 4);
         pyr_resize_area2_u8<<<grid, block, 0, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh);
     } else {
-        dim3 grid(div_up(dw, 256), div_up(dh, 4), n_frames), block(64, 4);
-        pyr_resize_linear_u8<<<grid, block, 0, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh, xtab, ytab);
+        const size_t smem = (size_t)bp * bh;
+        if (smem > 200 * 1024) return tb_fail(ctx, TB_E_UNSUPPORTED, "resize: scale factor too small for the shared-memory tile");
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), n_frames), block(64, 4);
+        pyr_resize_linear_u8<<<grid, block, smem, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh, xtab, ytab, bp);
     }
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
