@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--height', type=int, default=1080)
     ap.add_argument('--cpu-sample', type=int, default=0, help='frames in the CPU-baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--match-impl', default='tc', choices=['popc', 'tc'], help='brute-force matcher kernel: LOP3+POPC or tcgen05 int8')
     ap.add_argument('--profile-out', default='', help='write the per-kernel time table (JSON) here')
     return ap.parse_args()
 
@@ -171,6 +172,7 @@ def run_ours(a):
     stream = torch.cuda.Stream()   # a real (non-NULL) stream handle: the ctx launches on it, the events time it
     torch.cuda.set_stream(stream)
     ctx = tb.Context(local_rank, stream.cuda_stream)
+    ctx.set_match_impl(1 if a.match_impl == 'tc' else 0)
     sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
     fe = tb.Frontend(ctx, lw, lh, max_batch=B, max_target=tgt)
     cap = fe.kp_cap
@@ -234,6 +236,7 @@ def run_ours(a):
     for k in range(2):
         st = torch.cuda.Stream()
         c2 = tb.Context(local_rank, st.cuda_stream)
+        c2.set_match_impl(1 if a.match_impl == 'tc' else 0)
         f2 = tb.Frontend(c2, lw, lh, max_batch=B, max_target=tgt)
         slots.append(dict(stream=st, ctx=c2, fe=f2,
                           matches=torch.zeros((max(P, 1), cap, 4), dtype=torch.int32, device='cuda'),
@@ -330,7 +333,7 @@ def run_ours(a):
                 'config': {'workload': workload_name(a), 'levels': 8, 'scale': 1.2, 'fast_th': [20, 7], 'frames_per_gpu': B,
                            'sharding': 'frame streams, %d rank(s), no collective' % world,
                            'l2': 'inputs (%.0f MB of frames per step) exceed the 126 MB L2' % (B * W * H / 1e6),
-                           'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches},
+                           'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches, 'match_impl': a.match_impl},
                 'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
                 'per_kernel_ms': {k: round(v['ms'], 3) for k, v in table.items()}}

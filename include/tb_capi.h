@@ -175,6 +175,10 @@ int tb_search_by_bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *
                          float ratio, float minTh, tb_match *out, int capacity, int *n);
 int tb_hamming_pairs_host(tb_ctx *ctx, const uint8_t *a, const uint8_t *b, int n, int32_t *dist);
 
+/* Implementation of the batched brute-force nearest-neighbour search: 0 = LOP3+POPC kernel,
+ * 1 = exact +-1 int8 tcgen05 MMA formulation (hamming = (256 - dot)/2). Results are identical. */
+int tb_set_match_impl(tb_ctx *ctx, int impl);
+
 /* Batched searchByBF over frame pairs of one frontend's last extract: pair p matches frame
  * q_frames[p] (query/F1) against t_frames[p] (train/F2). Outputs on the device:
  * matches_dptr[p*capacity + i], counts_dptr[p]. No host synchronisation. */

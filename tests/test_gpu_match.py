@@ -207,3 +207,35 @@ def test_features_in_area_vs_oracle(tb, ctx, oracle):
             got = ctx.features_in_area(k, cols, rows, x, y, r, int(lo), int(hi))
             exp = oracle.features_in_area(k, cols, rows, x, y, r, int(lo), int(hi))
             assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+def test_batched_bf_popc_and_tcgen05_agree_with_oracle(tb, ctx, oracle, images, impl):
+    """K7 (LOP3+POPC) and K8 (tcgen05 int8, hamming = (256 - dot)/2) must give identical bytes."""
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = 5, 0.8, 700, 40.0, 15.0
+    frames = np.stack([synth_frame(k, 640, 360) for k in range(4)] + [np.full((360, 640), 90, np.uint8)])   # last frame: no keypoints
+    sf, lw, lh = tb.pyramid_geometry(640, 360, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=5, max_target=tgt)
+    try:
+        ctx.set_match_impl(impl)
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(5)
+        fe.extract(5, sf, tgt, a, b)
+        cap = fe.kp_cap
+        pairs = [(0, 1), (1, 2), (3, 2), (0, 4), (4, 1), (2, 2)]
+        m = torch.zeros((len(pairs), cap, 4), dtype=torch.int32, device='cuda')
+        c = torch.zeros(len(pairs), dtype=torch.int32, device='cuda')
+        fe.search_by_bf([p[0] for p in pairs], [p[1] for p in pairs], 3.0, 60.0, m.data_ptr(), cap, c.data_ptr())
+        ctx.sync()
+        kps, desc, counts = fe.get_results_batch(5)
+        assert counts[4] == 0 and counts[0] > 300
+        cn = c.cpu().numpy()
+        mm = m.cpu().numpy().view(np.uint8).reshape(len(pairs), cap, 16)
+        for p, (qf, tf) in enumerate(pairs):
+            exp = oracle.search_by_bf(desc[qf, :counts[qf]], desc[tf, :counts[tf]], 3.0, 60.0)
+            assert cn[p] == len(exp), (impl, p)
+            assert mm[p, :cn[p]].tobytes() == exp.tobytes(), (impl, p)
+    finally:
+        ctx.set_match_impl(0)
+        fe.close()

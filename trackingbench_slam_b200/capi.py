@@ -21,7 +21,7 @@ TB_MAX_LEVELS = 16
 # every symbol include/tb_capi.h declares (tests check that the library exports all of them)
 EXPORTS = [
     'tb_ctx_create', 'tb_ctx_destroy', 'tb_sync', 'tb_last_error', 'tb_version', 'tb_launch_count',
-    'tb_profile_enable', 'tb_profile_report',
+    'tb_profile_enable', 'tb_profile_report', 'tb_set_match_impl',
     'tb_pyramid_geometry',
     'tb_frontend_create', 'tb_frontend_destroy', 'tb_frontend_kp_capacity', 'tb_frontend_level_layout',
     'tb_frontend_upload_level', 'tb_frontend_download_level', 'tb_frontend_upload_frames',
@@ -107,6 +107,10 @@ class Context:
 
     def launch_count(self):
         return lib().tb_launch_count(self.h)
+
+    def set_match_impl(self, impl):
+        """0 = LOP3+POPC (K7), 1 = tcgen05 int8 (K8)."""
+        self.check(lib().tb_set_match_impl(self.h, int(impl)))
 
     def profile_enable(self, on=True):
         self.check(lib().tb_profile_enable(self.h, int(on)))

@@ -20,6 +20,8 @@ struct tb_ctx {
     int64_t launches = 0;
     std::string err;
     struct MatchWs *mws = nullptr;   // lazily grown matching workspace (match.cu)
+    struct TcWs *tcws = nullptr;     // tensor-core matcher workspace (match_tc.cu)
+    int match_impl = 0;              // 0 = LOP3+POPC (K7), 1 = tcgen05 int8 (K8)
     // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
     bool profiling = false;
     struct ProfEvt { const char *name; cudaEvent_t a, b; };
@@ -40,6 +42,7 @@ struct ProfScope {
     ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream); }
 };
 void tb_match_ws_free(tb_ctx *ctx);
+void tb_match_tc_free(tb_ctx *ctx);
 
 static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "")
 {

@@ -34,6 +34,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     tb_match_ws_free(ctx);
+    tb_match_tc_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -45,6 +46,14 @@ extern "C" int tb_sync(tb_ctx *ctx)
 }
 extern "C" const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int64_t tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// 0 = LOP3+POPC kernel (K7), 1 = tcgen05 int8 +-1 formulation (K8) for the batched brute-force matcher.
+extern "C" int tb_set_match_impl(tb_ctx *ctx, int impl)
+{
+    if (!ctx || (impl != 0 && impl != 1)) return TB_E_INVALID;
+    ctx->match_impl = impl;
+    return TB_OK;
+}
 
 extern "C" int tb_profile_enable(tb_ctx *ctx, int on)
 {
@@ -485,6 +494,6 @@ extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int3
     if (!fe || n_pairs < 0 || !q_frames || !t_frames || !matches || !counts) return TB_E_INVALID;
     for (int p = 0; p < n_pairs; p++)
         if (q_frames[p] < 0 || q_frames[p] >= fe->B || t_frames[p] < 0 || t_frames[p] >= fe->B) return TB_E_INVALID;
-    return tb_match_bf_batched(fe->ctx, n_pairs, q_frames, t_frames, fe->desc, (size_t)fe->kp_cap * 32, fe->n_kp, fe->kp_cap,
+    return tb_match_bf_batched(fe->ctx, n_pairs, q_frames, t_frames, fe->B, fe->desc, (size_t)fe->kp_cap * 32, fe->n_kp, fe->kp_cap,
                                ratio, minTh, (tb_match *)matches, capacity, (int *)counts);
 }

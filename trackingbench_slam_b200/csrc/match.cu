@@ -11,6 +11,8 @@
 // broadcast), so the inner loop is 8 LOP3(xor) + 8 POPC + adds per pair and nothing else.
 // Ties are broken by lowest train index (strict < while scanning in index order).
 #include "common.cuh"
+#include "kernels.cuh"
+#include <cstdlib>
 
 #define KNN_THREADS 128
 #define KNN_TILE 128
@@ -326,7 +328,7 @@ extern "C" int tb_hamming_pairs_host(tb_ctx *ctx, const uint8_t *a, const uint8_
 }
 
 // Batched searchByBF over frames of one extract result (called by frontend.cu).
-int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host,
+int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host, int n_frames_total,
                         const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,
                         float ratio, float minTh, tb_match *matches, int capacity, int *out_counts)
 {
@@ -344,13 +346,24 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
     TB_CUDA(ctx, cudaMemcpyAsync(w.frames + n_pairs, t_frames_host, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     build_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w.pairs, n_pairs, w.frames, w.frames + n_pairs, desc, frame_stride, counts);
     TB_LAUNCH_CHECK(ctx);
-    dim3 grid(div_up(kp_cap, KNN_THREADS), 2 * n_pairs);
-    {
+    if (ctx->match_impl == 1) {
+        rc = tb_match_knn_tc(ctx, n_pairs, w.frames, w.frames + n_pairs, n_frames_total, desc, frame_stride, counts, kp_cap, w.best_idx, w.best_dist);
+        if (rc) return rc;
+    } else {
+        dim3 grid(div_up(kp_cap, KNN_THREADS), 2 * n_pairs);
         ProfScope prof__(ctx, "hamming_knn");
         hamming_knn<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, kp_cap, w.best_idx, w.best_dist, nullptr);
+        TB_LAUNCH_CHECK(ctx);
     }
-    TB_LAUNCH_CHECK(ctx);
     ProfScope prof2__(ctx, "bf_cross_filter");
+    if (const char *dump = getenv("TB_DUMP_KNN")) {   // developer aid: raw nearest-neighbour tables of both implementations
+        std::vector<int> hi((size_t)2 * n_pairs * kp_cap), hd((size_t)2 * n_pairs * kp_cap);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hi.data(), w.best_idx, hi.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hd.data(), w.best_dist, hd.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        std::string fn = std::string(dump) + (ctx->match_impl ? ".tc" : ".popc");
+        if (FILE *fp = fopen(fn.c_str(), "wb")) { fwrite(hi.data(), sizeof(int), hi.size(), fp); fwrite(hd.data(), sizeof(int), hd.size(), fp); fclose(fp); }
+    }
     bf_cross_filter<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, n_pairs, kp_cap, w.best_idx, w.best_dist, w.scratch, 1, ratio, minTh,
                                                       matches, capacity, out_counts);
     TB_LAUNCH_CHECK(ctx);
