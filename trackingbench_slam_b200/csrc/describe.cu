@@ -26,26 +26,6 @@ __device__ __forceinline__ int reflect101(int p, int len)
 
 struct W3 { uint32_t wm, w0, wp; };
 
-// the word holding pixels 4xw..4xw+3 of `row` and its two neighbours (reflected at the image border)
-__device__ __forceinline__ W3 gauss_load3(const uint8_t *__restrict__ row, int xw, int w)
-{
-    W3 r;
-    const int x = 4 * xw;
-    if (x >= 4 && x + 8 <= w) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
-        r.wm = __ldg(p - 1); r.w0 = __ldg(p); r.wp = __ldg(p + 1);
-    } else {
-        r.wm = r.w0 = r.wp = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            r.wm |= (uint32_t)row[reflect101(x - 4 + k, w)] << (8 * k);
-            r.w0 |= (uint32_t)row[reflect101(x + k, w)] << (8 * k);
-            r.wp |= (uint32_t)row[reflect101(x + 4 + k, w)] << (8 * k);
-        }
-    }
-    return r;
-}
-
 // horizontal 7-tap sums of the 4 pixels of the middle word (u16 range, exact)
 __device__ __forceinline__ void gauss_hrow(const W3 a, uint32_t h[4])
 {
@@ -57,15 +37,29 @@ __device__ __forceinline__ void gauss_hrow(const W3 a, uint32_t h[4])
     h[3] = __dp4a(a.w0, KA, __dp4a(a.wp, KB, 0u));
 }
 
+// BORDER = false: word columns whose 12-byte neighbourhood lies inside the row (plain 4-byte loads).
+// BORDER = true : the first word column and the last ones (per-byte reflected gather); a tiny second launch.
+// xw_first / n_xw select the word columns this launch covers.
+template <bool BORDER>
 __global__ void __launch_bounds__(128)
-gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride)
+gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride,
+            int xw_lo, int xw_hi)   // interior word columns are [xw_lo, xw_hi); the border launch takes the rest
 {
-    const int xw = blockIdx.x * 128 + threadIdx.x;
-    if (4 * xw >= w) return;
+    int xw;
+    if (!BORDER) {
+        xw = xw_lo + blockIdx.x * 128 + threadIdx.x;
+        if (xw >= xw_hi) return;
+    } else {
+        const int nwords = (w + 3) >> 2, nb = xw_lo + (nwords - xw_hi);   // border columns: [0,xw_lo) and [xw_hi,nwords)
+        const int i = blockIdx.x * 128 + threadIdx.x;
+        if (i >= nb) return;
+        xw = i < xw_lo ? i : xw_hi + (i - xw_lo);
+    }
     const int y0 = blockIdx.y * GB_ROWS;
     const int ny = min(GB_ROWS, h - y0);
     const uint8_t *s = src + (size_t)blockIdx.z * frame_stride;
     uint8_t *d = dst + (size_t)blockIdx.z * frame_stride;
+    const int x = 4 * xw;
     uint32_t win[7][4];
     // input rows y0-3 .. y0+ny+2; output row (r-6) is ready once input row r is in the window.
     // Each chunk first issues the loads of its 7 rows (21 independent requests per thread), then computes.
@@ -73,8 +67,22 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
         W3 in[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            const int r = min(base + k, ny + 5);
-            in[k] = gauss_load3(s + (size_t)reflect101(y0 - 3 + r, h) * pitch, xw, w);
+            int yy = y0 - 3 + min(base + k, ny + 5);
+            yy = yy < 0 ? -yy : yy;                      // REFLECT_101 (h >= 4 guaranteed by the launcher)
+            yy = yy >= h ? 2 * (h - 1) - yy : yy;
+            const uint8_t *row = s + (size_t)yy * pitch;
+            if (!BORDER) {
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
+                in[k].wm = __ldg(p - 1); in[k].w0 = __ldg(p); in[k].wp = __ldg(p + 1);
+            } else {
+                in[k].wm = in[k].w0 = in[k].wp = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    in[k].wm |= (uint32_t)row[reflect101(x - 4 + b, w)] << (8 * b);
+                    in[k].w0 |= (uint32_t)row[reflect101(x + b, w)] << (8 * b);
+                    in[k].wp |= (uint32_t)row[reflect101(x + 4 + b, w)] << (8 * b);
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < 7; k++) {
@@ -90,8 +98,8 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
                                            48u * (win[(k + 3) % 7][j] + win[(k + 5) % 7][j]) + 56u * win[(k + 4) % 7][j];
                         out |= ((v + 32768u) >> 16) << (8 * j);
                     }
-                    const int y = y0 + r - 6, x = 4 * xw;
-                    if (x + 3 < w) *reinterpret_cast<uint32_t *>(d + (size_t)y * pitch + x) = out;
+                    const int y = y0 + r - 6;
+                    if (!BORDER || x + 3 < w) *reinterpret_cast<uint32_t *>(d + (size_t)y * pitch + x) = out;
                     else for (int j = 0; j < 4 && x + j < w; j++) d[(size_t)y * pitch + x + j] = (uint8_t)(out >> (8 * j));
                 }
             }
@@ -99,12 +107,45 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
     }
 }
 
+// Images with fewer than 4 rows (never a pyramid level in practice): generic per-pixel version.
+__global__ void gauss7x7_u8_tiny(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *s = src + (size_t)blockIdx.z * frame_stride;
+    const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    uint32_t acc = 0;
+    for (int j = 0; j < 7; j++) {
+        const uint8_t *row = s + (size_t)reflect101(y + j - 3, h) * pitch;
+        uint32_t hs = 0;
+        for (int i = 0; i < 7; i++) hs += K[i] * row[reflect101(x + i - 3, w)];
+        acc += K[j] * hs;
+    }
+    dst[(size_t)blockIdx.z * frame_stride + (size_t)y * pitch + x] = (uint8_t)((acc + 32768u) >> 16);
+}
+
 int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
 {
     ProfScope prof__(ctx, "gauss7x7_u8");
-    dim3 grid(div_up(div_up(w, 4), 128), div_up(h, GB_ROWS), n_frames);
-    gauss7x7_u8<<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
-    TB_LAUNCH_CHECK(ctx);
+    if (h < 4 || w < 16) {
+        dim3 grid(div_up(w, 128), h, n_frames);
+        gauss7x7_u8_tiny<<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
+        TB_LAUNCH_CHECK(ctx);
+        return TB_OK;
+    }
+    // interior word columns: 4*xw >= 4 and 4*xw + 8 <= w
+    const int nwords = (w + 3) >> 2, xw_lo = 1, xw_hi = (w - 8) / 4 + 1;
+    {
+        dim3 grid(div_up(xw_hi - xw_lo, 128), div_up(h, GB_ROWS), n_frames);
+        gauss7x7_u8<false><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    {
+        const int nb = xw_lo + (nwords - xw_hi);
+        dim3 grid(div_up(nb, 128), div_up(h, GB_ROWS), n_frames);
+        gauss7x7_u8<true><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        TB_LAUNCH_CHECK(ctx);
+    }
     return TB_OK;
 }
 
