@@ -73,10 +73,35 @@ __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t c, uint32
     const uint32_t ad = __vabsdiffu4(ring, c);
     return ((ad & 0x7f7f7f7fu) + K) | ad;
 }
+// ring > centre per byte (unsigned), result in bit 7; clow = centre & 0x7f7f7f7f
+__device__ __forceinline__ uint32_t byte_gt(uint32_t ring, uint32_t c, uint32_t clow)
+{
+    const uint32_t t = (ring | 0x80808080u) - clow;            // bit 7: low 7 bits of ring >= those of centre
+    return (ring & ~c) | (~(ring ^ c) & t);                     // msb decides, else the low bits (ring != centre where used)
+}
+// compass test for one word of 4 centres: two ADJACENT compass pixels both brighter by > T or both darker by > T
+__device__ __forceinline__ uint32_t compass_signed(uint32_t n, uint32_t s_, uint32_t e, uint32_t w_, uint32_t c, uint32_t K)
+{
+    const uint32_t clow = c & 0x7f7f7f7fu;
+    const uint32_t aN = absdiff_gt(n, c, K), aS = absdiff_gt(s_, c, K), aE = absdiff_gt(e, c, K), aW = absdiff_gt(w_, c, K);
+    const uint32_t gN = byte_gt(n, c, clow), gS = byte_gt(s_, c, clow), gE = byte_gt(e, c, clow), gW = byte_gt(w_, c, clow);
+    const uint32_t bright = ((aN & gN) | (aS & gS)) & ((aE & gE) | (aW & gW));
+    const uint32_t dark = ((aN & ~gN) | (aS & ~gS)) & ((aE & ~gE) | (aW & ~gW));
+    return bright | dark;
+}
 
 // i / n for small i via multiply-high; magic = 2^32/n rounded up (n == 1 has no 32-bit magic)
 __device__ __forceinline__ uint32_t div_magic(int n) { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; }
 __device__ __forceinline__ int fast_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
+
+// plain shared-memory atomic add: the callers already aggregate per warp, so bypass the compiler's own
+// warp-aggregation wrapper around atomicAdd
+__device__ __forceinline__ int atom_add_shared(int *addr, int v)
+{
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+    return old;
+}
 
 // warp-aggregated append of `cnt` (0..8) items per lane: returns this lane's first slot
 __device__ __forceinline__ int warp_reserve(int cnt, int *counter)
@@ -91,7 +116,7 @@ __device__ __forceinline__ int warp_reserve(int cnt, int *counter)
     const int total = __shfl_sync(0xffffffffu, inc, 31);
     int base = 0;
     if (total) {
-        if (lane == 31) base = atomicAdd(counter, total);
+        if (lane == 31) base = atom_add_shared(counter, total);
         base = __shfl_sync(0xffffffffu, base, 31);
     }
     return base + inc - cnt;
@@ -103,7 +128,7 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
     const unsigned bal = __ballot_sync(0xffffffffu, pred);
     int base = 0;
     if (bal) {
-        if (lane == 0) base = atomicAdd(counter, __popc(bal));
+        if (lane == 0) base = atom_add_shared(counter, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
     }
     return base + __popc(bal & ((1u << lane) - 1));
@@ -113,9 +138,9 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 //   0  stage the u8 tile (+3-px halo) with 8-byte loads
 //   then, at T = initTh for every cell and again at T = minTh only for the cells that produced no
 //   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792):
-//   1  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
-//      (N,E,S,W at radius 3) with |d| > T  ->  (aN|aS) & (aE|aW); VABSDIFF4 + 3 ops per 4 px
-//   2  signed compass test on the survivors (both brighter or both darker)
+//   1+2  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
+//      (N,E,S,W at radius 3) both brighter than centre+T or both darker than centre-T; per 4 px and
+//      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
 //   3  full 16-pixel ring masks + 9-contiguous-arc test           -> corners at T
 //   4  score m of the corners                                     -> m map
 //   5  NMS inside the cell interior, emission with one global atomic per pass
@@ -154,8 +179,8 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                     const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
                     const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
                     const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
-                    c0 = (absdiff_gt(up.x, cen.x, K) | absdiff_gt(dn.x, cen.x, K)) & (absdiff_gt(lw0, cen.x, K) | absdiff_gt(rw0, cen.x, K)) & nd.x;
-                    c1 = (absdiff_gt(up.y, cen.y, K) | absdiff_gt(dn.y, cen.y, K)) & (absdiff_gt(lw1, cen.y, K) | absdiff_gt(rw1, cen.y, K)) & nd.y;
+                    c0 = compass_signed(dn.x, up.x, rw0, lw0, cen.x, K) & nd.x;
+                    c1 = compass_signed(dn.y, up.y, rw1, lw1, cen.y, K) & nd.y;
                 }
             }
             const int cnt = __popc(c0) + __popc(c1);
@@ -180,25 +205,12 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         }
     }
     __syncthreads();
-    // ---- stage 2: signed compass test (two adjacent compass pixels both brighter or both darker)
-    const int nA = s_cnt[0];
-    for (int base = 0; base < nA; base += 256) {
-        const int i = base + tid;
-        bool pass = false;
-        int e = 0;
-        if (i < nA) {
-            e = listA[i];
-            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
-            const int v = p[0], lo = v - T, hi = v + T;
-            const int pN = p[3 * tp], pE = p[3], pS = p[-3 * tp], pW = p[-3];
-            const bool bN = pN > hi, bE = pE > hi, bS = pS > hi, bW = pW > hi;
-            const bool dN = pN < lo, dE = pE < lo, dS = pS < lo, dW = pW < lo;
-            pass = ((bN | bS) & (bE | bW)) | ((dN | dS) & (dE | dW));
-        }
-        const int pos = warp_append1(pass, &s_cnt[1]);
-        if (pass) listB[pos] = (uint16_t)e;
+    // (stage 2, the signed compass test, is part of the SWAR prefilter; with T > 127 every pixel goes on)
+    {
+        uint16_t *t = listA; listA = listB; listB = t;   // stage 3 reads its input from listB
+        if (tid == 0) { s_cnt[1] = s_cnt[0]; }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- stage 3: full ring test at T
     const int nB = s_cnt[1];
     for (int base = 0; base < nB; base += 256) {

@@ -59,7 +59,8 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh)
 // entries in registers and reuses the horizontal interpolation of a source row shared by two
 // consecutive output rows.  Every source byte is read from HBM once, every output byte written once.
 #define PYR_TW 256
-#define PYR_TH 16
+#define PYR_TH 32
+#define PYR_RPT (PYR_TH / 4)   // output rows per thread
 extern __shared__ __align__(16) uint8_t pyr_smem[];
 
 __global__ void __launch_bounds__(256)
@@ -76,43 +77,50 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
     const int sx_lo = __ldg(&xtab[tx0]).x & ~15, sx_hi = __ldg(&xtab[tx1]).y;
     const int sy_lo = __ldg(&ytab[ty0]).x, sy_hi = __ldg(&ytab[ty1]).y;
     const int bw16 = (sx_hi - sx_lo + 16) >> 4, bh = sy_hi - sy_lo + 1;
+    const uint32_t magic = bw16 > 1 ? 0xFFFFFFFFu / (uint32_t)bw16 + 1u : 0u;
     for (int i = tid; i < bw16 * bh; i += 256) {
-        const int r = i / bw16, c = i - r * bw16;
+        const int r = magic ? (int)__umulhi((uint32_t)i, magic) : i, c = i - r * bw16;
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(sy_lo + r) * spitch + sx_lo) + c);
         *reinterpret_cast<uint4 *>(pyr_smem + r * bp + 16 * c) = v;
     }
-    __syncthreads();
     const int dx0 = tx0 + threadIdx.x * 4;
-    const int dy0 = ty0 + threadIdx.y * 4;
-    if (dx0 > tx1 || dy0 > ty1) return;
-    int4 xt[4];
+    const int dy0 = ty0 + threadIdx.y * PYR_RPT;
+    const bool active = dx0 <= tx1 && dy0 <= ty1;
+    int4 xt[4], yt[PYR_RPT];
+    if (active) {   // table entries of this thread, fetched while the box is in flight
 #pragma unroll
-    for (int k = 0; k < 4; k++) { xt[k] = __ldg(&xtab[min(dx0 + k, dw - 1)]); xt[k].x -= sx_lo; xt[k].y -= sx_lo; }
+        for (int k = 0; k < 4; k++) { xt[k] = __ldg(&xtab[min(dx0 + k, dw - 1)]); xt[k].x -= sx_lo; xt[k].y -= sx_lo; }
+#pragma unroll
+        for (int k = 0; k < PYR_RPT; k++) { yt[k] = __ldg(&ytab[min(dy0 + k, dh - 1)]); yt[k].x -= sy_lo; yt[k].y -= sy_lo; }
+    }
+    __syncthreads();
+    if (!active) return;
     int prev_row = -1;
     int hprev[4] = {0, 0, 0, 0};
-    const int dy1 = min(dy0 + 4, dh);
-    for (int dy = dy0; dy < dy1; dy++) {
-        const int4 yt = __ldg(&ytab[dy]);
+#pragma unroll
+    for (int kk = 0; kk < PYR_RPT; kk++) {
+        const int dy = dy0 + kk;
+        if (dy > ty1) break;
         int h0[4], h1[4];
-        if (yt.x == prev_row) {
+        if (yt[kk].x == prev_row) {
 #pragma unroll
             for (int k = 0; k < 4; k++) h0[k] = hprev[k];
         } else {
-            const uint8_t *r0 = pyr_smem + (yt.x - sy_lo) * bp;
+            const uint8_t *r0 = pyr_smem + yt[kk].x * bp;
 #pragma unroll
             for (int k = 0; k < 4; k++) h0[k] = (int)r0[xt[k].x] * xt[k].z + (int)r0[xt[k].y] * xt[k].w;
         }
-        const uint8_t *r1 = pyr_smem + (yt.y - sy_lo) * bp;
+        const uint8_t *r1 = pyr_smem + yt[kk].y * bp;
 #pragma unroll
         for (int k = 0; k < 4; k++) h1[k] = (int)r1[xt[k].x] * xt[k].z + (int)r1[xt[k].y] * xt[k].w;
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int v = (((yt.z * (h0[k] >> 4)) >> 16) + ((yt.w * (h1[k] >> 4)) >> 16) + 2) >> 2;
+            int v = (((yt[kk].z * (h0[k] >> 4)) >> 16) + ((yt[kk].w * (h1[k] >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 0xFF) << (8 * k);
             hprev[k] = h1[k];
         }
-        prev_row = yt.y;
+        prev_row = yt[kk].y;
         if (dx0 + 3 < dw) {
             *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
         } else {
