@@ -151,7 +151,8 @@ struct FastSmem {
 
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
                                           const int hEff, const int wEff, const int cs, const int ce, const int tp,
-                                          const int cand_x0, const int cand_y0, int *s_cnt, int *s_has, int *s_base)
+                                          const int cand_x0, const int cand_y0, int *s_cnt, int *s_has, int *s_base,
+                                          const int col_lo, const int col_hi)   // interior columns [col_lo, col_hi) to test
 {
     const int tid = threadIdx.x;
     uint8_t *tile = S.tile, *sc = S.sc;
@@ -159,7 +160,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     // ---- stage 1: SWAR compass prefilter (need[] holds 0x80 for the bytes this pass must test)
     if (T <= 127) {
         const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
-        const int g0 = cs >> 3, nG = ((ce + 7) >> 3) - g0;
+        const int g0 = (cs + col_lo) >> 3, nG = ((cs + col_hi + 7) >> 3) - g0;
         const uint32_t magic = div_magic(nG);
         const int items = hEff * nG;
         for (int base = 0; base < items; base += 256) {
@@ -184,6 +185,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 }
             }
             const int cnt = __popc(c0) + __popc(c1);
+            if (!__any_sync(0xffffffffu, cnt != 0)) continue;   // nothing in this warp's 256 pixels
             int pos = warp_reserve(cnt, &s_cnt[0]);
             if (cnt) {
                 const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
@@ -199,7 +201,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             const int i = base + tid;
             bool ok = false;
             int rr = 0, cc = 0;
-            if (i < hEff * wEff) { rr = i / wEff; cc = i - rr * wEff; ok = S.need[cs + cc] != 0; }
+            if (i < hEff * wEff) { rr = i / wEff; cc = i - rr * wEff; ok = S.need[cs + cc] != 0 && cc >= col_lo && cc < col_hi; }
             const int pos = warp_append1(ok, &s_cnt[0]);
             if (ok) listA[pos] = (uint16_t)((rr << 10) | cc);
         }
@@ -319,7 +321,7 @@ fast9_cells(FastArgs a)
     S.need = S.cellOf + ((a.scw + 15) & ~15);                        // tp : 0x80 where this pass tests the byte column
     S.listA = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
     S.listB = S.listA + ((cap + 7) & ~7);
-    __shared__ int s_cnt[4], s_base, s_again;
+    __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
     __shared__ int s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
@@ -331,28 +333,33 @@ fast9_cells(FastArgs a)
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
         *reinterpret_cast<uint2 *>(S.tile + rr * tp + 8 * ww) = v;
     }
-    for (int i = tid; i < (cap + 3) / 4; i += 256) reinterpret_cast<uint32_t *>(S.sc)[i] = 0;
-    for (int i = tid; i < a.scw; i += 256) S.cellOf[i] = (uint8_t)(i / a.wCell);
+    for (int i = tid; i < (cap + 15) / 16; i += 256) reinterpret_cast<uint4 *>(S.sc)[i] = make_uint4(0, 0, 0, 0);
+    {
+        const uint32_t mw = div_magic(a.wCell);
+        for (int i = tid; i < a.scw; i += 256) S.cellOf[i] = (uint8_t)fast_div(i, mw);
+    }
     for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
     if (tid < 4) s_cnt[tid] = 0;
     if (tid < 64) s_has[tid] = 0;
     __syncthreads();
 
     // pass 1: every cell at initTh (ORBextractor.cpp:785)
-    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base);
+    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base, 0, wEff);
     // pass 2: cells without a keypoint again at minTh (:788-792)
     const int nCells = (wEff + a.wCell - 1) / a.wCell;
     if (tid == 0) {
-        int again = 0;
-        for (int c = 0; c < nCells; c++) again |= !s_has[c];
-        s_again = again && (a.minTh != a.initTh);
+        int first = -1, last = -1;
+        for (int c = 0; c < nCells; c++) if (!s_has[c]) { if (first < 0) first = c; last = c; }
+        s_again = first >= 0 && (a.minTh != a.initTh);
+        s_lo = first < 0 ? 0 : first * a.wCell;
+        s_hi = first < 0 ? 0 : min((last + 1) * a.wCell, wEff);
     }
     if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
     if (!s_again) return;
     for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce && !s_has[S.cellOf[i - cs]]) ? 0x80 : 0;
     __syncthreads();
-    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base);
+    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base, s_lo, s_hi);
 }
 
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)

@@ -329,7 +329,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
             a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
             a.G = 256 / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
             a.scw = a.G * g.wCell;
-            a.tpitch = ((7 + a.scw + 6 + 7) & ~7) + 8;   // 8-byte aligned origin + halo + one spare word for the E-side read
+            a.tpitch = ((7 + a.scw + 6 + 15) & ~15) + 16;   // 8-byte aligned origin + halo + spare for the E-side read; multiple of 16 keeps every shared array 16-byte aligned
             a.initTh = (int)initTh; a.minTh = (int)minTh;
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
