@@ -240,6 +240,32 @@ class RefExtractor:
         return kps[:n].copy(), desc[:n].copy()
 
 
+def fast10(img, barrier=20):
+    img = _u8(img)
+    cap = img.size // 2 + 16
+    xy = np.zeros((cap, 2), np.int32)
+    sc = np.zeros(cap, np.int32)
+    n = lib().tbo_fast10(_p(img), img.shape[1], img.shape[0], img.strides[0], int(barrier), _p(xy), _p(sc), cap)
+    return xy[:n].copy(), sc[:n].copy()
+
+
+def fast_extract(levels, inv_sf, n_features, threshold, occupied=None):
+    """FASTExtractor::operator() (occupied None) / AddPoints (occupied = grid_occupancy_ flags). Returns None
+    where the reference would throw std::out_of_range."""
+    levels, ptrs, w, h, s = _level_args(levels)
+    inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+    out = np.zeros(n_features + 1, KP_DTYPE)
+    occ = None if occupied is None else _u8(occupied)
+    n = lib().tbo_fast_extract(ptrs, w, h, s, len(levels), _p(inv_sf), int(n_features), C.c_float(threshold),
+                               None if occ is None else _p(occ), _p(out), len(out))
+    return None if n < 0 else out[:n].copy()
+
+
+def fast_grid(w0, h0, n_features):
+    cell = int(np.sqrt(np.float32(np.float32(w0) * np.float32(h0) / np.float32(n_features))))
+    return cell, int(np.float32(w0) / np.float32(cell)), int(np.float32(h0) / np.float32(cell))
+
+
 # ---------------------------------------------------------------- matchers
 def hamming256(a, b):
     a, b = _u8(a), _u8(b)

@@ -980,3 +980,89 @@ float tbo_shi_tomasi(const u8 *img, int w, int h, int stride, int u, int v)
     dXX = dXX / (2.f * box_area); dYY = dYY / (2.f * box_area); dXY = dXY / (2.f * box_area);
     return 0.5f * (dXX + dYY - sqrtf((dXX + dYY) * (dXX + dYY) - 4 * (dXX * dYY - dXY * dXY)));
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FASTExtractor — src/extractors/FASTextractor.cpp (SVO-style grid FAST).  Detector restated from the
+ * public uzh-rpg/fast (Rosten) algorithm; see tb_oracle.h: parity unpinned.
+ * ------------------------------------------------------------------------------------------ */
+static int fast10_m(const u8 *p, int stride)
+{
+    int d[26];
+    int v = p[0];
+    for (int k = 0; k < 16; k++) d[k] = v - p[RING_DY[k] * stride + RING_DX[k]];
+    for (int k = 16; k < 26; k++) d[k] = d[k - 16];
+    int A = INT_MIN, B = INT_MIN;
+    for (int s = 0; s < 16; s++) {
+        int mn = INT_MAX, mx = INT_MIN;
+        for (int k = s; k < s + 10; k++) { mn = imin(mn, d[k]); mx = imax(mx, d[k]); }
+        A = imax(A, mn);
+        B = imax(B, -mx);
+    }
+    return imax(A, B);
+}
+
+/* fast_corner_detect_10 + fast_corner_score_10 + fast_nonmax_3x3: row-major list of surviving corners */
+int tbo_fast10(const u8 *img, int w, int h, int stride, int barrier, int32_t *xy, int32_t *scores, int cap)
+{
+    if (w < 7 || h < 7) return 0;
+    int *sc = (int *)calloc((size_t)w * h, sizeof(int)); /* score+1 for corners, 0 otherwise */
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            int m = fast10_m(img + (size_t)y * stride + x, stride);
+            if (m > barrier) sc[(size_t)y * w + x] = m; /* score = m - 1 >= barrier; keep m so that 0 = no corner */
+        }
+    int n = 0;
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            int m = sc[(size_t)y * w + x];
+            if (!m) continue;
+            int keep = 1;
+            for (int dy = -1; dy <= 1 && keep; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (!dx && !dy) continue;
+                    int m2 = sc[(size_t)(y + dy) * w + x + dx];
+                    if (m2 && m2 >= m) { keep = 0; break; } /* Compare(X,Y) ((X)>=(Y)) */
+                }
+            if (!keep) continue;
+            if (n < cap) { xy[2 * n] = x; xy[2 * n + 1] = y; scores[n] = m - 1; }
+            n++;
+        }
+    free(sc);
+    return n;
+}
+
+int tbo_fast_extract(const u8 *const *levels, const int *w, const int *h, const int *stride, int n_levels,
+                     const float *inv_sf, int nFeatures, float threshold, const u8 *occupied, tbo_kp *out, int cap)
+{
+    if (n_levels <= 0 || !levels[0] || w[0] <= 0 || h[0] <= 0 || nFeatures <= 0) return 0;
+    const int cell_size = (int)sqrtf((float)w[0] * (float)h[0] / (float)nFeatures);
+    if (cell_size <= 0) return -1;
+    const int grid_n_cols = (int)((float)w[0] / (float)cell_size);
+    const int grid_n_rows = (int)((float)h[0] / (float)cell_size);
+    const int ncell = grid_n_cols * grid_n_rows;
+    tbo_kp *grid = (tbo_kp *)calloc((size_t)nFeatures, sizeof(tbo_kp)); /* gridPoints.resize(nFeatures): response 0 */
+    int err = 0;
+    for (int L = 0; L < n_levels && !err; L++) {
+        int ccap = w[L] * h[L] / 2 + 16;
+        int32_t *xy = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)ccap), *sc = (int32_t *)malloc(sizeof(int32_t) * (size_t)ccap);
+        int n = tbo_fast10(levels[L], w[L], h[L], stride[L], 20, xy, sc, ccap);
+        for (int i = 0; i < n; i++) {
+            const int x = xy[2 * i], y = xy[2 * i + 1];
+            const int k = (int)(((float)y * inv_sf[L]) / (float)cell_size) * grid_n_cols + (int)(((float)x * inv_sf[L]) / (float)cell_size);
+            if (occupied && k >= 0 && k < ncell && occupied[k]) continue;
+            const float score = tbo_shi_tomasi(levels[L], w[L], h[L], stride[L], x, y);
+            if (k < 0 || k >= nFeatures) { err = 1; break; } /* gridPoints.at(k) throws */
+            if (score > grid[k].response) {
+                tbo_kp kp = {(float)x * inv_sf[L], (float)y * inv_sf[L], 1.f, 0.f, score, L, -1};
+                grid[k] = kp;
+            }
+        }
+        free(xy); free(sc);
+    }
+    int n = 0;
+    if (!err)
+        for (int k = 0; k < nFeatures; k++)
+            if (grid[k].response > (float)threshold) { if (n < cap) out[n] = grid[k]; n++; }
+    free(grid);
+    return err ? -1 : n;
+}

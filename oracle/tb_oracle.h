@@ -126,6 +126,20 @@ void tbo_three_maxima(const int *hist_sizes, int L, int *ind1, int *ind2, int *i
 /* FASTExtractor::shiTomasiScore (src/extractors/FASTextractor.cpp:87-127). */
 float tbo_shi_tomasi(const uint8_t *img, int w, int h, int stride, int u, int v);
 
+/* FASTExtractor::operator() / AddPoints (src/extractors/FASTextractor.cpp:8-80, :129-150).
+ * The FAST-10 detector / score / 3x3 non-max suppression come from uzh-rpg/fast (third_part/fast_lib,
+ * NOT in the reference tree, no version pin): restated from the published algorithm (Rosten's FAST-10:
+ * 10 contiguous ring pixels brighter than p+b or darker than p-b; score = largest b for which the pixel
+ * is still a corner = m10-1; nonmax keeps a corner unless an 8-neighbour corner has a score >= its own).
+ * PARITY UNPINNED for this function (no reference test calls it, test_frame.cpp:48-85 is commented out).
+ * occupied: grid_occupancy_ after AddPoints marked the exit points (NULL = operator() with reset).
+ * Returns the number of keypoints, or -1 where the reference would throw std::out_of_range
+ * (gridPoints.at(k) with k >= nFeatures). */
+int tbo_fast10(const uint8_t *img, int w, int h, int stride, int barrier, int32_t *xy, int32_t *scores, int cap);
+int tbo_fast_extract(const uint8_t *const *levels, const int *w, const int *h, const int *stride, int n_levels,
+                     const float *inv_sf, int nFeatures, float threshold, const uint8_t *occupied,
+                     tbo_kp *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,3 +162,45 @@ def test_invalid_arguments_fail_loudly(tb, ctx):
             fe.extract(1, np.array([1, 0.8], np.float32), 50, 20, 7, exit_kps=np.zeros(1, tb.KP_DTYPE))  # AddPoints before operator()
     finally:
         fe.close()
+
+
+def test_config5_4k_extract_and_projection_match(tb, ctx, oracle):
+    """BASELINE config 5 at full size (one stream step): 3840x2160, extract(2000), projection-guided match
+    F_k -> F_{k-1} with synthetic depth 10 m and a 1 px/frame pan."""
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = PARAM_SETS['B2000']
+    W, H = 3840, 2160
+    frames = np.stack([synth_frame(k, W, H, seed0=2000) for k in range(2)])
+    fe, sf = _frontend(tb, ctx, (H, W), nl, sc, 2, tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(2)
+        fe.extract(2, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(2)
+        ref = []
+        for f in range(2):
+            lv, _ = oracle.pyramid(frames[f], nl, sc)
+            ko, do, _ = oracle.orb_extract(lv, sf, tgt, a, b)
+            assert kp_bytes_equal(kps[f, :counts[f]], ko)
+            assert np.array_equal(desc[f, :counts[f]], do)
+            ref.append((ko, do))
+        # map points from frame 0's keypoints at 10 m; frame 1's camera moved so that the image pans by ~1 px
+        fx = fy = 2000.0
+        cx, cy = W / 2.0, H / 2.0
+        k0, d0 = ref[0]
+        depth = np.full(len(k0), 10.0, np.float32)
+        xyz = np.stack([(k0['x'] - np.float32(cx)) / np.float32(fx) * depth, (k0['y'] - np.float32(cy)) / np.float32(fy) * depth, depth], 1).astype(np.float32)
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3] = -10.0 / fx
+        valid = np.ones(len(k0), np.uint8)
+        p = tb.MatcherParams(30, 50, 30, 1, 30.0)
+        po = oracle.MatcherParams(30, 50, 30, 1, 30.0)
+        cam = tb.Pinhole(fx, fy, cx, cy, W, H, (tb.capi.C.c_float * 5)(0, 0, 0, 0, 0))
+        camo = oracle.Pinhole(fx, fy, cx, cy, W, H, (oracle.C.c_float * 5)(0, 0, 0, 0, 0))
+        k1, d1 = ref[1]
+        got = ctx.search_by_projection(p, cam, T, k1, d1, None, sf, W, H, k0, valid, xyz, d0)
+        exp = oracle.search_by_projection(po, camo, T, k1, d1, None, sf, W, H, k0, valid, xyz, d0)
+        assert got.tobytes() == exp.tobytes()
+        assert len(exp) > 50
+    finally:
+        fe.close()

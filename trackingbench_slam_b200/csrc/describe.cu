@@ -213,15 +213,17 @@ orb_describe(DescArgs a)
     int m10 = 0, m01 = 0;
     const int u = lane - 15;
     if (lane < 31) {
-#pragma unroll 1
+        // all 31 row loads are independent: issue them together (the kernel is latency bound otherwise)
+        int vals[31];
+#pragma unroll
         for (int v = -15; v <= 15; v++) {
-            int um = c_umax[v < 0 ? -v : v];
-            if (u >= -um && u <= um) {
-                int val = raw[v * L.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
+            const int um = c_umax[v < 0 ? -v : v];
+            vals[v + 15] = (u >= -um && u <= um) ? (int)raw[v * L.pitch + u] : 0;
         }
+        int s0 = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; v++) { s0 += vals[v + 15]; m01 += v * vals[v + 15]; }
+        m10 = u * s0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
