@@ -287,7 +287,7 @@ def run_ours(a):
         s['ctx'].close()
 
     # per-kernel times of one step (CUDA events around every launch) for the roofline
-    roof, table = None, {}
+    roof, table, hamming = None, {}, None
     if rank == 0:
         ctx.profile_enable(True)
         step()
@@ -315,6 +315,11 @@ def run_ours(a):
         roof = {'kernel': dom, 'bound': 'hbm', 'achieved': table[dom]['GBps'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                 'frac': table[dom]['GBps'] / peak, 'traffic': traffic,
                 'launches_per_step': table[dom]['launches'], 'step_share': table[dom]['share']}
+        # Hamming throughput of the matcher kernel alone (both cross-check directions are evaluated)
+        mk = 'hamming_i8mma' if a.match_impl == 'tc' else 'hamming_knn'
+        pair_evals = 2.0 * float((counts[:-1].astype(np.float64) * counts[1:].astype(np.float64)).sum())
+        hamming = {'kernel': mk, 'pair_evaluations_per_step': pair_evals,
+                   'Gpairs_per_s': pair_evals / (table[mk]['ms'] * 1e-3) / 1e9 if mk in table and table[mk]['ms'] > 0 else None}
         if a.profile_out:
             json.dump({'per_kernel': table, 'step_ms_profiled': tot}, open(a.profile_out, 'w'), indent=1)
 
@@ -335,7 +340,7 @@ def run_ours(a):
                            'l2': 'inputs (%.0f MB of frames per step) exceed the 126 MB L2' % (B * W * H / 1e6),
                            'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches, 'match_impl': a.match_impl},
                 'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'hamming': hamming,
                 'per_kernel_ms': {k: round(v['ms'], 3) for k, v in table.items()}}
         print(json.dumps(line))
     fe.close()

@@ -54,8 +54,10 @@ def test_bf_golden(tb, ctx, pname):
     assert ctx.search_by_bf_device(t1.data_ptr(), len(gl['desc']), t2.data_ptr(), len(gr['desc']), 10.0, 30.0).tobytes() == gm['filtered'].tobytes()
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('nq,nt', [(1, 1), (7, 1), (100, 257), (513, 1024), (3000, 2500)])
-def test_knn2_vs_oracle(tb, ctx, oracle, nq, nt):
+def test_knn2_vs_oracle(tb, ctx, oracle, nq, nt, impl):
+    ctx.set_match_impl(impl)
     rng = np.random.default_rng(nq + nt)
     q, t = _rand_desc(rng, nq, nt)
     tq, tt = dev(q), dev(t)
@@ -64,7 +66,9 @@ def test_knn2_vs_oracle(tb, ctx, oracle, nq, nt):
     second = torch.empty_like(idx)
     ctx.knn2_device(tq.data_ptr(), nq, tt.data_ptr(), nt, idx.data_ptr(), best.data_ptr(), second.data_ptr())
     torch.cuda.synchronize()
+    ctx.set_match_impl(0)
     io, bo, so = oracle.knn2(q, t)
+    so = np.where(so == np.iinfo(np.int32).max, 0x7fffffff, so)
     assert np.array_equal(idx.cpu().numpy(), io) and np.array_equal(best.cpu().numpy(), bo) and np.array_equal(second.cpu().numpy(), so)
 
 

@@ -56,6 +56,7 @@ struct DescArgs {
 int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames);
 int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *d_t_frames, int n_frames_used,
                     const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap, int *best_idx, int *best_dist);
+int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *best, int *second);
 int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host, int n_frames_total,
                         const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,
                         float ratio, float minTh, tb_match *matches, int capacity, int *out_counts);

@@ -229,6 +229,8 @@ extern "C" int tb_knn2_device(tb_ctx *ctx, const void *q, int nq, const void *t,
 {
     if (!ctx || nq < 0 || nt < 0) return TB_E_INVALID;
     if (nq == 0) return TB_OK;
+    if (ctx->match_impl == 1 && nt > 0)
+        return tb_knn2_tc(ctx, (const uint8_t *)q, nq, (const uint8_t *)t, nt, (int *)idx, (int *)best, (int *)second);
     int rc = ws_reserve(ctx, 2, 1);
     if (rc) return rc;
     MatchWs &w = ws_of(ctx);

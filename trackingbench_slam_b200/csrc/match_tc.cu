@@ -23,7 +23,7 @@
 #define TC_KB 256         // bytes (= int8 elements) per expanded descriptor
 #define TC_A_BYTES (TC_M * TC_KB)
 #define TC_B_BYTES (TC_N * TC_KB)
-#define TC_THREADS 192
+#define TC_THREADS 320      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct TcPair {
     const int8_t *q, *t;   // expanded descriptor blocks of the query / train frame
@@ -32,7 +32,7 @@ struct TcPair {
 
 // ---- expansion: 32-byte descriptors -> 256 int8 (+1 for a 0 bit, -1 for a 1 bit), rows >= count are 0
 __global__ void __launch_bounds__(256)
-expand_desc_i8(const uint8_t *__restrict__ desc, size_t in_stride, const int *__restrict__ counts,
+expand_desc_i8(const uint8_t *__restrict__ desc, size_t in_stride, const int *__restrict__ counts, int n_fixed,
                int8_t *__restrict__ out, size_t out_stride, int rows_pad)
 {
     const int f = blockIdx.y;
@@ -40,7 +40,7 @@ expand_desc_i8(const uint8_t *__restrict__ desc, size_t in_stride, const int *__
     const int row = item >> 4, c = item & 15;
     if (row >= rows_pad) return;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < counts[f]) {
+    if (row < (counts ? counts[f] : n_fixed)) {
         const uint8_t *d = desc + (size_t)f * in_stride + (size_t)32 * row + 2 * c;
         const uint32_t bits = d[0] | ((uint32_t)d[1] << 8);
         uint32_t w[4];
@@ -119,12 +119,15 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 struct __align__(16) TcShared {
     uint64_t fullA, full[2], empty[2], tfull[2], tempty[2];
     uint32_t tmem_base;
+    int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // partial results of the upper-half-column warps
 };
 
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
+template <bool SECOND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist)
+hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist,
+              int *__restrict__ second_dist)
 {
     const TcPair pd = pairs[blockIdx.y];
     const int q0 = blockIdx.x * TC_M;
@@ -137,7 +140,7 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
 
     if (threadIdx.x == 0) {
         mbar_init(&S->fullA, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {   // TMEM: 512 columns = two 128x256 int32 accumulators
@@ -148,6 +151,7 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = S->tmem_base;
+    int best = -1000, second = -1000, bidx = -1;   // running (max dot, second, arg) of an epilogue thread
 
     if (warp == 0) {
         if (lane == 0) {
@@ -183,20 +187,21 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
             }
         }
     } else {
-        // ---- epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 = query rows
+        // ---- epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31 = query rows; warps 2..5 scan the lower 128
+        //      columns of every accumulator tile, warps 6..9 the upper 128
         const int lane_base = 32 * (warp & 3);
+        const int half = (warp - 2) >> 2;
         const int row = q0 + lane_base + lane;
-        int best = -1000, bidx = -1;
         for (int t = 0; t < NT; t++) {
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&S->tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int col0 = t * TC_N;
+            const int col0 = t * TC_N + half * (TC_N / 2);
 #pragma unroll 1
-            for (int c = 0; c < TC_N; c += 32) {
+            for (int c = 0; c < TC_N / 2; c += 32) {
                 if (col0 + c >= pd.nt) break;   // warp-uniform
                 uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(s * TC_N + c);
+                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(s * TC_N + half * (TC_N / 2) + c);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -211,22 +216,42 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int d = (int)v[j];
-                    if (j < lim && d > best) { best = d; bidx = col0 + c + j; }
+                    if (SECOND) {
+                        if (j < lim) {
+                            if (d > best) { second = best; best = d; bidx = col0 + c + j; }
+                            else if (d > second) second = d;
+                        }
+                    } else {
+                        if (j < lim && d > best) { best = d; bidx = col0 + c + j; }
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->tempty[s]);
         }
-        if (row < pd.nq) {
-            const size_t o = (size_t)blockIdx.y * out_stride + row;
-            best_idx[o] = bidx;
-            best_dist[o] = bidx >= 0 ? (256 - best) >> 1 : 0x7fffffff;
-        }
+        if (half == 1) { S->part_best[lane_base + lane] = best; S->part_second[lane_base + lane] = second; S->part_idx[lane_base + lane] = bidx; }
+        (void)row;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp >= 2 && warp < 6) {
+        // merge the two column halves (lowest index wins ties) and write the row's result
+        const int r = 32 * (warp & 3) + lane, row = q0 + r;
+        const int b1 = S->part_best[r], s1 = S->part_second[r], i1 = S->part_idx[r];
+        if (i1 >= 0 && (bidx < 0 || b1 > best || (b1 == best && i1 < bidx))) {
+            second = max(s1, best); best = b1; bidx = i1;
+        } else if (i1 >= 0) {
+            second = max(second, b1);
+        }
+        if (row < pd.nq) {
+            const size_t o = (size_t)blockIdx.y * out_stride + row;
+            best_idx[o] = bidx;
+            best_dist[o] = bidx >= 0 ? (256 - best) >> 1 : 0x7fffffff;
+            if (SECOND) second_dist[o] = second > -1000 ? (256 - second) >> 1 : 0x7fffffff;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -270,19 +295,62 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *
     {
         ProfScope prof__(ctx, "expand_desc_i8");
         dim3 grid(div_up(rows_pad * 16, 256), n_frames_used);
-        expand_desc_i8<<<grid, 256, 0, ctx->stream>>>(desc, frame_stride, counts, w->exp, exp_stride, rows_pad);
+        expand_desc_i8<<<grid, 256, 0, ctx->stream>>>(desc, frame_stride, counts, 0, w->exp, exp_stride, rows_pad);
         TB_LAUNCH_CHECK(ctx);
     }
     build_tc_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w->pairs, n_pairs, d_q_frames, d_t_frames, w->exp, exp_stride, counts);
     TB_LAUNCH_CHECK(ctx);
     static bool attr_set = false;
     const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
-    if (!attr_set) { cudaFuncSetAttribute(hamming_i8mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(hamming_i8mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
     {
         ProfScope prof__(ctx, "hamming_i8mma");
         dim3 grid(div_up(kp_cap, TC_M), 2 * n_pairs);
-        hamming_i8mma<<<grid, TC_THREADS, smem, ctx->stream>>>(w->pairs, kp_cap, best_idx, best_dist);
+        hamming_i8mma<false><<<grid, TC_THREADS, smem, ctx->stream>>>(w->pairs, kp_cap, best_idx, best_dist, nullptr);
         TB_LAUNCH_CHECK(ctx);
     }
+    return TB_OK;
+}
+
+// best / second / argbest of nq query rows against nt train rows (tb_knn2_device with the tensor-core matcher)
+int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *best, int *second)
+{
+    TcWs *w = tcws(ctx);
+    const size_t q_rows = (size_t)(nq + TC_N - 1) / TC_N * TC_N, t_rows = (size_t)(nt + TC_N - 1) / TC_N * TC_N;
+    const size_t need = (q_rows + t_rows) * TC_KB;
+    if (need > w->exp_bytes) {
+        if (w->exp) cudaFree(w->exp);
+        w->exp = nullptr; w->exp_bytes = 0;
+        TB_CUDA(ctx, cudaMalloc(&w->exp, need));
+        w->exp_bytes = need;
+    }
+    if (w->pairs_cap < 2) {
+        if (w->pairs) cudaFree(w->pairs);
+        TB_CUDA(ctx, cudaMalloc(&w->pairs, sizeof(TcPair) * 2));
+        w->pairs_cap = 2;
+    }
+    int8_t *eq = w->exp, *et = w->exp + q_rows * TC_KB;
+    {
+        ProfScope prof__(ctx, "expand_desc_i8");
+        expand_desc_i8<<<dim3(div_up((int)q_rows * 16, 256), 1), 256, 0, ctx->stream>>>(q, 0, nullptr, nq, eq, 0, (int)q_rows);
+        TB_LAUNCH_CHECK(ctx);
+        expand_desc_i8<<<dim3(div_up((int)t_rows * 16, 256), 1), 256, 0, ctx->stream>>>(t, 0, nullptr, nt, et, 0, (int)t_rows);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    TcPair pd = {eq, et, nq, nt};
+    TB_CUDA(ctx, cudaMemcpyAsync(w->pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
+    static bool attr_set = false;
+    const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
+    if (!attr_set) { cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    {
+        ProfScope prof__(ctx, "hamming_i8mma");
+        hamming_i8mma<true><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, smem, ctx->stream>>>(w->pairs, 0, idx, best, second);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pair descriptor came from pageable host memory
     return TB_OK;
 }
