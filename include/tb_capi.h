@@ -147,6 +147,16 @@ int tb_orb_extract_host(tb_frontend *fe, const uint8_t *const *levels, const siz
                         const tb_keypoint *exit_kps, int n_exit,
                         tb_keypoint *kps, uint8_t *desc, int capacity, int *n);
 
+/* FASTExtractor::operator() (src/extractors/FASTextractor.cpp:8-80) when exit_kps == NULL, AddPoints
+ * (:129-150) otherwise: FAST-10 (barrier 20) + 3x3 non-max + Shi-Tomasi score (:87-127), best corner per
+ * grid cell over all levels, emitted in cell order if response > threshold. inv_sf = the per-level factors
+ * the caller passes (coordinates are multiplied by them). The FAST-10 detector comes from a library that is
+ * absent from the reference tree (uzh-rpg/fast): parity of that part is unpinned.
+ * Returns TB_E_INVALID where the reference throws std::out_of_range (gridPoints.at(k), k >= nFeatures). */
+int tb_fast_extract_host(tb_ctx *ctx, const uint8_t *const *levels, const int32_t *w, const int32_t *h, const size_t *host_strides,
+                         int n_levels, const float *inv_sf, int n_features, float threshold,
+                         const tb_keypoint *exit_kps, int n_exit, tb_keypoint *out, int capacity, int *n);
+
 /* ------------------------------------------------------------------ matching (device-resident inputs)
  * Descriptors are rows of 32 bytes. */
 

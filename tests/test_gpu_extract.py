@@ -204,3 +204,36 @@ def test_config5_4k_extract_and_projection_match(tb, ctx, oracle):
         assert len(exp) > 50
     finally:
         fe.close()
+
+
+def test_fast_extractor_vs_oracle(tb, ctx, oracle, images):
+    """FASTExtractor (SVO-style grid FAST-10 + Shi-Tomasi). The detector library is absent from the reference
+    tree, so parity is pinned to the restatement only; Shi-Tomasi scores are compared bit-exact
+    (north_star asks for 1e-4 relative)."""
+    rng = np.random.default_rng(21)
+    base = images['left'][:360, :640]
+    for img, nf in ((np.ascontiguousarray(np.tile(base, (2, 1))[:480, :640]), 300), (rng.integers(0, 256, (480, 640), dtype=np.uint8), 300)):
+        lv, sf = oracle.pyramid(img, 3, 0.8)
+        inv = (np.float32(1.0) / sf).astype(np.float32)   # FASTextractor.cpp multiplies by the factors it is given
+        # keep every level's corners inside the 20x15 grid so that gridPoints.at(k) never throws
+        assert oracle.fast_grid(640, 480, nf) == (32, 20, 15)
+        inv_used = np.minimum(inv, np.float32(1.0))
+        exp = oracle.fast_extract(lv, inv_used, nf, 20.0)
+        got = ctx.fast_extract_host(lv, inv_used, nf, 20.0)
+        assert exp is not None and len(exp) > 20
+        assert kp_bytes_equal(got, exp)
+        # AddPoints: cells of every 3rd keypoint are occupied
+        ex = exp[::3]
+        cell, ncols, nrows = oracle.fast_grid(640, 480, nf)
+        occ = np.zeros(ncols * nrows, np.uint8)
+        occ[(ex['y'] / np.float32(cell)).astype(np.int32) * ncols + (ex['x'] / np.float32(cell)).astype(np.int32)] = 1
+        exp2 = oracle.fast_extract(lv, inv_used, nf, 20.0, occupied=occ)
+        got2 = ctx.fast_extract_host(lv, inv_used, nf, 20.0, exit_kps=ex)
+        assert kp_bytes_equal(got2, exp2) and len(exp2) < len(exp)
+    # the reference throws std::out_of_range on ordinary inputs (bottom-row corners map to k >= nFeatures)
+    lv, sf = oracle.pyramid(images['left'], 5, 0.8)
+    inv = (np.float32(1.0) / sf).astype(np.float32)
+    assert oracle.fast_extract(lv, inv, 500, 20.0) is None
+    with pytest.raises(tb.TbError) as ei:
+        ctx.fast_extract_host(lv, inv, 500, 20.0)
+    assert ei.value.code == tb.capi.TB_E_INVALID

@@ -28,7 +28,7 @@ EXPORTS = [
     'tb_frontend_build_pyramid', 'tb_frontend_extract', 'tb_frontend_results_device',
     'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_results_batch_async',
     'tb_frontend_status', 'tb_frontend_get_candidates',
-    'tb_frontend_get_level_counts', 'tb_orb_extract_host',
+    'tb_frontend_get_level_counts', 'tb_orb_extract_host', 'tb_fast_extract_host',
     'tb_hamming_pairs_device', 'tb_knn2_device', 'tb_match_bf_cross_device', 'tb_search_by_bf_device',
     'tb_match_bf_cross_host', 'tb_search_by_bf_host', 'tb_hamming_pairs_host',
     'tb_frontend_search_by_bf', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
@@ -151,6 +151,22 @@ class Context:
         self.check(lib().tb_search_by_bf_device(self.h, _vp(d1_dptr), int(n1), _vp(d2_dptr), int(n2),
                                                 C.c_float(ratio), C.c_float(minTh), _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+    def fast_extract_host(self, levels, inv_sf, n_features, threshold, exit_kps=None):
+        """FASTExtractor::operator() / AddPoints. Raises TbError(TB_E_INVALID) where the reference throws."""
+        levels = [np.ascontiguousarray(l, np.uint8) for l in levels]
+        n = len(levels)
+        ptrs = (C.c_void_p * n)(*[l.ctypes.data for l in levels])
+        w = np.array([l.shape[1] for l in levels], np.int32)
+        h = np.array([l.shape[0] for l in levels], np.int32)
+        strides = (C.c_size_t * n)(*[l.strides[0] for l in levels])
+        inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+        ex = None if exit_kps is None else np.ascontiguousarray(exit_kps, KP_DTYPE)
+        out = np.zeros(n_features + 1, KP_DTYPE)
+        cnt = C.c_int()
+        self.check(lib().tb_fast_extract_host(self.h, ptrs, _vp(w), _vp(h), strides, n, _vp(inv_sf), int(n_features), C.c_float(threshold),
+                                              _vp(ex), 0 if ex is None else len(ex), _vp(out), len(out), C.byref(cnt)))
+        return out[:cnt.value].copy()
 
     # ---- windowed matchers (host in / host out)
     def features_in_area(self, kps, cols, rows, x, y, r, minLevel=-1, maxLevel=-1):
