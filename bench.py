@@ -247,13 +247,22 @@ def run_ours(a):
                           h_matches=torch.empty((max(P, 1), cap, 4), dtype=torch.int32, pin_memory=True),
                           h_mcounts=torch.empty(max(P, 1), dtype=torch.int32, pin_memory=True)))
 
+    compute_done = [None]
+
     def step_e2e(s):
         fe2 = s['fe']
         fe2.upload_frames_ptr(0, B, host.data_ptr(), W)
+        # kernels of consecutive steps run back to back (not interleaved), so that this step's upload
+        # overlaps the previous step's kernels and the next step's upload overlaps these
+        if compute_done[0] is not None:
+            s['stream'].wait_event(compute_done[0])
         fe2.build_pyramid(B)
         fe2.extract(B, sf, tgt, PSET['initTh'], PSET['minTh'])
         if P > 0:
             fe2.search_by_bf(qf, tf, PSET['ratio'], PSET['match_minTh'], s['matches'].data_ptr(), cap, s['mcounts'].data_ptr())
+        ev = torch.cuda.Event()
+        ev.record(s['stream'])
+        compute_done[0] = ev
         fe2.get_results_batch_async(B, s['h_kps'].numpy().view(tb.KP_DTYPE).reshape(B, cap), s['h_desc'].numpy(), s['h_counts'].numpy())
         with torch.cuda.stream(s['stream']):
             s['h_matches'].copy_(s['matches'], non_blocking=True)
