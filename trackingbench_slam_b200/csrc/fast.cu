@@ -161,7 +161,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     if (T <= 127) {
         const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
         const int g0 = (cs + col_lo) >> 3, nG = ((cs + col_hi + 7) >> 3) - g0;
-        const uint32_t magic = div_magic(nG);
+        const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);   // full-width tiles use the host's value
         const int items = hEff * nG;
         for (int base = 0; base < items; base += 256) {
             const int it = base + tid;
@@ -225,11 +225,31 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             const int v = p[0], lo = v - T, hi = v + T;
             int r[16];
             RING_LOAD(p, tp);
-            uint32_t mb = 0, md = 0;
+            uint32_t mb, md;
+            if (T <= 127) {
+                // byte-SIMD over ring positions: word i holds ring pixels i, i+4, i+8, i+12
+                const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
+                const uint32_t vv = (uint32_t)v * 0x01010101u, vlow = vv & 0x7f7f7f7fu;
+                uint32_t fb = 0, fd = 0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
-                md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t w = __byte_perm(__byte_perm(r[i], r[i + 4], 0x0040), __byte_perm(r[i + 8], r[i + 12], 0x0040), 0x5410);
+                    const uint32_t a = absdiff_gt(w, vv, K), g = byte_gt(w, vv, vlow);
+                    fb |= ((a & g) >> (7 - i)) & (0x01010101u << i);    // ring brighter than v+T
+                    fd |= ((a & ~g) >> (7 - i)) & (0x01010101u << i);   // ring darker than v-T
+                }
+                // byte j now holds ring positions 4j..4j+3 in its low nibble: squeeze the four nibbles together
+                uint32_t t = fb | (fb >> 4);
+                mb = (t & 0x00FFu) | ((t >> 8) & 0xFF00u);
+                t = fd | (fd >> 4);
+                md = (t & 0x00FFu) | ((t >> 8) & 0xFF00u);
+            } else {
+                mb = 0; md = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
+                    md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
+                }
             }
             corner = arc9(mb) || arc9(md);
         }
@@ -327,7 +347,7 @@ fast9_cells(FastArgs a)
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
     // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 8-byte words
     const int w8 = (ox + wEff + 6 + 7) >> 3;
-    const uint32_t magic8 = div_magic(w8);
+    const uint32_t magic8 = (wEff == a.scw && a.magic_w8 != 0xFFFFFFFFu) ? a.magic_w8 : div_magic(w8);
     for (int i = tid; i < rows * w8; i += 256) {
         const int rr = fast_div(i, magic8), ww = i - rr * w8;
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
@@ -335,7 +355,7 @@ fast9_cells(FastArgs a)
     }
     for (int i = tid; i < (cap + 15) / 16; i += 256) reinterpret_cast<uint4 *>(S.sc)[i] = make_uint4(0, 0, 0, 0);
     {
-        const uint32_t mw = div_magic(a.wCell);
+        const uint32_t mw = a.magic_wcell;
         for (int i = tid; i < a.scw; i += 256) S.cellOf[i] = (uint8_t)fast_div(i, mw);
     }
     for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;

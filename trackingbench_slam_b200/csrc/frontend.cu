@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------ ctx
@@ -327,9 +328,19 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
             FastArgs a;
             a.img = fe->pyr[l]; a.pitch = g.pitch; a.frame_stride = g.frame_stride; a.w = g.w; a.h = g.h;
             a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
-            a.G = 256 / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
+            static const int gpx = getenv("TB_FAST_GPX") ? atoi(getenv("TB_FAST_GPX")) : 256;   // tile width in pixels (tuning knob)
+            a.G = gpx / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
             a.scw = a.G * g.wCell;
             a.tpitch = ((7 + a.scw + 6 + 15) & ~15) + 16;   // 8-byte aligned origin + halo + spare for the E-side read; multiple of 16 keeps every shared array 16-byte aligned
+            {
+                // full-width tile: x0 = 16 + k*G*wCell; when that is a multiple of 8 for every k the tile geometry is fixed
+                auto magic = [](int n) -> uint32_t { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; };
+                const int ox = 16 & 7, cs = ox + 3, ce = cs + a.scw;     // valid when (G*wCell) % 8 == 0; otherwise the kernel recomputes
+                const bool fixed = ((a.G * g.wCell) & 7) == 0;
+                a.magic_groups = fixed ? magic(((ce + 7) >> 3) - (cs >> 3)) : 0xFFFFFFFFu;
+                a.magic_w8 = fixed ? magic((ox + a.scw + 6 + 7) >> 3) : 0xFFFFFFFFu;
+                a.magic_wcell = magic(g.wCell);
+            }
             a.initTh = (int)initTh; a.minTh = (int)minTh;
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;

@@ -14,6 +14,7 @@ struct FastArgs {
     int w, h;
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
     int G, tpitch, scw;
+    uint32_t magic_groups, magic_w8, magic_wcell;   // 2^32/n rounded up for the full-width tile (0 when n == 1)
     int initTh, minTh;
     uint32_t *cand; int cand_cap;
     int *n_cand; int n_cand_stride;
