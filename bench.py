@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=0, help='frames in the CPU-baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--match-impl', default='tc', choices=['popc', 'tc'], help='brute-force matcher kernel: LOP3+POPC or tcgen05 int8')
+    ap.add_argument('--fast-th', default='', help='developer knob: initTh,minTh override (not the benchmark config)')
     ap.add_argument('--profile-out', default='', help='write the per-kernel time table (JSON) here')
     return ap.parse_args()
 
@@ -157,6 +158,8 @@ def algorithmic_bytes(lw, lh, B, n_kp_total):
 
 
 def run_ours(a):
+    if a.fast_th:
+        PSET['initTh'], PSET['minTh'] = [float(x) for x in a.fast_th.split(',')]
     import torch
     import torch.distributed as dist
     import trackingbench_slam_b200 as tb

@@ -345,20 +345,45 @@ fast9_cells(FastArgs a)
     __shared__ int s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
-    // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 8-byte words
-    const int w8 = (ox + wEff + 6 + 7) >> 3;
-    const uint32_t magic8 = (wEff == a.scw && a.magic_w8 != 0xFFFFFFFFu) ? a.magic_w8 : div_magic(w8);
-    for (int i = tid; i < rows * w8; i += 256) {
-        const int rr = fast_div(i, magic8), ww = i - rr * w8;
-        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(img + (size_t)(y0 + rr) * a.pitch + xa) + ww);
-        *reinterpret_cast<uint2 *>(S.tile + rr * tp + 8 * ww) = v;
+    // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 16-byte words (xa is 8-byte aligned: the
+    //      first word of a row is fetched as two 8-byte halves when xa is not 16-byte aligned)
+    {
+        const int xa16 = xa & ~15;                     // 16-byte aligned start; tile byte 0 = image byte xa
+        const int lead = xa - xa16;                    // 0 or 8
+        const int w16 = (lead + ox + wEff + 6 + 15) >> 4;
+        const uint32_t magic16 = div_magic(w16);
+        const int total = rows * w16;
+        for (int i0 = tid; i0 < total; i0 += 512) {
+            uint4 v[2];
+            int dst[2], first[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int i = i0 + 256 * k;
+                dst[k] = -1;
+                if (i < total) {
+                    const int rr = fast_div(i, magic16), ww = i - rr * w16;
+                    v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(y0 + rr) * a.pitch + xa16) + ww);
+                    dst[k] = rr * tp + 16 * ww;      // tile offset of this word if lead were 0
+                    first[k] = ww == 0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (dst[k] < 0) continue;
+                if (lead == 0) {
+                    *reinterpret_cast<uint4 *>(S.tile + dst[k]) = v[k];
+                } else {   // tile origin sits 8 bytes into the 16-byte word: two 8-byte stores, drop what lies before the row
+                    if (!first[k]) *reinterpret_cast<uint2 *>(S.tile + dst[k] - 8) = make_uint2(v[k].x, v[k].y);
+                    *reinterpret_cast<uint2 *>(S.tile + dst[k]) = make_uint2(v[k].z, v[k].w);
+                }
+            }
+        }
     }
     for (int i = tid; i < (cap + 15) / 16; i += 256) reinterpret_cast<uint4 *>(S.sc)[i] = make_uint4(0, 0, 0, 0);
-    {
-        const uint32_t mw = a.magic_wcell;
-        for (int i = tid; i < a.scw; i += 256) S.cellOf[i] = (uint8_t)fast_div(i, mw);
+    for (int i = tid; i < tp; i += 256) {
+        S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
+        if (i < a.scw) S.cellOf[i] = (uint8_t)fast_div(i, a.magic_wcell);
     }
-    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
     if (tid < 4) s_cnt[tid] = 0;
     if (tid < 64) s_has[tid] = 0;
     __syncthreads();
