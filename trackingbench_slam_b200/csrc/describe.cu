@@ -40,23 +40,26 @@ __device__ __forceinline__ void gauss_hrow(const W3 a, uint32_t h[4])
 // BORDER = false: word columns whose 12-byte neighbourhood lies inside the row (plain 4-byte loads).
 // BORDER = true : the first word column and the last ones (per-byte reflected gather); a tiny second launch.
 // xw_first / n_xw select the word columns this launch covers.
-template <bool BORDER>
+template <bool BORDER, int ROWS>
 __global__ void __launch_bounds__(128)
 gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride,
             int xw_lo, int xw_hi)   // interior word columns are [xw_lo, xw_hi); the border launch takes the rest
 {
     int xw;
+    int ystrip = blockIdx.y;
     if (!BORDER) {
         xw = xw_lo + blockIdx.x * 128 + threadIdx.x;
         if (xw >= xw_hi) return;
     } else {
+        // few columns, many short row strips: thread = (strip within the CTA, border column)
         const int nwords = (w + 3) >> 2, nb = xw_lo + (nwords - xw_hi);   // border columns: [0,xw_lo) and [xw_hi,nwords)
-        const int i = blockIdx.x * 128 + threadIdx.x;
-        if (i >= nb) return;
+        const int i = threadIdx.x & 7;
+        ystrip = blockIdx.y * 16 + (threadIdx.x >> 3);
+        if (i >= nb || ystrip * ROWS >= h) return;
         xw = i < xw_lo ? i : xw_hi + (i - xw_lo);
     }
-    const int y0 = blockIdx.y * GB_ROWS;
-    const int ny = min(GB_ROWS, h - y0);
+    const int y0 = ystrip * ROWS;
+    const int ny = min(ROWS, h - y0);
     const uint8_t *s = src + (size_t)blockIdx.z * frame_stride;
     uint8_t *d = dst + (size_t)blockIdx.z * frame_stride;
     const int x = 4 * xw;
@@ -137,13 +140,14 @@ int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h,
     const int nwords = (w + 3) >> 2, xw_lo = 1, xw_hi = (w - 8) / 4 + 1;
     {
         dim3 grid(div_up(xw_hi - xw_lo, 128), div_up(h, GB_ROWS), n_frames);
-        gauss7x7_u8<false><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
         TB_LAUNCH_CHECK(ctx);
     }
     {
-        const int nb = xw_lo + (nwords - xw_hi);
-        dim3 grid(div_up(nb, 128), div_up(h, GB_ROWS), n_frames);
-        gauss7x7_u8<true><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        const int nb = xw_lo + (nwords - xw_hi);   // <= 4 (< 8) border word columns
+        (void)nb;
+        dim3 grid(1, div_up(div_up(h, 8), 16), n_frames);   // 8-row strips, 16 strips x 8 column slots per CTA
+        gauss7x7_u8<true, 8><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;

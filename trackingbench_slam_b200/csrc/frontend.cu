@@ -308,7 +308,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
     if (add_points && n_exit > 0) {
         if (n_exit > fe->exit_cap) {
             int rc = dev_alloc(fe, &fe->exit_xy, (size_t)n_exit);
-            if (!rc) rc = dev_alloc(fe, &fe->enid, (size_t)n_exit * fe->B);
+            if (!rc) rc = dev_alloc(fe, &fe->enid, (size_t)n_exit * fe->B * fe->L);   // per (level, frame): all levels run in one launch
             if (rc) return rc;
             fe->exit_cap = n_exit;
         }
@@ -322,6 +322,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
     TB_CUDA(ctx, cudaMemsetAsync(fe->overflow, 0, sizeof(int) * 4, ctx->stream));
 
     int max_budget = 0;
+    OctArgs oct[TB_MAX_LEVELS];
     for (int l = 0; l < L; l++) {
         const LevelGeom &g = fe->g[l];
         if (g.nColsRun > 0 && g.nRowsRun > 0) {
@@ -349,16 +350,18 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
             int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
             if (rc) return rc;
         }
-        OctArgs o;
+        OctArgs &o = oct[l];
         o.cand = fe->cand[l]; o.cand_cap = g.cand_cap; o.n_cand = fe->n_cand + l; o.n_stride = L;
         o.nid = fe->nid[l]; o.N = fe->budget[l];
         o.W = g.maxBX - 16; o.H = g.maxBY - 16; o.nIni = g.nIni; o.hX = g.hX; o.wCell = g.wCell; o.hCell = g.hCell;
-        o.exit_xy = fe->exit_xy; o.n_exit = add_points ? n_exit : 0; o.enid = fe->enid;
+        o.exit_xy = fe->exit_xy; o.n_exit = add_points ? n_exit : 0; o.enid = fe->enid ? fe->enid + (size_t)l * fe->exit_cap * fe->B : nullptr;
         o.kept = fe->kept[l]; o.kept_cap = fe->kept_cap; o.n_kept = fe->n_kept + l; o.overflow = fe->overflow;
         o.node_cap = fe->budget[l] + 4 * (g.nIni > 0 ? g.nIni : 1) + 8;
-        int rc = tb_launch_octree(ctx, o, n_frames);
-        if (rc) return rc;
         if (fe->budget[l] > max_budget) max_budget = fe->budget[l];
+    }
+    {
+        int rc = tb_launch_octree(ctx, oct, L, n_frames);
+        if (rc) return rc;
     }
     for (int l = 0; l < L; l++) {
         const LevelGeom &g = fe->g[l];

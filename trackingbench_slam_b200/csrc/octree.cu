@@ -103,9 +103,14 @@ __device__ void block_bitonic_desc(unsigned long long *key, int m)
 
 extern __shared__ __align__(16) uint8_t oct_smem_raw[];
 
+struct OctArgsAll { OctArgs lv[TB_MAX_LEVELS]; };
+
+// grid = (frames, levels): all (frame, level) problems of a batch in ONE launch, so the short per-level
+// tails overlap instead of serialising eight launches that are each bounded by their slowest CTA.
 __global__ void __launch_bounds__(OCT_THREADS)
-octree_distribute(OctArgs a)
+octree_distribute(const __grid_constant__ OctArgsAll all)
 {
+    const OctArgs &a = all.lv[blockIdx.y];
     const int tid = threadIdx.x;
     const int f = blockIdx.x;
     const int NC = a.node_cap;
@@ -358,17 +363,22 @@ size_t tb_octree_smem_bytes(int node_cap)
     return sizeof(unsigned long long) * m2 + (size_t)node_cap * (2 * sizeof(short4) + 2 * sizeof(int) + 4 * sizeof(int) + 2 * sizeof(int));
 }
 
-int tb_launch_octree(tb_ctx *ctx, const OctArgs &a, int n_frames)
+int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames)
 {
-    size_t smem = tb_octree_smem_bytes(a.node_cap);
-    if (smem > 200 * 1024 || a.node_cap > 8191) return tb_fail(ctx, TB_E_UNSUPPORTED, "octree: per-level budget too large for shared memory");
+    OctArgsAll all;
+    memset(&all, 0, sizeof all);
+    int max_cap = 0;
+    for (int l = 0; l < n_levels; l++) { all.lv[l] = levels[l]; if (levels[l].node_cap > max_cap) max_cap = levels[l].node_cap; }
+    for (int l = 0; l < n_levels; l++) all.lv[l].node_cap = max_cap;   // one shared-memory carve-up for the launch
+    size_t smem = tb_octree_smem_bytes(max_cap);
+    if (smem > 200 * 1024 || max_cap > 8191) return tb_fail(ctx, TB_E_UNSUPPORTED, "octree: per-level budget too large for shared memory");
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(octree_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     ProfScope prof__(ctx, "octree_distribute");
-    octree_distribute<<<n_frames, OCT_THREADS, smem, ctx->stream>>>(a);
+    octree_distribute<<<dim3(n_frames, n_levels), OCT_THREADS, smem, ctx->stream>>>(all);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
