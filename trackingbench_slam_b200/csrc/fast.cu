@@ -65,6 +65,30 @@ __device__ __forceinline__ int fast9_score_m(const uint8_t *p, int tp)
     return max(A, -Bm);
 }
 
+// Same m, both polarities at once in 16-bit lanes: lane 0 = v - ring + 256, lane 1 = ring - v + 256 (both in
+// [1,511], so one 32-bit subtraction per ring pixel forms both without borrows), min/max networks on
+// VIMNMX3.U16x2.  m = max(lane0, lane1) - 256.
+__device__ __forceinline__ int fast9_score_packed(const uint8_t *p, int tp)
+{
+    int r[16];
+    RING_LOAD(p, tp);
+    const uint32_t v = p[0];
+    const uint32_t C = (v | ((255u - v) << 16)) + 0x01000100u;
+    uint32_t P[25];
+#pragma unroll
+    for (int k = 0; k < 16; k++) P[k] = C - ((uint32_t)r[k] * 0xFFFF0001u + 0x00FF0000u);   // ring | (255-ring)<<16
+#pragma unroll
+    for (int k = 16; k < 25; k++) P[k] = P[k - 16];
+    uint32_t best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a = __vimin3_u16x2(__vimin3_u16x2(P[k + 1], P[k + 2], P[k + 3]), __vimin3_u16x2(P[k + 4], P[k + 5], P[k + 6]),
+                                          __vminu2(P[k + 7], P[k + 8]));
+        best = __vimax3_u16x2(best, __vminu2(a, P[k]), __vminu2(a, P[k + 9]));
+    }
+    return max((int)(best & 0xFFFFu), (int)(best >> 16)) - 256;
+}
+
 extern __shared__ __align__(16) uint8_t fast_smem[];
 
 // |ring - centre| > T per byte, result in bit 7 of each byte (T <= 127; K = (127-T)*0x01010101)
@@ -141,8 +165,7 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 //   1+2  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
 //      (N,E,S,W at radius 3) both brighter than centre+T or both darker than centre-T; per 4 px and
 //      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
-//   3  full 16-pixel ring masks + 9-contiguous-arc test           -> corners at T
-//   4  score m of the corners                                     -> m map
+//   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map
 //   5  NMS inside the cell interior, emission with one global atomic per pass
 struct FastSmem {
     uint8_t *tile, *sc, *cellOf, *need;
@@ -213,7 +236,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         if (tid == 0) { s_cnt[1] = s_cnt[0]; }
         __syncthreads();
     }
-    // ---- stage 3: full ring test at T
+    // ---- stage 3+4: arc score m of every prefilter survivor; corner at T <=> m > T (cornerScore is threshold free)
     const int nB = s_cnt[1];
     for (int base = 0; base < nB; base += 256) {
         const int i = base + tid;
@@ -221,50 +244,16 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         int e = 0;
         if (i < nB) {
             e = listB[i];
-            const uint8_t *p = tile + ((e >> 10) + 3) * tp + cs + (e & 1023);
-            const int v = p[0], lo = v - T, hi = v + T;
-            int r[16];
-            RING_LOAD(p, tp);
-            uint32_t mb, md;
-            if (T <= 127) {
-                // byte-SIMD over ring positions: word i holds ring pixels i, i+4, i+8, i+12
-                const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
-                const uint32_t vv = (uint32_t)v * 0x01010101u, vlow = vv & 0x7f7f7f7fu;
-                uint32_t fb = 0, fd = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t w = __byte_perm(__byte_perm(r[i], r[i + 4], 0x0040), __byte_perm(r[i + 8], r[i + 12], 0x0040), 0x5410);
-                    const uint32_t a = absdiff_gt(w, vv, K), g = byte_gt(w, vv, vlow);
-                    fb |= ((a & g) >> (7 - i)) & (0x01010101u << i);    // ring brighter than v+T
-                    fd |= ((a & ~g) >> (7 - i)) & (0x01010101u << i);   // ring darker than v-T
-                }
-                // byte j now holds ring positions 4j..4j+3 in its low nibble: squeeze the four nibbles together
-                uint32_t t = fb | (fb >> 4);
-                mb = (t & 0x00FFu) | ((t >> 8) & 0xFF00u);
-                t = fd | (fd >> 4);
-                md = (t & 0x00FFu) | ((t >> 8) & 0xFF00u);
-            } else {
-                mb = 0; md = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    mb |= ((uint32_t)(hi - r[k]) >> 31) << k;   // ring brighter  (d < -T)
-                    md |= ((uint32_t)(r[k] - lo) >> 31) << k;   // ring darker    (d >  T)
-                }
-            }
-            corner = arc9(mb) || arc9(md);
+            const int rr = e >> 10, cc = e & 1023;
+            const int m = fast9_score_packed(tile + (rr + 3) * tp + cs + cc, tp);
+            corner = m > T;
+            if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
         }
         const int pos = warp_append1(corner, &s_cnt[2]);
         if (corner) listA[pos] = (uint16_t)e;
     }
     __syncthreads();
-    // ---- stage 4: score of the corners
     const int nc = s_cnt[2];
-    for (int i = tid; i < nc; i += 256) {
-        const int e = listA[i];
-        const int rr = e >> 10, cc = e & 1023;
-        sc[rr * a.scw + cc] = (uint8_t)fast9_score_m(tile + (rr + 3) * tp + cs + cc, tp);
-    }
-    __syncthreads();
     // ---- stage 5: NMS inside the cell interior; survivors are staged in listB (free now)
     uint32_t *stage = reinterpret_cast<uint32_t *>(listB);
     for (int base = 0; base < nc; base += 256) {

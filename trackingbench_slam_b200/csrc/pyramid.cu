@@ -52,28 +52,32 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh)
 }
 
 // xtab: int4 per output column {ofs0, ofs1, c0, c1}; ytab likewise.
-// One CTA produces a PYR_TW x PYR_TH output tile.  The source box it needs (rows ytab[first].x ..
-// ytab[last].y, columns xtab[first].x .. xtab[last].y) is staged in shared memory with 16-byte loads
-// that are all issued before any arithmetic (memory-level parallelism: the kernel is HBM-latency bound
-// otherwise); a thread then owns 4 output columns x 4 consecutive output rows, keeps its 4 column
-// entries in registers and reuses the horizontal interpolation of a source row shared by two
-// consecutive output rows.  Every source byte is read from HBM once, every output byte written once.
+// One CTA produces a PYR_TW x PYR_TH output tile in three phases:
+//  (0) the source box it needs (rows ytab[first].x .. ytab[last].y, columns xtab[first].x .. xtab[last].y)
+//      is staged in shared memory with 16-byte loads, all issued before any arithmetic;
+//  (1) horizontal pass ONCE per source row: H[row][dx] = (S[sx0]*a0 + S[sx1]*a1) >> 4  (fits u16), a thread
+//      owns 4 output columns (its 4 table entries stay in registers) and walks the box rows;
+//  (2) vertical pass: dst = (((b0*H0) >> 16) + ((b1*H1) >> 16) + 2) >> 2, 4 pixels per 8-byte H read,
+//      4-byte stores.
+// Every source byte is read from HBM once, every output byte written once; consecutive output rows share
+// their source rows through H instead of recomputing the horizontal interpolation.
 #define PYR_TW 256
 #define PYR_TH 32
-#define PYR_RPT (PYR_TH / 4)   // output rows per thread
 extern __shared__ __align__(16) uint8_t pyr_smem[];
 
 __global__ void __launch_bounds__(256)
 pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
                      uint8_t *__restrict__ dst, int dpitch, size_t dframe,
-                     int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bp)
+                     int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bp, int bh_max)
 {
     const int tid = threadIdx.y * 64 + threadIdx.x;
     const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
     const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
     const uint8_t *s = src + (size_t)blockIdx.z * sframe;
     uint8_t *d = dst + (size_t)blockIdx.z * dframe;
-    // source box (tables are monotone)
+    uint8_t *box = pyr_smem;                                                    // bh_max x bp bytes
+    uint16_t *Hs = reinterpret_cast<uint16_t *>(pyr_smem + (size_t)bh_max * bp); // bh_max x PYR_TW u16
+    // ---- phase 0: source box (tables are monotone)
     const int sx_lo = __ldg(&xtab[tx0]).x & ~15, sx_hi = __ldg(&xtab[tx1]).y;
     const int sy_lo = __ldg(&ytab[ty0]).x, sy_hi = __ldg(&ytab[ty1]).y;
     const int bw16 = (sx_hi - sx_lo + 16) >> 4, bh = sy_hi - sy_lo + 1;
@@ -81,46 +85,41 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
     for (int i = tid; i < bw16 * bh; i += 256) {
         const int r = magic ? (int)__umulhi((uint32_t)i, magic) : i, c = i - r * bw16;
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(sy_lo + r) * spitch + sx_lo) + c);
-        *reinterpret_cast<uint4 *>(pyr_smem + r * bp + 16 * c) = v;
+        *reinterpret_cast<uint4 *>(box + r * bp + 16 * c) = v;
     }
-    const int dx0 = tx0 + threadIdx.x * 4;
-    const int dy0 = ty0 + threadIdx.y * PYR_RPT;
-    const bool active = dx0 <= tx1 && dy0 <= ty1;
-    int4 xt[4], yt[PYR_RPT];
-    if (active) {   // table entries of this thread, fetched while the box is in flight
+    // this thread's 4 output columns (phase 1) — fetched while the box is in flight
+    const int cx = threadIdx.x * 4;               // column group inside the tile
+    int4 xt[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { xt[k] = __ldg(&xtab[min(dx0 + k, dw - 1)]); xt[k].x -= sx_lo; xt[k].y -= sx_lo; }
+    for (int k = 0; k < 4; k++) { xt[k] = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]); xt[k].x -= sx_lo; xt[k].y -= sx_lo; }
+    __syncthreads();
+    // ---- phase 1: horizontal pass, rows threadIdx.y, +4, ...
+    for (int r = threadIdx.y; r < bh; r += 4) {
+        const uint8_t *row = box + r * bp;
+        uint32_t h[4];
 #pragma unroll
-        for (int k = 0; k < PYR_RPT; k++) { yt[k] = __ldg(&ytab[min(dy0 + k, dh - 1)]); yt[k].x -= sy_lo; yt[k].y -= sy_lo; }
+        for (int k = 0; k < 4; k++) h[k] = (uint32_t)((int)row[xt[k].x] * xt[k].z + (int)row[xt[k].y] * xt[k].w) >> 4;
+        *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
     }
     __syncthreads();
-    if (!active) return;
-    int prev_row = -1;
-    int hprev[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int kk = 0; kk < PYR_RPT; kk++) {
-        const int dy = dy0 + kk;
+    // ---- phase 2: vertical pass, 4 columns x 8 rows per thread
+    const int dx0 = tx0 + cx;
+    if (dx0 > tx1) return;
+#pragma unroll 2
+    for (int kk = 0; kk < PYR_TH / 4; kk++) {
+        const int dy = ty0 + threadIdx.y * (PYR_TH / 4) + kk;
         if (dy > ty1) break;
-        int h0[4], h1[4];
-        if (yt[kk].x == prev_row) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) h0[k] = hprev[k];
-        } else {
-            const uint8_t *r0 = pyr_smem + yt[kk].x * bp;
-#pragma unroll
-            for (int k = 0; k < 4; k++) h0[k] = (int)r0[xt[k].x] * xt[k].z + (int)r0[xt[k].y] * xt[k].w;
-        }
-        const uint8_t *r1 = pyr_smem + yt[kk].y * bp;
-#pragma unroll
-        for (int k = 0; k < 4; k++) h1[k] = (int)r1[xt[k].x] * xt[k].z + (int)r1[xt[k].y] * xt[k].w;
+        const int4 yt = __ldg(&ytab[dy]);
+        const uint2 a = *reinterpret_cast<const uint2 *>(Hs + (yt.x - sy_lo) * PYR_TW + cx);
+        const uint2 b = *reinterpret_cast<const uint2 *>(Hs + (yt.y - sy_lo) * PYR_TW + cx);
+        const int h0[4] = {(int)(a.x & 0xFFFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16)};
+        const int h1[4] = {(int)(b.x & 0xFFFF), (int)(b.x >> 16), (int)(b.y & 0xFFFF), (int)(b.y >> 16)};
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int v = (((yt[kk].z * (h0[k] >> 4)) >> 16) + ((yt[kk].w * (h1[k] >> 4)) >> 16) + 2) >> 2;
+            const int v = (((yt.z * h0[k]) >> 16) + ((yt.w * h1[k]) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 0xFF) << (8 * k);
-            hprev[k] = h1[k];
         }
-        prev_row = yt[kk].y;
         if (dx0 + 3 < dw) {
             *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
         } else {
@@ -162,12 +161,12 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
         dim3 grid(div_up(dw, 64), div_up(dh, 4), n_frames), block(64, 4);
         pyr_resize_area2_u8<<<grid, block, 0, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh);
     } else {
-        const size_t smem = (size_t)bp * bh;
+        const size_t smem = (size_t)bp * bh + (size_t)bh * PYR_TW * sizeof(uint16_t);
         if (smem > 200 * 1024) return tb_fail(ctx, TB_E_UNSUPPORTED, "resize: scale factor too small for the shared-memory tile");
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), n_frames), block(64, 4);
-        pyr_resize_linear_u8<<<grid, block, smem, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh, xtab, ytab, bp);
+        pyr_resize_linear_u8<<<grid, block, smem, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh, xtab, ytab, bp, bh);
     }
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
