@@ -231,37 +231,32 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     }
     __syncthreads();
     // (stage 2, the signed compass test, is part of the SWAR prefilter; with T > 127 every pixel goes on)
-    {
-        uint16_t *t = listA; listA = listB; listB = t;   // stage 3 reads its input from listB
-        if (tid == 0) { s_cnt[1] = s_cnt[0]; }
-        __syncthreads();
-    }
     // ---- stage 3+4: arc score m of every prefilter survivor; corner at T <=> m > T (cornerScore is threshold free)
-    const int nB = s_cnt[1];
+    const int nB = s_cnt[0];
     for (int base = 0; base < nB; base += 256) {
         const int i = base + tid;
         bool corner = false;
         int e = 0;
         if (i < nB) {
-            e = listB[i];
+            e = listA[i];
             const int rr = e >> 10, cc = e & 1023;
             const int m = fast9_score_packed(tile + (rr + 3) * tp + cs + cc, tp);
             corner = m > T;
             if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
         }
         const int pos = warp_append1(corner, &s_cnt[2]);
-        if (corner) listA[pos] = (uint16_t)e;
+        if (corner) listB[pos] = (uint16_t)e;
     }
     __syncthreads();
     const int nc = s_cnt[2];
-    // ---- stage 5: NMS inside the cell interior; survivors are staged in listB (free now)
-    uint32_t *stage = reinterpret_cast<uint32_t *>(listB);
+    // ---- stage 5: NMS inside the cell interior; survivors are staged in listA (free now)
+    uint32_t *stage = reinterpret_cast<uint32_t *>(listA);
     for (int base = 0; base < nc; base += 256) {
         const int i = base + tid;
         bool keep = false;
         uint32_t val = 0;
         if (i < nc) {
-            const int e = listA[i];
+            const int e = listB[i];
             const int rr = e >> 10, cc = e & 1023;
             const int m = sc[rr * a.scw + cc];
             const int cell = S.cellOf[cc];
