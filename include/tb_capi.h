@@ -195,6 +195,18 @@ int tb_set_match_impl(tb_ctx *ctx, int impl);
 int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int32_t *q_frames, const int32_t *t_frames,
                              float ratio, float minTh, void *matches_dptr, int capacity, void *counts_i32_dptr);
 
+/* Device-resident, batched Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531) over frames of the frontend's
+ * last extract (test_vo-style tracking, BASELINE config 5): pair p projects the map points attached to frame
+ * f2_frames[p]'s keypoints into frame f1_frames[p] whose pose is Tcw1[16*p..] (host, row-major). Map points are
+ * device arrays indexed [frame][tb_frontend_kp_capacity()]: mp_valid (u8), mp_xyz (3 x f32); a map point carries
+ * the descriptor of the keypoint it was created from. f1_matched (u8, same indexing) may be NULL.
+ * Outputs on the device: matches_dptr[p*capacity + i] (cv::DMatch), counts_dptr[p]. No host synchronisation
+ * besides staging the small pair table. */
+int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs,
+                                     const int32_t *f1_frames, const int32_t *f2_frames, const float *Tcw1,
+                                     const void *f1_matched_dptr, const void *mp_valid_dptr, const void *mp_xyz_dptr,
+                                     const float *sf1, void *matches_dptr, int capacity, void *counts_i32_dptr);
+
 /* Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/types/Frame.cpp:187-265) as a query:
  * indices in the reference's traversal order. kps on the host. */
 int tb_features_in_area(tb_ctx *ctx, const tb_keypoint *kps, int n, int img_cols, int img_rows,

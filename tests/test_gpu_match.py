@@ -243,3 +243,62 @@ def test_batched_bf_popc_and_tcgen05_agree_with_oracle(tb, ctx, oracle, images, 
     finally:
         ctx.set_match_impl(0)
         fe.close()
+
+
+def test_frontend_batched_projection_device_resident(tb, ctx, oracle, images):
+    """tb_frontend_search_by_projection: map points, descriptors and results stay on the device (config 5 path)."""
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    frames = np.stack([images['left'], images['right'], synth_frame(1, W, H), synth_frame(2, W, H)])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=4, max_target=tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(4)
+        fe.extract(4, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(4)
+        cap = fe.kp_cap
+        fx, fy, cx, cy = 718.856, 718.856, 607.1928, 185.2157
+        rng = np.random.default_rng(9)
+        valid = np.zeros((4, cap), np.uint8)
+        xyz = np.zeros((4, cap, 3), np.float32)
+        matched = (rng.random((4, cap)) < 0.2).astype(np.uint8)
+        for f in range(4):
+            n = counts[f]
+            depth = rng.uniform(4.0, 40.0, n).astype(np.float32)
+            valid[f, :n] = rng.random(n) < 0.9
+            xyz[f, :n, 0] = (kps[f, :n]['x'] - np.float32(cx)) / np.float32(fx) * depth
+            xyz[f, :n, 1] = (kps[f, :n]['y'] - np.float32(cy)) / np.float32(fy) * depth
+            xyz[f, :n, 2] = depth
+        pairs = [(1, 0), (0, 1), (3, 2), (2, 3), (0, 0)]
+        T = np.tile(np.eye(4, dtype=np.float32), (len(pairs), 1, 1))
+        T[0, 0, 3] = -0.573
+        T[1, 0, 3] = 0.573
+        T[2, 0, 3], T[2, 1, 3] = -0.02, 0.01
+        T[3, :3, :3] = np.array([[0.9999, -0.01, 0.0], [0.01, 0.9999, 0.0], [0.0, 0.0, 1.0]], np.float32)
+        cam = tb.Pinhole(fx, fy, cx, cy, W, H, (tb.capi.C.c_float * 5)(0, 0, 0, 0, 0))
+        camo = oracle.Pinhole(fx, fy, cx, cy, W, H, (oracle.C.c_float * 5)(0, 0, 0, 0, 0))
+        for chk, use_matched in ((1, False), (0, True)):
+            p = tb.MatcherParams(30, 60, 30, chk, 25.0)
+            po = oracle.MatcherParams(30, 60, 30, chk, 25.0)
+            d_valid, d_xyz, d_matched = dev(valid), dev(xyz), dev(matched)
+            m = torch.zeros((len(pairs), cap, 4), dtype=torch.int32, device='cuda')
+            c = torch.zeros(len(pairs), dtype=torch.int32, device='cuda')
+            fe.search_by_projection(p, cam, [q[0] for q in pairs], [q[1] for q in pairs], T,
+                                    d_matched.data_ptr() if use_matched else None, d_valid.data_ptr(), d_xyz.data_ptr(), sf,
+                                    m.data_ptr(), cap, c.data_ptr())
+            ctx.sync()
+            cn = c.cpu().numpy()
+            mm = m.cpu().numpy().view(np.uint8).reshape(len(pairs), cap, 16)
+            total = 0
+            for i, (f1, f2) in enumerate(pairs):
+                n1, n2 = counts[f1], counts[f2]
+                exp = oracle.search_by_projection(po, camo, T[i], kps[f1, :n1], desc[f1, :n1], matched[f1, :n1] if use_matched else None, sf, W, H,
+                                                  kps[f2, :n2], valid[f2, :n2], xyz[f2, :n2], desc[f2, :n2])
+                assert cn[i] == len(exp), (chk, i, cn[i], len(exp))
+                assert mm[i, :cn[i]].tobytes() == exp.tobytes(), (chk, i)
+                total += len(exp)
+            assert total > 200
+    finally:
+        fe.close()

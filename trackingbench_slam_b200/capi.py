@@ -31,7 +31,7 @@ EXPORTS = [
     'tb_frontend_get_level_counts', 'tb_orb_extract_host', 'tb_fast_extract_host',
     'tb_hamming_pairs_device', 'tb_knn2_device', 'tb_match_bf_cross_device', 'tb_search_by_bf_device',
     'tb_match_bf_cross_host', 'tb_search_by_bf_host', 'tb_hamming_pairs_host',
-    'tb_frontend_search_by_bf', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
+    'tb_frontend_search_by_bf', 'tb_frontend_search_by_projection', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
     'tb_search_by_projection_map', 'tb_three_maxima',
 ]
 
@@ -336,3 +336,18 @@ class Frontend:
         t = np.ascontiguousarray(t_frames, np.int32)
         self.ctx.check(lib().tb_frontend_search_by_bf(self.h, len(q), _vp(q), _vp(t), C.c_float(ratio), C.c_float(minTh),
                                                       _vp(matches_dptr), int(capacity), _vp(counts_dptr)))
+
+
+def _frontend_search_by_projection(self, params, cam, f1_frames, f2_frames, Tcw1, f1_matched_dptr, mp_valid_dptr, mp_xyz_dptr,
+                                   sf1, matches_dptr, capacity, counts_dptr):
+    """Batched device-resident searchByProjection(F1,F2); Tcw1: [n_pairs,4,4] float32 host array."""
+    f1 = np.ascontiguousarray(f1_frames, np.int32)
+    f2 = np.ascontiguousarray(f2_frames, np.int32)
+    T = np.ascontiguousarray(Tcw1, np.float32).reshape(len(f1), 16)
+    sf1 = np.ascontiguousarray(sf1, np.float32)
+    self.ctx.check(lib().tb_frontend_search_by_projection(self.h, C.byref(params), C.byref(cam), len(f1), _vp(f1), _vp(f2), _vp(T),
+                                                          _vp(f1_matched_dptr), _vp(mp_valid_dptr), _vp(mp_xyz_dptr), _vp(sf1),
+                                                          _vp(matches_dptr), int(capacity), _vp(counts_dptr)))
+
+
+Frontend.search_by_projection = _frontend_search_by_projection

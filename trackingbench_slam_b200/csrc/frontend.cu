@@ -36,6 +36,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     cudaSetDevice(ctx->device);
     tb_match_ws_free(ctx);
     tb_match_tc_free(ctx);
+    tb_window_ws_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -510,4 +511,17 @@ extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int3
         if (q_frames[p] < 0 || q_frames[p] >= fe->B || t_frames[p] < 0 || t_frames[p] >= fe->B) return TB_E_INVALID;
     return tb_match_bf_batched(fe->ctx, n_pairs, q_frames, t_frames, fe->B, fe->desc, (size_t)fe->kp_cap * 32, fe->n_kp, fe->kp_cap,
                                ratio, minTh, (tb_match *)matches, capacity, (int *)counts);
+}
+
+extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs,
+                                                const int32_t *f1_frames, const int32_t *f2_frames, const float *Tcw1,
+                                                const void *f1_matched, const void *mp_valid, const void *mp_xyz,
+                                                const float *sf1, void *matches, int capacity, void *counts)
+{
+    if (!fe || !p || !cam || n_pairs < 0 || !f1_frames || !f2_frames || !Tcw1 || !mp_valid || !mp_xyz || !sf1 || !matches || !counts) return TB_E_INVALID;
+    for (int i = 0; i < n_pairs; i++)
+        if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
+    return tb_window_projection_batched(fe->ctx, p, cam, n_pairs, f1_frames, f2_frames, Tcw1, fe->B, fe->kps, fe->desc, fe->kp_cap, fe->n_kp,
+                                        (const uint8_t *)f1_matched, (const uint8_t *)mp_valid, (const float *)mp_xyz, sf1, fe->L,
+                                        fe->g[0].w, fe->g[0].h, (tb_match *)matches, capacity, (int *)counts);
 }

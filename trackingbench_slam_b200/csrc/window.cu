@@ -552,3 +552,229 @@ extern "C" int tb_search_by_projection_map(tb_ctx *ctx, const tb_matcher_params 
     // no orientation check in this overload (matcher.cpp:539-617)
     return emit_and_download(ctx, buf, res, n_mp, 0, p->HISTO_LENGTH > 0 ? p->HISTO_LENGTH : 1, out, capacity, n);
 }
+
+// ------------------------------------------------------------------------------------------
+// Device-resident, batched searchByProjection over frames of one extract result (BASELINE config 5:
+// test_vo-style tracking).  Nothing leaves the GPU: grids are built per frame by one CTA, one warp per
+// (pair, F2 keypoint) walks the window, one CTA per pair applies the rotation histogram and compacts.
+// ------------------------------------------------------------------------------------------
+#define GB_MAXKP 8192
+
+// CSR grid of every frame: cell_start[f][GRID_CELLS+1], items[f][kp_cap] (insertion = index order)
+__global__ void __launch_bounds__(1024)
+grid_build_batched(const tb_keypoint *__restrict__ kps, int kp_cap, const int *__restrict__ counts, float wInv, float hInv,
+                   int *__restrict__ cell_start, int *__restrict__ items)
+{
+    __shared__ short s_cell[GB_MAXKP];
+    __shared__ int s_cnt[GRID_CELLS + 1];
+    __shared__ int s_part[1024];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(counts[f], min(kp_cap, GB_MAXKP));
+    const tb_keypoint *k = kps + (size_t)f * kp_cap;
+    for (int i = tid; i <= GRID_CELLS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int px = (int)roundf(__fmul_rn(k[i].x, wInv)), py = (int)roundf(__fmul_rn(k[i].y, hInv));
+        int c = -1;
+        if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) { c = px * GRID_ROWS + py; atomicAdd(&s_cnt[c], 1); }
+        s_cell[i] = (short)c;
+    }
+    __syncthreads();
+    // exclusive scan of the 4320 cell counts
+    const int ipt = (GRID_CELLS + 1023) / 1024;
+    const int b0 = min(tid * ipt, GRID_CELLS), b1 = min(b0 + ipt, GRID_CELLS);
+    int sum = 0;
+    for (int i = b0; i < b1; i++) sum += s_cnt[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { int v = tid >= o ? s_part[tid - o] : 0; __syncthreads(); s_part[tid] += v; __syncthreads(); }
+    int run = s_part[tid] - sum;
+    int *cs = cell_start + (size_t)f * (GRID_CELLS + 1);
+    for (int i = b0; i < b1; i++) { const int c = s_cnt[i]; s_cnt[i] = run; cs[i] = run; run += c; }
+    if (tid == 1023) cs[GRID_CELLS] = s_part[1023];
+    __syncthreads();
+    // place every keypoint at cell_start + (number of earlier keypoints in the same cell)
+    int *it = items + (size_t)f * kp_cap;
+    for (int i = tid; i < n; i += 1024) {
+        const int c = s_cell[i];
+        if (c < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < i; j++) rank += (s_cell[j] == c);
+        it[s_cnt[c] + rank] = i;
+    }
+}
+
+struct ProjPair { int f1, f2; float T[16]; };
+
+__global__ void __launch_bounds__(256)
+projection_query_batched(const ProjPair *__restrict__ pairs, const tb_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc,
+                         int kp_cap, const int *__restrict__ counts, const int *__restrict__ cell_start, const int *__restrict__ items,
+                         float wInv, float hInv, const uint8_t *__restrict__ f1_matched, SfTab sf1, tb_pinhole cam,
+                         const uint8_t *__restrict__ mp_valid, const float *__restrict__ mp_xyz, tb_matcher_params p, QRes *__restrict__ res)
+{
+    const ProjPair &pr = pairs[blockIdx.y];
+    const int i2 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int n2 = min(counts[pr.f2], kp_cap);
+    if (i2 >= n2) return;
+    GridDev g1;
+    g1.cell_start = cell_start + (size_t)pr.f1 * (GRID_CELLS + 1);
+    g1.items = items + (size_t)pr.f1 * kp_cap;
+    g1.kps = kps + (size_t)pr.f1 * kp_cap;
+    g1.wInv = wInv; g1.hInv = hInv;
+    const uint8_t *d1 = desc + (size_t)pr.f1 * kp_cap * 32;
+    const uint8_t *matched = f1_matched ? f1_matched + (size_t)pr.f1 * kp_cap : nullptr;
+    const size_t o2 = (size_t)pr.f2 * kp_cap + i2;
+    QRes r = {0, -1, i2, 0, 0};
+    bool go = mp_valid[o2] != 0;
+    float u = 0, v = 0;
+    Pose T;
+#pragma unroll
+    for (int k = 0; k < 16; k++) T.T[k] = pr.T[k];
+    if (go) {
+        float xc[3];
+        transform_pt(T, mp_xyz + 3 * o2, xc);
+        const float invzc = __fdiv_rn(1.0f, xc[2]);
+        if (invzc < 0) go = false;
+        else {
+            world2cam(cam, xc, u, v);
+            if (!is_in_frame(cam, u, v)) go = false;
+        }
+    }
+    if (go) {
+        const tb_keypoint kp2 = kps[o2];
+        const int oct = kp2.octave;
+        const float radius = __fmul_rn(p.nRatio, sf1.sf[oct]);
+        uint32_t q[8];
+        load_desc(q, desc + o2 * 32);   // the map point carries the descriptor of the keypoint that created it
+        Top2 t = window_scan(g1, u, v, radius, oct - 1, oct + 1, q, d1, matched, nullptr, nullptr);
+        if (t.i1 >= 0) {
+            const int bestDist = (int)(t.k1 >> 20);
+            if (bestDist <= p.TH_HIGH && bestDist < 256) {
+                r.ok = 1; r.q = t.i1; r.dist = bestDist;
+                if (p.checkOrientation) r.bin = rot_bin(kp2.angle, g1.kps[t.i1].angle, p.HISTO_LENGTH);
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0) res[(size_t)blockIdx.y * kp_cap + i2] = r;
+}
+
+__global__ void __launch_bounds__(256)
+emit_matches_batched(const ProjPair *__restrict__ pairs, const QRes *__restrict__ res, int kp_cap, const int *__restrict__ counts,
+                     int check_orientation, int histo, tb_match *__restrict__ out, int capacity, int *__restrict__ out_n)
+{
+    // same logic as emit_matches, one CTA per pair
+    __shared__ int s_hist[256];
+    __shared__ int s_sel[3], s_nsel;
+    __shared__ int s_chunk[2048];
+    __shared__ int s_run;
+    const int tid = threadIdx.x, pidx = blockIdx.x;
+    const int n = min(counts[pairs[pidx].f2], kp_cap);
+    const QRes *rs = res + (size_t)pidx * kp_cap;
+    tb_match *o = out + (size_t)pidx * capacity;
+    s_hist[tid] = 0;
+    __syncthreads();
+    if (check_orientation) {
+        for (int i = tid; i < n; i += 256) if (rs[i].ok) atomicAdd(&s_hist[rs[i].bin], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < histo; i++) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            int ns = 0;
+            for (int b = 0; b < histo; b++) if (b == ind1 || b == ind2 || b == ind3) s_sel[ns++] = b;
+            s_nsel = ns;
+        }
+    } else if (tid == 0) { s_nsel = 1; s_sel[0] = -1; }
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int sidx = 0; sidx < s_nsel; sidx++) {
+        const int bsel = s_sel[sidx];
+        for (int base = 0; base < n; base += 2048) {
+            const int m = min(2048, n - base);
+            int mine[8]; int nm = 0;
+            for (int i = tid; i < m; i += 256) {
+                const QRes r = rs[base + i];
+                const int fl = (r.ok && (bsel < 0 || r.bin == bsel)) ? 1 : 0;
+                s_chunk[i] = fl; mine[nm++] = fl;
+            }
+            __syncthreads();
+            const int tot = scan256w(s_chunk, m);
+            const int run = s_run;
+            nm = 0;
+            for (int i = tid; i < m; i += 256) {
+                if (mine[nm++]) {
+                    const int pos = run + s_chunk[i];
+                    if (pos < capacity) { const QRes r = rs[base + i]; tb_match mt = {r.q, r.t, 0, (float)r.dist}; o[pos] = mt; }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_run = run + tot;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) out_n[pidx] = s_run;
+}
+
+struct WinWs { int *cell_start = nullptr, *items = nullptr; QRes *res = nullptr; ProjPair *pairs = nullptr; size_t frames = 0, pairs_cap = 0, kp_cap = 0; };
+
+int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs, const int32_t *f1_frames,
+                                 const int32_t *f2_frames, const float *Tcw1, int n_frames, const tb_keypoint *kps, const uint8_t *desc,
+                                 int kp_cap, const int *counts, const uint8_t *f1_matched, const uint8_t *mp_valid, const float *mp_xyz,
+                                 const float *sf1, int n_levels, int cols, int rows, tb_match *matches, int capacity, int *out_counts)
+{
+    if (n_pairs <= 0) return TB_OK;
+    if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched projection matcher supports up to 8192 keypoints per frame");
+    if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (!ctx->wws) ctx->wws = new WinWs();
+    WinWs &w = *ctx->wws;
+    if ((size_t)n_frames > w.frames || (size_t)kp_cap != w.kp_cap) {
+        cudaFree(w.cell_start); cudaFree(w.items);
+        TB_CUDA(ctx, cudaMalloc(&w.cell_start, sizeof(int) * (size_t)n_frames * (GRID_CELLS + 1)));
+        TB_CUDA(ctx, cudaMalloc(&w.items, sizeof(int) * (size_t)n_frames * kp_cap));
+        w.frames = n_frames; w.kp_cap = kp_cap; w.pairs_cap = 0;
+    }
+    if ((size_t)n_pairs > w.pairs_cap) {
+        cudaFree(w.res); cudaFree(w.pairs);
+        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
+        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
+        w.pairs_cap = n_pairs;
+    }
+    std::vector<ProjPair> hp(n_pairs);
+    for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; memcpy(hp[i].T, Tcw1 + 16 * (size_t)i, sizeof(float) * 16); }
+    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    volatile float hInv = (float)GRID_COLS / (float)cols, wInv = (float)GRID_ROWS / (float)rows;   // Frame.cpp:30-31
+    {
+        ProfScope prof__(ctx, "grid_build_batched");
+        grid_build_batched<<<n_frames, 1024, 0, ctx->stream>>>(kps, kp_cap, counts, wInv, hInv, w.cell_start, w.items);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    SfTab sf; memset(&sf, 0, sizeof sf);
+    for (int i = 0; i < n_levels && i < TB_MAX_LEVELS; i++) sf.sf[i] = sf1[i];
+    {
+        ProfScope prof__(ctx, "projection_query_batched");
+        projection_query_batched<<<dim3(div_up(kp_cap, 8), n_pairs), 256, 0, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, w.cell_start, w.items,
+                                                                                              wInv, hInv, f1_matched, sf, *cam, mp_valid, mp_xyz, *p, w.res);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope prof__(ctx, "emit_matches_batched");
+        emit_matches_batched<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, w.res, kp_cap, counts, p->checkOrientation, p->HISTO_LENGTH, matches, capacity, out_counts);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    return TB_OK;
+}
+
+void tb_window_ws_free(tb_ctx *ctx)
+{
+    if (!ctx->wws) return;
+    cudaFree(ctx->wws->cell_start); cudaFree(ctx->wws->items); cudaFree(ctx->wws->res); cudaFree(ctx->wws->pairs);
+    delete ctx->wws;
+    ctx->wws = nullptr;
+}
