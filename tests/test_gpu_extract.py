@@ -237,3 +237,39 @@ def test_fast_extractor_vs_oracle(tb, ctx, oracle, images):
     with pytest.raises(tb.TbError) as ei:
         ctx.fast_extract_host(lv, inv, 500, 20.0)
     assert ei.value.code == tb.capi.TB_E_INVALID
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_random_shapes_and_thresholds_sweep(tb, ctx, oracle, images, seed):
+    """Property sweep: odd sizes (cell widths 30..40, tiles whose origin is not 8-byte aligned, clipped last cells,
+    1-3 initial octree nodes), random thresholds / budgets / level counts; textured and noisy content."""
+    rng = np.random.default_rng(100 + seed)
+    L = images['left']
+    for _ in range(6):
+        w = int(rng.choice([int(rng.integers(120, 700)), int(rng.integers(353, 363)), int(rng.integers(290, 300))]))
+        h = int(rng.integers(100, 380))
+        x0, y0 = int(rng.integers(0, L.shape[1] - w)), int(rng.integers(0, L.shape[0] - h + 1)) if h < L.shape[0] else 0
+        img = np.ascontiguousarray(L[y0:y0 + h, x0:x0 + w])
+        if rng.random() < 0.4:
+            img = np.clip(img.astype(np.int16) + rng.integers(-12, 13, img.shape), 0, 255).astype(np.uint8)
+        nl = int(rng.integers(1, 5))
+        sc = float(rng.choice([0.8, 1 / 1.2, 0.6, 0.9]))
+        tgt = int(rng.integers(50, 900))
+        a = float(rng.choice([20, 40, 80, 130]))
+        b = float(rng.choice([5, 7, 30]))
+        if b > a:
+            a, b = b, a
+        sf, lw, lh = tb.pyramid_geometry(w, h, max(nl, 2), sc)
+        sf, lw, lh = sf[:max(nl, 2)], lw[:max(nl, 2)], lh[:max(nl, 2)]
+        fe = tb.Frontend(ctx, lw, lh, max_batch=1, max_target=tgt)
+        try:
+            fe.upload_frames(0, img[None])
+            fe.build_pyramid(1)
+            fe.extract(1, sf, tgt, a, b)
+            k, d = fe.get_results(0)
+            lv, sfo = oracle.pyramid(img, max(nl, 2), sc)
+            ko, do, _ = oracle.orb_extract(lv, sfo, tgt, a, b)
+            assert kp_bytes_equal(k, ko), (w, h, nl, sc, tgt, a, b, len(k), len(ko))
+            assert np.array_equal(d, do), (w, h, nl, sc, tgt, a, b)
+        finally:
+            fe.close()
