@@ -16,6 +16,9 @@ struct tb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side stream + events: the Gaussian levels run here, concurrently with the latency-bound octree kernel
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;

@@ -127,12 +127,12 @@ __global__ void gauss7x7_u8_tiny(const uint8_t *__restrict__ src, uint8_t *__res
     dst[(size_t)blockIdx.z * frame_stride + (size_t)y * pitch + x] = (uint8_t)((acc + 32768u) >> 16);
 }
 
-int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
+int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
 {
     ProfScope prof__(ctx, "gauss7x7_u8");
     if (h < 4 || w < 16) {
         dim3 grid(div_up(w, 128), h, n_frames);
-        gauss7x7_u8_tiny<<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride);
+        gauss7x7_u8_tiny<<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride);
         TB_LAUNCH_CHECK(ctx);
         return TB_OK;
     }
@@ -140,14 +140,14 @@ int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h,
     const int nwords = (w + 3) >> 2, xw_lo = 1, xw_hi = (w - 8) / 4 + 1;
     {
         dim3 grid(div_up(xw_hi - xw_lo, 128), div_up(h, GB_ROWS), n_frames);
-        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
         TB_LAUNCH_CHECK(ctx);
     }
     {
         const int nb = xw_lo + (nwords - xw_hi);   // <= 4 (< 8) border word columns
         (void)nb;
         dim3 grid(1, div_up(div_up(h, 8), 16), n_frames);   // 8-row strips, 16 strips x 8 column slots per CTA
-        gauss7x7_u8<true, 8><<<grid, 128, 0, ctx->stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        gauss7x7_u8<true, 8><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;

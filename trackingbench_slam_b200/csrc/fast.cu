@@ -32,39 +32,6 @@ __device__ __forceinline__ int max3i(int a, int b, int c) { return __vimax3_s32(
     r[8] = (p)[-3 * (tp)];      r[9] = (p)[-3 * (tp) - 1];  r[10] = (p)[-2 * (tp) - 2]; r[11] = (p)[-(tp) - 3];    \
     r[12] = (p)[-3];            r[13] = (p)[(tp) - 3];      r[14] = (p)[2 * (tp) - 2];  r[15] = (p)[3 * (tp) - 1]; }
 
-// 9 contiguous set bits in a 16-bit circular mask
-__device__ __forceinline__ bool arc9(uint32_t m16)
-{
-    uint32_t x = m16 | (m16 << 16);
-    uint32_t t = x & (x >> 1);
-    t &= t >> 2;
-    t &= t >> 4;     // runs >= 8
-    t &= x >> 8;     // runs >= 9
-    return t != 0;
-}
-
-// m = max(A,B) for a pixel known to be a corner (OpenCV cornerScore<16> without the threshold floor)
-__device__ __forceinline__ int fast9_score_m(const uint8_t *p, int tp)
-{
-    int r[16];
-    RING_LOAD(p, tp);
-    const int v = p[0];
-    int d[25];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - r[k];
-#pragma unroll
-    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
-    int A = -256, Bm = 256; // Bm = min over arcs of max
-#pragma unroll
-    for (int k = 0; k < 16; k += 2) {
-        int a = min3i(min3i(d[k + 1], d[k + 2], d[k + 3]), min3i(d[k + 4], d[k + 5], d[k + 6]), min(d[k + 7], d[k + 8]));
-        A = max3i(A, min(a, d[k]), min(a, d[k + 9]));
-        int b = max3i(max3i(d[k + 1], d[k + 2], d[k + 3]), max3i(d[k + 4], d[k + 5], d[k + 6]), max(d[k + 7], d[k + 8]));
-        Bm = min3i(Bm, max(b, d[k]), max(b, d[k + 9]));
-    }
-    return max(A, -Bm);
-}
-
 // Same m, both polarities at once in 16-bit lanes: lane 0 = v - ring + 256, lane 1 = ring - v + 256 (both in
 // [1,511], so one 32-bit subtraction per ring pixel forms both without borrows), min/max networks on
 // VIMNMX3.U16x2.  m = max(lane0, lane1) - 256.
@@ -399,14 +366,11 @@ size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     ProfScope prof__(ctx, "fast9_cells");
     dim3 grid(div_up(nColsRun, a.G), nRowsRun, n_frames);
     fast9_cells<<<grid, 256, smem, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
+
+void tb_fast_init_device() { cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }

@@ -27,6 +27,14 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return TB_E_CUDA;
+    }
+    tb_fast_init_device(); tb_octree_init_device(); tb_pyramid_init_device(); tb_match_tc_init_device();
     *out = c;
     return TB_OK;
 }
@@ -37,6 +45,9 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_match_ws_free(ctx);
     tb_match_tc_free(ctx);
     tb_window_ws_free(ctx);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -360,14 +371,27 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
         o.node_cap = fe->budget[l] + 4 * (g.nIni > 0 ? g.nIni : 1) + 8;
         if (fe->budget[l] > max_budget) max_budget = fe->budget[l];
     }
+    // The octree kernel is latency bound (one CTA per (frame, level), most SMs idle) while the Gaussian only
+    // needs the pyramid: run the Gaussian levels on the side stream, concurrently with the octree.
+    // (With per-kernel profiling on, everything stays on the main stream so the event pairs stay meaningful.)
+    const bool overlap = !ctx->profiling;
+    cudaStream_t gs = overlap ? ctx->side : ctx->stream;
+    if (overlap) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    }
     {
         int rc = tb_launch_octree(ctx, oct, L, n_frames);
         if (rc) return rc;
     }
     for (int l = 0; l < L; l++) {
         const LevelGeom &g = fe->g[l];
-        int rc = tb_launch_gauss(ctx, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
+        int rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
         if (rc) return rc;
+    }
+    if (overlap) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     DescArgs d;
     memset(&d, 0, sizeof d);

@@ -39,7 +39,7 @@ struct OctArgs {
 };
 size_t tb_octree_smem_bytes(int node_cap);
 int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames);
-int tb_launch_gauss(tb_ctx *ctx, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames);
+int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames);
 struct DescLevel {
     const uint8_t *raw, *blur;
     int pitch; size_t frame_stride;
@@ -66,3 +66,8 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
                                  const int32_t *f2_frames, const float *Tcw1, int n_frames, const tb_keypoint *kps, const uint8_t *desc,
                                  int kp_cap, const int *counts, const uint8_t *f1_matched, const uint8_t *mp_valid, const float *mp_xyz,
                                  const float *sf1, int n_levels, int cols, int rows, tb_match *matches, int capacity, int *out_counts);
+// per-device kernel attributes (dynamic shared memory opt-in); called by tb_ctx_create for its device
+void tb_fast_init_device();
+void tb_octree_init_device();
+void tb_pyramid_init_device();
+void tb_match_tc_init_device();

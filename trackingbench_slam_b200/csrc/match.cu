@@ -12,7 +12,6 @@
 // Ties are broken by lowest train index (strict < while scanning in index order).
 #include "common.cuh"
 #include "kernels.cuh"
-#include <cstdlib>
 
 #define KNN_THREADS 128
 #define KNN_TILE 128
@@ -358,14 +357,6 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
         TB_LAUNCH_CHECK(ctx);
     }
     ProfScope prof2__(ctx, "bf_cross_filter");
-    if (const char *dump = getenv("TB_DUMP_KNN")) {   // developer aid: raw nearest-neighbour tables of both implementations
-        std::vector<int> hi((size_t)2 * n_pairs * kp_cap), hd((size_t)2 * n_pairs * kp_cap);
-        cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(hi.data(), w.best_idx, hi.size() * sizeof(int), cudaMemcpyDeviceToHost);
-        cudaMemcpy(hd.data(), w.best_dist, hd.size() * sizeof(int), cudaMemcpyDeviceToHost);
-        std::string fn = std::string(dump) + (ctx->match_impl ? ".tc" : ".popc");
-        if (FILE *fp = fopen(fn.c_str(), "wb")) { fwrite(hi.data(), sizeof(int), hi.size(), fp); fwrite(hd.data(), sizeof(int), hd.size(), fp); fclose(fp); }
-    }
     bf_cross_filter<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, n_pairs, kp_cap, w.best_idx, w.best_dist, w.scratch, 1, ratio, minTh,
                                                       matches, capacity, out_counts);
     TB_LAUNCH_CHECK(ctx);

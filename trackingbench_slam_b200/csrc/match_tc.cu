@@ -300,13 +300,7 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *
     }
     build_tc_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w->pairs, n_pairs, d_q_frames, d_t_frames, w->exp, exp_stride, counts);
     TB_LAUNCH_CHECK(ctx);
-    static bool attr_set = false;
     const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
-    if (!attr_set) {
-        cudaFuncSetAttribute(hamming_i8mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     {
         ProfScope prof__(ctx, "hamming_i8mma");
         dim3 grid(div_up(kp_cap, TC_M), 2 * n_pairs);
@@ -343,9 +337,7 @@ int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, 
     }
     TcPair pd = {eq, et, nq, nt};
     TB_CUDA(ctx, cudaMemcpyAsync(w->pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
-    static bool attr_set = false;
     const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
-    if (!attr_set) { cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     {
         ProfScope prof__(ctx, "hamming_i8mma");
         hamming_i8mma<true><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, smem, ctx->stream>>>(w->pairs, 0, idx, best, second);
@@ -353,4 +345,11 @@ int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, 
     }
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pair descriptor came from pageable host memory
     return TB_OK;
+}
+
+void tb_match_tc_init_device()
+{
+    const int smem = (int)(TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64);
+    cudaFuncSetAttribute(hamming_i8mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }

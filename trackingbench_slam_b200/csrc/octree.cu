@@ -372,13 +372,10 @@ int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_fra
     for (int l = 0; l < n_levels; l++) all.lv[l].node_cap = max_cap;   // one shared-memory carve-up for the launch
     size_t smem = tb_octree_smem_bytes(max_cap);
     if (smem > 200 * 1024 || max_cap > 8191) return tb_fail(ctx, TB_E_UNSUPPORTED, "octree: per-level budget too large for shared memory");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(octree_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     ProfScope prof__(ctx, "octree_distribute");
     octree_distribute<<<dim3(n_frames, n_levels), OCT_THREADS, smem, ctx->stream>>>(all);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
+
+void tb_octree_init_device() { cudaFuncSetAttribute(octree_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }

@@ -163,11 +163,11 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
     } else {
         const size_t smem = (size_t)bp * bh + (size_t)bh * PYR_TW * sizeof(uint16_t);
         if (smem > 200 * 1024) return tb_fail(ctx, TB_E_UNSUPPORTED, "resize: scale factor too small for the shared-memory tile");
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), n_frames), block(64, 4);
         pyr_resize_linear_u8<<<grid, block, smem, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh, xtab, ytab, bp, bh);
     }
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
+
+void tb_pyramid_init_device() { cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
