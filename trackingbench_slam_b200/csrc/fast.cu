@@ -128,15 +128,18 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 // Pipeline of one CTA (G cells of one cell row), every stage on dense lanes:
 //   0  stage the u8 tile (+3-px halo) with 8-byte loads
 //   then, at T = initTh for every cell and again at T = minTh only for the cells that produced no
-//   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792):
+//   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792) — stages 1-4 are fused per
+//   warp (private survivor queue, no block barrier in between):
 //   1+2  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
 //      (N,E,S,W at radius 3) both brighter than centre+T or both darker than centre-T; per 4 px and
 //      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
 //   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map
 //   5  NMS inside the cell interior, emission with one global atomic per pass
+#define FAST_QCAP 288   // per-warp survivor queue: up to 31 waiting + 256 new per iteration
 struct FastSmem {
     uint8_t *tile, *sc, *cellOf, *need;
-    uint16_t *listA, *listB;
+    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (capacity = all pixels)
+    uint32_t *stage;           // NMS survivors staged for the single global reservation (<= cap/4 + 1 entries)
 };
 
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
@@ -146,13 +149,31 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
 {
     const int tid = threadIdx.x;
     uint8_t *tile = S.tile, *sc = S.sc;
-    uint16_t *listA = S.listA, *listB = S.listB;
-    // ---- stage 1: SWAR compass prefilter (need[] holds 0x80 for the bytes this pass must test)
-    if (T <= 127) {
-        const uint32_t K = (uint32_t)(127 - T) * 0x01010101u;
+    uint16_t *listB = S.listB;
+    // ---- stages 1-4, fused per warp (no block barrier, no block-wide list): every warp prefilters 256 pixels
+    //      per iteration (need[] holds 0x80 for the bytes this pass must test), pushes the survivors into its own
+    //      shared-memory queue and, whenever 32 are waiting, scores them on dense lanes.
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        uint16_t *q = S.queue + warp * FAST_QCAP;
+        int qn = 0;                                     // warp-uniform queue fill
+        const bool swar = T <= 127;                     // larger thresholds skip the byte-SIMD test: everything is scored
+        const uint32_t K = (uint32_t)(127 - (swar ? T : 0)) * 0x01010101u;
         const int g0 = (cs + col_lo) >> 3, nG = ((cs + col_hi + 7) >> 3) - g0;
-        const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);   // full-width tiles use the host's value
+        const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
         const int items = hEff * nG;
+        // score 32 (or, for the final flush, fewer) queued pixels; corners go to the block's corner list
+        auto score_batch = [&](int e, bool valid) {
+            bool corner = false;
+            if (valid) {
+                const int rr = e >> 10, cc = e & 1023;
+                const int m = fast9_score_packed(tile + (rr + 3) * tp + cs + cc, tp);
+                corner = m > T;
+                if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
+            }
+            const int pos = warp_append1(corner, &s_cnt[2]);
+            if (corner) listB[pos] = (uint16_t)e;
+        };
         for (int base = 0; base < items; base += 256) {
             const int it = base + tid;
             uint32_t c0 = 0, c1 = 0;
@@ -162,62 +183,48 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 o = 8 * (it - r * nG + g0);
                 const uint2 nd = *reinterpret_cast<const uint2 *>(S.need + o);
                 if (nd.x | nd.y) {
-                    const uint8_t *row = tile + (r + 3) * tp + o;
-                    const uint2 cen = *reinterpret_cast<const uint2 *>(row);
-                    const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
-                    const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
-                    const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
-                    const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
-                    const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
-                    const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
-                    c0 = compass_signed(dn.x, up.x, rw0, lw0, cen.x, K) & nd.x;
-                    c1 = compass_signed(dn.y, up.y, rw1, lw1, cen.y, K) & nd.y;
+                    if (swar) {
+                        const uint8_t *row = tile + (r + 3) * tp + o;
+                        const uint2 cen = *reinterpret_cast<const uint2 *>(row);
+                        const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
+                        const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
+                        const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
+                        const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
+                        const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
+                        const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
+                        c0 = compass_signed(dn.x, up.x, rw0, lw0, cen.x, K) & nd.x;
+                        c1 = compass_signed(dn.y, up.y, rw1, lw1, cen.y, K) & nd.y;
+                    } else { c0 = nd.x; c1 = nd.y; }
                 }
             }
             const int cnt = __popc(c0) + __popc(c1);
-            if (!__any_sync(0xffffffffu, cnt != 0)) continue;   // nothing in this warp's 256 pixels
-            int pos = warp_reserve(cnt, &s_cnt[0]);
+            int inc = cnt;                               // inclusive warp scan of the survivor counts
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total == 0) continue;                    // nothing in this warp's 256 pixels
             if (cnt) {
+                int pos = qn + inc - cnt;
                 const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
 #pragma unroll
-                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + b);
+                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) q[pos++] = (uint16_t)(e0 + b);
 #pragma unroll
-                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) listA[pos++] = (uint16_t)(e0 + 4 + b);
+                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) q[pos++] = (uint16_t)(e0 + 4 + b);
             }
+            qn += total;
+            __syncwarp();
+            while (qn >= 32) {
+                qn -= 32;
+                score_batch(q[qn + lane], true);
+            }
+            __syncwarp();                                // queue reads above happen before the next pushes
         }
-    } else {
-        // thresholds above 127 do not fit the SWAR compare: every needed interior pixel goes to stage 2
-        for (int base = 0; base < hEff * wEff; base += 256) {
-            const int i = base + tid;
-            bool ok = false;
-            int rr = 0, cc = 0;
-            if (i < hEff * wEff) { rr = i / wEff; cc = i - rr * wEff; ok = S.need[cs + cc] != 0 && cc >= col_lo && cc < col_hi; }
-            const int pos = warp_append1(ok, &s_cnt[0]);
-            if (ok) listA[pos] = (uint16_t)((rr << 10) | cc);
-        }
-    }
-    __syncthreads();
-    // (stage 2, the signed compass test, is part of the SWAR prefilter; with T > 127 every pixel goes on)
-    // ---- stage 3+4: arc score m of every prefilter survivor; corner at T <=> m > T (cornerScore is threshold free)
-    const int nB = s_cnt[0];
-    for (int base = 0; base < nB; base += 256) {
-        const int i = base + tid;
-        bool corner = false;
-        int e = 0;
-        if (i < nB) {
-            e = listA[i];
-            const int rr = e >> 10, cc = e & 1023;
-            const int m = fast9_score_packed(tile + (rr + 3) * tp + cs + cc, tp);
-            corner = m > T;
-            if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
-        }
-        const int pos = warp_append1(corner, &s_cnt[2]);
-        if (corner) listB[pos] = (uint16_t)e;
+        if (qn > 0) score_batch(lane < qn ? q[lane] : 0, lane < qn);
     }
     __syncthreads();
     const int nc = s_cnt[2];
-    // ---- stage 5: NMS inside the cell interior; survivors are staged in listA (free now)
-    uint32_t *stage = reinterpret_cast<uint32_t *>(listA);
+    // ---- stage 5: NMS inside the cell interior; survivors are staged for the global write
+    uint32_t *stage = S.stage;
     for (int base = 0; base < nc; base += 256) {
         const int i = base + tid;
         bool keep = false;
@@ -290,8 +297,9 @@ fast9_cells(FastArgs a)
     S.sc = S.tile + (size_t)(a.hCell + 6) * tp;                      // hCell * scw : m map (0 = not a corner)
     S.cellOf = S.sc + ((cap + 15) & ~15);                            // scw : cell index of an interior column
     S.need = S.cellOf + ((a.scw + 15) & ~15);                        // tp : 0x80 where this pass tests the byte column
-    S.listA = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
-    S.listB = S.listA + ((cap + 7) & ~7);
+    S.queue = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
+    S.listB = S.queue + 8 * FAST_QCAP;
+    S.stage = reinterpret_cast<uint32_t *>(S.listB + ((cap + 7) & ~7));
     __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
     __shared__ int s_has[64];
 
@@ -361,7 +369,10 @@ fast9_cells(FastArgs a)
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
 {
     const int cap = hCell * scw;
-    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) + 2 * sizeof(uint16_t) * ((cap + 7) & ~7) + 64;
+    // tile + m map + cellOf + need + per-warp queues + corner list (u16 per pixel) + survivor staging (NMS keeps at most
+    // ceil(h/2)*ceil(w/2) pixels of a tile)
+    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) +
+           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
