@@ -219,6 +219,29 @@ int tb_search_by_violence(tb_ctx *ctx, const tb_matcher_params *p,
                           int min_level, int max_level, float search_r,
                           tb_match *out, int capacity, int *n);
 
+/* ---- bag of words ----
+ * ORBVocabulary (include/types/Frame.h:22 = DBoW2::TemplatedVocabulary<FORB>) flattened in node-id order as
+ * loadFromTextFile builds it (third_part/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1420): node 0 = root, node i+1 =
+ * line i of the vocabulary file; parent[i] < i; is_leaf[i] = the file's leaf flag (word ids follow it in file
+ * order); desc[32*i]; weight[i]. depth_levels = m_L. The tree is copied to the device once. */
+typedef struct tb_vocab tb_vocab;
+int tb_vocab_create(tb_ctx *ctx, int n_nodes, int depth_levels, const int32_t *parent, const uint8_t *is_leaf,
+                    const uint8_t *desc, const double *weight, tb_vocab **out);
+void tb_vocab_destroy(tb_vocab *v);
+/* Frame::SetBow (src/types/Frame.cpp:267-270) -> TemplatedVocabulary::transform(feature, word, weight, nid, levelsup)
+ * (:1218-1259) for n descriptors: word id, FeatureVector node id (level L-levelsup) and word weight per feature. A
+ * feature enters the BowVector / FeatureVector only if weight > 0 (:1157, :1185). Any output may be NULL. */
+int tb_bow_transform(tb_ctx *ctx, const tb_vocab *v, const uint8_t *desc, int n, int levelsup,
+                     int32_t *word_id, int32_t *node_id, double *weight);
+int tb_bow_transform_device(tb_ctx *ctx, const tb_vocab *v, const uint8_t *d_desc, long long n, int levelsup,
+                            int32_t *d_word_id, int32_t *d_node_id, double *d_weight);
+/* Matcher::searchByBow (matcher.cpp:619-721). node1/node2 = FeatureVector node of each feature, -1 = feature not in
+ * the FeatureVector; mp_valid2[i2] = (F2->GetMapPoint(i2) != nullptr), only read when map_point_only. Host in/out. */
+int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p,
+                     const tb_keypoint *k1, const uint8_t *d1, const int32_t *node1, int n1,
+                     const tb_keypoint *k2, const uint8_t *d2, const int32_t *node2, int n2,
+                     const uint8_t *mp_valid2, int map_point_only, tb_match *out, int capacity, int *n);
+
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
  * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */

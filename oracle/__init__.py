@@ -34,7 +34,8 @@ def build(force=False):
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
         for f in ('tb_oracle.c', 'tb_oracle.h', 'orb_pattern.inc'))
     if force or src_newer or (os.path.exists('/root/reference/src/extractors/ORBextractor.cpp')
-                              and not os.path.exists(os.path.join(_HERE, '_ref', 'libtb_ref.so'))):
+                              and not all(os.path.exists(os.path.join(_HERE, '_ref', n))
+                                          for n in ('libtb_ref.so', 'libtb_ref_bow.so'))):
         subprocess.check_call(['make', '-C', _HERE, '-s'] + (['-B'] if force else []))
 
 
@@ -351,3 +352,71 @@ def three_maxima(hist_sizes):
     a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
     lib().tbo_three_maxima(_p(hs), len(hs), C.byref(a), C.byref(b), C.byref(c))
     return a.value, b.value, c.value
+
+
+# ---- bag of words -------------------------------------------------------------------------------
+class _Vocab(C.Structure):
+    _fields_ = [('n_nodes', C.c_int), ('L', C.c_int), ('parent', C.c_void_p), ('child_start', C.c_void_p),
+                ('children', C.c_void_p), ('word_id', C.c_void_p), ('desc', C.c_void_p), ('weight', C.c_void_p)]
+
+
+def bow_transform(voc, desc, levelsup=4):
+    """voc: trackingbench_slam_b200.vocab.Vocabulary (flat arrays only). Returns (word_id, node_id, weight)."""
+    start, children, word = voc.csr()
+    keep = (start, children, word, voc.parent, voc.desc, voc.weight)
+    v = _Vocab(voc.n_nodes, voc.L, _p(voc.parent).value, _p(start).value, _p(children).value, _p(word).value,
+               _p(voc.desc).value, _p(voc.weight).value)
+    desc = _u8(desc)
+    n = len(desc)
+    wid, nid, w = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+    lib().tbo_bow_transform(C.byref(v), _p(desc), n, int(levelsup), _p(wid), _p(nid), _p(w))
+    del keep
+    return wid, nid, w
+
+
+def search_by_bow(params, k1, d1, node1, k2, d2, node2, mp_valid2=None, map_point_only=False):
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, d2 = _u8(d1), _u8(d2)
+    node1, node2 = np.ascontiguousarray(node1, np.int32), np.ascontiguousarray(node2, np.int32)
+    mv = None if mp_valid2 is None else _u8(mp_valid2)
+    out = np.zeros(len(k1) + 1, MATCH_DTYPE)
+    n = lib().tbo_search_by_bow(C.byref(params), _p(k1), _p(d1), _p(node1), len(k1), _p(k2), _p(d2), _p(node2), len(k2),
+                                None if mv is None else _p(mv), int(bool(map_point_only)), _p(out))
+    return out[:n].copy()
+
+
+def ref_bow_available():
+    return os.path.exists(os.path.join(_HERE, '_ref', 'libtb_ref_bow.so'))
+
+
+class RefVocabulary:
+    """The reference's vendored DBoW2 (oracle/_ref/libtb_ref_bow.so): loadFromTextFile + transform as Frame::SetBow."""
+
+    def __init__(self, path):
+        if 'bow' not in _ref:
+            L = C.CDLL(os.path.join(_HERE, '_ref', 'libtb_ref_bow.so'))
+            L.tbref_vocab_load_text.restype = C.c_void_p
+            L.tbref_vocab_free.argtypes = [C.c_void_p]
+            L.tbref_vocab_size.argtypes = [C.c_void_p]
+            _ref['bow'] = L
+        self.L = _ref['bow']
+        self.h = self.L.tbref_vocab_load_text(path.encode())
+        if not self.h:
+            raise RuntimeError('reference loadFromTextFile failed for %s' % path)
+
+    def size(self):
+        return self.L.tbref_vocab_size(self.h)
+
+    def set_bow(self, desc, levelsup=4):
+        """Returns (node_id per feature (-1 = not in FeatureVector), word_id per feature, bow ids, bow values)."""
+        desc = _u8(desc)
+        n = len(desc)
+        nid, wid = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ids, vals = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.float64)
+        m = self.L.tbref_set_bow(C.c_void_p(self.h), _p(desc), n, int(levelsup), _p(nid), _p(wid), _p(ids), _p(vals), n + 1)
+        return nid, wid, ids[:m].copy(), vals[:m].copy()
+
+    def close(self):
+        if self.h:
+            self.L.tbref_vocab_free(self.h)
+            self.h = None

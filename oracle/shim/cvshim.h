@@ -18,6 +18,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 static inline int cvRound(double v) { return _mm_cvtsd_si32(_mm_set_sd(v)); }
 static inline int cvRound(float v) { return _mm_cvtss_si32(_mm_set_ss(v)); }
@@ -86,6 +87,8 @@ public:
     template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step.v + c); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step.v; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step.v; }
+    template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step.v); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step.v); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step.v; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
     Mat clone() const {

@@ -811,6 +811,97 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
     return m;
 }
 
+/* TemplatedVocabulary::transform per feature — TemplatedVocabulary.h:1218-1259; FORB::distance is the
+ * 256-bit Hamming distance (FORB.cpp:81-101); first minimum wins (strict d < best_d). */
+void tbo_bow_transform(const tbo_vocab *v, const u8 *desc, int n, int levelsup,
+                       int32_t *word_id, int32_t *node_id, double *weight)
+{
+    const int nid_level = v->L - levelsup;
+    for (int i = 0; i < n; i++) {
+        const u8 *f = desc + 32 * (size_t)i;
+        int nid = (nid_level <= 0) ? 0 : -1;
+        int final_id = 0, level = 0;
+        do {
+            level++;
+            const int cs = v->child_start[final_id], ce = v->child_start[final_id + 1];
+            int best = v->children[cs];
+            int best_d = tbo_hamming256(f, v->desc + 32 * (size_t)best);
+            for (int c = cs + 1; c < ce; c++) {
+                const int id = v->children[c];
+                const int d = tbo_hamming256(f, v->desc + 32 * (size_t)id);
+                if (d < best_d) { best_d = d; best = id; }
+            }
+            final_id = best;
+            if (level == nid_level) nid = final_id;
+        } while (v->child_start[final_id + 1] > v->child_start[final_id]);
+        if (nid < 0) nid = final_id; /* leaf above nid_level: UB in the reference, pinned to the leaf */
+        word_id[i] = v->word_id[final_id];
+        node_id[i] = nid;
+        weight[i] = v->weight[final_id];
+    }
+}
+
+/* searchByBow — matcher.cpp:619-721.  The two FeatureVectors are std::map<NodeId, vector<idx>>: walk the common
+ * node ids in ascending order, members in insertion (feature index) order. */
+static int bow_cmp(const void *a, const void *b)
+{
+    const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+    return (x > y) - (x < y);
+}
+int tbo_search_by_bow(const tbo_matcher_params *p, const tbo_kp *k1, const u8 *d1, const int32_t *node1, int n1,
+                      const tbo_kp *k2, const u8 *d2, const int32_t *node2, int n2,
+                      const u8 *mp_valid2, int map_point_only, tbo_match *out)
+{
+    int64_t *o1 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n1 + 1));
+    int64_t *o2 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n2 + 1));
+    tbo_match *raw = (tbo_match *)malloc(sizeof(tbo_match) * (size_t)(n1 + 1));
+    int *bins = (int *)malloc(sizeof(int) * (size_t)(n1 + 1));
+    int m1 = 0, m2 = 0, n = 0;
+    for (int i = 0; i < n1; i++) if (node1[i] >= 0) o1[m1++] = ((int64_t)node1[i] << 32) | (uint32_t)i;
+    for (int i = 0; i < n2; i++) if (node2[i] >= 0) o2[m2++] = ((int64_t)node2[i] << 32) | (uint32_t)i;
+    qsort(o1, (size_t)m1, sizeof(int64_t), bow_cmp);
+    qsort(o2, (size_t)m2, sizeof(int64_t), bow_cmp);
+    const float factor = 1.f / (float)p->HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < m1 && b < m2) {
+        const int na = (int)(o1[a] >> 32), nb = (int)(o2[b] >> 32);
+        if (na < nb) { a++; continue; }
+        if (nb < na) { b++; continue; }
+        int ae = a, be = b;
+        while (ae < m1 && (int)(o1[ae] >> 32) == na) ae++;
+        while (be < m2 && (int)(o2[be] >> 32) == na) be++;
+        for (int x = a; x < ae; x++) {
+            const int idx1 = (int)(o1[x] & 0xffffffff);
+            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            for (int y = b; y < be; y++) {
+                const int idx2 = (int)(o2[y] & 0xffffffff);
+                if (map_point_only && !(mp_valid2 && mp_valid2[idx2])) continue;
+                const int dist = tbo_hamming256(d1 + 32 * (size_t)idx1, d2 + 32 * (size_t)idx2);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestIdx2 >= 0 && bestDist1 < p->TH_LOW && (float)bestDist1 < p->nRatio * (float)bestDist2) {
+                tbo_match m = {idx1, bestIdx2, 0, (float)bestDist1};
+                raw[n] = m;
+                if (p->checkOrientation) {
+                    float rot = k1[idx1].angle - k2[bestIdx2].angle;
+                    if (rot < 0) rot += 360.f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == p->HISTO_LENGTH) bin = 0;
+                    bins[n] = bin;
+                }
+                n++;
+            }
+        }
+        a = ae; b = be;
+    }
+    int m;
+    if (p->checkOrientation) m = rot_hist_filter(raw, bins, n, p->HISTO_LENGTH, out);
+    else { memcpy(out, raw, sizeof(tbo_match) * (size_t)n); m = n; }
+    free(o1); free(o2); free(raw); free(bins);
+    return m;
+}
+
 /* PinholeCamera::World2Cam without distortion — CameraModel.cpp:63-74; IsInFrame on truncated
  * ints — CameraModel.h:33-39 (boundary 0, scale 1). */
 static void world2cam(const tbo_pinhole *c, const float *xyz, float *u, float *v)

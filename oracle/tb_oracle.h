@@ -96,6 +96,30 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
                            const tbo_kp *k2, const uint8_t *d2, int n2, int cols2, int rows2,
                            int min_level, int max_level, float search_r, tbo_match *out);
 
+/* ---- bag of words (rank-2 "next" row of SURVEY.md 8f) ----
+ * Flattened DBoW2 vocabulary in node-id order as loadFromTextFile builds it (third_part/DBoW2/DBoW2/
+ * TemplatedVocabulary.h:1338-1420): node 0 = root, node i+1 = line i of the file, children of a node in
+ * ascending id, word ids handed out to leaves in file order. */
+typedef struct {
+    int n_nodes, L;              /* L = m_L (depth levels) */
+    const int32_t *parent;       /* [n_nodes], parent[0] = -1 */
+    const int32_t *child_start;  /* [n_nodes+1] CSR into children */
+    const int32_t *children;     /* node ids */
+    const int32_t *word_id;      /* [n_nodes], -1 for inner nodes */
+    const uint8_t *desc;         /* [n_nodes*32] (row 0 unused) */
+    const double *weight;        /* [n_nodes] */
+} tbo_vocab;
+/* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) (:1218-1259) for n features.
+ * node_id = the node visited at level L-levelsup (0 if that level <= 0).  If a leaf is reached above that level
+ * the reference leaves *nid unset (UB); here node_id = that leaf. */
+void tbo_bow_transform(const tbo_vocab *v, const uint8_t *desc, int n, int levelsup,
+                       int32_t *word_id, int32_t *node_id, double *weight);
+/* Matcher::searchByBow (matcher.cpp:619-721).  node1/node2 = FeatureVector node per feature (-1 = feature not
+ * in the FeatureVector, i.e. stopped word); buckets iterate in ascending node id, members in feature order. */
+int tbo_search_by_bow(const tbo_matcher_params *p, const tbo_kp *k1, const uint8_t *d1, const int32_t *node1, int n1,
+                      const tbo_kp *k2, const uint8_t *d2, const int32_t *node2, int n2,
+                      const uint8_t *mp_valid2, int map_point_only, tbo_match *out);
+
 typedef struct {
     float fx, fy, cx, cy;
     int width, height;

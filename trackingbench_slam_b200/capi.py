@@ -33,6 +33,7 @@ EXPORTS = [
     'tb_match_bf_cross_host', 'tb_search_by_bf_host', 'tb_hamming_pairs_host',
     'tb_frontend_search_by_bf', 'tb_frontend_search_by_projection', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
     'tb_search_by_projection_map', 'tb_three_maxima',
+    'tb_vocab_create', 'tb_vocab_destroy', 'tb_bow_transform', 'tb_bow_transform_device', 'tb_search_by_bow',
 ]
 
 
@@ -189,6 +190,36 @@ class Context:
                                                _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
 
+    def vocab_create(self, voc):
+        """voc: vocab.Vocabulary -> DeviceVocabulary (tree resident in HBM)."""
+        return DeviceVocabulary(self, voc)
+
+    def bow_transform(self, dvoc, desc, levelsup=4):
+        """Frame::SetBow's per-feature transform: (word_id, node_id, weight)."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        wid, nid, w = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+        self.check(lib().tb_bow_transform(self.h, dvoc.h, _vp(desc), n, int(levelsup), _vp(wid), _vp(nid), _vp(w)))
+        return wid, nid, w
+
+    def bow_transform_device(self, dvoc, desc_dptr, n, levelsup, word_dptr, node_dptr, weight_dptr):
+        self.check(lib().tb_bow_transform_device(self.h, dvoc.h, C.c_void_p(desc_dptr), C.c_longlong(n), int(levelsup),
+                                                 C.c_void_p(word_dptr), C.c_void_p(node_dptr), C.c_void_p(weight_dptr)))
+
+    def search_by_bow(self, params, k1, d1, node1, k2, d2, node2, mp_valid2=None, map_point_only=False):
+        k1 = np.ascontiguousarray(k1, KP_DTYPE)
+        k2 = np.ascontiguousarray(k2, KP_DTYPE)
+        d1 = np.ascontiguousarray(d1, np.uint8)
+        d2 = np.ascontiguousarray(d2, np.uint8)
+        node1 = np.ascontiguousarray(node1, np.int32)
+        node2 = np.ascontiguousarray(node2, np.int32)
+        mv = None if mp_valid2 is None else np.ascontiguousarray(mp_valid2, np.uint8)
+        out = np.zeros(len(k1) + 1, MATCH_DTYPE)
+        n = C.c_int()
+        self.check(lib().tb_search_by_bow(self.h, C.byref(params), _vp(k1), _vp(d1), _vp(node1), len(k1), _vp(k2), _vp(d2),
+                                          _vp(node2), len(k2), _vp(mv), int(bool(map_point_only)), _vp(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def search_by_projection(self, params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1, k2, mp_valid, mp_xyz, mp_desc):
         k1 = np.ascontiguousarray(k1, KP_DTYPE)
         k2 = np.ascontiguousarray(k2, KP_DTYPE)
@@ -224,6 +255,21 @@ class Context:
                                                      _vp(mp_xyz), _vp(mp_normal), _vp(mp_desc), C.c_float(radio),
                                                      _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+class DeviceVocabulary:
+    """tb_vocab: the flattened ORBVocabulary on the device."""
+
+    def __init__(self, ctx, voc):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.check(lib().tb_vocab_create(ctx.h, voc.n_nodes, voc.L, _vp(voc.parent), _vp(voc.is_leaf), _vp(voc.desc),
+                                        _vp(voc.weight), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().tb_vocab_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Frontend:

@@ -6,6 +6,7 @@
 //   Matcher::searchByProjection(map,F1,r) + Frame::IsInFrustum    src/matchers/matcher.cpp:539-617, Frame.cpp:370-412
 //   rotation histogram + ComputeThreeMaxima                       src/matchers/matcher.cpp:359-393, :493-529, :810-851
 //   PinholeCamera::World2Cam / CameraModel::IsInFrame             src/camera/CameraModel.cpp:63-94, CameraModel.h:33-39
+//   Frame::SetBow (DBoW2 vocabulary transform) + Matcher::searchByBow  src/types/Frame.cpp:267-270, matcher.cpp:619-721
 //
 // Grid = CSR over the reference's 120x36 cells (cell (ix,iy) at ix*36+iy, items in insertion order),
 // so the candidates of one ix column and iy range are ONE contiguous item range, already in the
@@ -769,6 +770,200 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ bag of words
+// Frame::SetBow (src/types/Frame.cpp:267-270) = ORBVocabulary::transform(features, bowVec, featVec, 4)
+// (third_part/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1194): every descriptor walks the vocabulary tree, at each
+// node taking the child with the smallest Hamming distance (first minimum in child order, :1236-1248), until a leaf;
+// the FeatureVector bucket is the node passed at level L-levelsup.  Matcher::searchByBow (matcher.cpp:619-721)
+// then compares only features that fell into the same bucket.
+// The tree lives in HBM as CSR (children in ascending node id = loadFromTextFile order); one thread walks one
+// descriptor (6 levels x 10 children for ORBvoc: 60 distances, the 35 MB of node descriptors stay in L2).
+struct tb_vocab {
+    tb_ctx *ctx;
+    int n_nodes, L;
+    int *child_start, *children, *word_id;
+    uint8_t *desc;
+    double *weight;
+};
+
+__global__ void __launch_bounds__(128)
+bow_transform(const int *__restrict__ child_start, const int *__restrict__ children, const int *__restrict__ word_of,
+              const uint8_t *__restrict__ vdesc, const double *__restrict__ vweight, int L, int levelsup,
+              const uint8_t *__restrict__ desc, long long n, int32_t *__restrict__ word_id, int32_t *__restrict__ node_id,
+              double *__restrict__ weight)
+{
+    const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t q[8];
+    load_desc(q, desc + 32 * (size_t)i);
+    const int nid_level = L - levelsup;
+    int nid = nid_level <= 0 ? 0 : -1;
+    int cur = 0, level = 0;
+    int cs = child_start[0], ce = child_start[1];
+    do {
+        level++;
+        int best = children[cs];
+        int best_d = ham256_g(q, vdesc + 32 * (size_t)best);
+        for (int c = cs + 1; c < ce; c++) {
+            const int id = children[c];
+            const int d = ham256_g(q, vdesc + 32 * (size_t)id);
+            if (d < best_d) { best_d = d; best = id; }
+        }
+        cur = best;
+        if (level == nid_level) nid = cur;
+        cs = child_start[cur]; ce = child_start[cur + 1];
+    } while (ce > cs);
+    if (nid < 0) nid = cur;   // leaf above the bucket level: *nid is left unset by the reference (UB), pinned to the leaf
+    if (word_id) word_id[i] = word_of[cur];
+    if (node_id) node_id[i] = nid;
+    if (weight) weight[i] = vweight[cur];
+}
+
+extern "C" int tb_vocab_create(tb_ctx *ctx, int n_nodes, int depth_levels, const int32_t *parent, const uint8_t *is_leaf,
+                               const uint8_t *desc, const double *weight, tb_vocab **out)
+{
+    if (!ctx || !out || n_nodes < 2 || !parent || !is_leaf || !desc || !weight) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_vocab_create: bad arguments") : TB_E_INVALID;
+    // children of a node in ascending id (the order loadFromTextFile pushes them); word ids to leaves in id order
+    std::vector<int> start(n_nodes + 1, 0), kids(n_nodes - 1), word(n_nodes, -1);
+    for (int i = 1; i < n_nodes; i++) {
+        if (parent[i] < 0 || parent[i] >= i) return tb_fail(ctx, TB_E_INVALID, "tb_vocab_create: parent id must refer to an earlier node");
+        start[parent[i] + 1]++;
+    }
+    for (int i = 0; i < n_nodes; i++) start[i + 1] += start[i];
+    { std::vector<int> fill(start.begin(), start.end() - 1); for (int i = 1; i < n_nodes; i++) kids[fill[parent[i]]++] = i; }
+    if (start[1] == start[0]) return tb_fail(ctx, TB_E_INVALID, "tb_vocab_create: the root has no children");
+    int nw = 0;
+    for (int i = 1; i < n_nodes; i++) {
+        const bool leaf = start[i + 1] == start[i];
+        if (is_leaf[i]) word[i] = nw++;        // word ids follow the file's leaf flag (TemplatedVocabulary.h:1403-1410)
+        else if (leaf) word[i] = 0;            // childless node not flagged as a word: Node() default word_id 0 (:315)
+    }
+    tb_vocab *v = new tb_vocab();
+    v->ctx = ctx; v->n_nodes = n_nodes; v->L = depth_levels;
+    v->child_start = v->children = v->word_id = nullptr; v->desc = nullptr; v->weight = nullptr;
+    bool ok = cudaMalloc(&v->child_start, sizeof(int) * (n_nodes + 1)) == cudaSuccess && cudaMalloc(&v->children, sizeof(int) * n_nodes) == cudaSuccess &&
+              cudaMalloc(&v->word_id, sizeof(int) * n_nodes) == cudaSuccess && cudaMalloc(&v->desc, (size_t)32 * n_nodes) == cudaSuccess &&
+              cudaMalloc(&v->weight, sizeof(double) * n_nodes) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(v->child_start, start.data(), sizeof(int) * (n_nodes + 1), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(v->children, kids.data(), sizeof(int) * (n_nodes - 1), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(v->word_id, word.data(), sizeof(int) * n_nodes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(v->desc, desc, (size_t)32 * n_nodes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(v->weight, weight, sizeof(double) * n_nodes, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        cudaFree(v->child_start); cudaFree(v->children); cudaFree(v->word_id); cudaFree(v->desc); cudaFree(v->weight);
+        delete v;
+        return tb_fail(ctx, TB_E_NOMEM, "tb_vocab_create: device allocation or upload failed");
+    }
+    *out = v;
+    return TB_OK;
+}
+
+extern "C" void tb_vocab_destroy(tb_vocab *v)
+{
+    if (!v) return;
+    cudaFree(v->child_start); cudaFree(v->children); cudaFree(v->word_id); cudaFree(v->desc); cudaFree(v->weight);
+    delete v;
+}
+
+extern "C" int tb_bow_transform_device(tb_ctx *ctx, const tb_vocab *v, const uint8_t *d_desc, long long n, int levelsup,
+                                       int32_t *d_word_id, int32_t *d_node_id, double *d_weight)
+{
+    if (!ctx || !v || n < 0 || (n > 0 && !d_desc)) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_bow_transform_device: bad arguments") : TB_E_INVALID;
+    if (n == 0) return TB_OK;
+    ProfScope prof__(ctx, "bow_transform");
+    bow_transform<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(v->child_start, v->children, v->word_id, v->desc, v->weight, v->L, levelsup,
+                                                                          d_desc, n, d_word_id, d_node_id, d_weight);
+    TB_LAUNCH_CHECK(ctx);
+    return TB_OK;
+}
+
+extern "C" int tb_bow_transform(tb_ctx *ctx, const tb_vocab *v, const uint8_t *desc, int n, int levelsup,
+                                int32_t *word_id, int32_t *node_id, double *weight)
+{
+    if (!ctx || !v || n < 0 || (n > 0 && !desc)) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_bow_transform: bad arguments") : TB_E_INVALID;
+    if (n == 0) return TB_OK;
+    DevBuf buf;
+    uint8_t *dd = buf.upload(desc, (size_t)32 * n, ctx->stream);
+    int32_t *dw = buf.alloc<int32_t>(n), *dn = buf.alloc<int32_t>(n);
+    double *dwt = buf.alloc<double>(n);
+    if (!dd || !dw || !dn || !dwt) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    int rc = tb_bow_transform_device(ctx, v, dd, n, levelsup, dw, dn, dwt);
+    if (rc) return rc;
+    if (word_id) TB_CUDA(ctx, cudaMemcpyAsync(word_id, dw, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_id) TB_CUDA(ctx, cudaMemcpyAsync(node_id, dn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weight) TB_CUDA(ctx, cudaMemcpyAsync(weight, dwt, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
+}
+
+// searchByBow inner loops: one warp per F1 feature.  The reference walks the two FeatureVectors (std::map node ->
+// feature indices in insertion order) in ascending node id; the slot of feature i1 in that walk is its rank under
+// (node, index) among the features that have a bucket, counted here directly.  Candidates are F2's features of the same
+// bucket in index order: "first strict minimum" = smallest (distance, index) key.
+__global__ void __launch_bounds__(256)
+bow_query(const tb_keypoint *__restrict__ k1, const uint8_t *__restrict__ d1, const int32_t *__restrict__ node1, int n1,
+          const tb_keypoint *__restrict__ k2, const uint8_t *__restrict__ d2, const int32_t *__restrict__ node2, int n2,
+          const uint8_t *__restrict__ mp_valid2, int map_point_only, tb_matcher_params p, QRes *__restrict__ res)
+{
+    const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i1 >= n1) return;
+    const int node = node1[i1];
+    if (node < 0) return;                       // not in the FeatureVector (stopped word)
+    int before = 0;
+    for (int i = lane; i < n1; i += 32) {
+        const int nd = node1[i];
+        before += (nd >= 0 && (nd < node || (nd == node && i < i1)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    uint32_t q[8];
+    load_desc(q, d1 + (size_t)32 * i1);
+    Top2 t = {0xFFFFFFFFu, 0xFFFFFFFFu, -1, -1};
+    for (int j = lane; j < n2; j += 32) {
+        if (node2[j] != node) continue;
+        if (map_point_only && !(mp_valid2 && mp_valid2[j])) continue;
+        const int d = ham256_g(q, d2 + (size_t)32 * j);
+        if (d < 256) top2_push(t, ((uint32_t)d << 20) | (uint32_t)j, j);   // bestDist1/2 start at 256 (matcher.cpp:645-647)
+    }
+    t = top2_warp_merge(t);
+    if (lane == 0) {
+        QRes r = {0, i1, -1, 0, 0};
+        if (t.i1 >= 0) {
+            const int bestDist1 = (int)(t.k1 >> 20);
+            const int bestDist2 = t.i2 >= 0 ? (int)(t.k2 >> 20) : 256;
+            if (bestDist1 < p.TH_LOW && (float)bestDist1 < __fmul_rn(p.nRatio, (float)bestDist2)) {
+                r.ok = 1; r.t = t.i1; r.dist = bestDist1;
+                if (p.checkOrientation) r.bin = rot_bin(k1[i1].angle, k2[t.i1].angle, p.HISTO_LENGTH);
+            }
+        }
+        res[before] = r;
+    }
+}
+
+extern "C" int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p, const tb_keypoint *k1, const uint8_t *d1, const int32_t *node1, int n1,
+                                const tb_keypoint *k2, const uint8_t *d2, const int32_t *node2, int n2, const uint8_t *mp_valid2,
+                                int map_point_only, tb_match *out, int capacity, int *n)
+{
+    if (!ctx || !p || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
+    *n = 0;
+    if (n1 == 0 || n2 == 0) return TB_OK;
+    if (n2 >= (1 << 20)) return tb_fail(ctx, TB_E_UNSUPPORTED, "searchByBow supports fewer than 2^20 features per frame");
+    DevBuf buf;
+    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream), *dd2 = buf.upload(d2, (size_t)32 * n2, ctx->stream);
+    int32_t *dn1 = buf.upload(node1, n1, ctx->stream), *dn2 = buf.upload(node2, n2, ctx->stream);
+    uint8_t *dv = mp_valid2 ? buf.upload(mp_valid2, n2, ctx->stream) : nullptr;
+    QRes *res = buf.alloc<QRes>(n1);
+    if (!dk1 || !dk2 || !dd1 || !dd2 || !dn1 || !dn2 || !res || (mp_valid2 && !dv)) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    TB_CUDA(ctx, cudaMemsetAsync(res, 0, sizeof(QRes) * n1, ctx->stream));   // slots past the bucketed features stay ok = 0
+    {
+        ProfScope prof__(ctx, "bow_query");
+        bow_query<<<div_up(n1, 8), 256, 0, ctx->stream>>>(dk1, dd1, dn1, n1, dk2, dd2, dn2, n2, dv, map_point_only, *p, res);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    return emit_and_download(ctx, buf, res, n1, p->checkOrientation, p->HISTO_LENGTH, out, capacity, n);
 }
 
 void tb_window_ws_free(tb_ctx *ctx)
