@@ -82,5 +82,24 @@ int main(int argc, char **argv)
     matches = matcher_ptr->searchByProjection(frame2_ptr, frame1_ptr);
     std::printf("projection %zu %llx\n", matches.size(), digest(matches));
     std::printf("dist01 %d\n", Matcher::DescriptorDistance(descriptors1.row(0), descriptors1.row(1)));
+
+    // bag of words (test_vo.cpp:661-705 loads ORBvoc.txt and calls SetBow per keyframe); optional 4th argument
+    if (argc > 4) {
+        auto vocabulary = std::make_shared<ORBVocabulary>();
+        if (!vocabulary->loadFromTextFile(argv[4])) { std::fprintf(stderr, "Failed to open vocabulary\n"); return 2; }
+        frame1_ptr->SetBow(vocabulary);
+        frame2_ptr->SetBow(vocabulary);
+        unsigned long long h = 1469598103934665603ull;
+        for (const auto &e : frame1_ptr->GetBowVector()) {
+            h = fnv(&e.first, sizeof e.first, h);
+            h = fnv(&e.second, sizeof e.second, h);
+        }
+        std::printf("bowvec %zu %llx\n", frame1_ptr->GetBowVector().size(), h);
+        matcher_ptr->setBowParam(50, 100, 30, true, 0.9f);
+        matches = matcher_ptr->searchByBow(frame1_ptr, frame2_ptr);
+        std::printf("bow %zu %llx\n", matches.size(), digest(matches));
+        matches = matcher_ptr->searchByBow(frame2_ptr, frame1_ptr, true);   // only features of F1 that carry a map point
+        std::printf("bow_mp %zu %llx\n", matches.size(), digest(matches));
+    }
     return 0;
 }

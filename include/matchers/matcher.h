@@ -1,8 +1,8 @@
 // matcher.h — drop-in facade of the reference's include/matchers/matcher.h:17-183 for the
-// descriptor matchers on the hot path (searchByBF, searchByViolence, searchByProjection x2,
+// descriptor matchers on the hot path (searchByBF, searchByViolence, searchByProjection x2, searchByBow,
 // DescriptorDistance, ComputeThreeMaxima).  Public members, setters, method names and argument
 // meaning are the reference's; bodies (src/matchers/matcher.cpp:168-617,793-851) run on the GPU.
-// searchByNN (approximate FLANN-LSH), searchByBow, searchByOPFlow and the direct-alignment methods are
+// searchByNN (approximate FLANN-LSH), searchByOPFlow and the direct-alignment methods are
 // out of scope for this path.
 #ifndef TRACKING_BENCH_MATCHER_H
 #define TRACKING_BENCH_MATCHER_H
@@ -103,6 +103,24 @@ public:
         tb_check(tb_search_by_projection_map(ctx, &p, &cam, F1->GetPose(), kp(F1), d1.data, n1, matched.data(), sf.data(), F1->cols(), F1->rows(),
                                              nm, bad.data(), xyz.data(), nrm.data(), mdesc.data(), r, out.data(), (int)out.size(), &n),
                  ctx, "tb_search_by_projection_map");
+        return to_dmatch(out, n);
+    }
+    // matcher.cpp:619 — features that fell into the same vocabulary node (Frame::SetBow first).
+    std::vector<cv::DMatch> searchByBow(const std::shared_ptr<Frame> &F1, const std::shared_ptr<Frame> &F2, bool MapPointOnly = false)
+    {
+        tb_ctx *ctx = tb_default_ctx();
+        const int n1 = (int)F1->GetKeys().size(), n2 = (int)F2->GetKeys().size();
+        std::vector<int32_t> node1(n1 + 1, -1), node2(n2 + 1, -1);
+        for (const auto &e : F1->GetFeatureVector()) for (unsigned i : e.second) node1[i] = (int32_t)e.first;
+        for (const auto &e : F2->GetFeatureVector()) for (unsigned i : e.second) node2[i] = (int32_t)e.first;
+        std::vector<uint8_t> has_mp(n2 + 1, 0);
+        if (MapPointOnly) for (int i = 0; i < n2; i++) has_mp[i] = F2->GetMapPoint(i) ? 1 : 0;
+        cv::Mat d1 = contiguous(F1->GetDescriptors()), d2 = contiguous(F2->GetDescriptors());
+        tb_matcher_params p = params();
+        std::vector<tb_match> out(n1 + 1);
+        int n = 0;
+        tb_check(tb_search_by_bow(ctx, &p, kp(F1), d1.data, node1.data(), n1, kp(F2), d2.data, node2.data(), n2, has_mp.data(),
+                                  MapPointOnly ? 1 : 0, out.data(), (int)out.size(), &n), ctx, "tb_search_by_bow");
         return to_dmatch(out, n);
     }
     // matcher.cpp:793

@@ -242,6 +242,17 @@ int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p,
                      const tb_keypoint *k2, const uint8_t *d2, const int32_t *node2, int n2,
                      const uint8_t *mp_valid2, int map_point_only, tb_match *out, int capacity, int *n);
 
+/* Device-resident, batched Frame::SetBow + Matcher::searchByBow over the frames of the frontend's last extract.
+ * tb_frontend_set_bow writes the FeatureVector of every frame as node_dptr[frame][tb_frontend_kp_capacity()] (i32; -1 =
+ * stopped word or slot beyond the frame's keypoint count) and optionally the per-feature word id (i32) / weight (f64).
+ * tb_frontend_search_by_bow matches pair p = (f1_frames[p], f2_frames[p]); mp_valid_dptr (u8, same indexing, may be
+ * NULL) is only read when map_point_only. Outputs on the device: matches_dptr[p*capacity + i], counts_dptr[p]. */
+int tb_frontend_set_bow(tb_frontend *fe, const tb_vocab *voc, int n_frames, int levelsup,
+                        void *node_i32_dptr, void *word_i32_dptr, void *weight_f64_dptr);
+int tb_frontend_search_by_bow(tb_frontend *fe, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames,
+                              const void *node_i32_dptr, const void *mp_valid_dptr, int map_point_only,
+                              void *matches_dptr, int capacity, void *counts_i32_dptr);
+
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
  * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */

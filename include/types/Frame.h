@@ -2,10 +2,16 @@
 // tracking path touches: construction (scale tables + pyramid, src/types/Frame.cpp:13-33, :414-427),
 // keypoints / descriptors (SetKeys :69), the pose, the flattened map-point side data the projection
 // matchers read, and the search-grid query (AssignFeaturesToGrid / GetFeaturesInArea :187-265, run
-// on the GPU).  Eigen / DBoW2 / Map bookkeeping of the reference Frame are out of scope.
+// on the GPU), and the bag-of-words vectors (SetBow :267-270: the vocabulary walk runs on the GPU).
+// Eigen / Map bookkeeping of the reference Frame are out of scope.
 #ifndef TRACKING_BENCH_FRAME_H
 #define TRACKING_BENCH_FRAME_H
+#include <cmath>
+#include <fstream>
+#include <map>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 #include "../camera/CameraModel.h"
 #include "../tb_cv_compat.h"
@@ -23,6 +29,84 @@ struct MapPointLite {
     uint8_t desc[32] = {0};        // GetDescriptor()
     bool bad = false;              // isBad()
     int observations = 0;          // Observations()
+};
+
+// ORBVocabulary (reference include/types/Frame.h:22 = DBoW2::TemplatedVocabulary<FORB>): the text-file loader
+// (third_part/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1420) keeps the tree as flat arrays and hands it to the device;
+// transform() is Frame::SetBow's call (TemplatedVocabulary.h:1127-1194) with the tree walk on the GPU and the
+// BowVector accumulation / normalisation (BowVector.cpp:62-84) on the host in the reference's order.
+typedef std::map<unsigned int, double> BowVector;                       // DBoW2::BowVector
+typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector;   // DBoW2::FeatureVector
+class ORBVocabulary {
+public:
+    ORBVocabulary() = default;
+    ~ORBVocabulary() { if (voc_) tb_vocab_destroy(voc_); }
+    ORBVocabulary(const ORBVocabulary &) = delete;
+    ORBVocabulary &operator=(const ORBVocabulary &) = delete;
+    bool empty() const { return voc_ == nullptr; }
+    unsigned int size() const { return n_words_; }
+    bool loadFromTextFile(const std::string &filename)
+    {
+        std::ifstream f(filename.c_str());
+        if (!f.is_open()) return false;
+        std::string s;
+        std::getline(f, s);
+        std::stringstream ss(s);
+        int n1 = -1, n2 = -1;
+        k_ = L_ = -1;
+        ss >> k_ >> L_ >> n1 >> n2;
+        if (k_ < 0 || k_ > 20 || L_ < 1 || L_ > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) return false;   // :1359
+        scoring_ = n1; weighting_ = n2;
+        std::vector<int32_t> parent(1, -1);
+        std::vector<uint8_t> leaf(1, 0), desc(32, 0);
+        std::vector<double> weight(1, 0.0);
+        while (std::getline(f, s)) {
+            std::stringstream sn(s);
+            int pid, isLeaf;
+            if (!(sn >> pid >> isLeaf)) continue;   // blank line: see trackingbench_slam_b200/vocab.py:save_text
+            parent.push_back(pid); leaf.push_back(isLeaf > 0 ? 1 : 0);
+            for (int i = 0; i < 32; i++) { int b = 0; sn >> b; desc.push_back((uint8_t)b); }
+            double w = 0; sn >> w; weight.push_back(w);
+        }
+        n_words_ = 0;
+        for (size_t i = 0; i < leaf.size(); i++) n_words_ += leaf[i];
+        tb_ctx *ctx = tb_default_ctx();
+        if (voc_) { tb_vocab_destroy(voc_); voc_ = nullptr; }
+        return tb_vocab_create(ctx, (int)parent.size(), L_, parent.data(), leaf.data(), desc.data(), weight.data(), &voc_) == TB_OK;
+    }
+    // transform(features, v, fv, levelsup): descriptors as one contiguous n x 32 cv::Mat (Frame keeps them that way)
+    void transform(const cv::Mat &descriptors, BowVector &v, FeatureVector &fv, int levelsup) const
+    {
+        v.clear(); fv.clear();
+        if (empty() || descriptors.rows == 0) return;
+        tb_ctx *ctx = tb_default_ctx();
+        const int n = descriptors.rows;
+        cv::Mat d = ((size_t)descriptors.step == (size_t)descriptors.cols) ? descriptors : descriptors.clone();
+        std::vector<int32_t> word(n), node(n);
+        std::vector<double> w(n);
+        tb_check(tb_bow_transform(ctx, voc_, d.data, n, levelsup, word.data(), node.data(), w.data()), ctx, "tb_bow_transform");
+        const bool tf = (weighting_ == 0 || weighting_ == 1);          // TF_IDF, TF accumulate; IDF, BINARY keep the first
+        for (int i = 0; i < n; i++) {
+            if (!(w[i] > 0)) continue;                                  // stopped word (:1157, :1185)
+            if (tf) v[(unsigned)word[i]] += w[i];
+            else if (v.find((unsigned)word[i]) == v.end()) v[(unsigned)word[i]] = w[i];
+            fv[(unsigned)node[i]].push_back((unsigned)i);
+        }
+        const bool must = (scoring_ == 0 || scoring_ == 1);            // L1_NORM, L2_NORM
+        if (tf && !v.empty() && !must) { const double nd = (double)v.size(); for (auto &e : v) e.second /= nd; }
+        if (must) {
+            double norm = 0.0;
+            if (scoring_ == 0) for (auto &e : v) norm += std::fabs(e.second);
+            else { for (auto &e : v) norm += e.second * e.second; norm = std::sqrt(norm); }
+            if (norm > 0.0) for (auto &e : v) e.second /= norm;
+        }
+    }
+    tb_vocab *handle() const { return voc_; }
+
+private:
+    tb_vocab *voc_ = nullptr;
+    int k_ = 0, L_ = 0, scoring_ = 0, weighting_ = 0;
+    unsigned int n_words_ = 0;
 };
 
 class Frame {
@@ -62,6 +146,10 @@ public:
                                      x, y, r, minLevel, maxLevel, out.data(), (int)out.size(), &n), ctx, "tb_features_in_area");
         return std::vector<size_t>(out.begin(), out.begin() + n);
     }
+    // bag of words (Frame.cpp:267-270)
+    void SetBow(const std::shared_ptr<ORBVocabulary> &voc) { voc->transform(mDescriptors, mBowVec, mFeatVec, 4); }
+    const BowVector &GetBowVector() const { return mBowVec; }
+    const FeatureVector &GetFeatureVector() const { return mFeatVec; }
     // map points
     void AddMapPoint(std::shared_ptr<MapPointLite> &pMP, const size_t &idx) { mvpMapPoints.at(idx) = pMP; }
     std::shared_ptr<MapPointLite> GetMapPoint(const size_t &idx) { return mvpMapPoints.at(idx); }
@@ -100,6 +188,8 @@ protected:
     std::vector<cv::KeyPoint> mvKeys;
     cv::Mat mDescriptors;
     std::vector<std::shared_ptr<MapPointLite>> mvpMapPoints;
+    BowVector mBowVec;
+    FeatureVector mFeatVec;
     std::shared_ptr<CameraModel> mpCamera;
     int nLevels;
     float scaleFactor;

@@ -106,3 +106,61 @@ def test_vocab_create_rejects_bad_trees(tb, ctx):
     rc = tb.lib().tb_vocab_create(ctx.h, voc.n_nodes, voc.L, bad.ctypes.data_as(C.c_void_p), voc.is_leaf.ctypes.data_as(C.c_void_p),
                                   voc.desc.ctypes.data_as(C.c_void_p), voc.weight.ctypes.data_as(C.c_void_p), C.byref(h))
     assert rc == tb.TB_E_INVALID
+
+
+def test_frontend_batched_bow_device_resident(tb, ctx, oracle, images):
+    """tb_frontend_set_bow + tb_frontend_search_by_bow: descriptors, FeatureVectors and matches never leave the device."""
+    from trackingbench_slam_b200.synth import synth_frame
+    from .conftest import PARAM_SETS
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    frames = np.stack([images['left'], images['right'], synth_frame(1, W, H), synth_frame(2, W, H)])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=4, max_target=tgt)
+    voc = V.synth_vocabulary(10, 4, 7)
+    dv = ctx.vocab_create(voc)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(4)
+        fe.extract(4, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(4)
+        cap = fe.kp_cap
+        node = torch.full((4, cap), 12345, dtype=torch.int32, device='cuda')
+        word = torch.zeros((4, cap), dtype=torch.int32, device='cuda')
+        wt = torch.zeros((4, cap), dtype=torch.float64, device='cuda')
+        fe.set_bow(dv, 4, 2, node.data_ptr(), word.data_ptr(), wt.data_ptr())
+        ctx.sync()
+        node_h, word_h, wt_h = node.cpu().numpy(), word.cpu().numpy(), wt.cpu().numpy()
+        fvs = []
+        for f in range(4):
+            n = counts[f]
+            wid, nid, w = oracle.bow_transform(voc, desc[f, :n], 2)
+            fv = V.feature_vector(nid, w)
+            fvs.append(fv)
+            assert np.array_equal(node_h[f, :n], fv) and np.all(node_h[f, n:] == -1)
+            assert np.array_equal(word_h[f, :n], wid) and np.array_equal(wt_h[f, :n], w)
+        rng = np.random.default_rng(3)
+        valid = (rng.random((4, cap)) < 0.8).astype(np.uint8)
+        d_valid = torch.from_numpy(valid).cuda()
+        pairs = [(0, 1), (1, 0), (2, 3), (3, 2), (0, 0), (0, 2)]
+        for chk, mpo in ((1, False), (0, True), (1, True)):
+            p = tb.MatcherParams(60, 100, 30, chk, 0.9)
+            po = oracle.MatcherParams(60, 100, 30, chk, 0.9)
+            m = torch.zeros((len(pairs), cap, 4), dtype=torch.int32, device='cuda')
+            c = torch.zeros(len(pairs), dtype=torch.int32, device='cuda')
+            fe.search_by_bow(p, [q[0] for q in pairs], [q[1] for q in pairs], node.data_ptr(), d_valid.data_ptr() if mpo else None, mpo,
+                             m.data_ptr(), cap, c.data_ptr())
+            ctx.sync()
+            cn = c.cpu().numpy()
+            mm = m.cpu().numpy().view(np.uint8).reshape(len(pairs), cap, 16)
+            total = 0
+            for i, (f1, f2) in enumerate(pairs):
+                n1, n2 = counts[f1], counts[f2]
+                exp = oracle.search_by_bow(po, kps[f1, :n1], desc[f1, :n1], fvs[f1], kps[f2, :n2], desc[f2, :n2], fvs[f2], valid[f2, :n2], mpo)
+                assert cn[i] == len(exp), (chk, mpo, i, cn[i], len(exp))
+                assert mm[i, :cn[i]].tobytes() == exp.tobytes(), (chk, mpo, i)
+                total += len(exp)
+            assert total > 100
+    finally:
+        dv.close()
+        fe.close()

@@ -40,6 +40,11 @@ def test_headless_test_matcher(tmp_path, oracle, images):
             f.write(b'P5\n%d %d\n255\n' % (im.shape[1], im.shape[0]))
             f.write(im.tobytes())
         paths.append(p)
+    from trackingbench_slam_b200 import vocab as V
+    voc = V.synth_vocabulary(10, 5, 4)   # levelsup is fixed to 4 by SetBow: buckets at level 1
+    vpath = str(tmp_path / 'voc.txt')
+    voc.save_text(vpath)
+    paths.append(vpath)
     out = subprocess.check_output([exe] + paths).decode().split('\n')
     got = {l.split()[0]: l.split()[1:] for l in out if l.strip()}
     nl, sc, tgt, a, b = PARAM_SETS['A1000']
@@ -68,3 +73,18 @@ def test_headless_test_matcher(tmp_path, oracle, images):
     proj = oracle.search_by_projection(oracle.MatcherParams(30, 50, 30, 1, 30.0), cam, T, k2, d2, None, sf, W, H, k1, valid, xyz, d1)
     assert got['projection'] == [str(len(proj)), '%x' % _digest(proj)]
     assert got['dist01'] == [str(oracle.hamming256(d1[0], d1[1]))]
+    # bag of words: Frame::SetBow (levelsup 4) + searchByBow, with and without MapPointOnly
+    w1, n1, wt1 = oracle.bow_transform(voc, d1, 4)
+    w2, n2, wt2 = oracle.bow_transform(voc, d2, 4)
+    ids, vals = V.bow_vector(w1, wt1, voc.weighting, voc.scoring)
+    h = 1469598103934665603
+    for i, v in zip(ids.tolist(), vals.tolist()):
+        h = _fnv(np.uint32(i).tobytes(), h)
+        h = _fnv(np.float64(v).tobytes(), h)
+    assert got['bowvec'] == [str(len(ids)), '%x' % h]
+    fv1, fv2 = V.feature_vector(n1, wt1), V.feature_vector(n2, wt2)
+    pb = oracle.MatcherParams(50, 100, 30, 1, 0.9)
+    bow = oracle.search_by_bow(pb, k1, d1, fv1, k2, d2, fv2)
+    assert len(bow) > 10 and got['bow'] == [str(len(bow)), '%x' % _digest(bow)]
+    bow_mp = oracle.search_by_bow(pb, k2, d2, fv2, k1, d1, fv1, valid, True)
+    assert len(bow_mp) > 10 and got['bow_mp'] == [str(len(bow_mp)), '%x' % _digest(bow_mp)]

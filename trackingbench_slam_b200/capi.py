@@ -34,6 +34,7 @@ EXPORTS = [
     'tb_frontend_search_by_bf', 'tb_frontend_search_by_projection', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
     'tb_search_by_projection_map', 'tb_three_maxima',
     'tb_vocab_create', 'tb_vocab_destroy', 'tb_bow_transform', 'tb_bow_transform_device', 'tb_search_by_bow',
+    'tb_frontend_set_bow', 'tb_frontend_search_by_bow',
 ]
 
 
@@ -397,3 +398,19 @@ def _frontend_search_by_projection(self, params, cam, f1_frames, f2_frames, Tcw1
 
 
 Frontend.search_by_projection = _frontend_search_by_projection
+
+
+def _frontend_set_bow(self, dvoc, n_frames, levelsup, node_dptr, word_dptr=None, weight_dptr=None):
+    """Frame::SetBow for every frame of the last extract; outputs stay on the device ([frame][kp_capacity])."""
+    self.ctx.check(lib().tb_frontend_set_bow(self.h, dvoc.h, int(n_frames), int(levelsup), _vp(node_dptr), _vp(word_dptr), _vp(weight_dptr)))
+
+
+def _frontend_search_by_bow(self, params, f1_frames, f2_frames, node_dptr, mp_valid_dptr, map_point_only, matches_dptr, capacity, counts_dptr):
+    f1 = np.ascontiguousarray(f1_frames, np.int32)
+    f2 = np.ascontiguousarray(f2_frames, np.int32)
+    self.ctx.check(lib().tb_frontend_search_by_bow(self.h, C.byref(params), len(f1), _vp(f1), _vp(f2), _vp(node_dptr), _vp(mp_valid_dptr),
+                                                   int(bool(map_point_only)), _vp(matches_dptr), int(capacity), _vp(counts_dptr)))
+
+
+Frontend.set_bow = _frontend_set_bow
+Frontend.search_by_bow = _frontend_search_by_bow

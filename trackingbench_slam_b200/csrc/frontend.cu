@@ -537,6 +537,22 @@ extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int3
                                ratio, minTh, (tb_match *)matches, capacity, (int *)counts);
 }
 
+extern "C" int tb_frontend_set_bow(tb_frontend *fe, const tb_vocab *voc, int n_frames, int levelsup, void *node, void *word, void *weight)
+{
+    if (!fe || !voc || n_frames < 0 || n_frames > fe->B || !node) return TB_E_INVALID;
+    return tb_window_set_bow_batched(fe->ctx, voc, n_frames, levelsup, fe->desc, fe->kp_cap, fe->n_kp, (int32_t *)node, (int32_t *)word, (double *)weight);
+}
+
+extern "C" int tb_frontend_search_by_bow(tb_frontend *fe, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames,
+                                         const void *node, const void *mp_valid, int map_point_only, void *matches, int capacity, void *counts)
+{
+    if (!fe || !p || n_pairs < 0 || !f1_frames || !f2_frames || !node || !matches || !counts) return TB_E_INVALID;
+    for (int i = 0; i < n_pairs; i++)
+        if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
+    return tb_window_bow_batched(fe->ctx, p, n_pairs, f1_frames, f2_frames, fe->B, fe->kps, fe->desc, fe->kp_cap, fe->n_kp, (const int32_t *)node,
+                                 (const uint8_t *)mp_valid, map_point_only, (tb_match *)matches, capacity, (int *)counts);
+}
+
 extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs,
                                                 const int32_t *f1_frames, const int32_t *f2_frames, const float *Tcw1,
                                                 const void *f1_matched, const void *mp_valid, const void *mp_xyz,

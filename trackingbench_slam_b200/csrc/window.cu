@@ -661,7 +661,7 @@ projection_query_batched(const ProjPair *__restrict__ pairs, const tb_keypoint *
 
 __global__ void __launch_bounds__(256)
 emit_matches_batched(const ProjPair *__restrict__ pairs, const QRes *__restrict__ res, int kp_cap, const int *__restrict__ counts,
-                     int check_orientation, int histo, tb_match *__restrict__ out, int capacity, int *__restrict__ out_n)
+                     int check_orientation, int histo, tb_match *__restrict__ out, int capacity, int *__restrict__ out_n, int queries_from_f1)
 {
     // same logic as emit_matches, one CTA per pair
     __shared__ int s_hist[256];
@@ -669,7 +669,7 @@ emit_matches_batched(const ProjPair *__restrict__ pairs, const QRes *__restrict_
     __shared__ int s_chunk[2048];
     __shared__ int s_run;
     const int tid = threadIdx.x, pidx = blockIdx.x;
-    const int n = min(counts[pairs[pidx].f2], kp_cap);
+    const int n = min(counts[queries_from_f1 ? pairs[pidx].f1 : pairs[pidx].f2], kp_cap);
     const QRes *rs = res + (size_t)pidx * kp_cap;
     tb_match *o = out + (size_t)pidx * capacity;
     s_hist[tid] = 0;
@@ -766,7 +766,7 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
     }
     {
         ProfScope prof__(ctx, "emit_matches_batched");
-        emit_matches_batched<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, w.res, kp_cap, counts, p->checkOrientation, p->HISTO_LENGTH, matches, capacity, out_counts);
+        emit_matches_batched<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, w.res, kp_cap, counts, p->checkOrientation, p->HISTO_LENGTH, matches, capacity, out_counts, 0);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
@@ -964,6 +964,144 @@ extern "C" int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p, const t
         TB_LAUNCH_CHECK(ctx);
     }
     return emit_and_download(ctx, buf, res, n1, p->checkOrientation, p->HISTO_LENGTH, out, capacity, n);
+}
+
+// ---- device-resident, batched bag of words over the frames of a frontend
+// FeatureVector of every frame: node[f][i] = bucket of keypoint i, -1 for a stopped word or i >= counts[f]
+__global__ void __launch_bounds__(128)
+bow_transform_frames(const int *__restrict__ child_start, const int *__restrict__ children, const int *__restrict__ word_of,
+                     const uint8_t *__restrict__ vdesc, const double *__restrict__ vweight, int L, int levelsup,
+                     const uint8_t *__restrict__ desc, int kp_cap, const int *__restrict__ counts,
+                     int32_t *__restrict__ node_id, int32_t *__restrict__ word_id, double *__restrict__ weight)
+{
+    const int f = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= kp_cap) return;
+    const size_t o = (size_t)f * kp_cap + i;
+    if (i >= min(counts[f], kp_cap)) { node_id[o] = -1; if (word_id) word_id[o] = -1; if (weight) weight[o] = 0.0; return; }
+    uint32_t q[8];
+    load_desc(q, desc + 32 * o);
+    const int nid_level = L - levelsup;
+    int nid = nid_level <= 0 ? 0 : -1;
+    int cur = 0, level = 0;
+    int cs = child_start[0], ce = child_start[1];
+    do {
+        level++;
+        int best = children[cs];
+        int best_d = ham256_g(q, vdesc + 32 * (size_t)best);
+        for (int c = cs + 1; c < ce; c++) {
+            const int id = children[c];
+            const int d = ham256_g(q, vdesc + 32 * (size_t)id);
+            if (d < best_d) { best_d = d; best = id; }
+        }
+        cur = best;
+        if (level == nid_level) nid = cur;
+        cs = child_start[cur]; ce = child_start[cur + 1];
+    } while (ce > cs);
+    if (nid < 0) nid = cur;
+    const double w = vweight[cur];
+    node_id[o] = w > 0 ? nid : -1;           // "if(w > 0) fv.addFeature(nid, i_feature)" (TemplatedVocabulary.h:1157-1161)
+    if (word_id) word_id[o] = word_of[cur];
+    if (weight) weight[o] = w;
+}
+
+int tb_window_set_bow_batched(tb_ctx *ctx, const tb_vocab *v, int n_frames, int levelsup, const uint8_t *desc, int kp_cap, const int *counts,
+                              int32_t *node_id, int32_t *word_id, double *weight)
+{
+    if (n_frames <= 0) return TB_OK;
+    ProfScope prof__(ctx, "bow_transform_frames");
+    bow_transform_frames<<<dim3(div_up(kp_cap, 128), n_frames), 128, 0, ctx->stream>>>(v->child_start, v->children, v->word_id, v->desc, v->weight, v->L,
+                                                                                        levelsup, desc, kp_cap, counts, node_id, word_id, weight);
+    TB_LAUNCH_CHECK(ctx);
+    return TB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+bow_query_batched(const ProjPair *__restrict__ pairs, const tb_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc, int kp_cap,
+                  const int *__restrict__ counts, const int32_t *__restrict__ node, const uint8_t *__restrict__ mp_valid, int map_point_only,
+                  tb_matcher_params p, QRes *__restrict__ res)
+{
+    const int f1 = pairs[blockIdx.y].f1, f2 = pairs[blockIdx.y].f2;
+    const int n1 = min(counts[f1], kp_cap), n2 = min(counts[f2], kp_cap);
+    const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i1 >= n1) return;
+    QRes *rs = res + (size_t)blockIdx.y * kp_cap;
+    const int32_t *node1 = node + (size_t)f1 * kp_cap, *node2 = node + (size_t)f2 * kp_cap;
+    const int nd1 = node1[i1];
+    int before = 0, bucketed = 0;
+    for (int i = lane; i < n1; i += 32) {
+        const int nd = node1[i];
+        bucketed += (nd >= 0);
+        before += (nd >= 0 && nd1 >= 0 && (nd < nd1 || (nd == nd1 && i < i1)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); bucketed += __shfl_xor_sync(0xffffffffu, bucketed, o); }
+    if (nd1 < 0) {
+        // features without a bucket fill the slots behind the bucketed ones with empty records (any order)
+        int skipped = 0;
+        for (int i = lane; i < i1; i += 32) skipped += (node1[i] < 0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+        if (lane == 0) { QRes r = {0, i1, -1, 0, 0}; rs[bucketed + skipped] = r; }
+        return;
+    }
+    uint32_t q[8];
+    load_desc(q, desc + 32 * ((size_t)f1 * kp_cap + i1));
+    const uint8_t *d2 = desc + 32 * (size_t)f2 * kp_cap;
+    const uint8_t *mv = mp_valid ? mp_valid + (size_t)f2 * kp_cap : nullptr;
+    Top2 t = {0xFFFFFFFFu, 0xFFFFFFFFu, -1, -1};
+    for (int j = lane; j < n2; j += 32) {
+        if (node2[j] != nd1) continue;
+        if (map_point_only && !(mv && mv[j])) continue;
+        const int d = ham256_g(q, d2 + (size_t)32 * j);
+        if (d < 256) top2_push(t, ((uint32_t)d << 20) | (uint32_t)j, j);
+    }
+    t = top2_warp_merge(t);
+    if (lane == 0) {
+        QRes r = {0, i1, -1, 0, 0};
+        if (t.i1 >= 0) {
+            const int bestDist1 = (int)(t.k1 >> 20);
+            const int bestDist2 = t.i2 >= 0 ? (int)(t.k2 >> 20) : 256;
+            if (bestDist1 < p.TH_LOW && (float)bestDist1 < __fmul_rn(p.nRatio, (float)bestDist2)) {
+                r.ok = 1; r.t = t.i1; r.dist = bestDist1;
+                if (p.checkOrientation) r.bin = rot_bin(kps[(size_t)f1 * kp_cap + i1].angle, kps[(size_t)f2 * kp_cap + t.i1].angle, p.HISTO_LENGTH);
+            }
+        }
+        rs[before] = r;
+    }
+}
+
+int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames, int n_frames,
+                          const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const int32_t *node,
+                          const uint8_t *mp_valid, int map_point_only, tb_match *matches, int capacity, int *out_counts)
+{
+    (void)n_frames;
+    if (n_pairs <= 0) return TB_OK;
+    if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (!ctx->wws) ctx->wws = new WinWs();
+    WinWs &w = *ctx->wws;
+    if ((size_t)n_pairs > w.pairs_cap || (size_t)kp_cap != w.kp_cap) {
+        cudaFree(w.res); cudaFree(w.pairs); cudaFree(w.cell_start); cudaFree(w.items);
+        w.res = nullptr; w.pairs = nullptr; w.cell_start = nullptr; w.items = nullptr; w.frames = 0;
+        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
+        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
+        w.pairs_cap = n_pairs; w.kp_cap = kp_cap;
+    }
+    std::vector<ProjPair> hp(n_pairs);
+    memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
+    for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; }
+    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    {
+        ProfScope prof__(ctx, "bow_query_batched");
+        bow_query_batched<<<dim3(div_up(kp_cap, 8), n_pairs), 256, 0, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, node, mp_valid, map_point_only, *p, w.res);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope prof__(ctx, "emit_matches_batched");
+        emit_matches_batched<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, w.res, kp_cap, counts, p->checkOrientation, p->HISTO_LENGTH, matches, capacity, out_counts, 1);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    return TB_OK;
 }
 
 void tb_window_ws_free(tb_ctx *ctx)
