@@ -219,6 +219,32 @@ int tb_search_by_violence(tb_ctx *ctx, const tb_matcher_params *p,
                           int min_level, int max_level, float search_r,
                           tb_match *out, int capacity, int *n);
 
+/* ---- frame ingest (the step in front of the pyramid in test_vo.cpp:178 and Frame::Equalize) ----
+ * cv::initUndistortRectifyMap(K, D, Mat(), K, Size(width,height), CV_32F, map1, map2) exactly as PinholeCamera's
+ * constructor calls it (src/camera/CameraModel.cpp:15-18; K and D are float, promoted to double): map1 = x, map2 = y,
+ * both width*height floats. Host computation (one-time camera setup). */
+int tb_init_undistort_rectify_map(const tb_pinhole *cam, float *map1, float *map2);
+/* The maps of PinholeCamera (mUndistMap1/2, include/camera/CameraModel.h:86) converted once to fixed point on the device. */
+typedef struct tb_undistort tb_undistort;
+int tb_undistort_create(tb_ctx *ctx, int dst_w, int dst_h, const float *map1, const float *map2, tb_undistort **out);
+void tb_undistort_destroy(tb_undistort *u);
+/* PinholeCamera::UndistortImage = cv::remap(raw, rectified, map1, map2, INTER_LINEAR), BORDER_CONSTANT 0
+ * (src/camera/CameraModel.cpp:96-102), for n_frames images laid out at *_frame_stride bytes. Never in place. */
+int tb_undistort_image_device(tb_ctx *ctx, const tb_undistort *u, const void *src_dptr, int src_w, int src_h, size_t src_pitch,
+                              size_t src_frame_stride, void *dst_dptr, size_t dst_pitch, size_t dst_frame_stride, int n_frames);
+int tb_undistort_image_host(tb_ctx *ctx, const tb_undistort *u, const uint8_t *src, int src_w, int src_h, size_t src_stride,
+                            uint8_t *dst, size_t dst_stride);
+/* Raw (distorted) frames -> level 0 of frames [first, first+n) through the remap, from device or host memory. */
+int tb_frontend_undistort_device(tb_frontend *fe, const tb_undistort *u, int first, int n, const void *raw_dptr, int raw_w, int raw_h,
+                                 size_t raw_pitch, size_t raw_frame_stride);
+int tb_frontend_upload_frames_undistort(tb_frontend *fe, const tb_undistort *u, int first, int n, const uint8_t *host_frames,
+                                        int raw_w, int raw_h, size_t host_stride);
+/* Frame::Equalize = cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply (src/types/Frame.cpp:453-458 uses 3.0, 8x8). */
+int tb_clahe_device(tb_ctx *ctx, const void *src_dptr, int w, int h, size_t src_pitch, size_t src_frame_stride, void *dst_dptr,
+                    size_t dst_pitch, size_t dst_frame_stride, int n_frames, double clip_limit, int tiles_x, int tiles_y);
+int tb_clahe_host(tb_ctx *ctx, const uint8_t *src, int w, int h, size_t src_stride, uint8_t *dst, size_t dst_stride,
+                  double clip_limit, int tiles_x, int tiles_y);
+
 /* ---- bag of words ----
  * ORBVocabulary (include/types/Frame.h:22 = DBoW2::TemplatedVocabulary<FORB>) flattened in node-id order as
  * loadFromTextFile builds it (third_part/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1420): node 0 = root, node i+1 =

@@ -420,3 +420,28 @@ class RefVocabulary:
         if self.h:
             self.L.tbref_vocab_free(self.h)
             self.h = None
+
+
+# ---- frame ingest -------------------------------------------------------------------------------
+def init_undistort_rectify_map(fx, fy, cx, cy, d, w, h):
+    d = np.ascontiguousarray(d, np.float32)
+    m1, m2 = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    lib().tbo_init_undistort_rectify_map(C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(d), w, h, _p(m1), _p(m2))
+    return m1, m2
+
+
+def remap_linear(src, map1, map2):
+    src = _u8(src)
+    map1, map2 = np.ascontiguousarray(map1, np.float32), np.ascontiguousarray(map2, np.float32)
+    dst = np.zeros(map1.shape, np.uint8)
+    lib().tbo_remap_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(map1), _p(map2),
+                              map1.shape[1], map1.shape[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def clahe(src, clip_limit=3.0, tiles=(8, 8)):
+    src = _u8(src)
+    dst = np.zeros_like(src)
+    lib().tbo_clahe_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], C.c_double(clip_limit), int(tiles[0]), int(tiles[1]),
+                       _p(dst), dst.strides[0])
+    return dst

@@ -811,6 +811,130 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
     return m;
 }
 
+/* ---- frame ingest ------------------------------------------------------------------------------
+ * cv::initUndistortRectifyMap (OpenCV imgproc/undistort.dispatch.cpp): R = I, new camera matrix = K, so
+ * ir = K^-1 by cv::invert's closed-form 3x3 (cofactors * 1/det, double); per row the homogeneous (x,y,w)
+ * is advanced by column 0 of ir; radial k1,k2,k3 + tangential p1,p2; result rounded to float. */
+void tbo_init_undistort_rectify_map(float ffx, float ffy, float fcx, float fcy, const float d[5], int w, int h,
+                                    float *map1, float *map2)
+{
+    const double S[3][3] = {{ffx, 0, fcx}, {0, ffy, fcy}, {0, 0, 1}};
+    double det = S[0][0] * (S[1][1] * S[2][2] - S[1][2] * S[2][1]) - S[0][1] * (S[1][0] * S[2][2] - S[1][2] * S[2][0]) +
+                 S[0][2] * (S[1][0] * S[2][1] - S[1][1] * S[2][0]);
+    det = 1.0 / det;
+    double ir[9];
+    ir[0] = (S[1][1] * S[2][2] - S[1][2] * S[2][1]) * det;
+    ir[1] = (S[0][2] * S[2][1] - S[0][1] * S[2][2]) * det;
+    ir[2] = (S[0][1] * S[1][2] - S[0][2] * S[1][1]) * det;
+    ir[3] = (S[1][2] * S[2][0] - S[1][0] * S[2][2]) * det;
+    ir[4] = (S[0][0] * S[2][2] - S[0][2] * S[2][0]) * det;
+    ir[5] = (S[0][2] * S[1][0] - S[0][0] * S[1][2]) * det;
+    ir[6] = (S[1][0] * S[2][1] - S[1][1] * S[2][0]) * det;
+    ir[7] = (S[0][1] * S[2][0] - S[0][0] * S[2][1]) * det;
+    ir[8] = (S[0][0] * S[1][1] - S[0][1] * S[1][0]) * det;
+    const double fx = ffx, fy = ffy, u0 = fcx, v0 = fcy;
+    const double k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+    for (int i = 0; i < h; i++) {
+        double _x = i * ir[1] + ir[2], _y = i * ir[4] + ir[5], _w = i * ir[7] + ir[8];
+        for (int j = 0; j < w; j++, _x += ir[0], _y += ir[3], _w += ir[6]) {
+            const double ww = 1. / _w, x = _x * ww, y = _y * ww;
+            const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((0 * r2 + 0) * r2 + 0) * r2);
+            const double xd = (x * kr + p1 * _2xy + p2 * (r2 + 2 * x2) + 0 * r2 + 0 * r2 * r2);
+            const double yd = (y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy + 0 * r2 + 0 * r2 * r2);
+            map1[(size_t)i * w + j] = (float)(fx * 1.0 * xd + u0);
+            map2[(size_t)i * w + j] = (float)(fy * 1.0 * yd + v0);
+        }
+    }
+}
+
+/* cvRound(float) as SSE cvtss2si computes it: NaN / out-of-range give INT_MIN ("integer indefinite") */
+static inline int cv_round_f_indef(float v)
+{
+    if (!(v >= -2147483648.f && v < 2147483648.f)) return INT_MIN;
+    return (int)lrintf(v);
+}
+static inline int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+void tbo_remap_linear_u8(const u8 *src, int sw, int sh, int sstride, const float *map1, const float *map2,
+                         int dw, int dh, u8 *dst, int dstride)
+{
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            const int sx = cv_round_f_indef(map1[(size_t)y * dw + x] * 32.f), sy = cv_round_f_indef(map2[(size_t)y * dw + x] * 32.f);
+            const int fx = sx & 31, fy = sy & 31;
+            const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+            int v[4];
+            for (int t = 0; t < 4; t++) {
+                const int xx = ix + (t & 1), yy = iy + (t >> 1);
+                v[t] = (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sstride + xx] : 0;
+            }
+            const int sum = v[0] * ((32 - fy) * (32 - fx) * 32) + v[1] * ((32 - fy) * fx * 32) + v[2] * (fy * (32 - fx) * 32) + v[3] * (fy * fx * 32);
+            const int r = (sum + (1 << 14)) >> 15;
+            dst[(size_t)y * dstride + x] = (u8)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+}
+
+/* cv::CLAHE (OpenCV imgproc/clahe.cpp), 8-bit: tile LUTs from clipped + redistributed histograms of the image
+ * extended (BORDER_REFLECT_101, right/bottom) to a multiple of the tile grid, then per-pixel bilinear blend of
+ * the four neighbouring tiles' LUT values in float, saturate_cast<uchar> (round-half-even). */
+void tbo_clahe_u8(const u8 *src, int w, int h, int stride, double clip_limit, int tiles_x, int tiles_y, u8 *dst, int dstride)
+{
+    const int ew = (w % tiles_x == 0 && h % tiles_y == 0) ? w : w + (tiles_x - w % tiles_x);
+    const int eh = (w % tiles_x == 0 && h % tiles_y == 0) ? h : h + (tiles_y - h % tiles_y);
+    const int tw = ew / tiles_x, th = eh / tiles_y, area = tw * th;
+    const float lutScale = (float)255 / (float)area;
+    int clip = 0;
+    if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = imax(clip, 1); }
+    u8 *lut = (u8 *)malloc((size_t)tiles_x * tiles_y * 256);
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++) {
+            int hist[256];
+            memset(hist, 0, sizeof hist);
+            for (int y = ty * th; y < (ty + 1) * th; y++)
+                for (int x = tx * tw; x < (tx + 1) * tw; x++)
+                    hist[src[(size_t)reflect101(y, h) * stride + reflect101(x, w)]]++;
+            if (clip > 0) {
+                int clipped = 0;
+                for (int i = 0; i < 256; i++) if (hist[i] > clip) { clipped += hist[i] - clip; hist[i] = clip; }
+                const int batch = clipped / 256;
+                int residual = clipped - batch * 256;
+                for (int i = 0; i < 256; i++) hist[i] += batch;
+                if (residual != 0) {
+                    const int step = imax(256 / residual, 1);
+                    for (int i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++;
+                }
+            }
+            u8 *l = lut + ((size_t)ty * tiles_x + tx) * 256;
+            int sum = 0;
+            for (int i = 0; i < 256; i++) {
+                sum += hist[i];
+                const int r = cv_round_f((float)sum * lutScale);
+                l[i] = (u8)(r < 0 ? 0 : (r > 255 ? 255 : r));
+            }
+        }
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    for (int y = 0; y < h; y++) {
+        const float tyf = (float)y * inv_th - 0.5f;
+        int ty1 = cv_floor_f(tyf), ty2 = ty1 + 1;
+        const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+        ty1 = imax(ty1, 0); ty2 = imin(ty2, tiles_y - 1);
+        for (int x = 0; x < w; x++) {
+            const float txf = (float)x * inv_tw - 0.5f;
+            int tx1 = cv_floor_f(txf), tx2 = tx1 + 1;
+            const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+            tx1 = imax(tx1, 0); tx2 = imin(tx2, tiles_x - 1);
+            const int v = src[(size_t)y * stride + x];
+            const float a = lut[((size_t)ty1 * tiles_x + tx1) * 256 + v], b = lut[((size_t)ty1 * tiles_x + tx2) * 256 + v];
+            const float c = lut[((size_t)ty2 * tiles_x + tx1) * 256 + v], e = lut[((size_t)ty2 * tiles_x + tx2) * 256 + v];
+            const float res = (a * xa1 + b * xa) * ya1 + (c * xa1 + e * xa) * ya;
+            const int r = cv_round_f(res);
+            dst[(size_t)y * dstride + x] = (u8)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+    }
+    free(lut);
+}
+
 /* TemplatedVocabulary::transform per feature — TemplatedVocabulary.h:1218-1259; FORB::distance is the
  * 256-bit Hamming distance (FORB.cpp:81-101); first minimum wins (strict d < best_d). */
 void tbo_bow_transform(const tbo_vocab *v, const u8 *desc, int n, int levelsup,

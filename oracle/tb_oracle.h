@@ -96,6 +96,21 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
                            const tbo_kp *k2, const uint8_t *d2, int n2, int cols2, int rows2,
                            int min_level, int max_level, float search_r, tbo_match *out);
 
+/* ---- frame ingest (rank-4 "next" row of SURVEY.md 8f): undistortion remap and CLAHE ----
+ * Arithmetic lives in OpenCV (un-vendored dependency of the reference); restated from its published algorithm and
+ * pinned bit-exact against cv2 4.13 in tests/test_oracle_cv2.py. */
+/* cv::initUndistortRectifyMap(K, D, Mat(), K, size, CV_32F, map1, map2) as PinholeCamera's constructor calls it
+ * (src/camera/CameraModel.cpp:15-18): K, D are float matrices promoted to double; map1 = x, map2 = y. */
+void tbo_init_undistort_rectify_map(float fx, float fy, float cx, float cy, const float d[5], int w, int h,
+                                    float *map1, float *map2);
+/* cv::remap(src, dst, map1, map2, INTER_LINEAR) with float maps, BORDER_CONSTANT 0 (PinholeCamera::UndistortImage,
+ * CameraModel.cpp:96-102): 5 fractional bits, weights (32-fy)(32-fx)*32 of 2^15, (sum + 2^14) >> 15. */
+void tbo_remap_linear_u8(const uint8_t *src, int sw, int sh, int sstride, const float *map1, const float *map2,
+                         int dw, int dh, uint8_t *dst, int dstride);
+/* cv::createCLAHE(clip, Size(tiles_x, tiles_y))->apply (Frame::Equalize, src/types/Frame.cpp:453-458 with 3.0, 8x8). */
+void tbo_clahe_u8(const uint8_t *src, int w, int h, int stride, double clip_limit, int tiles_x, int tiles_y,
+                  uint8_t *dst, int dstride);
+
 /* ---- bag of words (rank-2 "next" row of SURVEY.md 8f) ----
  * Flattened DBoW2 vocabulary in node-id order as loadFromTextFile builds it (third_part/DBoW2/DBoW2/
  * TemplatedVocabulary.h:1338-1420): node 0 = root, node i+1 = line i of the file, children of a node in

@@ -62,3 +62,20 @@ def test_product_does_not_import_oracle():
     for dp, _, fs in os.walk(os.path.join(ROOT, 'include')):
         for f in fs:
             assert 'tb_oracle' not in open(os.path.join(dp, f)).read(), f
+
+
+def test_init_undistort_rectify_map_host_matches_cv2_and_oracle():
+    """tb_init_undistort_rectify_map is host arithmetic (one-time camera setup): checked here without a GPU."""
+    import cv2
+    import numpy as np
+    import oracle as O
+    import trackingbench_slam_b200 as tb
+    for (w, h, fx, fy, cx, cy, d) in [(1241, 376, 718.856, 718.856, 607.1928, 185.2157, [-0.28, 0.07, 0.0002, 0.00002, 0.0]),
+                                      (640, 480, 517.3, 516.5, 318.6, 255.3, [0.2624, -0.9531, -0.0054, 0.0026, 1.1633])]:
+        cam = tb.Pinhole(fx, fy, cx, cy, w, h, (tb.capi.C.c_float * 5)(*d))
+        m1, m2 = tb.init_undistort_rectify_map(cam)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        c1, c2 = cv2.initUndistortRectifyMap(K, np.array(d, np.float32).reshape(1, 5), None, K, (w, h), cv2.CV_32F)
+        assert m1.tobytes() == c1.tobytes() and m2.tobytes() == c2.tobytes()
+        o1, o2 = O.init_undistort_rectify_map(fx, fy, cx, cy, d, w, h)
+        assert m1.tobytes() == o1.tobytes() and m2.tobytes() == o2.tobytes()

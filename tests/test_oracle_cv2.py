@@ -75,3 +75,54 @@ def test_hamming_swar(oracle):
     b = rng.integers(0, 256, (50, 32), dtype=np.uint8)
     for x, y in zip(a, b):
         assert oracle.hamming256(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+# ---- frame ingest: undistortion maps, remap, CLAHE — pinned to the real OpenCV
+CAMERAS = [  # (w, h, fx, fy, cx, cy, d[5])
+    (1241, 376, 718.856, 718.856, 607.1928, 185.2157, [-0.28, 0.07, 0.0002, 0.00002, 0.0]),
+    (752, 480, 458.654, 457.296, 367.215, 248.375, [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]),
+    (640, 480, 517.3, 516.5, 318.6, 255.3, [0.2624, -0.9531, -0.0054, 0.0026, 1.1633]),
+]
+
+
+def _cv_maps(w, h, fx, fy, cx, cy, d):
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)          # CameraModel.cpp:15-16: float matrices
+    D = np.array(d, np.float32).reshape(1, 5)
+    return cv2.initUndistortRectifyMap(K, D, None, K, (w, h), cv2.CV_32F)
+
+
+@pytest.mark.parametrize('cam', CAMERAS)
+def test_undistort_maps_and_remap_match_cv2(oracle, cam):
+    w, h, fx, fy, cx, cy, d = cam
+    m1, m2 = _cv_maps(*cam)
+    a1, a2 = oracle.init_undistort_rectify_map(fx, fy, cx, cy, d, w, h)
+    assert a1.tobytes() == m1.tobytes() and a2.tobytes() == m2.tobytes()
+    img = np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)
+    assert np.array_equal(oracle.remap_linear(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+
+
+def test_remap_borders_and_nonfinite_match_cv2(oracle):
+    rng = np.random.default_rng(0)
+    m1 = rng.uniform(-50, 700, (300, 400)).astype(np.float32)
+    m2 = rng.uniform(-50, 530, (300, 400)).astype(np.float32)
+    m1[0, 0] = np.nan; m2[1, 1] = np.inf; m1[2, 2] = 1e9; m1[3, 3] = -1e9; m2[4, 4] = -np.inf
+    m1[5, :8] = [-1.0, -0.5, -0.015625, 0.0, 638.5, 639.0, 639.5, 640.0]
+    m2[5, :8] = 100.0
+    m2[6, :8] = [-1.0, -0.5, -0.015625, 0.0, 478.5, 479.0, 479.5, 480.0]
+    m1[6, :8] = 100.0
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    assert np.array_equal(oracle.remap_linear(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize('shape', [(376, 1241), (480, 640), (1080, 1920), (377, 1243), (301, 535), (64, 72), (9, 17)])
+def test_clahe_matches_cv2(oracle, images, shape):
+    h, w = shape
+    rng = np.random.default_rng(h * w)
+    cases = [rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(100, 130, (h, w)).astype(np.uint8)]
+    if h <= 376 and w <= 1241:
+        cases.append(np.ascontiguousarray(images['left'][:h, :w]))
+    for img in cases:
+        ref = cv2.createCLAHE(3.0, (8, 8)).apply(img)                          # Frame::Equalize, Frame.cpp:453-458
+        assert np.array_equal(oracle.clahe(img, 3.0, (8, 8)), ref)
+    ref = cv2.createCLAHE(40.0, (4, 6)).apply(cases[0])
+    assert np.array_equal(oracle.clahe(cases[0], 40.0, (4, 6)), ref)

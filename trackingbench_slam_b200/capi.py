@@ -35,6 +35,9 @@ EXPORTS = [
     'tb_search_by_projection_map', 'tb_three_maxima',
     'tb_vocab_create', 'tb_vocab_destroy', 'tb_bow_transform', 'tb_bow_transform_device', 'tb_search_by_bow',
     'tb_frontend_set_bow', 'tb_frontend_search_by_bow',
+    'tb_init_undistort_rectify_map', 'tb_undistort_create', 'tb_undistort_destroy', 'tb_undistort_image_device',
+    'tb_undistort_image_host', 'tb_frontend_undistort_device', 'tb_frontend_upload_frames_undistort',
+    'tb_clahe_device', 'tb_clahe_host',
 ]
 
 
@@ -221,6 +224,20 @@ class Context:
                                           _vp(node2), len(k2), _vp(mv), int(bool(map_point_only)), _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
 
+    def clahe_host(self, img, clip_limit=3.0, tiles=(8, 8)):
+        """Frame::Equalize on one host image."""
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros_like(img)
+        self.check(lib().tb_clahe_host(self.h, _vp(img), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]), _vp(out),
+                                       C.c_size_t(out.strides[0]), C.c_double(clip_limit), int(tiles[0]), int(tiles[1])))
+        return out
+
+    def clahe_device(self, src_dptr, w, h, src_pitch, src_frame_stride, dst_dptr, dst_pitch, dst_frame_stride, n_frames,
+                     clip_limit=3.0, tiles=(8, 8)):
+        self.check(lib().tb_clahe_device(self.h, C.c_void_p(src_dptr), int(w), int(h), C.c_size_t(src_pitch), C.c_size_t(src_frame_stride),
+                                         C.c_void_p(dst_dptr), C.c_size_t(dst_pitch), C.c_size_t(dst_frame_stride), int(n_frames),
+                                         C.c_double(clip_limit), int(tiles[0]), int(tiles[1])))
+
     def search_by_projection(self, params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1, k2, mp_valid, mp_xyz, mp_desc):
         k1 = np.ascontiguousarray(k1, KP_DTYPE)
         k2 = np.ascontiguousarray(k2, KP_DTYPE)
@@ -256,6 +273,46 @@ class Context:
                                                      _vp(mp_xyz), _vp(mp_normal), _vp(mp_desc), C.c_float(radio),
                                                      _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+def init_undistort_rectify_map(cam):
+    """cv::initUndistortRectifyMap as PinholeCamera's constructor calls it: (map1 = x, map2 = y), float32 [h, w]."""
+    m1 = np.zeros((cam.height, cam.width), np.float32)
+    m2 = np.zeros((cam.height, cam.width), np.float32)
+    rc = lib().tb_init_undistort_rectify_map(C.byref(cam), _vp(m1), _vp(m2))
+    if rc:
+        raise TbError(rc, 'tb_init_undistort_rectify_map')
+    return m1, m2
+
+
+class Undistorter:
+    """tb_undistort: PinholeCamera's undistortion maps in fixed point on the device."""
+
+    def __init__(self, ctx, map1, map2):
+        map1 = np.ascontiguousarray(map1, np.float32)
+        map2 = np.ascontiguousarray(map2, np.float32)
+        assert map1.shape == map2.shape and map1.ndim == 2
+        self.ctx, self.h_, self.w_ = ctx, map1.shape[0], map1.shape[1]
+        self.h = C.c_void_p()
+        ctx.check(lib().tb_undistort_create(ctx.h, self.w_, self.h_, _vp(map1), _vp(map2), C.byref(self.h)))
+
+    def apply_host(self, img):
+        """PinholeCamera::UndistortImage on one host image."""
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros((self.h_, self.w_), np.uint8)
+        self.ctx.check(lib().tb_undistort_image_host(self.ctx.h, self.h, _vp(img), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]),
+                                                     _vp(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def apply_device(self, src_dptr, src_w, src_h, src_pitch, src_frame_stride, dst_dptr, dst_pitch, dst_frame_stride, n_frames):
+        self.ctx.check(lib().tb_undistort_image_device(self.ctx.h, self.h, C.c_void_p(src_dptr), int(src_w), int(src_h), C.c_size_t(src_pitch),
+                                                       C.c_size_t(src_frame_stride), C.c_void_p(dst_dptr), C.c_size_t(dst_pitch),
+                                                       C.c_size_t(dst_frame_stride), int(n_frames)))
+
+    def close(self):
+        if self.h:
+            lib().tb_undistort_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class DeviceVocabulary:
@@ -414,3 +471,19 @@ def _frontend_search_by_bow(self, params, f1_frames, f2_frames, node_dptr, mp_va
 
 Frontend.set_bow = _frontend_set_bow
 Frontend.search_by_bow = _frontend_search_by_bow
+
+
+def _frontend_upload_frames_undistort(self, und, first, frames):
+    """Raw (distorted) host frames [n, h, w] -> remap -> level 0 of frames first.. (test_vo.cpp:178 before the Frame ctor)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    self.ctx.check(lib().tb_frontend_upload_frames_undistort(self.h, und.h, int(first), n, _vp(frames), w, h, C.c_size_t(frames.strides[1])))
+
+
+def _frontend_undistort_device(self, und, first, n, raw_dptr, raw_w, raw_h, raw_pitch, raw_frame_stride):
+    self.ctx.check(lib().tb_frontend_undistort_device(self.h, und.h, int(first), int(n), C.c_void_p(raw_dptr), int(raw_w), int(raw_h),
+                                                      C.c_size_t(raw_pitch), C.c_size_t(raw_frame_stride)))
+
+
+Frontend.upload_frames_undistort = _frontend_upload_frames_undistort
+Frontend.undistort_device = _frontend_undistort_device

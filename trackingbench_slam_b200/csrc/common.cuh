@@ -25,6 +25,7 @@ struct tb_ctx {
     struct MatchWs *mws = nullptr;   // lazily grown matching workspace (match.cu)
     struct TcWs *tcws = nullptr;     // tensor-core matcher workspace (match_tc.cu)
     struct WinWs *wws = nullptr;     // batched windowed-matcher workspace (window.cu)
+    struct IngestWs *iws = nullptr;  // CLAHE tile LUTs (ingest.cu)
     int match_impl = 0;              // 0 = LOP3+POPC (K7), 1 = tcgen05 int8 (K8)
     // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
     bool profiling = false;
@@ -48,6 +49,7 @@ struct ProfScope {
 void tb_match_ws_free(tb_ctx *ctx);
 void tb_match_tc_free(tb_ctx *ctx);
 void tb_window_ws_free(tb_ctx *ctx);
+void tb_ingest_ws_free(tb_ctx *ctx);
 
 static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "")
 {

@@ -45,6 +45,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_match_ws_free(ctx);
     tb_match_tc_free(ctx);
     tb_window_ws_free(ctx);
+    tb_ingest_ws_free(ctx);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -132,6 +133,7 @@ struct tb_frontend {
     float2 *exit_xy = nullptr; int16_t *enid = nullptr; int exit_cap = 0;
     int budget[TB_MAX_LEVELS] = {};
     bool has_budget = false;
+    uint8_t *raw = nullptr; size_t raw_bytes = 0;   // staging for distorted frames (tb_frontend_upload_frames_undistort)
     std::vector<void *> allocs;
 };
 
@@ -172,6 +174,7 @@ extern "C" void tb_frontend_destroy(tb_frontend *fe)
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
     for (void *p : fe->allocs) cudaFree(p);
+    cudaFree(fe->raw);
     delete fe;
 }
 
@@ -261,6 +264,32 @@ extern "C" int tb_frontend_upload_frames(tb_frontend *fe, int first, int n, cons
     TB_CUDA(fe->ctx, cudaMemcpy2DAsync(fe->pyr[0] + (size_t)first * g.frame_stride, g.pitch, host, host_stride, g.w, (size_t)g.h * n,
                                        cudaMemcpyHostToDevice, fe->ctx->stream));
     return TB_OK;
+}
+
+// PinholeCamera::UndistortImage in front of the pyramid (test_vo.cpp:178): raw frames -> level 0 through the remap
+extern "C" int tb_frontend_undistort_device(tb_frontend *fe, const tb_undistort *und, int first, int n, const void *raw, int raw_w, int raw_h,
+                                            size_t raw_pitch, size_t raw_frame_stride)
+{
+    if (!fe || !und || !raw || first < 0 || n < 0 || first + n > fe->B) return TB_E_INVALID;
+    const LevelGeom &g = fe->g[0];
+    return tb_undistort_image_device(fe->ctx, und, raw, raw_w, raw_h, raw_pitch, raw_frame_stride, fe->pyr[0] + (size_t)first * g.frame_stride,
+                                     g.pitch, g.frame_stride, n);
+}
+
+extern "C" int tb_frontend_upload_frames_undistort(tb_frontend *fe, const tb_undistort *und, int first, int n, const uint8_t *host,
+                                                   int raw_w, int raw_h, size_t host_stride)
+{
+    if (!fe || !und || !host || first < 0 || n < 0 || first + n > fe->B || raw_w <= 0 || raw_h <= 0 || host_stride < (size_t)raw_w) return TB_E_INVALID;
+    if (n == 0) return TB_OK;
+    const size_t pitch = align_up((size_t)raw_w, 64), need = pitch * raw_h * n;
+    if (need > fe->raw_bytes) {
+        TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
+        cudaFree(fe->raw); fe->raw = nullptr; fe->raw_bytes = 0;
+        TB_CUDA(fe->ctx, cudaMalloc(&fe->raw, need));
+        fe->raw_bytes = need;
+    }
+    TB_CUDA(fe->ctx, cudaMemcpy2DAsync(fe->raw, pitch, host, host_stride, raw_w, (size_t)raw_h * n, cudaMemcpyHostToDevice, fe->ctx->stream));
+    return tb_frontend_undistort_device(fe, und, first, n, fe->raw, raw_w, raw_h, pitch, pitch * raw_h);
 }
 
 extern "C" int tb_frontend_download_level(tb_frontend *fe, int frame, int level, int blurred, uint8_t *host, size_t host_stride)

@@ -136,3 +136,27 @@ def feature_vector(node_id, weight):
     node_id = np.asarray(node_id, np.int32).copy()
     node_id[~(np.asarray(weight) > 0)] = -1
     return node_id
+
+
+def synth_vocabulary_fast(k=10, L=6, seed=0, p_flip=0.12):
+    """ORBvoc-sized (k=10, L=6: 1.1 M nodes) synthetic tree, vectorised: a child = its parent with each bit toggled
+    with probability p_flip (root children: 0.5). Breadth-first node order, every leaf at depth L, weights in [0.5, 8)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    parent = [np.array([-1], np.int32)]
+    desc = [np.zeros((1, 32), np.uint8)]
+    first, count = 0, 1
+    prev = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    for level in range(1, L + 1):
+        n = count * k
+        par = np.repeat(np.arange(first, first + count, dtype=np.int32), k)
+        d = np.repeat(prev, k, axis=0)
+        for s in range(0, n, 1 << 16):
+            e = min(n, s + (1 << 16))
+            d[s:e] ^= np.packbits(rng.random((e - s, 256)) < (0.5 if level == 1 else p_flip), axis=1)
+        parent.append(par); desc.append(d)
+        first, count, prev = first + count, n, d
+    parent = np.concatenate(parent); desc = np.concatenate(desc)
+    n_nodes = len(parent)
+    is_leaf = np.zeros(n_nodes, np.uint8); is_leaf[first:] = 1
+    weight = np.zeros(n_nodes, np.float64); weight[first:] = rng.uniform(0.5, 8.0, count)
+    return Vocabulary(k, L, parent, is_leaf, desc, weight)
