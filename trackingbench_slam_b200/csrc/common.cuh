@@ -1,5 +1,6 @@
 // common.cuh — shared declarations for libtb_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -71,6 +72,28 @@ static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a 
         cudaError_t e__ = cudaGetLastError();                                                 \
         if (e__ != cudaSuccess) return tb_fail((ctx), TB_E_CUDA, "kernel launch: %s", cudaGetErrorString(e__)); \
     } while (0)
+
+// 3-D (x, y, frame) u8 tensor map for TMA tile loads of boxw x boxh x 1 (zero fill outside the image). The driver entry
+// point is fetched through the runtime so libcuda is not a link dependency. base, pitch and frame stride must be
+// multiples of 16 bytes; at run time the box origin must be a multiple of 16 in x (an unaligned origin faults).
+static inline bool tb_encode_tiled_u8_3d(CUtensorMap *tm, const void *base, int w, int h, int n, size_t pitch, size_t fstride, int boxw, int boxh)
+{
+    typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                            const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static PFN encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+        encode = (PFN)fn;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (fstride & 15) || boxw > 256 || boxh > 256 || (boxw & 15)) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

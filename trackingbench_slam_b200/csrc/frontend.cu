@@ -125,6 +125,8 @@ struct tb_frontend {
     int4 *xtab[TB_MAX_LEVELS] = {}, *ytab[TB_MAX_LEVELS] = {};
     bool area2[TB_MAX_LEVELS] = {};
     int box_pitch[TB_MAX_LEVELS] = {}, box_rows[TB_MAX_LEVELS] = {};   // K1 shared-memory source box
+    CUtensorMap pyr_tmap[TB_MAX_LEVELS];                               // K1 TMA: tensor map over level l-1 (source of level l)
+    bool has_tmap[TB_MAX_LEVELS] = {};
     uint32_t *cand[TB_MAX_LEVELS] = {}, *kept[TB_MAX_LEVELS] = {};
     uint16_t *nid[TB_MAX_LEVELS] = {};
     int *n_cand = nullptr, *n_kept = nullptr, *n_kp = nullptr, *overflow = nullptr;
@@ -216,6 +218,9 @@ extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, 
             if ((rc = dev_alloc(fe, &fe->ytab[l], hy.size()))) break;
             cudaMemcpy(fe->xtab[l], hx.data(), hx.size() * sizeof(int4), cudaMemcpyHostToDevice);
             cudaMemcpy(fe->ytab[l], hy.data(), hy.size() * sizeof(int4), cudaMemcpyHostToDevice);
+            if (!fe->area2[l])
+                fe->has_tmap[l] = tb_resize_tensor_map(&fe->pyr_tmap[l], fe->pyr[l - 1], lw[l - 1], lh[l - 1], B, fe->g[l - 1].pitch,
+                                                       fe->g[l - 1].frame_stride, fe->box_rows[l]);
         }
     }
     if (!rc) rc = dev_alloc(fe, &fe->n_cand, B * n_levels);
@@ -309,7 +314,8 @@ extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
     for (int l = 1; l < fe->L; l++) {
         const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
         int rc = tb_launch_resize(fe->ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
-                                  d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames, fe->box_pitch[l], fe->box_rows[l]);
+                                  d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames, fe->box_pitch[l], fe->box_rows[l],
+                                  fe->has_tmap[l] ? &fe->pyr_tmap[l] : nullptr);
         if (rc) return rc;
     }
     return TB_OK;

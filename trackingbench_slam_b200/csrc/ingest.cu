@@ -396,9 +396,6 @@ clahe_apply(ClaheGeom g, const uint8_t *__restrict__ src, size_t spitch, size_t 
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_tb_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // cv::initUndistortRectifyMap with R = I and newCameraMatrix = K: double arithmetic, inverse by cofactors (cv::invert 3x3)
 extern "C" int tb_init_undistort_rectify_map(const tb_pinhole *cam, float *map1, float *map2)
 {
@@ -478,19 +475,9 @@ extern "C" int tb_undistort_image_device(tb_ctx *ctx, const tb_undistort *u, con
     const size_t fstride = n_frames > 1 ? src_frame_stride : src_pitch * (size_t)src_h;
     static const bool use_tma = !(getenv("TB_REMAP_TMA") && atoi(getenv("TB_REMAP_TMA")) == 0);   // A/B knob: 0 forces the gather kernel
     if (use_tma && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (src_pitch & 15) == 0 && (fstride & 15) == 0 && fstride >= src_pitch * (size_t)src_h) {
-        static PFN_tb_encodeTiled encode = nullptr;
-        if (!encode) {
-            void *fn = nullptr;
-            cudaDriverEntryPointQueryResult q;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (PFN_tb_encodeTiled)fn;
-        }
-        if (encode) {
-            CUtensorMap tm;
-            const cuuint64_t gdim[3] = {(cuuint64_t)src_w, (cuuint64_t)src_h, (cuuint64_t)n_frames};
-            const cuuint64_t gstr[2] = {(cuuint64_t)src_pitch, (cuuint64_t)fstride};
-            const cuuint32_t box[3] = {RM_BOXW, RM_BOXH, 1}, estr[3] = {1, 1, 1};
-            if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        CUtensorMap tm;
+        if (tb_encode_tiled_u8_3d(&tm, src, src_w, src_h, n_frames, src_pitch, fstride, RM_BOXW, RM_BOXH)) {
+            {
                 ProfScope prof__(ctx, "remap_linear_u8_tma");
                 dim3 grid(div_up(u->w, 128), div_up(u->h, 16), div_up(n_frames, RM_FPC));
                 remap_linear_u8_tma<<<grid, 256, 0, ctx->stream>>>(tm, u->fix, u->w, u->h, (const uint8_t *)src, src_w, src_h, src_pitch, fstride,

@@ -8,7 +8,9 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh);
 void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
                    const std::vector<int32_t> &y1, int *bp, int *bh);
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
-                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh);
+                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh,
+                     const CUtensorMap *tmap);
+bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows);
 struct FastArgs {
     const uint8_t *img; int pitch; size_t frame_stride;
     int w, h;

@@ -8,6 +8,7 @@
 // integer only and HBM-bound: every source byte is fetched once from DRAM (neighbouring threads
 // share rows through L1), every destination byte written once with 4-byte stores.
 #include "common.cuh"
+#include <cstdlib>
 #include "kernels.cuh"
 #include <cfloat>
 #include <cmath>
@@ -63,7 +64,7 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh)
 // their source rows through H instead of recomputing the horizontal interpolation.
 #define PYR_TW 256
 #define PYR_TH 32
-extern __shared__ __align__(16) uint8_t pyr_smem[];
+extern __shared__ __align__(128) uint8_t pyr_smem[];
 
 __global__ void __launch_bounds__(256)
 pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
@@ -128,6 +129,115 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
     }
 }
 
+// ---- TMA variant: same three phases and arithmetic, but the CTA keeps its output tile and walks PYR_FPC frames. The
+// source box of frame f+2 is fetched by the TMA unit (cp.async.bulk.tensor over a 3-D x/y/frame tensor map, two 192-byte
+// wide boxes side by side because a box dimension is limited to 256) into a 2-stage mbarrier ring while frames f and f+1
+// are interpolated, so no thread issues a global load and the table entries are read once per CTA instead of once per frame.
+#define PYR_BOXW 192
+#define PYR_FPC 8
+__device__ __forceinline__ uint32_t pyr_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pyr_tma_box(void *dst, const CUtensorMap *tm, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(pyr_s32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(pyr_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void pyr_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(pyr_s32(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 3)
+pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, int dpitch, size_t dframe,
+                         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames)
+{
+    __shared__ alignas(8) uint64_t s_full[2];
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+    const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
+    const int f0 = blockIdx.z * PYR_FPC, nf = min(n_frames, f0 + PYR_FPC) - f0;
+    const int box_bytes = (bh_max * PYR_BOXW + 127) & ~127;                       // one 192-wide box, 128-byte aligned
+    uint8_t *boxes = pyr_smem;                                                    // [2 stages][2 boxes][box_bytes]
+    uint16_t *Hs = reinterpret_cast<uint16_t *>(pyr_smem + 4 * (size_t)box_bytes); // bh_max x PYR_TW u16
+    const int sx_lo = __ldg(&xtab[tx0]).x & ~15;
+    const int sy_lo = __ldg(&ytab[ty0]).x, sy_hi = __ldg(&ytab[ty1]).y;
+    const int bh = sy_hi - sy_lo + 1;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < 2 && s < nf; s++) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
+            pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f0 + s, &s_full[s]);
+            pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f0 + s, &s_full[s]);
+        }
+    }
+    // this thread's 4 output columns: tap offsets inside a stage (left box, or right box at +box_bytes) and weights
+    const int cx = threadIdx.x * 4;
+    uint32_t xo[4], xc[4];     // packed: tap offsets (16 bits each) and the two 11-bit weights
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int4 xt = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]);
+        const int a = xt.x - sx_lo, b = xt.y - sx_lo;
+        xo[k] = (uint32_t)(a < PYR_BOXW ? a : box_bytes + a - PYR_BOXW) | ((uint32_t)(b < PYR_BOXW ? b : box_bytes + b - PYR_BOXW) << 16);
+        xc[k] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+    }
+    // this thread's output rows (phase 2): table entries once per CTA
+    const int dx0 = tx0 + cx;
+    uint32_t yr[PYR_TH / 4], yc[PYR_TH / 4];   // packed: the two H rows (relative to sy_lo) and the two weights
+#pragma unroll
+    for (int kk = 0; kk < PYR_TH / 4; kk++) {
+        const int4 yt = __ldg(&ytab[min(ty0 + threadIdx.y * (PYR_TH / 4) + kk, dh - 1)]);
+        yr[kk] = (uint32_t)(yt.x - sy_lo) | ((uint32_t)(yt.y - sy_lo) << 16);
+        yc[kk] = (uint32_t)yt.z | ((uint32_t)yt.w << 16);
+    }
+    __syncthreads();                                       // barriers initialised before anyone waits
+    for (int f = 0; f < nf; f++) {
+        const int s = f & 1;
+        pyr_mbar_wait(&s_full[s], (uint32_t)((f >> 1) & 1));
+        // ---- phase 1: horizontal pass, rows threadIdx.y, +4, ...
+        const uint8_t *stage = boxes + (size_t)(2 * s) * box_bytes;
+        for (int r = threadIdx.y; r < bh; r += 4) {
+            const uint8_t *row = stage + r * PYR_BOXW;
+            uint32_t h[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                h[k] = (uint32_t)((int)row[xo[k] & 0xFFFF] * (int)(xc[k] & 0xFFFF) + (int)row[xo[k] >> 16] * (int)(xc[k] >> 16)) >> 4;
+            *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        }
+        __syncthreads();                                   // H complete, stage s drained
+        if (tid == 0 && f + 2 < nf) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
+            pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f0 + f + 2, &s_full[s]);
+            pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f0 + f + 2, &s_full[s]);
+        }
+        // ---- phase 2: vertical pass, 4 columns x 8 rows per thread
+        if (dx0 <= tx1) {
+            uint8_t *d = dst + (size_t)(f0 + f) * dframe;
+#pragma unroll
+            for (int kk = 0; kk < PYR_TH / 4; kk++) {
+                const int dy = ty0 + threadIdx.y * (PYR_TH / 4) + kk;
+                if (dy > ty1) break;
+                const uint2 a = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] & 0xFFFF) * PYR_TW + cx);
+                const uint2 b = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] >> 16) * PYR_TW + cx);
+                const int w0 = (int)(yc[kk] & 0xFFFF), w1 = (int)(yc[kk] >> 16);
+                const int h0[4] = {(int)(a.x & 0xFFFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16)};
+                const int h1[4] = {(int)(b.x & 0xFFFF), (int)(b.x >> 16), (int)(b.y & 0xFFFF), (int)(b.y >> 16)};
+                uint32_t out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int v = (((w0 * h0[k]) >> 16) + ((w1 * h1[k]) >> 16) + 2) >> 2;
+                    out |= (uint32_t)(v & 0xFF) << (8 * k);
+                }
+                if (dx0 + 3 < dw) *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
+                else for (int k = 0; k < 4 && dx0 + k < dw; k++) d[(size_t)dy * dpitch + dx0 + k] = (uint8_t)(out >> (8 * k));
+            }
+        }
+        __syncthreads();                                   // H free for the next frame
+    }
+}
+
 // Host: shared-memory box (pitch, rows) needed by the worst tile of a level.
 void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
                    const std::vector<int32_t> &y1, int *bp, int *bh)
@@ -154,9 +264,21 @@ pyr_resize_area2_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 }
 
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
-                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh)
+                     size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh,
+                     const CUtensorMap *tmap)
 {
     ProfScope prof__(ctx, "pyr_resize");
+    static const bool use_tma = !(getenv("TB_PYR_TMA") && atoi(getenv("TB_PYR_TMA")) == 0);   // A/B knob: 0 forces the LDG-staged kernel
+    if (!area2 && tmap && use_tma && bp <= 2 * PYR_BOXW && bh <= 256) {
+        const size_t box_bytes = ((size_t)bh * PYR_BOXW + 127) & ~(size_t)127;
+        const size_t smem = 4 * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
+        if (smem <= 200 * 1024) {
+            dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, PYR_FPC)), block(64, 4);
+            pyr_resize_linear_u8_tma<<<grid, block, smem, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames);
+            TB_LAUNCH_CHECK(ctx);
+            return TB_OK;
+        }
+    }
     if (area2) {
         dim3 grid(div_up(dw, 64), div_up(dh, 4), n_frames), block(64, 4);
         pyr_resize_area2_u8<<<grid, block, 0, ctx->stream>>>(src, spitch, sframe, dst, dpitch, dframe, dw, dh);
@@ -170,4 +292,13 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
     return TB_OK;
 }
 
-void tb_pyramid_init_device() { cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
+void tb_pyramid_init_device()
+{
+    cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pyr_resize_linear_u8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+// tensor map over a level's frames for the TMA resize (box = PYR_BOXW x box_rows); false if the layout does not qualify
+bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows)
+{
+    return tb_encode_tiled_u8_3d(tm, src, w, h, n_frames, (size_t)pitch, frame_stride, PYR_BOXW, box_rows);
+}
