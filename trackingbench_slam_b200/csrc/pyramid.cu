@@ -150,13 +150,13 @@ __device__ __forceinline__ void pyr_mbar_wait(uint64_t *bar, uint32_t parity)
 
 __global__ void __launch_bounds__(256, 3)
 pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, int dpitch, size_t dframe,
-                         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames)
+                         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames, int fpc)
 {
     __shared__ alignas(8) uint64_t s_full[2];
     const int tid = threadIdx.y * 64 + threadIdx.x;
     const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
     const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
-    const int f0 = blockIdx.z * PYR_FPC, nf = min(n_frames, f0 + PYR_FPC) - f0;
+    const int f0 = blockIdx.z * fpc, nf = min(n_frames, f0 + fpc) - f0;
     const int box_bytes = (bh_max * PYR_BOXW + 127) & ~127;                       // one 192-wide box, 128-byte aligned
     uint8_t *boxes = pyr_smem;                                                    // [2 stages][2 boxes][box_bytes]
     uint16_t *Hs = reinterpret_cast<uint16_t *>(pyr_smem + 4 * (size_t)box_bytes); // bh_max x PYR_TW u16
@@ -273,8 +273,9 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
         const size_t box_bytes = ((size_t)bh * PYR_BOXW + 127) & ~(size_t)127;
         const size_t smem = 4 * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
         if (smem <= 200 * 1024) {
-            dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, PYR_FPC)), block(64, 4);
-            pyr_resize_linear_u8_tma<<<grid, block, smem, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames);
+            static const int fpc = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;   // frames per CTA (tuning knob)
+            dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, fpc)), block(64, 4);
+            pyr_resize_linear_u8_tma<<<grid, block, smem, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
             TB_LAUNCH_CHECK(ctx);
             return TB_OK;
         }
