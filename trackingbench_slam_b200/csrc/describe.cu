@@ -185,94 +185,113 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 
-__global__ void __launch_bounds__(256)
+// pattern transposed once per device into global memory: g_pat_t[k*32 + lane] = pair 8*lane+k as (x0,y0,x1,y1) int8x4
+// (reading c_pattern with a per-lane index serialises in the constant cache, so no kernel does that per CTA)
+__device__ uint32_t g_pat_t[256];
+__global__ void describe_init_pattern()
+{
+    const int tid = threadIdx.x, k = tid >> 5, ln = tid & 31;
+    const int8_t *q = &c_pattern[4 * (8 * ln + k)];
+    g_pat_t[tid] = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8) | ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
+}
+void tb_describe_init_device() { describe_init_pattern<<<1, 256>>>(); cudaDeviceSynchronize(); }
+
+#define DESC_KPB 64   // keypoints per CTA (8 warps x 8 rounds)
+__global__ void __launch_bounds__(256, 4)
 orb_describe(DescArgs a)
 {
     __shared__ uint32_t s_pat[256]; // [k][lane]: pair 8*lane+k as (x0,y0,x1,y1) int8x4, conflict-free
+    __shared__ int s_ofs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = blockIdx.y, f = blockIdx.z;
-    {
-        int k = tid >> 5, ln = tid & 31; // tid = k*32 + ln
-        const int8_t *q = &c_pattern[4 * (8 * ln + k)];
-        s_pat[tid] = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8) | ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
+    const int *nk = a.n_kept + (size_t)f * a.n_levels;
+    const int nkl = nk[l];
+    const bool first = blockIdx.x == 0 && l == 0;
+    if (blockIdx.x * DESC_KPB >= nkl && !first) return;          // nothing for this CTA (uniform)
+    s_pat[tid] = g_pat_t[tid];
+    if (warp == 0) {
+        // output offset of this level = keypoints of the levels below; the frame's total goes to n_kp
+        int c = lane < a.n_levels ? nk[lane] : 0;
+        int below = lane < l ? c : 0, total = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+        if (lane == 0) {
+            s_ofs = below;
+            if (first) {
+                a.n_kp[f] = min(total, a.kp_cap);
+                if (total > a.kp_cap) atomicExch(a.overflow, 4);
+            }
+        }
     }
     __syncthreads();
-    const int *nk = a.n_kept + (size_t)f * a.n_levels;
-    int ofs = 0, total = 0;
-    for (int i = 0; i < a.n_levels; i++) { int c = nk[i]; if (i < l) ofs += c; total += c; }
-    if (blockIdx.x == 0 && l == 0 && tid == 0) {
-        a.n_kp[f] = min(total, a.kp_cap);
-        if (total > a.kp_cap) atomicExch(a.overflow, 4);
-    }
-    const int i = blockIdx.x * 8 + warp;
-    if (i >= nk[l]) return;
+    const int ofs = s_ofs;
     const DescLevel L = a.lv[l];
-    const uint32_t c = L.kept[(size_t)f * L.kept_cap + i];
-    const int cx = cand_x(c) + 16, cy = cand_y(c) + 16; // + minBorder (:816-817)
-    const int out = ofs + i;
-    if (out >= a.kp_cap) return;
-
-    // ---- IC_Angle on the un-blurred level: lanes 0..30 = u in [-15,15], loop over rows
-    const uint8_t *raw = L.raw + (size_t)f * L.frame_stride + (size_t)cy * L.pitch + cx;
-    int m10 = 0, m01 = 0;
-    const int u = lane - 15;
-    if (lane < 31) {
-        // all 31 row loads are independent: issue them together (the kernel is latency bound otherwise)
-        int vals[31];
-#pragma unroll
-        for (int v = -15; v <= 15; v++) {
-            const int um = c_umax[v < 0 ? -v : v];
-            vals[v + 15] = (u >= -um && u <= um) ? (int)raw[v * L.pitch + u] : 0;
-        }
-        int s0 = 0;
-#pragma unroll
-        for (int v = -15; v <= 15; v++) { s0 += vals[v + 15]; m01 += v * vals[v + 15]; }
-        m10 = u * s0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- steered rBRIEF on the blurred level; lane i produces byte i
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    // glibc cosf/sinf are (nearly always) correctly rounded; evaluate in double and round once
-    const float ca = (float)cos((double)ang), sb = (float)sin((double)ang);
-    const uint8_t *blur = L.blur + (size_t)f * L.frame_stride + (size_t)cy * L.pitch + cx;
-    int val = 0;
+    for (int i = blockIdx.x * DESC_KPB + warp; i < min(nkl, (int)(blockIdx.x + 1) * DESC_KPB); i += 8) {
+        const uint32_t c = L.kept[(size_t)f * L.kept_cap + i];
+        const int cx = cand_x(c) + 16, cy = cand_y(c) + 16; // + minBorder (:816-817)
+        const int out = ofs + i;
+        if (out >= a.kp_cap) break;
+
+        // ---- IC_Angle on the un-blurred level: lanes 0..30 = u in [-15,15], loop over rows
+        const uint8_t *raw = L.raw + (size_t)f * L.frame_stride + (size_t)cy * L.pitch + cx;
+        int m10 = 0, m01 = 0;
+        const int u = lane - 15;
+        if (lane < 31) {
+            // all 31 row loads are independent: issue them together (the kernel is latency bound otherwise)
+            const int au = u < 0 ? -u : u;
+            int vals[31];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        uint32_t q = s_pat[k * 32 + lane];
-        float x0 = (float)(int8_t)(q & 0xFF), y0 = (float)(int8_t)((q >> 8) & 0xFF);
-        float x1 = (float)(int8_t)((q >> 16) & 0xFF), y1 = (float)(int8_t)(q >> 24);
-        int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
-        int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
-        int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
-        int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
-        int t0 = blur[r0 * L.pitch + c0], t1 = blur[r1 * L.pitch + c1];
-        val |= (t0 < t1) << k;
-    }
-    a.desc[((size_t)f * a.kp_cap + out) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        tb_keypoint kp;
-        kp.x = (float)cx; kp.y = (float)cy;
-        if (l != 0) { kp.x = __fmul_rn(kp.x, L.sf); kp.y = __fmul_rn(kp.y, L.sf); } // :969-974 (multiplies; replicated)
-        kp.size = L.size;
-        kp.angle = angle;
-        kp.response = (float)(cand_m(c) - 1);
-        kp.octave = l;
-        kp.class_id = -1;
-        a.kps[(size_t)f * a.kp_cap + out] = kp;
+            for (int v = -15; v <= 15; v++) vals[v + 15] = (au <= c_umax[v < 0 ? -v : v]) ? (int)raw[v * L.pitch + u] : 0;
+            int s0 = 0;
+#pragma unroll
+            for (int v = -15; v <= 15; v++) { s0 += vals[v + 15]; m01 += v * vals[v + 15]; }
+            m10 = u * s0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- steered rBRIEF on the blurred level; lane i produces byte i
+        const float ang = __fmul_rn(angle, factorPI);
+        // glibc cosf/sinf are (nearly always) correctly rounded; evaluate in double and round once
+        const float ca = (float)cos((double)ang), sb = (float)sin((double)ang);
+        const uint8_t *blur = L.blur + (size_t)f * L.frame_stride + (size_t)cy * L.pitch + cx;
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t q = s_pat[k * 32 + lane];
+            float x0 = (float)(int8_t)(q & 0xFF), y0 = (float)(int8_t)((q >> 8) & 0xFF);
+            float x1 = (float)(int8_t)((q >> 16) & 0xFF), y1 = (float)(int8_t)(q >> 24);
+            int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
+            int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
+            int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
+            int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
+            int t0 = blur[r0 * L.pitch + c0], t1 = blur[r1 * L.pitch + c1];
+            val |= (t0 < t1) << k;
+        }
+        a.desc[((size_t)f * a.kp_cap + out) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            tb_keypoint kp;
+            kp.x = (float)cx; kp.y = (float)cy;
+            if (l != 0) { kp.x = __fmul_rn(kp.x, L.sf); kp.y = __fmul_rn(kp.y, L.sf); } // :969-974 (multiplies; replicated)
+            kp.size = L.size;
+            kp.angle = angle;
+            kp.response = (float)(cand_m(c) - 1);
+            kp.octave = l;
+            kp.class_id = -1;
+            a.kps[(size_t)f * a.kp_cap + out] = kp;
+        }
     }
 }
 
 int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames)
 {
     ProfScope prof__(ctx, "orb_describe");
-    dim3 grid(div_up(max_kept_per_level, 8), a.n_levels, n_frames);
+    dim3 grid(div_up(max_kept_per_level, DESC_KPB), a.n_levels, n_frames);
     orb_describe<<<grid, 256, 0, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;

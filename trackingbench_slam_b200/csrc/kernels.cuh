@@ -79,3 +79,4 @@ void tb_fast_init_device();
 void tb_octree_init_device();
 void tb_pyramid_init_device();
 void tb_match_tc_init_device();
+void tb_describe_init_device();
