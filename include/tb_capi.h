@@ -268,6 +268,13 @@ int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p,
                      const tb_keypoint *k2, const uint8_t *d2, const int32_t *node2, int n2,
                      const uint8_t *mp_valid2, int map_point_only, tb_match *out, int capacity, int *n);
 
+/* Device-resident, batched Matcher::searchByViolence (matcher.cpp:299-395, MapPointOnly=false) over frames of the
+ * frontend's last extract: pair p matches the keypoints of frame f1_frames[p] inside windows of half-size search_r on the
+ * search grid of frame f2_frames[p]. Outputs on the device: matches_dptr[p*capacity + i], counts_dptr[p]. */
+int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames,
+                                   const int32_t *f2_frames, int min_level, int max_level, float search_r,
+                                   void *matches_dptr, int capacity, void *counts_i32_dptr);
+
 /* Device-resident, batched Frame::SetBow + Matcher::searchByBow over the frames of the frontend's last extract.
  * tb_frontend_set_bow writes the FeatureVector of every frame as node_dptr[frame][tb_frontend_kp_capacity()] (i32; -1 =
  * stopped word or slot beyond the frame's keypoint count) and optionally the per-feature word id (i32) / weight (f64).

@@ -302,3 +302,39 @@ def test_frontend_batched_projection_device_resident(tb, ctx, oracle, images):
             assert total > 200
     finally:
         fe.close()
+
+
+def test_frontend_batched_violence_device_resident(tb, ctx, oracle, images):
+    """tb_frontend_search_by_violence: keypoints, descriptors, grids and matches stay on the device."""
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    frames = np.stack([images['left'], images['right'], synth_frame(1, W, H), synth_frame(2, W, H)])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=4, max_target=tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(4)
+        fe.extract(4, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(4)
+        cap = fe.kp_cap
+        pairs = [(0, 1), (1, 0), (2, 3), (3, 2), (0, 0), (0, 3)]
+        for chk, lo, hi, r, ratio in ((1, 0, nl, 50.0, 5.0), (0, 0, 1, 10.0, 0.8), (1, 1, 3, 30.0, 0.9)):
+            p = tb.MatcherParams(30, 100, 30, chk, ratio)
+            po = oracle.MatcherParams(30, 100, 30, chk, ratio)
+            m = torch.zeros((len(pairs), cap, 4), dtype=torch.int32, device='cuda')
+            c = torch.zeros(len(pairs), dtype=torch.int32, device='cuda')
+            fe.search_by_violence(p, [q[0] for q in pairs], [q[1] for q in pairs], lo, hi, r, m.data_ptr(), cap, c.data_ptr())
+            ctx.sync()
+            cn = c.cpu().numpy()
+            mm = m.cpu().numpy().view(np.uint8).reshape(len(pairs), cap, 16)
+            total = 0
+            for i, (f1, f2) in enumerate(pairs):
+                n1, n2 = counts[f1], counts[f2]
+                exp = oracle.search_by_violence(po, kps[f1, :n1], desc[f1, :n1], kps[f2, :n2], desc[f2, :n2], W, H, lo, hi, r)
+                assert cn[i] == len(exp), (chk, i, cn[i], len(exp))
+                assert mm[i, :cn[i]].tobytes() == exp.tobytes(), (chk, i)
+                total += len(exp)
+            assert total > 50
+    finally:
+        fe.close()

@@ -34,7 +34,7 @@ EXPORTS = [
     'tb_frontend_search_by_bf', 'tb_frontend_search_by_projection', 'tb_features_in_area', 'tb_search_by_violence', 'tb_search_by_projection',
     'tb_search_by_projection_map', 'tb_three_maxima',
     'tb_vocab_create', 'tb_vocab_destroy', 'tb_bow_transform', 'tb_bow_transform_device', 'tb_search_by_bow',
-    'tb_frontend_set_bow', 'tb_frontend_search_by_bow',
+    'tb_frontend_set_bow', 'tb_frontend_search_by_bow', 'tb_frontend_search_by_violence',
     'tb_init_undistort_rectify_map', 'tb_undistort_create', 'tb_undistort_destroy', 'tb_undistort_image_device',
     'tb_undistort_image_host', 'tb_frontend_undistort_device', 'tb_frontend_upload_frames_undistort',
     'tb_clahe_device', 'tb_clahe_host',
@@ -487,3 +487,13 @@ def _frontend_undistort_device(self, und, first, n, raw_dptr, raw_w, raw_h, raw_
 
 Frontend.upload_frames_undistort = _frontend_upload_frames_undistort
 Frontend.undistort_device = _frontend_undistort_device
+
+
+def _frontend_search_by_violence(self, params, f1_frames, f2_frames, min_level, max_level, search_r, matches_dptr, capacity, counts_dptr):
+    f1 = np.ascontiguousarray(f1_frames, np.int32)
+    f2 = np.ascontiguousarray(f2_frames, np.int32)
+    self.ctx.check(lib().tb_frontend_search_by_violence(self.h, C.byref(params), len(f1), _vp(f1), _vp(f2), int(min_level), int(max_level),
+                                                        C.c_float(search_r), _vp(matches_dptr), int(capacity), _vp(counts_dptr)))
+
+
+Frontend.search_by_violence = _frontend_search_by_violence

@@ -588,6 +588,17 @@ extern "C" int tb_frontend_search_by_bow(tb_frontend *fe, const tb_matcher_param
                                  (const uint8_t *)mp_valid, map_point_only, (tb_match *)matches, capacity, (int *)counts);
 }
 
+extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames,
+                                              const int32_t *f2_frames, int min_level, int max_level, float search_r,
+                                              void *matches, int capacity, void *counts)
+{
+    if (!fe || !p || n_pairs < 0 || !f1_frames || !f2_frames || !matches || !counts) return TB_E_INVALID;
+    for (int i = 0; i < n_pairs; i++)
+        if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
+    return tb_window_violence_batched(fe->ctx, p, n_pairs, f1_frames, f2_frames, fe->B, fe->kps, fe->desc, fe->kp_cap, fe->n_kp,
+                                      fe->g[0].w, fe->g[0].h, min_level, max_level, search_r, (tb_match *)matches, capacity, (int *)counts);
+}
+
 extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs,
                                                 const int32_t *f1_frames, const int32_t *f2_frames, const float *Tcw1,
                                                 const void *f1_matched, const void *mp_valid, const void *mp_xyz,

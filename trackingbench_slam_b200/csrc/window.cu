@@ -722,7 +722,64 @@ emit_matches_batched(const ProjPair *__restrict__ pairs, const QRes *__restrict_
     if (tid == 0) out_n[pidx] = s_run;
 }
 
+// searchByViolence over frames of one frontend: pair p matches the keypoints of frame f1 inside windows on the grid of f2
+__global__ void __launch_bounds__(256)
+violence_query_batched(const ProjPair *__restrict__ pairs, const tb_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc,
+                       int kp_cap, const int *__restrict__ counts, const int *__restrict__ cell_start, const int *__restrict__ items,
+                       float wInv, float hInv, int min_level, int max_level, float search_r, tb_matcher_params p, QRes *__restrict__ res)
+{
+    const ProjPair &pr = pairs[blockIdx.y];
+    const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int n1 = min(counts[pr.f1], kp_cap);
+    if (i1 >= n1) return;
+    GridDev g2;
+    g2.cell_start = cell_start + (size_t)pr.f2 * (GRID_CELLS + 1);
+    g2.items = items + (size_t)pr.f2 * kp_cap;
+    g2.kps = kps + (size_t)pr.f2 * kp_cap;
+    g2.wInv = wInv; g2.hInv = hInv;
+    const uint8_t *d2 = desc + (size_t)pr.f2 * kp_cap * 32;
+    const size_t o1 = (size_t)pr.f1 * kp_cap + i1;
+    uint32_t q[8];
+    load_desc(q, desc + o1 * 32);
+    const tb_keypoint kp = kps[o1];
+    Top2 t = window_scan(g2, kp.x, kp.y, search_r, min_level, max_level, q, d2, nullptr, nullptr, nullptr);
+    if ((threadIdx.x & 31) == 0) {
+        QRes r = {0, i1, -1, 0, 0};
+        if (t.i1 >= 0) {
+            const int bestDist = (int)(t.k1 >> 20);
+            const int bestDist2 = t.i2 >= 0 ? (int)(t.k2 >> 20) : 0x7fffffff;
+            if (bestDist <= p.TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, p.nRatio)) {
+                r.ok = 1; r.t = t.i1; r.dist = bestDist;
+                if (p.checkOrientation) r.bin = rot_bin(kp.angle, g2.kps[t.i1].angle, p.HISTO_LENGTH);
+            }
+        }
+        res[(size_t)blockIdx.y * kp_cap + i1] = r;
+    }
+}
+
 struct WinWs { int *cell_start = nullptr, *items = nullptr; QRes *res = nullptr; ProjPair *pairs = nullptr; size_t frames = 0, pairs_cap = 0, kp_cap = 0; };
+
+static int win_ws_reserve(tb_ctx *ctx, int n_frames, int n_pairs, int kp_cap, bool need_grid)
+{
+    if (!ctx->wws) ctx->wws = new WinWs();
+    WinWs &w = *ctx->wws;
+    if ((size_t)kp_cap != w.kp_cap || (need_grid && (size_t)n_frames > w.frames)) {
+        cudaFree(w.cell_start); cudaFree(w.items); cudaFree(w.res); cudaFree(w.pairs);
+        w.cell_start = nullptr; w.items = nullptr; w.res = nullptr; w.pairs = nullptr; w.frames = 0; w.pairs_cap = 0; w.kp_cap = kp_cap;
+    }
+    if (need_grid && (size_t)n_frames > w.frames) {
+        TB_CUDA(ctx, cudaMalloc(&w.cell_start, sizeof(int) * (size_t)n_frames * (GRID_CELLS + 1)));
+        TB_CUDA(ctx, cudaMalloc(&w.items, sizeof(int) * (size_t)n_frames * kp_cap));
+        w.frames = n_frames;
+    }
+    if ((size_t)n_pairs > w.pairs_cap) {
+        cudaFree(w.res); cudaFree(w.pairs); w.res = nullptr; w.pairs = nullptr;
+        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
+        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
+        w.pairs_cap = n_pairs;
+    }
+    return TB_OK;
+}
 
 int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs, const int32_t *f1_frames,
                                  const int32_t *f2_frames, const float *Tcw1, int n_frames, const tb_keypoint *kps, const uint8_t *desc,
@@ -732,20 +789,9 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
     if (n_pairs <= 0) return TB_OK;
     if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched projection matcher supports up to 8192 keypoints per frame");
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
-    if (!ctx->wws) ctx->wws = new WinWs();
+    int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
+    if (rc) return rc;
     WinWs &w = *ctx->wws;
-    if ((size_t)n_frames > w.frames || (size_t)kp_cap != w.kp_cap) {
-        cudaFree(w.cell_start); cudaFree(w.items);
-        TB_CUDA(ctx, cudaMalloc(&w.cell_start, sizeof(int) * (size_t)n_frames * (GRID_CELLS + 1)));
-        TB_CUDA(ctx, cudaMalloc(&w.items, sizeof(int) * (size_t)n_frames * kp_cap));
-        w.frames = n_frames; w.kp_cap = kp_cap; w.pairs_cap = 0;
-    }
-    if ((size_t)n_pairs > w.pairs_cap) {
-        cudaFree(w.res); cudaFree(w.pairs);
-        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
-        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
-        w.pairs_cap = n_pairs;
-    }
     std::vector<ProjPair> hp(n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; memcpy(hp[i].T, Tcw1 + 16 * (size_t)i, sizeof(float) * 16); }
     TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -1077,15 +1123,9 @@ int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, 
     (void)n_frames;
     if (n_pairs <= 0) return TB_OK;
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
-    if (!ctx->wws) ctx->wws = new WinWs();
+    int rc = win_ws_reserve(ctx, 0, n_pairs, kp_cap, false);
+    if (rc) return rc;
     WinWs &w = *ctx->wws;
-    if ((size_t)n_pairs > w.pairs_cap || (size_t)kp_cap != w.kp_cap) {
-        cudaFree(w.res); cudaFree(w.pairs); cudaFree(w.cell_start); cudaFree(w.items);
-        w.res = nullptr; w.pairs = nullptr; w.cell_start = nullptr; w.items = nullptr; w.frames = 0;
-        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
-        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
-        w.pairs_cap = n_pairs; w.kp_cap = kp_cap;
-    }
     std::vector<ProjPair> hp(n_pairs);
     memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; }
@@ -1094,6 +1134,41 @@ int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, 
     {
         ProfScope prof__(ctx, "bow_query_batched");
         bow_query_batched<<<dim3(div_up(kp_cap, 8), n_pairs), 256, 0, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, node, mp_valid, map_point_only, *p, w.res);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope prof__(ctx, "emit_matches_batched");
+        emit_matches_batched<<<n_pairs, 256, 0, ctx->stream>>>(w.pairs, w.res, kp_cap, counts, p->checkOrientation, p->HISTO_LENGTH, matches, capacity, out_counts, 1);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    return TB_OK;
+}
+
+int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames,
+                               int n_frames, const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, int cols, int rows,
+                               int min_level, int max_level, float search_r, tb_match *matches, int capacity, int *out_counts)
+{
+    if (n_pairs <= 0) return TB_OK;
+    if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched windowed matcher supports up to 8192 keypoints per frame");
+    if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
+    if (rc) return rc;
+    WinWs &w = *ctx->wws;
+    std::vector<ProjPair> hp(n_pairs);
+    memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
+    for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; }
+    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    volatile float hInv = (float)GRID_COLS / (float)cols, wInv = (float)GRID_ROWS / (float)rows;   // Frame.cpp:30-31
+    {
+        ProfScope prof__(ctx, "grid_build_batched");
+        grid_build_batched<<<n_frames, 1024, 0, ctx->stream>>>(kps, kp_cap, counts, wInv, hInv, w.cell_start, w.items);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope prof__(ctx, "violence_query_batched");
+        violence_query_batched<<<dim3(div_up(kp_cap, 8), n_pairs), 256, 0, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, w.cell_start, w.items,
+                                                                                            wInv, hInv, min_level, max_level, search_r, *p, w.res);
         TB_LAUNCH_CHECK(ctx);
     }
     {
