@@ -18,8 +18,9 @@ struct tb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // side stream + events: the Gaussian levels run here, concurrently with the latency-bound octree kernel
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;   // side: Gaussian levels; side2: per-level octree launches behind FAST
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_lvl[TB_MAX_LEVELS] = {};
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;

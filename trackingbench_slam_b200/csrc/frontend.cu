@@ -27,9 +27,15 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ev_ok = true;
+    for (int l = 0; l < TB_MAX_LEVELS; l++) ev_ok = ev_ok && cudaEventCreateWithFlags(&c->ev_lvl[l], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok || cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||   // its few CTAs go first
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
         return TB_E_CUDA;
@@ -47,8 +53,11 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_window_ws_free(ctx);
     tb_ingest_ws_free(ctx);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+    for (int l = 0; l < TB_MAX_LEVELS; l++) if (ctx->ev_lvl[l]) cudaEventDestroy(ctx->ev_lvl[l]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -368,6 +377,24 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
     TB_CUDA(ctx, cudaMemsetAsync(fe->n_kept, 0, sizeof(int) * (size_t)n_frames * L, ctx->stream));
     TB_CUDA(ctx, cudaMemsetAsync(fe->overflow, 0, sizeof(int) * 4, ctx->stream));
 
+    // Three streams inside one extract (joined before the describe launch):
+    //   main : FAST level 0..L-1 (instruction bound, the critical path)
+    //   side : the Gaussian levels — they only need the pyramid, so they start right away and fill FAST's issue gaps
+    //   side2: the octree of level l as soon as FAST(l) is done — latency bound (one CTA per frame), it hides entirely
+    //          behind FAST of the following levels
+    // (With per-kernel profiling on, everything stays on the main stream so the event pairs stay meaningful.)
+    const bool overlap = !ctx->profiling;
+    cudaStream_t gs = overlap ? ctx->side : ctx->stream, os = overlap ? ctx->side2 : ctx->stream;
+    if (overlap) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        for (int l = 0; l < L; l++) {
+            const LevelGeom &g = fe->g[l];
+            int rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
+            if (rc) return rc;
+        }
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+    }
     int max_budget = 0;
     OctArgs oct[TB_MAX_LEVELS];
     for (int l = 0; l < L; l++) {
@@ -405,28 +432,25 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
         o.kept = fe->kept[l]; o.kept_cap = fe->kept_cap; o.n_kept = fe->n_kept + l; o.overflow = fe->overflow;
         o.node_cap = fe->budget[l] + 4 * (g.nIni > 0 ? g.nIni : 1) + 8;
         if (fe->budget[l] > max_budget) max_budget = fe->budget[l];
-    }
-    // The octree kernel is latency bound (one CTA per (frame, level), most SMs idle) while the Gaussian only
-    // needs the pyramid: run the Gaussian levels on the side stream, concurrently with the octree.
-    // (With per-kernel profiling on, everything stays on the main stream so the event pairs stay meaningful.)
-    const bool overlap = !ctx->profiling;
-    cudaStream_t gs = overlap ? ctx->side : ctx->stream;
-    if (overlap) {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    }
-    {
-        int rc = tb_launch_octree(ctx, oct, L, n_frames);
-        if (rc) return rc;
-    }
-    for (int l = 0; l < L; l++) {
-        const LevelGeom &g = fe->g[l];
-        int rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
-        if (rc) return rc;
+        if (overlap) {
+            TB_CUDA(ctx, cudaEventRecord(ctx->ev_lvl[l], ctx->stream));
+            TB_CUDA(ctx, cudaStreamWaitEvent(os, ctx->ev_lvl[l], 0));
+            int rc = tb_launch_octree(ctx, &oct[l], 1, n_frames, os);
+            if (rc) return rc;
+        }
     }
     if (overlap) {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_join2, os));
         TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+    } else {
+        int rc = tb_launch_octree(ctx, oct, L, n_frames, ctx->stream);
+        if (rc) return rc;
+        for (int l = 0; l < L; l++) {
+            const LevelGeom &g = fe->g[l];
+            rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
+            if (rc) return rc;
+        }
     }
     DescArgs d;
     memset(&d, 0, sizeof d);

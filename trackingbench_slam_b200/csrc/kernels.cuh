@@ -40,7 +40,7 @@ struct OctArgs {
     int node_cap;
 };
 size_t tb_octree_smem_bytes(int node_cap);
-int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames);
+int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames, cudaStream_t stream);
 int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames);
 struct DescLevel {
     const uint8_t *raw, *blur;

@@ -363,7 +363,7 @@ size_t tb_octree_smem_bytes(int node_cap)
     return sizeof(unsigned long long) * m2 + (size_t)node_cap * (2 * sizeof(short4) + 2 * sizeof(int) + 4 * sizeof(int) + 2 * sizeof(int));
 }
 
-int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames)
+int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames, cudaStream_t stream)
 {
     OctArgsAll all;
     memset(&all, 0, sizeof all);
@@ -373,7 +373,7 @@ int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_fra
     size_t smem = tb_octree_smem_bytes(max_cap);
     if (smem > 200 * 1024 || max_cap > 8191) return tb_fail(ctx, TB_E_UNSUPPORTED, "octree: per-level budget too large for shared memory");
     ProfScope prof__(ctx, "octree_distribute");
-    octree_distribute<<<dim3(n_frames, n_levels), OCT_THREADS, smem, ctx->stream>>>(all);
+    octree_distribute<<<dim3(n_frames, n_levels), OCT_THREADS, smem, stream>>>(all);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
