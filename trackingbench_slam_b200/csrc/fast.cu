@@ -135,11 +135,13 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 //      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
 //   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map
 //   5  NMS inside the cell interior, emission with one global atomic per pass
-#define FAST_QCAP 288   // per-warp survivor queue: up to 31 waiting + 256 new per iteration
+__device__ uint32_t g_bitpos[256];   // set-bit positions of a byte (3 bits each, lowest first), filled by tb_fast_init_device
+#define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
 struct FastSmem {
     uint8_t *tile, *sc, *cellOf, *need;
     uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (capacity = all pixels)
     uint32_t *stage;           // NMS survivors staged for the single global reservation (<= cap/4 + 1 entries)
+    uint32_t *bitpos;          // [256] positions of the set bits of a byte, 3 bits each, lowest first
 };
 
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
@@ -159,7 +161,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         int qn = 0;                                     // warp-uniform queue fill
         const bool swar = T <= 127;                     // larger thresholds skip the byte-SIMD test: everything is scored
         const uint32_t K = (uint32_t)(127 - (swar ? T : 0)) * 0x01010101u;
-        const int g0 = (cs + col_lo) >> 3, nG = ((cs + col_hi + 7) >> 3) - g0;
+        const int g0 = (cs + col_lo) >> 4, nG = ((cs + col_hi + 15) >> 4) - g0;      // 16-pixel groups
         const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
         const int items = hEff * nG;
         // score 32 (or, for the final flush, fewer) queued pixels; corners go to the block's corner list
@@ -176,40 +178,49 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         };
         for (int base = 0; base < items; base += 256) {
             const int it = base + tid;
-            uint32_t c0 = 0, c1 = 0;
+            uint32_t c[4] = {0, 0, 0, 0};
             int r = 0, o = 0;
             if (it < items) {
                 r = fast_div(it, magic);
-                o = 8 * (it - r * nG + g0);
-                const uint2 nd = *reinterpret_cast<const uint2 *>(S.need + o);
-                if (nd.x | nd.y) {
+                o = 16 * (it - r * nG + g0);
+                const uint4 nd = *reinterpret_cast<const uint4 *>(S.need + o);
+                if (nd.x | nd.y | nd.z | nd.w) {
                     if (swar) {
                         const uint8_t *row = tile + (r + 3) * tp + o;
-                        const uint2 cen = *reinterpret_cast<const uint2 *>(row);
-                        const uint2 up = *reinterpret_cast<const uint2 *>(row - 3 * tp);
-                        const uint2 dn = *reinterpret_cast<const uint2 *>(row + 3 * tp);
+                        const uint4 cen = *reinterpret_cast<const uint4 *>(row);
+                        const uint4 up = *reinterpret_cast<const uint4 *>(row - 3 * tp);
+                        const uint4 dn = *reinterpret_cast<const uint4 *>(row + 3 * tp);
                         const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
-                        const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 8);
-                        const uint32_t lw0 = __byte_perm(L, cen.x, 0x4321), lw1 = __byte_perm(cen.x, cen.y, 0x4321);
-                        const uint32_t rw0 = __byte_perm(cen.x, cen.y, 0x6543), rw1 = __byte_perm(cen.y, R, 0x6543);
-                        c0 = compass_signed(dn.x, up.x, rw0, lw0, cen.x, K) & nd.x;
-                        c1 = compass_signed(dn.y, up.y, rw1, lw1, cen.y, K) & nd.y;
-                    } else { c0 = nd.x; c1 = nd.y; }
+                        const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 16);
+                        // west = pixel x-3, east = pixel x+3 of every byte lane
+                        c[0] = compass_signed(dn.x, up.x, __byte_perm(cen.x, cen.y, 0x6543), __byte_perm(L, cen.x, 0x4321), cen.x, K) & nd.x;
+                        c[1] = compass_signed(dn.y, up.y, __byte_perm(cen.y, cen.z, 0x6543), __byte_perm(cen.x, cen.y, 0x4321), cen.y, K) & nd.y;
+                        c[2] = compass_signed(dn.z, up.z, __byte_perm(cen.z, cen.w, 0x6543), __byte_perm(cen.y, cen.z, 0x4321), cen.z, K) & nd.z;
+                        c[3] = compass_signed(dn.w, up.w, __byte_perm(cen.w, R, 0x6543), __byte_perm(cen.z, cen.w, 0x4321), cen.w, K) & nd.w;
+                    } else { c[0] = nd.x; c[1] = nd.y; c[2] = nd.z; c[3] = nd.w; }
                 }
             }
-            const int cnt = __popc(c0) + __popc(c1);
+            // bit 7 of every byte -> one flag bit per pixel (the multiply moves bits 7,15,23,31 to 28..31 without carries)
+            const uint32_t m16 = ((c[0] & 0x80808080u) * 0x00204081u >> 28) | (((c[1] & 0x80808080u) * 0x00204081u >> 28) << 4) |
+                                 (((c[2] & 0x80808080u) * 0x00204081u >> 28) << 8) | (((c[3] & 0x80808080u) * 0x00204081u >> 28) << 12);
+            const int cnt = __popc(m16);
             int inc = cnt;                               // inclusive warp scan of the survivor counts
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (total == 0) continue;                    // nothing in this warp's 256 pixels
+            if (total == 0) continue;                    // nothing in this warp's 512 pixels
             if (cnt) {
-                int pos = qn + inc - cnt;
+                // set-bit positions of each flag byte from a 256-entry table (eight 3-bit positions per entry)
                 const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
+                uint16_t *qp = q + qn + inc - cnt;
+                const uint32_t lo = m16 & 0xFF, hi = m16 >> 8;
+                const uint32_t tl = S.bitpos[lo], th = S.bitpos[hi];
+                const int nl = __popc(lo);
 #pragma unroll
-                for (int b = 0; b < 4; b++) if (c0 & (0x80u << (8 * b))) q[pos++] = (uint16_t)(e0 + b);
+                for (int j = 0; j < 8; j++) if (j < nl) qp[j] = (uint16_t)(e0 + ((tl >> (3 * j)) & 7));
+                qp += nl;
 #pragma unroll
-                for (int b = 0; b < 4; b++) if (c1 & (0x80u << (8 * b))) q[pos++] = (uint16_t)(e0 + 4 + b);
+                for (int j = 0; j < 8; j++) if (j < cnt - nl) qp[j] = (uint16_t)(e0 + 8 + ((th >> (3 * j)) & 7));
             }
             qn += total;
             __syncwarp();
@@ -300,6 +311,7 @@ fast9_cells(FastArgs a)
     S.queue = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
     S.listB = S.queue + 8 * FAST_QCAP;
     S.stage = reinterpret_cast<uint32_t *>(S.listB + ((cap + 7) & ~7));
+    S.bitpos = S.stage + (((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8);
     __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
     __shared__ int s_has[64];
 
@@ -343,6 +355,7 @@ fast9_cells(FastArgs a)
         S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
         if (i < a.scw) S.cellOf[i] = (uint8_t)fast_div(i, a.magic_wcell);
     }
+    S.bitpos[tid] = g_bitpos[tid];
     if (tid < 4) s_cnt[tid] = 0;
     if (tid < 64) s_has[tid] = 0;
     __syncthreads();
@@ -372,7 +385,7 @@ size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
     // tile + m map + cellOf + need + per-warp queues + corner list (u16 per pixel) + survivor staging (NMS keeps at most
     // ceil(h/2)*ceil(w/2) pixels of a tile)
     return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) +
-           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8) + 64;
+           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8 + 256) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
@@ -384,4 +397,15 @@ int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, i
     return TB_OK;
 }
 
-void tb_fast_init_device() { cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }
+void tb_fast_init_device()
+{
+    cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    uint32_t lut[256];
+    for (int m = 0; m < 256; m++) {
+        uint32_t v = 0;
+        int n = 0;
+        for (int b = 0; b < 8; b++) if (m & (1 << b)) v |= (uint32_t)b << (3 * n++);
+        lut[m] = v;
+    }
+    cudaMemcpyToSymbol(g_bitpos, lut, sizeof lut);
+}

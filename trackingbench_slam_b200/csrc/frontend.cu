@@ -412,7 +412,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
                 auto magic = [](int n) -> uint32_t { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; };
                 const int ox = 16 & 7, cs = ox + 3, ce = cs + a.scw;     // valid when (G*wCell) % 8 == 0; otherwise the kernel recomputes
                 const bool fixed = ((a.G * g.wCell) & 7) == 0;
-                a.magic_groups = fixed ? magic(((ce + 7) >> 3) - (cs >> 3)) : 0xFFFFFFFFu;
+                a.magic_groups = fixed ? magic(((ce + 15) >> 4) - (cs >> 4)) : 0xFFFFFFFFu;   // 16-pixel prefilter groups per tile row
                 a.magic_w8 = fixed ? magic((ox + a.scw + 6 + 7) >> 3) : 0xFFFFFFFFu;
                 a.magic_wcell = magic(g.wCell);
             }
