@@ -40,34 +40,47 @@ __device__ __forceinline__ int fast9_score_packed(const uint8_t *p, int tp)
     int r[16];
     RING_LOAD(p, tp);
     const uint32_t v = p[0];
-    const uint32_t C = (v | ((255u - v) << 16)) + 0x01000100u;
-    uint32_t P[25];
+    // P[k] = (v - ring + 256) | (ring - v + 256) << 16 as ONE multiply-add per ring pixel (FMA pipe; the kernel is bound by
+    // the half-rate integer ALU pipe): ring * 0xFFFF adds ring << 16 and subtracts ring from the low lane
+    const uint32_t C = (v | ((255u - v) << 16)) + 0x01000100u - 0x00FF0000u;
+    uint32_t P[18];
 #pragma unroll
-    for (int k = 0; k < 16; k++) P[k] = C - ((uint32_t)r[k] * 0xFFFF0001u + 0x00FF0000u);   // ring | (255-ring)<<16
+    for (int k = 0; k < 16; k++) P[k] = (uint32_t)r[k] * 0x0000FFFFu + C;
+    P[16] = P[0]; P[17] = P[1];
+    // minimum of every 9-arc = min3 of three overlapping triple minima; 16 + 16 + 8 three-input ops
+    uint32_t m3[16];
 #pragma unroll
-    for (int k = 16; k < 25; k++) P[k] = P[k - 16];
+    for (int k = 0; k < 16; k++) m3[k] = __vimin3_u16x2(P[k], P[k + 1], P[k + 2]);
     uint32_t best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const uint32_t a = __vimin3_u16x2(__vimin3_u16x2(P[k + 1], P[k + 2], P[k + 3]), __vimin3_u16x2(P[k + 4], P[k + 5], P[k + 6]),
-                                          __vminu2(P[k + 7], P[k + 8]));
-        best = __vimax3_u16x2(best, __vminu2(a, P[k]), __vminu2(a, P[k + 9]));
+        const uint32_t w0 = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const uint32_t w1 = __vimin3_u16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        best = __vimax3_u16x2(best, w0, w1);
     }
     return max((int)(best & 0xFFFFu), (int)(best >> 16)) - 256;
 }
 
 extern __shared__ __align__(16) uint8_t fast_smem[];
 
+// a + b issued as a multiply-add: the kernel is bound by the half-rate integer ALU pipe (LOP3 / VIMNMX / IADD), the FMA
+// pipe that executes IMAD is mostly idle
+__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 // |ring - centre| > T per byte, result in bit 7 of each byte (T <= 127; K = (127-T)*0x01010101)
 __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t c, uint32_t K)
 {
     const uint32_t ad = __vabsdiffu4(ring, c);
-    return ((ad & 0x7f7f7f7fu) + K) | ad;
+    return add_fma_pipe(ad & 0x7f7f7f7fu, K) | ad;
 }
 // ring > centre per byte (unsigned), result in bit 7; clow = centre & 0x7f7f7f7f
 __device__ __forceinline__ uint32_t byte_gt(uint32_t ring, uint32_t c, uint32_t clow)
 {
-    const uint32_t t = (ring | 0x80808080u) - clow;            // bit 7: low 7 bits of ring >= those of centre
+    const uint32_t t = add_fma_pipe(ring | 0x80808080u, 0u - clow);   // bit 7: low 7 bits of ring >= those of centre
     return (ring & ~c) | (~(ring ^ c) & t);                     // msb decides, else the low bits (ring != centre where used)
 }
 // compass test for one word of 4 centres: two ADJACENT compass pixels both brighter by > T or both darker by > T
