@@ -227,7 +227,7 @@ extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, 
             if ((rc = dev_alloc(fe, &fe->ytab[l], hy.size()))) break;
             cudaMemcpy(fe->xtab[l], hx.data(), hx.size() * sizeof(int4), cudaMemcpyHostToDevice);
             cudaMemcpy(fe->ytab[l], hy.data(), hy.size() * sizeof(int4), cudaMemcpyHostToDevice);
-            if (!fe->area2[l])
+            if (!fe->area2[l] && tb_resize_span_ok(tx, x1))
                 fe->has_tmap[l] = tb_resize_tensor_map(&fe->pyr_tmap[l], fe->pyr[l - 1], lw[l - 1], lh[l - 1], B, fe->g[l - 1].pitch,
                                                        fe->g[l - 1].frame_stride, fe->box_rows[l]);
         }

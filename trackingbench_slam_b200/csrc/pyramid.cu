@@ -175,13 +175,32 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
     }
     // this thread's 4 output columns: tap offsets inside a stage (left box, or right box at +box_bytes) and weights
     const int cx = threadIdx.x * 4;
-    uint32_t xo[4], xc[4];     // packed: tap offsets (16 bits each) and the two 11-bit weights
+    // The eight taps of a thread's 4 columns span at most 8 source bytes (checked by the launcher): per source row the thread
+    // loads the three aligned words that hold them, funnel-shifts them into an 8-byte window that starts at its first tap,
+    // and picks each column's tap pair with one PRMT. The 11-bit weights are split into low/high bytes so that
+    // a*c0 + b*c1 = DP4A(pair, lo bytes) + 256 * DP4A(pair, hi bytes): shared memory sees 3 word loads instead of 8 byte
+    // loads per row (the LSU data path, not the issue rate, bounds this kernel).
+    int woff[3];               // stage offsets of the three words
+    uint32_t sel[4], clo[4], chi[4];
+    int wsh;
+    {
+        int4 xt[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int4 xt = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]);
-        const int a = xt.x - sx_lo, b = xt.y - sx_lo;
-        xo[k] = (uint32_t)(a < PYR_BOXW ? a : box_bytes + a - PYR_BOXW) | ((uint32_t)(b < PYR_BOXW ? b : box_bytes + b - PYR_BOXW) << 16);
-        xc[k] = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+        for (int k = 0; k < 4; k++) xt[k] = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]);
+        const int o_first = xt[0].x - sx_lo;
+        wsh = 8 * (o_first & 3);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int x = min(4 * ((o_first >> 2) + j), 2 * PYR_BOXW - 4);
+            woff[j] = x < PYR_BOXW ? x : box_bytes + x - PYR_BOXW;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t ia = (uint32_t)(xt[k].x - sx_lo - o_first), ib = (uint32_t)(xt[k].y - sx_lo - o_first);
+            sel[k] = ia | (ib << 4) | (ia << 8) | (ib << 12);
+            clo[k] = ((uint32_t)xt[k].z & 0xFF) | (((uint32_t)xt[k].w & 0xFF) << 8);
+            chi[k] = ((uint32_t)xt[k].z >> 8) | (((uint32_t)xt[k].w >> 8) << 8);
+        }
     }
     // this thread's output rows (phase 2): table entries once per CTA
     const int dx0 = tx0 + cx;
@@ -200,10 +219,15 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
         const uint8_t *stage = boxes + (size_t)(2 * s) * box_bytes;
         for (int r = threadIdx.y; r < bh; r += 4) {
             const uint8_t *row = stage + r * PYR_BOXW;
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + woff[0]), w1 = *reinterpret_cast<const uint32_t *>(row + woff[1]),
+                           w2 = *reinterpret_cast<const uint32_t *>(row + woff[2]);
+            const uint32_t lo = __funnelshift_r(w0, w1, wsh), hi = __funnelshift_r(w1, w2, wsh);
             uint32_t h[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                h[k] = (uint32_t)((int)row[xo[k] & 0xFFFF] * (int)(xc[k] & 0xFFFF) + (int)row[xo[k] >> 16] * (int)(xc[k] >> 16)) >> 4;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t pair = __byte_perm(lo, hi, sel[k]);            // (a, b, a, b)
+                h[k] = (__dp4a(pair, clo[k], 0u) + (__dp4a(pair, chi[k], 0u) << 8)) >> 4;
+            }
             *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
         }
         __syncthreads();                                   // H complete, stage s drained
@@ -214,24 +238,24 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
         }
         // ---- phase 2: vertical pass, 4 columns x 8 rows per thread
         if (dx0 <= tx1) {
-            uint8_t *d = dst + (size_t)(f0 + f) * dframe;
+            const int dy0 = ty0 + threadIdx.y * (PYR_TH / 4);
+            uint8_t *dp = dst + (size_t)(f0 + f) * dframe + (size_t)dy0 * dpitch + dx0;   // advances by the pitch
+            const bool wordst = dx0 + 3 < dw;
 #pragma unroll
             for (int kk = 0; kk < PYR_TH / 4; kk++) {
-                const int dy = ty0 + threadIdx.y * (PYR_TH / 4) + kk;
-                if (dy > ty1) break;
+                if (dy0 + kk > ty1) break;
                 const uint2 a = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] & 0xFFFF) * PYR_TW + cx);
                 const uint2 b = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] >> 16) * PYR_TW + cx);
                 const int w0 = (int)(yc[kk] & 0xFFFF), w1 = (int)(yc[kk] >> 16);
                 const int h0[4] = {(int)(a.x & 0xFFFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16)};
                 const int h1[4] = {(int)(b.x & 0xFFFF), (int)(b.x >> 16), (int)(b.y & 0xFFFF), (int)(b.y >> 16)};
-                uint32_t out = 0;
+                uint32_t v[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int v = (((w0 * h0[k]) >> 16) + ((w1 * h1[k]) >> 16) + 2) >> 2;
-                    out |= (uint32_t)(v & 0xFF) << (8 * k);
-                }
-                if (dx0 + 3 < dw) *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
-                else for (int k = 0; k < 4 && dx0 + k < dw; k++) d[(size_t)dy * dpitch + dx0 + k] = (uint8_t)(out >> (8 * k));
+                for (int k = 0; k < 4; k++) v[k] = (uint32_t)((((w0 * h0[k]) >> 16) + ((w1 * h1[k]) >> 16) + 2) >> 2);   // <= 255
+                const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                if (wordst) *reinterpret_cast<uint32_t *>(dp) = out;
+                else for (int k = 0; k < 4 && dx0 + k < dw; k++) dp[k] = (uint8_t)(out >> (8 * k));
+                dp += dpitch;
             }
         }
         __syncthreads();                                   // H free for the next frame
@@ -248,6 +272,17 @@ void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> 
     for (int a = 0; a < dh; a += PYR_TH) { int b = std::min(a + PYR_TH, dh) - 1; mh = std::max(mh, y1[b] - ty[a].ofs + 1); }
     *bp = ((mw + 15) & ~15) + 16;
     *bh = mh;
+}
+
+// Host: the TMA kernel needs the 8 taps of every thread's 4 adjacent output columns inside 8 source bytes.
+bool tb_resize_span_ok(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1)
+{
+    const int dw = (int)tx.size();
+    for (int c = 0; c < dw; c += 4) {
+        const int last = std::min(c + 3, dw - 1);
+        for (int k = c; k <= last; k++) if (tx[k].ofs < tx[c].ofs || x1[k] - tx[c].ofs > 7) return false;
+    }
+    return true;
 }
 
 // Exact 2x: OpenCV switches INTER_LINEAR to INTER_AREA (2x2 mean with rounding).
