@@ -148,13 +148,13 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 //      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
 //   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map
 //   5  NMS inside the cell interior, emission with one global atomic per pass
-__device__ uint32_t g_bitpos[256];   // set-bit positions of a byte (3 bits each, lowest first), filled by tb_fast_init_device
+__device__ uint2 g_bitpos[256];   // set-bit positions of a byte (one byte each, lowest first), filled by tb_fast_init_device
 #define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
 struct FastSmem {
     uint8_t *tile, *sc, *cellOf, *need;
     uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (capacity = all pixels)
     uint32_t *stage;           // NMS survivors staged for the single global reservation (<= cap/4 + 1 entries)
-    uint32_t *bitpos;          // [256] positions of the set bits of a byte, 3 bits each, lowest first
+    uint2 *bitpos;             // [256] positions of the set bits of a byte, one byte each, lowest first
 };
 
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
@@ -227,13 +227,19 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
                 uint16_t *qp = q + qn + inc - cnt;
                 const uint32_t lo = m16 & 0xFF, hi = m16 >> 8;
-                const uint32_t tl = S.bitpos[lo], th = S.bitpos[hi];
-                const int nl = __popc(lo);
+                const uint2 tl = S.bitpos[lo], th = S.bitpos[hi];     // eight byte-wide positions each
+                const int nl = __popc(lo), nh = cnt - nl;
+                const uint32_t e8 = (uint32_t)(e0 + 8);
+                // PRMT pulls position j out zero-extended, the add rides the FMA pipe (the integer ALU pipe is the bottleneck)
 #pragma unroll
-                for (int j = 0; j < 8; j++) if (j < nl) qp[j] = (uint16_t)(e0 + ((tl >> (3 * j)) & 7));
+                for (int j = 0; j < 4; j++) if (j < nl) qp[j] = (uint16_t)add_fma_pipe(__byte_perm(tl.x, 0u, 0x4440 + j), (uint32_t)e0);
+#pragma unroll
+                for (int j = 4; j < 8; j++) if (j < nl) qp[j] = (uint16_t)add_fma_pipe(__byte_perm(tl.y, 0u, 0x4440 + j - 4), (uint32_t)e0);
                 qp += nl;
 #pragma unroll
-                for (int j = 0; j < 8; j++) if (j < cnt - nl) qp[j] = (uint16_t)(e0 + 8 + ((th >> (3 * j)) & 7));
+                for (int j = 0; j < 4; j++) if (j < nh) qp[j] = (uint16_t)add_fma_pipe(__byte_perm(th.x, 0u, 0x4440 + j), e8);
+#pragma unroll
+                for (int j = 4; j < 8; j++) if (j < nh) qp[j] = (uint16_t)add_fma_pipe(__byte_perm(th.y, 0u, 0x4440 + j - 4), e8);
             }
             qn += total;
             __syncwarp();
@@ -259,21 +265,15 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             const int m = sc[rr * a.scw + cc];
             const int cell = S.cellOf[cc];
             const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
-            keep = true;
-#pragma unroll
-            for (int dr = -1; dr <= 1; dr++) {
-                const int r2 = rr + dr;
-                if (r2 < 0 || r2 >= hEff) continue;
-#pragma unroll
-                for (int dc = -1; dc <= 1; dc++) {
-                    if (!dr && !dc) continue;
-                    const int c2 = cc + dc;
-                    if (c2 < cl || c2 >= chi) continue;
-                    const int m2 = sc[r2 * a.scw + c2];
-                    // scores are m-1, non-corners hold 0 in OpenCV's buffer: keep iff m-1 > max(m2-1, 0)
-                    if (!(m - 1 > max(m2 - 1, 0))) keep = false;
-                }
-            }
+            // OpenCV's buffer holds m-1 for corners and 0 elsewhere: keep iff m-1 > max(m2-1, 0) for every neighbour inside the
+            // cell's ROI interior, i.e. m > (largest in-range neighbour) and, if there is any neighbour, m > 1
+            const bool up = rr > 0, dn = rr + 1 < hEff, lf = cc > cl, rt = cc + 1 < chi;
+            const uint8_t *q = sc + rr * a.scw + cc;
+            const int n0 = (up && lf) ? q[-a.scw - 1] : 0, n1 = up ? q[-a.scw] : 0, n2 = (up && rt) ? q[-a.scw + 1] : 0;
+            const int n3 = lf ? q[-1] : 0, n4 = rt ? q[1] : 0;
+            const int n5 = (dn && lf) ? q[a.scw - 1] : 0, n6 = dn ? q[a.scw] : 0, n7 = (dn && rt) ? q[a.scw + 1] : 0;
+            const int mx = max3i(max3i(n0, n1, n2), max3i(n3, n4, n5), max(n6, n7));
+            keep = m > mx && (m > 1 || !(up || dn || lf || rt));
             if (keep) {
                 s_has[cell] = 1;
                 // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
@@ -324,7 +324,7 @@ fast9_cells(FastArgs a)
     S.queue = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
     S.listB = S.queue + 8 * FAST_QCAP;
     S.stage = reinterpret_cast<uint32_t *>(S.listB + ((cap + 7) & ~7));
-    S.bitpos = S.stage + (((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8);
+    S.bitpos = reinterpret_cast<uint2 *>(S.stage + ((((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8 + 1) & ~1));
     __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
     __shared__ int s_has[64];
 
@@ -398,7 +398,7 @@ size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
     // tile + m map + cellOf + need + per-warp queues + corner list (u16 per pixel) + survivor staging (NMS keeps at most
     // ceil(h/2)*ceil(w/2) pixels of a tile)
     return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) +
-           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8 + 256) + 64;
+           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8 + 2 + 512) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
@@ -413,12 +413,12 @@ int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, i
 void tb_fast_init_device()
 {
     cudaFuncSetAttribute(fast9_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    uint32_t lut[256];
+    uint2 lut[256];
     for (int m = 0; m < 256; m++) {
-        uint32_t v = 0;
+        unsigned long long v = 0;
         int n = 0;
-        for (int b = 0; b < 8; b++) if (m & (1 << b)) v |= (uint32_t)b << (3 * n++);
-        lut[m] = v;
+        for (int b = 0; b < 8; b++) if (m & (1 << b)) v |= (unsigned long long)b << (8 * n++);
+        lut[m] = make_uint2((unsigned)(v & 0xFFFFFFFFu), (unsigned)(v >> 32));
     }
     cudaMemcpyToSymbol(g_bitpos, lut, sizeof lut);
 }
