@@ -231,70 +231,95 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * a.steps / (ms / 1000.0)
 
-    # end to end through the C ABI with HOST buffers: every step uploads its frames from pinned memory,
-    # runs the path and reads keypoints/descriptors/matches back.  Two ctx/frontend slots alternate so
-    # that the copies of one step overlap the kernels of the other (still one upload + one readback per
-    # step, all inside the timed region).
-    slots = []
-    for k in range(2):
+    # end to end through the C ABI with HOST buffers: every step uploads its frames from pinned memory, runs the path
+    # and reads keypoints/descriptors/matches back, all inside the timed region.  NSLOT ctx/stream/frontend sets rotate
+    # between steps so that the upload of one step (the PCIe link is the end-to-end bound: 531 MB per step at the
+    # measured 55.6 GB/s takes 9.55 ms, as long as the kernels) overlaps the kernels of the previous one.  The timed
+    # region starts with an empty pipeline, so K steps cost about K uploads + one step of kernels + one readback.
+    # TB_E2E_CHUNKS > 1 additionally splits a step into chunks of the batch (each chunk carries the first frame of the
+    # next one as its last frame so the k <-> k+1 matches across the boundary are still produced); measured slower
+    # (smaller launches are less efficient: 64-frame batches cost +15 % kernel time), so the default is 1.
+    NCH = max(1, min(int(os.environ.get('TB_E2E_CHUNKS', '1')), B // 16))
+    NSLOT = int(os.environ.get('TB_E2E_SLOTS', '3'))
+    bounds = [(c * B // NCH, (c + 1) * B // NCH) for c in range(NCH)]
+    chunk_slots = []
+    for k in range(NSLOT * NCH):
+        c = k % NCH
+        f_lo, f_hi = bounds[c]
+        n_out = f_hi - f_lo                                   # frames whose results this chunk reports
+        n_in = n_out + (1 if c < NCH - 1 else 0)              # + the next chunk's first frame (match partner)
+        n_pairs = n_in - 1
         st = torch.cuda.Stream()
         c2 = tb.Context(local_rank, st.cuda_stream)
         c2.set_match_impl(1 if a.match_impl == 'tc' else 0)
-        f2 = tb.Frontend(c2, lw, lh, max_batch=B, max_target=tgt)
-        slots.append(dict(stream=st, ctx=c2, fe=f2,
-                          matches=torch.zeros((max(P, 1), cap, 4), dtype=torch.int32, device='cuda'),
-                          mcounts=torch.zeros(max(P, 1), dtype=torch.int32, device='cuda'),
-                          h_kps=torch.empty((B, cap, 7), dtype=torch.float32, pin_memory=True),
-                          h_desc=torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True),
-                          h_counts=torch.empty(B, dtype=torch.int32, pin_memory=True),
-                          h_matches=torch.empty((max(P, 1), cap, 4), dtype=torch.int32, pin_memory=True),
-                          h_mcounts=torch.empty(max(P, 1), dtype=torch.int32, pin_memory=True)))
+        f2 = tb.Frontend(c2, lw, lh, max_batch=n_in, max_target=tgt)
+        chunk_slots.append(dict(stream=st, ctx=c2, fe=f2, f_lo=f_lo, n_in=n_in, n_out=n_out, n_pairs=n_pairs,
+                                qf=np.arange(0, n_pairs, dtype=np.int32), tf=np.arange(1, n_pairs + 1, dtype=np.int32),
+                                matches=torch.zeros((max(n_pairs, 1), cap, 4), dtype=torch.int32, device='cuda'),
+                                mcounts=torch.zeros(max(n_pairs, 1), dtype=torch.int32, device='cuda'),
+                                h_kps=torch.empty((n_out, cap, 7), dtype=torch.float32, pin_memory=True),
+                                h_desc=torch.empty((n_out, cap, 32), dtype=torch.uint8, pin_memory=True),
+                                h_counts=torch.empty(n_out, dtype=torch.int32, pin_memory=True),
+                                h_matches=torch.empty((max(n_pairs, 1), cap, 4), dtype=torch.int32, pin_memory=True),
+                                h_mcounts=torch.empty(max(n_pairs, 1), dtype=torch.int32, pin_memory=True)))
 
     compute_done = [None]
 
-    def step_e2e(s):
+    def chunk_e2e(s):
         fe2 = s['fe']
-        fe2.upload_frames_ptr(0, B, host.data_ptr(), W)
-        # kernels of consecutive steps run back to back (not interleaved), so that this step's upload
-        # overlaps the previous step's kernels and the next step's upload overlaps these
+        fe2.upload_frames_ptr(0, s['n_in'], host.data_ptr() + s['f_lo'] * W * H, W)
+        # kernels of consecutive chunks run back to back (not interleaved), so that this chunk's upload
+        # overlaps the previous chunk's kernels and the next chunk's upload overlaps these
         if compute_done[0] is not None:
             s['stream'].wait_event(compute_done[0])
-        fe2.build_pyramid(B)
-        fe2.extract(B, sf, tgt, PSET['initTh'], PSET['minTh'])
-        if P > 0:
-            fe2.search_by_bf(qf, tf, PSET['ratio'], PSET['match_minTh'], s['matches'].data_ptr(), cap, s['mcounts'].data_ptr())
+        fe2.build_pyramid(s['n_in'])
+        fe2.extract(s['n_in'], sf, tgt, PSET['initTh'], PSET['minTh'])
+        if s['n_pairs'] > 0:
+            fe2.search_by_bf(s['qf'], s['tf'], PSET['ratio'], PSET['match_minTh'], s['matches'].data_ptr(), cap, s['mcounts'].data_ptr())
         ev = torch.cuda.Event()
         ev.record(s['stream'])
         compute_done[0] = ev
-        fe2.get_results_batch_async(B, s['h_kps'].numpy().view(tb.KP_DTYPE).reshape(B, cap), s['h_desc'].numpy(), s['h_counts'].numpy())
+        fe2.get_results_batch_async(s['n_out'], s['h_kps'].numpy().view(tb.KP_DTYPE).reshape(s['n_out'], cap), s['h_desc'].numpy(),
+                                    s['h_counts'].numpy())
         with torch.cuda.stream(s['stream']):
             s['h_matches'].copy_(s['matches'], non_blocking=True)
             s['h_mcounts'].copy_(s['mcounts'], non_blocking=True)
 
-    for s in slots:
-        step_e2e(s)
-    for s in slots:
+    def step_e2e(i, reuse):
+        for c in range(NCH):
+            s = chunk_slots[(i % NSLOT) * NCH + c]
+            if reuse:
+                s['fe'].status()      # the slot's previous results are complete (and read) before it is reused
+            chunk_e2e(s)
+
+    for i in range(NSLOT):
+        step_e2e(i, False)
+    for s in chunk_slots:
         s['fe'].status()
     barrier()
     t0 = time.perf_counter()
     for i in range(a.steps):
-        s = slots[i % 2]
-        if i >= 2:
-            s['fe'].status()          # the slot's previous results are complete (and read) before it is reused
-        step_e2e(s)
-    for s in slots:
+        step_e2e(i, i >= NSLOT)
+    for s in chunk_slots:
         s['fe'].status()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
     e2e_value = B * world * a.steps / (e2e_ms / 1000.0)
-    h2d = B * W * H
-    d2h = B * (cap * (28 + 32) + 4) + max(P, 1) * (cap * 16 + 4)
-    counts = slots[0]['h_counts'].numpy().copy()
-    n_matches = int(slots[0]['h_mcounts'].numpy()[:P].sum()) if P > 0 else 0
+    h2d = sum(s['n_in'] for s in chunk_slots[:NCH]) * W * H
+    d2h = sum(s['n_out'] * (cap * (28 + 32) + 4) + max(s['n_pairs'], 1) * (cap * 16 + 4) for s in chunk_slots[:NCH])
+    li = ((a.steps - 1) % NSLOT) * NCH if a.steps > 0 else 0
+    last = chunk_slots[li:li + NCH]
+    counts = np.concatenate([s['h_counts'].numpy() for s in last])
+    n_matches = int(sum(int(s['h_mcounts'].numpy()[:s['n_pairs']].sum()) for s in last)) if P > 0 else 0
     # the pipelined results are the same bytes as the device-resident run's
     fe.get_results_batch(B, h_kps.numpy().view(tb.KP_DTYPE).reshape(B, cap), h_desc.numpy(), h_counts.numpy())
-    assert np.array_equal(h_counts.numpy(), counts) and np.array_equal(h_desc.numpy(), slots[0]['h_desc'].numpy())
-    for s in slots:
+    h_mcounts.copy_(mcounts)
+    torch.cuda.synchronize()
+    assert np.array_equal(h_counts.numpy(), counts)
+    assert np.array_equal(h_desc.numpy(), np.concatenate([s['h_desc'].numpy() for s in last]))
+    if P > 0:
+        assert np.array_equal(h_mcounts.numpy()[:P], np.concatenate([s['h_mcounts'].numpy()[:s['n_pairs']] for s in last]))
+    for s in chunk_slots:
         s['fe'].close()
         s['ctx'].close()
 
@@ -350,7 +375,8 @@ def run_ours(a):
                 'config': {'workload': workload_name(a), 'levels': 8, 'scale': 1.2, 'fast_th': [20, 7], 'frames_per_gpu': B,
                            'sharding': 'frame streams, %d rank(s), no collective' % world,
                            'l2': 'inputs (%.0f MB of frames per step) exceed the 126 MB L2' % (B * W * H / 1e6),
-                           'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches, 'match_impl': a.match_impl},
+                           'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches, 'match_impl': a.match_impl,
+                           'e2e_pipeline': '%d chunk(s) per step x %d rotating slots; bound: PCIe upload of the frames' % (NCH, NSLOT)},
                 'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'hamming': hamming,
                 'per_kernel_ms': {k: round(v['ms'], 3) for k, v in table.items()}}
