@@ -384,7 +384,10 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
     //          behind FAST of the following levels
     // (With per-kernel profiling on, everything stays on the main stream so the event pairs stay meaningful.)
     const bool overlap = !ctx->profiling;
-    cudaStream_t gs = overlap ? ctx->side : ctx->stream, os = overlap ? ctx->side2 : ctx->stream;
+    // per-level octree launches only pay when FAST of the next level is long enough to hide them; for small batches (the
+    // single-frame host entries) one launch with all levels side by side has the lower latency
+    const bool per_level = overlap && n_frames >= 32;
+    cudaStream_t gs = overlap ? ctx->side : ctx->stream, os = per_level ? ctx->side2 : ctx->stream;
     if (overlap) {
         TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
         TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
@@ -432,20 +435,25 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
         o.kept = fe->kept[l]; o.kept_cap = fe->kept_cap; o.n_kept = fe->n_kept + l; o.overflow = fe->overflow;
         o.node_cap = fe->budget[l] + 4 * (g.nIni > 0 ? g.nIni : 1) + 8;
         if (fe->budget[l] > max_budget) max_budget = fe->budget[l];
-        if (overlap) {
+        if (per_level) {
             TB_CUDA(ctx, cudaEventRecord(ctx->ev_lvl[l], ctx->stream));
             TB_CUDA(ctx, cudaStreamWaitEvent(os, ctx->ev_lvl[l], 0));
             int rc = tb_launch_octree(ctx, &oct[l], 1, n_frames, os);
             if (rc) return rc;
         }
     }
-    if (overlap) {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev_join2, os));
-        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
-    } else {
+    if (!per_level) {
         int rc = tb_launch_octree(ctx, oct, L, n_frames, ctx->stream);
         if (rc) return rc;
+    }
+    if (overlap) {
+        if (per_level) {
+            TB_CUDA(ctx, cudaEventRecord(ctx->ev_join2, os));
+            TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+        }
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    } else {
+        int rc = TB_OK;
         for (int l = 0; l < L; l++) {
             const LevelGeom &g = fe->g[l];
             rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
