@@ -6,6 +6,7 @@
 //   keypoint finishing (border offset, octave, size, pt *= sf)        :812-822, :969-977
 #include "common.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------------------------------
 // K5: cv::GaussianBlur 7x7 sigma=2 on 8U = OpenCV's fixed-point kernel {18,34,48,56,48,34,18}/256:
@@ -53,21 +54,29 @@ __device__ __forceinline__ uint32_t gauss_vcol(const uint32_t (&win)[7][4])
     return __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
 }
 
+// Border word columns (the first one and the last one or two of a row): each of their three input words is 4 reflected
+// pixels that lie inside two adjacent aligned words of the row, so it is one PRMT of two aligned loads; word offsets and
+// selectors are computed on the host per level (BORDER_REFLECT_101 in x without byte gathers).
+struct GaussEdge {
+    int wofs[4][3];       // [border column][wm, w0, wp]: index of the first aligned word
+    uint32_t sel[4][3];   // PRMT selector over (word, word + 1)
+};
+
 // A thread owns one 4-pixel word column and a strip of ROWS output rows.
 // BORDER = false: word columns whose 12-byte neighbourhood lies inside the row.
 //  * fast path (a full strip with its 3+3 halo rows inside the image — almost every thread): plain 4-byte loads through
 //    a row pointer that advances by the pitch, no reflection, no per-row index arithmetic; the 7-row chunks are peeled so
 //    that no row needs an "is an output ready" test;
 //  * general path (first and last strips): per-row REFLECT_101.
-// BORDER = true : the first word column and the last ones (per-byte reflected gather) in short strips so that these slow
-//    threads are many and short-lived; a tiny second launch. (Folding them into the main launch, with byte gathers or
-//    with host-made PRMT selectors, was measured slower: 2.98 / 1.88 ms vs 1.40 ms per step.)
+// BORDER = true : the first word column and the last ones, reflected through the GaussEdge selectors, in a small second
+//    launch. (Folding them into the main launch, with byte gathers or with the selectors, was measured slower: 2.98 /
+//    1.88 ms vs 1.40 ms per step; byte gathers in 8-row strips cost 0.35 ms per step, a quarter of the Gaussian.)
 template <bool BORDER, int ROWS>
 __global__ void __launch_bounds__(128, 8)
 gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride,
-            int xw_lo, int xw_hi)   // interior word columns are [xw_lo, xw_hi); the border launch takes the rest
+            int xw_lo, int xw_hi, const GaussEdge edge)   // interior word columns are [xw_lo, xw_hi); the border launch takes the rest
 {
-    int xw;
+    int xw, bi = 0;
     int ystrip = blockIdx.y;
     if (!BORDER) {
         xw = xw_lo + blockIdx.x * 128 + threadIdx.x;
@@ -79,6 +88,13 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
         ystrip = blockIdx.y * 16 + (threadIdx.x >> 3);
         if (i >= nb || ystrip * ROWS >= h) return;
         xw = i < xw_lo ? i : xw_hi + (i - xw_lo);
+        bi = i;
+    }
+    int eo[3] = {0, 0, 0};
+    uint32_t es[3] = {0, 0, 0};
+    if (BORDER) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) { eo[t] = edge.wofs[bi][t]; es[t] = edge.sel[bi][t]; }
     }
     const int y0 = ystrip * ROWS;
     const int ny = min(ROWS, h - y0);
@@ -134,13 +150,10 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
                 const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
                 in[k].wm = __ldg(p - 1); in[k].w0 = __ldg(p); in[k].wp = __ldg(p + 1);
             } else {
-                in[k].wm = in[k].w0 = in[k].wp = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    in[k].wm |= (uint32_t)row[reflect101(x - 4 + b, w)] << (8 * b);
-                    in[k].w0 |= (uint32_t)row[reflect101(x + b, w)] << (8 * b);
-                    in[k].wp |= (uint32_t)row[reflect101(x + 4 + b, w)] << (8 * b);
-                }
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(row);
+                in[k].wm = __byte_perm(__ldg(p + eo[0]), __ldg(p + eo[0] + 1), es[0]);
+                in[k].w0 = __byte_perm(__ldg(p + eo[1]), __ldg(p + eo[1] + 1), es[1]);
+                in[k].wp = __byte_perm(__ldg(p + eo[2]), __ldg(p + eo[2] + 1), es[2]);
             }
         }
 #pragma unroll
@@ -165,6 +178,49 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
     }
 }
 
+// Border word columns, one warp per (border column, strip of GB_BROWS output rows): lane = input row (3 halo rows on
+// either side), so every lane issues its six word loads at once (one memory round trip per warp), does the horizontal
+// pass of its row and fetches the six neighbouring rows' sums with shuffles for the vertical pass. The per-thread
+// 64-row walk of the main kernel is latency bound on so few columns (it took a quarter of the Gaussian's time).
+#define GB_BROWS 26    // 32 lanes = 26 output rows + 3 + 3 halo rows
+__global__ void __launch_bounds__(128)
+gauss7x7_border(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride,
+                int xw_lo, int xw_hi, int nb, int nstrips, const GaussEdge edge)
+{
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x * 4 + (threadIdx.x >> 5);        // (strip, border column)
+    if (job >= nstrips * nb) return;
+    const int bi = job % nb, strip = job / nb;
+    const int xw = bi < xw_lo ? bi : xw_hi + (bi - xw_lo);
+    const int x = 4 * xw, y0 = strip * GB_BROWS;
+    int yy = y0 - 3 + lane;                                      // BORDER_REFLECT_101 in y (h >= 4 guaranteed by the launcher)
+    yy = yy < 0 ? -yy : yy;
+    yy = yy >= h ? 2 * (h - 1) - yy : yy;
+    yy = min(max(yy, 0), h - 1);                                 // lanes past the last needed halo row: any valid row
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * frame_stride + (size_t)yy * pitch);
+    W3 in;
+    in.wm = __byte_perm(__ldg(p + edge.wofs[bi][0]), __ldg(p + edge.wofs[bi][0] + 1), edge.sel[bi][0]);
+    in.w0 = __byte_perm(__ldg(p + edge.wofs[bi][1]), __ldg(p + edge.wofs[bi][1] + 1), edge.sel[bi][1]);
+    in.wp = __byte_perm(__ldg(p + edge.wofs[bi][2]), __ldg(p + edge.wofs[bi][2] + 1), edge.sel[bi][2]);
+    uint32_t hh[4];
+    gauss_hrow(in, hh);
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t a3 = __shfl_sync(0xffffffffu, hh[j], (lane + 29) & 31), b3 = __shfl_sync(0xffffffffu, hh[j], (lane + 3) & 31);
+        const uint32_t a2 = __shfl_sync(0xffffffffu, hh[j], (lane + 30) & 31), b2 = __shfl_sync(0xffffffffu, hh[j], (lane + 2) & 31);
+        const uint32_t a1 = __shfl_sync(0xffffffffu, hh[j], (lane + 31) & 31), b1 = __shfl_sync(0xffffffffu, hh[j], (lane + 1) & 31);
+        const uint32_t v = 18u * (a3 + b3) + 34u * (a2 + b2) + 48u * (a1 + b1) + 56u * hh[j];
+        out |= ((v + 32768u) >> 16) << (8 * j);
+    }
+    const int y = y0 + lane - 3;
+    if (lane >= 3 && lane < 3 + GB_BROWS && y < h) {
+        uint8_t *d = dst + (size_t)blockIdx.z * frame_stride + (size_t)y * pitch + x;
+        if (x + 3 < w) *reinterpret_cast<uint32_t *>(d) = out;
+        else for (int j = 0; j < 4 && x + j < w; j++) d[j] = (uint8_t)(out >> (8 * j));
+    }
+}
+
 // Images with fewer than 4 rows (never a pyramid level in practice): generic per-pixel version.
 __global__ void gauss7x7_u8_tiny(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride)
 {
@@ -184,25 +240,48 @@ __global__ void gauss7x7_u8_tiny(const uint8_t *__restrict__ src, uint8_t *__res
 
 int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_t *dst, int w, int h, int pitch, size_t frame_stride, int n_frames)
 {
-    ProfScope prof__(ctx, "gauss7x7_u8");
     if (h < 4 || w < 16) {
+        ProfScope prof__(ctx, "gauss7x7_u8");
         dim3 grid(div_up(w, 128), h, n_frames);
         gauss7x7_u8_tiny<<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride);
         TB_LAUNCH_CHECK(ctx);
         return TB_OK;
     }
-    // interior word columns: 4*xw >= 4 and 4*xw + 8 <= w
+    // interior word columns: 4*xw >= 4 and 4*xw + 8 <= w; the others (at most 4) get their words through GaussEdge
     const int nwords = (w + 3) >> 2, xw_lo = 1, xw_hi = (w - 8) / 4 + 1;
+    GaussEdge edge;
+    memset(&edge, 0, sizeof edge);
+    const int nb = xw_lo + (nwords - xw_hi);
+    if (nb > 4) return tb_fail(ctx, TB_E_UNSUPPORTED, "gauss: unexpected border layout");
+    for (int bi = 0; bi < nb; bi++) {
+        const int xw = bi < xw_lo ? bi : xw_hi + (bi - xw_lo);
+        for (int t = 0; t < 3; t++) {
+            int px[4], lo = 1 << 30;
+            for (int b = 0; b < 4; b++) {
+                int q = 4 * (xw + t - 1) + b;                 // BORDER_REFLECT_101 in x
+                while (q < 0 || q >= w) q = q < 0 ? -q : 2 * (w - 1) - q;
+                px[b] = q; lo = std::min(lo, q);
+            }
+            const int wa = lo >> 2;
+            uint32_t sel = 0;
+            for (int b = 0; b < 4; b++) {
+                if (px[b] - 4 * wa > 7) return tb_fail(ctx, TB_E_UNSUPPORTED, "gauss: reflected word spans more than two words");
+                sel |= (uint32_t)(px[b] - 4 * wa) << (4 * b);
+            }
+            edge.wofs[bi][t] = wa; edge.sel[bi][t] = sel;
+        }
+    }
     {
+        ProfScope prof_i__(ctx, "gauss7x7_u8");
         dim3 grid(div_up(xw_hi - xw_lo, 128), div_up(h, GB_ROWS), n_frames);
-        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi, edge);
         TB_LAUNCH_CHECK(ctx);
     }
     {
-        const int nb = xw_lo + (nwords - xw_hi);   // <= 4 (< 8) border word columns
-        (void)nb;
-        dim3 grid(1, div_up(div_up(h, 8), 16), n_frames);   // 8-row strips, 16 strips x 8 column slots per CTA
-        gauss7x7_u8<true, 8><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
+        ProfScope prof_b__(ctx, "gauss7x7_border");
+        const int nstrips = div_up(h, GB_BROWS);
+        gauss7x7_border<<<dim3(div_up(nstrips * nb, 4), 1, n_frames), 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi, nb,
+                                                                                          nstrips, edge);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
