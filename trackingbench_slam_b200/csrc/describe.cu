@@ -62,47 +62,29 @@ struct GaussEdge {
     uint32_t sel[4][3];   // PRMT selector over (word, word + 1)
 };
 
-// A thread owns one 4-pixel word column and a strip of ROWS output rows.
-// BORDER = false: word columns whose 12-byte neighbourhood lies inside the row.
+// Interior word columns (their 12-byte neighbourhood lies inside the row): a thread owns one 4-pixel word column and a
+// strip of ROWS output rows.
 //  * fast path (a full strip with its 3+3 halo rows inside the image — almost every thread): plain 4-byte loads through
 //    a row pointer that advances by the pitch, no reflection, no per-row index arithmetic; the 7-row chunks are peeled so
 //    that no row needs an "is an output ready" test;
 //  * general path (first and last strips): per-row REFLECT_101.
-// BORDER = true : the first word column and the last ones, reflected through the GaussEdge selectors, in a small second
-//    launch. (Folding them into the main launch, with byte gathers or with the selectors, was measured slower: 2.98 /
-//    1.88 ms vs 1.40 ms per step; byte gathers in 8-row strips cost 0.35 ms per step, a quarter of the Gaussian.)
-template <bool BORDER, int ROWS>
+// The first word column and the last ones are done by gauss7x7_border below. (Folding them into this launch, with byte
+// gathers or with PRMT selectors, was measured slower: 2.98 / 1.88 ms vs 1.40 ms per step — a few slow threads stretch
+// every CTA that holds them.)
+template <int ROWS>
 __global__ void __launch_bounds__(128, 8)
 gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h, int pitch, size_t frame_stride,
-            int xw_lo, int xw_hi, const GaussEdge edge)   // interior word columns are [xw_lo, xw_hi); the border launch takes the rest
+            int xw_lo, int xw_hi)   // interior word columns are [xw_lo, xw_hi)
 {
-    int xw, bi = 0;
-    int ystrip = blockIdx.y;
-    if (!BORDER) {
-        xw = xw_lo + blockIdx.x * 128 + threadIdx.x;
-        if (xw >= xw_hi) return;
-    } else {
-        // few columns, many short row strips: thread = (strip within the CTA, border column)
-        const int nwords = (w + 3) >> 2, nb = xw_lo + (nwords - xw_hi);   // border columns: [0,xw_lo) and [xw_hi,nwords)
-        const int i = threadIdx.x & 7;
-        ystrip = blockIdx.y * 16 + (threadIdx.x >> 3);
-        if (i >= nb || ystrip * ROWS >= h) return;
-        xw = i < xw_lo ? i : xw_hi + (i - xw_lo);
-        bi = i;
-    }
-    int eo[3] = {0, 0, 0};
-    uint32_t es[3] = {0, 0, 0};
-    if (BORDER) {
-#pragma unroll
-        for (int t = 0; t < 3; t++) { eo[t] = edge.wofs[bi][t]; es[t] = edge.sel[bi][t]; }
-    }
-    const int y0 = ystrip * ROWS;
+    const int xw = xw_lo + blockIdx.x * 128 + threadIdx.x;
+    if (xw >= xw_hi) return;
+    const int y0 = blockIdx.y * ROWS;
     const int ny = min(ROWS, h - y0);
     const uint8_t *s = src + (size_t)blockIdx.z * frame_stride;
     uint8_t *d = dst + (size_t)blockIdx.z * frame_stride;
     const int x = 4 * xw;
     uint32_t win[7][4];
-    if (!BORDER && (ROWS + 6) % 7 == 0 && y0 >= 3 && y0 + ROWS + 3 <= h) {
+    if ((ROWS + 6) % 7 == 0 && y0 >= 3 && y0 + ROWS + 3 <= h) {
         const uint8_t *sp = s + (size_t)(y0 - 3) * pitch + x;
         uint8_t *dp = d + (size_t)y0 * pitch + x;
         {   // first chunk: rows y0-3 .. y0+3 fill the window, one output
@@ -145,16 +127,8 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
             int yy = y0 - 3 + min(base + k, ny + 5);
             yy = yy < 0 ? -yy : yy;                      // REFLECT_101 (h >= 4 guaranteed by the launcher)
             yy = yy >= h ? 2 * (h - 1) - yy : yy;
-            const uint8_t *row = s + (size_t)yy * pitch;
-            if (!BORDER) {
-                const uint32_t *p = reinterpret_cast<const uint32_t *>(row + x);
-                in[k].wm = __ldg(p - 1); in[k].w0 = __ldg(p); in[k].wp = __ldg(p + 1);
-            } else {
-                const uint32_t *p = reinterpret_cast<const uint32_t *>(row);
-                in[k].wm = __byte_perm(__ldg(p + eo[0]), __ldg(p + eo[0] + 1), es[0]);
-                in[k].w0 = __byte_perm(__ldg(p + eo[1]), __ldg(p + eo[1] + 1), es[1]);
-                in[k].wp = __byte_perm(__ldg(p + eo[2]), __ldg(p + eo[2] + 1), es[2]);
-            }
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(s + (size_t)yy * pitch + x);
+            in[k].wm = __ldg(p - 1); in[k].w0 = __ldg(p); in[k].wp = __ldg(p + 1);
         }
 #pragma unroll
         for (int k = 0; k < 7; k++) {
@@ -169,9 +143,7 @@ gauss7x7_u8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, i
                                            48u * (win[(k + 3) % 7][j] + win[(k + 5) % 7][j]) + 56u * win[(k + 4) % 7][j];
                         out |= ((v + 32768u) >> 16) << (8 * j);
                     }
-                    const int y = y0 + r - 6;
-                    if (!BORDER || x + 3 < w) *reinterpret_cast<uint32_t *>(d + (size_t)y * pitch + x) = out;
-                    else for (int j = 0; j < 4 && x + j < w; j++) d[(size_t)y * pitch + x + j] = (uint8_t)(out >> (8 * j));
+                    *reinterpret_cast<uint32_t *>(d + (size_t)(y0 + r - 6) * pitch + x) = out;
                 }
             }
         }
@@ -274,7 +246,7 @@ int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_
     {
         ProfScope prof_i__(ctx, "gauss7x7_u8");
         dim3 grid(div_up(xw_hi - xw_lo, 128), div_up(h, GB_ROWS), n_frames);
-        gauss7x7_u8<false, GB_ROWS><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi, edge);
+        gauss7x7_u8<GB_ROWS><<<grid, 128, 0, stream>>>(src, dst, w, h, pitch, frame_stride, xw_lo, xw_hi);
         TB_LAUNCH_CHECK(ctx);
     }
     {
