@@ -30,12 +30,15 @@ struct W3 { uint32_t wm, w0, wp; };
 // horizontal 7-tap sums of the 4 pixels of the middle word (u16 range, exact)
 __device__ __forceinline__ void gauss_hrow(const W3 a, uint32_t h[4])
 {
-    const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps -3..0
-    const uint32_t KB = 48u | (34u << 8) | (18u << 16);                 // taps +1..+3
-    h[0] = __dp4a(__byte_perm(a.wm, a.w0, 0x4321), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x4321), KB, 0u));
-    h[1] = __dp4a(__byte_perm(a.wm, a.w0, 0x5432), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x5432), KB, 0u));
-    h[2] = __dp4a(__byte_perm(a.wm, a.w0, 0x6543), KA, __dp4a(__byte_perm(a.w0, a.wp, 0x6543), KB, 0u));
-    h[3] = __dp4a(a.w0, KA, __dp4a(a.wp, KB, 0u));
+    // shifted KERNELS instead of shifted data: 10 DP4A and no byte permutes (the permutes sat on the busier integer pipe)
+    const uint32_t K0m = (18u << 8) | (34u << 16) | (48u << 24), K0c = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+    const uint32_t K1m = (18u << 16) | (34u << 24), K1c = 48u | (56u << 8) | (48u << 16) | (34u << 24), K1p = 18u;
+    const uint32_t K2m = (18u << 24), K2c = 34u | (48u << 8) | (56u << 16) | (48u << 24), K2p = 34u | (18u << 8);
+    const uint32_t K3c = 18u | (34u << 8) | (48u << 16) | (56u << 24), K3p = 48u | (34u << 8) | (18u << 16);
+    h[0] = __dp4a(a.wm, K0m, __dp4a(a.w0, K0c, 0u));
+    h[1] = __dp4a(a.wm, K1m, __dp4a(a.w0, K1c, __dp4a(a.wp, K1p, 0u)));
+    h[2] = __dp4a(a.wm, K2m, __dp4a(a.w0, K2c, __dp4a(a.wp, K2p, 0u)));
+    h[3] = __dp4a(a.w0, K3c, __dp4a(a.wp, K3p, 0u));
 }
 
 // vertical 7-tap of the 4 pixels of a word column; window rows oldest..newest = win[(K+1)%7] .. win[K]; returns the 4 output
