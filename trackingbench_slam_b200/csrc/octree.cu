@@ -19,6 +19,7 @@
 //  * exit keys (AddPoints, :526-529, :467-480, :718-729) ride along as a second key set.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 
 #define OCT_THREADS 512
 
@@ -103,7 +104,7 @@ __device__ void block_bitonic_desc(unsigned long long *key, int m)
 
 extern __shared__ __align__(16) uint8_t oct_smem_raw[];
 
-struct OctArgsAll { OctArgs lv[TB_MAX_LEVELS]; };
+struct OctArgsAll { OctArgs lv[TB_MAX_LEVELS]; int nid_cache_keys; };
 
 // grid = (frames, levels): all (frame, level) problems of a batch in ONE launch, so the short per-level
 // tails overlap instead of serialising eight launches that are each bounded by their slowest CTA.
@@ -117,7 +118,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
     int n = a.n_cand[(size_t)f * a.n_stride];
     if (n > a.cand_cap) n = a.cand_cap;
     const uint32_t *cand = a.cand + (size_t)f * a.cand_cap;
-    uint16_t *nid = a.nid + (size_t)f * a.cand_cap;
+    uint16_t *nid = a.nid + (size_t)f * a.cand_cap;   // per-key node index; lives in shared memory when the keys fit (below)
     int16_t *enid = a.n_exit ? a.enid + (size_t)f * a.n_exit : nullptr;
     const int NE = a.n_exit;
 
@@ -134,6 +135,9 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         S.child = reinterpret_cast<int *>(p); p += sizeof(int) * NC * 4;
         S.aux = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         S.aux2 = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
+        // every pass reads and rewrites nid[k] of all keys (27 k at level 0 of a 1080p frame): keep it in shared memory
+        // instead of L2 when it fits the launch's key cache
+        if (n <= all.nid_cache_keys) nid = reinterpret_cast<uint16_t *>(p);
     }
     __shared__ int s_L, s_exp, s_cut, s_fail;
     if (tid == 0) s_fail = 0;
@@ -372,6 +376,15 @@ int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_fra
     for (int l = 0; l < n_levels; l++) all.lv[l].node_cap = max_cap;   // one shared-memory carve-up for the launch
     size_t smem = tb_octree_smem_bytes(max_cap);
     if (smem > 200 * 1024 || max_cap > 8191) return tb_fail(ctx, TB_E_UNSUPPORTED, "octree: per-level budget too large for shared memory");
+    // key cache: whatever keeps two CTAs per SM (the register file allows two), at most 32 Ki keys
+    {
+        int max_keys = 0;
+        for (int l = 0; l < n_levels; l++) max_keys = std::max(max_keys, levels[l].cand_cap);
+        const size_t room = smem < 108 * 1024 ? 108 * 1024 - smem : 0;
+        all.nid_cache_keys = (int)std::min<size_t>(std::min<size_t>(room / sizeof(uint16_t), 32768), (size_t)max_keys);
+        all.nid_cache_keys &= ~7;
+        smem += (size_t)all.nid_cache_keys * sizeof(uint16_t);
+    }
     ProfScope prof__(ctx, "octree_distribute");
     octree_distribute<<<dim3(n_frames, n_levels), OCT_THREADS, smem, stream>>>(all);
     TB_LAUNCH_CHECK(ctx);
