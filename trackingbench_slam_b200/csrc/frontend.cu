@@ -145,6 +145,10 @@ struct tb_frontend {
     int budget[TB_MAX_LEVELS] = {};
     bool has_budget = false;
     uint8_t *raw = nullptr; size_t raw_bytes = 0;   // staging for distorted frames (tb_frontend_upload_frames_undistort)
+    // CUDA graphs of the launch sequences of small batches (the single-frame host entries are launch bound: ~50 launches
+    // for well under a millisecond of kernels): captured once per parameter set, replayed afterwards
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; int n_frames = 0, target = 0; float initTh = 0, minTh = 0; float sf[TB_MAX_LEVELS] = {}; int64_t launches = 0; };
+    GraphSlot g_extract, g_pyramid;
     std::vector<void *> allocs;
 };
 
@@ -184,6 +188,8 @@ extern "C" void tb_frontend_destroy(tb_frontend *fe)
     if (!fe) return;
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
+    if (fe->g_extract.exec) cudaGraphExecDestroy(fe->g_extract.exec);
+    if (fe->g_pyramid.exec) cudaGraphExecDestroy(fe->g_pyramid.exec);
     for (void *p : fe->allocs) cudaFree(p);
     cudaFree(fe->raw);
     delete fe;
@@ -316,10 +322,38 @@ extern "C" int tb_frontend_download_level(tb_frontend *fe, int frame, int level,
     return TB_OK;
 }
 
-extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
+// batches up to this size replay captured graphs (TB_GRAPHS=0 disables; profiling always launches directly)
+static int graph_max_frames()
 {
-    if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
-    if (n_frames == 0) return TB_OK;
+    static const int v = getenv("TB_GRAPHS") ? atoi(getenv("TB_GRAPHS")) : 16;
+    return v;
+}
+// capture `enqueue` on the ctx stream into slot (or replay it if the slot already holds this parameter set)
+template <typename F>
+static int run_captured(tb_ctx *ctx, tb_frontend::GraphSlot &slot, bool same, F enqueue)
+{
+    if (!same || !slot.exec) {
+        if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+        const int64_t l0 = ctx->launches;
+        TB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) return tb_fail(ctx, TB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        const cudaError_t ei = cudaGraphInstantiate(&slot.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { slot.exec = nullptr; return tb_fail(ctx, TB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei)); }
+        slot.launches = ctx->launches - l0;
+        ctx->launches = l0;
+    }
+    TB_CUDA(ctx, cudaGraphLaunch(slot.exec, ctx->stream));
+    ctx->launches += slot.launches;
+    return TB_OK;
+}
+
+static int pyramid_enqueue(tb_frontend *fe, int n_frames)
+{
     for (int l = 1; l < fe->L; l++) {
         const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
         int rc = tb_launch_resize(fe->ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
@@ -328,6 +362,17 @@ extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
         if (rc) return rc;
     }
     return TB_OK;
+}
+
+extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
+{
+    if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
+    if (n_frames == 0) return TB_OK;
+    tb_ctx *ctx = fe->ctx;
+    if (ctx->profiling || n_frames > graph_max_frames()) return pyramid_enqueue(fe, n_frames);
+    const bool same = fe->g_pyramid.n_frames == n_frames;
+    fe->g_pyramid.n_frames = n_frames;
+    return run_captured(ctx, fe->g_pyramid, same, [&]() { return pyramid_enqueue(fe, n_frames); });
 }
 
 // ORBextractor.cpp:919-930
@@ -344,6 +389,8 @@ static void orb_budget(int L, float factor, int target, int *per_level)
     }
     per_level[L - 1] = target - sum > 0 ? target - sum : 0;
 }
+
+static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float initTh, float minTh, bool add_points, int n_exit);
 
 extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
                                    const tb_keypoint *exit_kps, int n_exit)
@@ -373,6 +420,21 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
         TB_CUDA(ctx, cudaMemcpyAsync(fe->exit_xy, xy.data(), sizeof(float2) * n_exit, cudaMemcpyHostToDevice, ctx->stream));
         TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (add_points || ctx->profiling || n_frames > graph_max_frames())
+        return extract_enqueue(fe, n_frames, sf, initTh, minTh, add_points, n_exit);
+    tb_frontend::GraphSlot &gs = fe->g_extract;
+    bool same = gs.n_frames == n_frames && gs.target == target && gs.initTh == initTh && gs.minTh == minTh;
+    for (int l = 0; l < L && same; l++) same = gs.sf[l] == sf[l];
+    gs.n_frames = n_frames; gs.target = target; gs.initTh = initTh; gs.minTh = minTh;
+    for (int l = 0; l < L; l++) gs.sf[l] = sf[l];
+    return run_captured(ctx, gs, same, [&]() { return extract_enqueue(fe, n_frames, sf, initTh, minTh, false, 0); });
+}
+
+// the launch sequence of one extract (captured into a graph for small batches)
+static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float initTh, float minTh, bool add_points, int n_exit)
+{
+    tb_ctx *ctx = fe->ctx;
+    const int L = fe->L;
     TB_CUDA(ctx, cudaMemsetAsync(fe->n_cand, 0, sizeof(int) * (size_t)n_frames * L, ctx->stream));
     TB_CUDA(ctx, cudaMemsetAsync(fe->n_kept, 0, sizeof(int) * (size_t)n_frames * L, ctx->stream));
     TB_CUDA(ctx, cudaMemsetAsync(fe->overflow, 0, sizeof(int) * 4, ctx->stream));
