@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from .conftest import GOLDEN, PARAM_SETS, kp_bytes_equal
+from .conftest import GOLDEN, PARAM_SETS, ROOT, kp_bytes_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -273,3 +273,32 @@ def test_random_shapes_and_thresholds_sweep(tb, ctx, oracle, images, seed):
             assert np.array_equal(d, do), (w, h, nl, sc, tgt, a, b)
         finally:
             fe.close()
+
+
+def test_fast_corner_list_overflow_path_is_exact():
+    """fast9_cells keeps a bounded corner list per tile and falls back to scanning its score map when a tile has more
+    corners. TB_FAST_LISTCAP=8 forces that path for every tile (read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np, cv2
+sys.path.insert(0, %r)
+import trackingbench_slam_b200 as tb
+from tests.conftest import PARAM_SETS, GOLDEN
+ctx = tb.Context(0)
+for pname in ('A1000', 'B2000'):
+    nl, sc, tgt, a, b = PARAM_SETS[pname]
+    for iname in ('left', 'right'):
+        img = cv2.imread(os.path.join(GOLDEN, 'data', iname + '.png'), 0)
+        g = np.load(os.path.join(GOLDEN, 'extract_%%s_%%s.npz' %% (iname, pname)))
+        sf, lw, lh = tb.pyramid_geometry(img.shape[1], img.shape[0], nl, sc)
+        fe = tb.Frontend(ctx, lw, lh, max_batch=1, max_target=tgt)
+        fe.upload_level(0, 0, img); fe.build_pyramid(1); fe.extract(1, sf, tgt, a, b)
+        k, d = fe.get_results(0)
+        assert k.tobytes() == g['kps'].tobytes() and d.tobytes() == g['desc'].tobytes(), (pname, iname)
+        fe.close()
+print('overflow path ok')
+''' % ROOT
+    env = dict(os.environ, TB_FAST_LISTCAP='8')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and 'overflow path ok' in out.stdout, out.stdout + out.stderr

@@ -19,6 +19,7 @@
 // derives the reference's order (cell row, cell col, y, x) from the coordinates themselves.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 
 
 __device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
@@ -152,9 +153,8 @@ __device__ uint2 g_bitpos[256];   // set-bit positions of a byte (one byte each,
 #define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
 struct FastSmem {
     uint8_t *tile, *sc, *cellOf, *need;
-    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (capacity = all pixels)
+    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (a.list_cap entries)
     uint32_t *stage;           // NMS survivors staged for the single global reservation (<= cap/4 + 1 entries)
-    uint2 *bitpos;             // [256] positions of the set bits of a byte, one byte each, lowest first
 };
 
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
@@ -187,7 +187,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
             }
             const int pos = warp_append1(corner, &s_cnt[2]);
-            if (corner) listB[pos] = (uint16_t)e;
+            if (corner && pos < a.list_cap) listB[pos] = (uint16_t)e;
         };
         for (int base = 0; base < items; base += 256) {
             const int it = base + tid;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
                 uint16_t *qp = q + qn + inc - cnt;
                 const uint32_t lo = m16 & 0xFF, hi = m16 >> 8;
-                const uint2 tl = S.bitpos[lo], th = S.bitpos[hi];     // eight byte-wide positions each
+                const uint2 tl = __ldg(&g_bitpos[lo]), th = __ldg(&g_bitpos[hi]);   // eight byte-wide positions each (2 KB, L1 resident)
                 const int nl = __popc(lo), nh = cnt - nl;
                 const uint32_t e8 = (uint32_t)(e0 + 8);
                 // PRMT pulls position j out zero-extended, the add rides the FMA pipe (the integer ALU pipe is the bottleneck)
@@ -253,15 +253,27 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     }
     __syncthreads();
     const int nc = s_cnt[2];
-    // ---- stage 5: NMS inside the cell interior; survivors are staged for the global write
+    // ---- stage 5: NMS inside the cell interior; survivors are staged for the global write.
+    // The corner list holds a.list_cap entries (a quarter of the tile's pixels: the list of ALL pixels cost 15 KB of shared
+    // memory and two resident CTAs per SM). If a tile ever has more corners, the m map is scanned instead: slower, same result.
     uint32_t *stage = S.stage;
-    for (int base = 0; base < nc; base += 256) {
+    const bool listed = nc <= a.list_cap;
+    const int n_iter = listed ? nc : hEff * a.scw;
+    for (int base = 0; base < n_iter; base += 256) {
         const int i = base + tid;
         bool keep = false;
         uint32_t val = 0;
-        if (i < nc) {
-            const int e = listB[i];
-            const int rr = e >> 10, cc = e & 1023;
+        int rr = 0, cc = 0;
+        bool is_corner = false;
+        if (i < n_iter) {
+            if (listed) { const int e = listB[i]; rr = e >> 10; cc = e & 1023; is_corner = true; }
+            else {
+                // overflow path: pixel i of the m map; only columns this pass tested (pass 2 leaves pass-1 cells alone)
+                rr = i / a.scw; cc = i - rr * a.scw;
+                is_corner = cc < wEff && sc[i] != 0 && S.need[cs + cc] != 0;
+            }
+        }
+        if (is_corner) {
             const int m = sc[rr * a.scw + cc];
             const int cell = S.cellOf[cc];
             const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
@@ -322,9 +334,14 @@ fast9_cells(FastArgs a)
     S.cellOf = S.sc + ((cap + 15) & ~15);                            // scw : cell index of an interior column
     S.need = S.cellOf + ((a.scw + 15) & ~15);                        // tp : 0x80 where this pass tests the byte column
     S.queue = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
-    S.listB = S.queue + 8 * FAST_QCAP;
-    S.stage = reinterpret_cast<uint32_t *>(S.listB + ((cap + 7) & ~7));
-    S.bitpos = reinterpret_cast<uint2 *>(S.stage + ((((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8 + 1) & ~1));
+    {   // queues and the NMS staging area share one region (see below): the larger of the two, 16-byte granular
+        const size_t qbytes = sizeof(uint16_t) * 8 * FAST_QCAP, sbytes = sizeof(uint32_t) * (((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8);
+        S.listB = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.queue) + (((qbytes > sbytes ? qbytes : sbytes) + 15) & ~(size_t)15));
+    }
+    // the NMS survivors are staged where the per-warp queues were: the queues are dead once the fused stages 1-4 are over,
+    // and the staging area is read out (emission) before pass 2 fills the queues again. With the position table read
+    // through L1 instead of copied here, the CTA fits 5 to an SM.
+    S.stage = reinterpret_cast<uint32_t *>(S.queue);
     __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
     __shared__ int s_has[64];
 
@@ -368,7 +385,6 @@ fast9_cells(FastArgs a)
         S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
         if (i < a.scw) S.cellOf[i] = (uint8_t)fast_div(i, a.magic_wcell);
     }
-    S.bitpos[tid] = g_bitpos[tid];
     if (tid < 4) s_cnt[tid] = 0;
     if (tid < 64) s_has[tid] = 0;
     __syncthreads();
@@ -392,13 +408,14 @@ fast9_cells(FastArgs a)
     fast_pass(a, S, a.minTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base, s_lo, s_hi);
 }
 
-size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch)
+size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap)
 {
     const int cap = hCell * scw;
     // tile + m map + cellOf + need + per-warp queues + corner list (u16 per pixel) + survivor staging (NMS keeps at most
     // ceil(h/2)*ceil(w/2) pixels of a tile)
     return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) +
-           sizeof(uint16_t) * (8 * FAST_QCAP + ((cap + 7) & ~7)) + sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8 + 2 + 512) + 64;
+           ((std::max(sizeof(uint16_t) * 8 * FAST_QCAP, sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8)) + 15) & ~(size_t)15) +
+           sizeof(uint16_t) * ((list_cap + 7) & ~7) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)

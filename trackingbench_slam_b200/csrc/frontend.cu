@@ -485,7 +485,12 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
             a.overflow = fe->overflow;
-            size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch);
+            {
+                // a quarter of the tile's pixels (TB_FAST_LISTCAP overrides: tests force the overflow path with a tiny list)
+                static const int forced = getenv("TB_FAST_LISTCAP") ? atoi(getenv("TB_FAST_LISTCAP")) : 0;
+                a.list_cap = forced > 0 ? forced : std::max(256, (g.hCell * a.scw) / 4);
+            }
+            size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, a.list_cap);
             int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
             if (rc) return rc;
         }

@@ -17,13 +17,14 @@ struct FastArgs {
     int w, h;
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
     int G, tpitch, scw;
+    int list_cap;      // entries of the per-tile corner list (more corners than that: the NMS scans the score map)
     uint32_t magic_groups, magic_w8, magic_wcell;   // 2^32/n rounded up for the full-width tile (0 when n == 1)
     int initTh, minTh;
     uint32_t *cand; int cand_cap;
     int *n_cand; int n_cand_stride;
     int *overflow;
 };
-size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch);
+size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap);
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem);
 struct OctArgs {
     const uint32_t *cand; int cand_cap;
