@@ -18,11 +18,12 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-#define TC_M 128          // query rows per CTA
-#define TC_N 256          // train rows per tile
+#define TC_M 128          // rows of one MMA (TMEM lanes)
+#define TC_MB_MAX 2       // M blocks per CTA (template parameter MB): with 2, 256 query rows share every train tile, which halves
+                          // the L2 -> shared-memory traffic that bounds the batched frame-pair matcher; the 200k x 200k kNN-2
+                          // keeps 1 (its top-2 epilogue is the bound and 128-row CTAs fill the last wave better)
+#define TC_PAD 256        // expanded frames are padded to a multiple of this many rows
 #define TC_KB 256         // bytes (= int8 elements) per expanded descriptor
-#define TC_A_BYTES (TC_M * TC_KB)
-#define TC_B_BYTES (TC_N * TC_KB)
 #define TC_THREADS 320      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct TcPair {
@@ -119,31 +120,35 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 struct __align__(16) TcShared {
     uint64_t fullA, full[2], empty[2], tfull[2], tempty[2];
     uint32_t tmem_base;
-    int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // partial results of the upper-half-column warps
+    int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // MB = 1: partial results of the upper-half-column warps
 };
 
+#define TC_SMEM_BYTES (160 * 1024 + sizeof(TcShared) + 64)   // MB = 1: A 32 KB + B 2 x 64 KB; MB = 2: A 64 KB + B 2 x 32 KB
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
-template <bool SECOND>
+template <bool SECOND, int MB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist,
               int *__restrict__ second_dist)
 {
     const TcPair pd = pairs[blockIdx.y];
-    const int q0 = blockIdx.x * TC_M;
+    constexpr int TC_ROWS = TC_M * MB;
+    constexpr int TN = MB == 1 ? 256 : 128;            // train rows per tile: TMEM holds 2 stages x MB blocks x TN = 512 columns
+    constexpr int TB_BYTES = TN * TC_KB;
+    const int q0 = blockIdx.x * TC_ROWS;
     if (q0 >= pd.nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *sA = tc_smem;                                  // 32 KB
-    uint8_t *sB = tc_smem + TC_A_BYTES;                     // 2 x 64 KB
-    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_A_BYTES + 2 * TC_B_BYTES);
-    const int NT = (pd.nt + TC_N - 1) / TC_N;
+    uint8_t *sA = tc_smem;                                  // 2 x 32 KB (two M blocks)
+    uint8_t *sB = tc_smem + TC_ROWS * TC_KB;                // two stages of TN rows
+    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + 2 * TB_BYTES);
+    const int NT = (pd.nt + TN - 1) / TN;
 
     if (threadIdx.x == 0) {
         mbar_init(&S->fullA, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: 512 columns = two 128x256 int32 accumulators
+    if (warp == 0) {   // TMEM: 512 columns = 2 stages x 2 M blocks of 128x128 int32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -157,51 +162,57 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
         if (lane == 0) {
             // ---- producer
             const int8_t *qa = pd.q + (size_t)q0 * TC_KB;   // rows q0.. are contiguous in the canonical layout
-            mbar_expect_tx(&S->fullA, TC_A_BYTES);
-            for (int c = 0; c < TC_A_BYTES; c += 16384) bulk_g2s(sA + c, qa + c, 16384, &S->fullA);
+            mbar_expect_tx(&S->fullA, TC_ROWS * TC_KB);
+            for (int c = 0; c < TC_ROWS * TC_KB; c += 16384) bulk_g2s(sA + c, qa + c, 16384, &S->fullA);
             for (int t = 0; t < NT; t++) {
                 const int s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait(&S->empty[s], ph ^ 1);
-                mbar_expect_tx(&S->full[s], TC_B_BYTES);
-                const int8_t *tb = pd.t + (size_t)t * TC_B_BYTES;
-                for (int c = 0; c < TC_B_BYTES; c += 16384) bulk_g2s(sB + s * TC_B_BYTES + c, tb + c, 16384, &S->full[s]);
+                mbar_expect_tx(&S->full[s], TB_BYTES);
+                const int8_t *tb = pd.t + (size_t)t * TB_BYTES;
+                for (int c = 0; c < TB_BYTES; c += 16384) bulk_g2s(sB + s * TB_BYTES + c, tb + c, 16384, &S->full[s]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---- MMA issuer: idesc = D s32 | A s8 | B s8 | K-major both | N=256 | M=128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             mbar_wait(&S->fullA, 0);
-            const uint64_t adesc = make_desc(smem_u32(sA));
+            const uint64_t adesc0 = make_desc(smem_u32(sA)), adesc1 = make_desc(smem_u32(sA + TC_M * TC_KB));
             for (int t = 0; t < NT; t++) {
                 const int s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait(&S->full[s], ph);
                 mbar_wait(&S->tempty[s], ph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t bdesc = make_desc(smem_u32(sB + s * TC_B_BYTES));
+                const uint64_t bdesc = make_desc(smem_u32(sB + s * TB_BYTES));
 #pragma unroll
                 for (int k = 0; k < TC_KB / 32; k++)   // K step = 32 bytes = two 16-byte core-matrix columns = 256 B in this layout
-                    mma_i8(tmem + s * TC_N, adesc + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                    mma_i8(tmem + (s * MB + 0) * TN, adesc0 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                if (MB > 1)
+#pragma unroll
+                for (int k = 0; k < TC_KB / 32; k++)
+                    mma_i8(tmem + (s * MB + 1) * TN, adesc1 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
                 tc_commit(&S->empty[s]);    // shared-memory stage reusable once these MMAs retire
                 tc_commit(&S->tfull[s]);    // accumulator ready for the epilogue
             }
         }
     } else {
-        // ---- epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31 = query rows; warps 2..5 scan the lower 128
-        //      columns of every accumulator tile, warps 6..9 the upper 128
+        // ---- epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; warps 2..5 own the query rows of M block 0,
+        //      warps 6..9 those of M block 1 — one thread per query row, all columns
+        // (MB = 1: both warps of a lane quarter share the rows and split every tile's columns; merged at the end)
         const int lane_base = 32 * (warp & 3);
-        const int half = (warp - 2) >> 2;
-        const int row = q0 + lane_base + lane;
+        const int grp = (warp - 2) >> 2;
+        const int mb = MB > 1 ? grp : 0;
+        const int cbeg = MB > 1 ? 0 : grp * (TN / 2), cend = MB > 1 ? TN : cbeg + TN / 2;
         for (int t = 0; t < NT; t++) {
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&S->tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int col0 = t * TC_N + half * (TC_N / 2);
+            const int col0 = t * TN;
 #pragma unroll 1
-            for (int c = 0; c < TC_N / 2; c += 32) {
+            for (int c = cbeg; c < cend; c += 32) {
                 if (col0 + c >= pd.nt) break;   // warp-uniform
                 uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(s * TC_N + half * (TC_N / 2) + c);
+                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)((s * MB + mb) * TN + c);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -269,13 +280,21 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->tempty[s]);
         }
-        if (half == 1) { S->part_best[lane_base + lane] = best; S->part_second[lane_base + lane] = second; S->part_idx[lane_base + lane] = bidx; }
-        (void)row;
+        if (MB == 1 && grp == 1) { S->part_best[lane_base + lane] = best; S->part_second[lane_base + lane] = second; S->part_idx[lane_base + lane] = bidx; }
+        if (MB > 1) {
+            const int row = q0 + mb * TC_M + lane_base + lane;
+            if (row < pd.nq) {
+                const size_t o = (size_t)blockIdx.y * out_stride + row;
+                best_idx[o] = bidx;
+                best_dist[o] = bidx >= 0 ? (256 - best) >> 1 : 0x7fffffff;
+                if (SECOND) second_dist[o] = second > -1000 ? (256 - second) >> 1 : 0x7fffffff;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
-    if (warp >= 2 && warp < 6) {
+    if (MB == 1 && warp >= 2 && warp < 6) {
         // merge the two column halves (lowest index wins ties) and write the row's result
         const int r = 32 * (warp & 3) + lane, row = q0 + r;
         const int b1 = S->part_best[r], s1 = S->part_second[r], i1 = S->part_idx[r];
@@ -318,7 +337,7 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *
                     const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap, int *best_idx, int *best_dist)
 {
     TcWs *w = tcws(ctx);
-    const int rows_pad = (kp_cap + TC_N - 1) / TC_N * TC_N;
+    const int rows_pad = (kp_cap + TC_PAD - 1) / TC_PAD * TC_PAD;
     const size_t exp_stride = (size_t)rows_pad * TC_KB;
     const size_t need = exp_stride * (size_t)n_frames_used;
     if (need > w->exp_bytes) {
@@ -339,11 +358,11 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *
     }
     build_tc_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w->pairs, n_pairs, d_q_frames, d_t_frames, w->exp, exp_stride, counts);
     TB_LAUNCH_CHECK(ctx);
-    const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
+    const size_t smem = TC_SMEM_BYTES;
     {
         ProfScope prof__(ctx, "hamming_i8mma");
-        dim3 grid(div_up(kp_cap, TC_M), 2 * n_pairs);
-        hamming_i8mma<false><<<grid, TC_THREADS, smem, ctx->stream>>>(w->pairs, kp_cap, best_idx, best_dist, nullptr);
+        dim3 grid(div_up(kp_cap, TC_M * 2), 2 * n_pairs);
+        hamming_i8mma<false, 2><<<grid, TC_THREADS, smem, ctx->stream>>>(w->pairs, kp_cap, best_idx, best_dist, nullptr);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
@@ -353,7 +372,7 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *
 int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *best, int *second)
 {
     TcWs *w = tcws(ctx);
-    const size_t q_rows = (size_t)(nq + TC_N - 1) / TC_N * TC_N, t_rows = (size_t)(nt + TC_N - 1) / TC_N * TC_N;
+    const size_t q_rows = (size_t)(nq + TC_PAD - 1) / TC_PAD * TC_PAD, t_rows = (size_t)(nt + TC_PAD - 1) / TC_PAD * TC_PAD;
     const size_t need = (q_rows + t_rows) * TC_KB;
     if (need > w->exp_bytes) {
         if (w->exp) cudaFree(w->exp);
@@ -376,10 +395,10 @@ int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, 
     }
     TcPair pd = {eq, et, nq, nt};
     TB_CUDA(ctx, cudaMemcpyAsync(w->pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64;
+    const size_t smem = TC_SMEM_BYTES;
     {
         ProfScope prof__(ctx, "hamming_i8mma");
-        hamming_i8mma<true><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, smem, ctx->stream>>>(w->pairs, 0, idx, best, second);
+        hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, smem, ctx->stream>>>(w->pairs, 0, idx, best, second);
         TB_LAUNCH_CHECK(ctx);
     }
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pair descriptor came from pageable host memory
@@ -388,7 +407,7 @@ int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, 
 
 void tb_match_tc_init_device()
 {
-    const int smem = (int)(TC_A_BYTES + 2 * TC_B_BYTES + sizeof(TcShared) + 64);
-    cudaFuncSetAttribute(hamming_i8mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(hamming_i8mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)(TC_SMEM_BYTES);
+    cudaFuncSetAttribute(hamming_i8mma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
