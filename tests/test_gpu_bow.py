@@ -164,3 +164,32 @@ def test_frontend_batched_bow_device_resident(tb, ctx, oracle, images):
     finally:
         dv.close()
         fe.close()
+
+
+def test_bow_and_ingest_edge_cases(tb, ctx, oracle):
+    """Empty inputs and invalid arguments of the next-row entry points behave like the rest of the ABI."""
+    import ctypes as C
+    voc = V.synth_vocabulary(3, 2, 0)
+    dv = ctx.vocab_create(voc)
+    wid, nid, w = ctx.bow_transform(dv, np.zeros((0, 32), np.uint8), 4)
+    assert len(wid) == 0 and len(nid) == 0 and len(w) == 0
+    k0, d0 = np.zeros(0, tb.KP_DTYPE), np.zeros((0, 32), np.uint8)
+    k3, d3 = np.zeros(3, tb.KP_DTYPE), np.zeros((3, 32), np.uint8)
+    p = tb.MatcherParams(50, 100, 30, 1, 0.9)
+    assert len(ctx.search_by_bow(p, k0, d0, np.zeros(0, np.int32), k3, d3, np.zeros(3, np.int32))) == 0
+    assert len(ctx.search_by_bow(p, k3, d3, np.zeros(3, np.int32), k0, d0, np.zeros(0, np.int32))) == 0
+    # all features of F1 unbucketed (-1): nothing to match
+    assert len(ctx.search_by_bow(p, k3, d3, np.full(3, -1, np.int32), k3, d3, np.zeros(3, np.int32))) == 0
+    # identical descriptors in one bucket: best == second, ratio test rejects (bestDist1 < nRatio * bestDist2 with 0 < 0 false)
+    assert len(ctx.search_by_bow(p, k3, d3, np.zeros(3, np.int32), k3, d3, np.zeros(3, np.int32))) == 0
+    assert len(oracle.search_by_bow(oracle.MatcherParams(50, 100, 30, 1, 0.9), k3, d3, np.zeros(3, np.int32), k3, d3, np.zeros(3, np.int32))) == 0
+    dv.close()
+    # ingest: bad arguments
+    m = np.zeros((8, 8), np.float32)
+    und = tb.Undistorter(ctx, m, m)
+    rc = tb.lib().tb_undistort_image_device(ctx.h, und.h, C.c_void_p(0), 8, 8, C.c_size_t(8), C.c_size_t(64), C.c_void_p(0), C.c_size_t(8), C.c_size_t(64), 1)
+    assert rc == tb.TB_E_INVALID
+    und.close()
+    img = np.zeros((4, 4), np.uint8)
+    with pytest.raises(tb.TbError):
+        ctx.clahe_host(img, 3.0, (8, 8))          # padding to the tile grid would exceed the image: unsupported, not silently wrong
