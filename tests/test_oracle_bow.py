@@ -133,3 +133,28 @@ def test_search_by_bow_golden(vname):
         assert np.array_equal(O.search_by_bow(p, kl, dl, g['left_node'], kr, dr, g['right_node'], mv, True), g['bow_mp_only'])
         p2 = O.MatcherParams(80, 100, 30, 0, 0.95)
         assert np.array_equal(O.search_by_bow(p2, kl, dl, g['left_node'], kr, dr, g['right_node']), g['bow_nocheck'])
+
+
+def test_vocabulary_text_roundtrip_and_csr(tmp_path):
+    """Runs everywhere (no reference build needed): ORBvoc.txt layout round trip and the flattened tree's invariants."""
+    voc = V.synth_vocabulary(4, 3, 5, stop_frac=0.2)
+    path = str(tmp_path / 'voc.txt')
+    voc.save_text(path)
+    assert not open(path).read().endswith('\n')       # a trailing newline would add a bogus root child in the reference loader
+    back = V.Vocabulary.load_text(path)
+    for name in ('parent', 'is_leaf', 'desc', 'weight'):
+        assert np.array_equal(getattr(back, name), getattr(voc, name)), name
+    assert (back.k, back.L, back.scoring, back.weighting) == (voc.k, voc.L, voc.scoring, voc.weighting)
+    start, children, word = voc.csr()
+    n = voc.n_nodes
+    assert start[0] == 0 and start[-1] == n - 1 and len(children) == n - 1
+    for i in range(n):
+        kids = children[start[i]:start[i + 1]]
+        assert np.all(voc.parent[kids] == i) and np.all(np.diff(kids) > 0)      # children in ascending id
+    leaves = np.flatnonzero(voc.is_leaf)
+    assert np.array_equal(word[leaves], np.arange(len(leaves)))                  # word ids in file order
+    assert np.all(word[(start[1:] > start[:-1])] == -1)                          # inner nodes carry no word
+    fast = V.synth_vocabulary_fast(3, 3, 1)
+    assert fast.n_nodes == 1 + 3 + 9 + 27 and int(fast.is_leaf.sum()) == 27
+    wid, nid, w = O.bow_transform(fast, fast.desc[-5:], 1)                       # leaves map to themselves
+    assert np.array_equal(wid, np.arange(22, 27))
