@@ -179,6 +179,7 @@ struct MatchWs { // lazily grown per-ctx workspace
     PairDesc *pairs = nullptr; int pairs_cap = 0;
     int *best_idx = nullptr, *best_dist = nullptr, *second = nullptr, *scratch = nullptr; size_t ws_cap = 0;
     int *frames = nullptr; int frames_cap = 0;
+    std::vector<int32_t> frames_shadow;   // host copy of what the device frame lists hold (skip identical re-uploads)
     tb_match *out = nullptr; int *out_count = nullptr; size_t out_cap = 0;
 };
 static MatchWs &ws_of(tb_ctx *ctx)
@@ -341,10 +342,20 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
         if (w.frames) cudaFree(w.frames);
         TB_CUDA(ctx, cudaMalloc(&w.frames, sizeof(int) * 2 * n_pairs));
         w.frames_cap = 2 * n_pairs;
+        w.frames_shadow.clear();
     }
-    // frame index lists are tiny; stage them through a pinned-free synchronous copy on the stream
-    TB_CUDA(ctx, cudaMemcpyAsync(w.frames, q_frames_host, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(w.frames + n_pairs, t_frames_host, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    // The frame index lists are tiny, but a host-to-device copy queues on the same copy engine as the NEXT batch's frame
+    // upload (already running in a pipelined caller) and would hold this batch's matcher back until that upload ends:
+    // re-upload only when the lists changed (a streaming caller passes the same k <-> k+1 lists every step).
+    const bool same = w.frames_shadow.size() == (size_t)2 * n_pairs &&
+                      memcmp(w.frames_shadow.data(), q_frames_host, sizeof(int32_t) * n_pairs) == 0 &&
+                      memcmp(w.frames_shadow.data() + n_pairs, t_frames_host, sizeof(int32_t) * n_pairs) == 0;
+    if (!same) {
+        w.frames_shadow.assign(q_frames_host, q_frames_host + n_pairs);
+        w.frames_shadow.insert(w.frames_shadow.end(), t_frames_host, t_frames_host + n_pairs);
+        TB_CUDA(ctx, cudaMemcpyAsync(w.frames, w.frames_shadow.data(), sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the shadow may be reallocated by a later call while the copy is pending
+    }
     build_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w.pairs, n_pairs, w.frames, w.frames + n_pairs, desc, frame_stride, counts);
     TB_LAUNCH_CHECK(ctx);
     if (ctx->match_impl == 1) {
