@@ -135,6 +135,7 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 // are interpolated, so no thread issues a global load and the table entries are read once per CTA instead of once per frame.
 #define PYR_BOXW 192
 #define PYR_FPC 8
+#define PYR_STAGES 3   // source boxes in flight (the register file limits the kernel to 3 CTAs/SM, shared memory has room)
 __device__ __forceinline__ uint32_t pyr_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pyr_tma_box(void *dst, const CUtensorMap *tm, int x, int y, int z, uint64_t *bar)
 {
@@ -152,22 +153,21 @@ __global__ void __launch_bounds__(256, 3)
 pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, int dpitch, size_t dframe,
                          int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames, int fpc)
 {
-    __shared__ alignas(8) uint64_t s_full[2];
+    __shared__ alignas(8) uint64_t s_full[PYR_STAGES];
     const int tid = threadIdx.y * 64 + threadIdx.x;
     const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
     const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
     const int f0 = blockIdx.z * fpc, nf = min(n_frames, f0 + fpc) - f0;
     const int box_bytes = (bh_max * PYR_BOXW + 127) & ~127;                       // one 192-wide box, 128-byte aligned
     uint8_t *boxes = pyr_smem;                                                    // [2 stages][2 boxes][box_bytes]
-    uint16_t *Hs = reinterpret_cast<uint16_t *>(pyr_smem + 4 * (size_t)box_bytes); // bh_max x PYR_TW u16
+    uint16_t *Hs = reinterpret_cast<uint16_t *>(pyr_smem + 2 * PYR_STAGES * (size_t)box_bytes); // bh_max x PYR_TW u16
     const int sx_lo = __ldg(&xtab[tx0]).x & ~15;
     const int sy_lo = __ldg(&ytab[ty0]).x, sy_hi = __ldg(&ytab[ty1]).y;
     const int bh = sy_hi - sy_lo + 1;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[0])), "r"(1));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[1])), "r"(1));
+        for (int s = 0; s < PYR_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int s = 0; s < 2 && s < nf; s++) {
+        for (int s = 0; s < PYR_STAGES && s < nf; s++) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
             pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f0 + s, &s_full[s]);
             pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f0 + s, &s_full[s]);
@@ -213,8 +213,8 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
     }
     __syncthreads();                                       // barriers initialised before anyone waits
     for (int f = 0; f < nf; f++) {
-        const int s = f & 1;
-        pyr_mbar_wait(&s_full[s], (uint32_t)((f >> 1) & 1));
+        const int s = f % PYR_STAGES;
+        pyr_mbar_wait(&s_full[s], (uint32_t)((f / PYR_STAGES) & 1));
         // ---- phase 1: horizontal pass, rows threadIdx.y, +4, ...
         const uint8_t *stage = boxes + (size_t)(2 * s) * box_bytes;
         for (int r = threadIdx.y; r < bh; r += 4) {
@@ -231,10 +231,10 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
             *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
         }
         __syncthreads();                                   // H complete, stage s drained
-        if (tid == 0 && f + 2 < nf) {
+        if (tid == 0 && f + PYR_STAGES < nf) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
-            pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f0 + f + 2, &s_full[s]);
-            pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f0 + f + 2, &s_full[s]);
+            pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f0 + f + PYR_STAGES, &s_full[s]);
+            pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f0 + f + PYR_STAGES, &s_full[s]);
         }
         // ---- phase 2: vertical pass, 4 columns x 8 rows per thread
         if (dx0 <= tx1) {
@@ -306,7 +306,7 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
     static const bool use_tma = !(getenv("TB_PYR_TMA") && atoi(getenv("TB_PYR_TMA")) == 0);   // A/B knob: 0 forces the LDG-staged kernel
     if (!area2 && tmap && use_tma && bp <= 2 * PYR_BOXW && bh <= 256) {
         const size_t box_bytes = ((size_t)bh * PYR_BOXW + 127) & ~(size_t)127;
-        const size_t smem = 4 * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
+        const size_t smem = 2 * PYR_STAGES * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
         if (smem <= 200 * 1024) {
             static const int fpc = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;   // frames per CTA (tuning knob)
             dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, fpc)), block(64, 4);
