@@ -27,7 +27,8 @@
 struct OctSmem {
     short4 *box[2];   // {ulx, urx, uly, bry}
     int *cnt[2];
-    int *child;       // [node_cap*4] child counts, then child new positions
+    int *child;       // [node_cap*4] child votes of the current pass, turned into the children's new list positions
+    int *child2;      // [node_cap*4] votes for the NEXT pass, cast while the keys are remapped (the two swap every pass)
     int *aux;         // [node_cap] per-node scratch (scan input / remap of unsplit nodes)
     int *aux2;        // [node_cap] nchild / split flags
     unsigned long long *skey; // [pow2(node_cap)] sort keys / best keys
@@ -133,6 +134,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         S.cnt[0] = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         S.cnt[1] = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         S.child = reinterpret_cast<int *>(p); p += sizeof(int) * NC * 4;
+        S.child2 = reinterpret_cast<int *>(p); p += sizeof(int) * NC * 4;
         S.aux = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         S.aux2 = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         // every pass reads and rewrites nid[k] of all keys (27 k at level 0 of a 1080p frame): keep it in shared memory
@@ -181,26 +183,33 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
     }
 
     bool phase2 = false;
-    for (;;) {
-        const int L = s_L;
-        short4 *box = S.box[cur], *nbox = S.box[cur ^ 1];
-        int *cnt = S.cnt[cur], *ncnt = S.cnt[cur ^ 1];
-        // ---- (A) child votes of every node with >1 key
-        for (int i = tid; i < 4 * L; i += OCT_THREADS) S.child[i] = 0;
+    int *V = S.child, *W = S.child2;     // votes of this pass / of the next one
+    // ---- (A) child votes of every node with >1 key, first pass only: later passes get theirs from the remap loop (C) of
+    //      the pass before, which already has the key's coordinates in hand (one sweep over the keys per pass, not two)
+    {
+        const int L0 = s_L;
+        const short4 *box = S.box[cur];
+        const int *cnt = S.cnt[cur];
+        for (int i = tid; i < 4 * L0; i += OCT_THREADS) V[i] = 0;
         __syncthreads();
         for (int k = tid; k < n; k += OCT_THREADS) {
             int ni = nid[k];
             if (cnt[ni] > 1) {
                 uint32_t c = cand[k];
-                atomicAdd(&S.child[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))], 1);
+                atomicAdd(&V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))], 1);
             }
         }
         __syncthreads();
+    }
+    for (;;) {
+        const int L = s_L;
+        short4 *box = S.box[cur], *nbox = S.box[cur ^ 1];
+        int *cnt = S.cnt[cur], *ncnt = S.cnt[cur ^ 1];
         // ---- (B) who splits, in which processing order
         // aux2[i] = number of non-empty children (0 for nodes that cannot split)
         for (int i = tid; i < L; i += OCT_THREADS) {
             int nch = 0;
-            if (cnt[i] > 1) nch = (S.child[4 * i] > 0) + (S.child[4 * i + 1] > 0) + (S.child[4 * i + 2] > 0) + (S.child[4 * i + 3] > 0);
+            if (cnt[i] > 1) nch = (V[4 * i] > 0) + (V[4 * i + 1] > 0) + (V[4 * i + 2] > 0) + (V[4 * i + 3] > 0);
             S.aux2[i] = nch;
         }
         __syncthreads();
@@ -215,12 +224,12 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
                 if (S.aux2[i] > 0) {
                     int P = S.aux[i], o = 0;
                     for (int c = 0; c < 4; c++) {
-                        int cc = S.child[4 * i + c];
+                        int cc = V[4 * i + c];
                         if (cc > 0) {
                             int pos = TC - P - 1 - o; o++;
                             nbox[pos] = oct_child_box(box[i], c); ncnt[pos] = cc;
-                            S.child[4 * i + c] = pos;
-                        } else S.child[4 * i + c] = -1;
+                            V[4 * i + c] = pos;
+                        } else V[4 * i + c] = -1;
                     }
                 }
             }
@@ -259,12 +268,12 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
                 int i = (int)(S.skey[j] & 0x1FFF);
                 int P = S.aux[j], o = 0;
                 for (int c = 0; c < 4; c++) {
-                    int cc = S.child[4 * i + c];
+                    int cc = V[4 * i + c];
                     if (cc > 0) {
                         int pos = TC - P - 1 - o; o++;
                         nbox[pos] = oct_child_box(box[i], c); ncnt[pos] = cc;
-                        S.child[4 * i + c] = pos;
-                    } else S.child[4 * i + c] = -1;
+                        V[4 * i + c] = pos;
+                    } else V[4 * i + c] = -1;
                 }
             }
             __syncthreads();
@@ -282,20 +291,30 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         for (int i = tid; i < L; i += OCT_THREADS)
             if (S.aux2[i] == 0) { int pos = TC + S.aux[i]; nbox[pos] = box[i]; ncnt[pos] = cnt[i]; S.aux[i] = pos; }
         __syncthreads();
-        // ---- (C) remap keys
+        // ---- (C) remap keys, and vote for the next pass in the same sweep
+        for (int i = tid; i < 4 * newL; i += OCT_THREADS) W[i] = 0;
+        __syncthreads();
         for (int k = tid; k < n; k += OCT_THREADS) {
-            int ni = nid[k];
+            const int ni = nid[k];
+            uint32_t c = 0;
+            bool have = false;
+            int nn;
             if (S.aux2[ni] > 0) {
-                uint32_t c = cand[k];
-                nid[k] = (uint16_t)S.child[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))];
-            } else nid[k] = (uint16_t)S.aux[ni];
+                c = cand[k]; have = true;
+                nn = V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))];
+            } else nn = S.aux[ni];
+            nid[k] = (uint16_t)nn;
+            if (ncnt[nn] > 1) {
+                if (!have) c = cand[k];
+                atomicAdd(&W[4 * nn + oct_child(nbox[nn], (float)cand_x(c), (float)cand_y(c))], 1);
+            }
         }
         for (int e = tid; e < NE; e += OCT_THREADS) {
             int ni = enid[e];
             if (ni >= 0) {
                 if (S.aux2[ni] > 0) {
                     float2 p = a.exit_xy[e];
-                    enid[e] = (int16_t)S.child[4 * ni + oct_child(box[ni], p.x, p.y)]; // -1 if that child is empty
+                    enid[e] = (int16_t)V[4 * ni + oct_child(box[ni], p.x, p.y)]; // -1 if that child is empty
                 } else enid[e] = (int16_t)S.aux[ni];
             }
         }
@@ -309,6 +328,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         }
         __syncthreads();
         cur ^= 1;
+        { int *t = V; V = W; W = t; }
         const int nExp = s_exp;
         if (tid == 0) s_L = newL;
         __syncthreads();
@@ -364,7 +384,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
 size_t tb_octree_smem_bytes(int node_cap)
 {
     int m2 = 1; while (m2 < node_cap) m2 <<= 1;
-    return sizeof(unsigned long long) * m2 + (size_t)node_cap * (2 * sizeof(short4) + 2 * sizeof(int) + 4 * sizeof(int) + 2 * sizeof(int));
+    return sizeof(unsigned long long) * m2 + (size_t)node_cap * (2 * sizeof(short4) + 2 * sizeof(int) + 8 * sizeof(int) + 2 * sizeof(int));
 }
 
 int tb_launch_octree(tb_ctx *ctx, const OctArgs *levels, int n_levels, int n_frames, cudaStream_t stream)
