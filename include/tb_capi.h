@@ -286,6 +286,31 @@ int tb_frontend_search_by_bow(tb_frontend *fe, const tb_matcher_params *p, int n
                               const void *node_i32_dptr, const void *mp_valid_dptr, int map_point_only,
                               void *matches_dptr, int capacity, void *counts_i32_dptr);
 
+/* ORB stereo row-band matcher: the block-commented body of LocalBA::AddMapPointsByStereo (src/mapping/LocalBA.cpp:69-288)
+ * as its text stands (coarse ORB match per image row band + depth = bf/|xL-xR|; the SAD refinement and median filter carry
+ * their own // inside that block and are not part of it).  Right key iR is a candidate of left key iL when
+ * floor(yR-r) <= (size_t)yL <= ceil(yR+r), r = band * inv_sf[octaveR] (:84-92), |octaveR-octaveL| <= octave_tol (:131) and
+ * min_u <= xR <= max_u (:136); the first candidate in index order with the smallest non-zero distance wins (:140); it is a
+ * match when that distance < th_dist (:148).  Matches come out in iL order with imgIdx = -1 (cv::DMatch default). */
+typedef struct {
+    float bf;           /* baseline * fx */
+    float band;         /* reference: 2.f */
+    float min_u, max_u; /* reference: 0, 100000 */
+    int32_t th_dist;    /* reference: 30 */
+    int32_t octave_tol; /* reference: 1 */
+} tb_stereo_params;
+/* Host in/out. inv_sf = Frame::GetInverseScaleFactors() (n_levels floats), n_rows = rows of pyramid level 0;
+ * depth (may be NULL) receives nL floats, -1 where there is no match. */
+int tb_stereo_match(tb_ctx *ctx, const tb_stereo_params *p, const tb_keypoint *kL, const uint8_t *dL, int nL,
+                    const tb_keypoint *kR, const uint8_t *dR, int nR, const float *inv_sf, int n_levels, int n_rows,
+                    tb_match *out, int capacity, int *n, float *depth);
+/* Device-resident, batched over frames of the frontend's last extract: pair p = (left_frames[p], right_frames[p]).
+ * Outputs on the device: matches_dptr[p*capacity + i], counts_dptr[p], depth_f32_dptr[p*tb_frontend_kp_capacity() + iL]
+ * (may be NULL). */
+int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames,
+                             const int32_t *right_frames, const float *inv_sf, void *matches_dptr, int capacity,
+                             void *counts_i32_dptr, void *depth_f32_dptr);
+
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
  * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */

@@ -22,6 +22,14 @@ class MatcherParams(C.Structure):
                 ('checkOrientation', C.c_int), ('nRatio', C.c_float)]
 
 
+class StereoParams(C.Structure):
+    _fields_ = [('bf', C.c_float), ('band', C.c_float), ('min_u', C.c_float), ('max_u', C.c_float),
+                ('th_dist', C.c_int), ('octave_tol', C.c_int)]
+
+    def __init__(self, bf=1.0, band=2.0, min_u=0.0, max_u=100000.0, th_dist=30, octave_tol=1):
+        super().__init__(bf, band, min_u, max_u, th_dist, octave_tol)
+
+
 class Pinhole(C.Structure):
     _fields_ = [('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float),
                 ('width', C.c_int), ('height', C.c_int), ('d', C.c_float * 5)]
@@ -312,6 +320,18 @@ def search_by_violence(params, k1, d1, k2, d2, cols2, rows2, min_level=0, max_le
     n = lib().tbo_search_by_violence(C.byref(params), _p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2),
                                      cols2, rows2, min_level, max_level, C.c_float(search_r), _p(out))
     return out[:n].copy()
+
+
+def stereo_rowband(params, kL, dL, kR, dR, inv_sf, n_rows):
+    """LocalBA.cpp:69-288 (block-commented ORB stereo matcher) -> (matches, depth[nL])."""
+    kL, kR = np.ascontiguousarray(kL, KP_DTYPE), np.ascontiguousarray(kR, KP_DTYPE)
+    dL, dR = _u8(dL), _u8(dR)
+    inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+    out = np.zeros(len(kL) + 1, MATCH_DTYPE)
+    depth = np.zeros(len(kL), np.float32)
+    n = lib().tbo_stereo_rowband(C.byref(params), _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR),
+                                 _p(inv_sf), len(inv_sf), int(n_rows), _p(out), _p(depth))
+    return out[:n].copy(), depth
 
 
 def search_by_projection(params, cam, Tcw1, k1, d1, f1_matched, sf1, cols1, rows1, k2, mp_valid, mp_xyz, mp_desc):

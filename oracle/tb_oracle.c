@@ -1281,3 +1281,58 @@ int tbo_fast_extract(const u8 *const *levels, const int *w, const int *h, const 
     free(grid);
     return err ? -1 : n;
 }
+
+/* ORB stereo row-band matcher — block-commented body of LocalBA::AddMapPointsByStereo, LocalBA.cpp:69-288 (see header). */
+int tbo_stereo_rowband(const tbo_stereo_params *p, const tbo_kp *kL, const u8 *dL, int nL,
+                       const tbo_kp *kR, const u8 *dR, int nR, const float *inv_sf, int n_levels, int n_rows,
+                       tbo_match *out, float *depth)
+{
+    /* row table (:78-93): vRowIndices[yi] lists right keys in push (= index) order */
+    int *cnt = (int *)calloc((size_t)n_rows + 1, sizeof(int));
+    int *lo = (int *)malloc(sizeof(int) * (size_t)(nR + 1)), *hi = (int *)malloc(sizeof(int) * (size_t)(nR + 1));
+    for (int iR = 0; iR < nR; iR++) {
+        const float kpY = kR[iR].y;
+        int oc = kR[iR].octave;
+        if (oc < 0) oc = 0;
+        if (oc >= n_levels) oc = n_levels - 1;
+        const float r = p->band * inv_sf[oc];
+        const float a = kpY + r, b = kpY - r;
+        int max_r = (int)ceilf(a), min_r = (int)floorf(b);
+        if (min_r < 0) min_r = 0;
+        if (max_r > n_rows - 1) max_r = n_rows - 1;
+        lo[iR] = min_r; hi[iR] = max_r;
+        for (int yi = min_r; yi <= max_r; yi++) cnt[yi + 1]++;
+    }
+    for (int y = 0; y < n_rows; y++) cnt[y + 1] += cnt[y];
+    int *items = (int *)malloc(sizeof(int) * (size_t)(cnt[n_rows] + 1));
+    int *cur = (int *)malloc(sizeof(int) * (size_t)(n_rows + 1));
+    memcpy(cur, cnt, sizeof(int) * (size_t)(n_rows + 1));
+    for (int iR = 0; iR < nR; iR++)
+        for (int yi = lo[iR]; yi <= hi[iR]; yi++) items[cur[yi]++] = iR;
+    int n = 0;
+    for (int iL = 0; iL < nL; iL++) {
+        depth[iL] = -1.0f;
+        const int levelL = kL[iL].octave;
+        const float vL = kL[iL].y, uL = kL[iL].x;
+        if (!(vL > -1.f) || vL >= (float)n_rows) continue;
+        const int row = (int)vL; /* (size_t)vL, :110 */
+        int bestDist0 = 0x7fffffff, bestIdxR0 = 0;
+        for (int k = cnt[row]; k < cnt[row + 1]; k++) {
+            const int iR = items[k];
+            if (kR[iR].octave < levelL - p->octave_tol || kR[iR].octave > levelL + p->octave_tol) continue; /* :131 */
+            const float uR = kR[iR].x;
+            if (uR >= p->min_u && uR <= p->max_u) { /* :136 */
+                const int dist = tbo_hamming256(dL + 32 * (size_t)iL, dR + 32 * (size_t)iR);
+                if (dist < bestDist0 && dist > 0) { bestDist0 = dist; bestIdxR0 = iR; } /* :140 */
+            }
+        }
+        if (bestDist0 < p->th_dist) { /* :148 */
+            out[n].queryIdx = iL; out[n].trainIdx = bestIdxR0; out[n].imgIdx = -1; out[n].distance = (float)bestDist0;
+            n++;
+            const float dx = fabsf(uL - kR[bestIdxR0].x); /* :168-171 */
+            depth[iL] = dx > 0.f ? p->bf / dx : -1.0f;
+        }
+    }
+    free(cnt); free(lo); free(hi); free(items); free(cur);
+    return n;
+}

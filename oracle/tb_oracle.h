@@ -135,6 +135,26 @@ int tbo_search_by_bow(const tbo_matcher_params *p, const tbo_kp *k1, const uint8
                       const tbo_kp *k2, const uint8_t *d2, const int32_t *node2, int n2,
                       const uint8_t *mp_valid2, int map_point_only, tbo_match *out);
 
+/* ---- ORB stereo row-band matcher (rank-3 "next" row of SURVEY.md 8f) ----
+ * Restates the block-commented body of LocalBA::AddMapPointsByStereo (src/mapping/LocalBA.cpp:69-288) as its text
+ * stands: the lines inside the block that carry their own // (SAD sub-pixel refinement :175-238, median filter
+ * :241-253) are not part of it.  Parity unpinned: the block is dead code in the reference (never compiled), so there is
+ * no reference output to pin against; tests pin this C restatement against an independent numpy restatement.
+ * current (left) frame = kL/dL, stereo (right) frame = kR/dR; inv_sf = Frame::GetInverseScaleFactors();
+ * n_rows = rows of pyramid level 0.  Row table entries outside [0, n_rows) are dropped (the reference would write out
+ * of bounds), left keys with (size_t)y >= n_rows are skipped.  depth[nL] gets bf/|xL-xR| or -1; returns the number of
+ * matches (queryIdx = iL, trainIdx = best iR, distance = Hamming), in iL order. */
+typedef struct {
+    float bf;          /* baseline * fx */
+    float band;        /* 2.f   (:87  r = 2.f * inverse scale factor of the right key's octave) */
+    float min_u, max_u;/* 0, 100000 (:117-118) */
+    int32_t th_dist;   /* 30    (:148) */
+    int32_t octave_tol;/* 1     (:131) */
+} tbo_stereo_params;
+int tbo_stereo_rowband(const tbo_stereo_params *p, const tbo_kp *kL, const uint8_t *dL, int nL,
+                       const tbo_kp *kR, const uint8_t *dR, int nR, const float *inv_sf, int n_levels, int n_rows,
+                       tbo_match *out, float *depth);
+
 typedef struct {
     float fx, fy, cx, cy;
     int width, height;

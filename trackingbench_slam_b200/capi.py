@@ -38,12 +38,22 @@ EXPORTS = [
     'tb_init_undistort_rectify_map', 'tb_undistort_create', 'tb_undistort_destroy', 'tb_undistort_image_device',
     'tb_undistort_image_host', 'tb_frontend_undistort_device', 'tb_frontend_upload_frames_undistort',
     'tb_clahe_device', 'tb_clahe_host',
+    'tb_stereo_match', 'tb_frontend_stereo_match',
 ]
 
 
 class MatcherParams(C.Structure):
     _fields_ = [('TH_LOW', C.c_int32), ('TH_HIGH', C.c_int32), ('HISTO_LENGTH', C.c_int32),
                 ('checkOrientation', C.c_int32), ('nRatio', C.c_float)]
+
+
+class StereoParams(C.Structure):
+    """tb_stereo_params; defaults = the constants of LocalBA.cpp:69-288 (bf is the caller's)."""
+    _fields_ = [('bf', C.c_float), ('band', C.c_float), ('min_u', C.c_float), ('max_u', C.c_float),
+                ('th_dist', C.c_int32), ('octave_tol', C.c_int32)]
+
+    def __init__(self, bf=1.0, band=2.0, min_u=0.0, max_u=100000.0, th_dist=30, octave_tol=1):
+        super().__init__(bf, band, min_u, max_u, th_dist, octave_tol)
 
 
 class Pinhole(C.Structure):
@@ -193,6 +203,20 @@ class Context:
                                                int(cols2), int(rows2), int(min_level), int(max_level), C.c_float(search_r),
                                                _vp(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+    def stereo_match(self, params, kL, dL, kR, dR, inv_sf, n_rows):
+        """ORB stereo row-band matcher (LocalBA.cpp:69-288) -> (matches, depth[nL])."""
+        kL = np.ascontiguousarray(kL, KP_DTYPE)
+        kR = np.ascontiguousarray(kR, KP_DTYPE)
+        dL = np.ascontiguousarray(dL, np.uint8)
+        dR = np.ascontiguousarray(dR, np.uint8)
+        inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+        out = np.zeros(len(kL) + 1, MATCH_DTYPE)
+        depth = np.zeros(len(kL), np.float32)
+        n = C.c_int()
+        self.check(lib().tb_stereo_match(self.h, C.byref(params), _vp(kL), _vp(dL), len(kL), _vp(kR), _vp(dR), len(kR),
+                                         _vp(inv_sf), len(inv_sf), int(n_rows), _vp(out), len(out), C.byref(n), _vp(depth)))
+        return out[:n.value].copy(), depth
 
     def vocab_create(self, voc):
         """voc: vocab.Vocabulary -> DeviceVocabulary (tree resident in HBM)."""
@@ -497,3 +521,14 @@ def _frontend_search_by_violence(self, params, f1_frames, f2_frames, min_level, 
 
 
 Frontend.search_by_violence = _frontend_search_by_violence
+
+
+def _frontend_stereo_match(self, params, left_frames, right_frames, inv_sf, matches_dptr, capacity, counts_dptr, depth_dptr=None):
+    fl = np.ascontiguousarray(left_frames, np.int32)
+    fr = np.ascontiguousarray(right_frames, np.int32)
+    inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+    self.ctx.check(lib().tb_frontend_stereo_match(self.h, C.byref(params), len(fl), _vp(fl), _vp(fr), _vp(inv_sf), _vp(matches_dptr),
+                                                  int(capacity), _vp(counts_dptr), _vp(depth_dptr)))
+
+
+Frontend.stereo_match = _frontend_stereo_match

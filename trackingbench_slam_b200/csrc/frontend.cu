@@ -698,6 +698,17 @@ extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_
                                       fe->g[0].w, fe->g[0].h, min_level, max_level, search_r, (tb_match *)matches, capacity, (int *)counts);
 }
 
+extern "C" int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames,
+                                        const int32_t *right_frames, const float *inv_sf, void *matches, int capacity,
+                                        void *counts, void *depth)
+{
+    if (!fe || !p || n_pairs < 0 || !left_frames || !right_frames || !inv_sf || !matches || !counts || capacity < 0) return TB_E_INVALID;
+    for (int i = 0; i < n_pairs; i++)
+        if (left_frames[i] < 0 || left_frames[i] >= fe->B || right_frames[i] < 0 || right_frames[i] >= fe->B) return TB_E_INVALID;
+    return tb_window_stereo_batched(fe->ctx, p, n_pairs, left_frames, right_frames, fe->kps, fe->desc, fe->kp_cap, fe->n_kp, inv_sf, fe->L,
+                                    fe->g[0].h, (tb_match *)matches, capacity, (int *)counts, (float *)depth);
+}
+
 extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matcher_params *p, const tb_pinhole *cam, int n_pairs,
                                                 const int32_t *f1_frames, const int32_t *f2_frames, const float *Tcw1,
                                                 const void *f1_matched, const void *mp_valid, const void *mp_xyz,

@@ -72,6 +72,9 @@ int tb_window_set_bow_batched(tb_ctx *ctx, const tb_vocab *v, int n_frames, int 
 int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames, int n_frames,
                           const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const int32_t *node,
                           const uint8_t *mp_valid, int map_point_only, tb_match *matches, int capacity, int *out_counts);
+int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames, const int32_t *right_frames,
+                             const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const float *inv_sf, int n_levels,
+                             int n_rows, tb_match *matches, int capacity, int *out_counts, float *depth);
 int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames,
                                int n_frames, const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, int cols, int rows,
                                int min_level, int max_level, float search_r, tb_match *matches, int capacity, int *out_counts);

@@ -1179,6 +1179,205 @@ int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pa
     return TB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ORB stereo row-band matcher: the block-commented body of LocalBA::AddMapPointsByStereo
+// (src/mapping/LocalBA.cpp:69-288).  One CTA per (left, right) frame pair.  The reference's row table lists a right key
+// under every row of [floor(y-r), ceil(y+r)]; here each right key is counting-sorted ONCE by floor(y) in shared memory
+// with its row interval packed beside it, and a left key on row v scans the bins [v-R, v+R] (one contiguous range of the
+// sorted list) testing the interval — same candidate set, one entry per key instead of up to 2r+2.  First-minimum
+// (`dist < best`, candidates in index order) = minimum of the key dist<<16 | iR, so the scan order is free.
+struct StereoSf { float inv[TB_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(512)
+stereo_rowband_batched(const ProjPair *__restrict__ pairs, const tb_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc,
+                       int kp_cap, const int *__restrict__ counts, StereoSf sf, int n_levels, int n_rows, int R, tb_stereo_params p,
+                       tb_match *__restrict__ matches, int capacity, int *__restrict__ out_counts, float *__restrict__ depth)
+{
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    int *start = reinterpret_cast<int *>(st_smem);                 // [n_rows + 1] bin starts (after the scan)
+    int *cur = start + (n_rows + 1);                               // [n_rows + 1] counts, then fill cursors
+    uint2 *ent = reinterpret_cast<uint2 *>(cur + (n_rows + 1));                               // [kp_cap] (2(n_rows+1) ints before it: 8-byte aligned)
+    __shared__ int warp_sum[16];
+    __shared__ int s_base;
+    const ProjPair pr = pairs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nL = min(counts[pr.f1], kp_cap), nR = min(counts[pr.f2], kp_cap);
+    const tb_keypoint *kL = kps + (size_t)pr.f1 * kp_cap, *kR = kps + (size_t)pr.f2 * kp_cap;
+    const uint8_t *dL = desc + (size_t)pr.f1 * kp_cap * 32, *dR = desc + (size_t)pr.f2 * kp_cap * 32;
+
+    for (int i = tid; i <= n_rows; i += 512) cur[i] = 0;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 512) {
+        const float y = __ldg(&kR[i].y);
+        const int b = min(max((int)floorf(y), 0), n_rows - 1);
+        atomicAdd(&cur[b], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cur[0..n_rows) -> start[0..n_rows]: a serial chunk per thread, warp scans over the chunk sums
+    {
+        const int per = (n_rows + 511) / 512, b0 = min(tid * per, n_rows), b1 = min(b0 + per, n_rows);
+        int sum = 0;
+        for (int i = b0; i < b1; i++) sum += cur[i];
+        int inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) warp_sum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int v = lane < 16 ? warp_sum[lane] : 0, w = v;
+            for (int o = 1; o < 16; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+            if (lane < 16) warp_sum[lane] = w - v;
+        }
+        __syncthreads();
+        int run = warp_sum[wid] + inc - sum;
+        for (int i = b0; i < b1; i++) { const int c = cur[i]; start[i] = run; cur[i] = run; run += c; }
+        if (tid == 511) start[n_rows] = run;   // thread 511 owns the tail (b1 == n_rows), run == nR
+    }
+    __syncthreads();
+    for (int i = tid; i < nR; i += 512) {
+        const float y = __ldg(&kR[i].y), x = __ldg(&kR[i].x);
+        const int oc = __ldg(&kR[i].octave);
+        const float r = __fmul_rn(p.band, sf.inv[min(max(oc, 0), n_levels - 1)]);
+        int max_r = (int)ceilf(__fadd_rn(y, r)), min_r = (int)floorf(__fsub_rn(y, r));   // LocalBA.cpp:87-89
+        min_r = max(min_r, 0); max_r = min(max_r, n_rows - 1);
+        const int b = min(max((int)floorf(y), 0), n_rows - 1);
+        const int ok = (x >= p.min_u && x <= p.max_u && min_r <= max_r) ? 1 : 0;         // :136
+        const int slot = atomicAdd(&cur[b], 1);
+        ent[slot] = make_uint2((uint32_t)i | ((uint32_t)(oc & 0x7f) << 16) | ((uint32_t)ok << 24) | (oc < 0 || oc > 127 ? 0x80000000u : 0u),
+                               (uint32_t)max(min_r, 0) | ((uint32_t)max(max_r, 0) << 16));
+    }
+    __syncthreads();
+
+    tb_match *out = matches + (size_t)blockIdx.x * capacity;
+    float *dep = depth ? depth + (size_t)blockIdx.x * kp_cap : nullptr;
+    for (int i0 = 0; i0 < nL; i0 += 512) {
+        const int iL = i0 + tid;
+        uint32_t best = 0xFFFFFFFFu;
+        float uL = 0.f;
+        if (iL < nL) {
+            const float vL = __ldg(&kL[iL].y);
+            uL = __ldg(&kL[iL].x);
+            const int levelL = __ldg(&kL[iL].octave);
+            if (vL > -1.f && vL < (float)n_rows) {
+                const int row = (int)vL;                                                   // (size_t)vL, :110
+                const int e0 = start[max(row - R, 0)], e1 = start[min(row + R, n_rows - 1) + 1];
+                uint32_t q[8];
+                {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(dL + (size_t)iL * 32)), b = __ldg(reinterpret_cast<const uint4 *>(dL + (size_t)iL * 32) + 1);
+                    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+                }
+                for (int e = e0; e < e1; e++) {
+                    const uint2 en = ent[e];
+                    const int lo = en.y & 0xffff, hi = en.y >> 16;
+                    if (row < lo || row > hi || !(en.x & 0x01000000u)) continue;
+                    if (!(en.x & 0x80000000u)) {
+                        const int oc = (en.x >> 16) & 0x7f;
+                        if (oc < levelL - p.octave_tol || oc > levelL + p.octave_tol) continue;   // :131
+                    } else {
+                        const int oc = __ldg(&kR[en.x & 0xffff].octave);
+                        if (oc < levelL - p.octave_tol || oc > levelL + p.octave_tol) continue;
+                    }
+                    const int iR = en.x & 0xffff;
+                    const int d = ham256_g(q, dR + (size_t)iR * 32);
+                    if (d > 0) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);       // :140
+                }
+            }
+        }
+        const int hit = (iL < nL) && (int)(best >> 16) < p.th_dist;                         // :148
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_sum[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base + __popc(bal & ((1u << lane) - 1));
+        for (int w = 0; w < wid; w++) off += warp_sum[w];
+        if (iL < nL) {
+            float dz = -1.0f;
+            if (hit) {
+                const int iR = best & 0xffff;
+                const float dx = fabsf(__fsub_rn(uL, __ldg(&kR[iR].x)));                    // :168-171
+                if (dx > 0.f) dz = __fdiv_rn(p.bf, dx);
+                if (off < capacity) { tb_match mt = {iL, iR, -1, (float)(best >> 16)}; out[off] = mt; }
+            }
+            if (dep) dep[iL] = dz;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 16; w++) t += warp_sum[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (dep) for (int i = nL + tid; i < kp_cap; i += 512) dep[i] = -1.0f;
+    if (tid == 0) out_counts[blockIdx.x] = s_base;
+}
+
+int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames, const int32_t *right_frames,
+                             const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const float *inv_sf, int n_levels,
+                             int n_rows, tb_match *matches, int capacity, int *out_counts, float *depth)
+{
+    if (n_pairs <= 0) return TB_OK;
+    if (kp_cap > 65535) return tb_fail(ctx, TB_E_UNSUPPORTED, "stereo row-band matcher supports up to 65535 keypoints per frame");
+    if (n_levels < 1 || n_levels > TB_MAX_LEVELS || n_rows < 1 || n_rows > 65535) return tb_fail(ctx, TB_E_UNSUPPORTED, "stereo row-band matcher: 1..16 levels, 1..65535 rows");
+    if (!(p->band >= 0.f) || p->th_dist > 257) return tb_fail(ctx, TB_E_INVALID, "stereo row-band matcher: band >= 0, th_dist <= 257");
+    StereoSf sf;
+    float rmax = 0.f;
+    for (int l = 0; l < n_levels; l++) { sf.inv[l] = inv_sf[l]; volatile float r = p->band * inv_sf[l]; if (r > rmax) rmax = r; }
+    if (!(rmax < 32768.f)) return tb_fail(ctx, TB_E_INVALID, "stereo row-band matcher: band * inverse scale factor out of range");
+    const int R = (int)ceilf(rmax) + 1;
+    const size_t smem = sizeof(int) * (2 * (size_t)(n_rows + 1) + 1) + sizeof(uint2) * (size_t)kp_cap;
+    if (smem > 200 * 1024) return tb_fail(ctx, TB_E_UNSUPPORTED, "stereo row-band matcher: rows*8 + keypoint capacity*8 must fit 200 KB of shared memory");
+    int rc = win_ws_reserve(ctx, 0, n_pairs, kp_cap, false);
+    if (rc) return rc;
+    WinWs &w = *ctx->wws;
+    std::vector<ProjPair> hp(n_pairs);
+    memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
+    for (int i = 0; i < n_pairs; i++) { hp[i].f1 = left_frames[i]; hp[i].f2 = right_frames[i]; }
+    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    static bool attr_set = false;
+    if (!attr_set) { TB_CUDA(ctx, cudaFuncSetAttribute(stereo_rowband_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    {
+        ProfScope prof__(ctx, "stereo_rowband_batched");
+        stereo_rowband_batched<<<n_pairs, 512, smem, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, sf, n_levels, n_rows, R, *p,
+                                                                     matches, capacity, out_counts, depth);
+        TB_LAUNCH_CHECK(ctx);
+    }
+    return TB_OK;
+}
+
+// Host-buffer form: left keys/descriptors become frame 0, right ones frame 1 of a temporary two-frame layout.
+extern "C" int tb_stereo_match(tb_ctx *ctx, const tb_stereo_params *p, const tb_keypoint *kL, const uint8_t *dL, int nL,
+                               const tb_keypoint *kR, const uint8_t *dR, int nR, const float *inv_sf, int n_levels, int n_rows,
+                               tb_match *out, int capacity, int *n, float *depth)
+{
+    if (!ctx || !p || nL < 0 || nR < 0 || (nL && (!kL || !dL)) || (nR && (!kR || !dR)) || !inv_sf || !n || capacity < 0 || (capacity && !out)) return TB_E_INVALID;
+    *n = 0;
+    if (nL == 0) return TB_OK;
+    const int cap = std::max(std::max(nL, nR), 1);
+    DevBuf buf;
+    tb_keypoint *d_k = buf.alloc<tb_keypoint>(2 * (size_t)cap);
+    uint8_t *d_d = buf.alloc<uint8_t>(64 * (size_t)cap);
+    int *d_cnt = buf.alloc<int>(3);
+    tb_match *d_m = buf.alloc<tb_match>(nL);
+    float *d_z = buf.alloc<float>(cap);
+    if (!d_k || !d_d || !d_cnt || !d_m || !d_z) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    const int cnt[2] = {nL, nR};
+    TB_CUDA(ctx, cudaMemcpyAsync(d_k, kL, sizeof(tb_keypoint) * nL, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(d_d, dL, 32 * (size_t)nL, cudaMemcpyHostToDevice, ctx->stream));
+    if (nR) {
+        TB_CUDA(ctx, cudaMemcpyAsync(d_k + cap, kR, sizeof(tb_keypoint) * nR, cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaMemcpyAsync(d_d + 32 * (size_t)cap, dR, 32 * (size_t)nR, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TB_CUDA(ctx, cudaMemcpyAsync(d_cnt, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    const int32_t f1 = 0, f2 = 1;
+    int rc = tb_window_stereo_batched(ctx, p, 1, &f1, &f2, d_k, d_d, cap, d_cnt, inv_sf, n_levels, n_rows, d_m, nL, d_cnt + 2, d_z);
+    if (rc) return rc;
+    int m = 0;
+    TB_CUDA(ctx, cudaMemcpyAsync(&m, d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = m;
+    const int take = std::min(m, capacity);
+    if (take > 0) TB_CUDA(ctx, cudaMemcpy(out, d_m, sizeof(tb_match) * take, cudaMemcpyDeviceToHost));
+    if (depth) TB_CUDA(ctx, cudaMemcpy(depth, d_z, sizeof(float) * nL, cudaMemcpyDeviceToHost));
+    return m > capacity ? tb_fail(ctx, TB_E_CAPACITY, "stereo match buffer too small") : TB_OK;
+}
+
 void tb_window_ws_free(tb_ctx *ctx)
 {
     if (!ctx->wws) return;
