@@ -311,6 +311,36 @@ int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_p
                              const int32_t *right_frames, const float *inv_sf, void *matches_dptr, int capacity,
                              void *counts_i32_dptr, void *depth_f32_dptr);
 
+/* Pyramidal Lucas-Kanade tracking = the cv::calcOpticalFlowPyrLK(img2, img1, F2->GetCVKeys(), cur_points, status, err,
+ * cv::Size(21,21), 3) call of Matcher::searchByOPFlow (src/matchers/matcher.cpp:745): OpenCV's fixed-point patches and
+ * stop rules; the 2x2 sums are exact integers (OpenCV's SIMD build sums them in float lanes), so results agree with
+ * OpenCV within a tolerance (tests/test_oracle_cv2.py) and with the oracle bit for bit. status = 1 where the track is
+ * valid; err = OpenCV's mean absolute patch difference / 32. rejectWithF (RANSAC, matcher.cpp:751-755) is not included. */
+typedef struct {
+    int32_t win;       /* reference: 21 (3..21) */
+    int32_t max_level; /* reference: 3 */
+    int32_t max_iter;  /* OpenCV default TermCriteria: 30 */
+    float eps;         /* OpenCV default: 0.01 */
+    float min_eig;     /* OpenCV default minEigThreshold: 1e-4 */
+} tb_lk_params;
+/* Host in/out, one image pair: prev_xy/next_xy are n x 2 floats, status n bytes, err n floats (may be NULL). */
+int tb_lk_flow_host(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, const uint8_t *next, int w, int h, size_t stride,
+                    const float *prev_xy, int n, float *next_xy, uint8_t *status, float *err);
+/* Device, batched: two stacks of w x h images (frame f at base + f*frame_stride; the stacks may be the same memory);
+ * pair q tracks the points pts[q][0..counts[q]) (float2, pts_cap per pair, counts on the device) from image
+ * prev_idx[q] of the first stack into image next_idx[q] of the second. Outputs [pair][pts_cap]. */
+int tb_lk_flow_device(tb_ctx *ctx, const tb_lk_params *p, const void *prev_dptr, size_t prev_pitch, size_t prev_frame_stride, int n_prev,
+                      const void *next_dptr, size_t next_pitch, size_t next_frame_stride, int n_next, int w, int h,
+                      int n_pairs, const int32_t *prev_idx, const int32_t *next_idx, const void *pts_f32x2_dptr,
+                      const void *counts_i32_dptr, int pts_cap, void *next_pts_f32x2_dptr, void *status_u8_dptr, void *err_f32_dptr);
+/* Matcher::searchByOPFlow(F1, F2, cur_points, equalized, reject=false) (matcher.cpp:724-768) over frames [0, n_frames) of
+ * the frontend (level 0 resident, keypoints from the last extract): pair q tracks the keypoints of frame f2_frames[q] into
+ * frame f1_frames[q] (CLAHE'd first when equalized), then clears status where IsInFrame(Vector2i(pt)) fails (:747-749).
+ * The reference's match list is {i,i} for every status[i] != 0. Outputs on the device, [pair][tb_frontend_kp_capacity()]. */
+int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_frames, int n_pairs, const int32_t *f1_frames,
+                                 const int32_t *f2_frames, int equalized, void *next_pts_f32x2_dptr, void *status_u8_dptr,
+                                 void *err_f32_dptr);
+
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
  * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */

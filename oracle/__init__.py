@@ -322,6 +322,34 @@ def search_by_violence(params, k1, d1, k2, d2, cols2, rows2, min_level=0, max_le
     return out[:n].copy()
 
 
+class LKParams(C.Structure):
+    _fields_ = [('win', C.c_int), ('max_level', C.c_int), ('max_iter', C.c_int), ('eps', C.c_float), ('min_eig', C.c_float)]
+
+    def __init__(self, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=1e-4):
+        super().__init__(win, max_level, max_iter, eps, min_eig)
+
+
+def pyrdown(img):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().tbo_pyrdown_u8(_p(img), w, h, img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def lk_flow(params, prev, nxt, pts):
+    """cv::calcOpticalFlowPyrLK(prev, next, pts, ..., Size(21,21), 3) as Matcher::searchByOPFlow calls it
+    (matcher.cpp:745) -> (next_pts [n,2] f32, status [n] u8, err [n] f32)."""
+    prev, nxt = _u8(prev), _u8(nxt)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    h, w = prev.shape
+    out = np.zeros_like(pts)
+    st = np.zeros(len(pts), np.uint8)
+    err = np.zeros(len(pts), np.float32)
+    lib().tbo_lk_flow(C.byref(params), _p(prev), _p(nxt), w, h, prev.strides[0], _p(pts), len(pts), _p(out), _p(st), _p(err))
+    return out, st, err
+
+
 def stereo_rowband(params, kL, dL, kR, dR, inv_sf, n_rows):
     """LocalBA.cpp:69-288 (block-commented ORB stereo matcher) -> (matches, depth[nL])."""
     kL, kR = np.ascontiguousarray(kL, KP_DTYPE), np.ascontiguousarray(kR, KP_DTYPE)

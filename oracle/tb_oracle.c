@@ -1336,3 +1336,169 @@ int tbo_stereo_rowband(const tbo_stereo_params *p, const tbo_kp *kL, const u8 *d
     free(cnt); free(lo); free(hi); free(items); free(cur);
     return n;
 }
+
+/* ---- cv::pyrDown 8UC1 (imgproc/pyramids.cpp): 1-4-6-4-1 both ways in int, (v + 128) >> 8, BORDER_REFLECT_101 ---- */
+void tbo_pyrdown_u8(const u8 *src, int w, int h, int sstride, u8 *dst, int dstride)
+{
+    const int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    int *rows = (int *)malloc(sizeof(int) * (size_t)dw * 5);
+    for (int y = 0; y < dh; y++) {
+        for (int k = 0; k < 5; k++) {
+            const u8 *r = src + (size_t)reflect101(2 * y - 2 + k, h) * sstride;
+            int *o = rows + (size_t)k * dw;
+            for (int x = 0; x < dw; x++)
+                o[x] = r[reflect101(2 * x, w)] * 6 + (r[reflect101(2 * x - 1, w)] + r[reflect101(2 * x + 1, w)]) * 4 +
+                       r[reflect101(2 * x - 2, w)] + r[reflect101(2 * x + 2, w)];
+        }
+        for (int x = 0; x < dw; x++) {
+            const int v = rows[2 * dw + x] * 6 + (rows[dw + x] + rows[3 * dw + x]) * 4 + rows[x] + rows[4 * dw + x];
+            dst[(size_t)y * dstride + x] = (u8)((v + 128) >> 8);
+        }
+    }
+    free(rows);
+}
+
+/* ---- cv::calcOpticalFlowPyrLK (video/lkpyramid.cpp), 8UC1, flags 0 ---- */
+typedef struct { const u8 *p; int w, h, stride; } lk_img;
+static inline int lk_px(const lk_img *im, int x, int y) /* pyramid level with its REFLECT_101 border */
+{
+    return im->p[(size_t)reflect101(y, im->h) * im->stride + reflect101(x, im->w)];
+}
+/* calcSharrDeriv at (x,y) inside the level; the derivative image has a zero (BORDER_CONSTANT) border */
+static inline void lk_scharr(const lk_img *im, int x, int y, int *dx, int *dy)
+{
+    if (x < 0 || y < 0 || x >= im->w || y >= im->h) { *dx = *dy = 0; return; }
+    int t0[3], t1[3];
+    for (int k = 0; k < 3; k++) {
+        const int xx = x + k - 1;
+        const int a = lk_px(im, xx, y - 1), b = lk_px(im, xx, y), c = lk_px(im, xx, y + 1);
+        t0[k] = (a + c) * 3 + b * 10;
+        t1[k] = c - a;
+    }
+    *dx = t0[2] - t0[0];
+    *dy = (t1[2] + t1[0]) * 3 + t1[1] * 10;
+}
+#define LK_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+int tbo_lk_flow(const tbo_lk_params *p, const u8 *prev, const u8 *next, int w, int h, int stride,
+                const float *prev_xy, int n, float *next_xy, u8 *status, float *err)
+{
+    const int win = p->win;
+    lk_img I[16], J[16];
+    u8 *own[32];
+    int n_own = 0, maxLevel = 0;
+    I[0].p = prev; I[0].w = w; I[0].h = h; I[0].stride = stride;
+    J[0].p = next; J[0].w = w; J[0].h = h; J[0].stride = stride;
+    for (int l = 1; l <= p->max_level && l < 16; l++) { /* buildOpticalFlowPyramid */
+        const int lw = (I[l - 1].w + 1) / 2, lh = (I[l - 1].h + 1) / 2;
+        if (lw <= win || lh <= win) break;
+        for (int k = 0; k < 2; k++) {
+            lk_img *P = k ? J : I;
+            u8 *b = (u8 *)malloc((size_t)lw * lh);
+            tbo_pyrdown_u8(P[l - 1].p, P[l - 1].w, P[l - 1].h, P[l - 1].stride, b, lw);
+            P[l].p = b; P[l].w = lw; P[l].h = lh; P[l].stride = lw;
+            own[n_own++] = b;
+        }
+        maxLevel = l;
+    }
+    int maxCount = p->max_iter;
+    if (maxCount < 0) maxCount = 0;
+    if (maxCount > 100) maxCount = 100;
+    double epsilon = (double)p->eps;
+    if (epsilon < 0.) epsilon = 0.;
+    if (epsilon > 10.) epsilon = 10.;
+    epsilon *= epsilon;
+    const float halfWin = (float)(win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    short *Ibuf = (short *)malloc(sizeof(short) * (size_t)win * win * 3);
+    short *dIx = Ibuf + win * win, *dIy = dIx + win * win;
+    for (int i = 0; i < n; i++) { status[i] = 1; if (err) err[i] = 0.f; }
+    for (int level = maxLevel; level >= 0; level--) {
+        const lk_img *Il = &I[level], *Jl = &J[level];
+        for (int i = 0; i < n; i++) {
+            const float sc = (float)(1. / (1 << level));
+            float px = prev_xy[2 * i] * sc, py = prev_xy[2 * i + 1] * sc, nx, ny;
+            if (level == maxLevel) { nx = px; ny = py; }
+            else { nx = next_xy[2 * i] * 2.f; ny = next_xy[2 * i + 1] * 2.f; }
+            next_xy[2 * i] = nx; next_xy[2 * i + 1] = ny;
+            px -= halfWin; py -= halfWin;
+            const int ipx = cv_floor_f(px), ipy = cv_floor_f(py);
+            if (ipx < -win || ipx >= Il->w || ipy < -win || ipy >= Il->h) {
+                if (level == 0) { status[i] = 0; if (err) err[i] = 0.f; }
+                continue;
+            }
+            float a = px - (float)ipx, b = py - (float)ipy;
+            int iw00 = cv_round_f((1.f - a) * (1.f - b) * (float)(1 << 14)), iw01 = cv_round_f(a * (1.f - b) * (float)(1 << 14)),
+                iw10 = cv_round_f((1.f - a) * b * (float)(1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
+            int64_t iA11 = 0, iA12 = 0, iA22 = 0;
+            for (int y = 0; y < win; y++)
+                for (int x = 0; x < win; x++) {
+                    const int X = ipx + x, Y = ipy + y;
+                    int dx00, dy00, dx01, dy01, dx10, dy10, dx11, dy11;
+                    lk_scharr(Il, X, Y, &dx00, &dy00); lk_scharr(Il, X + 1, Y, &dx01, &dy01);
+                    lk_scharr(Il, X, Y + 1, &dx10, &dy10); lk_scharr(Il, X + 1, Y + 1, &dx11, &dy11);
+                    const int ival = LK_DESCALE(lk_px(Il, X, Y) * iw00 + lk_px(Il, X + 1, Y) * iw01 + lk_px(Il, X, Y + 1) * iw10 + lk_px(Il, X + 1, Y + 1) * iw11, 9);
+                    const int ixval = LK_DESCALE(dx00 * iw00 + dx01 * iw01 + dx10 * iw10 + dx11 * iw11, 14);
+                    const int iyval = LK_DESCALE(dy00 * iw00 + dy01 * iw01 + dy10 * iw10 + dy11 * iw11, 14);
+                    Ibuf[y * win + x] = (short)ival; dIx[y * win + x] = (short)ixval; dIy[y * win + x] = (short)iyval;
+                    iA11 += (int64_t)ixval * ixval; iA12 += (int64_t)ixval * iyval; iA22 += (int64_t)iyval * iyval;
+                }
+            const float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
+            float D = A11 * A22 - A12 * A12;
+            const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+            if ((double)minEig < (double)p->min_eig || D < 1.1920929e-07f) {
+                if (level == 0) status[i] = 0;
+                continue;
+            }
+            D = 1.f / D;
+            nx -= halfWin; ny -= halfWin;
+            float pdx = 0.f, pdy = 0.f;
+            for (int j = 0; j < maxCount; j++) {
+                const int inx = cv_floor_f(nx), iny = cv_floor_f(ny);
+                if (inx < -win || inx >= Jl->w || iny < -win || iny >= Jl->h) {
+                    if (level == 0) status[i] = 0;
+                    break;
+                }
+                a = nx - (float)inx; b = ny - (float)iny;
+                iw00 = cv_round_f((1.f - a) * (1.f - b) * (float)(1 << 14)); iw01 = cv_round_f(a * (1.f - b) * (float)(1 << 14));
+                iw10 = cv_round_f((1.f - a) * b * (float)(1 << 14)); iw11 = (1 << 14) - iw00 - iw01 - iw10;
+                int64_t ib1 = 0, ib2 = 0;
+                for (int y = 0; y < win; y++)
+                    for (int x = 0; x < win; x++) {
+                        const int X = inx + x, Y = iny + y;
+                        const int diff = LK_DESCALE(lk_px(Jl, X, Y) * iw00 + lk_px(Jl, X + 1, Y) * iw01 + lk_px(Jl, X, Y + 1) * iw10 + lk_px(Jl, X + 1, Y + 1) * iw11, 9) - Ibuf[y * win + x];
+                        ib1 += (int64_t)diff * dIx[y * win + x]; ib2 += (int64_t)diff * dIy[y * win + x];
+                    }
+                const float b1 = (float)ib1 * FLT_SCALE, b2 = (float)ib2 * FLT_SCALE;
+                const float ddx = (A12 * b2 - A22 * b1) * D, ddy = (A12 * b1 - A11 * b2) * D;
+                nx += ddx; ny += ddy;
+                next_xy[2 * i] = nx + halfWin; next_xy[2 * i + 1] = ny + halfWin;
+                if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= epsilon) break;
+                if (j > 0 && fabs((double)(ddx + pdx)) < 0.01 && fabs((double)(ddy + pdy)) < 0.01) {
+                    next_xy[2 * i] -= ddx * 0.5f; next_xy[2 * i + 1] -= ddy * 0.5f;
+                    break;
+                }
+                pdx = ddx; pdy = ddy;
+            }
+            if (status[i] && level == 0) { /* the reference passes `err`, so the final window check runs */
+                const float fx = next_xy[2 * i] - halfWin, fy = next_xy[2 * i + 1] - halfWin;
+                const int inx = cv_floor_f(fx), iny = cv_floor_f(fy);
+                if (inx < -win || inx >= Jl->w || iny < -win || iny >= Jl->h) { status[i] = 0; continue; }
+                a = fx - (float)inx; b = fy - (float)iny;
+                iw00 = cv_round_f((1.f - a) * (1.f - b) * (float)(1 << 14)); iw01 = cv_round_f(a * (1.f - b) * (float)(1 << 14));
+                iw10 = cv_round_f((1.f - a) * b * (float)(1 << 14)); iw11 = (1 << 14) - iw00 - iw01 - iw10;
+                float errval = 0.f;
+                for (int y = 0; y < win; y++)
+                    for (int x = 0; x < win; x++) {
+                        const int X = inx + x, Y = iny + y;
+                        const int diff = LK_DESCALE(lk_px(Jl, X, Y) * iw00 + lk_px(Jl, X + 1, Y) * iw01 + lk_px(Jl, X, Y + 1) * iw10 + lk_px(Jl, X + 1, Y + 1) * iw11, 9) - Ibuf[y * win + x];
+                        errval += fabsf((float)diff);
+                    }
+                if (err) err[i] = errval * 1.f / (float)(32 * win * win);
+            }
+        }
+    }
+    free(Ibuf);
+    for (int k = 0; k < n_own; k++) free(own[k]);
+    return maxLevel;
+}

@@ -135,6 +135,25 @@ int tbo_search_by_bow(const tbo_matcher_params *p, const tbo_kp *k1, const uint8
                       const tbo_kp *k2, const uint8_t *d2, const int32_t *node2, int n2,
                       const uint8_t *mp_valid2, int map_point_only, tbo_match *out);
 
+/* ---- pyramidal Lucas-Kanade flow (second half of SURVEY.md 8f rank 3) ----
+ * Matcher::searchByOPFlow (matcher.cpp:724-768) calls cv::calcOpticalFlowPyrLK(img2, img1, keys, pts, status, err,
+ * Size(21,21), 3) (:745).  The arithmetic lives in OpenCV (un-vendored dependency): restated from its published
+ * algorithm (video/lkpyramid.cpp: pyrDown pyramid with REFLECT_101 border, Scharr derivatives with zero border,
+ * 14-bit fixed-point bilinear patches, iterative 2x2 solve) and pinned against cv2 4.13 in tests/test_oracle_cv2.py:
+ * pyrDown bit-exact; points within a stated tolerance (cv2's SIMD build accumulates the 2x2 system in float lanes, this
+ * restatement in exact integers, so borderline iteration stops may differ). */
+void tbo_pyrdown_u8(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride); /* dst (w+1)/2 x (h+1)/2 */
+typedef struct {
+    int32_t win;       /* 21 (square window) */
+    int32_t max_level; /* 3 */
+    int32_t max_iter;  /* 30 (TermCriteria default) */
+    float eps;         /* 0.01 */
+    float min_eig;     /* 1e-4 */
+} tbo_lk_params;
+/* prev_xy/next_xy: n x 2 floats; status n bytes; err n floats (may be NULL). Returns the number of pyramid levels - 1. */
+int tbo_lk_flow(const tbo_lk_params *p, const uint8_t *prev, const uint8_t *next, int w, int h, int stride,
+                const float *prev_xy, int n, float *next_xy, uint8_t *status, float *err);
+
 /* ---- ORB stereo row-band matcher (rank-3 "next" row of SURVEY.md 8f) ----
  * Restates the block-commented body of LocalBA::AddMapPointsByStereo (src/mapping/LocalBA.cpp:69-288) as its text
  * stands: the lines inside the block that carry their own // (SAD sub-pixel refinement :175-238, median filter

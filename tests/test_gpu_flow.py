@@ -1,0 +1,89 @@
+"""GPU parity tests of the pyramidal Lucas-Kanade tracker (Matcher::searchByOPFlow's cv::calcOpticalFlowPyrLK call,
+matcher.cpp:745) through the C ABI against the oracle.  The 2x2 sums are exact integers on both sides
+and every float step is one IEEE operation in the same order, so points, status and err must be bit-identical (tolerance
+0); the oracle itself is pinned to cv2 within the tolerance stated in tests/test_oracle_cv2.py."""
+import numpy as np
+import pytest
+import torch
+
+from .conftest import PARAM_SETS
+from .test_oracle_cv2 import lk_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('params', [dict(), dict(max_level=0), dict(max_level=5, win=15), dict(win=9, max_iter=5, eps=0.03), dict(min_eig=1e-2)])
+def test_lk_host_entry_vs_oracle(tb, ctx, oracle, images, params):
+    for name, prev, nxt, pts in lk_inputs(images):
+        en, es, ee = oracle.lk_flow(oracle.LKParams(**params), prev, nxt, pts)
+        n, s, e = ctx.lk_flow(tb.LKParams(**params), prev, nxt, pts)
+        assert (s == es).all(), (name, params)
+        assert n.tobytes() == en.tobytes(), (name, params, np.abs(n - en).max())
+        assert e.tobytes() == ee.tobytes(), (name, params)
+        if name != 'flat':
+            assert s.sum() > len(pts) // 4
+
+
+def test_lk_close_to_cv2(tb, ctx, images):
+    import cv2
+    name, prev, nxt, pts = lk_inputs(images)[0]
+    n, s, e = ctx.lk_flow(tb.LKParams(), prev, nxt, pts)
+    n1, s1, e1 = cv2.calcOpticalFlowPyrLK(prev, nxt, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+    n1, s1 = n1.reshape(-1, 2), s1.ravel()
+    ok = (s == 1) & (s1 == 1)
+    d = np.abs(n - n1).max(1)[ok]
+    assert (s == s1).mean() >= 0.99 and (d <= 0.05).mean() >= 0.98 and np.median(d) <= 1e-3
+
+
+def test_lk_device_batched_and_frontend_opflow(tb, ctx, oracle, images):
+    """tb_lk_flow_device on stacks + tb_frontend_search_by_opflow (CLAHE'd current frame, IsInFrame filter)."""
+    from trackingbench_slam_b200.synth import synth_frame
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    s2 = synth_frame(2, W, H)
+    frames = np.stack([images['left'], images['right'], s2, np.roll(s2, 2, axis=1)])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=4, max_target=tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(4)
+        fe.extract(4, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(4)
+        cap = fe.kp_cap
+        pairs = [(1, 0), (0, 1), (3, 2), (2, 2)]          # (F1 = current, F2 = previous with keys)
+        for eq in (0, 1):
+            pts = torch.zeros((len(pairs), cap, 2), dtype=torch.float32, device='cuda')
+            st = torch.zeros((len(pairs), cap), dtype=torch.uint8, device='cuda')
+            er = torch.zeros((len(pairs), cap), dtype=torch.float32, device='cuda')
+            fe.search_by_opflow(tb.LKParams(), 4, [q[0] for q in pairs], [q[1] for q in pairs], eq, pts.data_ptr(), st.data_ptr(), er.data_ptr())
+            ctx.sync()
+            P, S, E = pts.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy()
+            tracked = 0
+            for i, (f1, f2) in enumerate(pairs):
+                n2 = counts[f2]
+                img1 = oracle.clahe(frames[f1], 3.0, (8, 8)) if eq else frames[f1]
+                kp = np.stack([kps[f2, :n2]['x'], kps[f2, :n2]['y']], 1)
+                en, es, ee = oracle.lk_flow(oracle.LKParams(), frames[f2], img1, kp)
+                xi, yi = en[:, 0].astype(np.int32), en[:, 1].astype(np.int32)          # matcher.cpp:747-749
+                es = es & ((xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)).astype(np.uint8)
+                assert (S[i, :n2] == es).all() and (S[i, n2:] == 0).all(), (eq, i)
+                assert P[i, :n2].tobytes() == en.tobytes() and E[i, :n2].tobytes() == ee.tobytes(), (eq, i)
+                tracked += int(es.sum())
+            assert tracked > 500
+        # the generic device entry on the same stacks: float2 points per pair
+        base, pitch, fstride = fe.level_layout(0)
+        n0 = int(counts[0])
+        pin = torch.zeros((2, cap, 2), dtype=torch.float32, device='cuda')
+        pin[0, :n0] = torch.from_numpy(np.stack([kps[0, :n0]['x'], kps[0, :n0]['y']], 1)).cuda()
+        pin[1, :50] = pin[0, :50]
+        cnt = torch.tensor([n0, 50], dtype=torch.int32, device='cuda')
+        pts = torch.zeros((2, cap, 2), dtype=torch.float32, device='cuda')
+        st = torch.zeros((2, cap), dtype=torch.uint8, device='cuda')
+        ctx.lk_flow_device(tb.LKParams(), base, pitch, fstride, 4, base, pitch, fstride, 4, W, H, [0, 0], [1, 1], pin.data_ptr(), cnt.data_ptr(), cap,
+                           pts.data_ptr(), st.data_ptr())
+        ctx.sync()
+        en, es, _ = oracle.lk_flow(oracle.LKParams(), frames[0], frames[1], pin[0, :n0].cpu().numpy())
+        assert pts[0, :n0].cpu().numpy().tobytes() == en.tobytes() and (st[0, :n0].cpu().numpy() == es).all()
+        assert pts[1, :50].cpu().numpy().tobytes() == en[:50].tobytes() and (st[1, 50:].cpu().numpy() == 0).all()
+    finally:
+        fe.close()

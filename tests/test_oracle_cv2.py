@@ -126,3 +126,55 @@ def test_clahe_matches_cv2(oracle, images, shape):
         assert np.array_equal(oracle.clahe(img, 3.0, (8, 8)), ref)
     ref = cv2.createCLAHE(40.0, (4, 6)).apply(cases[0])
     assert np.array_equal(oracle.clahe(cases[0], 40.0, (4, 6)), ref)
+
+
+@pytest.mark.parametrize('shape', [(376, 1241), (61, 83), (100, 101), (23, 45), (1, 7), (7, 1)])
+def test_pyrdown_matches_cv2(oracle, shape):
+    img = np.random.default_rng(shape[0]).integers(0, 256, shape, dtype=np.uint8)
+    assert (oracle.pyrdown(img) == cv2.pyrDown(img)).all()
+
+
+def lk_inputs(images):
+    """(prev, next, pts) cases for the LK tests (shared with tests/test_gpu_flow.py): the KITTI stereo pair with the golden
+    ORB keypoints, a shifted/noisy synthetic pair with points up to the image border, and a small image that stops the
+    pyramid early."""
+    import os
+    from .conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'extract_left_B1000.npz'))
+    cases = [('kitti', images['left'], images['right'], np.stack([g['kps']['x'], g['kps']['y']], 1).astype(np.float32))]
+    rng = np.random.default_rng(5)
+    base = cv2.GaussianBlur(rng.integers(0, 256, (200, 260), dtype=np.uint8), (0, 0), 2.0)
+    base = cv2.normalize(base, None, 0, 255, cv2.NORM_MINMAX)
+    M = np.float32([[1.01, 0.01, 2.3], [-0.01, 0.99, -1.7]])
+    nxt = cv2.warpAffine(base, M, (260, 200), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    pts = np.stack([rng.uniform(-3, 263, 400), rng.uniform(-3, 203, 400)], 1).astype(np.float32)
+    pts[:8] = [[0, 0], [259, 199], [0.5, 100], [130, 0.25], [259.5, 50], [100, 199.75], [-30, 20], [20, 400]]
+    cases.append(('affine', base, nxt, pts))
+    small = base[:50, :70].copy()
+    cases.append(('small', small, np.roll(small, 1, axis=1), np.stack([rng.uniform(0, 70, 60), rng.uniform(0, 50, 60)], 1).astype(np.float32)))
+    flat = np.full((120, 160), 77, np.uint8)
+    cases.append(('flat', flat, flat, np.stack([rng.uniform(0, 160, 30), rng.uniform(0, 120, 30)], 1).astype(np.float32)))
+    return cases
+
+
+@pytest.mark.parametrize('max_level', [3, 0])
+def test_lk_flow_matches_cv2_within_tolerance(oracle, images, max_level):
+    """cv2's SIMD build sums the 2x2 system in float lanes, the restatement in exact integers: most tracks are bit-identical,
+    the rest differ by rounding, and a stop decision on the 0.01-pixel threshold may flip (then the difference is of that
+    order). Tolerance: status equal on >= 99 % of the points; of the tracks both call valid, >= 98 % within 0.05 px and
+    the median within 1e-3 px."""
+    for name, prev, nxt, pts in lk_inputs(images):
+        n2, s2, e2 = oracle.lk_flow(oracle.LKParams(max_level=max_level), prev, nxt, pts)
+        n1, s1, e1 = cv2.calcOpticalFlowPyrLK(prev, nxt, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=max_level)
+        n1, s1, e1 = n1.reshape(-1, 2), s1.ravel(), e1.ravel()
+        assert (s1 == s2).mean() >= 0.99, (name, (s1 == s2).mean())
+        ok = (s1 == 1) & (s2 == 1)
+        if name == 'flat':
+            assert ok.sum() == 0      # no texture: minEig below the threshold everywhere
+            continue
+        assert ok.sum() > len(pts) // 3, name
+        d = np.abs(n1 - n2).max(1)[ok]
+        assert (d <= 0.05).mean() >= 0.98 and np.median(d) <= 1e-3, (name, (d <= 0.05).mean(), np.median(d))
+        close = ok.copy()
+        close[ok] = d <= 1e-3
+        assert np.abs(e1 - e2)[close].max() <= 0.05, name

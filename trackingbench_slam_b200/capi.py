@@ -39,6 +39,7 @@ EXPORTS = [
     'tb_undistort_image_host', 'tb_frontend_undistort_device', 'tb_frontend_upload_frames_undistort',
     'tb_clahe_device', 'tb_clahe_host',
     'tb_stereo_match', 'tb_frontend_stereo_match',
+    'tb_lk_flow_host', 'tb_lk_flow_device', 'tb_frontend_search_by_opflow',
 ]
 
 
@@ -54,6 +55,14 @@ class StereoParams(C.Structure):
 
     def __init__(self, bf=1.0, band=2.0, min_u=0.0, max_u=100000.0, th_dist=30, octave_tol=1):
         super().__init__(bf, band, min_u, max_u, th_dist, octave_tol)
+
+
+class LKParams(C.Structure):
+    """tb_lk_params; defaults = the arguments of matcher.cpp:745 and OpenCV's defaults."""
+    _fields_ = [('win', C.c_int32), ('max_level', C.c_int32), ('max_iter', C.c_int32), ('eps', C.c_float), ('min_eig', C.c_float)]
+
+    def __init__(self, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=1e-4):
+        super().__init__(win, max_level, max_iter, eps, min_eig)
 
 
 class Pinhole(C.Structure):
@@ -217,6 +226,29 @@ class Context:
         self.check(lib().tb_stereo_match(self.h, C.byref(params), _vp(kL), _vp(dL), len(kL), _vp(kR), _vp(dR), len(kR),
                                          _vp(inv_sf), len(inv_sf), int(n_rows), _vp(out), len(out), C.byref(n), _vp(depth)))
         return out[:n.value].copy(), depth
+
+    def lk_flow(self, params, prev, nxt, pts):
+        """cv::calcOpticalFlowPyrLK(prev, next, pts, ...) as matcher.cpp:745 -> (next_pts [n,2], status [n], err [n])."""
+        prev = np.ascontiguousarray(prev, np.uint8)
+        nxt = np.ascontiguousarray(nxt, np.uint8)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        h, w = prev.shape
+        assert nxt.shape == prev.shape
+        out = np.zeros_like(pts)
+        st = np.zeros(len(pts), np.uint8)
+        err = np.zeros(len(pts), np.float32)
+        self.check(lib().tb_lk_flow_host(self.h, C.byref(params), _vp(prev), _vp(nxt), w, h, C.c_size_t(prev.strides[0]), _vp(pts), len(pts),
+                                         _vp(out), _vp(st), _vp(err)))
+        return out, st, err
+
+    def lk_flow_device(self, params, prev_dptr, prev_pitch, prev_frame_stride, n_prev, next_dptr, next_pitch, next_frame_stride, n_next, w, h,
+                       prev_idx, next_idx, pts_dptr, counts_dptr, pts_cap, next_pts_dptr, status_dptr, err_dptr=None):
+        a = np.ascontiguousarray(prev_idx, np.int32)
+        b = np.ascontiguousarray(next_idx, np.int32)
+        self.check(lib().tb_lk_flow_device(self.h, C.byref(params), _vp(prev_dptr), C.c_size_t(prev_pitch), C.c_size_t(prev_frame_stride), int(n_prev),
+                                           _vp(next_dptr), C.c_size_t(next_pitch), C.c_size_t(next_frame_stride), int(n_next), int(w), int(h),
+                                           len(a), _vp(a), _vp(b), _vp(pts_dptr), _vp(counts_dptr), int(pts_cap), _vp(next_pts_dptr),
+                                           _vp(status_dptr), _vp(err_dptr)))
 
     def vocab_create(self, voc):
         """voc: vocab.Vocabulary -> DeviceVocabulary (tree resident in HBM)."""
@@ -532,3 +564,13 @@ def _frontend_stereo_match(self, params, left_frames, right_frames, inv_sf, matc
 
 
 Frontend.stereo_match = _frontend_stereo_match
+
+
+def _frontend_search_by_opflow(self, params, n_frames, f1_frames, f2_frames, equalized, next_pts_dptr, status_dptr, err_dptr=None):
+    f1 = np.ascontiguousarray(f1_frames, np.int32)
+    f2 = np.ascontiguousarray(f2_frames, np.int32)
+    self.ctx.check(lib().tb_frontend_search_by_opflow(self.h, C.byref(params), int(n_frames), len(f1), _vp(f1), _vp(f2), int(bool(equalized)),
+                                                      _vp(next_pts_dptr), _vp(status_dptr), _vp(err_dptr)))
+
+
+Frontend.search_by_opflow = _frontend_search_by_opflow

@@ -28,6 +28,7 @@ struct tb_ctx {
     struct TcWs *tcws = nullptr;     // tensor-core matcher workspace (match_tc.cu)
     struct WinWs *wws = nullptr;     // batched windowed-matcher workspace (window.cu)
     struct IngestWs *iws = nullptr;  // CLAHE tile LUTs (ingest.cu)
+    struct FlowWs *fws = nullptr;    // LK pyramids + pair descriptors (flow.cu)
     int match_impl = 0;              // 0 = LOP3+POPC (K7), 1 = tcgen05 int8 (K8)
     // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
     bool profiling = false;
@@ -52,6 +53,7 @@ void tb_match_ws_free(tb_ctx *ctx);
 void tb_match_tc_free(tb_ctx *ctx);
 void tb_window_ws_free(tb_ctx *ctx);
 void tb_ingest_ws_free(tb_ctx *ctx);
+void tb_flow_ws_free(tb_ctx *ctx);
 
 static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "")
 {

@@ -52,6 +52,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_match_tc_free(ctx);
     tb_window_ws_free(ctx);
     tb_ingest_ws_free(ctx);
+    tb_flow_ws_free(ctx);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -696,6 +697,28 @@ extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_
         if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
     return tb_window_violence_batched(fe->ctx, p, n_pairs, f1_frames, f2_frames, fe->B, fe->kps, fe->desc, fe->kp_cap, fe->n_kp,
                                       fe->g[0].w, fe->g[0].h, min_level, max_level, search_r, (tb_match *)matches, capacity, (int *)counts);
+}
+
+extern "C" int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_frames, int n_pairs, const int32_t *f1_frames,
+                                            const int32_t *f2_frames, int equalized, void *next_pts, void *status, void *err)
+{
+    if (!fe || !p || n_frames < 1 || n_frames > fe->B || n_pairs < 0 || !f1_frames || !f2_frames || !next_pts || !status) return TB_E_INVALID;
+    for (int i = 0; i < n_pairs; i++)
+        if (f1_frames[i] < 0 || f1_frames[i] >= n_frames || f2_frames[i] < 0 || f2_frames[i] >= n_frames) return TB_E_INVALID;
+    const LevelGeom &g = fe->g[0];
+    const uint8_t *next = fe->pyr[0];
+    if (equalized) {   // img1 = F1->Equalize(): CLAHE(3.0, 8x8) of level 0 (matcher.cpp:734-737, Frame.cpp:453-458)
+        uint8_t *eq = nullptr;
+        int rc = tb_flow_eq_reserve(fe->ctx, g.frame_stride * (size_t)n_frames, &eq);
+        if (rc) return rc;
+        rc = tb_clahe_device(fe->ctx, fe->pyr[0], g.w, g.h, (size_t)g.pitch, g.frame_stride, eq, (size_t)g.pitch, g.frame_stride, n_frames, 3.0, 8, 8);
+        if (rc) return rc;
+        next = eq;
+    }
+    // calcOpticalFlowPyrLK(img2, img1, F2 keys, ...): previous image = F2 (with its keypoints), next image = F1 (matcher.cpp:745)
+    return tb_flow_batched(fe->ctx, p, fe->pyr[0], (size_t)g.pitch, g.frame_stride, n_frames, next, (size_t)g.pitch, g.frame_stride, n_frames, g.w, g.h,
+                           n_pairs, f2_frames, f1_frames, (const uint8_t *)fe->kps, sizeof(tb_keypoint), sizeof(tb_keypoint) * (size_t)fe->kp_cap, f2_frames,
+                           fe->n_kp, fe->kp_cap, 1, (float2 *)next_pts, (uint8_t *)status, (float *)err);
 }
 
 extern "C" int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames,
