@@ -77,14 +77,25 @@ struct LkWarpSmem {
 };
 
 // stage the n x n neighbourhood with origin (x0, y0) of a level (REFLECT_101 outside) into nb
-__device__ __forceinline__ void lk_stage(const LkLevel &L, int x0, int y0, int n, uint8_t *nb, int lane)
+// (n is a compile-time constant in the WIN = 21 instantiation: the index split is a multiply-shift and the loop unrolls)
+__device__ __forceinline__ void lk_stage(const LkLevel &L, int x0, int y0, const int n, uint8_t *nb, int lane)
 {
+    if (x0 >= 0 && y0 >= 0 && x0 + n <= L.w && y0 + n <= L.h) {   // warp-uniform: window inside the level, no reflection
+        const uint8_t *b = L.p + (size_t)y0 * L.pitch + x0;
+#pragma unroll 6
+        for (int i = lane; i < n * n; i += 32) {
+            const int yy = i / n, xx = i - yy * n;
+            nb[i] = __ldg(b + yy * L.pitch + xx);
+        }
+        return;
+    }
     for (int i = lane; i < n * n; i += 32) {
         const int yy = i / n, xx = i - yy * n;
         nb[i] = __ldg(L.p + (size_t)lk_reflect(y0 + yy, L.h) * L.pitch + lk_reflect(x0 + xx, L.w));
     }
 }
 
+template <int WIN>   // WIN = 21: the reference's window as a compile-time constant; WIN = 0: p.win at run time
 __global__ void __launch_bounds__(LK_WARPS * 32)
 lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t pts_stride, int pts_cap, int frame_w, int frame_h,
          int check_in_frame, float2 *__restrict__ out_pts, uint8_t *__restrict__ out_status, float *__restrict__ out_err)
@@ -101,7 +112,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         if (lane == 0) { out_pts[o] = make_float2(0.f, 0.f); out_status[o] = 0; if (out_err) out_err[o] = 0.f; }
         return;
     }
-    const int win = p.win, win1 = win + 1, win3 = win + 3;
+    const int win = WIN ? WIN : p.win, win1 = win + 1, win3 = win + 3;
     const float halfWin = __fmul_rn((float)(win - 1), 0.5f);
     const float FLT_SCALE = 1.f / (1 << 20);
     int maxCount = min(max(p.max_iter, 0), 100);
@@ -184,6 +195,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
             __syncwarp();
             wt = lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
             int b1i = 0, b2i = 0;
+#pragma unroll
             for (int k = lane; k < win * win; k += 32) {
                 const int yy = k / win, xx = k - yy * win;
                 const uint8_t *c = S.nb + yy * win1 + xx;
@@ -320,11 +332,16 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
     static bool attr_set = false;
     const size_t smem = sizeof(LkWarpSmem) * LK_WARPS;
-    if (!attr_set) { TB_CUDA(ctx, cudaFuncSetAttribute(lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (!attr_set) {
+        TB_CUDA(ctx, cudaFuncSetAttribute(lk_track<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TB_CUDA(ctx, cudaFuncSetAttribute(lk_track<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     {
         ProfScope prof__(ctx, "lk_track");
-        lk_track<<<dim3(div_up(pts_cap, LK_WARPS), n_pairs), LK_WARPS * 32, smem, ctx->stream>>>(W.pairs, *p, g.levels, pts_stride, pts_cap, w, h, check_in_frame,
-                                                                                                  out_pts, out_status, out_err);
+        const dim3 grid(div_up(pts_cap, LK_WARPS), n_pairs);
+        if (p->win == 21) lk_track<21><<<grid, LK_WARPS * 32, smem, ctx->stream>>>(W.pairs, *p, g.levels, pts_stride, pts_cap, w, h, check_in_frame, out_pts, out_status, out_err);
+        else lk_track<0><<<grid, LK_WARPS * 32, smem, ctx->stream>>>(W.pairs, *p, g.levels, pts_stride, pts_cap, w, h, check_in_frame, out_pts, out_status, out_err);
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
