@@ -83,6 +83,15 @@ int main(int argc, char **argv)
     std::printf("projection %zu %llx\n", matches.size(), digest(matches));
     std::printf("dist01 %d\n", Matcher::DescriptorDistance(descriptors1.row(0), descriptors1.row(1)));
 
+    // optical flow (LocalBA.cpp:54 calls searchByOPFlow(stereo_frame, current_frame, pts, true, true); reject is not built)
+    for (int eq = 0; eq < 2; eq++) {
+        std::vector<cv::Point2f> cur_points;
+        matches = matcher_ptr->searchByOPFlow(frame2_ptr, frame1_ptr, cur_points, eq != 0, false);
+        unsigned long long h = fnv(cur_points.data(), cur_points.size() * sizeof(cv::Point2f));
+        for (const auto &m : matches) h = fnv(&m.queryIdx, sizeof m.queryIdx, h);
+        std::printf("opflow%d %zu %llx\n", eq, matches.size(), h);
+    }
+
     // bag of words (test_vo.cpp:661-705 loads ORBvoc.txt and calls SetBow per keyframe); optional 4th argument
     if (argc > 4) {
         auto vocabulary = std::make_shared<ORBVocabulary>();

@@ -2,8 +2,8 @@
 // descriptor matchers on the hot path (searchByBF, searchByViolence, searchByProjection x2, searchByBow,
 // DescriptorDistance, ComputeThreeMaxima).  Public members, setters, method names and argument
 // meaning are the reference's; bodies (src/matchers/matcher.cpp:168-617,793-851) run on the GPU.
-// searchByNN (approximate FLANN-LSH), searchByOPFlow and the direct-alignment methods are
-// out of scope for this path.
+// searchByOPFlow (matcher.cpp:724) runs its pyramidal LK on the GPU; its optional rejectWithF (RANSAC) is not built.
+// searchByNN (approximate FLANN-LSH) and the direct-alignment methods are out of scope.
 #ifndef TRACKING_BENCH_MATCHER_H
 #define TRACKING_BENCH_MATCHER_H
 #include <cassert>
@@ -122,6 +122,31 @@ public:
         tb_check(tb_search_by_bow(ctx, &p, kp(F1), d1.data, node1.data(), n1, kp(F2), d2.data, node2.data(), n2, has_mp.data(),
                                   MapPointOnly ? 1 : 0, out.data(), (int)out.size(), &n), ctx, "tb_search_by_bow");
         return to_dmatch(out, n);
+    }
+    // matcher.cpp:724 — LK tracks of F2's keypoints into F1 (cv::calcOpticalFlowPyrLK, Size(21,21), 3 levels), status
+    // cleared outside the frame (:747-749); matches are {i, i}. reject=true (rejectWithF, RANSAC) is not on this path.
+    std::vector<cv::DMatch> searchByOPFlow(const std::shared_ptr<Frame> &F1, const std::shared_ptr<Frame> &F2, std::vector<cv::Point2f> &cur_points,
+                                           bool equalized, bool reject, bool MapPointOnly = false)
+    {
+        (void)MapPointOnly;   // unused by the reference body as well
+        if (reject) throw std::invalid_argument("searchByOPFlow(reject=true): rejectWithF is not on the accelerated path");
+        tb_ctx *ctx = tb_default_ctx();
+        cv::Mat img1 = contiguous(equalized ? F1->Equalize() : F1->GetImage()), img2 = contiguous(F2->GetImage());
+        const std::vector<cv::Point2f> prev = F2->GetCVKeys();
+        const int n = (int)prev.size();
+        cur_points.assign(n, cv::Point2f());
+        std::vector<uint8_t> status(n + 1, 0);
+        tb_lk_params lk = {21, 3, 30, 0.01f, 1e-4f};
+        static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f must be two packed floats");
+        if (n) tb_check(tb_lk_flow_host(ctx, &lk, img2.data, img1.data, img2.cols, img2.rows, img2.step, (const float *)prev.data(), n,
+                                        (float *)cur_points.data(), status.data(), nullptr), ctx, "tb_lk_flow_host");
+        std::vector<cv::DMatch> matches;
+        const int W = F1->GetCameraModel()->Width(), H = F1->GetCameraModel()->Height();
+        for (int i = 0; i < n; i++) {
+            const int xi = (int)cur_points[i].x, yi = (int)cur_points[i].y;
+            if (status[i] && xi >= 0 && xi < W && yi >= 0 && yi < H) { cv::DMatch m; m.queryIdx = i; m.trainIdx = i; matches.push_back(m); }
+        }
+        return matches;
     }
     // matcher.cpp:793
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b)

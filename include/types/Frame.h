@@ -161,6 +161,17 @@ public:
     std::vector<float> GetInverseScaleFactors() { return mvInvScaleFactor; }
     std::vector<cv::Mat> &GetImagePyramid() { return mvImagePyramid; }
     cv::Mat GetImage() { return mvImagePyramid[0]; }
+    // Frame::Equalize (Frame.cpp:453-458): cv::createCLAHE(3.0, Size(8,8))->apply(level 0)
+    cv::Mat Equalize()
+    {
+        tb_ctx *ctx = tb_default_ctx();
+        const cv::Mat &src = mvImagePyramid[0];
+        cv::Mat dst(src.rows, src.cols, CV_8U);
+        tb_check(tb_clahe_host(ctx, src.data, src.cols, src.rows, src.step, dst.data, dst.step, 3.0, 8, 8), ctx, "tb_clahe_host");
+        return dst;
+    }
+    // Frame::GetCVKeys: the keypoint positions as cv::Point2f (the prevPts of searchByOPFlow)
+    std::vector<cv::Point2f> GetCVKeys() { std::vector<cv::Point2f> v; v.reserve(mvKeys.size()); for (const auto &k : mvKeys) v.push_back(k.pt); return v; }
     std::shared_ptr<CameraModel> GetCameraModel() { return mpCamera; }
     int cols() const { return cols_; }
     int rows() const { return rows_; }

@@ -73,6 +73,16 @@ def test_headless_test_matcher(tmp_path, oracle, images):
     proj = oracle.search_by_projection(oracle.MatcherParams(30, 50, 30, 1, 30.0), cam, T, k2, d2, None, sf, W, H, k1, valid, xyz, d1)
     assert got['projection'] == [str(len(proj)), '%x' % _digest(proj)]
     assert got['dist01'] == [str(oracle.hamming256(d1[0], d1[1]))]
+    # searchByOPFlow(F1 = right frame, F2 = left frame with its keypoints), raw and CLAHE'd current image
+    for eq in (0, 1):
+        img1 = oracle.clahe(images['right'], 3.0, (8, 8)) if eq else images['right']
+        pts, st, _ = oracle.lk_flow(oracle.LKParams(), images['left'], img1, np.stack([k1['x'], k1['y']], 1))
+        xi, yi = pts[:, 0].astype(np.int32), pts[:, 1].astype(np.int32)
+        idx = np.nonzero((st == 1) & (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H))[0].astype(np.int32)
+        h = _fnv(pts.tobytes())
+        for i in idx:
+            h = _fnv(np.int32(i).tobytes(), h)
+        assert len(idx) > 300 and got['opflow%d' % eq] == [str(len(idx)), '%x' % h]
     # bag of words: Frame::SetBow (levelsup 4) + searchByBow, with and without MapPointOnly
     w1, n1, wt1 = oracle.bow_transform(voc, d1, 4)
     w2, n2, wt2 = oracle.bow_transform(voc, d2, 4)
