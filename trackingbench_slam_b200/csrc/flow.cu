@@ -21,6 +21,7 @@
 #define LK_MAX_LEVELS 8
 #define LK_MAX_WIN 21
 #define LK_WARPS 8
+#define LK_REG 32      // side of the staged region of the next image: a (win+1)^2 window can move (32-22)/2 = 5 px each way inside it
 
 struct LkLevel { const uint8_t *p; int w, h, pitch; };
 struct LkPair { LkLevel I[LK_MAX_LEVELS], J[LK_MAX_LEVELS]; const uint8_t *pts; const int *count; };
@@ -63,14 +64,17 @@ __device__ __forceinline__ LkWeights lk_weights(float a, float b)
     k.w11 = 16384 - k.w00 - k.w01 - k.w10;
     return k;
 }
-__device__ __forceinline__ long long lk_warp_sum(long long v)
+// exact warp sum of 32-bit partials: the low 16 bits and the (signed) high part go through redux.sync separately, so
+// neither 32-lane sum can overflow; 2 REDUX instead of 5 rounds of 64-bit shuffle + add
+__device__ __forceinline__ long long lk_warp_sum(int v)
 {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return (long long)hi * 65536 + (long long)lo;
 }
 
 struct LkWarpSmem {
-    uint8_t nb[(LK_MAX_WIN + 3) * (LK_MAX_WIN + 3) + 4];       // staged neighbourhood: (win+3)^2 of I, then (win+1)^2 of J
+    uint8_t nb[LK_REG * LK_REG];                               // staged bytes: (win+3)^2 of I, then a 32x32 region of J
     short2 d[(LK_MAX_WIN + 1) * (LK_MAX_WIN + 1)];             // Scharr (dx, dy) on the (win+1)^2 grid
     short I[LK_MAX_WIN * LK_MAX_WIN];
     short2 dI[LK_MAX_WIN * LK_MAX_WIN];
@@ -93,6 +97,19 @@ __device__ __forceinline__ void lk_stage(const LkLevel &L, int x0, int y0, const
         const int yy = i / n, xx = i - yy * n;
         nb[i] = __ldg(L.p + (size_t)lk_reflect(y0 + yy, L.h) * L.pitch + lk_reflect(x0 + xx, L.w));
     }
+}
+
+// stage the LK_REG x LK_REG region with origin (x0, y0): lane = column, one coalesced 32-byte row read per step
+__device__ __forceinline__ void lk_stage_region(const LkLevel &L, int x0, int y0, uint8_t *nb, int lane)
+{
+    if (x0 >= 0 && y0 >= 0 && x0 + LK_REG <= L.w && y0 + LK_REG <= L.h) {
+        const uint8_t *b = L.p + (size_t)y0 * L.pitch + x0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < LK_REG; r++) nb[r * LK_REG + lane] = __ldg(b + r * L.pitch);
+        return;
+    }
+    const int xr = lk_reflect(x0 + lane, L.w);
+    for (int r = 0; r < LK_REG; r++) nb[r * LK_REG + lane] = __ldg(L.p + (size_t)lk_reflect(y0 + r, L.h) * L.pitch + xr);
 }
 
 template <int WIN>   // WIN = 21: the reference's window as a compile-time constant; WIN = 0: p.win at run time
@@ -184,22 +201,29 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, halfWin); ny = __fsub_rn(ny, halfWin);
         float pdx = 0.f, pdy = 0.f;
+        int rx = 0, ry = 0;
+        bool staged = false;   // S.nb holds the region [rx, rx+32) x [ry, ry+32) of J (the I neighbourhood was there before)
         for (int j = 0; j < maxCount; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= Jl.w || iny < -win || iny >= Jl.h) {
                 if (level == 0) status = 0;
                 break;
             }
-            __syncwarp();
-            lk_stage(Jl, inx, iny, win1, S.nb, lane);
-            __syncwarp();
+            if (!staged || inx < rx || iny < ry || inx + win1 > rx + LK_REG || iny + win1 > ry + LK_REG) {
+                rx = inx - (LK_REG - win1) / 2; ry = iny - (LK_REG - win1) / 2;
+                __syncwarp();
+                lk_stage_region(Jl, rx, ry, S.nb, lane);
+                __syncwarp();
+                staged = true;
+            }
+            const uint8_t *c0 = S.nb + (iny - ry) * LK_REG + (inx - rx);
             wt = lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
             int b1i = 0, b2i = 0;
 #pragma unroll
             for (int k = lane; k < win * win; k += 32) {
                 const int yy = k / win, xx = k - yy * win;
-                const uint8_t *c = S.nb + yy * win1 + xx;
-                const int diff = ((c[0] * wt.w00 + c[1] * wt.w01 + c[win1] * wt.w10 + c[win1 + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k];
+                const uint8_t *c = c0 + yy * LK_REG + xx;
+                const int diff = ((c[0] * wt.w00 + c[1] * wt.w01 + c[LK_REG] * wt.w10 + c[LK_REG + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k];
                 const short2 g = S.dI[k];
                 b1i += diff * g.x; b2i += diff * g.y;
             }
@@ -219,15 +243,20 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
             const float fx = __fsub_rn(outx, halfWin), fy = __fsub_rn(outy, halfWin);
             const int inx = (int)floorf(fx), iny = (int)floorf(fy);
             if (inx < -win || inx >= Jl.w || iny < -win || iny >= Jl.h) { status = 0; continue; }
-            __syncwarp();
-            lk_stage(Jl, inx, iny, win1, S.nb, lane);
-            __syncwarp();
+            if (!staged || inx < rx || iny < ry || inx + win1 > rx + LK_REG || iny + win1 > ry + LK_REG) {
+                rx = inx - (LK_REG - win1) / 2; ry = iny - (LK_REG - win1) / 2;
+                __syncwarp();
+                lk_stage_region(Jl, rx, ry, S.nb, lane);
+                __syncwarp();
+            }
+            const uint8_t *c0 = S.nb + (iny - ry) * LK_REG + (inx - rx);
             wt = lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny));
             int e = 0;
+#pragma unroll
             for (int k = lane; k < win * win; k += 32) {
                 const int yy = k / win, xx = k - yy * win;
-                const uint8_t *c = S.nb + yy * win1 + xx;
-                e += abs(((c[0] * wt.w00 + c[1] * wt.w01 + c[win1] * wt.w10 + c[win1 + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k]);
+                const uint8_t *c = c0 + yy * LK_REG + xx;
+                e += abs(((c[0] * wt.w00 + c[1] * wt.w01 + c[LK_REG] * wt.w10 + c[LK_REG + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k]);
             }
             // sum of |diff| < 2^24: the reference's running float sum is exact, so the integer sum converts to the same float
             errv = __fdiv_rn(__fmul_rn(__ll2float_rn(lk_warp_sum(e)), 1.f), (float)(32 * win * win));
