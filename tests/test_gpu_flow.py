@@ -87,3 +87,17 @@ def test_lk_device_batched_and_frontend_opflow(tb, ctx, oracle, images):
         assert pts[1, :50].cpu().numpy().tobytes() == en[:50].tobytes() and (st[1, 50:].cpu().numpy() == 0).all()
     finally:
         fe.close()
+
+
+def test_lk_edge_cases(tb, ctx, oracle, images):
+    prev, nxt = images['left'], images['right']
+    n, s, e = ctx.lk_flow(tb.LKParams(), prev, nxt, np.zeros((0, 2), np.float32))          # no points
+    assert n.shape == (0, 2) and len(s) == 0
+    with pytest.raises(tb.TbError) as ei:                                                    # window larger than the kernel supports
+        ctx.lk_flow(tb.LKParams(win=25), prev, nxt, np.float32([[100, 100]]))
+    assert ei.value.code == -4
+    pts = np.float32([[1e6, 5], [-1e6, -1e6], [np.nan, 3], [620.5, 188.25]])                # far outside / NaN points
+    en, es, ee = oracle.lk_flow(oracle.LKParams(), prev, nxt, pts)
+    n, s, e = ctx.lk_flow(tb.LKParams(), prev, nxt, pts)
+    assert (s == es).all() and s[3] == 1 and not s[:2].any()
+    assert n[3].tobytes() == en[3].tobytes() and n[:2].tobytes() == en[:2].tobytes()

@@ -53,6 +53,11 @@ lk_pyrdown_u8(const uint8_t *__restrict__ src, int sw, int sh, size_t spitch, si
     dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)((v + 128) >> 8);
 }
 
+// cvFloor as x86 computes it (cvttss2si): NaN and out-of-range values give INT_MIN, which every range check rejects
+__device__ __forceinline__ int lk_floor(float v)
+{
+    return (v >= -2147483648.f && v < 2147483648.f) ? (int)floorf(v) : (-2147483647 - 1);
+}
 struct LkWeights { int w00, w01, w10, w11; };
 __device__ __forceinline__ LkWeights lk_weights(float a, float b)
 {
@@ -148,7 +153,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
         outx = nx; outy = ny;
         px = __fsub_rn(px, halfWin); py = __fsub_rn(py, halfWin);
-        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        const int ipx = lk_floor(px), ipy = lk_floor(py);
         if (ipx < -win || ipx >= Il.w || ipy < -win || ipy >= Il.h) {
             if (level == 0) { status = 0; errv = 0.f; }
             continue;
@@ -204,7 +209,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         int rx = 0, ry = 0;
         bool staged = false;   // S.nb holds the region [rx, rx+32) x [ry, ry+32) of J (the I neighbourhood was there before)
         for (int j = 0; j < maxCount; j++) {
-            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            const int inx = lk_floor(nx), iny = lk_floor(ny);
             if (inx < -win || inx >= Jl.w || iny < -win || iny >= Jl.h) {
                 if (level == 0) status = 0;
                 break;
@@ -241,7 +246,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         }
         if (status && level == 0) {   // final window check + error measure (the reference passes `err`)
             const float fx = __fsub_rn(outx, halfWin), fy = __fsub_rn(outy, halfWin);
-            const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+            const int inx = lk_floor(fx), iny = lk_floor(fy);
             if (inx < -win || inx >= Jl.w || iny < -win || iny >= Jl.h) { status = 0; continue; }
             if (!staged || inx < rx || iny < ry || inx + win1 > rx + LK_REG || iny + win1 > ry + LK_REG) {
                 rx = inx - (LK_REG - win1) / 2; ry = iny - (LK_REG - win1) / 2;
@@ -359,13 +364,7 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
     }
     TB_CUDA(ctx, cudaMemcpyAsync(W.pairs, hp.data(), sizeof(LkPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
-    static bool attr_set = false;
     const size_t smem = sizeof(LkWarpSmem) * LK_WARPS;
-    if (!attr_set) {
-        TB_CUDA(ctx, cudaFuncSetAttribute(lk_track<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TB_CUDA(ctx, cudaFuncSetAttribute(lk_track<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     {
         ProfScope prof__(ctx, "lk_track");
         const dim3 grid(div_up(pts_cap, LK_WARPS), n_pairs);
@@ -374,6 +373,12 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
         TB_LAUNCH_CHECK(ctx);
     }
     return TB_OK;
+}
+
+void tb_flow_init_device()   // per device, from tb_ctx_create
+{
+    cudaFuncSetAttribute(lk_track<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LkWarpSmem) * LK_WARPS));
+    cudaFuncSetAttribute(lk_track<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(LkWarpSmem) * LK_WARPS));
 }
 
 extern "C" int tb_lk_flow_device(tb_ctx *ctx, const tb_lk_params *p, const void *prev, size_t prev_pitch, size_t prev_frame_stride, int n_prev,

@@ -41,6 +41,7 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
         return TB_E_CUDA;
     }
     tb_fast_init_device(); tb_octree_init_device(); tb_pyramid_init_device(); tb_match_tc_init_device(); tb_describe_init_device();
+    tb_window_init_device(); tb_flow_init_device();
     *out = c;
     return TB_OK;
 }

@@ -94,3 +94,5 @@ void tb_octree_init_device();
 void tb_pyramid_init_device();
 void tb_match_tc_init_device();
 void tb_describe_init_device();
+void tb_window_init_device();
+void tb_flow_init_device();

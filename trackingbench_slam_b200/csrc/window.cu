@@ -1330,8 +1330,6 @@ int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = left_frames[i]; hp[i].f2 = right_frames[i]; }
     TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
-    static bool attr_set = false;
-    if (!attr_set) { TB_CUDA(ctx, cudaFuncSetAttribute(stereo_rowband_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     {
         ProfScope prof__(ctx, "stereo_rowband_batched");
         stereo_rowband_batched<<<n_pairs, 512, smem, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, sf, n_levels, n_rows, R, *p,
@@ -1340,6 +1338,8 @@ int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs
     }
     return TB_OK;
 }
+
+void tb_window_init_device() { cudaFuncSetAttribute(stereo_rowband_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }   // per device
 
 // Host-buffer form: left keys/descriptors become frame 0, right ones frame 1 of a temporary two-frame layout.
 extern "C" int tb_stereo_match(tb_ctx *ctx, const tb_stereo_params *p, const tb_keypoint *kL, const uint8_t *dL, int nL,
