@@ -79,10 +79,13 @@ __device__ __forceinline__ long long lk_warp_sum(int v)
 }
 
 struct LkWarpSmem {
-    uint8_t nb[LK_REG * LK_REG];                               // staged bytes: (win+3)^2 of I, then a 32x32 region of J
+    union {
+        uint8_t nb[(LK_MAX_WIN + 3) * (LK_MAX_WIN + 3) + 4];   // (win+3)^2 bytes of the previous image
+        uint16_t nb16[LK_REG * LK_REG];                        // 32x32 region of the next image as overlapping pairs: px(x) | px(x+1) << 8
+    };
     short2 d[(LK_MAX_WIN + 1) * (LK_MAX_WIN + 1)];             // Scharr (dx, dy) on the (win+1)^2 grid
-    short I[LK_MAX_WIN * LK_MAX_WIN];
-    short2 dI[LK_MAX_WIN * LK_MAX_WIN];
+    int2 dI[LK_MAX_WIN * LK_MAX_WIN];                          // patch of I: (ixval, iyval) and ival, widened to 32 bits once so the
+    int I[LK_MAX_WIN * LK_MAX_WIN];                            // iterations need no sign extension (9.3 KB per warp: 3 CTAs per SM)
 };
 
 // stage the n x n neighbourhood with origin (x0, y0) of a level (REFLECT_101 outside) into nb
@@ -104,17 +107,33 @@ __device__ __forceinline__ void lk_stage(const LkLevel &L, int x0, int y0, const
     }
 }
 
-// stage the LK_REG x LK_REG region with origin (x0, y0): lane = column, one coalesced 32-byte row read per step
-__device__ __forceinline__ void lk_stage_region(const LkLevel &L, int x0, int y0, uint8_t *nb, int lane)
+// stage the LK_REG x LK_REG region with origin (x0, y0) as overlapping byte pairs (px(x), px(x+1)): a bilinear tap row is
+// then one 16-bit load and one dp2a. lane = column, one coalesced row read per step, the right neighbour by shuffle.
+__device__ __forceinline__ void lk_stage_region(const LkLevel &L, int x0, int y0, uint16_t *nb16, int lane)
 {
-    if (x0 >= 0 && y0 >= 0 && x0 + LK_REG <= L.w && y0 + LK_REG <= L.h) {
+    if (x0 >= 0 && y0 >= 0 && x0 + LK_REG + 1 <= L.w && y0 + LK_REG <= L.h) {
         const uint8_t *b = L.p + (size_t)y0 * L.pitch + x0 + lane;
 #pragma unroll 8
-        for (int r = 0; r < LK_REG; r++) nb[r * LK_REG + lane] = __ldg(b + r * L.pitch);
+        for (int r = 0; r < LK_REG; r++) {
+            const unsigned v = __ldg(b + r * L.pitch);
+            unsigned nx = __shfl_down_sync(0xffffffffu, v, 1);
+            if (lane == 31) nx = __ldg(b + r * L.pitch + 1);
+            nb16[r * LK_REG + lane] = (uint16_t)(v | (nx << 8));
+        }
         return;
     }
-    const int xr = lk_reflect(x0 + lane, L.w);
-    for (int r = 0; r < LK_REG; r++) nb[r * LK_REG + lane] = __ldg(L.p + (size_t)lk_reflect(y0 + r, L.h) * L.pitch + xr);
+    const int xa = lk_reflect(x0 + lane, L.w), xb = lk_reflect(x0 + lane + 1, L.w);
+    for (int r = 0; r < LK_REG; r++) {
+        const uint8_t *row = L.p + (size_t)lk_reflect(y0 + r, L.h) * L.pitch;
+        nb16[r * LK_REG + lane] = (uint16_t)(__ldg(row + xa) | ((unsigned)__ldg(row + xb) << 8));
+    }
+}
+// w_lo * px(x) + w_hi * px(x+1) + acc: signed 16-bit weights (w11 can be -1), unsigned bytes
+__device__ __forceinline__ int lk_dp2a(int w_pair, unsigned px_pair, int acc)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w_pair), "r"(px_pair), "r"(acc));
+    return d;
 }
 
 template <int WIN>   // WIN = 21: the reference's window as a compile-time constant; WIN = 0: p.win at run time
@@ -189,7 +208,7 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
             const int ix = (d00.x * wt.w00 + d01.x * wt.w01 + d10.x * wt.w10 + d11.x * wt.w11 + (1 << 13)) >> 14;
             const int iy = (d00.y * wt.w00 + d01.y * wt.w01 + d10.y * wt.w10 + d11.y * wt.w11 + (1 << 13)) >> 14;
             S.I[k] = (short)ival;
-            S.dI[k] = make_short2((short)ix, (short)iy);
+            S.dI[k] = make_int2((short)ix, (short)iy);
             a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
         }
         const float A11 = __fmul_rn(__ll2float_rn(lk_warp_sum(a11)), FLT_SCALE);
@@ -217,19 +236,20 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
             if (!staged || inx < rx || iny < ry || inx + win1 > rx + LK_REG || iny + win1 > ry + LK_REG) {
                 rx = inx - (LK_REG - win1) / 2; ry = iny - (LK_REG - win1) / 2;
                 __syncwarp();
-                lk_stage_region(Jl, rx, ry, S.nb, lane);
+                lk_stage_region(Jl, rx, ry, S.nb16, lane);
                 __syncwarp();
                 staged = true;
             }
-            const uint8_t *c0 = S.nb + (iny - ry) * LK_REG + (inx - rx);
+            const uint16_t *c0 = S.nb16 + (iny - ry) * LK_REG + (inx - rx);
             wt = lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
+            const int wtop = (wt.w00 & 0xffff) | (wt.w01 << 16), wbot = (wt.w10 & 0xffff) | (wt.w11 << 16);
             int b1i = 0, b2i = 0;
 #pragma unroll
             for (int k = lane; k < win * win; k += 32) {
                 const int yy = k / win, xx = k - yy * win;
-                const uint8_t *c = c0 + yy * LK_REG + xx;
-                const int diff = ((c[0] * wt.w00 + c[1] * wt.w01 + c[LK_REG] * wt.w10 + c[LK_REG + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k];
-                const short2 g = S.dI[k];
+                const uint16_t *c = c0 + yy * LK_REG + xx;
+                const int2 g = S.dI[k];
+                const int diff = (lk_dp2a(wbot, c[LK_REG], lk_dp2a(wtop, c[0], 1 << 8)) >> 9) - S.I[k];
                 b1i += diff * g.x; b2i += diff * g.y;
             }
             const float b1 = __fmul_rn(__ll2float_rn(lk_warp_sum(b1i)), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(lk_warp_sum(b2i)), FLT_SCALE);
@@ -251,17 +271,18 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
             if (!staged || inx < rx || iny < ry || inx + win1 > rx + LK_REG || iny + win1 > ry + LK_REG) {
                 rx = inx - (LK_REG - win1) / 2; ry = iny - (LK_REG - win1) / 2;
                 __syncwarp();
-                lk_stage_region(Jl, rx, ry, S.nb, lane);
+                lk_stage_region(Jl, rx, ry, S.nb16, lane);
                 __syncwarp();
             }
-            const uint8_t *c0 = S.nb + (iny - ry) * LK_REG + (inx - rx);
+            const uint16_t *c0 = S.nb16 + (iny - ry) * LK_REG + (inx - rx);
             wt = lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny));
+            const int wtop = (wt.w00 & 0xffff) | (wt.w01 << 16), wbot = (wt.w10 & 0xffff) | (wt.w11 << 16);
             int e = 0;
 #pragma unroll
             for (int k = lane; k < win * win; k += 32) {
                 const int yy = k / win, xx = k - yy * win;
-                const uint8_t *c = c0 + yy * LK_REG + xx;
-                e += abs(((c[0] * wt.w00 + c[1] * wt.w01 + c[LK_REG] * wt.w10 + c[LK_REG + 1] * wt.w11 + (1 << 8)) >> 9) - S.I[k]);
+                const uint16_t *c = c0 + yy * LK_REG + xx;
+                e += abs((lk_dp2a(wbot, c[LK_REG], lk_dp2a(wtop, c[0], 1 << 8)) >> 9) - S.I[k]);
             }
             // sum of |diff| < 2^24: the reference's running float sum is exact, so the integer sum converts to the same float
             errv = __fdiv_rn(__fmul_rn(__ll2float_rn(lk_warp_sum(e)), 1.f), (float)(32 * win * win));
