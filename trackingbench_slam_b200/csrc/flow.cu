@@ -181,20 +181,28 @@ lk_track(const LkPair *__restrict__ pairs, tb_lk_params p, int max_level, size_t
         __syncwarp();
         lk_stage(Il, ipx - 1, ipy - 1, win3, S.nb, lane);
         __syncwarp();
-        for (int k = lane; k < win1 * win1; k += 32) {
-            const int yy = k / win1, xx = k - yy * win1;
-            const int X = ipx + xx, Y = ipy + yy;
-            short2 dv = make_short2(0, 0);
-            if (X >= 0 && Y >= 0 && X < Il.w && Y < Il.h) {          // zero border of the derivative image
-                const uint8_t *c = S.nb + (yy + 1) * win3 + (xx + 1);
-                const int a0 = c[-win3 - 1], a1 = c[-win3], a2 = c[-win3 + 1];
-                const int b0 = c[-1], b2 = c[1];
-                const int c0 = c[win3 - 1], c1 = c[win3], c2 = c[win3 + 1];
-                const int t0l = (a0 + c0) * 3 + b0 * 10, t0r = (a2 + c2) * 3 + b2 * 10;
-                const int t1l = c0 - a0, t1m = c1 - a1, t1r = c2 - a2;
-                dv = make_short2((short)(t0r - t0l), (short)((t1r + t1l) * 3 + t1m * 10));
+        // Scharr on the (win+1)^2 grid: a lane owns half a row and slides along x, so a position costs 3 new bytes, not 8
+        {
+            const int halfw = (win1 + 1) >> 1;
+#pragma unroll
+            for (int item = lane; item < 2 * win1; item += 32) {
+                const int yy = item >> 1, xs = (item & 1) ? halfw : 0, xe = (item & 1) ? win1 : halfw;
+                const bool yin = (unsigned)(ipy + yy) < (unsigned)Il.h;
+                const uint8_t *r = S.nb + yy * win3 + xs;              // rows yy..yy+2, columns xx..xx+2 of the staged bytes
+                int a = r[0], b = r[win3], c = r[2 * win3];
+                int t0l = (a + c) * 3 + b * 10, t1l = c - a;
+                a = r[1]; b = r[win3 + 1]; c = r[2 * win3 + 1];
+                int t0m = (a + c) * 3 + b * 10, t1m = c - a;
+                short2 *dst = S.d + yy * win1 + xs;
+                for (int xx = xs; xx < xe; xx++, r++, dst++) {
+                    a = r[2]; b = r[win3 + 2]; c = r[2 * win3 + 2];
+                    const int t0r = (a + c) * 3 + b * 10, t1r = c - a;
+                    short2 dv = make_short2(0, 0);                         // zero border of the derivative image
+                    if (yin && (unsigned)(ipx + xx) < (unsigned)Il.w) dv = make_short2((short)(t0r - t0l), (short)((t1r + t1l) * 3 + t1m * 10));
+                    *dst = dv;
+                    t0l = t0m; t1l = t1m; t0m = t0r; t1m = t1r;
+                }
             }
-            S.d[k] = dv;
         }
         __syncwarp();
         LkWeights wt = lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
