@@ -362,7 +362,8 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
     if (!ctx->fws) ctx->fws = new FlowWs();
     FlowWs &W = *ctx->fws;
     const bool same = prev == next && prev_pitch == next_pitch && prev_frame_stride == next_frame_stride;
-    const size_t need = g.frame_bytes * ((size_t)n_prev + (same ? 0 : (size_t)n_next)) + 256;
+    const int n_first = same ? (n_prev > n_next ? n_prev : n_next) : n_prev;   // one shared pyramid stack covers both index ranges
+    const size_t need = g.frame_bytes * ((size_t)n_first + (same ? 0 : (size_t)n_next)) + 256;
     if (need > W.pyr_bytes) {
         cudaFree(W.pyr); W.pyr = nullptr; W.pyr_bytes = 0;
         TB_CUDA(ctx, cudaMalloc(&W.pyr, need));
@@ -373,8 +374,8 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
         TB_CUDA(ctx, cudaMalloc(&W.pairs, sizeof(LkPair) * (size_t)n_pairs));
         W.pairs_cap = n_pairs;
     }
-    uint8_t *ws_prev = W.pyr, *ws_next = same ? W.pyr : W.pyr + g.frame_bytes * (size_t)n_prev;
-    int rc = lk_build_pyramid(ctx, g, prev, prev_pitch, prev_frame_stride, n_prev, ws_prev);
+    uint8_t *ws_prev = W.pyr, *ws_next = same ? W.pyr : W.pyr + g.frame_bytes * (size_t)n_first;
+    int rc = lk_build_pyramid(ctx, g, prev, prev_pitch, prev_frame_stride, n_first, ws_prev);
     if (rc) return rc;
     if (!same) { rc = lk_build_pyramid(ctx, g, next, next_pitch, next_frame_stride, n_next, ws_next); if (rc) return rc; }
     std::vector<LkPair> hp(n_pairs);
