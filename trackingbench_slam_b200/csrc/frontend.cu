@@ -31,7 +31,8 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     bool ev_ok = true;
     for (int l = 0; l < TB_MAX_LEVELS; l++) ev_ok = ev_ok && cudaEventCreateWithFlags(&c->ev_lvl[l], cudaEventDisableTiming) == cudaSuccess;
-    if (!ev_ok || cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+    const int side_prio = getenv("TB_GAUSS_PRIO") ? (atoi(getenv("TB_GAUSS_PRIO")) > 0 ? prio_hi : prio_lo) : 0;   // tuning knob (default priority measured best)
+    if (!ev_ok || cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_prio) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||   // its few CTAs go first
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
