@@ -83,6 +83,15 @@ int main(int argc, char **argv)
     std::printf("projection %zu %llx\n", matches.size(), digest(matches));
     std::printf("dist01 %d\n", Matcher::DescriptorDistance(descriptors1.row(0), descriptors1.row(1)));
 
+    // a distorted camera: PinholeCamera::UndistortImage / UndistortPoint (CameraModel.cpp:96-121, test_vo.cpp:178)
+    {
+        PinholeCamera dcam(img1.cols, img1.rows, 718.856f, 718.856f, 607.1928f, 185.2157f, -0.28f, 0.07f, 0.0002f, 0.00002f, 0.f);
+        cv::Mat rect;
+        dcam.UndistortImage(img1, rect);
+        const std::vector<cv::Point2f> un = dcam.UndistortPoints(frame1_ptr->GetCVKeys());
+        std::printf("undistort %llx %llx\n", fnv(rect.data, (size_t)rect.rows * rect.cols), fnv(un.data(), un.size() * sizeof(cv::Point2f)));
+    }
+
     // optical flow (LocalBA.cpp:54 calls searchByOPFlow(stereo_frame, current_frame, pts, true, true); reject is not built)
     for (int eq = 0; eq < 2; eq++) {
         std::vector<cv::Point2f> cur_points;

@@ -239,6 +239,14 @@ int tb_frontend_undistort_device(tb_frontend *fe, const tb_undistort *u, int fir
                                  size_t raw_pitch, size_t raw_frame_stride);
 int tb_frontend_upload_frames_undistort(tb_frontend *fe, const tb_undistort *u, int first, int n, const uint8_t *host_frames,
                                         int raw_w, int raw_h, size_t host_stride);
+/* PinholeCamera::UndistortPoint (src/camera/CameraModel.cpp:104-121) = cv::undistortPoints(src, dst, K, D, Mat(), K): five
+ * iterations in double, bit-exact vs OpenCV; identity when |d[0]| <= 1e-7. xy arrays are n x 2 floats (host); the device
+ * form reads point i at pts_dptr + i*stride (x, y = first two floats: float2 or tb_keypoint) and writes float2.
+ * tb_frontend_undistort_points = Frame::UnDistortPoints (src/types/Frame.cpp:165-171) over the keypoints of the last
+ * extract: out_f32x2_dptr[frame][tb_frontend_kp_capacity()], zeros beyond a frame's count. */
+int tb_undistort_points(tb_ctx *ctx, const tb_pinhole *cam, const float *xy_in, int n, float *xy_out);
+int tb_undistort_points_device(tb_ctx *ctx, const tb_pinhole *cam, const void *pts_dptr, size_t stride, long long n, void *out_f32x2_dptr);
+int tb_frontend_undistort_points(tb_frontend *fe, const tb_pinhole *cam, int n_frames, void *out_f32x2_dptr);
 /* Frame::Equalize = cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply (src/types/Frame.cpp:453-458 uses 3.0, 8x8). */
 int tb_clahe_device(tb_ctx *ctx, const void *src_dptr, int w, int h, size_t src_pitch, size_t src_frame_stride, void *dst_dptr,
                     size_t dst_pitch, size_t dst_frame_stride, int n_frames, double clip_limit, int tiles_x, int tiles_y);

@@ -170,6 +170,15 @@ public:
         tb_check(tb_clahe_host(ctx, src.data, src.cols, src.rows, src.step, dst.data, dst.step, 3.0, 8, 8), ctx, "tb_clahe_host");
         return dst;
     }
+    // Frame::UnDistortPoints (Frame.cpp:165-171): px_un of every key through PinholeCamera::UndistortPoint
+    void UnDistortPoints()
+    {
+        auto cam = std::dynamic_pointer_cast<PinholeCamera>(mpCamera);
+        mvKeysUn = cam ? cam->UndistortPoints(GetCVKeys()) : GetCVKeys();
+    }
+    const std::vector<cv::Point2f> &GetUndistortedKeys() const { return mvKeysUn; }
+    // Frame::UnDistortImage (Frame.cpp:173-176) on level 0
+    void UnDistortImage() { cv::Mat out; mpCamera->UndistortImage(mvImagePyramid[0], out); mvImagePyramid[0] = out; }
     // Frame::GetCVKeys: the keypoint positions as cv::Point2f (the prevPts of searchByOPFlow)
     std::vector<cv::Point2f> GetCVKeys() { std::vector<cv::Point2f> v; v.reserve(mvKeys.size()); for (const auto &k : mvKeys) v.push_back(k.pt); return v; }
     std::shared_ptr<CameraModel> GetCameraModel() { return mpCamera; }
@@ -197,6 +206,7 @@ protected:
     double mTimeStamp{};
     float mTcw[16];
     std::vector<cv::KeyPoint> mvKeys;
+    std::vector<cv::Point2f> mvKeysUn;
     cv::Mat mDescriptors;
     std::vector<std::shared_ptr<MapPointLite>> mvpMapPoints;
     BowVector mBowVec;

@@ -478,6 +478,15 @@ def init_undistort_rectify_map(fx, fy, cx, cy, d, w, h):
     return m1, m2
 
 
+def undistort_points(fx, fy, cx, cy, d, pts):
+    """PinholeCamera::UndistortPoint (CameraModel.cpp:104-121) on n points -> [n, 2] float32."""
+    d = np.ascontiguousarray(d, np.float32)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(pts)
+    lib().tbo_undistort_points(C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(d), _p(pts), len(pts), _p(out))
+    return out
+
+
 def remap_linear(src, map1, map2):
     src = _u8(src)
     map1, map2 = np.ascontiguousarray(map1, np.float32), np.ascontiguousarray(map2, np.float32)

@@ -1502,3 +1502,33 @@ int tbo_lk_flow(const tbo_lk_params *p, const u8 *prev, const u8 *next, int w, i
     for (int k = 0; k < n_own; k++) free(own[k]);
     return maxLevel;
 }
+
+/* PinholeCamera::UndistortPoint — CameraModel.cpp:104-121; cv::undistortPoints (calib3d/undistort) with the default
+ * TermCriteria(MAX_ITER, 5, 0.01), R = I, P = K; K and D are float matrices promoted to double. */
+void tbo_undistort_points(float ffx, float ffy, float fcx, float fcy, const float d[5], const float *xy_in, int n, float *xy_out)
+{
+    if (!(fabsf(d[0]) > 1e-7f)) { /* mbDistortion false: returned as is */
+        memcpy(xy_out, xy_in, sizeof(float) * 2 * (size_t)n);
+        return;
+    }
+    const double fx = ffx, fy = ffy, cx = fcx, cy = fcy;
+    const double k0 = d[0], k1 = d[1], k2 = d[2], k3 = d[3], k4 = d[4];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = xy_in[2 * i], v = xy_in[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+            const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0. * r2 + 0. * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        xy_out[2 * i] = (float)(xx * ww);
+        xy_out[2 * i + 1] = (float)(yy * ww);
+    }
+}

@@ -103,6 +103,10 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
  * (src/camera/CameraModel.cpp:15-18): K, D are float matrices promoted to double; map1 = x, map2 = y. */
 void tbo_init_undistort_rectify_map(float fx, float fy, float cx, float cy, const float d[5], int w, int h,
                                     float *map1, float *map2);
+/* PinholeCamera::UndistortPoint (CameraModel.cpp:104-121) = cv::undistortPoints(src, dst, K, D, Mat(), K): 5 fixed-point
+ * iterations in double (radtan, k1 k2 p1 p2 k3), re-projection with K; identity when |d[0]| <= 1e-7 (:9). Pinned
+ * bit-exact against cv2 4.13 in tests/test_oracle_cv2.py. xy_in/xy_out: n x 2 floats. */
+void tbo_undistort_points(float fx, float fy, float cx, float cy, const float d[5], const float *xy_in, int n, float *xy_out);
 /* cv::remap(src, dst, map1, map2, INTER_LINEAR) with float maps, BORDER_CONSTANT 0 (PinholeCamera::UndistortImage,
  * CameraModel.cpp:96-102): 5 fractional bits, weights (32-fy)(32-fx)*32 of 2^15, (sum + 2^14) >> 15. */
 void tbo_remap_linear_u8(const uint8_t *src, int sw, int sh, int sstride, const float *map1, const float *map2,

@@ -73,6 +73,12 @@ def test_headless_test_matcher(tmp_path, oracle, images):
     proj = oracle.search_by_projection(oracle.MatcherParams(30, 50, 30, 1, 30.0), cam, T, k2, d2, None, sf, W, H, k1, valid, xyz, d1)
     assert got['projection'] == [str(len(proj)), '%x' % _digest(proj)]
     assert got['dist01'] == [str(oracle.hamming256(d1[0], d1[1]))]
+    # PinholeCamera::UndistortImage / UndistortPoint with a distorted camera
+    dd = [-0.28, 0.07, 0.0002, 0.00002, 0.0]
+    m1, m2 = oracle.init_undistort_rectify_map(718.856, 718.856, 607.1928, 185.2157, dd, W, H)
+    rect = oracle.remap_linear(images['left'], m1, m2)
+    un = oracle.undistort_points(718.856, 718.856, 607.1928, 185.2157, dd, np.stack([k1['x'], k1['y']], 1))
+    assert got['undistort'] == ['%x' % _fnv(rect.tobytes()), '%x' % _fnv(un.tobytes())]
     # searchByOPFlow(F1 = right frame, F2 = left frame with its keypoints), raw and CLAHE'd current image
     for eq in (0, 1):
         img1 = oracle.clahe(images['right'], 3.0, (8, 8)) if eq else images['right']

@@ -127,3 +127,37 @@ def test_frontend_upload_undistort_then_extract(tb, ctx, oracle, images):
     finally:
         fe.close()
         und.close()
+
+
+def test_undistort_points_host_device_frontend(tb, ctx, oracle, images):
+    """PinholeCamera::UndistortPoint / Frame::UnDistortPoints: double arithmetic in OpenCV's order, bit-exact."""
+    from .test_oracle_cv2 import POINT_CAMERAS
+    for c in POINT_CAMERAS:
+        w, h, fx, fy, cx, cy, d = c
+        rng = np.random.default_rng(w * 3 + h)
+        pts = np.stack([rng.uniform(-200, w + 200, 5000), rng.uniform(-100, h + 100, 5000)], 1).astype(np.float32)
+        exp = oracle.undistort_points(np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), d, pts)
+        got = ctx.undistort_points(_cam(tb, c), pts)
+        assert got.tobytes() == exp.tobytes(), c
+    assert ctx.undistort_points(_cam(tb, POINT_CAMERAS[0]), np.zeros((0, 2), np.float32)).shape == (0, 2)
+    # Frame::UnDistortPoints over the keypoints of an extraction (tb_keypoint stride), device-resident
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    c = POINT_CAMERAS[0]
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=2, max_target=tgt)
+    try:
+        fe.upload_frames(0, np.stack([images['left'], images['right']]))
+        fe.build_pyramid(2)
+        fe.extract(2, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(2)
+        out = torch.full((2, fe.kp_cap, 2), -7.0, dtype=torch.float32, device='cuda')
+        fe.undistort_points(_cam(tb, c), 2, out.data_ptr())
+        ctx.sync()
+        o = out.cpu().numpy()
+        for f in range(2):
+            n = counts[f]
+            exp = oracle.undistort_points(np.float32(c[2]), np.float32(c[3]), np.float32(c[4]), np.float32(c[5]), c[6], np.stack([kps[f, :n]['x'], kps[f, :n]['y']], 1))
+            assert o[f, :n].tobytes() == exp.tobytes() and (o[f, n:] == 0).all()
+    finally:
+        fe.close()

@@ -178,3 +178,25 @@ def test_lk_flow_matches_cv2_within_tolerance(oracle, images, max_level):
         close = ok.copy()
         close[ok] = d <= 1e-3
         assert np.abs(e1 - e2)[close].max() <= 0.05, name
+
+
+POINT_CAMERAS = CAMERAS + [
+    (1241, 376, 718.856, 700.5, 607.1928, 185.2157, [-3.0, 2.0, 0.1, 0.1, -1.0]),     # icdist < 0 branch for far points
+    (1241, 376, 718.856, 718.856, 607.1928, 185.2157, [1e-8, 0.2, 0.0, 0.0, 0.0]),    # mbDistortion false: identity
+]
+
+
+@pytest.mark.parametrize('cam', POINT_CAMERAS)
+def test_undistort_points_match_cv2(oracle, cam):
+    """PinholeCamera::UndistortPoint = cv::undistortPoints(src, dst, K, D, Mat(), K) (CameraModel.cpp:104-121): bit-exact."""
+    w, h, fx, fy, cx, cy, d = cam
+    rng = np.random.default_rng(w + h)
+    pts = np.stack([rng.uniform(-200, w + 200, 3000), rng.uniform(-100, h + 100, 3000)], 1).astype(np.float32)
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    D = np.array(d, np.float32)
+    got = oracle.undistort_points(K[0, 0], K[1, 1], K[0, 2], K[1, 2], D, pts)
+    if abs(D[0]) > 1e-7:
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K.astype(np.float64), D.astype(np.float64), None, K.astype(np.float64)).reshape(-1, 2)
+    else:
+        ref = pts
+    assert got.tobytes() == ref.tobytes()

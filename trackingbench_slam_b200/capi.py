@@ -40,6 +40,7 @@ EXPORTS = [
     'tb_clahe_device', 'tb_clahe_host',
     'tb_stereo_match', 'tb_frontend_stereo_match',
     'tb_lk_flow_host', 'tb_lk_flow_device', 'tb_frontend_search_by_opflow',
+    'tb_undistort_points', 'tb_undistort_points_device', 'tb_frontend_undistort_points',
 ]
 
 
@@ -249,6 +250,16 @@ class Context:
                                            _vp(next_dptr), C.c_size_t(next_pitch), C.c_size_t(next_frame_stride), int(n_next), int(w), int(h),
                                            len(a), _vp(a), _vp(b), _vp(pts_dptr), _vp(counts_dptr), int(pts_cap), _vp(next_pts_dptr),
                                            _vp(status_dptr), _vp(err_dptr)))
+
+    def undistort_points(self, cam, pts):
+        """PinholeCamera::UndistortPoint on n points (host in/out) -> [n, 2] float32."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        out = np.zeros_like(pts)
+        self.check(lib().tb_undistort_points(self.h, C.byref(cam), _vp(pts), len(pts), _vp(out)))
+        return out
+
+    def undistort_points_device(self, cam, pts_dptr, stride, n, out_dptr):
+        self.check(lib().tb_undistort_points_device(self.h, C.byref(cam), _vp(pts_dptr), C.c_size_t(stride), C.c_longlong(n), _vp(out_dptr)))
 
     def vocab_create(self, voc):
         """voc: vocab.Vocabulary -> DeviceVocabulary (tree resident in HBM)."""
@@ -574,3 +585,10 @@ def _frontend_search_by_opflow(self, params, n_frames, f1_frames, f2_frames, equ
 
 
 Frontend.search_by_opflow = _frontend_search_by_opflow
+
+
+def _frontend_undistort_points(self, cam, n_frames, out_dptr):
+    self.ctx.check(lib().tb_frontend_undistort_points(self.h, C.byref(cam), int(n_frames), _vp(out_dptr)))
+
+
+Frontend.undistort_points = _frontend_undistort_points

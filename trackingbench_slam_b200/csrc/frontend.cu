@@ -701,6 +701,13 @@ extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_
                                       fe->g[0].w, fe->g[0].h, min_level, max_level, search_r, (tb_match *)matches, capacity, (int *)counts);
 }
 
+extern "C" int tb_frontend_undistort_points(tb_frontend *fe, const tb_pinhole *cam, int n_frames, void *out)
+{
+    if (!fe || !cam || n_frames < 0 || n_frames > fe->B || !out) return TB_E_INVALID;
+    return tb_undistort_points_launch(fe->ctx, cam, (const uint8_t *)fe->kps, sizeof(tb_keypoint), sizeof(tb_keypoint) * (size_t)fe->kp_cap, fe->n_kp,
+                                      fe->kp_cap, n_frames, (float2 *)out);
+}
+
 extern "C" int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_frames, int n_pairs, const int32_t *f1_frames,
                                             const int32_t *f2_frames, int equalized, void *next_pts, void *status, void *err)
 {

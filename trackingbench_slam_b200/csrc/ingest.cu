@@ -590,3 +590,72 @@ extern "C" int tb_clahe_host(tb_ctx *ctx, const uint8_t *src, int w, int h, size
     if (e != cudaSuccess) return tb_fail(ctx, TB_E_CUDA, "tb_clahe_host: %s", cudaGetErrorString(e));
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// PinholeCamera::UndistortPoint / Frame::UnDistortPoints (src/camera/CameraModel.cpp:104-121, src/types/Frame.cpp:165-171)
+// = cv::undistortPoints(src, dst, K, D, Mat(), K): 5 fixed-point iterations of the radtan model in double, re-projection
+// with K. One thread per point; every operation is a single IEEE double operation in OpenCV's order (the library is built
+// with --fmad=false), bit-exact vs cv2 4.13 through the oracle.
+__global__ void __launch_bounds__(256)
+undistort_points_kernel(const uint8_t *__restrict__ pts, size_t stride, size_t slot_stride, const int *__restrict__ counts, int cap,
+                        tb_pinhole cam, float2 *__restrict__ out)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x, slot = blockIdx.y;
+    const int n = counts ? min(counts[slot], cap) : cap;
+    if (i >= cap) return;
+    float2 *o = out + (size_t)slot * cap + i;
+    if (i >= n) { *o = make_float2(0.f, 0.f); return; }
+    const float *p = reinterpret_cast<const float *>(pts + (size_t)slot * slot_stride + (size_t)i * stride);
+    const float pu = __ldg(p), pv = __ldg(p + 1);
+    if (!(fabsf(cam.d[0]) > 1e-7f)) { *o = make_float2(pu, pv); return; }     // mbDistortion false (CameraModel.cpp:9)
+    const double fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy;
+    const double k0 = cam.d[0], k1 = cam.d[1], k2 = cam.d[2], k3 = cam.d[3], k4 = cam.d[4];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double u = pu, v = pv;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+        if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+        const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+        const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0. * r2 + 0. * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+    *o = make_float2((float)(xx * ww), (float)(yy * ww));
+}
+
+int tb_undistort_points_launch(tb_ctx *ctx, const tb_pinhole *cam, const uint8_t *pts, size_t stride, size_t slot_stride, const int *counts,
+                               int cap, int n_slots, float2 *out)
+{
+    if (cap <= 0 || n_slots <= 0) return TB_OK;
+    ProfScope prof__(ctx, "undistort_points");
+    undistort_points_kernel<<<dim3(div_up(cap, 256), n_slots), 256, 0, ctx->stream>>>(pts, stride, slot_stride, counts, cap, *cam, out);
+    TB_LAUNCH_CHECK(ctx);
+    return TB_OK;
+}
+
+extern "C" int tb_undistort_points_device(tb_ctx *ctx, const tb_pinhole *cam, const void *pts_dptr, size_t stride, long long n, void *out_dptr)
+{
+    if (!ctx || !cam || n < 0 || n > 0x7fffffff || (n && (!pts_dptr || !out_dptr)) || stride < 8)
+        return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_points_device: bad arguments") : TB_E_INVALID;
+    return tb_undistort_points_launch(ctx, cam, (const uint8_t *)pts_dptr, stride, 0, nullptr, (int)n, 1, (float2 *)out_dptr);
+}
+
+extern "C" int tb_undistort_points(tb_ctx *ctx, const tb_pinhole *cam, const float *xy_in, int n, float *xy_out)
+{
+    if (!ctx || !cam || n < 0 || (n && (!xy_in || !xy_out))) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_points: bad arguments") : TB_E_INVALID;
+    if (n == 0) return TB_OK;
+    float2 *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, sizeof(float2) * (size_t)n) != cudaSuccess) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    if (cudaMalloc(&d_out, sizeof(float2) * (size_t)n) != cudaSuccess) { cudaFree(d_in); return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed"); }
+    int rc = TB_OK;
+    if (cudaMemcpyAsync(d_in, xy_in, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = tb_fail(ctx, TB_E_CUDA, "upload failed");
+    if (!rc) rc = tb_undistort_points_launch(ctx, cam, (const uint8_t *)d_in, sizeof(float2), 0, nullptr, n, 1, d_out);
+    if (!rc && (cudaMemcpyAsync(xy_out, d_out, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = tb_fail(ctx, TB_E_CUDA, "download failed");
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}

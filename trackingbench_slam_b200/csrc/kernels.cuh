@@ -72,6 +72,8 @@ int tb_window_set_bow_batched(tb_ctx *ctx, const tb_vocab *v, int n_frames, int 
 int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames, int n_frames,
                           const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const int32_t *node,
                           const uint8_t *mp_valid, int map_point_only, tb_match *matches, int capacity, int *out_counts);
+int tb_undistort_points_launch(tb_ctx *ctx, const tb_pinhole *cam, const uint8_t *pts, size_t stride, size_t slot_stride, const int *counts,
+                               int cap, int n_slots, float2 *out);
 int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, size_t prev_pitch, size_t prev_frame_stride, int n_prev,
                     const uint8_t *next, size_t next_pitch, size_t next_frame_stride, int n_next, int w, int h,
                     int n_pairs, const int32_t *prev_idx, const int32_t *next_idx,
