@@ -120,6 +120,10 @@ public:
         tb_check(tb_pyramid_geometry(imGray.cols, imGray.rows, nLevels, scale, mvScaleFactor.data(), w.data(), h.data()), ctx, "tb_pyramid_geometry");
         mvInvScaleFactor.assign(nLevels, 1.f);
         for (int i = 1; i < nLevels; i++) mvInvScaleFactor[i] = mvInvScaleFactor[i - 1] / scale;
+        mvLevelSigma2.assign(nLevels, 1.f); mvInvLevelSigma2.assign(nLevels, 1.f);           // Frame.cpp:20-28
+        for (int i = 1; i < nLevels; i++) { mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i]; mvInvLevelSigma2[i] = 1.f / mvLevelSigma2[i]; }
+        mfGridElementHeightInv = static_cast<float>(FRAME_GRID_COLS) / (float)imGray.cols;    // Frame.cpp:30-31 (names as in the reference)
+        mfGridElementWidthInv = static_cast<float>(FRAME_GRID_ROWS) / (float)imGray.rows;
         cols_ = imGray.cols; rows_ = imGray.rows;
         ComputePyramid(imGray, w, h);
         for (int i = 0; i < 16; i++) mTcw[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -136,6 +140,18 @@ public:
     }
     std::vector<cv::KeyPoint> &GetKeys() { return mvKeys; }
     cv::Mat GetDescriptors() const { return mDescriptors; }
+    cv::Mat GetDescriptor(int id) const { return mDescriptors.row(id); }
+    std::vector<cv::Mat> GetVectorDescriptors() const { std::vector<cv::Mat> v; v.reserve(mDescriptors.rows); for (int j = 0; j < mDescriptors.rows; j++) v.push_back(mDescriptors.row(j)); return v; }
+    std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+    // Frame.cpp:257-265
+    bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY) const
+    {
+        posX = (int)std::round((kp.pt.x) * mfGridElementWidthInv);
+        posY = (int)std::round((kp.pt.y) * mfGridElementHeightInv);
+        return !(posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS);
+    }
+    bool IsInImage(const float &, const float &) const { return false; }   // Frame.cpp:364-368: the reference's stub
     void AssignFeaturesToGrid() {}   // the grid is (re)built on the device inside each windowed query
     std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, int minLevel = -1, int maxLevel = -1) const
     {
@@ -215,7 +231,8 @@ protected:
     int nLevels;
     float scaleFactor;
     int cols_ = 0, rows_ = 0;
-    std::vector<float> mvScaleFactor, mvInvScaleFactor;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    float mfGridElementWidthInv = 0.f, mfGridElementHeightInv = 0.f;
     std::vector<cv::Mat> mvImagePyramid;
 };
 }  // namespace TRACKING_BENCH
