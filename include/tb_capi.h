@@ -326,7 +326,7 @@ int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_p
  * valid; err = OpenCV's mean absolute patch difference / 32. rejectWithF (RANSAC, matcher.cpp:751-755) is not included. */
 typedef struct {
     int32_t win;       /* reference: 21 (3..21) */
-    int32_t max_level; /* reference: 3 */
+    int32_t max_level; /* reference: 3; at most 7 levels above level 0 are built (else TB_E_UNSUPPORTED) */
     int32_t max_iter;  /* OpenCV default TermCriteria: 30 */
     float eps;         /* OpenCV default: 0.01 */
     float min_eig;     /* OpenCV default minEigThreshold: 1e-4 */

@@ -325,9 +325,10 @@ struct LkGeom { int levels; int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS], pitch[LK_MAX
 static void lk_geometry(int w, int h, int win, int max_level, LkGeom &g)
 {
     g.levels = 0; g.w[0] = w; g.h[0] = h; g.pitch[0] = 0; g.off[0] = 0; g.frame_bytes = 0;
-    for (int l = 1; l <= max_level && l < LK_MAX_LEVELS; l++) {   // buildOpticalFlowPyramid's stop rule
+    for (int l = 1; l <= max_level; l++) {   // buildOpticalFlowPyramid's stop rule
         const int lw = (g.w[l - 1] + 1) / 2, lh = (g.h[l - 1] + 1) / 2;
         if (lw <= win || lh <= win) break;
+        if (l >= LK_MAX_LEVELS) { g.levels = -1; return; }   // OpenCV would build more levels than the kernel holds
         g.w[l] = lw; g.h[l] = lh; g.pitch[l] = (int)align_up((size_t)lw, 16);
         g.off[l] = g.frame_bytes;
         g.frame_bytes += align_up((size_t)g.pitch[l] * lh, 256);
@@ -359,6 +360,7 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
     if (w < 2 || h < 2) return tb_fail(ctx, TB_E_UNSUPPORTED, "LK: image must be at least 2x2");
     LkGeom g;
     lk_geometry(w, h, p->win, p->max_level, g);
+    if (g.levels < 0) return tb_fail(ctx, TB_E_UNSUPPORTED, "LK: more than 7 pyramid levels above level 0 (image too large for this max_level)");
     if (!ctx->fws) ctx->fws = new FlowWs();
     FlowWs &W = *ctx->fws;
     const bool same = prev == next && prev_pitch == next_pitch && prev_frame_stride == next_frame_stride;
