@@ -45,6 +45,9 @@ def oracle():
 @pytest.fixture(scope='session')
 def tb():
     import trackingbench_slam_b200 as tb
+    from trackingbench_slam_b200 import build as B
+    if not os.path.exists(B.LIB):   # a fresh checkout: build the CUDA library once (nvcc cross-compiles without a GPU)
+        B.build()
     return tb
 
 
