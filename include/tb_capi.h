@@ -349,6 +349,14 @@ int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_f
                                  const int32_t *f2_frames, int equalized, void *next_pts_f32x2_dptr, void *status_u8_dptr,
                                  void *err_f32_dptr);
 
+/* LocalBA::AddMapPointsByStereo's live body (src/mapping/LocalBA.cpp:46-68) without rejectWithF: pair q tracks the keypoints of
+ * frame current_frames[q] into frame stereo_frames[q] (searchByOPFlow(stereo, current, pts, equalized, ...), :54) and writes
+ * depth_f32_dptr[q][i] = bf / |pts[i].x - kp[i].x| for every valid track, -1 elsewhere (:61-65). The tracks and their status
+ * are returned as well ([pair][tb_frontend_kp_capacity()]) so that the caller can run the reference's RANSAC rejection. */
+int tb_frontend_stereo_depth_by_opflow(tb_frontend *fe, const tb_lk_params *p, float bf, int n_frames, int n_pairs,
+                                       const int32_t *current_frames, const int32_t *stereo_frames, int equalized,
+                                       void *depth_f32_dptr, void *next_pts_f32x2_dptr, void *status_u8_dptr);
+
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];
  * f1_matched[i1] != 0 iff F1->GetMapPoint(i1)->Observations() > 0 (may be NULL). Tcw1 row-major 4x4. */

@@ -101,3 +101,40 @@ def test_lk_edge_cases(tb, ctx, oracle, images):
     n, s, e = ctx.lk_flow(tb.LKParams(), prev, nxt, pts)
     assert (s == es).all() and s[3] == 1 and not s[:2].any()
     assert n[3].tobytes() == en[3].tobytes() and n[:2].tobytes() == en[:2].tobytes()
+
+
+def test_frontend_stereo_depth_by_opflow(tb, ctx, oracle, images):
+    """LocalBA::AddMapPointsByStereo's live body (LocalBA.cpp:46-68) without the RANSAC rejection: LK tracks of the left
+    keypoints into the CLAHE'd right image, Depth = bf / |x_tracked - x_left|."""
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    frames = np.stack([images['left'], images['right']])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=2, max_target=tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(2)
+        fe.extract(2, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(2)
+        cap = fe.kp_cap
+        bf = np.float32(0.573 * 718.856)
+        for eq in (1, 0):
+            z = torch.zeros((1, cap), dtype=torch.float32, device='cuda')
+            pts = torch.zeros((1, cap, 2), dtype=torch.float32, device='cuda')
+            st = torch.zeros((1, cap), dtype=torch.uint8, device='cuda')
+            fe.stereo_depth_by_opflow(tb.LKParams(), bf, 2, [0], [1], eq, z.data_ptr(), pts.data_ptr(), st.data_ptr())
+            ctx.sync()
+            n = counts[0]
+            kp = np.stack([kps[0, :n]['x'], kps[0, :n]['y']], 1)
+            img1 = oracle.clahe(frames[1], 3.0, (8, 8)) if eq else frames[1]
+            en, es, _ = oracle.lk_flow(oracle.LKParams(), frames[0], img1, kp)
+            xi, yi = en[:, 0].astype(np.int32), en[:, 1].astype(np.int32)
+            es = es & ((xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)).astype(np.uint8)
+            with np.errstate(divide='ignore'):
+                ez = np.where(es == 1, bf / np.abs(en[:, 0] - kp[:, 0]), np.float32(-1.0)).astype(np.float32)
+            got = z[0].cpu().numpy()
+            assert (st[0, :n].cpu().numpy() == es).all() and got[:n].tobytes() == ez.tobytes() and (got[n:] == -1).all()
+            good = (es == 1) & (ez > 0) & (ez < 200)
+            assert good.sum() > 300
+    finally:
+        fe.close()

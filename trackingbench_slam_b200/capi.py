@@ -41,6 +41,7 @@ EXPORTS = [
     'tb_stereo_match', 'tb_frontend_stereo_match',
     'tb_lk_flow_host', 'tb_lk_flow_device', 'tb_frontend_search_by_opflow',
     'tb_undistort_points', 'tb_undistort_points_device', 'tb_frontend_undistort_points',
+    'tb_frontend_stereo_depth_by_opflow',
 ]
 
 
@@ -592,3 +593,13 @@ def _frontend_undistort_points(self, cam, n_frames, out_dptr):
 
 
 Frontend.undistort_points = _frontend_undistort_points
+
+
+def _frontend_stereo_depth_by_opflow(self, params, bf, n_frames, current_frames, stereo_frames, equalized, depth_dptr, next_pts_dptr, status_dptr):
+    fc = np.ascontiguousarray(current_frames, np.int32)
+    fs = np.ascontiguousarray(stereo_frames, np.int32)
+    self.ctx.check(lib().tb_frontend_stereo_depth_by_opflow(self.h, C.byref(params), C.c_float(bf), int(n_frames), len(fc), _vp(fc), _vp(fs),
+                                                            int(bool(equalized)), _vp(depth_dptr), _vp(next_pts_dptr), _vp(status_dptr)))
+
+
+Frontend.stereo_depth_by_opflow = _frontend_stereo_depth_by_opflow

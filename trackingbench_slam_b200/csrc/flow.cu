@@ -476,3 +476,29 @@ int tb_flow_eq_reserve(tb_ctx *ctx, size_t bytes, uint8_t **out)
     *out = W.eq;
     return TB_OK;
 }
+
+// LocalBA::AddMapPointsByStereo's live body (src/mapping/LocalBA.cpp:46-68) after the tracks: Depth[i] = bf / |pt_i.x - kp_i.x|
+// for every valid track, -1 elsewhere (one IEEE division).
+__global__ void __launch_bounds__(256)
+lk_stereo_depth(const LkPair *__restrict__ pairs, size_t pts_stride, int pts_cap, float bf, const float2 *__restrict__ tracked,
+                const uint8_t *__restrict__ status, float *__restrict__ depth)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= pts_cap) return;
+    const size_t o = (size_t)blockIdx.y * pts_cap + i;
+    float z = -1.0f;
+    if (status[o]) {
+        const float x0 = __ldg(reinterpret_cast<const float *>(pairs[blockIdx.y].pts + (size_t)i * pts_stride));
+        z = __fdiv_rn(bf, fabsf(__fsub_rn(tracked[o].x, x0)));
+    }
+    depth[o] = z;
+}
+
+int tb_flow_stereo_depth(tb_ctx *ctx, int n_pairs, size_t pts_stride, int pts_cap, float bf, const float2 *tracked, const uint8_t *status, float *depth)
+{
+    if (n_pairs <= 0 || pts_cap <= 0) return TB_OK;
+    ProfScope prof__(ctx, "lk_stereo_depth");   // pair descriptors are the ones tb_flow_batched has just uploaded
+    lk_stereo_depth<<<dim3(div_up(pts_cap, 256), n_pairs), 256, 0, ctx->stream>>>(ctx->fws->pairs, pts_stride, pts_cap, bf, tracked, status, depth);
+    TB_LAUNCH_CHECK(ctx);
+    return TB_OK;
+}

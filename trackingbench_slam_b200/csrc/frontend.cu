@@ -730,6 +730,17 @@ extern "C" int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params 
                            fe->n_kp, fe->kp_cap, 1, (float2 *)next_pts, (uint8_t *)status, (float *)err);
 }
 
+extern "C" int tb_frontend_stereo_depth_by_opflow(tb_frontend *fe, const tb_lk_params *p, float bf, int n_frames, int n_pairs,
+                                                  const int32_t *current_frames, const int32_t *stereo_frames, int equalized,
+                                                  void *depth, void *next_pts, void *status)
+{
+    if (!depth || !next_pts || !status) return TB_E_INVALID;
+    // searchByOPFlow(stereo_frame, current_frame, pts, equalized, ...): F1 = stereo frame, F2 = current frame with its keys (LocalBA.cpp:54)
+    int rc = tb_frontend_search_by_opflow(fe, p, n_frames, n_pairs, stereo_frames, current_frames, equalized, next_pts, status, nullptr);
+    if (rc) return rc;
+    return tb_flow_stereo_depth(fe->ctx, n_pairs, sizeof(tb_keypoint), fe->kp_cap, bf, (const float2 *)next_pts, (const uint8_t *)status, (float *)depth);
+}
+
 extern "C" int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames,
                                         const int32_t *right_frames, const float *inv_sf, void *matches, int capacity,
                                         void *counts, void *depth)

@@ -80,6 +80,7 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
                     const uint8_t *pts, size_t pts_stride, size_t pts_slot_stride, const int32_t *pts_slot, const int *counts, int pts_cap,
                     int check_in_frame, float2 *out_pts, uint8_t *out_status, float *out_err);
 int tb_flow_eq_reserve(tb_ctx *ctx, size_t bytes, uint8_t **out);
+int tb_flow_stereo_depth(tb_ctx *ctx, int n_pairs, size_t pts_stride, int pts_cap, float bf, const float2 *tracked, const uint8_t *status, float *depth);
 int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs, const int32_t *left_frames, const int32_t *right_frames,
                              const tb_keypoint *kps, const uint8_t *desc, int kp_cap, const int *counts, const float *inv_sf, int n_levels,
                              int n_rows, tb_match *matches, int capacity, int *out_counts, float *depth);
