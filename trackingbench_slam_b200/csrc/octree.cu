@@ -141,8 +141,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         // instead of L2 when it fits the launch's key cache
         if (n <= all.nid_cache_keys) nid = reinterpret_cast<uint16_t *>(p);
     }
-    __shared__ int s_L, s_exp, s_cut, s_fail;
-    if (tid == 0) s_fail = 0;
+    __shared__ int s_L, s_exp, s_cut;
 
     if (n == 0 || a.nIni <= 0) {
         if (tid == 0) a.n_kept[(size_t)f * a.n_stride] = 0;
@@ -339,7 +338,6 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
 
     // ---- best key per leaf (:700-716): max response, first in vKeys order
     const int L = s_L;
-    const int *cnt = S.cnt[cur]; (void)cnt;
     for (int i = tid; i < L; i += OCT_THREADS) { S.skey[i] = 0; S.aux2[i] = 1; }
     __syncthreads();
     for (int k = tid; k < n; k += OCT_THREADS) {
