@@ -43,7 +43,7 @@ def build(force=False):
         for f in ('tb_oracle.c', 'tb_oracle.h', 'orb_pattern.inc'))
     if force or src_newer or (os.path.exists('/root/reference/src/extractors/ORBextractor.cpp')
                               and not all(os.path.exists(os.path.join(_HERE, '_ref', n))
-                                          for n in ('libtb_ref.so', 'libtb_ref_bow.so'))):
+                                          for n in ('libtb_ref.so', 'libtb_ref_bow.so', 'libtb_ref_matcher.so'))):
         subprocess.check_call(['make', '-C', _HERE, '-s'] + (['-B'] if force else []))
 
 
@@ -502,3 +502,248 @@ def clahe(src, clip_limit=3.0, tiles=(8, 8)):
     lib().tbo_clahe_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], C.c_double(clip_limit), int(tiles[0]), int(tiles[1]),
                        _p(dst), dst.strides[0])
     return dst
+
+
+# ---- the reference's own Frame / MapPoint / Map / CameraModel / Matcher / FASTExtractor code -------------------
+# oracle/_ref/libtb_ref_matcher.so (oracle/ref_matcher_build.cpp): Frame.cpp, MapPoint.cpp, Map.cpp, CameraModel.cpp and
+# FASTextractor.cpp compiled unmodified, matcher.cpp's hot-path member functions by line range.
+def ref_matcher_available():
+    return os.path.exists(os.path.join(_HERE, '_ref', 'libtb_ref_matcher.so'))
+
+
+def ref_matcher_lib():
+    if 'matcher' not in _ref:
+        build()
+        L = C.CDLL(os.path.join(_HERE, '_ref', 'libtb_ref_matcher.so'))
+        for n in ('tbrefm_camera_new', 'tbrefm_frame_new', 'tbrefm_map_points_new', 'tbrefm_matcher_new', 'tbrefm_vocab_load_text'):
+            getattr(L, n).restype = C.c_void_p
+        L.tbrefm_shi_tomasi.restype = C.c_float
+        _ref['matcher'] = L
+    return _ref['matcher']
+
+
+class RefCamera:
+    """TRACKING_BENCH::PinholeCamera (src/camera/CameraModel.cpp, compiled unmodified)."""
+
+    def __init__(self, w, h, fx, fy, cx, cy, d=(0, 0, 0, 0, 0)):
+        self.L = ref_matcher_lib()
+        dd = np.ascontiguousarray(d, np.float32)
+        self.w, self.h = int(w), int(h)
+        self.h_ = C.c_void_p(self.L.tbrefm_camera_new(int(w), int(h), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(dd)))
+
+    def world2cam(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        uv = np.zeros(2, np.float32)
+        self.L.tbrefm_camera_world2cam(self.h_, _p(xyz), _p(uv))
+        return uv
+
+    def is_in_frame(self, x, y):
+        return bool(self.L.tbrefm_camera_is_in_frame(self.h_, int(x), int(y)))
+
+    def undistort_point(self, uv):
+        uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros(2, np.float32)
+        self.L.tbrefm_camera_undistort_point(self.h_, _p(uv), _p(out))
+        return out
+
+    def undistort_image(self, raw):
+        raw = _u8(raw)
+        out = np.zeros((self.h, self.w), np.uint8)
+        self.L.tbrefm_camera_undistort_image(self.h_, _p(raw), raw.shape[1], raw.shape[0], raw.strides[0], _p(out))
+        return out
+
+
+class RefFrame:
+    """TRACKING_BENCH::Frame (src/types/Frame.cpp, compiled unmodified): constructor = scale tables + ComputePyramid."""
+
+    def __init__(self, img, levels, scale, cam):
+        self.L = ref_matcher_lib()
+        img = _u8(img)
+        self.levels, self.cam, self.n = int(levels), cam, 0
+        self.h_ = C.c_void_p(self.L.tbrefm_frame_new(_p(img), img.shape[1], img.shape[0], img.strides[0], int(levels), C.c_float(scale), cam.h_))
+
+    def close(self):
+        if self.h_:
+            self.L.tbrefm_frame_free(self.h_)
+            self.h_ = None
+
+    def geometry(self):
+        n = self.levels
+        f = [np.zeros(n, np.float32) for _ in range(4)]
+        w, h = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.tbrefm_frame_geometry(self.h_, _p(f[0]), _p(f[1]), _p(f[2]), _p(f[3]), _p(w), _p(h))
+        return dict(sf=f[0], inv_sf=f[1], sigma2=f[2], inv_sigma2=f[3], w=w, h=h)
+
+    def level(self, l):
+        g = self.geometry()
+        out = np.zeros((int(g['h'][l]), int(g['w'][l])), np.uint8)
+        self.L.tbrefm_frame_level(self.h_, int(l), _p(out))
+        return out
+
+    def equalize(self):
+        g = self.geometry()
+        out = np.zeros((int(g['h'][0]), int(g['w'][0])), np.uint8)
+        self.L.tbrefm_frame_equalize(self.h_, _p(out))
+        return out
+
+    def set_keys(self, kps, desc, undistort=False):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = _u8(desc)
+        self.n = len(kps)
+        self.L.tbrefm_frame_set_keys(self.h_, _p(kps), _p(desc), len(kps), int(undistort))
+
+    def assign_grid(self):
+        self.L.tbrefm_frame_assign_grid(self.h_)
+
+    def set_pose(self, Tcw):
+        T = np.ascontiguousarray(Tcw, np.float32)
+        self.L.tbrefm_frame_set_pose(self.h_, _p(T))
+
+    def camera_center(self):
+        o = np.zeros(3, np.float32)
+        self.L.tbrefm_frame_camera_center(self.h_, _p(o))
+        return o
+
+    def pos_in_grid(self, kp):
+        kp = np.ascontiguousarray(kp, KP_DTYPE).reshape(1)
+        x, y = C.c_int(), C.c_int()
+        ok = self.L.tbrefm_frame_pos_in_grid(self.h_, _p(kp), C.byref(x), C.byref(y))
+        return bool(ok), x.value, y.value
+
+    def features_in_area(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.zeros(self.n + 1, np.int32)
+        n = self.L.tbrefm_frame_features_in_area(self.h_, C.c_float(x), C.c_float(y), C.c_float(r), int(minLevel), int(maxLevel), _p(out), len(out))
+        return out[:n].copy()
+
+    def undistort_points(self):
+        out = np.zeros((self.n, 2), np.float32)
+        self.L.tbrefm_frame_undistort_points(self.h_, _p(out))
+        return out
+
+    def set_feature_vector(self, node):
+        node = np.ascontiguousarray(node, np.int32)
+        self.L.tbrefm_frame_set_feature_vector(self.h_, _p(node), len(node))
+
+    def set_bow(self, voc_handle):
+        self.L.tbrefm_frame_set_bow(self.h_, voc_handle)
+
+    def feature_vector(self):
+        node = np.zeros(self.n, np.int32)
+        self.L.tbrefm_frame_get_feature_vector(self.h_, _p(node), self.n)
+        return node
+
+    def attach_map_point(self, idx, mps, i):
+        self.L.tbrefm_frame_attach_map_point(self.h_, int(idx), mps.h_, int(i))
+
+    def is_in_frustum(self, mps, i, view_cos_limit=0.5):
+        lvl, x, y, vc = C.c_int(), C.c_float(), C.c_float(), C.c_float()
+        ok = self.L.tbrefm_frame_is_in_frustum(self.h_, mps.h_, int(i), C.c_float(view_cos_limit), C.byref(lvl), C.byref(x), C.byref(y), C.byref(vc))
+        return bool(ok), lvl.value, x.value, y.value, vc.value
+
+
+class RefMapPoints:
+    """MapPoint::MapPoint (src/types/MapPoint.cpp:13-44) for every valid slot, created from key i of `frame` and held in a
+    Map; the points lie in one arena so that the Map's std::set (address order) iterates in slot order."""
+
+    def __init__(self, frame, valid, xyz, attach=True):
+        self.L = ref_matcher_lib()
+        self.valid = _u8(valid)
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        self.h_ = C.c_void_p(self.L.tbrefm_map_points_new(frame.h_, _p(self.valid), _p(xyz), len(self.valid), int(attach)))
+
+    def close(self):
+        if self.h_:
+            self.L.tbrefm_map_points_free(self.h_)
+            self.h_ = None
+
+    def set_bad(self, i):
+        self.L.tbrefm_map_point_set_bad(self.h_, int(i))
+
+    def set_obs(self, i, n):
+        self.L.tbrefm_map_point_set_obs(self.h_, int(i), int(n))
+
+    def get(self, i):
+        xyz, nrm, d = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(32, np.uint8)
+        self.L.tbrefm_map_point_get(self.h_, int(i), _p(xyz), _p(nrm), _p(d))
+        return xyz, nrm, d
+
+
+class RefMatcher:
+    """TRACKING_BENCH::Matcher: the member functions of src/matchers/matcher.cpp cut out by line range at build time."""
+
+    def __init__(self, low=50, high=100, histo=30, check=True, ratio=0.0):
+        self.L = ref_matcher_lib()
+        self.h_ = C.c_void_p(self.L.tbrefm_matcher_new())
+        self.set(low, high, histo, check, ratio)
+
+    def __del__(self):
+        try:
+            self.L.tbrefm_matcher_free(self.h_)
+        except Exception:
+            pass
+
+    def set(self, low, high, histo, check, ratio):
+        self.L.tbrefm_matcher_set(self.h_, int(low), int(high), int(histo), int(bool(check)), C.c_float(ratio))
+
+    @staticmethod
+    def _out(n):
+        return np.zeros(n + 1, MATCH_DTYPE)
+
+    def search_by_bf(self, f1, f2, minLevel, maxLevel, ratio, minTh):
+        out = self._out(f1.n)
+        n = self.L.tbrefm_search_by_bf(self.h_, f1.h_, f2.h_, int(minLevel), int(maxLevel), C.c_float(ratio), C.c_float(minTh), _p(out), len(out))
+        return out[:n].copy()
+
+    def search_by_violence(self, f1, f2, min_level=0, max_level=1, search_r=10.0, mp_only=False):
+        out = self._out(f1.n)
+        n = self.L.tbrefm_search_by_violence(self.h_, f1.h_, f2.h_, int(min_level), int(max_level), C.c_float(search_r), int(mp_only), _p(out), len(out))
+        return out[:n].copy()
+
+    def search_by_projection(self, f1, f2):
+        out = self._out(f2.n)
+        n = self.L.tbrefm_search_by_projection(self.h_, f1.h_, f2.h_, _p(out), len(out))
+        return out[:n].copy()
+
+    def search_by_projection_map(self, mps, f1, radio):
+        out = self._out(len(mps.valid))
+        n = self.L.tbrefm_search_by_projection_map(self.h_, mps.h_, f1.h_, C.c_float(radio), _p(out), len(out))
+        return out[:n].copy()
+
+    def search_by_bow(self, f1, f2, mp_only=False):
+        out = self._out(f1.n)
+        n = self.L.tbrefm_search_by_bow(self.h_, f1.h_, f2.h_, int(mp_only), _p(out), len(out))
+        return out[:n].copy()
+
+    def search_by_opflow(self, f1, f2, equalized=False):
+        out = self._out(f2.n)
+        cur = np.zeros((f2.n, 2), np.float32)
+        n = self.L.tbrefm_search_by_opflow(self.h_, f1.h_, f2.h_, int(equalized), _p(cur), _p(out), len(out))
+        return out[:n].copy(), cur
+
+    def descriptor_distance(self, a, b):
+        a, b = _u8(a), _u8(b)
+        return self.L.tbrefm_descriptor_distance(_p(a), _p(b))
+
+    def three_maxima(self, hist_sizes):
+        hs = np.ascontiguousarray(hist_sizes, np.int32)
+        a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+        self.L.tbrefm_three_maxima(_p(hs), len(hs), C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+
+def ref_fast_extract(levels, inv_sf, n_features, threshold, exit_kps=None):
+    """The reference's FASTExtractor (src/extractors/FASTextractor.cpp compiled unmodified; uzh-rpg/fast stand-in):
+    operator() (exit_kps None) / AddPoints. None where it throws std::out_of_range."""
+    L = ref_matcher_lib()
+    levels, ptrs, w, h, s = _level_args(levels)
+    inv_sf = np.ascontiguousarray(inv_sf, np.float32)
+    out = np.zeros(n_features + 1, KP_DTYPE)
+    ex = None if exit_kps is None else np.ascontiguousarray(exit_kps, KP_DTYPE)
+    n = L.tbrefm_fast_extract(ptrs, w, h, s, len(levels), _p(inv_sf), int(n_features), C.c_float(threshold),
+                              None if ex is None else _p(ex), -1 if ex is None else len(ex), _p(out), len(out))
+    return None if n < 0 else out[:n].copy()
+
+
+def ref_shi_tomasi(img, u, v):
+    img = _u8(img)
+    return ref_matcher_lib().tbrefm_shi_tomasi(_p(img), img.shape[1], img.shape[0], img.strides[0], int(u), int(v))

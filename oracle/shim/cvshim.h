@@ -18,7 +18,11 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_16SC2 11
 #define CV_32F 5
+#define CV_32FC1 5
+#define CV_32FC2 13
+#define CV_64F 6
 
 static inline int cvRound(double v) { return _mm_cvtsd_si32(_mm_set_sd(v)); }
 static inline int cvRound(float v) { return _mm_cvtss_si32(_mm_set_ss(v)); }
@@ -58,11 +62,23 @@ enum { BORDER_REFLECT_101 = 4 };
 
 struct MatStep {
     size_t v;
-    MatStep(size_t s = 0) : v(s) {}
+    size_t buf[2];
+    size_t* p;  // OpenCV exposes step.p[0] (FASTextractor.cpp:104)
+    MatStep(size_t s = 0) : v(s), p(buf) { buf[0] = s; buf[1] = 0; }
+    MatStep(const MatStep& o) : v(o.v), p(buf) { buf[0] = o.buf[0]; buf[1] = o.buf[1]; }
+    MatStep& operator=(const MatStep& o) { v = o.v; buf[0] = o.buf[0]; buf[1] = o.buf[1]; return *this; }
+    MatStep& operator=(size_t s) { v = s; buf[0] = s; return *this; }
     operator size_t() const { return v; }
 };
 
-struct MatZeros { int rows, cols; };
+struct MatZeros { int rows, cols, type; };
+
+// bytes per element of a CV_MAKETYPE(depth, channels) type code
+static inline size_t tb_elem_size(int type)
+{
+    static const size_t depth_size[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+    return depth_size[type & 7] * (size_t)((type >> 3) + 1);
+}
 
 class Mat {
 public:
@@ -70,36 +86,45 @@ public:
     uchar* data;
     int rows, cols;
     MatStep step;
-    Mat() : data(nullptr), rows(0), cols(0), step(0) {}
-    Mat(int r, int c, int /*type*/) : data(nullptr), rows(0), cols(0), step(0) { create(r, c, 0); }
-    // wrap external memory (no ownership)
-    Mat(int r, int c, int /*type*/, void* p, size_t s) : data((uchar*)p), rows(r), cols(c), step(s) {}
-    void create(int r, int c, int /*type*/) {
-        if (data && r == rows && c == cols) return;  // cv::Mat::create keeps the buffer when size/type match
-        buf.reset(new uchar[(size_t)r * c + 64], std::default_delete<uchar[]>());
-        data = buf.get(); rows = r; cols = c; step = (size_t)c;
+    int tp;
+    Mat() : data(nullptr), rows(0), cols(0), step(0), tp(0) {}
+    Mat(int r, int c, int type) : data(nullptr), rows(0), cols(0), step(0), tp(0) { create(r, c, type); }
+    Mat(Size sz, int type) : data(nullptr), rows(0), cols(0), step(0), tp(0) { create(sz.height, sz.width, type); }
+    // wrap external memory (no ownership); s == 0 is OpenCV's AUTO_STEP
+    Mat(int r, int c, int type, void* p, size_t s = 0) : data((uchar*)p), rows(r), cols(c), step(s ? s : (size_t)c * tb_elem_size(type)), tp(type) {}
+    size_t elemSize() const { return tb_elem_size(tp); }
+    void create(int r, int c, int type) {
+        if (data && r == rows && c == cols && type == tp) return;  // cv::Mat::create keeps the buffer when size/type match
+        const size_t esz = tb_elem_size(type);
+        buf.reset(new uchar[(size_t)r * c * esz + 64], std::default_delete<uchar[]>());
+        data = buf.get(); rows = r; cols = c; tp = type; step = (size_t)c * esz;
     }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
+    int type() const { return tp; }
     size_t step1() const { return step.v; }
-    template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step.v + c); }
-    template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step.v + c); }
+    template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step.v + (size_t)c * sizeof(T)); }
+    template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step.v + (size_t)c * sizeof(T)); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step.v; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step.v; }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step.v); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step.v); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step.v; m.rows = b - a; return m; }
-    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * elemSize(); m.cols = b - a; return m; }
+    Mat row(int r) const { return rowRange(r, r + 1); }
     Mat clone() const {
-        Mat m; m.create(rows, cols, 0);
-        for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), (size_t)cols);
+        Mat m; m.create(rows, cols, tp);
+        for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize());
         return m;
     }
-    static MatZeros zeros(int r, int c, int) { return MatZeros{r, c}; }
+    void copyTo(Mat& m) const {
+        m.create(rows, cols, tp);
+        for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * elemSize());
+    }
+    static MatZeros zeros(int r, int c, int type) { return MatZeros{r, c, type}; }
     Mat& operator=(const MatZeros& z) {  // MatExpr assignment: create() (no realloc on match) then fill
-        create(z.rows, z.cols, 0);
-        for (int r = 0; r < rows; r++) std::memset(ptr(r), 0, (size_t)cols);
+        create(z.rows, z.cols, z.type);
+        for (int r = 0; r < rows; r++) std::memset(ptr(r), 0, (size_t)cols * elemSize());
         return *this;
     }
 };

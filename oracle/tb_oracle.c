@@ -791,7 +791,7 @@ int tbo_search_by_violence(const tbo_matcher_params *p, const tbo_kp *k1, const 
             else if (dist < bestDist2) bestDist2 = dist;
         }
         if (bestDist <= p->TH_LOW && (float)bestDist < (float)bestDist2 * p->nRatio) {
-            tbo_match m = {i1, bestIdx2, 0, (float)bestDist};
+            tbo_match m = {i1, bestIdx2, -1, (float)bestDist};
             raw[n] = m;
             if (p->checkOrientation) {
                 float rot = k1[i1].angle - k2[bestIdx2].angle;
@@ -1005,7 +1005,7 @@ int tbo_search_by_bow(const tbo_matcher_params *p, const tbo_kp *k1, const u8 *d
                 else if (dist < bestDist2) bestDist2 = dist;
             }
             if (bestIdx2 >= 0 && bestDist1 < p->TH_LOW && (float)bestDist1 < p->nRatio * (float)bestDist2) {
-                tbo_match m = {idx1, bestIdx2, 0, (float)bestDist1};
+                tbo_match m = {idx1, bestIdx2, -1, (float)bestDist1};
                 raw[n] = m;
                 if (p->checkOrientation) {
                     float rot = k1[idx1].angle - k2[bestIdx2].angle;
@@ -1097,7 +1097,7 @@ int tbo_search_by_projection(const tbo_matcher_params *p, const tbo_pinhole *cam
             if (dist < bestDist) { bestDist = dist; bestIdx1 = i1; }
         }
         if (bestDist <= p->TH_HIGH) {
-            tbo_match m = {bestIdx1, i2, 0, (float)bestDist};
+            tbo_match m = {bestIdx1, i2, -1, (float)bestDist};
             raw[n] = m;
             if (p->checkOrientation) {
                 float rot = k2[i2].angle - k1[bestIdx1].angle;
@@ -1167,7 +1167,7 @@ int tbo_search_by_projection_map(const tbo_matcher_params *p, const tbo_pinhole 
         }
         if (bestDist <= p->TH_HIGH) {
             if (bestLevel == bestLevel2 && bestDist > radio * bestDist2) continue;
-            tbo_match m = {bestIdx, cnt - 1, 0, (float)bestDist};
+            tbo_match m = {bestIdx, cnt - 1, -1, (float)bestDist};
             out[n++] = m;
         }
     }

@@ -5,8 +5,9 @@ Sources of truth, strongest first:
   * extraction: oracle/_ref = the reference's own src/extractors/ORBextractor.cpp compiled unmodified
     (comparator pinned, oracle/ref_build.cpp) on pyramids made by the real cv2.resize;
   * primitives: the real OpenCV (cv2 4.13.0): resize / GaussianBlur level digests, BFMatcher lists;
-  * matchers whose arithmetic lives only in matcher.cpp (no OpenCV equivalent): the C restatement
-    (oracle/tb_oracle.c), stored so that later oracle edits cannot drift silently.
+  * windowed / projection matchers and the search grid: oracle/_ref/libtb_ref_matcher.so = the reference's own
+    Frame.cpp / MapPoint.cpp / Map.cpp / CameraModel.cpp compiled unmodified + matcher.cpp's member functions by
+    line range (oracle/ref_matcher_build.cpp).  The C restatement must reproduce every list (asserted here).
 """
 import hashlib
 import os
@@ -64,14 +65,20 @@ for pname in PARAM_SETS:
     thr = min(np.float32(10.0) * np.float32(mind), np.float32(30.0))
     filt = cross[cross['distance'] < thr]  # searchByBF(F1,F2,0,nLevels,10,30): matcher.cpp:209-218
     out = dict(cross=cross, filtered=filt)
-    # searchByViolence with setViolenceParam(30,100,30,true,5) / search_r 50 (test_matcher.cpp:70-72)
+    # searchByViolence with setViolenceParam(30,100,30,true,5) / search_r 50 (test_matcher.cpp:70-72) — run by the reference's code
     H, W = imgs['left'].shape
+    nl, sc = PARAM_SETS[pname][0], np.float32(PARAM_SETS[pname][1])
+    fx, fy, cx, cy, base = 718.856, 718.856, 607.1928, 185.2157, 0.573
+    rcam = O.RefCamera(W, H, fx, fy, cx, cy)
+    FL, FR = O.RefFrame(imgs['left'], nl, sc, rcam), O.RefFrame(imgs['right'], nl, sc, rcam)
+    FL.set_keys(kl, dl); FL.assign_grid()
+    FR.set_keys(kr, dr); FR.assign_grid()
+    assert O.RefMatcher().search_by_bf(FL, FR, 0, nl, 10.0, 30.0).tobytes() == filt.tobytes()
     p = O.MatcherParams(30, 100, 30, 1, 5.0)
-    nl = PARAM_SETS[pname][0]
-    out['violence'] = O.search_by_violence(p, kl, dl, kr, dr, W, H, 0, nl, 50.0)
+    out['violence'] = O.RefMatcher(30, 100, 30, True, 5.0).search_by_violence(FL, FR, 0, nl, 50.0)
+    assert out['violence'].tobytes() == O.search_by_violence(p, kl, dl, kr, dr, W, H, 0, nl, 50.0).tobytes()
     # config 2: stereo projection. Map points from the LEFT keypoints with depth = b*fx/disparity
     # (test_vo.cpp:414,496-498), right camera pose = translation (-0.573,0,0); searchByProjection(R, L)
-    fx, fy, cx, cy, base = 718.856, 718.856, 607.1928, 185.2157, 0.573
     cam = O.Pinhole(fx, fy, cx, cy, W, H, (O.C.c_float * 5)(0, 0, 0, 0, 0))
     disp = imgs['disparity']
     u = np.clip(kl['x'].astype(np.int32), 0, W - 1)
@@ -82,16 +89,26 @@ for pname in PARAM_SETS:
     xyz = np.stack([(kl['x'] - np.float32(cx)) / np.float32(fx) * depth, (kl['y'] - np.float32(cy)) / np.float32(fy) * depth, depth], 1).astype(np.float32)
     T = np.eye(4, dtype=np.float32)
     T[0, 3] = -base
-    sf = O.scale_factors(nl, PARAM_SETS[pname][1])
+    FL.set_pose(np.eye(4, dtype=np.float32))
+    FR.set_pose(T)
+    # one MapPoint per left key (MapPoint::MapPoint: descriptor of the key, normal from the left camera centre); keys without
+    # disparity carry a point flagged bad, so slot i of the Map == key i and trainIdx counts every slot (matcher.cpp:549-553)
+    mps = O.RefMapPoints(FL, np.ones(len(kl), np.uint8), xyz, attach=True)
+    for i in np.flatnonzero(valid == 0):
+        mps.set_bad(i)
+    sf = O.scale_factors(nl, sc)
     pp = O.MatcherParams(30, 50, 30, 1, 30.0)  # setProjectionParam(30,50,30,true,30)
-    out['projection'] = O.search_by_projection(pp, cam, T, kr, dr, None, sf, W, H, kl, valid, xyz, dl)
+    out['projection'] = O.RefMatcher(30, 50, 30, True, 30.0).search_by_projection(FR, FL)
+    assert out['projection'].tobytes() == O.search_by_projection(pp, cam, T, kr, dr, None, sf, W, H, kl, valid, xyz, dl).tobytes()
     out['mp_valid'] = valid
     out['mp_xyz'] = xyz
-    # searchByProjection(map, F1, radio): same map points, normals = unit vector from the left camera centre
-    nrm = xyz / np.maximum(np.linalg.norm(xyz, axis=1, keepdims=True), 1e-9)
+    nrm = np.stack([mps.get(i)[1] for i in range(len(kl))]).astype(np.float32)
+    nrm[valid == 0] = 0
     pm = O.MatcherParams(30, 100, 30, 1, 5.0)
-    out['projection_map'] = O.search_by_projection_map(pm, cam, T, kr, dr, None, sf, W, H, 1 - valid, xyz, nrm.astype(np.float32), dl, 0.8)
-    out['mp_normal'] = nrm.astype(np.float32)
+    out['projection_map'] = O.RefMatcher(30, 100, 30, True, 5.0).search_by_projection_map(mps, FR, 0.8)
+    assert out['projection_map'].tobytes() == O.search_by_projection_map(pm, cam, T, kr, dr, None, sf, W, H, 1 - valid, xyz, nrm, dl, 0.8).tobytes()
+    out['mp_normal'] = nrm
+    mps.close(); FL.close(); FR.close()
     np.savez_compressed(os.path.join(G, 'match_%s.npz' % pname), **out)
     print(pname, 'cross', len(cross), 'filtered', len(filt), 'violence', len(out['violence']),
           'projection', len(out['projection']), 'projection_map', len(out['projection_map']))

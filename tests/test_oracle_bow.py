@@ -86,7 +86,7 @@ def _bow_py(p, k1, d1, n1, k2, d2, n2, mv, mpo):
                 elif dist < best2:
                     best2 = dist
             if best1 < p.TH_LOW and np.float32(best1) < np.float32(p.nRatio) * np.float32(best2):
-                raw.append((i1, bidx, 0, float(best1)))
+                raw.append((i1, bidx, -1, float(best1)))   # cv::DMatch(q, t, dist) leaves imgIdx = -1
                 if p.checkOrientation:
                     rot = np.float32(k1['angle'][i1]) - np.float32(k2['angle'][bidx])
                     if rot < 0:

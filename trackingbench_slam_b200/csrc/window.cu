@@ -398,7 +398,7 @@ emit_matches(const QRes *res, int n, int check_orientation, int histo, tb_match 
                     const int pos = run + s_chunk[i];
                     if (pos < capacity) {
                         const QRes r = res[base + i];
-                        tb_match mt = {r.q, r.t, 0, (float)r.dist};
+                        tb_match mt = {r.q, r.t, -1, (float)r.dist};
                         out[pos] = mt;
                     }
                 }
@@ -440,6 +440,7 @@ static int build_grid(tb_ctx *ctx, DevBuf &buf, const tb_keypoint *d_kps, int n,
 static int emit_and_download(tb_ctx *ctx, DevBuf &buf, const QRes *res, int nq, int check, int histo, tb_match *out, int capacity, int *n)
 {
     if (histo > 256 || histo < 1) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (check && histo < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     tb_match *d_out = buf.alloc<tb_match>(nq);
     int *d_n = buf.alloc<int>(1);
     if (!d_out || !d_n) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
@@ -711,7 +712,7 @@ emit_matches_batched(const ProjPair *__restrict__ pairs, const QRes *__restrict_
             for (int i = tid; i < m; i += 256) {
                 if (mine[nm++]) {
                     const int pos = run + s_chunk[i];
-                    if (pos < capacity) { const QRes r = rs[base + i]; tb_match mt = {r.q, r.t, 0, (float)r.dist}; o[pos] = mt; }
+                    if (pos < capacity) { const QRes r = rs[base + i]; tb_match mt = {r.q, r.t, -1, (float)r.dist}; o[pos] = mt; }
                 }
             }
             __syncthreads();
@@ -789,6 +790,7 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
     if (n_pairs <= 0) return TB_OK;
     if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched projection matcher supports up to 8192 keypoints per frame");
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (p->checkOrientation && p->HISTO_LENGTH < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
     if (rc) return rc;
     WinWs &w = *ctx->wws;
@@ -1123,6 +1125,7 @@ int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, 
     (void)n_frames;
     if (n_pairs <= 0) return TB_OK;
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (p->checkOrientation && p->HISTO_LENGTH < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     int rc = win_ws_reserve(ctx, 0, n_pairs, kp_cap, false);
     if (rc) return rc;
     WinWs &w = *ctx->wws;
@@ -1151,6 +1154,7 @@ int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pa
     if (n_pairs <= 0) return TB_OK;
     if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched windowed matcher supports up to 8192 keypoints per frame");
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
+    if (p->checkOrientation && p->HISTO_LENGTH < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
     if (rc) return rc;
     WinWs &w = *ctx->wws;
