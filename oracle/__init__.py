@@ -747,3 +747,13 @@ def ref_fast_extract(levels, inv_sf, n_features, threshold, exit_kps=None):
 def ref_shi_tomasi(img, u, v):
     img = _u8(img)
     return ref_matcher_lib().tbrefm_shi_tomasi(_p(img), img.shape[1], img.shape[0], img.strides[0], int(u), int(v))
+
+
+def ref_stereo_rowband(current, stereo, bf, fx):
+    """The block-commented ORB stereo matcher of LocalBA::AddMapPointsByStereo (src/mapping/LocalBA.cpp:69-288) compiled from
+    its own text (oracle/ref_matcher_build.cpp): current/stereo = RefFrame with keys -> (matches, depth[N])."""
+    L = ref_matcher_lib()
+    depth = np.zeros(current.n, np.float32)
+    out = np.zeros(current.n + 1, MATCH_DTYPE)
+    n = L.tbrefm_stereo_rowband(current.h_, stereo.h_, C.c_float(bf), C.c_float(fx), _p(depth), _p(out), len(out))
+    return out[:n].copy(), depth

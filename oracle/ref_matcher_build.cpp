@@ -41,6 +41,22 @@
 #include "src/extractors/FASTextractor.cpp"
 #include "_ref/matcher_extract.inc"
 
+// LocalBA::AddMapPointsByStereo's block-commented ORB row-band matcher (LocalBA.cpp:69-288) compiled from its own text as
+// the body of a function with the live function's parameters; its final cv::imshow("Stereo", show) is the hook that
+// hands the local `matches` vector out.
+namespace cv { inline void tb_capture_matches(const std::vector<DMatch>& m); }
+namespace TRACKING_BENCH {
+static std::vector<cv::DMatch> tb_stereo_matches;
+#define imshow(name, img) tb_capture_matches(matches)
+static std::vector<float> tb_stereo_rowband_body(const std::shared_ptr<Frame>& current_frame, const std::shared_ptr<Frame>& stereo_frame,
+                                                 const float bf, const float fx)
+{
+#include "_ref/stereo_extract.inc"
+}
+#undef imshow
+}  // namespace TRACKING_BENCH
+namespace cv { inline void tb_capture_matches(const std::vector<DMatch>& m) { TRACKING_BENCH::tb_stereo_matches = m; } }
+
 using namespace TRACKING_BENCH;
 
 typedef std::shared_ptr<Frame> FramePtr;
@@ -290,6 +306,14 @@ void tbrefm_three_maxima(const int32_t* hist_sizes, int L, int* i1, int* i2, int
     std::vector<std::vector<int> > h((size_t)L);
     for (int i = 0; i < L; i++) h[i].resize((size_t)hist_sizes[i]);
     Matcher::ComputeThreeMaxima(h.data(), L, *i1, *i2, *i3);
+}
+
+// ---- ORB stereo row-band matcher (LocalBA.cpp:69-288, dead code in the reference): depth[N] and the match list
+int tbrefm_stereo_rowband(void* current, void* stereo, float bf, float fx, float* depth, tbo_match* out, int cap)
+{
+    std::vector<float> d = tb_stereo_rowband_body(*(FramePtr*)current, *(FramePtr*)stereo, bf, fx);
+    for (size_t i = 0; i < d.size(); i++) depth[i] = d[i];
+    return put_matches(tb_stereo_matches, out, cap);
 }
 
 // ---- FASTExtractor (FASTextractor.cpp, whole file): operator() when n_exit < 0, AddPoints otherwise.

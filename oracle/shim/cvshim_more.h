@@ -165,5 +165,12 @@ inline Mat findFundamentalMat(const std::vector<Point2f>&, const std::vector<Poi
     std::abort();
 }
 
+// drawing / display calls of the block-commented stereo matcher (LocalBA.cpp:104-105,153-158,279-286): no-ops
+#define CV_GRAY2BGR 8
+struct Scalar { Scalar(double = 0, double = 0, double = 0, double = 0) {} };
+inline void cvtColor(const Mat&, Mat&, int) {}
+template <typename P> inline void circle(Mat&, P, int, Scalar, int = 1) {}
+template <typename P, typename Q> inline void line(Mat&, P, Q, Scalar, int = 1) {}
+
 }  // namespace cv
 #endif

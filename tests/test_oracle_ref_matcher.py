@@ -419,3 +419,34 @@ def test_opflow_and_ingest_glue_equal_reference(images):
     f.set_keys(kl[:200], dl[:200], undistort=True)
     assert np.array_equal(f.undistort_points(), exp)
     f.close()
+
+
+# ------------------------------------------------------------------ f3: ORB stereo row-band matcher (LocalBA.cpp:69-288, dead code in the
+# reference: its text is compiled by line range as a function body — the strongest pin a block that the reference never builds can have)
+@pytest.mark.parametrize('pname', sorted(PARAM_SETS))
+def test_stereo_rowband_equals_reference_text(images, pname):
+    nl, sc = PARAM_SETS[pname][:2]
+    h, w = images['left'].shape
+    cam = O.RefCamera(w, h, FX, FY, CX, CY)
+    kl, dl = _ext('left', pname)
+    kr, dr = _ext('right', pname)
+    fl, fr = O.RefFrame(images['left'], nl, np.float32(sc), cam), O.RefFrame(images['right'], nl, np.float32(sc), cam)
+    inv_sf = fl.geometry()['inv_sf']
+
+    def inside(k):
+        # LocalBA.cpp:89-90 writes vRowIndices[yi] unchecked: a key whose band [floor(y-r), ceil(y+r)] leaves the image is an
+        # out-of-bounds write in the reference (it crashes on the 8-level sets, where the `pt *= sf` keys sit near row 0).
+        # The oracle and the CUDA path drop those rows; the comparison with the reference's text uses the keys it can take.
+        r = np.float32(2) * inv_sf[k['octave']]
+        return (np.floor(k['y'] - r) >= 0) & (np.ceil(k['y'] + r) <= h - 1)
+
+    ml, mr = inside(kl), inside(kr)
+    kl, dl, kr, dr = kl[ml], dl[ml], kr[mr], dr[mr]
+    fl.set_keys(kl, dl); fr.set_keys(kr, dr)
+    for (cur, ste, kc, dc, ks, ds) in [(fl, fr, kl, dl, kr, dr), (fr, fl, kr, dr, kl, dl)]:
+        ref_m, ref_d = O.ref_stereo_rowband(cur, ste, BASE * FX, FX)
+        got_m, got_d = O.stereo_rowband(O.StereoParams(bf=BASE * FX), kc, dc, ks, ds, inv_sf, h)
+        assert len(ref_m) > 30
+        assert ref_m.tobytes() == got_m.tobytes()
+        assert ref_d.tobytes() == got_d.tobytes()
+    fl.close(); fr.close()
