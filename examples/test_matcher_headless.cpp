@@ -33,7 +33,7 @@ static unsigned long long fnv(const void *p, size_t n, unsigned long long h = 14
 static unsigned long long digest(const std::vector<cv::DMatch> &m)
 {
     unsigned long long h = 1469598103934665603ull;
-    for (auto &x : m) { int v[2] = {x.queryIdx, x.trainIdx}; h = fnv(v, sizeof v, h); h = fnv(&x.distance, 4, h); }
+    for (auto &x : m) { int v[3] = {x.queryIdx, x.trainIdx, x.imgIdx}; h = fnv(v, sizeof v, h); h = fnv(&x.distance, 4, h); }
     return h;
 }
 
@@ -82,6 +82,23 @@ int main(int argc, char **argv)
     matches = matcher_ptr->searchByProjection(frame2_ptr, frame1_ptr);
     std::printf("projection %zu %llx\n", matches.size(), digest(matches));
     std::printf("dist01 %d\n", Matcher::DescriptorDistance(descriptors1.row(0), descriptors1.row(1)));
+
+    // AddPoints after the extractor's workspace was re-sized by a larger target: the per-level budget of the last operator()
+    // (mnFeaturesPerLevel) must survive, as it does in the reference (test_frame.cpp:36 flow)
+    {
+        std::vector<cv::KeyPoint> exitPoints, newPoints;
+        for (size_t i = 0; i < keypoints1.size(); i += 5) exitPoints.push_back(keypoints1[i]);
+        cv::Mat nd;
+        extractor_ptr->operator()(frame1_ptr->GetImagePyramid(), frame1_ptr->GetScaleFactors(), 1000, 80, 30, keypoints1, descriptors1);
+        std::vector<float> sfv = frame1_ptr->GetScaleFactors();   // AddPoints takes the factors by non-const reference (ORBextractor.h:58)
+        extractor_ptr->AddPoints(frame1_ptr->GetImagePyramid(), sfv, 1500, 80, 30, exitPoints, newPoints, nd);
+        std::printf("addpoints %zu %llx\n", newPoints.size(), fnv(newPoints.data(), newPoints.size() * sizeof(cv::KeyPoint)));
+        ExtractorNode root, c1, c2, c3, c4;
+        root.UL = cv::Point2i(0, 0); root.UR = cv::Point2i(101, 0); root.BL = cv::Point2i(0, 57); root.BR = cv::Point2i(101, 57);
+        for (auto &k : keypoints1) if (k.pt.x < 101 && k.pt.y < 57) root.vKeys.push_back(k);
+        root.DivideNode(c1, c2, c3, c4);
+        std::printf("dividenode %zu %zu %zu %zu %zu %d %d\n", root.vKeys.size(), c1.vKeys.size(), c2.vKeys.size(), c3.vKeys.size(), c4.vKeys.size(), c1.UR.x, c1.BL.y);
+    }
 
     // a distorted camera: PinholeCamera::UndistortImage / UndistortPoint (CameraModel.cpp:96-121, test_vo.cpp:178)
     {

@@ -3,11 +3,45 @@
 // (src/extractors/ORBextractor.cpp:840-978) are replaced by one call into the CUDA library.
 #ifndef TRACKING_BENCH_ORBEXTRACTOR_H
 #define TRACKING_BENCH_ORBEXTRACTOR_H
+#include <cmath>
+#include <list>
 #include <vector>
 #include "../tb_cv_compat.h"
 #include "../tb_runtime.h"
 
 namespace TRACKING_BENCH {
+// ORBextractor.h:9-21 — the quadtree node of DistributeOctTree.  The distribution itself runs on the device
+// (csrc/octree.cu); the type is kept so that code written against the reference header still compiles.  DivideNode
+// (ORBextractor.cpp:416-491): children split at ceil(w/2), ceil(h/2); a key goes left/up when its coordinate is strictly
+// below the split; a child holding exactly one key is final (bNoMore).
+class ExtractorNode {
+public:
+    ExtractorNode() : bNoMore(false) {}
+    void DivideNode(ExtractorNode &n1, ExtractorNode &n2, ExtractorNode &n3, ExtractorNode &n4)
+    {
+        ExtractorNode *child[4] = {&n1, &n2, &n3, &n4};
+        const int mx = UL.x + (int)std::ceil(static_cast<float>(UR.x - UL.x) / 2), my = UL.y + (int)std::ceil(static_cast<float>(BR.y - UL.y) / 2);
+        const int xs[3] = {UL.x, mx, UR.x}, ys[3] = {UL.y, my, BL.y};
+        for (int q = 0; q < 4; q++) {   // q = 2*row + column: n1 upper-left, n2 upper-right, n3 lower-left, n4 lower-right
+            const int cx = q & 1, cy = q >> 1;
+            child[q]->UL = cv::Point2i(xs[cx], ys[cy]);     child[q]->UR = cv::Point2i(xs[cx + 1], ys[cy]);
+            child[q]->BL = cv::Point2i(xs[cx], ys[cy + 1]); child[q]->BR = cv::Point2i(xs[cx + 1], ys[cy + 1]);
+            child[q]->vKeys.reserve(vKeys.size());
+            child[q]->vExitKeys.reserve(vExitKeys.size());
+        }
+        n2.BR.y = my; n4.BR = BR;   // right column ends at this node's own right edge (UR.x / BR), as in the reference
+        auto quadrant = [&](const cv::KeyPoint &kp) { return (kp.pt.x < (float)mx ? 0 : 1) + (kp.pt.y < (float)my ? 0 : 2); };
+        for (const cv::KeyPoint &kp : vKeys) child[quadrant(kp)]->vKeys.push_back(kp);
+        for (const cv::KeyPoint &kp : vExitKeys) child[quadrant(kp)]->vExitKeys.push_back(kp);
+        for (int q = 0; q < 4; q++) if (child[q]->vKeys.size() == 1) child[q]->bNoMore = true;
+    }
+    std::vector<cv::KeyPoint> vKeys;
+    std::vector<cv::KeyPoint> vExitKeys;
+    cv::Point2i UL, UR, BL, BR;
+    std::list<ExtractorNode>::iterator lit;
+    bool bNoMore;
+};
+
 class ORBExtractor {
 public:
     enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
@@ -45,10 +79,15 @@ protected:
         std::vector<int32_t> w(L), h(L);
         for (int l = 0; l < L; l++) { w[l] = images[l].cols; h[l] = images[l].rows; }
         if (!fe_ || w != w_ || h != h_ || target > max_target_) {   // (re)size the device workspace
-            if (fe_) tb_frontend_destroy(fe_);
+            // mnFeaturesPerLevel (ORBextractor.h:88) outlives the workspace: AddPoints after a re-size still finds the budget
+            int32_t budget[TB_MAX_LEVELS] = {0};
+            int nb = 0;
+            if (fe_) { tb_frontend_get_budget(fe_, budget, &nb); tb_frontend_destroy(fe_); }
             fe_ = nullptr;
             max_target_ = target > max_target_ ? target : max_target_;
+            for (int l = 0; l < nb; l++) if (budget[l] > max_target_) max_target_ = budget[l];
             tb_check(tb_frontend_create(ctx, L, w.data(), h.data(), 1, max_target_, &fe_), ctx, "tb_frontend_create");
+            if (nb == L) tb_check(tb_frontend_set_budget(fe_, budget, nb), ctx, "tb_frontend_set_budget");
             w_ = w; h_ = h;
         }
         std::vector<const uint8_t *> ptr(L);

@@ -177,7 +177,7 @@ private:
     {
         std::vector<cv::DMatch> out;
         out.reserve(n);
-        for (int i = 0; i < n; i++) out.push_back(cv::DMatch(m[i].queryIdx, m[i].trainIdx, m[i].distance));
+        for (int i = 0; i < n; i++) out.push_back(cv::DMatch(m[i].queryIdx, m[i].trainIdx, m[i].imgIdx, m[i].distance));   // imgIdx: 0 from BFMatcher, -1 from DMatch(q,t,dist)
         return out;
     }
 };

@@ -122,6 +122,11 @@ int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames);
 int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
                         const tb_keypoint *exit_kps, int n_exit);
 
+/* ORBExtractor::mnFeaturesPerLevel (include/extractors/ORBextractor.h:88; written by operator(), read by AddPoints): read it
+ * out of a frontend (n_levels = 0 while no extract has run) and install it into another one of the same level count. */
+int tb_frontend_get_budget(const tb_frontend *fe, int32_t *per_level /*[TB_MAX_LEVELS]*/, int *n_levels);
+int tb_frontend_set_budget(tb_frontend *fe, const int32_t *per_level, int n_levels);
+
 /* Results of the last extract. Device views: keypoints of frame f at kps + f*kp_capacity,
  * descriptors at desc + f*kp_capacity*32, counts[f]. */
 int tb_frontend_results_device(const tb_frontend *fe, void **kps_dptr, void **desc_dptr, void **counts_dptr);

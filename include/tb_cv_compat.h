@@ -46,6 +46,7 @@ struct DMatch {
     float distance;
     DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.402823466e+38f) {}
     DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    DMatch(int q, int t, int i, float d) : queryIdx(q), trainIdx(t), imgIdx(i), distance(d) {}
 };
 // 2-D, 8-bit, single channel, reference counted; enough for images and descriptor matrices.
 class Mat {

@@ -25,7 +25,7 @@ def med(fn, n=30):
 
 
 for name, (imgs, nl, sc, tgt, a, b) in {
-        'kitti_1241x376_5lvl_0.8_1000_80_30': ([cv2.imread(os.path.join(ROOT, 'tests/golden/data', n + '.png'), 0) for n in ('left', 'right')], 5, 0.8, 1000, 80.0, 30.0),
+        'kitti_1241x376_5lvl_0.8_1000_80_30': ([cv2.imread(os.path.join(ROOT, 'trackingbench_slam_b200/data', n + '.png'), 0) for n in ('left', 'right')], 5, 0.8, 1000, 80.0, 30.0),
         'synthetic_1920x1080_8lvl_1.2_2000_20_7': ([synth_frame(0, 1920, 1080), synth_frame(1, 1920, 1080)], 8, 1 / 1.2, 2000, 20.0, 7.0)}.items():
     H, W = imgs[0].shape
     sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)

@@ -5,8 +5,8 @@ import numpy as np, cv2
 import oracle as O
 import trackingbench_slam_b200 as tb
 
-left = cv2.imread('tests/golden/data/left.png', 0)
-right = cv2.imread('tests/golden/data/right.png', 0)
+left = cv2.imread('trackingbench_slam_b200/data/left.png', 0)
+right = cv2.imread('trackingbench_slam_b200/data/right.png', 0)
 ctx = tb.Context(0)
 fails = 0
 def check(name, ok, extra=''):

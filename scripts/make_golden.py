@@ -22,7 +22,7 @@ import oracle as O  # noqa: E402
 from tests.conftest import PARAM_SETS  # noqa: E402
 
 G = os.path.join(ROOT, 'tests', 'golden')
-imgs = {n: cv2.imread(os.path.join(G, 'data', n + '.png'), 0) for n in ('left', 'right', 'disparity')}
+imgs = {n: cv2.imread(os.path.join(ROOT, 'trackingbench_slam_b200', 'data', n + '.png'), 0) for n in ('left', 'right', 'disparity')}
 assert O.ref_available(), 'oracle/_ref missing: run make -C oracle'
 ref = O.RefExtractor()
 

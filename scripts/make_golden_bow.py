@@ -43,7 +43,7 @@ for vname, (k, L, seed, levelsup) in VOCABS.items():
         kl, dl, nl = feats['left']
         kr, dr, nr = feats['right']
         import cv2
-        left, right = (cv2.imread(os.path.join(G, 'data', n + '.png'), 0) for n in ('left', 'right'))
+        left, right = (cv2.imread(os.path.join(ROOT, 'trackingbench_slam_b200', 'data', n + '.png'), 0) for n in ('left', 'right'))
         nlv, sc = PARAM_SETS[pname][0], np.float32(PARAM_SETS[pname][1])
         cam = O.RefCamera(left.shape[1], left.shape[0], 718.856, 718.856, 607.1928, 185.2157)
         FL, FR = O.RefFrame(left, nlv, sc, cam), O.RefFrame(right, nlv, sc, cam)

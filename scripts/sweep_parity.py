@@ -13,7 +13,7 @@ from trackingbench_slam_b200.synth import synth_frame
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-left = cv2.imread(os.path.join(ROOT, 'tests/golden/data/left.png'), 0)
+left = cv2.imread(os.path.join(ROOT, 'trackingbench_slam_b200/data/left.png'), 0)
 ctx = tb.Context(0)
 bad = 0
 t0 = time.time()

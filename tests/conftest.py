@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-DATA = os.path.join(GOLDEN, 'data')
+DATA = os.path.join(ROOT, 'trackingbench_slam_b200', 'data')   # the package's input images (the reference's data/*.png)
 
 # (n_levels, scale, target, initTh, minTh): A = the reference's own call sites
 # (test_matcher.cpp:25-39, test_vo.cpp:194-200), B = BASELINE.json's "8 levels, scale 1.2".

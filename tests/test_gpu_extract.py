@@ -284,12 +284,12 @@ def test_fast_corner_list_overflow_path_is_exact():
 import os, sys, numpy as np, cv2
 sys.path.insert(0, %r)
 import trackingbench_slam_b200 as tb
-from tests.conftest import PARAM_SETS, GOLDEN
+from tests.conftest import PARAM_SETS, GOLDEN, DATA
 ctx = tb.Context(0)
 for pname in ('A1000', 'B2000'):
     nl, sc, tgt, a, b = PARAM_SETS[pname]
     for iname in ('left', 'right'):
-        img = cv2.imread(os.path.join(GOLDEN, 'data', iname + '.png'), 0)
+        img = cv2.imread(os.path.join(DATA, iname + '.png'), 0)
         g = np.load(os.path.join(GOLDEN, 'extract_%%s_%%s.npz' %% (iname, pname)))
         sf, lw, lh = tb.pyramid_geometry(img.shape[1], img.shape[0], nl, sc)
         fe = tb.Frontend(ctx, lw, lh, max_batch=1, max_target=tgt)

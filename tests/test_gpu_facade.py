@@ -21,7 +21,7 @@ def _fnv(b, h=1469598103934665603):
 def _digest(m):
     h = 1469598103934665603
     for r in m:
-        h = _fnv(np.array([r['queryIdx'], r['trainIdx']], np.int32).tobytes(), h)
+        h = _fnv(np.array([r['queryIdx'], r['trainIdx'], r['imgIdx']], np.int32).tobytes(), h)
         h = _fnv(np.float32(r['distance']).tobytes(), h)
     return h
 
@@ -73,6 +73,13 @@ def test_headless_test_matcher(tmp_path, oracle, images):
     proj = oracle.search_by_projection(oracle.MatcherParams(30, 50, 30, 1, 30.0), cam, T, k2, d2, None, sf, W, H, k1, valid, xyz, d1)
     assert got['projection'] == [str(len(proj)), '%x' % _digest(proj)]
     assert got['dist01'] == [str(oracle.hamming256(d1[0], d1[1]))]
+    # AddPoints with a larger target than the last operator(): budget = that of operator()(…, 1000, …) (ORBextractor.cpp:840-904)
+    lv, sf = oracle.pyramid(images['left'], nl, sc)
+    ko2, _, _ = oracle.orb_extract(lv, sf, 1500, a, b, exit_kps=k1[::5], budget=oracle.orb_budget(nl, sf[1], 1000))
+    assert got['addpoints'] == [str(len(ko2)), '%x' % _fnv(ko2.tobytes())]
+    inside = k1[(k1['x'] < 101) & (k1['y'] < 57)]
+    q = (inside['x'] >= 51).astype(int) + 2 * (inside['y'] >= 29).astype(int)
+    assert got['dividenode'] == [str(len(inside))] + [str(int((q == i).sum())) for i in range(4)] + ['51', '29']
     # PinholeCamera::UndistortImage / UndistortPoint with a distorted camera
     dd = [-0.28, 0.07, 0.0002, 0.00002, 0.0]
     m1, m2 = oracle.init_undistort_rectify_map(718.856, 718.856, 607.1928, 185.2157, dd, W, H)

@@ -20,7 +20,7 @@ def _free_port():
 
 def _worker(rank, world, port, n, ret):
     import oracle as O
-    from trackingbench_slam_b200.sharding import shard_range, gather_rows
+    from trackingbench_slam_b200.sharding import shard_range, gather_rows, cross_check
     from trackingbench_slam_b200.synth import synth_descriptors
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -30,9 +30,18 @@ def _worker(rank, world, port, n, ret):
     idx, best, second = O.knn2(Q[lo:hi], T)
     packed = torch.from_numpy(np.stack([idx, best, second], 1))
     full = gather_rows(packed, n).numpy()
+    # cross-check variant: the transposed problem sharded the same way + a second gather
+    lo2, hi2 = shard_range(len(T), rank, world)
+    idx2, best2, second2 = O.knn2(T[lo2:hi2], Q)
+    full2 = gather_rows(torch.from_numpy(np.stack([idx2, best2, second2], 1)), len(T)).numpy()
+    mutual = cross_check(torch.from_numpy(full[:, 0].copy()), torch.from_numpy(full2[:, 0].copy())).numpy()
     if rank == 0:
         i0, b0, s0 = O.knn2(Q, T)
-        ret['ok'] = bool(np.array_equal(full[:, 0], i0) and np.array_equal(full[:, 1], b0) and np.array_equal(full[:, 2], s0))
+        ok = bool(np.array_equal(full[:, 0], i0) and np.array_equal(full[:, 1], b0) and np.array_equal(full[:, 2], s0))
+        bf = O.bf_cross(Q, T)      # cv::BFMatcher(HAMMING, crossCheck=true) restatement
+        ok = ok and np.array_equal(np.flatnonzero(mutual), bf['queryIdx']) and np.array_equal(full[mutual, 0], bf['trainIdx'])
+        ok = ok and np.array_equal(full[mutual, 1].astype(np.float32), bf['distance'])
+        ret['ok'] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -24,6 +24,7 @@ EXPORTS = [
     'tb_profile_enable', 'tb_profile_report', 'tb_set_match_impl',
     'tb_pyramid_geometry',
     'tb_frontend_create', 'tb_frontend_destroy', 'tb_frontend_kp_capacity', 'tb_frontend_level_layout',
+    'tb_frontend_get_budget', 'tb_frontend_set_budget',
     'tb_frontend_upload_level', 'tb_frontend_download_level', 'tb_frontend_upload_frames',
     'tb_frontend_build_pyramid', 'tb_frontend_extract', 'tb_frontend_results_device',
     'tb_frontend_get_results', 'tb_frontend_get_results_batch', 'tb_frontend_get_results_batch_async',
@@ -450,6 +451,17 @@ class Frontend:
         ex = None if exit_kps is None else np.ascontiguousarray(exit_kps, KP_DTYPE)
         self.ctx.check(lib().tb_frontend_extract(self.h, n_frames, _vp(sf), int(target), C.c_float(initTh), C.c_float(minTh),
                                                  _vp(ex), 0 if ex is None else len(ex)))
+
+    def get_budget(self):
+        """ORBExtractor::mnFeaturesPerLevel of the last extract (empty before the first one)."""
+        b = np.zeros(16, np.int32)
+        n = C.c_int()
+        self.ctx.check(lib().tb_frontend_get_budget(self.h, _vp(b), C.byref(n)))
+        return b[:n.value].copy()
+
+    def set_budget(self, per_level):
+        b = np.ascontiguousarray(per_level, np.int32)
+        self.ctx.check(lib().tb_frontend_set_budget(self.h, _vp(b), len(b)))
 
     def results_device(self):
         k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -13,6 +13,57 @@
 #define TB_HOST_ONLY 1
 #endif
 
+// Device scratch of the host-facing entry points (the facade's per-call work buffers): chunks are kept between calls and
+// rewound when a call ends, so a steady caller performs no cudaMalloc/cudaFree; a call that outgrew the first chunk leaves
+// several chunks behind, which the next rewind merges into one (after making sure the stream no longer uses them).
+struct DevArena {
+    struct Chunk { char *p; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    void *alloc(size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!bytes) bytes = 256;
+        for (Chunk &c : chunks)
+            if (c.cap - c.used >= bytes) { void *r = c.p + c.used; c.used += bytes; return r; }
+        size_t total = 0;
+        for (Chunk &c : chunks) total += c.cap;
+        Chunk n;
+        n.cap = bytes > total ? bytes : total;            // geometric growth
+        if (n.cap < ((size_t)1 << 20)) n.cap = (size_t)1 << 20;
+        n.used = bytes;
+        void *q = nullptr;
+        if (cudaMalloc(&q, n.cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        n.p = (char *)q;
+        chunks.push_back(n);
+        return n.p;
+    }
+    void rewind(cudaStream_t stream)
+    {
+        if (chunks.size() > 1) {
+            size_t total = 0;
+            for (Chunk &c : chunks) total += c.cap;
+            cudaStreamSynchronize(stream);
+            for (Chunk &c : chunks) cudaFree(c.p);
+            chunks.clear();
+            void *q = nullptr;
+            if (cudaMalloc(&q, total) == cudaSuccess) { Chunk n = {(char *)q, total, 0}; chunks.push_back(n); } else cudaGetLastError();
+        }
+        for (Chunk &c : chunks) c.used = 0;
+    }
+    void destroy() { for (Chunk &c : chunks) cudaFree(c.p); chunks.clear(); }
+};
+
+// Pinned staging ring for the small host tables an entry point hands to its kernels (frame-pair lists, poses): the table is
+// copied into a pinned slot and uploaded asynchronously, so the entry point does not have to wait for the copy before its
+// pageable source goes out of scope (no cudaStreamSynchronize between extract and read-back).
+struct StageRing {
+    enum { SLOTS = 8 };
+    struct Slot { char *p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
+    Slot slot[SLOTS];
+    int next = 0;
+    void destroy() { for (Slot &s : slot) { if (s.p) cudaFreeHost(s.p); if (s.ev) cudaEventDestroy(s.ev); s = Slot(); } }
+};
+
 struct tb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -29,7 +80,9 @@ struct tb_ctx {
     struct WinWs *wws = nullptr;     // batched windowed-matcher workspace (window.cu)
     struct IngestWs *iws = nullptr;  // CLAHE tile LUTs (ingest.cu)
     struct FlowWs *fws = nullptr;    // LK pyramids + pair descriptors (flow.cu)
-    int match_impl = 0;              // 0 = LOP3+POPC (K7), 1 = tcgen05 int8 (K8)
+    int match_impl = 1;              // 1 = tcgen05 int8 (K8, the default), 0 = LOP3+POPC (K7)
+    DevArena arena;                  // scratch of the host-facing entry points
+    StageRing stage;                 // pinned staging of small host tables
     // optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
     bool profiling = false;
     struct ProfEvt { const char *name; cudaEvent_t a, b; };
@@ -62,6 +115,10 @@ static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a 
     if (ctx) ctx->err = buf;
     return code;
 }
+
+// every extern "C" entry point makes its ctx's device current first: two ctxs on different GPUs may share a host thread, and the
+// caller (e.g. torch) may have switched devices between calls
+#define TB_DEVICE_GUARD(c) do { const tb_ctx *c__ = (c); if (c__) cudaSetDevice(c__->device); } while (0)
 
 #define TB_CUDA(ctx, expr)                                                                    \
     do {                                                                                      \
@@ -97,6 +154,49 @@ static inline bool tb_encode_tiled_u8_3d(CUtensorMap *tm, const void *base, int 
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+// cudaMemcpyAsync(dst_dev <- src_host) of a small pageable table through the ctx's pinned staging ring (returns at once)
+static inline int tb_stage_upload(tb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!bytes) return TB_OK;
+    StageRing::Slot &s = ctx->stage.slot[ctx->stage.next];
+    ctx->stage.next = (ctx->stage.next + 1) % StageRing::SLOTS;
+    if (s.busy) { TB_CUDA(ctx, cudaEventSynchronize(s.ev)); s.busy = false; }
+    if (bytes > s.cap) {
+        if (s.p) cudaFreeHost(s.p);
+        s.p = nullptr; s.cap = 0;
+        const size_t cap = bytes < 65536 ? 65536 : bytes;
+        TB_CUDA(ctx, cudaHostAlloc((void **)&s.p, cap, cudaHostAllocDefault));
+        s.cap = cap;
+    }
+    if (!s.ev) TB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    memcpy(s.p, src_host, bytes);
+    TB_CUDA(ctx, cudaMemcpyAsync(dst_dev, s.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaEventRecord(s.ev, ctx->stream));
+    s.busy = true;
+    return TB_OK;
+}
+// Grow path of a persistent workspace buffer: the old buffer is released and the pointer cleared BEFORE the new allocation,
+// so that a failed cudaMalloc leaves a null pointer (callers reset their capacity first and set it only after success).
+template <typename T> static inline int tb_regrow(tb_ctx *ctx, T *&p, size_t n_elems)
+{
+    if (p) { cudaFree(p); p = nullptr; }
+    TB_CUDA(ctx, cudaMalloc((void **)&p, sizeof(T) * (n_elems ? n_elems : 1)));
+    return TB_OK;
+}
+// RAII view of the ctx arena for one host-facing call: typed bump allocations, rewound when the call returns
+struct ArenaScope {
+    tb_ctx *c;
+    explicit ArenaScope(tb_ctx *ctx) : c(ctx) {}
+    ~ArenaScope() { c->arena.rewind(c->stream); }
+    template <typename T> T *alloc(size_t n) { return (T *)c->arena.alloc((n ? n : 1) * sizeof(T) + 64); }
+    template <typename T> T *upload(const T *h, size_t n)
+    {
+        T *d = alloc<T>(n);
+        if (d && n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+        return d;
+    }
+};
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

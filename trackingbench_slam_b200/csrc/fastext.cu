@@ -150,6 +150,7 @@ extern "C" int tb_fast_extract_host(tb_ctx *ctx, const uint8_t *const *levels, c
                                     int n_levels, const float *inv_sf, int n_features, float threshold,
                                     const tb_keypoint *exit_kps, int n_exit, tb_keypoint *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !levels || !w || !h || !strides || !inv_sf || !n || n_levels <= 0 || n_levels > TB_MAX_LEVELS || n_features <= 0 || n_exit < 0)
         return TB_E_INVALID;
     *n = 0;
@@ -170,8 +171,8 @@ extern "C" int tb_fast_extract_host(tb_ctx *ctx, const uint8_t *const *levels, c
             occ[k] = 1;
         }
     }
-    struct Bufs { std::vector<void *> p; ~Bufs() { for (void *q : p) cudaFree(q); } } bufs;
-    auto dalloc = [&](size_t bytes) -> void * { void *q = nullptr; if (cudaMalloc(&q, bytes + 256) != cudaSuccess) return nullptr; bufs.p.push_back(q); return q; };
+    ArenaScope bufs(ctx);   // per-ctx scratch, rewound when the call returns (no cudaMalloc/cudaFree in steady state)
+    auto dalloc = [&](size_t bytes) -> void * { return bufs.alloc<uint8_t>(bytes + 256); };
     unsigned long long *cell_key = (unsigned long long *)dalloc(sizeof(unsigned long long) * n_features);
     int *flags = (int *)dalloc(sizeof(int) * 2);
     tb_keypoint *d_out = (tb_keypoint *)dalloc(sizeof(tb_keypoint) * n_features);

@@ -400,8 +400,7 @@ int tb_flow_batched(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, siz
         hp[i].pts = pts + (size_t)pts_slot[i] * pts_slot_stride;
         hp[i].count = counts + pts_slot[i];
     }
-    TB_CUDA(ctx, cudaMemcpyAsync(W.pairs, hp.data(), sizeof(LkPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    if ((rc = tb_stage_upload(ctx, W.pairs, hp.data(), sizeof(LkPair) * n_pairs))) return rc;   // through the pinned ring: no host wait
     const size_t smem = sizeof(LkWarpSmem) * LK_WARPS;
     {
         ProfScope prof__(ctx, "lk_track");
@@ -424,6 +423,7 @@ extern "C" int tb_lk_flow_device(tb_ctx *ctx, const tb_lk_params *p, const void 
                                  int n_pairs, const int32_t *prev_idx, const int32_t *next_idx, const void *pts_f32x2, const void *counts_i32,
                                  int pts_cap, void *next_pts, void *status, void *err)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || !prev || !next || n_pairs < 0 || (n_pairs && (!prev_idx || !next_idx)) || !pts_f32x2 || !counts_i32 || !next_pts || !status ||
         prev_pitch < (size_t)w || next_pitch < (size_t)w || pts_cap < 0)
         return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_lk_flow_device: bad arguments") : TB_E_INVALID;
@@ -434,19 +434,14 @@ extern "C" int tb_lk_flow_device(tb_ctx *ctx, const tb_lk_params *p, const void 
                            (const int *)counts_i32, pts_cap, 0, (float2 *)next_pts, (uint8_t *)status, (float *)err);
 }
 
-struct FlowBuf {
-    std::vector<void *> ptrs;
-    ~FlowBuf() { for (void *q : ptrs) cudaFree(q); }
-    template <typename T> T *alloc(size_t n) { void *q = nullptr; if (cudaMalloc(&q, (n ? n : 1) * sizeof(T) + 64) != cudaSuccess) return nullptr; ptrs.push_back(q); return (T *)q; }
-};
-
 extern "C" int tb_lk_flow_host(tb_ctx *ctx, const tb_lk_params *p, const uint8_t *prev, const uint8_t *next, int w, int h, size_t stride,
                                const float *prev_xy, int n, float *next_xy, uint8_t *status, float *err)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || !prev || !next || w <= 0 || h <= 0 || stride < (size_t)w || n < 0 || (n && (!prev_xy || !next_xy || !status)))
         return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_lk_flow_host: bad arguments") : TB_E_INVALID;
     if (n == 0) return TB_OK;
-    FlowBuf buf;
+    ArenaScope buf(ctx);
     const size_t pitch = align_up((size_t)w, 16), fs = align_up(pitch * h, 256);
     uint8_t *d_img = buf.alloc<uint8_t>(2 * fs);
     float2 *d_in = buf.alloc<float2>(n), *d_out = buf.alloc<float2>(n);

@@ -55,6 +55,8 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_window_ws_free(ctx);
     tb_ingest_ws_free(ctx);
     tb_flow_ws_free(ctx);
+    ctx->arena.destroy();
+    ctx->stage.destroy();
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -66,6 +68,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
 }
 extern "C" int tb_sync(tb_ctx *ctx)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx) return TB_E_INVALID;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TB_OK;
@@ -76,6 +79,7 @@ extern "C" int64_t tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launch
 // 0 = LOP3+POPC kernel (K7), 1 = tcgen05 int8 +-1 formulation (K8) for the batched brute-force matcher.
 extern "C" int tb_set_match_impl(tb_ctx *ctx, int impl)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || (impl != 0 && impl != 1)) return TB_E_INVALID;
     ctx->match_impl = impl;
     return TB_OK;
@@ -83,6 +87,7 @@ extern "C" int tb_set_match_impl(tb_ctx *ctx, int impl)
 
 extern "C" int tb_profile_enable(tb_ctx *ctx, int on)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx) return TB_E_INVALID;
     ctx->profiling = on != 0;
     return TB_OK;
@@ -90,6 +95,7 @@ extern "C" int tb_profile_enable(tb_ctx *ctx, int on)
 // Synchronises, then writes one line per kernel name: "name launches total_ms\n"; clears the log.
 extern "C" int tb_profile_report(tb_ctx *ctx, char *buf, size_t cap)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !buf || cap == 0) return TB_E_INVALID;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<std::string> names; std::vector<int> cnt; std::vector<double> ms;
@@ -188,6 +194,7 @@ static void level_geometry(LevelGeom &g, int w, int h, int B)
 
 extern "C" void tb_frontend_destroy(tb_frontend *fe)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe) return;
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
@@ -200,6 +207,7 @@ extern "C" void tb_frontend_destroy(tb_frontend *fe)
 
 extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, const int32_t *lh, int max_batch, int max_target, tb_frontend **out)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !out || !lw || !lh || n_levels <= 0 || n_levels > TB_MAX_LEVELS || max_batch <= 0 || max_target <= 0) return TB_E_INVALID;
     *out = nullptr;
     for (int l = 0; l < n_levels; l++) {
@@ -261,8 +269,29 @@ extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, 
 
 extern "C" int tb_frontend_kp_capacity(const tb_frontend *fe) { return fe ? fe->kp_cap : 0; }
 
+// ORBExtractor::mnFeaturesPerLevel (ORBextractor.h:88) lives in the frontend; a caller that re-creates its frontend (other
+// pyramid shape, larger target) carries it across with this pair, so that AddPoints still finds the budget of the last operator().
+extern "C" int tb_frontend_get_budget(const tb_frontend *fe, int32_t *per_level, int *n_levels)
+{
+    if (!fe || !per_level || !n_levels) return TB_E_INVALID;
+    *n_levels = fe->has_budget ? fe->L : 0;
+    for (int l = 0; l < *n_levels; l++) per_level[l] = fe->budget[l];
+    return TB_OK;
+}
+extern "C" int tb_frontend_set_budget(tb_frontend *fe, const int32_t *per_level, int n_levels)
+{
+    if (!fe || !per_level || n_levels != fe->L) return TB_E_INVALID;
+    for (int l = 0; l < n_levels; l++) {
+        if (per_level[l] < 0 || per_level[l] > fe->max_target + 8) return tb_fail(fe->ctx, TB_E_INVALID, "tb_frontend_set_budget: a level's budget exceeds the frontend's max_target");
+        fe->budget[l] = per_level[l];
+    }
+    fe->has_budget = true;
+    return TB_OK;
+}
+
 extern "C" int tb_frontend_level_layout(const tb_frontend *fe, int level, int blurred, void **base, size_t *pitch, size_t *frame_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || level < 0 || level >= fe->L) return TB_E_INVALID;
     if (base) *base = blurred ? fe->blur[level] : fe->pyr[level];
     if (pitch) *pitch = fe->g[level].pitch;
@@ -272,6 +301,7 @@ extern "C" int tb_frontend_level_layout(const tb_frontend *fe, int level, int bl
 
 extern "C" int tb_frontend_upload_level(tb_frontend *fe, int frame, int level, const uint8_t *host, size_t host_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !host || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L) return TB_E_INVALID;
     const LevelGeom &g = fe->g[level];
     TB_CUDA(fe->ctx, cudaMemcpy2DAsync(fe->pyr[level] + (size_t)frame * g.frame_stride, g.pitch, host, host_stride, g.w, g.h,
@@ -281,6 +311,7 @@ extern "C" int tb_frontend_upload_level(tb_frontend *fe, int frame, int level, c
 
 extern "C" int tb_frontend_upload_frames(tb_frontend *fe, int first, int n, const uint8_t *host, size_t host_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !host || first < 0 || n < 0 || first + n > fe->B) return TB_E_INVALID;
     const LevelGeom &g = fe->g[0];
     // frames are back to back on the host and at frame_stride on the device: one strided copy
@@ -293,8 +324,14 @@ extern "C" int tb_frontend_upload_frames(tb_frontend *fe, int first, int n, cons
 extern "C" int tb_frontend_undistort_device(tb_frontend *fe, const tb_undistort *und, int first, int n, const void *raw, int raw_w, int raw_h,
                                             size_t raw_pitch, size_t raw_frame_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !und || !raw || first < 0 || n < 0 || first + n > fe->B) return TB_E_INVALID;
     const LevelGeom &g = fe->g[0];
+    // the remap writes und->h rows of und->w pixels per frame: a map built for another size would run into the next frame
+    if (tb_undistort_width(und) != g.w || tb_undistort_height(und) != g.h)
+        return tb_fail(fe->ctx, TB_E_INVALID, "tb_frontend_undistort_device: the undistort map's size differs from pyramid level 0");
+    if (raw_w <= 0 || raw_h <= 0 || raw_pitch < (size_t)raw_w || (n > 1 && raw_frame_stride < raw_pitch * (size_t)raw_h))
+        return tb_fail(fe->ctx, TB_E_INVALID, "tb_frontend_undistort_device: raw frame layout (pitch < width or frame stride < pitch*height)");
     return tb_undistort_image_device(fe->ctx, und, raw, raw_w, raw_h, raw_pitch, raw_frame_stride, fe->pyr[0] + (size_t)first * g.frame_stride,
                                      g.pitch, g.frame_stride, n);
 }
@@ -302,6 +339,7 @@ extern "C" int tb_frontend_undistort_device(tb_frontend *fe, const tb_undistort 
 extern "C" int tb_frontend_upload_frames_undistort(tb_frontend *fe, const tb_undistort *und, int first, int n, const uint8_t *host,
                                                    int raw_w, int raw_h, size_t host_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !und || !host || first < 0 || n < 0 || first + n > fe->B || raw_w <= 0 || raw_h <= 0 || host_stride < (size_t)raw_w) return TB_E_INVALID;
     if (n == 0) return TB_OK;
     const size_t pitch = align_up((size_t)raw_w, 64), need = pitch * raw_h * n;
@@ -317,6 +355,7 @@ extern "C" int tb_frontend_upload_frames_undistort(tb_frontend *fe, const tb_und
 
 extern "C" int tb_frontend_download_level(tb_frontend *fe, int frame, int level, int blurred, uint8_t *host, size_t host_stride)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !host || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L) return TB_E_INVALID;
     const LevelGeom &g = fe->g[level];
     const uint8_t *src = (blurred ? fe->blur[level] : fe->pyr[level]) + (size_t)frame * g.frame_stride;
@@ -369,6 +408,7 @@ static int pyramid_enqueue(tb_frontend *fe, int n_frames)
 
 extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
     if (n_frames == 0) return TB_OK;
     tb_ctx *ctx = fe->ctx;
@@ -398,6 +438,7 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
 extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
                                    const tb_keypoint *exit_kps, int n_exit)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !sf || n_frames < 0 || n_frames > fe->B || target <= 0 || n_exit < 0) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     if (target > fe->max_target) return tb_fail(ctx, TB_E_INVALID, "target exceeds the frontend's max_target");
@@ -556,6 +597,7 @@ static int check_overflow(tb_frontend *fe)
 
 extern "C" int tb_frontend_results_device(const tb_frontend *fe, void **kps, void **desc, void **counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe) return TB_E_INVALID;
     if (kps) *kps = fe->kps;
     if (desc) *desc = fe->desc;
@@ -565,6 +607,7 @@ extern "C" int tb_frontend_results_device(const tb_frontend *fe, void **kps, voi
 
 extern "C" int tb_frontend_get_results(tb_frontend *fe, int frame, tb_keypoint *kps, uint8_t *desc, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || frame < 0 || frame >= fe->B || !n || capacity < 0) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     int rc = check_overflow(fe);
@@ -580,6 +623,7 @@ extern "C" int tb_frontend_get_results(tb_frontend *fe, int frame, tb_keypoint *
 
 extern "C" int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || n_frames < 0 || n_frames > fe->B || !counts || capacity < 0) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     if (n_frames == 0) return TB_OK;
@@ -597,6 +641,7 @@ extern "C" int tb_frontend_get_results_batch(tb_frontend *fe, int n_frames, tb_k
 
 extern "C" int tb_frontend_get_results_batch_async(tb_frontend *fe, int n_frames, tb_keypoint *kps, uint8_t *desc, int capacity, int32_t *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || n_frames < 0 || n_frames > fe->B || !counts || capacity < 0) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     if (n_frames == 0) return TB_OK;
@@ -611,12 +656,14 @@ extern "C" int tb_frontend_get_results_batch_async(tb_frontend *fe, int n_frames
 
 extern "C" int tb_frontend_status(tb_frontend *fe)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe) return TB_E_INVALID;
     return check_overflow(fe);
 }
 
 extern "C" int tb_frontend_get_level_counts(tb_frontend *fe, int frame, int32_t *n_per_level)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || frame < 0 || frame >= fe->B || !n_per_level) return TB_E_INVALID;
     TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
     TB_CUDA(fe->ctx, cudaMemcpy(n_per_level, fe->n_kept + (size_t)frame * fe->L, sizeof(int) * fe->L, cudaMemcpyDeviceToHost));
@@ -627,6 +674,7 @@ extern "C" int tb_frontend_get_level_counts(tb_frontend *fe, int frame, int32_t 
 // host for the stage test only (this accessor is test plumbing, not part of the data path).
 extern "C" int tb_frontend_get_candidates(tb_frontend *fe, int frame, int level, tb_keypoint *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L || !n) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -654,6 +702,7 @@ extern "C" int tb_orb_extract_host(tb_frontend *fe, const uint8_t *const *levels
                                    int target, float initTh, float minTh, const tb_keypoint *exit_kps, int n_exit,
                                    tb_keypoint *kps, uint8_t *desc, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !levels || !host_strides || !n) return TB_E_INVALID;
     for (int l = 0; l < fe->L; l++) {
         int rc = tb_frontend_upload_level(fe, 0, l, levels[l], host_strides[l]);
@@ -667,6 +716,7 @@ extern "C" int tb_orb_extract_host(tb_frontend *fe, const uint8_t *const *levels
 extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int32_t *q_frames, const int32_t *t_frames,
                                         float ratio, float minTh, void *matches, int capacity, void *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || n_pairs < 0 || !q_frames || !t_frames || !matches || !counts) return TB_E_INVALID;
     for (int p = 0; p < n_pairs; p++)
         if (q_frames[p] < 0 || q_frames[p] >= fe->B || t_frames[p] < 0 || t_frames[p] >= fe->B) return TB_E_INVALID;
@@ -676,6 +726,7 @@ extern "C" int tb_frontend_search_by_bf(tb_frontend *fe, int n_pairs, const int3
 
 extern "C" int tb_frontend_set_bow(tb_frontend *fe, const tb_vocab *voc, int n_frames, int levelsup, void *node, void *word, void *weight)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !voc || n_frames < 0 || n_frames > fe->B || !node) return TB_E_INVALID;
     return tb_window_set_bow_batched(fe->ctx, voc, n_frames, levelsup, fe->desc, fe->kp_cap, fe->n_kp, (int32_t *)node, (int32_t *)word, (double *)weight);
 }
@@ -683,6 +734,7 @@ extern "C" int tb_frontend_set_bow(tb_frontend *fe, const tb_vocab *voc, int n_f
 extern "C" int tb_frontend_search_by_bow(tb_frontend *fe, const tb_matcher_params *p, int n_pairs, const int32_t *f1_frames, const int32_t *f2_frames,
                                          const void *node, const void *mp_valid, int map_point_only, void *matches, int capacity, void *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !p || n_pairs < 0 || !f1_frames || !f2_frames || !node || !matches || !counts) return TB_E_INVALID;
     for (int i = 0; i < n_pairs; i++)
         if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
@@ -694,6 +746,7 @@ extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_
                                               const int32_t *f2_frames, int min_level, int max_level, float search_r,
                                               void *matches, int capacity, void *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !p || n_pairs < 0 || !f1_frames || !f2_frames || !matches || !counts) return TB_E_INVALID;
     for (int i = 0; i < n_pairs; i++)
         if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;
@@ -703,6 +756,7 @@ extern "C" int tb_frontend_search_by_violence(tb_frontend *fe, const tb_matcher_
 
 extern "C" int tb_frontend_undistort_points(tb_frontend *fe, const tb_pinhole *cam, int n_frames, void *out)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !cam || n_frames < 0 || n_frames > fe->B || !out) return TB_E_INVALID;
     return tb_undistort_points_launch(fe->ctx, cam, (const uint8_t *)fe->kps, sizeof(tb_keypoint), sizeof(tb_keypoint) * (size_t)fe->kp_cap, fe->n_kp,
                                       fe->kp_cap, n_frames, (float2 *)out);
@@ -711,6 +765,7 @@ extern "C" int tb_frontend_undistort_points(tb_frontend *fe, const tb_pinhole *c
 extern "C" int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_frames, int n_pairs, const int32_t *f1_frames,
                                             const int32_t *f2_frames, int equalized, void *next_pts, void *status, void *err)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !p || n_frames < 1 || n_frames > fe->B || n_pairs < 0 || !f1_frames || !f2_frames || !next_pts || !status) return TB_E_INVALID;
     for (int i = 0; i < n_pairs; i++)
         if (f1_frames[i] < 0 || f1_frames[i] >= n_frames || f2_frames[i] < 0 || f2_frames[i] >= n_frames) return TB_E_INVALID;
@@ -734,6 +789,7 @@ extern "C" int tb_frontend_stereo_depth_by_opflow(tb_frontend *fe, const tb_lk_p
                                                   const int32_t *current_frames, const int32_t *stereo_frames, int equalized,
                                                   void *depth, void *next_pts, void *status)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!depth || !next_pts || !status) return TB_E_INVALID;
     // searchByOPFlow(stereo_frame, current_frame, pts, equalized, ...): F1 = stereo frame, F2 = current frame with its keys (LocalBA.cpp:54)
     int rc = tb_frontend_search_by_opflow(fe, p, n_frames, n_pairs, stereo_frames, current_frames, equalized, next_pts, status, nullptr);
@@ -745,6 +801,7 @@ extern "C" int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params 
                                         const int32_t *right_frames, const float *inv_sf, void *matches, int capacity,
                                         void *counts, void *depth)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !p || n_pairs < 0 || !left_frames || !right_frames || !inv_sf || !matches || !counts || capacity < 0) return TB_E_INVALID;
     for (int i = 0; i < n_pairs; i++)
         if (left_frames[i] < 0 || left_frames[i] >= fe->B || right_frames[i] < 0 || right_frames[i] >= fe->B) return TB_E_INVALID;
@@ -757,6 +814,7 @@ extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matche
                                                 const void *f1_matched, const void *mp_valid, const void *mp_xyz,
                                                 const float *sf1, void *matches, int capacity, void *counts)
 {
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !p || !cam || n_pairs < 0 || !f1_frames || !f2_frames || !Tcw1 || !mp_valid || !mp_xyz || !sf1 || !matches || !counts) return TB_E_INVALID;
     for (int i = 0; i < n_pairs; i++)
         if (f1_frames[i] < 0 || f1_frames[i] >= fe->B || f2_frames[i] < 0 || f2_frames[i] >= fe->B) return TB_E_INVALID;

@@ -23,6 +23,9 @@ struct tb_undistort {
     uint2 *fix;        // [h][w]: .x = (ix & 0xFFFF) | (iy << 16) (int16 each), .y = fx | fy << 5
 };
 
+int tb_undistort_width(const tb_undistort *u) { return u->w; }
+int tb_undistort_height(const tb_undistort *u) { return u->h; }
+
 // cvRound(float) as cvtss2si: NaN and out-of-range values give INT_MIN
 __device__ __forceinline__ int cv_round_indef(float v)
 {
@@ -432,6 +435,7 @@ extern "C" int tb_init_undistort_rectify_map(const tb_pinhole *cam, float *map1,
 
 extern "C" int tb_undistort_create(tb_ctx *ctx, int dst_w, int dst_h, const float *map1, const float *map2, tb_undistort **out)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !out || dst_w <= 0 || dst_h <= 0 || !map1 || !map2) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_create: bad arguments") : TB_E_INVALID;
     const size_t n = (size_t)dst_w * dst_h;
     float *d1 = nullptr, *d2 = nullptr;
@@ -466,6 +470,7 @@ extern "C" void tb_undistort_destroy(tb_undistort *u)
 extern "C" int tb_undistort_image_device(tb_ctx *ctx, const tb_undistort *u, const void *src, int src_w, int src_h, size_t src_pitch,
                                          size_t src_frame_stride, void *dst, size_t dst_pitch, size_t dst_frame_stride, int n_frames)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !u || !src || !dst || src_w <= 0 || src_h <= 0 || n_frames < 0 || src_pitch < (size_t)src_w || dst_pitch < (size_t)u->w)
         return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_image_device: bad arguments") : TB_E_INVALID;
     if (src_w > 32767 || src_h > 32767) return tb_fail(ctx, TB_E_UNSUPPORTED, "remap: source larger than 32767 (int16 coordinates, as cv::remap)");
@@ -498,21 +503,18 @@ extern "C" int tb_undistort_image_device(tb_ctx *ctx, const tb_undistort *u, con
 extern "C" int tb_undistort_image_host(tb_ctx *ctx, const tb_undistort *u, const uint8_t *src, int src_w, int src_h, size_t src_stride,
                                        uint8_t *dst, size_t dst_stride)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !u || !src || !dst || src_w <= 0 || src_h <= 0) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_image_host: bad arguments") : TB_E_INVALID;
-    uint8_t *ds = nullptr, *dd = nullptr;
+    ArenaScope buf(ctx);
     const size_t sp = align_up((size_t)src_w, 64);
-    if (cudaMalloc(&ds, sp * src_h) != cudaSuccess || cudaMalloc(&dd, (size_t)u->w * u->h) != cudaSuccess) {
-        cudaFree(ds); cudaFree(dd);
-        return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
-    }
-    int rc = TB_OK;
-    cudaError_t e = cudaMemcpy2DAsync(ds, sp, src, src_stride, src_w, src_h, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) rc = tb_undistort_image_device(ctx, u, ds, src_w, src_h, sp, 0, dd, u->w, 0, 1);
-    if (e == cudaSuccess && rc == TB_OK) e = cudaMemcpy2DAsync(dst, dst_stride, dd, u->w, u->w, u->h, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && rc == TB_OK) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(ds); cudaFree(dd);
-    if (e != cudaSuccess) return tb_fail(ctx, TB_E_CUDA, "tb_undistort_image_host: %s", cudaGetErrorString(e));
-    return rc;
+    uint8_t *ds = buf.alloc<uint8_t>(sp * src_h), *dd = buf.alloc<uint8_t>((size_t)u->w * u->h);
+    if (!ds || !dd) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    TB_CUDA(ctx, cudaMemcpy2DAsync(ds, sp, src, src_stride, src_w, src_h, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tb_undistort_image_device(ctx, u, ds, src_w, src_h, sp, 0, dd, u->w, 0, 1);
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_stride, dd, u->w, u->w, u->h, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
 }
 
 struct IngestWs { uint8_t *lut = nullptr; uint32_t *quad = nullptr; size_t bytes = 0, quad_bytes = 0; };
@@ -527,6 +529,7 @@ void tb_ingest_ws_free(tb_ctx *ctx)
 extern "C" int tb_clahe_device(tb_ctx *ctx, const void *src, int w, int h, size_t src_pitch, size_t src_frame_stride, void *dst,
                                size_t dst_pitch, size_t dst_frame_stride, int n_frames, double clip_limit, int tiles_x, int tiles_y)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !src || !dst || w <= 0 || h <= 0 || n_frames < 0 || tiles_x < 1 || tiles_y < 1 || src_pitch < (size_t)w || dst_pitch < (size_t)w)
         return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_clahe_device: bad arguments") : TB_E_INVALID;
     if (n_frames == 0) return TB_OK;
@@ -575,20 +578,17 @@ extern "C" int tb_clahe_device(tb_ctx *ctx, const void *src, int w, int h, size_
 extern "C" int tb_clahe_host(tb_ctx *ctx, const uint8_t *src, int w, int h, size_t src_stride, uint8_t *dst, size_t dst_stride,
                              double clip_limit, int tiles_x, int tiles_y)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !src || !dst || w <= 0 || h <= 0) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_clahe_host: bad arguments") : TB_E_INVALID;
-    uint8_t *ds = nullptr, *dd = nullptr;
-    if (cudaMalloc(&ds, (size_t)w * h) != cudaSuccess || cudaMalloc(&dd, (size_t)w * h) != cudaSuccess) {
-        cudaFree(ds); cudaFree(dd);
-        return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
-    }
-    int rc = TB_OK;
-    cudaError_t e = cudaMemcpy2DAsync(ds, w, src, src_stride, w, h, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) rc = tb_clahe_device(ctx, ds, w, h, w, 0, dd, w, 0, 1, clip_limit, tiles_x, tiles_y);
-    if (e == cudaSuccess && rc == TB_OK) e = cudaMemcpy2DAsync(dst, dst_stride, dd, w, w, h, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && rc == TB_OK) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(ds); cudaFree(dd);
-    if (e != cudaSuccess) return tb_fail(ctx, TB_E_CUDA, "tb_clahe_host: %s", cudaGetErrorString(e));
-    return rc;
+    ArenaScope buf(ctx);
+    uint8_t *ds = buf.alloc<uint8_t>((size_t)w * h), *dd = buf.alloc<uint8_t>((size_t)w * h);
+    if (!ds || !dd) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    TB_CUDA(ctx, cudaMemcpy2DAsync(ds, w, src, src_stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tb_clahe_device(ctx, ds, w, h, w, 0, dd, w, 0, 1, clip_limit, tiles_x, tiles_y);
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_stride, dd, w, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -639,6 +639,7 @@ int tb_undistort_points_launch(tb_ctx *ctx, const tb_pinhole *cam, const uint8_t
 
 extern "C" int tb_undistort_points_device(tb_ctx *ctx, const tb_pinhole *cam, const void *pts_dptr, size_t stride, long long n, void *out_dptr)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !cam || n < 0 || n > 0x7fffffff || (n && (!pts_dptr || !out_dptr)) || stride < 8)
         return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_points_device: bad arguments") : TB_E_INVALID;
     return tb_undistort_points_launch(ctx, cam, (const uint8_t *)pts_dptr, stride, 0, nullptr, (int)n, 1, (float2 *)out_dptr);
@@ -646,16 +647,16 @@ extern "C" int tb_undistort_points_device(tb_ctx *ctx, const tb_pinhole *cam, co
 
 extern "C" int tb_undistort_points(tb_ctx *ctx, const tb_pinhole *cam, const float *xy_in, int n, float *xy_out)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !cam || n < 0 || (n && (!xy_in || !xy_out))) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_undistort_points: bad arguments") : TB_E_INVALID;
     if (n == 0) return TB_OK;
-    float2 *d_in = nullptr, *d_out = nullptr;
-    if (cudaMalloc(&d_in, sizeof(float2) * (size_t)n) != cudaSuccess) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
-    if (cudaMalloc(&d_out, sizeof(float2) * (size_t)n) != cudaSuccess) { cudaFree(d_in); return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed"); }
-    int rc = TB_OK;
-    if (cudaMemcpyAsync(d_in, xy_in, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = tb_fail(ctx, TB_E_CUDA, "upload failed");
-    if (!rc) rc = tb_undistort_points_launch(ctx, cam, (const uint8_t *)d_in, sizeof(float2), 0, nullptr, n, 1, d_out);
-    if (!rc && (cudaMemcpyAsync(xy_out, d_out, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-                cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = tb_fail(ctx, TB_E_CUDA, "download failed");
-    cudaFree(d_in); cudaFree(d_out);
-    return rc;
+    ArenaScope buf(ctx);
+    float2 *d_in = buf.alloc<float2>((size_t)n), *d_out = buf.alloc<float2>((size_t)n);
+    if (!d_in || !d_out) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    TB_CUDA(ctx, cudaMemcpyAsync(d_in, xy_in, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tb_undistort_points_launch(ctx, cam, (const uint8_t *)d_in, sizeof(float2), 0, nullptr, n, 1, d_out);
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaMemcpyAsync(xy_out, d_out, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
 }

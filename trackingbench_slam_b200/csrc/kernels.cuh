@@ -59,9 +59,14 @@ struct DescArgs {
     int *overflow;
 };
 int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames);
-int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *d_t_frames, int n_frames_used,
-                    const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap, int *best_idx, int *best_dist);
-int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *best, int *second);
+// one brute-force matching problem: nq query rows against nt train rows of 32-byte descriptors (device pointers)
+struct PairDesc {
+    const uint8_t *q, *t;
+    int nq, nt;
+};
+#define TB_TC_MIN_ROWS 256   // single-pair searchByBF takes the tensor-core kernel from this many rows on (one full 256-row CTA)
+int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_cap, int *best_idx, int *best_dist);
+int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pair, int nq, int *idx, int *best, int *second);
 int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host, int n_frames_total,
                         const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,
                         float ratio, float minTh, tb_match *matches, int capacity, int *out_counts);
@@ -91,6 +96,8 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
                                  const int32_t *f2_frames, const float *Tcw1, int n_frames, const tb_keypoint *kps, const uint8_t *desc,
                                  int kp_cap, const int *counts, const uint8_t *f1_matched, const uint8_t *mp_valid, const float *mp_xyz,
                                  const float *sf1, int n_levels, int cols, int rows, tb_match *matches, int capacity, int *out_counts);
+int tb_undistort_width(const tb_undistort *u);
+int tb_undistort_height(const tb_undistort *u);
 // per-device kernel attributes (dynamic shared memory opt-in); called by tb_ctx_create for its device
 void tb_fast_init_device();
 void tb_octree_init_device();

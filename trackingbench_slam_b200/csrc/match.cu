@@ -16,11 +16,6 @@
 #define KNN_THREADS 128
 #define KNN_TILE 128
 
-struct PairDesc {
-    const uint8_t *q, *t;
-    int nq, nt;
-};
-
 __device__ __forceinline__ int ham256(const uint32_t q[8], const uint4 a, const uint4 b)
 {
     return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
@@ -200,17 +195,16 @@ void tb_match_ws_free(tb_ctx *ctx)
 static int ws_reserve(tb_ctx *ctx, int n_pairs2, size_t rows)
 {
     MatchWs &w = ws_of(ctx);
+    int rc;
     if (n_pairs2 > w.pairs_cap) {
-        if (w.pairs) cudaFree(w.pairs);
-        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(PairDesc) * n_pairs2));
+        w.pairs_cap = 0;
+        if ((rc = tb_regrow(ctx, w.pairs, (size_t)n_pairs2))) return rc;
         w.pairs_cap = n_pairs2;
     }
     if (rows > w.ws_cap) {
-        if (w.best_idx) { cudaFree(w.best_idx); cudaFree(w.best_dist); cudaFree(w.second); cudaFree(w.scratch); }
-        TB_CUDA(ctx, cudaMalloc(&w.best_idx, sizeof(int) * rows));
-        TB_CUDA(ctx, cudaMalloc(&w.best_dist, sizeof(int) * rows));
-        TB_CUDA(ctx, cudaMalloc(&w.second, sizeof(int) * rows));
-        TB_CUDA(ctx, cudaMalloc(&w.scratch, sizeof(int) * rows));
+        w.ws_cap = 0;
+        if ((rc = tb_regrow(ctx, w.best_idx, rows)) || (rc = tb_regrow(ctx, w.best_dist, rows)) || (rc = tb_regrow(ctx, w.second, rows)) ||
+            (rc = tb_regrow(ctx, w.scratch, rows))) return rc;
         w.ws_cap = rows;
     }
     return TB_OK;
@@ -218,6 +212,7 @@ static int ws_reserve(tb_ctx *ctx, int n_pairs2, size_t rows)
 
 extern "C" int tb_hamming_pairs_device(tb_ctx *ctx, const void *a, const void *b, int n, void *dist)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || n < 0) return TB_E_INVALID;
     if (n == 0) return TB_OK;
     hamming_pairs<<<div_up(n, 256), 256, 0, ctx->stream>>>((const uint4 *)a, (const uint4 *)b, n, (int *)dist);
@@ -227,20 +222,19 @@ extern "C" int tb_hamming_pairs_device(tb_ctx *ctx, const void *a, const void *b
 
 extern "C" int tb_knn2_device(tb_ctx *ctx, const void *q, int nq, const void *t, int nt, void *idx, void *best, void *second)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || nq < 0 || nt < 0) return TB_E_INVALID;
     if (nq == 0) return TB_OK;
-    if (ctx->match_impl == 1 && nt > 0)
-        return tb_knn2_tc(ctx, (const uint8_t *)q, nq, (const uint8_t *)t, nt, (int *)idx, (int *)best, (int *)second);
     int rc = ws_reserve(ctx, 2, 1);
     if (rc) return rc;
     MatchWs &w = ws_of(ctx);
     PairDesc pd = {(const uint8_t *)q, (const uint8_t *)t, nq, nt};
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = tb_stage_upload(ctx, w.pairs, &pd, sizeof pd))) return rc;
+    if (ctx->match_impl == 1 && nt > 0) return tb_knn2_tc(ctx, w.pairs, nq, (int *)idx, (int *)best, (int *)second);
     dim3 grid(div_up(nq, KNN_THREADS), 1);
+    ProfScope prof__(ctx, "hamming_knn");
     hamming_knn<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, 0, (int *)idx, (int *)best, (int *)second);
     TB_LAUNCH_CHECK(ctx);
-    // the pair descriptor lives in pageable host memory: make the copy complete before returning
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TB_OK;
 }
 
@@ -255,16 +249,21 @@ static int bf_single(tb_ctx *ctx, const void *d1, int n1, const void *d2, int n2
     if (rc) return rc;
     MatchWs &w = ws_of(ctx);
     if ((size_t)n1 > w.out_cap) {
-        if (w.out) { cudaFree(w.out); cudaFree(w.out_count); }
-        TB_CUDA(ctx, cudaMalloc(&w.out, sizeof(tb_match) * n1));
-        TB_CUDA(ctx, cudaMalloc(&w.out_count, sizeof(int) * 4));
+        w.out_cap = 0;
+        if ((rc = tb_regrow(ctx, w.out, (size_t)n1)) || (rc = tb_regrow(ctx, w.out_count, 4))) return rc;
         w.out_cap = n1;
     }
     PairDesc pd[2] = {{(const uint8_t *)d1, (const uint8_t *)d2, n1, n2}, {(const uint8_t *)d2, (const uint8_t *)d1, n2, n1}};
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
-    dim3 grid(div_up((int)stride, KNN_THREADS), 2);
-    hamming_knn<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, (int)stride, w.best_idx, w.best_dist, nullptr);
-    TB_LAUNCH_CHECK(ctx);
+    if ((rc = tb_stage_upload(ctx, w.pairs, pd, sizeof pd))) return rc;
+    if (ctx->match_impl == 1 && stride >= TB_TC_MIN_ROWS) {
+        // tcgen05 int8 matcher (the default) once the problem fills at least one 256-row CTA; same best_idx/best_dist layout
+        if ((rc = tb_match_knn_tc(ctx, 1, w.pairs, (int)stride, w.best_idx, w.best_dist))) return rc;
+    } else {
+        dim3 grid(div_up((int)stride, KNN_THREADS), 2);
+        ProfScope prof__(ctx, "hamming_knn");
+        hamming_knn<false><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, (int)stride, w.best_idx, w.best_dist, nullptr);
+        TB_LAUNCH_CHECK(ctx);
+    }
     bf_cross_filter<<<1, 256, 0, ctx->stream>>>(w.pairs, 1, (int)stride, w.best_idx, w.best_dist, w.scratch, filter, ratio, minTh,
                                                 w.out, n1, w.out_count);
     TB_LAUNCH_CHECK(ctx);
@@ -279,12 +278,14 @@ static int bf_single(tb_ctx *ctx, const void *d1, int n1, const void *d2, int n2
 
 extern "C" int tb_match_bf_cross_device(tb_ctx *ctx, const void *d1, int n1, const void *d2, int n2, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     return bf_single(ctx, d1, n1, d2, n2, 0, 0.f, 0.f, out, capacity, n);
 }
 
 extern "C" int tb_search_by_bf_device(tb_ctx *ctx, const void *d1, int n1, const void *d2, int n2, float ratio, float minTh,
                                       tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     return bf_single(ctx, d1, n1, d2, n2, 1, ratio, minTh, out, capacity, n);
 }
 
@@ -294,39 +295,36 @@ static int bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, in
     if (!ctx || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
     *n = 0;
     if (n1 == 0 || n2 == 0) return TB_OK;
-    uint8_t *dd1 = nullptr, *dd2 = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&dd1, (size_t)32 * n1));
-    if (cudaMalloc(&dd2, (size_t)32 * n2) != cudaSuccess) { cudaFree(dd1); return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed"); }
-    cudaMemcpyAsync(dd1, d1, (size_t)32 * n1, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(dd2, d2, (size_t)32 * n2, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = bf_single(ctx, dd1, n1, dd2, n2, filter, ratio, minTh, out, capacity, n);
-    cudaFree(dd1); cudaFree(dd2);
-    return rc;
+    ArenaScope buf(ctx);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1), *dd2 = buf.upload(d2, (size_t)32 * n2);
+    if (!dd1 || !dd2) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
+    return bf_single(ctx, dd1, n1, dd2, n2, filter, ratio, minTh, out, capacity, n);
 }
 extern "C" int tb_match_bf_cross_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     return bf_host(ctx, d1, n1, d2, n2, 0, 0.f, 0.f, out, capacity, n);
 }
 extern "C" int tb_search_by_bf_host(tb_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, float ratio, float minTh,
                                     tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     return bf_host(ctx, d1, n1, d2, n2, 1, ratio, minTh, out, capacity, n);
 }
 extern "C" int tb_hamming_pairs_host(tb_ctx *ctx, const uint8_t *a, const uint8_t *b, int n, int32_t *dist)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || n < 0 || !dist) return TB_E_INVALID;
     if (n == 0) return TB_OK;
-    uint8_t *da = nullptr, *db = nullptr; int *dd = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&da, (size_t)32 * n));
-    TB_CUDA(ctx, cudaMalloc(&db, (size_t)32 * n));
-    TB_CUDA(ctx, cudaMalloc(&dd, sizeof(int) * (size_t)n));
-    cudaMemcpyAsync(da, a, (size_t)32 * n, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(db, b, (size_t)32 * n, cudaMemcpyHostToDevice, ctx->stream);
+    ArenaScope buf(ctx);
+    uint8_t *da = buf.upload(a, (size_t)32 * n), *db = buf.upload(b, (size_t)32 * n);
+    int *dd = buf.alloc<int>((size_t)n);
+    if (!da || !db || !dd) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     int rc = tb_hamming_pairs_device(ctx, da, db, n, dd);
-    if (!rc && cudaMemcpyAsync(dist, dd, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = TB_E_CUDA;
-    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = TB_E_CUDA;
-    cudaFree(da); cudaFree(db); cudaFree(dd);
-    return rc;
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaMemcpyAsync(dist, dd, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
 }
 
 // Batched searchByBF over frames of one extract result (called by frontend.cu).
@@ -339,10 +337,10 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
     if (rc) return rc;
     MatchWs &w = ws_of(ctx);
     if (2 * n_pairs > w.frames_cap) {
-        if (w.frames) cudaFree(w.frames);
-        TB_CUDA(ctx, cudaMalloc(&w.frames, sizeof(int) * 2 * n_pairs));
-        w.frames_cap = 2 * n_pairs;
+        w.frames_cap = 0;
         w.frames_shadow.clear();
+        if ((rc = tb_regrow(ctx, w.frames, (size_t)2 * n_pairs))) return rc;
+        w.frames_cap = 2 * n_pairs;
     }
     // The frame index lists are tiny, but a host-to-device copy queues on the same copy engine as the NEXT batch's frame
     // upload (already running in a pipelined caller) and would hold this batch's matcher back until that upload ends:
@@ -353,13 +351,12 @@ int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, 
     if (!same) {
         w.frames_shadow.assign(q_frames_host, q_frames_host + n_pairs);
         w.frames_shadow.insert(w.frames_shadow.end(), t_frames_host, t_frames_host + n_pairs);
-        TB_CUDA(ctx, cudaMemcpyAsync(w.frames, w.frames_shadow.data(), sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the shadow may be reallocated by a later call while the copy is pending
+        if ((rc = tb_stage_upload(ctx, w.frames, w.frames_shadow.data(), sizeof(int) * 2 * n_pairs))) return rc;   // through the pinned ring: no wait
     }
     build_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w.pairs, n_pairs, w.frames, w.frames + n_pairs, desc, frame_stride, counts);
     TB_LAUNCH_CHECK(ctx);
     if (ctx->match_impl == 1) {
-        rc = tb_match_knn_tc(ctx, n_pairs, w.frames, w.frames + n_pairs, n_frames_total, desc, frame_stride, counts, kp_cap, w.best_idx, w.best_dist);
+        rc = tb_match_knn_tc(ctx, n_pairs, w.pairs, kp_cap, w.best_idx, w.best_dist);
         if (rc) return rc;
     } else {
         dim3 grid(div_up(kp_cap, KNN_THREADS), 2 * n_pairs);

@@ -7,13 +7,15 @@
 // hamming = (256 - dot) / 2 exactly (all products are +-1, |sum| <= 256, int32 accumulation).
 // This is the only place the path is a dense contraction (north_star (c)).
 //
-//  * expand_desc_i8 writes every frame's descriptors once as int8 in the UMMA canonical K-major
-//    no-swizzle layout [row/8][k/16][row%8][16 B], so a 128-row (32 KB) or 256-row (64 KB) operand tile is
-//    one contiguous block of global memory and is staged with cp.async.bulk (TMA 1-D bulk copy).
-//  * hamming_i8mma: one CTA = 128 query rows.  Warp 0 = bulk-copy producer (2-stage ring of train
-//    tiles), warp 1 = tcgen05.mma issuer (kind::i8, M=128, N=256, 8 K-steps of 32), accumulators in TMEM
-//    (2 x 256 columns, double buffered), warps 2-5 = epilogue: tcgen05.ld 32 columns at a time, running
-//    (max dot, arg) per row in registers.  mbarriers connect the three roles; tcgen05.commit frees the
+//  * The +-1 int8 operands never exist in global memory: expander warps read the packed 32-byte descriptors (8 KB per
+//    256 rows) and write the expanded rows straight into shared memory in the UMMA canonical K-major no-swizzle layout
+//    [row/8][k/16][row%8][16 B] (generic-proxy stores + fence.proxy.async + mbarrier arrive).  The first version staged
+//    pre-expanded descriptors (256 B per row) from global memory with cp.async.bulk and was bound by that 8x L2 -> shared
+//    traffic (every CTA streams its whole train frame).
+//  * hamming_i8mma: one CTA = 128 (kNN-2) or 256 (frame pairs) query rows.  Warp 0 owns the TMEM allocation, warp 1 =
+//    tcgen05.mma issuer (kind::i8, M=128, N=TN, 8 K-steps of 32), accumulators in TMEM (2 stages x MB blocks x TN columns =
+//    512), warps 2-9 = epilogue: tcgen05.ld 32 columns at a time, running (max dot, arg) per row in registers, warps 10-13 =
+//    expanders (A operand once, then the ring of train tiles).  mbarriers connect the roles; tcgen05.commit frees the
 //    shared-memory stage and publishes the accumulator.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -22,51 +24,30 @@
 #define TC_MB_MAX 2       // M blocks per CTA (template parameter MB): with 2, 256 query rows share every train tile, which halves
                           // the L2 -> shared-memory traffic that bounds the batched frame-pair matcher; the 200k x 200k kNN-2
                           // keeps 1 (its top-2 epilogue is the bound and 128-row CTAs fill the last wave better)
-#define TC_PAD 256        // expanded frames are padded to a multiple of this many rows
 #define TC_KB 256         // bytes (= int8 elements) per expanded descriptor
-#define TC_THREADS 320      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
+#define TC_THREADS 448    // warp 0 TMEM allocation, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter), warps 10..13 expanders
+#define TC_EXP_THREADS 128
+#define TC_EXP_WARP0 10
 
-struct TcPair {
-    const int8_t *q, *t;   // expanded descriptor blocks of the query / train frame
-    int nq, nt;
-};
-
-// ---- expansion: 32-byte descriptors -> 256 int8 (+1 for a 0 bit, -1 for a 1 bit), rows >= count are 0
-__global__ void __launch_bounds__(256)
-expand_desc_i8(const uint8_t *__restrict__ desc, size_t in_stride, const int *__restrict__ counts, int n_fixed,
-               int8_t *__restrict__ out, size_t out_stride, int rows_pad)
+// ---- expansion of one descriptor row into its shared-memory tile: 32 packed bytes -> 256 int8 (+1 for a 0 bit, -1 for a 1
+//      bit; a row beyond the set's count is written as zeros).  Chunk c (16 bits -> 16 bytes) of row r lives at
+//      (r/8)*2048 + c*128 + (r%8)*16: the eight lanes of a quarter warp (consecutive rows) store 128 contiguous bytes.
+__device__ __forceinline__ void expand_row(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid)
 {
-    const int f = blockIdx.y;
-    const int item = blockIdx.x * 256 + threadIdx.x;       // (row, 16-bit chunk)
-    const int row = item >> 4, c = item & 15;
-    if (row >= rows_pad) return;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < (counts ? counts[f] : n_fixed)) {
-        const uint8_t *d = desc + (size_t)f * in_stride + (size_t)32 * row + 2 * c;
-        const uint32_t bits = d[0] | ((uint32_t)d[1] << 8);
+    uint8_t *o = tile + (size_t)(r >> 3) * 2048 + (size_t)(r & 7) * 16;
+    const uint32_t w32[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const uint32_t bits = (w32[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t nib = (bits >> (4 * k)) & 0xF;
             const uint32_t b = (nib * 0x00204081u) & 0x01010101u;   // bit i -> byte i
-            w[k] = 0x01010101u + 0xFEu * b;                           // per byte: 0 -> 0x01 (+1), 1 -> 0xFF (-1); no carries
+            w[k] = valid ? 0x01010101u + 0xFEu * b : 0u;              // per byte: 0 -> 0x01 (+1), 1 -> 0xFF (-1); no carries
         }
-        v = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    int8_t *o = out + (size_t)f * out_stride + (size_t)(row >> 3) * (16 * 128) + (size_t)c * 128 + (size_t)(row & 7) * 16;
-    *reinterpret_cast<uint4 *>(o) = v;
-}
-
-__global__ void build_tc_pairs(TcPair *pairs, int P, const int *q_frames, const int *t_frames,
-                               const int8_t *exp, size_t frame_stride, const int *counts)
-{
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    int qf = q_frames[p], tf = t_frames[p];
-    TcPair a = {exp + qf * frame_stride, exp + tf * frame_stride, counts[qf], counts[tf]};
-    TcPair b = {a.t, a.q, a.nt, a.nq};
-    pairs[p] = a;
-    pairs[P + p] = b;
 }
 
 // ---- PTX helpers
@@ -118,37 +99,39 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
 }
 
 struct __align__(16) TcShared {
-    uint64_t fullA, full[2], empty[2], tfull[2], tempty[2];
+    uint64_t fullA, full[3], empty[3], tfull[2], tempty[2];
     uint32_t tmem_base;
     int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // MB = 1: partial results of the upper-half-column warps
 };
 
-#define TC_SMEM_BYTES (160 * 1024 + sizeof(TcShared) + 64)   // MB = 1: A 32 KB + B 2 x 64 KB; MB = 2: A 64 KB + B 2 x 32 KB
+#define TC_SMEM_BYTES (160 * 1024 + sizeof(TcShared) + 64)   // MB = 1: A 32 KB + B 2 x 64 KB; MB = 2: A 64 KB + B 3 x 32 KB
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
 template <bool SECOND, int MB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist,
+hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist,
               int *__restrict__ second_dist)
 {
-    const TcPair pd = pairs[blockIdx.y];
+    const PairDesc pd = pairs[blockIdx.y];
     constexpr int TC_ROWS = TC_M * MB;
     constexpr int TN = MB == 1 ? 256 : 128;            // train rows per tile: TMEM holds 2 stages x MB blocks x TN = 512 columns
     constexpr int TB_BYTES = TN * TC_KB;
+    constexpr int NSB = MB == 1 ? 2 : 3;               // shared-memory stages of the train ring (the expanders run ahead of the MMAs)
     const int q0 = blockIdx.x * TC_ROWS;
     if (q0 >= pd.nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *sA = tc_smem;                                  // 2 x 32 KB (two M blocks)
-    uint8_t *sB = tc_smem + TC_ROWS * TC_KB;                // two stages of TN rows
-    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + 2 * TB_BYTES);
+    uint8_t *sA = tc_smem;                                  // MB x 32 KB
+    uint8_t *sB = tc_smem + TC_ROWS * TC_KB;                // NSB stages of TN rows
+    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES);
     const int NT = (pd.nt + TN - 1) / TN;
 
     if (threadIdx.x == 0) {
-        mbar_init(&S->fullA, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 8); }
+        mbar_init(&S->fullA, TC_EXP_THREADS);
+        for (int s = 0; s < 3; s++) { mbar_init(&S->full[s], TC_EXP_THREADS); mbar_init(&S->empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: 512 columns = 2 stages x 2 M blocks of 128x128 int32 accumulators
+    if (warp == 0) {   // TMEM: 512 columns = 2 stages x MB blocks of 128 x TN int32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -158,19 +141,46 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
     const uint32_t tmem = S->tmem_base;
     int best = -1000, second = -1000, bidx = -1;   // running (max dot, second, arg) of an epilogue thread
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---- producer
-            const int8_t *qa = pd.q + (size_t)q0 * TC_KB;   // rows q0.. are contiguous in the canonical layout
-            mbar_expect_tx(&S->fullA, TC_ROWS * TC_KB);
-            for (int c = 0; c < TC_ROWS * TC_KB; c += 16384) bulk_g2s(sA + c, qa + c, 16384, &S->fullA);
-            for (int t = 0; t < NT; t++) {
-                const int s = t & 1, ph = (t >> 1) & 1;
-                mbar_wait(&S->empty[s], ph ^ 1);
-                mbar_expect_tx(&S->full[s], TB_BYTES);
-                const int8_t *tb = pd.t + (size_t)t * TB_BYTES;
-                for (int c = 0; c < TB_BYTES; c += 16384) bulk_g2s(sB + s * TB_BYTES + c, tb + c, 16384, &S->full[s]);
+    if (warp >= TC_EXP_WARP0) {
+        // ---- expanders: packed descriptors (global, read-only path) -> +-1 int8 rows in shared memory
+        const int et = threadIdx.x - 32 * TC_EXP_WARP0;
+        constexpr int RPT = TN / TC_EXP_THREADS;              // train rows per expander thread and tile
+        const uint4 *tq = reinterpret_cast<const uint4 *>(pd.t);
+        uint4 lo[RPT], hi[RPT];
+        auto fetch = [&](int t) {
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const int row = t * TN + et + j * TC_EXP_THREADS;
+                if (row < pd.nt) { lo[j] = __ldg(tq + 2 * (size_t)row); hi[j] = __ldg(tq + 2 * (size_t)row + 1); }
             }
+        };
+        if (NT > 0) fetch(0);
+        {
+            const uint4 *qq = reinterpret_cast<const uint4 *>(pd.q);
+#pragma unroll 1
+            for (int r = et; r < TC_ROWS; r += TC_EXP_THREADS) {
+                const int row = q0 + r;
+                const bool valid = row < pd.nq;
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (valid) { a = __ldg(qq + 2 * (size_t)row); b = __ldg(qq + 2 * (size_t)row + 1); }
+                expand_row(sA, r, a, b, valid);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
+            mbar_arrive(&S->fullA);
+        }
+#pragma unroll 1
+        for (int t = 0; t < NT; t++) {
+            const int s = t % NSB, ph = (t / NSB) & 1;
+            mbar_wait(&S->empty[s], ph ^ 1);
+            uint8_t *tile = sB + s * TB_BYTES;
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const int r = et + j * TC_EXP_THREADS;
+                expand_row(tile, r, lo[j], hi[j], t * TN + r < pd.nt);
+            }
+            if (t + 1 < NT) fetch(t + 1);                     // in flight while the other roles consume this tile
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&S->full[s]);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -179,23 +189,24 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
             mbar_wait(&S->fullA, 0);
             const uint64_t adesc0 = make_desc(smem_u32(sA)), adesc1 = make_desc(smem_u32(sA + TC_M * TC_KB));
             for (int t = 0; t < NT; t++) {
-                const int s = t & 1, ph = (t >> 1) & 1;
+                const int s = t % NSB, ph = (t / NSB) & 1;      // shared-memory stage
+                const int ts = t & 1, tph = (t >> 1) & 1;       // TMEM stage
                 mbar_wait(&S->full[s], ph);
-                mbar_wait(&S->tempty[s], ph ^ 1);
+                mbar_wait(&S->tempty[ts], tph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t bdesc = make_desc(smem_u32(sB + s * TB_BYTES));
 #pragma unroll
                 for (int k = 0; k < TC_KB / 32; k++)   // K step = 32 bytes = two 16-byte core-matrix columns = 256 B in this layout
-                    mma_i8(tmem + (s * MB + 0) * TN, adesc0 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                    mma_i8(tmem + (ts * MB + 0) * TN, adesc0 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
                 if (MB > 1)
 #pragma unroll
                 for (int k = 0; k < TC_KB / 32; k++)
-                    mma_i8(tmem + (s * MB + 1) * TN, adesc1 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                    mma_i8(tmem + (ts * MB + 1) * TN, adesc1 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
                 tc_commit(&S->empty[s]);    // shared-memory stage reusable once these MMAs retire
-                tc_commit(&S->tfull[s]);    // accumulator ready for the epilogue
+                tc_commit(&S->tfull[ts]);   // accumulator ready for the epilogue
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ---- epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; warps 2..5 own the query rows of M block 0,
         //      warps 6..9 those of M block 1 — one thread per query row, all columns
         // (MB = 1: both warps of a lane quarter share the rows and split every tile's columns; merged at the end)
@@ -313,95 +324,25 @@ hamming_i8mma(const TcPair *__restrict__ pairs, int out_stride, int *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------ host side
-struct TcWs {
-    int8_t *exp = nullptr; size_t exp_bytes = 0;
-    TcPair *pairs = nullptr; int pairs_cap = 0;
-    int *frames = nullptr; int frames_cap = 0;
-};
-static TcWs *tcws(tb_ctx *ctx)
-{
-    if (!ctx->tcws) ctx->tcws = new TcWs();
-    return ctx->tcws;
-}
-void tb_match_tc_free(tb_ctx *ctx)
-{
-    TcWs *w = ctx->tcws;
-    if (!w) return;
-    cudaFree(w->exp); cudaFree(w->pairs); cudaFree(w->frames);
-    delete w;
-    ctx->tcws = nullptr;
-}
+void tb_match_tc_free(tb_ctx *) {}   // the tensor-core matcher keeps no workspace of its own any more (operands are expanded in the kernel)
 
-// Fills best_idx/best_dist[2P][kp_cap] exactly like hamming_knn<false> does for the pair table of match.cu.
-int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const int *d_q_frames, const int *d_t_frames, int n_frames_used,
-                    const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap, int *best_idx, int *best_dist)
+// Fills best_idx/best_dist[2P][kp_cap] exactly like hamming_knn<false> does for the same pair table (match.cu: build_pairs).
+int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_cap, int *best_idx, int *best_dist)
 {
-    TcWs *w = tcws(ctx);
-    const int rows_pad = (kp_cap + TC_PAD - 1) / TC_PAD * TC_PAD;
-    const size_t exp_stride = (size_t)rows_pad * TC_KB;
-    const size_t need = exp_stride * (size_t)n_frames_used;
-    if (need > w->exp_bytes) {
-        if (w->exp) cudaFree(w->exp);
-        TB_CUDA(ctx, cudaMalloc(&w->exp, need));
-        w->exp_bytes = need;
-    }
-    if (2 * n_pairs > w->pairs_cap) {
-        if (w->pairs) cudaFree(w->pairs);
-        TB_CUDA(ctx, cudaMalloc(&w->pairs, sizeof(TcPair) * 2 * n_pairs));
-        w->pairs_cap = 2 * n_pairs;
-    }
-    {
-        ProfScope prof__(ctx, "expand_desc_i8");
-        dim3 grid(div_up(rows_pad * 16, 256), n_frames_used);
-        expand_desc_i8<<<grid, 256, 0, ctx->stream>>>(desc, frame_stride, counts, 0, w->exp, exp_stride, rows_pad);
-        TB_LAUNCH_CHECK(ctx);
-    }
-    build_tc_pairs<<<div_up(n_pairs, 128), 128, 0, ctx->stream>>>(w->pairs, n_pairs, d_q_frames, d_t_frames, w->exp, exp_stride, counts);
+    ProfScope prof__(ctx, "hamming_i8mma");
+    dim3 grid(div_up(kp_cap, TC_M * 2), 2 * n_pairs);
+    hamming_i8mma<false, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, kp_cap, best_idx, best_dist, nullptr);
     TB_LAUNCH_CHECK(ctx);
-    const size_t smem = TC_SMEM_BYTES;
-    {
-        ProfScope prof__(ctx, "hamming_i8mma");
-        dim3 grid(div_up(kp_cap, TC_M * 2), 2 * n_pairs);
-        hamming_i8mma<false, 2><<<grid, TC_THREADS, smem, ctx->stream>>>(w->pairs, kp_cap, best_idx, best_dist, nullptr);
-        TB_LAUNCH_CHECK(ctx);
-    }
     return TB_OK;
 }
 
-// best / second / argbest of nq query rows against nt train rows (tb_knn2_device with the tensor-core matcher)
-int tb_knn2_tc(tb_ctx *ctx, const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *best, int *second)
+// best / second / argbest of nq query rows against nt train rows (tb_knn2_device with the tensor-core matcher);
+// d_pair = one PairDesc {q, t, nq, nt} already on the device
+int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pair, int nq, int *idx, int *best, int *second)
 {
-    TcWs *w = tcws(ctx);
-    const size_t q_rows = (size_t)(nq + TC_PAD - 1) / TC_PAD * TC_PAD, t_rows = (size_t)(nt + TC_PAD - 1) / TC_PAD * TC_PAD;
-    const size_t need = (q_rows + t_rows) * TC_KB;
-    if (need > w->exp_bytes) {
-        if (w->exp) cudaFree(w->exp);
-        w->exp = nullptr; w->exp_bytes = 0;
-        TB_CUDA(ctx, cudaMalloc(&w->exp, need));
-        w->exp_bytes = need;
-    }
-    if (w->pairs_cap < 2) {
-        if (w->pairs) cudaFree(w->pairs);
-        TB_CUDA(ctx, cudaMalloc(&w->pairs, sizeof(TcPair) * 2));
-        w->pairs_cap = 2;
-    }
-    int8_t *eq = w->exp, *et = w->exp + q_rows * TC_KB;
-    {
-        ProfScope prof__(ctx, "expand_desc_i8");
-        expand_desc_i8<<<dim3(div_up((int)q_rows * 16, 256), 1), 256, 0, ctx->stream>>>(q, 0, nullptr, nq, eq, 0, (int)q_rows);
-        TB_LAUNCH_CHECK(ctx);
-        expand_desc_i8<<<dim3(div_up((int)t_rows * 16, 256), 1), 256, 0, ctx->stream>>>(t, 0, nullptr, nt, et, 0, (int)t_rows);
-        TB_LAUNCH_CHECK(ctx);
-    }
-    TcPair pd = {eq, et, nq, nt};
-    TB_CUDA(ctx, cudaMemcpyAsync(w->pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = TC_SMEM_BYTES;
-    {
-        ProfScope prof__(ctx, "hamming_i8mma");
-        hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, smem, ctx->stream>>>(w->pairs, 0, idx, best, second);
-        TB_LAUNCH_CHECK(ctx);
-    }
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pair descriptor came from pageable host memory
+    ProfScope prof__(ctx, "hamming_i8mma");
+    hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pair, 0, idx, best, second);
+    TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
 

@@ -412,19 +412,7 @@ emit_matches(const QRes *res, int n, int check_orientation, int histo, tb_match 
 }
 
 // ------------------------------------------------------------------------------------------ host side
-struct DevBuf {
-    std::vector<void *> ptrs;
-    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
-    template <typename T> T *alloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, (n ? n : 1) * sizeof(T) + 64) != cudaSuccess) return nullptr; ptrs.push_back(p); return (T *)p; }
-    template <typename T> T *upload(const T *h, size_t n, cudaStream_t s)
-    {
-        T *d = alloc<T>(n);
-        if (d && n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
-        return d;
-    }
-};
-
-static int build_grid(tb_ctx *ctx, DevBuf &buf, const tb_keypoint *d_kps, int n, int cols, int rows, GridDev &g)
+static int build_grid(tb_ctx *ctx, ArenaScope &buf, const tb_keypoint *d_kps, int n, int cols, int rows, GridDev &g)
 {
     int *cellid = buf.alloc<int>(n), *count = buf.alloc<int>(GRID_CELLS), *start = buf.alloc<int>(GRID_CELLS + 1), *items = buf.alloc<int>(n);
     if (!cellid || !count || !start || !items) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
@@ -437,7 +425,7 @@ static int build_grid(tb_ctx *ctx, DevBuf &buf, const tb_keypoint *d_kps, int n,
     return TB_OK;
 }
 
-static int emit_and_download(tb_ctx *ctx, DevBuf &buf, const QRes *res, int nq, int check, int histo, tb_match *out, int capacity, int *n)
+static int emit_and_download(tb_ctx *ctx, ArenaScope &buf, const QRes *res, int nq, int check, int histo, tb_match *out, int capacity, int *n)
 {
     if (histo > 256 || histo < 1) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
     if (check && histo < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
@@ -458,9 +446,10 @@ static int emit_and_download(tb_ctx *ctx, DevBuf &buf, const QRes *res, int nq, 
 extern "C" int tb_features_in_area(tb_ctx *ctx, const tb_keypoint *kps, int n, int cols, int rows, float x, float y, float r,
                                    int minLevel, int maxLevel, int32_t *out, int capacity, int *n_out)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || n < 0 || !n_out || cols <= 0 || rows <= 0) return TB_E_INVALID;
-    DevBuf buf;
-    tb_keypoint *dk = buf.upload(kps, n, ctx->stream);
+    ArenaScope buf(ctx);
+    tb_keypoint *dk = buf.upload(kps, n);
     int *d_out = buf.alloc<int>(n + 32), *d_n = buf.alloc<int>(1);
     if (!dk || !d_out || !d_n) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     GridDev g;
@@ -481,12 +470,13 @@ extern "C" int tb_search_by_violence(tb_ctx *ctx, const tb_matcher_params *p, co
                                      const tb_keypoint *k2, const uint8_t *d2, int n2, int cols2, int rows2,
                                      int min_level, int max_level, float search_r, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
     *n = 0;
     if (n1 == 0) return TB_OK;
-    DevBuf buf;
-    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
-    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream), *dd2 = buf.upload(d2, (size_t)32 * n2, ctx->stream);
+    ArenaScope buf(ctx);
+    tb_keypoint *dk1 = buf.upload(k1, n1), *dk2 = buf.upload(k2, n2);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1), *dd2 = buf.upload(d2, (size_t)32 * n2);
     QRes *res = buf.alloc<QRes>(n1);
     if (!dk1 || !dk2 || !dd1 || !dd2 || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     GridDev g;
@@ -503,17 +493,18 @@ extern "C" int tb_search_by_projection(tb_ctx *ctx, const tb_matcher_params *p, 
                                        const tb_keypoint *k2, int n2, const uint8_t *mp_valid, const float *mp_xyz,
                                        const uint8_t *mp_desc, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || !cam || !Tcw1 || !sf1 || n1 < 0 || n2 < 0 || !n || n_levels1 <= 0 || n_levels1 > TB_MAX_LEVELS) return TB_E_INVALID;
     *n = 0;
     if (n2 == 0) return TB_OK;
     for (int i = 0; i < n2; i++) if (k2[i].octave < 0 || k2[i].octave >= n_levels1) return tb_fail(ctx, TB_E_INVALID, "octave outside the scale table");
-    DevBuf buf;
-    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
-    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream);
-    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1, ctx->stream) : nullptr;
-    uint8_t *dval = buf.upload(mp_valid, (size_t)n2, ctx->stream);
-    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n2, ctx->stream);
-    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n2, ctx->stream);
+    ArenaScope buf(ctx);
+    tb_keypoint *dk1 = buf.upload(k1, n1), *dk2 = buf.upload(k2, n2);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1);
+    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1) : nullptr;
+    uint8_t *dval = buf.upload(mp_valid, (size_t)n2);
+    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n2);
+    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n2);
     QRes *res = buf.alloc<QRes>(n2);
     if (!dk1 || !dk2 || !dd1 || !dval || !dxyz || !dmd || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     GridDev g;
@@ -533,16 +524,17 @@ extern "C" int tb_search_by_projection_map(tb_ctx *ctx, const tb_matcher_params 
                                            int n_mp, const uint8_t *mp_bad, const float *mp_xyz, const float *mp_normal,
                                            const uint8_t *mp_desc, float radio, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || !cam || !Tcw1 || !sf1 || n1 < 0 || n_mp < 0 || !n) return TB_E_INVALID;
     *n = 0;
     if (n_mp == 0) return TB_OK;
-    DevBuf buf;
-    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream);
-    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream);
-    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1, ctx->stream) : nullptr;
-    uint8_t *dbad = buf.upload(mp_bad, (size_t)n_mp, ctx->stream);
-    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n_mp, ctx->stream), *dnrm = buf.upload(mp_normal, (size_t)3 * n_mp, ctx->stream);
-    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n_mp, ctx->stream);
+    ArenaScope buf(ctx);
+    tb_keypoint *dk1 = buf.upload(k1, n1);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1);
+    uint8_t *dfm = f1_matched ? buf.upload(f1_matched, (size_t)n1) : nullptr;
+    uint8_t *dbad = buf.upload(mp_bad, (size_t)n_mp);
+    float *dxyz = buf.upload(mp_xyz, (size_t)3 * n_mp), *dnrm = buf.upload(mp_normal, (size_t)3 * n_mp);
+    uint8_t *dmd = buf.upload(mp_desc, (size_t)32 * n_mp);
     QRes *res = buf.alloc<QRes>(n_mp);
     if (!dk1 || !dd1 || !dbad || !dxyz || !dnrm || !dmd || !res) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     GridDev g;
@@ -560,26 +552,26 @@ extern "C" int tb_search_by_projection_map(tb_ctx *ctx, const tb_matcher_params 
 // test_vo-style tracking).  Nothing leaves the GPU: grids are built per frame by one CTA, one warp per
 // (pair, F2 keypoint) walks the window, one CTA per pair applies the rotation histogram and compacts.
 // ------------------------------------------------------------------------------------------
-#define GB_MAXKP 8192
 
 // CSR grid of every frame: cell_start[f][GRID_CELLS+1], items[f][kp_cap] (insertion = index order)
 __global__ void __launch_bounds__(1024)
 grid_build_batched(const tb_keypoint *__restrict__ kps, int kp_cap, const int *__restrict__ counts, float wInv, float hInv,
                    int *__restrict__ cell_start, int *__restrict__ items)
 {
-    __shared__ short s_cell[GB_MAXKP];
     __shared__ int s_cnt[GRID_CELLS + 1];
     __shared__ int s_part[1024];
     const int f = blockIdx.x, tid = threadIdx.x;
-    const int n = min(counts[f], min(kp_cap, GB_MAXKP));
+    const int n = min(counts[f], kp_cap);
     const tb_keypoint *k = kps + (size_t)f * kp_cap;
+    auto cell_of = [&](int i) {
+        const int px = (int)roundf(__fmul_rn(k[i].x, wInv)), py = (int)roundf(__fmul_rn(k[i].y, hInv));
+        return (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? -1 : px * GRID_ROWS + py;
+    };
     for (int i = tid; i <= GRID_CELLS; i += 1024) s_cnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
-        const int px = (int)roundf(__fmul_rn(k[i].x, wInv)), py = (int)roundf(__fmul_rn(k[i].y, hInv));
-        int c = -1;
-        if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) { c = px * GRID_ROWS + py; atomicAdd(&s_cnt[c], 1); }
-        s_cell[i] = (short)c;
+        const int c = cell_of(i);
+        if (c >= 0) atomicAdd(&s_cnt[c], 1);
     }
     __syncthreads();
     // exclusive scan of the 4320 cell counts
@@ -595,14 +587,24 @@ grid_build_batched(const tb_keypoint *__restrict__ kps, int kp_cap, const int *_
     for (int i = b0; i < b1; i++) { const int c = s_cnt[i]; s_cnt[i] = run; cs[i] = run; run += c; }
     if (tid == 1023) cs[GRID_CELLS] = s_part[1023];
     __syncthreads();
-    // place every keypoint at cell_start + (number of earlier keypoints in the same cell)
-    int *it = items + (size_t)f * kp_cap;
-    for (int i = tid; i < n; i += 1024) {
-        const int c = s_cell[i];
-        if (c < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < i; j++) rank += (s_cell[j] == c);
-        it[s_cnt[c] + rank] = i;
+    // stable placement in index order (the reference's push_back order, Frame.cpp:193-199): one warp walks the keypoints 32
+    // at a time; lanes of the same cell rank themselves with match_any, the cell's cursor advances by the group size
+    if (tid < 32) {
+        int *it = items + (size_t)f * kp_cap;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + tid;
+            const int c = i < n ? cell_of(i) : -1;
+            const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+            if (c >= 0) {
+                const unsigned same = __match_any_sync(act, c);
+                const int rank = __popc(same & ((1u << tid) - 1));
+                const int start = s_cnt[c];
+                it[start + rank] = i;
+                __syncwarp(act);
+                if (rank == 0) s_cnt[c] = start + __popc(same);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -768,15 +770,15 @@ static int win_ws_reserve(tb_ctx *ctx, int n_frames, int n_pairs, int kp_cap, bo
         cudaFree(w.cell_start); cudaFree(w.items); cudaFree(w.res); cudaFree(w.pairs);
         w.cell_start = nullptr; w.items = nullptr; w.res = nullptr; w.pairs = nullptr; w.frames = 0; w.pairs_cap = 0; w.kp_cap = kp_cap;
     }
+    int rc;
     if (need_grid && (size_t)n_frames > w.frames) {
-        TB_CUDA(ctx, cudaMalloc(&w.cell_start, sizeof(int) * (size_t)n_frames * (GRID_CELLS + 1)));
-        TB_CUDA(ctx, cudaMalloc(&w.items, sizeof(int) * (size_t)n_frames * kp_cap));
+        w.frames = 0;
+        if ((rc = tb_regrow(ctx, w.cell_start, (size_t)n_frames * (GRID_CELLS + 1))) || (rc = tb_regrow(ctx, w.items, (size_t)n_frames * kp_cap))) return rc;
         w.frames = n_frames;
     }
     if ((size_t)n_pairs > w.pairs_cap) {
-        cudaFree(w.res); cudaFree(w.pairs); w.res = nullptr; w.pairs = nullptr;
-        TB_CUDA(ctx, cudaMalloc(&w.res, sizeof(QRes) * (size_t)n_pairs * kp_cap));
-        TB_CUDA(ctx, cudaMalloc(&w.pairs, sizeof(ProjPair) * (size_t)n_pairs));
+        w.pairs_cap = 0;
+        if ((rc = tb_regrow(ctx, w.res, (size_t)n_pairs * kp_cap)) || (rc = tb_regrow(ctx, w.pairs, (size_t)n_pairs))) return rc;
         w.pairs_cap = n_pairs;
     }
     return TB_OK;
@@ -788,7 +790,6 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
                                  const float *sf1, int n_levels, int cols, int rows, tb_match *matches, int capacity, int *out_counts)
 {
     if (n_pairs <= 0) return TB_OK;
-    if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched projection matcher supports up to 8192 keypoints per frame");
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
     if (p->checkOrientation && p->HISTO_LENGTH < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
@@ -796,8 +797,7 @@ int tb_window_projection_batched(tb_ctx *ctx, const tb_matcher_params *p, const 
     WinWs &w = *ctx->wws;
     std::vector<ProjPair> hp(n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; memcpy(hp[i].T, Tcw1 + 16 * (size_t)i, sizeof(float) * 16); }
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    if ((rc = tb_stage_upload(ctx, w.pairs, hp.data(), sizeof(ProjPair) * n_pairs))) return rc;   // through the pinned ring: no host wait
     volatile float hInv = (float)GRID_COLS / (float)cols, wInv = (float)GRID_ROWS / (float)rows;   // Frame.cpp:30-31
     {
         ProfScope prof__(ctx, "grid_build_batched");
@@ -872,6 +872,7 @@ bow_transform(const int *__restrict__ child_start, const int *__restrict__ child
 extern "C" int tb_vocab_create(tb_ctx *ctx, int n_nodes, int depth_levels, const int32_t *parent, const uint8_t *is_leaf,
                                const uint8_t *desc, const double *weight, tb_vocab **out)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !out || n_nodes < 2 || !parent || !is_leaf || !desc || !weight) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_vocab_create: bad arguments") : TB_E_INVALID;
     // children of a node in ascending id (the order loadFromTextFile pushes them); word ids to leaves in id order
     std::vector<int> start(n_nodes + 1, 0), kids(n_nodes - 1), word(n_nodes, -1);
@@ -918,6 +919,7 @@ extern "C" void tb_vocab_destroy(tb_vocab *v)
 extern "C" int tb_bow_transform_device(tb_ctx *ctx, const tb_vocab *v, const uint8_t *d_desc, long long n, int levelsup,
                                        int32_t *d_word_id, int32_t *d_node_id, double *d_weight)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !v || n < 0 || (n > 0 && !d_desc)) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_bow_transform_device: bad arguments") : TB_E_INVALID;
     if (n == 0) return TB_OK;
     ProfScope prof__(ctx, "bow_transform");
@@ -930,10 +932,11 @@ extern "C" int tb_bow_transform_device(tb_ctx *ctx, const tb_vocab *v, const uin
 extern "C" int tb_bow_transform(tb_ctx *ctx, const tb_vocab *v, const uint8_t *desc, int n, int levelsup,
                                 int32_t *word_id, int32_t *node_id, double *weight)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !v || n < 0 || (n > 0 && !desc)) return ctx ? tb_fail(ctx, TB_E_INVALID, "tb_bow_transform: bad arguments") : TB_E_INVALID;
     if (n == 0) return TB_OK;
-    DevBuf buf;
-    uint8_t *dd = buf.upload(desc, (size_t)32 * n, ctx->stream);
+    ArenaScope buf(ctx);
+    uint8_t *dd = buf.upload(desc, (size_t)32 * n);
     int32_t *dw = buf.alloc<int32_t>(n), *dn = buf.alloc<int32_t>(n);
     double *dwt = buf.alloc<double>(n);
     if (!dd || !dw || !dn || !dwt) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
@@ -994,15 +997,16 @@ extern "C" int tb_search_by_bow(tb_ctx *ctx, const tb_matcher_params *p, const t
                                 const tb_keypoint *k2, const uint8_t *d2, const int32_t *node2, int n2, const uint8_t *mp_valid2,
                                 int map_point_only, tb_match *out, int capacity, int *n)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || n1 < 0 || n2 < 0 || !n) return TB_E_INVALID;
     *n = 0;
     if (n1 == 0 || n2 == 0) return TB_OK;
     if (n2 >= (1 << 20)) return tb_fail(ctx, TB_E_UNSUPPORTED, "searchByBow supports fewer than 2^20 features per frame");
-    DevBuf buf;
-    tb_keypoint *dk1 = buf.upload(k1, n1, ctx->stream), *dk2 = buf.upload(k2, n2, ctx->stream);
-    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1, ctx->stream), *dd2 = buf.upload(d2, (size_t)32 * n2, ctx->stream);
-    int32_t *dn1 = buf.upload(node1, n1, ctx->stream), *dn2 = buf.upload(node2, n2, ctx->stream);
-    uint8_t *dv = mp_valid2 ? buf.upload(mp_valid2, n2, ctx->stream) : nullptr;
+    ArenaScope buf(ctx);
+    tb_keypoint *dk1 = buf.upload(k1, n1), *dk2 = buf.upload(k2, n2);
+    uint8_t *dd1 = buf.upload(d1, (size_t)32 * n1), *dd2 = buf.upload(d2, (size_t)32 * n2);
+    int32_t *dn1 = buf.upload(node1, n1), *dn2 = buf.upload(node2, n2);
+    uint8_t *dv = mp_valid2 ? buf.upload(mp_valid2, n2) : nullptr;
     QRes *res = buf.alloc<QRes>(n1);
     if (!dk1 || !dk2 || !dd1 || !dd2 || !dn1 || !dn2 || !res || (mp_valid2 && !dv)) return tb_fail(ctx, TB_E_NOMEM, "cudaMalloc failed");
     TB_CUDA(ctx, cudaMemsetAsync(res, 0, sizeof(QRes) * n1, ctx->stream));   // slots past the bucketed features stay ok = 0
@@ -1132,8 +1136,7 @@ int tb_window_bow_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pairs, 
     std::vector<ProjPair> hp(n_pairs);
     memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; }
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    if ((rc = tb_stage_upload(ctx, w.pairs, hp.data(), sizeof(ProjPair) * n_pairs))) return rc;   // through the pinned ring: no host wait
     {
         ProfScope prof__(ctx, "bow_query_batched");
         bow_query_batched<<<dim3(div_up(kp_cap, 8), n_pairs), 256, 0, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, node, mp_valid, map_point_only, *p, w.res);
@@ -1152,7 +1155,6 @@ int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pa
                                int min_level, int max_level, float search_r, tb_match *matches, int capacity, int *out_counts)
 {
     if (n_pairs <= 0) return TB_OK;
-    if (kp_cap > GB_MAXKP) return tb_fail(ctx, TB_E_UNSUPPORTED, "batched windowed matcher supports up to 8192 keypoints per frame");
     if (p->HISTO_LENGTH < 1 || p->HISTO_LENGTH > 256) return tb_fail(ctx, TB_E_UNSUPPORTED, "HISTO_LENGTH must be in [1,256]");
     if (p->checkOrientation && p->HISTO_LENGTH < 19) return tb_fail(ctx, TB_E_INVALID, "checkOrientation needs HISTO_LENGTH >= 19: bins reach round(360/HISTO_LENGTH) and the reference asserts bin < HISTO_LENGTH");
     int rc = win_ws_reserve(ctx, n_frames, n_pairs, kp_cap, true);
@@ -1161,8 +1163,7 @@ int tb_window_violence_batched(tb_ctx *ctx, const tb_matcher_params *p, int n_pa
     std::vector<ProjPair> hp(n_pairs);
     memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = f1_frames[i]; hp[i].f2 = f2_frames[i]; }
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    if ((rc = tb_stage_upload(ctx, w.pairs, hp.data(), sizeof(ProjPair) * n_pairs))) return rc;   // through the pinned ring: no host wait
     volatile float hInv = (float)GRID_COLS / (float)cols, wInv = (float)GRID_ROWS / (float)rows;   // Frame.cpp:30-31
     {
         ProfScope prof__(ctx, "grid_build_batched");
@@ -1332,8 +1333,7 @@ int tb_window_stereo_batched(tb_ctx *ctx, const tb_stereo_params *p, int n_pairs
     std::vector<ProjPair> hp(n_pairs);
     memset(hp.data(), 0, sizeof(ProjPair) * n_pairs);
     for (int i = 0; i < n_pairs; i++) { hp[i].f1 = left_frames[i]; hp[i].f2 = right_frames[i]; }
-    TB_CUDA(ctx, cudaMemcpyAsync(w.pairs, hp.data(), sizeof(ProjPair) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hp is pageable and goes out of scope
+    if ((rc = tb_stage_upload(ctx, w.pairs, hp.data(), sizeof(ProjPair) * n_pairs))) return rc;   // through the pinned ring: no host wait
     {
         ProfScope prof__(ctx, "stereo_rowband_batched");
         stereo_rowband_batched<<<n_pairs, 512, smem, ctx->stream>>>(w.pairs, kps, desc, kp_cap, counts, sf, n_levels, n_rows, R, *p,
@@ -1350,11 +1350,12 @@ extern "C" int tb_stereo_match(tb_ctx *ctx, const tb_stereo_params *p, const tb_
                                const tb_keypoint *kR, const uint8_t *dR, int nR, const float *inv_sf, int n_levels, int n_rows,
                                tb_match *out, int capacity, int *n, float *depth)
 {
+    TB_DEVICE_GUARD(ctx);
     if (!ctx || !p || nL < 0 || nR < 0 || (nL && (!kL || !dL)) || (nR && (!kR || !dR)) || !inv_sf || !n || capacity < 0 || (capacity && !out)) return TB_E_INVALID;
     *n = 0;
     if (nL == 0) return TB_OK;
     const int cap = std::max(std::max(nL, nR), 1);
-    DevBuf buf;
+    ArenaScope buf(ctx);
     tb_keypoint *d_k = buf.alloc<tb_keypoint>(2 * (size_t)cap);
     uint8_t *d_d = buf.alloc<uint8_t>(64 * (size_t)cap);
     int *d_cnt = buf.alloc<int>(3);

@@ -5,6 +5,8 @@
 * large brute-force matching (BASELINE config 4) shards QUERY ROWS, the train set is replicated and the
   per-row (argbest, best, second) triples are assembled with one all_gather — the only collective.
 Works with any torch.distributed backend: nccl on GPUs, gloo in the CPU tests.
+The plumbing here (slices, the gather, the cross-check) is torch on the CURRENT stream: create the tb.Context on that stream
+(tb.Context(device, torch.cuda.current_stream().cuda_stream)) so that kernels and plumbing are ordered.
 """
 import torch
 import torch.distributed as dist
@@ -35,9 +37,11 @@ def gather_rows(local, n_total, group=None):
     return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
 
 
-def sharded_knn2(ctx, q_dev, t_dev, group=None):
+def sharded_knn2(ctx, q_dev, t_dev, group=None, events=None):
     """Config 4 on GPUs: every rank holds the full Q and T on its device, computes best / second /
-    argbest for its query rows with the CUDA kernel and gathers. Returns full (idx, best, second)."""
+    argbest for its query rows with the CUDA kernel and gathers. Returns full (idx, best, second).
+    events (optional list) receives three CUDA events recorded on the current stream: before the kernel,
+    after the kernel, after the gather — so the caller can split kernel time from collective time."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = q_dev.shape[0]
@@ -46,10 +50,36 @@ def sharded_knn2(ctx, q_dev, t_dev, group=None):
     idx = torch.empty(m, dtype=torch.int32, device=q_dev.device)
     best = torch.empty_like(idx)
     second = torch.empty_like(idx)
+
+    def mark():
+        if events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            events.append(e)
+
+    mark()
     if m:
         ctx.knn2_device(q_dev[lo:hi].data_ptr(), m, t_dev.data_ptr(), t_dev.shape[0], idx.data_ptr(), best.data_ptr(), second.data_ptr())
+    mark()
     if world == 1:
+        mark()
         return idx, best, second
     packed = torch.stack([idx, best, second], 1)
     full = gather_rows(packed, n, group)
+    mark()
     return full[:, 0].contiguous(), full[:, 1].contiguous(), full[:, 2].contiguous()
+
+
+def cross_check(idx12, idx21):
+    """cv::BFMatcher(crossCheck=true) on gathered argbest arrays: query q keeps its match t = idx12[q] iff idx21[t] == q
+    (lowest index on ties in both directions, as the kernels produce them)."""
+    n = idx12.shape[0]
+    return idx21[idx12.long()] == torch.arange(n, dtype=idx21.dtype, device=idx12.device)
+
+
+def sharded_knn2_cross(ctx, q_dev, t_dev, group=None, events=None):
+    """SURVEY.md §8(e) cross-check variant of config 4: the row-sharded kNN-2 of Q against T, the transposed problem
+    (T's rows sharded, against Q) and a second gather; returns (idx, best, second, mutual) for the query rows."""
+    i12, b12, s12 = sharded_knn2(ctx, q_dev, t_dev, group, events)
+    i21, _, _ = sharded_knn2(ctx, t_dev, q_dev, group, events)
+    return i12, b12, s12, cross_check(i12, i21)

@@ -1,12 +1,12 @@
 """Deterministic synthetic workloads (BASELINE.json configs 3-5).
 
 Inputs only — no algorithm lives here.  left.png is the KITTI-style fixture shipped in
-tests/golden/data (the reference's data/left.png)."""
+trackingbench_slam_b200/data (the reference's data/left.png)."""
 import os
 
 import numpy as np
 
-_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'data')
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 
 
 def load_gray(name):
