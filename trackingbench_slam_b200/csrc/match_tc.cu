@@ -24,17 +24,47 @@
 #define TC_MB_MAX 2       // M blocks per CTA (template parameter MB): with 2, 256 query rows share every train tile, which halves
                           // the L2 -> shared-memory traffic that bounds the batched frame-pair matcher; the 200k x 200k kNN-2
                           // keeps 1 (its top-2 epilogue is the bound and 128-row CTAs fill the last wave better)
-#define TC_KB 256         // bytes (= int8 elements) per expanded descriptor
+#define TC_KB 288         // bytes (= int8 elements) per expanded row: 256 descriptor bits + one more K step of 32 that carries the
+                          // tie-break key (see below)
+#define TC_SBO (TC_KB / 16 * 128)   // canonical layout: distance between 8-row groups
 #define TC_THREADS 448    // warp 0 TMEM allocation, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter), warps 10..13 expanders
 #define TC_EXP_THREADS 128
 #define TC_EXP_WARP0 10
+#define TC_LUT_BYTES (256 * 16 * 8)   // byte -> 8 x int8 table, 16 replicas (one per lane of a half warp: conflict-free LDS.64)
 
-// ---- expansion of one descriptor row into its shared-memory tile: 32 packed bytes -> 256 int8 (+1 for a 0 bit, -1 for a 1
-//      bit; a row beyond the set's count is written as zeros).  Chunk c (16 bits -> 16 bytes) of row r lives at
-//      (r/8)*2048 + c*128 + (r%8)*16: the eight lanes of a quarter warp (consecutive rows) store 128 contiguous bytes.
-__device__ __forceinline__ void expand_row(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid)
+// The key of the arg-max is produced by the tensor core itself.  Query rows are expanded to +-32 and carry a 1 in element
+// 256; train row j is expanded to +-1 and carries 31 - j%32 in element 256 (elements 257..287 are zero).  The accumulator is
+// then 32*dot + 31 - j%32: within a 32-column chunk a larger value means a larger dot product and, on ties, the lower column —
+// the epilogue only takes maxima (the first version spent one IMAD per element building these keys on the integer pipes,
+// which ncu showed to be the bound: ALU pipe 68 % busy, tensor pipe 45 %).
+//
+// Layout of an expanded row r inside its tile: chunk c (16 bytes = 16 K elements) at (r/8)*TC_SBO + c*128 + (r%8)*16 — the
+// UMMA canonical K-major no-swizzle layout; the eight lanes of a quarter warp (consecutive rows) store 128 contiguous bytes.
+
+// train rows: two table look-ups per chunk (the arithmetic expansion cost ~21 integer instructions per chunk)
+__device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid, const uint2 *lut)
 {
-    uint8_t *o = tile + (size_t)(r >> 3) * 2048 + (size_t)(r & 7) * 16;
+    uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
+    if (!valid) {
+#pragma unroll
+        for (int c = 0; c < 18; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint32_t w32[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t x = w32[w];
+        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
+    }
+    *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(31u - (uint32_t)(r & 31), 0, 0, 0);   // element 256: tie-break key (tiles start at multiples of 32)
+    *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
+}
+// query rows (once per CTA): +-32 and a 1 in element 256
+__device__ __forceinline__ void expand_row_query(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid)
+{
+    uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
     const uint32_t w32[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
     for (int c = 0; c < 16; c++) {
@@ -44,10 +74,12 @@ __device__ __forceinline__ void expand_row(uint8_t *tile, int r, const uint4 lo,
         for (int k = 0; k < 4; k++) {
             const uint32_t nib = (bits >> (4 * k)) & 0xF;
             const uint32_t b = (nib * 0x00204081u) & 0x01010101u;   // bit i -> byte i
-            w[k] = valid ? 0x01010101u + 0xFEu * b : 0u;              // per byte: 0 -> 0x01 (+1), 1 -> 0xFF (-1); no carries
+            w[k] = valid ? 0x20202020u + 0xC0u * b : 0u;              // per byte: 0 -> 0x20 (+32), 1 -> 0xE0 (-32); no carries
         }
         *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(valid ? 1u : 0u, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
 }
 
 // ---- PTX helpers
@@ -84,10 +116,10 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor: 8x16B core matrices, LBO = distance between the
-// two K-adjacent core matrices (128 B), SBO = distance between 8-row groups (2048 B), version 1 (sm_100).
+// two K-adjacent core matrices (128 B), SBO = distance between 8-row groups (TC_SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
 {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46);
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -104,7 +136,7 @@ struct __align__(16) TcShared {
     int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // MB = 1: partial results of the upper-half-column warps
 };
 
-#define TC_SMEM_BYTES (160 * 1024 + sizeof(TcShared) + 64)   // MB = 1: A 32 KB + B 2 x 64 KB; MB = 2: A 64 KB + B 3 x 32 KB
+#define TC_SMEM_BYTES (180 * 1024 + TC_LUT_BYTES + sizeof(TcShared) + 64)   // MB = 1: A 36 KB + B 2 x 72 KB; MB = 2: A 72 KB + B 3 x 36 KB; + table
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
 template <bool SECOND, int MB>
@@ -122,7 +154,8 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *sA = tc_smem;                                  // MB x 32 KB
     uint8_t *sB = tc_smem + TC_ROWS * TC_KB;                // NSB stages of TN rows
-    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES);
+    uint2 *lut = reinterpret_cast<uint2 *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES);
+    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES + TC_LUT_BYTES);
     const int NT = (pd.nt + TN - 1) / TN;
 
     if (threadIdx.x == 0) {
@@ -134,6 +167,11 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
     if (warp == 0) {   // TMEM: 512 columns = 2 stages x MB blocks of 128 x TN int32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += TC_THREADS) {   // byte e -> eight +-1 bytes, replica i % 16
+        const uint32_t e = (uint32_t)i >> 4;
+        const uint32_t b0 = ((e & 0xF) * 0x00204081u) & 0x01010101u, b1 = ((e >> 4) * 0x00204081u) & 0x01010101u;
+        lut[i] = make_uint2(0x01010101u + 0xFEu * b0, 0x01010101u + 0xFEu * b1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -163,7 +201,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                 const bool valid = row < pd.nq;
                 uint4 a = make_uint4(0, 0, 0, 0), b = a;
                 if (valid) { a = __ldg(qq + 2 * (size_t)row); b = __ldg(qq + 2 * (size_t)row + 1); }
-                expand_row(sA, r, a, b, valid);
+                expand_row_query(sA, r, a, b, valid);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
             mbar_arrive(&S->fullA);
@@ -176,7 +214,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
                 const int r = et + j * TC_EXP_THREADS;
-                expand_row(tile, r, lo[j], hi[j], t * TN + r < pd.nt);
+                expand_row_lut(tile, r, lo[j], hi[j], t * TN + r < pd.nt, lut + (lane & 15));
             }
             if (t + 1 < NT) fetch(t + 1);                     // in flight while the other roles consume this tile
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -236,12 +274,11 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int lim = pd.nt - (col0 + c);   // valid columns in this chunk
                 if (!SECOND && lim >= 32) {
-                    // best-only, full chunk: the epilogue is bound by the integer ALU pipe (compare + two selects per
-                    // element), so fold the column into the key with one IMAD each (dot * 32 + 31 - j: larger key = larger
-                    // dot, then lower column) and reduce the 32 keys with a max3 tree: ~0.6 ALU instructions per element
+                    // best-only, full chunk: the accumulators already are keys (dot * 32 + 31 - j: larger key = larger dot,
+                    // then lower column); reduce the 32 keys with a max3 tree: ~0.4 instructions per element
                     int k[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) k[j] = (int)v[j] * 32 + (31 - j);
+                    for (int j = 0; j < 32; j++) k[j] = (int)v[j];     // = dot * 32 + 31 - j, straight from the tensor core
 #pragma unroll
                     for (int j = 0; j < 30; j += 3) k[j / 3] = __vimax3_s32(k[j], k[j + 1], k[j + 2]);        // 30 -> 10
                     const int a0 = __vimax3_s32(k[0], k[1], k[2]), a1 = __vimax3_s32(k[3], k[4], k[5]), a2 = __vimax3_s32(k[6], k[7], k[8]);
@@ -257,7 +294,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                     int hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const int x = (int)v[2 * j] * 32 + (31 - 2 * j), y = (int)v[2 * j + 1] * 32 + (30 - 2 * j);
+                        const int x = (int)v[2 * j], y = (int)v[2 * j + 1];   // keys dot * 32 + 31 - column
                         hi[j] = max(x, y); lo[j] = min(x, y);
                     }
 #pragma unroll
@@ -276,7 +313,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const int d = (int)v[j];
+                    const int d = (int)v[j] >> 5;                        // key -> dot (arithmetic shift = floor, the key's low part is 0..31)
                     if (SECOND) {
                         if (j < lim) {
                             if (d > best) { second = best; best = d; bidx = col0 + c + j; }
