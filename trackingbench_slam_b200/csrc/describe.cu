@@ -303,7 +303,13 @@ __global__ void describe_init_pattern()
     const int8_t *q = &c_pattern[4 * (8 * ln + k)];
     g_pat_t[tid] = (uint32_t)(uint8_t)q[0] | ((uint32_t)(uint8_t)q[1] << 8) | ((uint32_t)(uint8_t)q[2] << 16) | ((uint32_t)(uint8_t)q[3] << 24);
 }
-void tb_describe_init_device() { describe_init_pattern<<<1, 256>>>(); cudaDeviceSynchronize(); }
+__global__ void orb_describe_fused(DescArgs a);
+void tb_describe_init_device()
+{
+    describe_init_pattern<<<1, 256>>>();
+    cudaFuncSetAttribute(orb_describe_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaDeviceSynchronize();
+}
 
 #define DESC_KPB 64   // keypoints per CTA (8 warps x 8 rounds)
 __global__ void __launch_bounds__(256, 4)
@@ -312,10 +318,10 @@ orb_describe(DescArgs a)
     __shared__ uint32_t s_pat[256]; // [k][lane]: pair 8*lane+k as (x0,y0,x1,y1) int8x4, conflict-free
     __shared__ int s_ofs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = blockIdx.y, f = blockIdx.z;
+    const int l = a.level_base + blockIdx.y, f = blockIdx.z;
     const int *nk = a.n_kept + (size_t)f * a.n_levels;
     const int nkl = nk[l];
-    const bool first = blockIdx.x == 0 && l == 0;
+    const bool first = blockIdx.x == 0 && l == a.n_levels - 1;   // the frame's total is written once every level's count exists
     if (blockIdx.x * DESC_KPB >= nkl && !first) return;          // nothing for this CTA (uniform)
     s_pat[tid] = g_pat_t[tid];
     if (warp == 0) {
@@ -397,11 +403,217 @@ orb_describe(DescArgs a)
     }
 }
 
-int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames)
+// ------------------------------------------------------------------------------------------
+// Fused K4+K5+K6 (the default): blur ON DEMAND.  computeOrbDescriptor only ever reads the blurred level inside a 37x37
+// window around each keypoint (the pattern's largest rotated coordinate is 18), i.e. <= 2000 x 1369 of the ~2 M pixels of a
+// 1080p level, and the dense Gaussian over all levels was 1.2 ms of the 8.2 ms step.  One warp per keypoint:
+//   1. stage the 43-row raw neighbourhood (rows cy-21..cy+21) as 12 aligned 32-bit words per row (the span that covers
+//      columns cx-21..cx+21) in shared memory; BORDER_REFLECT_101 rows are remapped, keypoints whose window leaves the level
+//      on the left/right (the outermost cell columns only) take a byte-wise path;
+//   2. IC_Angle from the staged bytes (same integer moments, same fastAtan2);
+//   3. horizontal 7-tap sums H (8.8 fixed point, u16, exact) of 40 columns x 43 rows with DP4A on shifted kernels, stored
+//      column-major so that a vertical window is contiguous;
+//   4. for each of the 512 pattern samples: 7 vertical taps as 4 DP2A on the u16 pairs, (v + 32768) >> 16 — the very
+//      integer OpenCV's fixed-point GaussianBlur produces — and the bit comparisons.
+// The dense kernels above stay for tb_frontend_download_level(blurred = 1) (the stage-by-stage parity tests).
+// ------------------------------------------------------------------------------------------
+#define FD_WARPS 8
+#define FD_PROW 13                      // words per staged row (12 used; 13 keeps lanes = consecutive rows conflict-free)
+#define FD_PWORDS (43 * FD_PROW)
+#define FD_HS 44                        // u16 per H column (43 rows + 1 pad); even: a column starts on a word
+#define FD_HWORDS (40 * FD_HS / 2)
+#define FD_WARP_WORDS (FD_PWORDS + FD_HWORDS + 1)
+extern __shared__ __align__(16) uint32_t fd_smem[];
+
+__global__ void __launch_bounds__(FD_WARPS * 32, 4)
+orb_describe_fused(DescArgs a)
 {
+    __shared__ uint32_t s_pat[256]; // [k][lane]: pair 8*lane+k as (x0,y0,x1,y1) int8x4, conflict-free
+    __shared__ int s_ofs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = a.level_base + blockIdx.y, f = blockIdx.z;
+    const int *nk = a.n_kept + (size_t)f * a.n_levels;
+    const int nkl = nk[l];
+    const bool first = blockIdx.x == 0 && l == a.n_levels - 1;   // the frame's total is written once every level's count exists
+    if (blockIdx.x * DESC_KPB >= nkl && !first) return;          // nothing for this CTA (uniform)
+    s_pat[tid] = g_pat_t[tid];
+    if (warp == 0) {
+        int c = lane < a.n_levels ? nk[lane] : 0;
+        int below = lane < l ? c : 0, total = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+        if (lane == 0) {
+            s_ofs = below;
+            if (first) {
+                a.n_kp[f] = min(total, a.kp_cap);
+                if (total > a.kp_cap) atomicExch(a.overflow, 4);
+            }
+        }
+    }
+    __syncthreads();
+    const int ofs = s_ofs;
+    const DescLevel L = a.lv[l];
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    uint32_t *Pw = fd_smem + (size_t)warp * FD_WARP_WORDS;      // staged rows
+    uint32_t *Hw = Pw + FD_PWORDS;                              // H, column-major u16 pairs
+    const uint8_t *Pb = reinterpret_cast<const uint8_t *>(Pw);
+    uint16_t *Hh = reinterpret_cast<uint16_t *>(Hw);
+    const uint8_t *img = L.raw + (size_t)f * L.frame_stride;
+    const int W = L.w, Hgt = L.h;
+    uint32_t disc = 0;                                          // bit v+15: row v of the radius-15 disc holds column u = lane-15
+    {
+        const int au = lane < 15 ? 15 - lane : lane - 15;
+#pragma unroll
+        for (int v = -15; v <= 15; v++) if (au <= c_umax[v < 0 ? -v : v]) disc |= 1u << (v + 15);
+    }
+
+    for (int i = blockIdx.x * DESC_KPB + warp; i < min(nkl, (int)(blockIdx.x + 1) * DESC_KPB); i += FD_WARPS) {
+        const uint32_t c = L.kept[(size_t)f * L.kept_cap + i];
+        const int cx = cand_x(c) + 16, cy = cand_y(c) + 16; // + minBorder (:816-817)
+        const int out = ofs + i;
+        if (out >= a.kp_cap) break;
+        __syncwarp();                                           // the previous keypoint's reads of P / H are over
+
+        // ---- 1. stage rows cy-21 .. cy+21; byte column of patch column 0 inside a staged row = sh
+        const int x0 = cx - 21;
+        int sh;
+        if (x0 >= 0 && cx + 21 < W && cy >= 21 && cy + 21 < Hgt) {
+            sh = x0 & 3;
+            // 4-byte aligned (pitch and frame stride are multiples of 64); 43 rows x 12 words = 516 words: 17 per lane, all
+            // loads in flight before the first store (the kernel was stalled on these loads one at a time)
+            const uint8_t *base = img + (size_t)(cy - 21) * L.pitch + (x0 - sh);
+#pragma unroll
+            for (int j0 = 0; j0 < 17; j0 += 9) {                // two batches (9 + 8 words per lane) keep the kernel at 64 registers
+                uint32_t v[9];
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    const int it = lane + 32 * (j0 + j), r = it / 12, k = it - r * 12;     // constant divisions
+                    if (j0 + j < 17 && it < 43 * 12) v[j] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * L.pitch) + k);
+                }
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    const int it = lane + 32 * (j0 + j), r = it / 12, k = it - r * 12;
+                    if (j0 + j < 17 && it < 43 * 12) Pw[r * FD_PROW + k] = v[j];
+                }
+            }
+        } else {                                                // window leaves the level (outermost cells only): byte-wise with reflection
+            sh = 0;
+            uint8_t *Pm = reinterpret_cast<uint8_t *>(Pw);
+#pragma unroll 1
+            for (int it = lane; it < 43 * 48; it += 32) {
+                const int r = it / 48, k = it - r * 48;
+                const int y = reflect101(cy - 21 + r, Hgt), x = reflect101(x0 + k, W);
+                Pm[r * (FD_PROW * 4) + k] = img[(size_t)y * L.pitch + x];
+            }
+        }
+        __syncwarp();
+
+        // ---- 2. IC_Angle on the staged (un-blurred) bytes: lanes 0..30 = u in [-15,15], rows v in [-15,15]
+        int m10 = 0, m01 = 0;
+        {
+            const int u = lane - 15;
+            if (lane < 31) {
+                const uint8_t *pc = Pb + 21 * (FD_PROW * 4) + sh + 21 + u;
+                int s0 = 0;
+#pragma unroll
+                for (int v = -15; v <= 15; v++) {
+                    const int val = ((disc >> (v + 15)) & 1u) ? (int)pc[v * (FD_PROW * 4)] : 0;
+                    s0 += val; m01 += v * val;
+                }
+                m10 = u * s0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            }
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- 3. horizontal sums: item = (4-column group g, row r); the four sums of patch columns 4g..4g+3 (+0..6)
+        {
+            const uint32_t K0a = 18u | (34u << 8) | (48u << 16) | (56u << 24), K0b = 48u | (34u << 8) | (18u << 16);
+            const uint32_t K1a = (18u << 8) | (34u << 16) | (48u << 24), K1b = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+            const uint32_t K2a = (18u << 16) | (34u << 24), K2b = 48u | (56u << 8) | (48u << 16) | (34u << 24), K2c = 18u;
+            const uint32_t K3a = (18u << 24), K3b = 34u | (48u << 8) | (56u << 16) | (48u << 24), K3c = 34u | (18u << 8);
+            const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)sh;   // PRMT selector: bytes sh .. sh+3 of a word pair
+#pragma unroll 1
+            for (int it = lane; it < 10 * 43; it += 32) {
+                const int g = it / 43, r = it - g * 43;
+                const uint32_t *row = Pw + r * FD_PROW + g;
+                const uint32_t q0 = row[0], q1 = row[1], q2 = row[2], q3 = g < 9 ? row[3] : 0u;   // group 9 ends at word 11
+                const uint32_t w0 = __byte_perm(q0, q1, sel), w1 = __byte_perm(q1, q2, sel), w2 = __byte_perm(q2, q3, sel);
+                const uint32_t h0 = __dp4a(w0, K0a, __dp4a(w1, K0b, 0u));
+                const uint32_t h1 = __dp4a(w0, K1a, __dp4a(w1, K1b, 0u));
+                const uint32_t h2 = __dp4a(w0, K2a, __dp4a(w1, K2b, __dp4a(w2, K2c, 0u)));
+                const uint32_t h3 = __dp4a(w0, K3a, __dp4a(w1, K3b, __dp4a(w2, K3c, 0u)));
+                uint16_t *hc = Hh + (4 * g) * FD_HS + r;
+                hc[0] = (uint16_t)h0; hc[FD_HS] = (uint16_t)h1; hc[2 * FD_HS] = (uint16_t)h2; hc[3 * FD_HS] = (uint16_t)h3;
+            }
+        }
+        __syncwarp();
+
+        // ---- 4. steered rBRIEF on the on-demand blur; lane i produces byte i
+        const float ang = __fmul_rn(angle, factorPI);
+        // glibc cosf/sinf are (nearly always) correctly rounded; evaluate in double and round once
+        const float ca = (float)cos((double)ang), sb = (float)sin((double)ang);
+        auto blurred = [&](int rr, int cc) -> int {             // rr, cc in [-18, 18] relative to the keypoint
+            const int j = cc + 18, r0 = rr + 18;                // H column, first of the 7 H rows
+            const bool odd = r0 & 1;
+            const uint32_t *hw = Hw + j * (FD_HS / 2) + (r0 >> 1);
+            const uint32_t A0 = hw[0], A1 = hw[1], A2 = hw[2], A3 = hw[3];
+            const uint32_t k0 = odd ? (18u << 8) : (18u | (34u << 8)), k1 = odd ? (34u | (48u << 8)) : (48u | (56u << 8));
+            const uint32_t k2 = odd ? (56u | (48u << 8)) : (48u | (34u << 8)), k3 = odd ? (34u | (18u << 8)) : 18u;
+            const uint32_t v = __dp2a_lo(A0, k0, __dp2a_lo(A1, k1, __dp2a_lo(A2, k2, __dp2a_lo(A3, k3, 32768u))));
+            return (int)(v >> 16);
+        };
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t q = s_pat[k * 32 + lane];
+            float px0 = (float)(int8_t)(q & 0xFF), py0 = (float)(int8_t)((q >> 8) & 0xFF);
+            float px1 = (float)(int8_t)((q >> 16) & 0xFF), py1 = (float)(int8_t)(q >> 24);
+            int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, sb), __fmul_rn(py0, ca)));
+            int c0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, ca), __fmul_rn(py0, sb)));
+            int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, sb), __fmul_rn(py1, ca)));
+            int c1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, ca), __fmul_rn(py1, sb)));
+            const int t0 = blurred(r0, c0), t1 = blurred(r1, c1);
+            val |= (t0 < t1) << k;
+        }
+        a.desc[((size_t)f * a.kp_cap + out) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            tb_keypoint kp;
+            kp.x = (float)cx; kp.y = (float)cy;
+            if (l != 0) { kp.x = __fmul_rn(kp.x, L.sf); kp.y = __fmul_rn(kp.y, L.sf); } // :969-974 (multiplies; replicated)
+            kp.size = L.size;
+            kp.angle = angle;
+            kp.response = (float)(cand_m(c) - 1);
+            kp.octave = l;
+            kp.class_id = -1;
+            a.kps[(size_t)f * a.kp_cap + out] = kp;
+        }
+    }
+}
+
+bool tb_describe_fused()
+{
+    static const bool v = !(getenv("TB_DESC_FUSED") && atoi(getenv("TB_DESC_FUSED")) == 0);
+    return v;
+}
+
+int tb_launch_describe(tb_ctx *ctx, const DescArgs &a0, int max_kept_per_level, int n_frames, int level_base, int n_levels_launch, cudaStream_t stream)
+{
+    DescArgs a = a0;
+    a.level_base = level_base;
+    dim3 grid(div_up(max_kept_per_level, DESC_KPB), n_levels_launch, n_frames);
+    if (tb_describe_fused()) {
+        ProfScope prof__(ctx, "orb_describe_fused");
+        orb_describe_fused<<<grid, FD_WARPS * 32, sizeof(uint32_t) * FD_WARP_WORDS * FD_WARPS, stream>>>(a);
+        TB_LAUNCH_CHECK(ctx);
+        return TB_OK;
+    }
     ProfScope prof__(ctx, "orb_describe");
-    dim3 grid(div_up(max_kept_per_level, DESC_KPB), a.n_levels, n_frames);
-    orb_describe<<<grid, 256, 0, ctx->stream>>>(a);
+    orb_describe<<<grid, 256, 0, stream>>>(a);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }

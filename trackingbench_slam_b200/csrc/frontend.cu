@@ -153,6 +153,7 @@ struct tb_frontend {
     float2 *exit_xy = nullptr; int16_t *enid = nullptr; int exit_cap = 0;
     int budget[TB_MAX_LEVELS] = {};
     bool has_budget = false;
+    bool blur_valid = false;   // the dense blurred levels hold the Gaussian of the current pyramid (else made on demand)
     uint8_t *raw = nullptr; size_t raw_bytes = 0;   // staging for distorted frames (tb_frontend_upload_frames_undistort)
     // CUDA graphs of the launch sequences of small batches (the single-frame host entries are launch bound: ~50 launches
     // for well under a millisecond of kernels): captured once per parameter set, replayed afterwards
@@ -358,6 +359,12 @@ extern "C" int tb_frontend_download_level(tb_frontend *fe, int frame, int level,
     TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || !host || frame < 0 || frame >= fe->B || level < 0 || level >= fe->L) return TB_E_INVALID;
     const LevelGeom &g = fe->g[level];
+    if (blurred && !fe->blur_valid) {
+        // blur on demand: ORBExtractor's GaussianBlur(7x7, sigma 2) of this frame's level (ORBextractor.cpp:959-960)
+        int rc = tb_launch_gauss(fe->ctx, fe->ctx->stream, fe->pyr[level] + (size_t)frame * g.frame_stride, fe->blur[level] + (size_t)frame * g.frame_stride,
+                                 g.w, g.h, g.pitch, g.frame_stride, 1);
+        if (rc) return rc;
+    }
     const uint8_t *src = (blurred ? fe->blur[level] : fe->pyr[level]) + (size_t)frame * g.frame_stride;
     TB_CUDA(fe->ctx, cudaMemcpy2DAsync(host, host_stride, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, fe->ctx->stream));
     TB_CUDA(fe->ctx, cudaStreamSynchronize(fe->ctx->stream));
@@ -369,6 +376,13 @@ static int graph_max_frames()
 {
     static const int v = getenv("TB_GRAPHS") ? atoi(getenv("TB_GRAPHS")) : 16;
     return v;
+}
+// Graph replay pays where a call is launch bound: small batches of small frames (a KITTI frame is ~50 launches for well under
+// a millisecond of kernels).  Above ~9 Mpx of level-0 pixels per call (one 4K frame, four 1080p frames) the kernels outlast the
+// launches and the call is enqueued directly.
+static bool graph_worthwhile(const tb_frontend *fe, int n_frames)
+{
+    return n_frames <= graph_max_frames() && (size_t)n_frames * fe->g[0].w * fe->g[0].h <= (size_t)9 << 20;
 }
 // capture `enqueue` on the ctx stream into slot (or replay it if the slot already holds this parameter set)
 template <typename F>
@@ -412,7 +426,7 @@ extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
     if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
     if (n_frames == 0) return TB_OK;
     tb_ctx *ctx = fe->ctx;
-    if (ctx->profiling || n_frames > graph_max_frames()) return pyramid_enqueue(fe, n_frames);
+    if (ctx->profiling || !graph_worthwhile(fe, n_frames)) return pyramid_enqueue(fe, n_frames);
     const bool same = fe->g_pyramid.n_frames == n_frames;
     fe->g_pyramid.n_frames = n_frames;
     return run_captured(ctx, fe->g_pyramid, same, [&]() { return pyramid_enqueue(fe, n_frames); });
@@ -464,7 +478,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
         TB_CUDA(ctx, cudaMemcpyAsync(fe->exit_xy, xy.data(), sizeof(float2) * n_exit, cudaMemcpyHostToDevice, ctx->stream));
         TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    if (add_points || ctx->profiling || n_frames > graph_max_frames())
+    if (add_points || ctx->profiling || !graph_worthwhile(fe, n_frames))
         return extract_enqueue(fe, n_frames, sf, initTh, minTh, add_points, n_exit);
     tb_frontend::GraphSlot &gs = fe->g_extract;
     bool same = gs.n_frames == n_frames && gs.target == target && gs.initTh == initTh && gs.minTh == minTh;
@@ -490,6 +504,8 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
     //          behind FAST of the following levels
     // (With per-kernel profiling on, everything stays on the main stream so the event pairs stay meaningful.)
     const bool overlap = !ctx->profiling;
+    const bool dense_blur = !tb_describe_fused();   // the fused describe kernel blurs on demand; the dense levels are made lazily
+    fe->blur_valid = dense_blur;
     // per-level octree launches only pay when FAST of the next level is long enough to hide them; for small batches (the
     // single-frame host entries) one launch with all levels side by side has the lower latency
     const bool per_level = overlap && n_frames >= 32;
@@ -497,13 +513,29 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
     if (overlap) {
         TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
         TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        for (int l = 0; l < L; l++) {
+        for (int l = 0; l < L && dense_blur; l++) {
             const LevelGeom &g = fe->g[l];
             int rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
             if (rc) return rc;
         }
         TB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
     }
+    DescArgs d;
+    memset(&d, 0, sizeof d);
+    d.n_levels = L; d.n_kept = fe->n_kept; d.kps = fe->kps; d.desc = fe->desc; d.kp_cap = fe->kp_cap; d.n_kp = fe->n_kp;
+    d.overflow = fe->overflow;
+    for (int l = 0; l < L; l++) {
+        const LevelGeom &g = fe->g[l];
+        d.lv[l].raw = fe->pyr[l]; d.lv[l].blur = fe->blur[l]; d.lv[l].pitch = g.pitch; d.lv[l].frame_stride = g.frame_stride;
+        d.lv[l].w = g.w; d.lv[l].h = g.h;
+        d.lv[l].kept = fe->kept[l]; d.lv[l].kept_cap = fe->kept_cap;
+        d.lv[l].sf = sf[l];
+        volatile float ps = 31 * sf[l];
+        d.lv[l].size = (float)(int)ps; // (int)(PATCH_SIZE*mvScaleFactor[level]) :812
+    }
+    // with blur on demand the describe kernel only needs the pyramid and the octree's winners: for large batches it follows the
+    // octree of its level on the side stream and hides behind FAST of the next levels, as the octree does
+    const bool desc_per_level = per_level && tb_describe_fused();
     int max_budget = 0;
     OctArgs oct[TB_MAX_LEVELS];
     for (int l = 0; l < L; l++) {
@@ -551,6 +583,7 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             TB_CUDA(ctx, cudaStreamWaitEvent(os, ctx->ev_lvl[l], 0));
             int rc = tb_launch_octree(ctx, &oct[l], 1, n_frames, os);
             if (rc) return rc;
+            if (desc_per_level) { rc = tb_launch_describe(ctx, d, fe->budget[l] + 4, n_frames, l, 1, os); if (rc) return rc; }
         }
     }
     if (!per_level) {
@@ -565,25 +598,14 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
         TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else {
         int rc = TB_OK;
-        for (int l = 0; l < L; l++) {
+        for (int l = 0; l < L && dense_blur; l++) {
             const LevelGeom &g = fe->g[l];
             rc = tb_launch_gauss(ctx, gs, fe->pyr[l], fe->blur[l], g.w, g.h, g.pitch, g.frame_stride, n_frames);
             if (rc) return rc;
         }
     }
-    DescArgs d;
-    memset(&d, 0, sizeof d);
-    d.n_levels = L; d.n_kept = fe->n_kept; d.kps = fe->kps; d.desc = fe->desc; d.kp_cap = fe->kp_cap; d.n_kp = fe->n_kp;
-    d.overflow = fe->overflow;
-    for (int l = 0; l < L; l++) {
-        const LevelGeom &g = fe->g[l];
-        d.lv[l].raw = fe->pyr[l]; d.lv[l].blur = fe->blur[l]; d.lv[l].pitch = g.pitch; d.lv[l].frame_stride = g.frame_stride;
-        d.lv[l].kept = fe->kept[l]; d.lv[l].kept_cap = fe->kept_cap;
-        d.lv[l].sf = sf[l];
-        volatile float ps = 31 * sf[l];
-        d.lv[l].size = (float)(int)ps; // (int)(PATCH_SIZE*mvScaleFactor[level]) :812
-    }
-    return tb_launch_describe(ctx, d, max_budget + 4, n_frames);
+    if (desc_per_level) return TB_OK;   // every level's describe launch already follows its octree on the side stream
+    return tb_launch_describe(ctx, d, max_budget + 4, n_frames, 0, L, ctx->stream);
 }
 
 static int check_overflow(tb_frontend *fe)

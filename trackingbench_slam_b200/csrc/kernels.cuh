@@ -47,18 +47,21 @@ int tb_launch_gauss(tb_ctx *ctx, cudaStream_t stream, const uint8_t *src, uint8_
 struct DescLevel {
     const uint8_t *raw, *blur;
     int pitch; size_t frame_stride;
+    int w, h;
     const uint32_t *kept; int kept_cap;
     float sf; float size;
 };
 struct DescArgs {
     DescLevel lv[TB_MAX_LEVELS];
     int n_levels;
+    int level_base;    // first level of this launch (blockIdx.y counts from it); the launch holding the last level writes n_kp
     const int *n_kept;
     tb_keypoint *kps; uint8_t *desc; int kp_cap;
     int *n_kp;
     int *overflow;
 };
-int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames);
+int tb_launch_describe(tb_ctx *ctx, const DescArgs &a, int max_kept_per_level, int n_frames, int level_base, int n_levels_launch, cudaStream_t stream);
+bool tb_describe_fused();   // blur on demand inside the describe kernel (default) instead of dense Gaussian levels
 // one brute-force matching problem: nq query rows against nt train rows of 32-byte descriptors (device pointers)
 struct PairDesc {
     const uint8_t *q, *t;
