@@ -460,6 +460,7 @@ orb_describe_fused(DescArgs a)
     uint16_t *Hh = reinterpret_cast<uint16_t *>(Hw);
     const uint8_t *img = L.raw + (size_t)f * L.frame_stride;
     const int W = L.w, Hgt = L.h;
+    const int st_r = lane >= 12 ? 1 : 0, st_k = lane - 12 * st_r;   // staging role of this lane (lanes 24..31 idle there)
     uint32_t disc = 0;                                          // bit v+15: row v of the radius-15 disc holds column u = lane-15
     {
         const int au = lane < 15 ? 15 - lane : lane - 15;
@@ -467,35 +468,44 @@ orb_describe_fused(DescArgs a)
         for (int v = -15; v <= 15; v++) if (au <= c_umax[v < 0 ? -v : v]) disc |= 1u << (v + 15);
     }
 
-    for (int i = blockIdx.x * DESC_KPB + warp; i < min(nkl, (int)(blockIdx.x + 1) * DESC_KPB); i += FD_WARPS) {
-        const uint32_t c = L.kept[(size_t)f * L.kept_cap + i];
+    // Staging of keypoint i+8 (this warp's next one) is issued with cp.async right after the H pass of keypoint i — the staged
+    // rows are dead from then on — so the global-memory latency hides behind the sampling phase.
+    const int i_end = min(nkl, (int)(blockIdx.x + 1) * DESC_KPB);
+    auto inside = [&](int cx, int cy) { return cx - 21 >= 0 && cx + 21 < W && cy >= 21 && cy + 21 < Hgt; };
+    auto prefetch = [&](uint32_t c) {                           // 43 rows x 12 aligned words -> P, asynchronously
+        const int cx = cand_x(c) + 16, cy = cand_y(c) + 16;
+        if (!inside(cx, cy)) return;
+        const int x0 = cx - 21, sh = x0 & 3;
+        const uint8_t *base = img + (size_t)(cy - 21) * L.pitch + (x0 - sh);   // 4-byte aligned (pitch, frame stride: multiples of 64)
+        // lanes 0..11 copy the 12 words of an even row, lanes 12..23 those of the odd row below it (22 steps; the address of a
+        // step is one multiply-add away from the lane's first one — a flat word index cost 15 instructions per copy)
+        if (lane < 24) {
+            const uint8_t *src = base + (size_t)st_r * L.pitch + 4 * st_k;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Pw) + 4u * (uint32_t)(st_r * FD_PROW + st_k);
+#pragma unroll
+            for (int j = 0; j < 22; j++)
+                if (2 * j + st_r < 43)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)(2 * FD_PROW * j)),
+                                 "l"(src + (size_t)(2 * j) * L.pitch) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int i = blockIdx.x * DESC_KPB + warp;
+    uint32_t c_next = 0;
+    if (i < i_end) { c_next = L.kept[(size_t)f * L.kept_cap + i]; prefetch(c_next); }
+    for (; i < i_end; i += FD_WARPS) {
+        const uint32_t c = c_next;
         const int cx = cand_x(c) + 16, cy = cand_y(c) + 16; // + minBorder (:816-817)
         const int out = ofs + i;
         if (out >= a.kp_cap) break;
-        __syncwarp();                                           // the previous keypoint's reads of P / H are over
+        if (i + FD_WARPS < i_end) c_next = L.kept[(size_t)f * L.kept_cap + i + FD_WARPS];
 
-        // ---- 1. stage rows cy-21 .. cy+21; byte column of patch column 0 inside a staged row = sh
+        // ---- 1. rows cy-21 .. cy+21 are staged (byte column of patch column 0 inside a staged row = sh)
         const int x0 = cx - 21;
         int sh;
-        if (x0 >= 0 && cx + 21 < W && cy >= 21 && cy + 21 < Hgt) {
+        if (inside(cx, cy)) {
             sh = x0 & 3;
-            // 4-byte aligned (pitch and frame stride are multiples of 64); 43 rows x 12 words = 516 words: 17 per lane, all
-            // loads in flight before the first store (the kernel was stalled on these loads one at a time)
-            const uint8_t *base = img + (size_t)(cy - 21) * L.pitch + (x0 - sh);
-#pragma unroll
-            for (int j0 = 0; j0 < 17; j0 += 9) {                // two batches (9 + 8 words per lane) keep the kernel at 64 registers
-                uint32_t v[9];
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int it = lane + 32 * (j0 + j), r = it / 12, k = it - r * 12;     // constant divisions
-                    if (j0 + j < 17 && it < 43 * 12) v[j] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * L.pitch) + k);
-                }
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int it = lane + 32 * (j0 + j), r = it / 12, k = it - r * 12;
-                    if (j0 + j < 17 && it < 43 * 12) Pw[r * FD_PROW + k] = v[j];
-                }
-            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         } else {                                                // window leaves the level (outermost cells only): byte-wise with reflection
             sh = 0;
             uint8_t *Pm = reinterpret_cast<uint8_t *>(Pw);
@@ -537,26 +547,38 @@ orb_describe_fused(DescArgs a)
             const uint32_t K2a = (18u << 16) | (34u << 24), K2b = 48u | (56u << 8) | (48u << 16) | (34u << 24), K2c = 18u;
             const uint32_t K3a = (18u << 24), K3b = 34u | (48u << 8) | (56u << 16) | (48u << 24), K3c = 34u | (18u << 8);
             const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)sh;   // PRMT selector: bytes sh .. sh+3 of a word pair
-#pragma unroll 1
-            for (int it = lane; it < 10 * 43; it += 32) {
-                const int g = it / 43, r = it - g * 43;
-                const uint32_t *row = Pw + r * FD_PROW + g;
-                const uint32_t q0 = row[0], q1 = row[1], q2 = row[2], q3 = g < 9 ? row[3] : 0u;   // group 9 ends at word 11
-                const uint32_t w0 = __byte_perm(q0, q1, sel), w1 = __byte_perm(q1, q2, sel), w2 = __byte_perm(q2, q3, sel);
-                const uint32_t h0 = __dp4a(w0, K0a, __dp4a(w1, K0b, 0u));
-                const uint32_t h1 = __dp4a(w0, K1a, __dp4a(w1, K1b, 0u));
-                const uint32_t h2 = __dp4a(w0, K2a, __dp4a(w1, K2b, __dp4a(w2, K2c, 0u)));
-                const uint32_t h3 = __dp4a(w0, K3a, __dp4a(w1, K3b, __dp4a(w2, K3c, 0u)));
-                uint16_t *hc = Hh + (4 * g) * FD_HS + r;
-                hc[0] = (uint16_t)h0; hc[FD_HS] = (uint16_t)h1; hc[2 * FD_HS] = (uint16_t)h2; hc[3 * FD_HS] = (uint16_t)h3;
+            // a lane owns a row (two passes: rows 0..31, then 32..42) and slides over its 12 words: one load and one byte
+            // permute per 4-column group, no address arithmetic (the flat (group, row) index spent a third of this phase on it)
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                const int r = lane + 32 * pass;
+                if (r < 43) {
+                    const uint32_t *row = Pw + r * FD_PROW;
+                    uint16_t *hc = Hh + r;
+                    uint32_t qa = row[0], qb = row[1], qc = row[2];
+                    uint32_t w0 = __byte_perm(qa, qb, sel), w1 = __byte_perm(qb, qc, sel);
+#pragma unroll
+                    for (int g = 0; g < 10; g++) {
+                        const uint32_t qd = g < 9 ? row[g + 3] : 0u;       // group 9 ends at word 11
+                        const uint32_t w2 = __byte_perm(qc, qd, sel);
+                        hc[(4 * g) * FD_HS] = (uint16_t)__dp4a(w0, K0a, __dp4a(w1, K0b, 0u));
+                        hc[(4 * g + 1) * FD_HS] = (uint16_t)__dp4a(w0, K1a, __dp4a(w1, K1b, 0u));
+                        hc[(4 * g + 2) * FD_HS] = (uint16_t)__dp4a(w0, K2a, __dp4a(w1, K2b, __dp4a(w2, K2c, 0u)));
+                        hc[(4 * g + 3) * FD_HS] = (uint16_t)__dp4a(w0, K3a, __dp4a(w1, K3b, __dp4a(w2, K3c, 0u)));
+                        w0 = w1; w1 = w2; qc = qd;
+                    }
+                }
             }
         }
-        __syncwarp();
+        __syncwarp();                                           // P is dead, H is complete
+        if (i + FD_WARPS < i_end && ofs + i + FD_WARPS < a.kp_cap) prefetch(c_next);
 
         // ---- 4. steered rBRIEF on the on-demand blur; lane i produces byte i
         const float ang = __fmul_rn(angle, factorPI);
         // glibc cosf/sinf are (nearly always) correctly rounded; evaluate in double and round once
-        const float ca = (float)cos((double)ang), sb = (float)sin((double)ang);
+        double dsn, dcs;
+        sincos((double)ang, &dsn, &dcs);                        // one argument reduction for both
+        const float ca = (float)dcs, sb = (float)dsn;
         auto blurred = [&](int rr, int cc) -> int {             // rr, cc in [-18, 18] relative to the keypoint
             const int j = cc + 18, r0 = rr + 18;                // H column, first of the 7 H rows
             const bool odd = r0 & 1;
@@ -593,6 +615,7 @@ orb_describe_fused(DescArgs a)
             a.kps[(size_t)f * a.kp_cap + out] = kp;
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");          // nothing in flight when the CTA retires (capacity break above)
 }
 
 bool tb_describe_fused()
