@@ -430,6 +430,10 @@ def run_ours(a):
     from trackingbench_slam_b200.synth import synth_stream
     rank, local_rank, world = env_rank()
     assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    # multi-GPU end-to-end runs are bound by pinned uploads: keep this rank (and the pinned pages it is about to allocate)
+    # on the CPUs next to its GPU (TB_BIND_NUMA=0 disables); the single-rank run keeps every core for the CPU baseline leg
+    from trackingbench_slam_b200.hostbind import bind_to_gpu
+    bound_cpus = bind_to_gpu(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
@@ -671,7 +675,8 @@ def run_ours(a):
                            'sharding': 'frame streams, %d rank(s), no collective' % world,
                            'l2': 'inputs (%.0f MB of frames per step) exceed the 126 MB L2' % (B * W * H / 1e6),
                            'mean_kpts_per_frame': float(counts.mean()), 'matches_per_step': n_matches, 'match_impl': a.match_impl,
-                           'e2e_pipeline': '%d chunk(s) per step x %d rotating slots; bound: PCIe upload of the frames' % (NCH, NSLOT)},
+                           'e2e_pipeline': '%d chunk(s) per step x %d rotating slots; bound: PCIe upload of the frames' % (NCH, NSLOT),
+                           'host_binding': ('rank 0 bound to %d CPUs local to its GPU' % len(bound_cpus)) if bound_cpus else 'none'},
                 'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'hamming': hamming,
                 'per_kernel_ms': {k: round(v['ms'], 3) for k, v in table.items()},
