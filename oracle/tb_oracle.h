@@ -12,11 +12,17 @@
  * against 3.3, the only OpenCV available here is cv2 4.13.0).
  *
  * PARITY PINNING: the reference's own tests hold no golden vectors (they are imshow demos), so
- * the oracle is pinned by (a) tests/test_oracle_cv2.py: every primitive bit-exact against cv2
- * 4.13.0 on images and random data; (b) tests/test_oracle_ref.py: the extractor restatement
- * bit-exact against oracle/_ref = the reference's own ORBextractor.cpp compiled unmodified here
- * (sort comparator pinned, see oracle/ref_build.cpp); (c) committed golden vectors in
- * tests/golden made by scripts/make_golden.py from (b).
+ * the oracle is pinned by (a) tests/test_oracle_cv2.py: every OpenCV primitive bit-exact against cv2
+ * 4.13.0 on images and random data (calcOpticalFlowPyrLK within a stated tolerance); (b) reference-run
+ * output: oracle/_ref = the reference's OWN sources compiled here from /root/reference —
+ * ORBextractor.cpp (libtb_ref.so, tests/test_oracle_golden.py), the vendored DBoW2 (libtb_ref_bow.so,
+ * tests/test_oracle_bow.py), and Frame.cpp / MapPoint.cpp / Map.cpp / CameraModel.cpp /
+ * FASTextractor.cpp unmodified plus matcher.cpp's hot-path member functions and LocalBA.cpp's
+ * block-commented stereo matcher by line range (libtb_ref_matcher.so, tests/test_oracle_ref_matcher.py);
+ * (c) committed golden vectors in tests/golden written from (b) by scripts/make_golden*.py.
+ * Deliberate pins, each stated in DESIGN.md section 7: the octree sort comparator, Eigen's 3-term
+ * reduction order, the Map's iteration order, and the FAST-10 detector of FASTExtractor (uzh-rpg/fast is
+ * absent from the reference tree: that detector alone is PARITY-UNPINNED).
  */
 #ifndef TB_ORACLE_H
 #define TB_ORACLE_H
