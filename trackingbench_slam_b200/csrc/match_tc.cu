@@ -13,10 +13,15 @@
 //    pre-expanded descriptors (256 B per row) from global memory with cp.async.bulk and was bound by that 8x L2 -> shared
 //    traffic (every CTA streams its whole train frame).
 //  * hamming_i8mma: one CTA = 128 (kNN-2) or 256 (frame pairs) query rows.  Warp 0 owns the TMEM allocation, warp 1 =
-//    tcgen05.mma issuer (kind::i8, M=128, N=TN, 8 K-steps of 32), accumulators in TMEM (2 stages x MB blocks x TN columns =
-//    512), warps 2-9 = epilogue: tcgen05.ld 32 columns at a time, running (max dot, arg) per row in registers, warps 10-13 =
-//    expanders (A operand once, then the ring of train tiles).  mbarriers connect the roles; tcgen05.commit frees the
-//    shared-memory stage and publishes the accumulator.
+//    tcgen05.mma issuer (kind::i8, M=128, N=TN, 9 K-steps of 32), accumulators in TMEM (2 stages x MB blocks x TN columns),
+//    warps 2-9 = epilogue: tcgen05.ld 32 columns at a time, running (max dot, arg) per row in registers, warps 10-13 =
+//    expanders (the ring of train tiles).  mbarriers connect the roles; tcgen05.commit frees the shared-memory stage and
+//    publishes the accumulator.
+//  * The query block (the A operand) lives in TENSOR MEMORY for the whole CTA: the epilogue warps expand their own query
+//    row once (lane = row, 72 columns = 288 int8) and write it with tcgen05.st; the MMAs then read A from TMEM
+//    (tcgen05.mma [d], [a], b-desc) and only the train tile from shared memory.  With both operands in shared memory an
+//    M128 x N128 x K32 step reads 8 KB per 64 tensor cycles = the whole 128 B/clk of the shared-memory pipe, which the
+//    expanders' stores and table look-ups share (ncu: pipe 90 % busy, tensor pipe 58 %); with A in TMEM it reads half.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -27,10 +32,13 @@
 #define TC_KB 288         // bytes (= int8 elements) per expanded row: 256 descriptor bits + one more K step of 32 that carries the
                           // tie-break key (see below)
 #define TC_SBO (TC_KB / 16 * 128)   // canonical layout: distance between 8-row groups
-#define TC_THREADS 448    // warp 0 TMEM allocation, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter), warps 10..13 expanders
+#define TC_THREADS 640    // warps 0..3 MMA issuers (warp 0 also owns the TMEM allocation), warps 4..11 epilogue (two per TMEM lane quarter), warps 12..19 expanders (two groups of 4: even / odd tiles)
 #define TC_EXP_THREADS 128
-#define TC_EXP_WARP0 10
+#define TC_EXP_WARP0 12
+#define TC_EPI_WARP0 4
 #define TC_LUT_BYTES (256 * 16 * 8)   // byte -> 8 x int8 table, 16 replicas (one per lane of a half warp: conflict-free LDS.64)
+#define TC_ACOLS (TC_KB / 4)          // TMEM columns of one expanded query block (A operand): 4 int8 per 32-bit cell
+#define TC_NSB_MAX 6
 
 // The key of the arg-max is produced by the tensor core itself.  Query rows are expanded to +-32 and carry a 1 in element
 // 256; train row j is expanded to +-1 and carries 31 - j%32 in element 256 (elements 257..287 are zero).  The accumulator is
@@ -61,25 +69,27 @@ __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4
     *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(31u - (uint32_t)(r & 31), 0, 0, 0);   // element 256: tie-break key (tiles start at multiples of 32)
     *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
 }
-// query rows (once per CTA): +-32 and a 1 in element 256
-__device__ __forceinline__ void expand_row_query(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid)
+// one half of a train row (tiles of 64 rows: two expander threads per row): half 0 = descriptor bytes 0..15 (chunks 0..7)
+// and the key chunk 16, half 1 = bytes 16..31 (chunks 8..15) and the zero chunk 17
+__device__ __forceinline__ void expand_half_lut(uint8_t *tile, int r, int half, const uint4 d, bool valid, const uint2 *lut)
 {
-    uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
-    const uint32_t w32[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint8_t *row = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
+    uint8_t *o = row + (size_t)half * 8 * 128, *ox = row + (size_t)(16 + half) * 128;
+    if (!valid) {
 #pragma unroll
-    for (int c = 0; c < 16; c++) {
-        const uint32_t bits = (w32[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t nib = (bits >> (4 * k)) & 0xF;
-            const uint32_t b = (nib * 0x00204081u) & 0x01010101u;   // bit i -> byte i
-            w[k] = valid ? 0x20202020u + 0xC0u * b : 0u;              // per byte: 0 -> 0x20 (+32), 1 -> 0xE0 (-32); no carries
-        }
-        *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(ox) = make_uint4(0, 0, 0, 0);
+        return;
     }
-    *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(valid ? 1u : 0u, 0, 0, 0);
-    *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
+    const uint32_t w32[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t x = w32[w];
+        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
+    }
+    *reinterpret_cast<uint4 *>(ox) = make_uint4(half == 0 ? 31u - (uint32_t)(r & 31) : 0u, 0, 0, 0);   // element 256: tie-break key
 }
 
 // ---- PTX helpers
@@ -130,13 +140,31 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// one thread of the (converged) warp, chosen by the hardware: unlike `lane == 0`, ptxas knows that the guarded region runs
+// in a single thread and keeps the tcgen05 operands in uniform registers without a per-instruction election loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// A operand from tensor memory (lane = row, 4 int8 per 32-bit column), B from shared memory
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 struct __align__(16) TcShared {
-    uint64_t fullA, full[3], empty[3], tfull[2], tempty[2];
+    uint64_t fullA, full[TC_NSB_MAX], empty[TC_NSB_MAX], tfull[2][TC_MB_MAX], tempty[2][TC_MB_MAX];   // [TMEM stage][M block]
     uint32_t tmem_base;
     int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // MB = 1: partial results of the upper-half-column warps
 };
 
-#define TC_SMEM_BYTES (180 * 1024 + TC_LUT_BYTES + sizeof(TcShared) + 64)   // MB = 1: A 36 KB + B 2 x 72 KB; MB = 2: A 72 KB + B 3 x 36 KB; + table
+#define TC_SMEM_BYTES (144 * 1024 + TC_LUT_BYTES + sizeof(TcShared) + 64)   // train ring: MB = 1: 4 x 36 KB; MB = 2: 6 x 18 KB; + table
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
 template <bool SECOND, int MB>
@@ -146,27 +174,59 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
 {
     const PairDesc pd = pairs[blockIdx.y];
     constexpr int TC_ROWS = TC_M * MB;
-    constexpr int TN = MB == 1 ? 256 : 128;            // train rows per tile: TMEM holds 2 stages x MB blocks x TN = 512 columns
+    constexpr int TN = MB == 1 ? 128 : 64;             // train rows per tile
     constexpr int TB_BYTES = TN * TC_KB;
-    constexpr int NSB = MB == 1 ? 2 : 3;               // shared-memory stages of the train ring (the expanders run ahead of the MMAs)
+    constexpr int NSB = MB == 1 ? 4 : 6;               // shared-memory stages of the train ring (the expanders run ahead of the MMAs)
+    constexpr int DCOLS = 2 * MB * TN;                 // TMEM: accumulators = 2 stages x MB blocks x TN columns, then MB query blocks
+    constexpr int PARTS = TC_EXP_THREADS / TN;         // expander threads per train row (1 or 2)
+    static_assert(DCOLS + MB * TC_ACOLS <= 512 && NSB <= TC_NSB_MAX && NSB * TB_BYTES <= 144 * 1024, "TMEM / shared-memory budget");
     const int q0 = blockIdx.x * TC_ROWS;
     if (q0 >= pd.nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *sA = tc_smem;                                  // MB x 32 KB
-    uint8_t *sB = tc_smem + TC_ROWS * TC_KB;                // NSB stages of TN rows
-    uint2 *lut = reinterpret_cast<uint2 *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES);
-    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + TC_ROWS * TC_KB + NSB * TB_BYTES + TC_LUT_BYTES);
+    uint8_t *sB = tc_smem;                                  // NSB stages of TN rows
+    uint2 *lut = reinterpret_cast<uint2 *>(tc_smem + NSB * TB_BYTES);
+    TcShared *S = reinterpret_cast<TcShared *>(tc_smem + NSB * TB_BYTES + TC_LUT_BYTES);
     const int NT = (pd.nt + TN - 1) / TN;
 
     if (threadIdx.x == 0) {
-        mbar_init(&S->fullA, TC_EXP_THREADS);
-        for (int s = 0; s < 3; s++) { mbar_init(&S->full[s], TC_EXP_THREADS); mbar_init(&S->empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&S->tfull[s], 1); mbar_init(&S->tempty[s], 8); }
+        mbar_init(&S->fullA, 8);
+        for (int s = 0; s < NSB; s++) { mbar_init(&S->full[s], TC_EXP_THREADS); mbar_init(&S->empty[s], MB); }   // one commit per issuer
+        for (int s = 0; s < 2; s++)
+            for (int b = 0; b < MB; b++) { mbar_init(&S->tfull[s][b], 1); mbar_init(&S->tempty[s][b], 8 / MB); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: 512 columns = 2 stages x MB blocks of 128 x TN int32 accumulators
+    if (warp == 0) {   // TMEM: 512 columns (accumulators + the query blocks)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // global loads that the roles need first are issued before the prologue's barrier (table build, TMEM allocation):
+    // expanders: the descriptors of the first TC_PF train tiles; epilogue warps: their query row
+    constexpr int TC_PF = 3;   // train tiles in flight in registers: one L2 round trip (~700 clk) is longer than a tile's MMAs
+    const int eg = (warp - TC_EXP_WARP0) >> 2;            // expander group: tiles t = eg mod 2 (a tile's LDS -> STS chains leave the
+                                                          // warp waiting most of the time; two groups keep two tiles in the works)
+    const int et = threadIdx.x - 32 * TC_EXP_WARP0 - eg * TC_EXP_THREADS;
+    const int r = et & (TN - 1), part = et / TN;          // PARTS = 2: two expander threads share a row (16 descriptor bytes each)
+    const uint4 *tq = reinterpret_cast<const uint4 *>(pd.t);
+    uint4 lo[TC_PF], hi[TC_PF];
+#pragma unroll
+    for (int i = 0; i < TC_PF; i++) lo[i] = hi[i] = make_uint4(0, 0, 0, 0);
+    auto fetch = [&](int t, uint4 &l, uint4 &h) {
+        const int row = t * TN + r;
+        if (t < NT && row < pd.nt) {
+            if (PARTS == 1) { l = __ldg(tq + 2 * (size_t)row); h = __ldg(tq + 2 * (size_t)row + 1); }
+            else l = __ldg(tq + 2 * (size_t)row + part);
+        }
+    };
+    const int e_lane_base = 32 * (warp & 3), e_grp = (warp - TC_EPI_WARP0) >> 2, e_mb = MB > 1 ? e_grp : 0;
+    const int e_row = q0 + e_mb * TC_M + e_lane_base + lane;
+    uint4 dlo = make_uint4(0, 0, 0, 0), dhi = dlo;
+    if (warp >= TC_EXP_WARP0) {
+#pragma unroll
+        for (int i = 0; i < TC_PF; i++) fetch(eg + 2 * i, lo[i], hi[i]);
+    } else if (warp >= TC_EPI_WARP0 && e_row < pd.nq) {
+        const uint4 *qq = reinterpret_cast<const uint4 *>(pd.q) + 2 * (size_t)e_row;
+        if (MB > 1 || e_grp == 0) dlo = __ldg(qq);       // MB = 1: the two warps of a lane quarter split the row
+        if (MB > 1 || e_grp == 1) dhi = __ldg(qq + 1);
     }
     for (int i = threadIdx.x; i < 256 * 16; i += TC_THREADS) {   // byte e -> eight +-1 bytes, replica i % 16
         const uint32_t e = (uint32_t)i >> 4;
@@ -181,97 +241,118 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
 
     if (warp >= TC_EXP_WARP0) {
         // ---- expanders: packed descriptors (global, read-only path) -> +-1 int8 rows in shared memory
-        const int et = threadIdx.x - 32 * TC_EXP_WARP0;
-        constexpr int RPT = TN / TC_EXP_THREADS;              // train rows per expander thread and tile
-        const uint4 *tq = reinterpret_cast<const uint4 *>(pd.t);
-        uint4 lo[RPT], hi[RPT];
-        auto fetch = [&](int t) {
-#pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                const int row = t * TN + et + j * TC_EXP_THREADS;
-                if (row < pd.nt) { lo[j] = __ldg(tq + 2 * (size_t)row); hi[j] = __ldg(tq + 2 * (size_t)row + 1); }
-            }
-        };
-        if (NT > 0) fetch(0);
-        {
-            const uint4 *qq = reinterpret_cast<const uint4 *>(pd.q);
 #pragma unroll 1
-            for (int r = et; r < TC_ROWS; r += TC_EXP_THREADS) {
-                const int row = q0 + r;
-                const bool valid = row < pd.nq;
-                uint4 a = make_uint4(0, 0, 0, 0), b = a;
-                if (valid) { a = __ldg(qq + 2 * (size_t)row); b = __ldg(qq + 2 * (size_t)row + 1); }
-                expand_row_query(sA, r, a, b, valid);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
-            mbar_arrive(&S->fullA);
-        }
-#pragma unroll 1
-        for (int t = 0; t < NT; t++) {
+        for (int t = eg; t < NT; t += 2) {
             const int s = t % NSB, ph = (t / NSB) & 1;
             mbar_wait(&S->empty[s], ph ^ 1);
             uint8_t *tile = sB + s * TB_BYTES;
+            if (PARTS == 1) expand_row_lut(tile, r, lo[0], hi[0], t * TN + r < pd.nt, lut + (lane & 15));
+            else expand_half_lut(tile, r, part, lo[0], t * TN + r < pd.nt, lut + (lane & 15));
 #pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                const int r = et + j * TC_EXP_THREADS;
-                expand_row_lut(tile, r, lo[j], hi[j], t * TN + r < pd.nt, lut + (lane & 15));
-            }
-            if (t + 1 < NT) fetch(t + 1);                     // in flight while the other roles consume this tile
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int i = 0; i + 1 < TC_PF; i++) { lo[i] = lo[i + 1]; hi[i] = hi[i + 1]; }
+            fetch(t + 2 * TC_PF, lo[TC_PF - 1], hi[TC_PF - 1]);   // in flight while the next tiles are expanded
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
             mbar_arrive(&S->full[s]);
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer: idesc = D s32 | A s8 | B s8 | K-major both | N=256 | M=128
+    } else if (warp < 2 * MB) {
+        if (elect_one()) {
+            // ---- MMA issuers.  A single thread gets a tcgen05.mma out every ~120 cycles (ncu: the issuing warp never waits
+            //      on a barrier; every instruction needs ~9 dependent uniform-datapath instructions of set-up), while an
+            //      M128 x N x K32 int8 step runs N/2 cycles on the tensor pipe.  So the tiles are dealt to 2 * MB issuing
+            //      threads: thread (block mbi, parity par) issues the nine K steps of block mbi for the tiles t = par mod 2
+            //      into TMEM stage par; accumulators of different threads are disjoint, so no ordering between them is needed.
+            // idesc = D s32 | A s8 | B s8 | K-major both | N = TN | M = 128
+            const int mbi = warp % MB, par = warp / MB;
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             mbar_wait(&S->fullA, 0);
-            const uint64_t adesc0 = make_desc(smem_u32(sA)), adesc1 = make_desc(smem_u32(sA + TC_M * TC_KB));
-            for (int t = 0; t < NT; t++) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int t = par; t < NT; t += 2) {
                 const int s = t % NSB, ph = (t / NSB) & 1;      // shared-memory stage
-                const int ts = t & 1, tph = (t >> 1) & 1;       // TMEM stage
+                const int tph = (t >> 1) & 1;                   // phase of TMEM stage par
                 mbar_wait(&S->full[s], ph);
-                mbar_wait(&S->tempty[ts], tph ^ 1);
+                mbar_wait(&S->tempty[par][mbi], tph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t bdesc = make_desc(smem_u32(sB + s * TB_BYTES));
 #pragma unroll
-                for (int k = 0; k < TC_KB / 32; k++)   // K step = 32 bytes = two 16-byte core-matrix columns = 256 B in this layout
-                    mma_i8(tmem + (ts * MB + 0) * TN, adesc0 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
-                if (MB > 1)
-#pragma unroll
-                for (int k = 0; k < TC_KB / 32; k++)
-                    mma_i8(tmem + (ts * MB + 1) * TN, adesc1 + (uint64_t)((k * 256) >> 4), bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
-                tc_commit(&S->empty[s]);    // shared-memory stage reusable once these MMAs retire
-                tc_commit(&S->tfull[ts]);   // accumulator ready for the epilogue
+                for (int k = 0; k < TC_KB / 32; k++)   // K step = 32 int8 = 8 TMEM columns of A = two 16-byte core-matrix columns (256 B) of B
+                    mma_i8_ts(tmem + (uint32_t)((par * MB + mbi) * TN), tmem + (uint32_t)(DCOLS + mbi * TC_ACOLS + 8 * k),
+                              bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                tc_commit(&S->empty[s]);          // shared-memory stage reusable once the MMAs of every block retire
+                tc_commit(&S->tfull[par][mbi]);   // accumulator ready for the epilogue
             }
         }
-    } else if (warp >= 2) {
-        // ---- epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; warps 2..5 own the query rows of M block 0,
-        //      warps 6..9 those of M block 1 — one thread per query row, all columns
+    } else if (warp >= TC_EPI_WARP0) {
+        // ---- epilogue warps 4..11: TMEM lanes 32*(warp%4) .. +31; warps 4..7 own the query rows of M block 0,
+        //      warps 8..11 those of M block 1 — one thread per query row, all columns
         // (MB = 1: both warps of a lane quarter share the rows and split every tile's columns; merged at the end)
         const int lane_base = 32 * (warp & 3);
-        const int grp = (warp - 2) >> 2;
+        const int grp = (warp - TC_EPI_WARP0) >> 2;
         const int mb = MB > 1 ? grp : 0;
-        const int cbeg = MB > 1 ? 0 : grp * (TN / 2), cend = MB > 1 ? TN : cbeg + TN / 2;
+        {
+            // A operand: this thread's query row, +-32 with a 1 in element 256, into TMEM lane lane_base + lane.  Eight
+            // columns (= 32 K elements = one 32-bit word of the descriptor) per tcgen05.st; group 8 carries the key element.
+            const int row = q0 + mb * TC_M + lane_base + lane;
+            const bool valid = row < pd.nq;
+            const bool first_half = MB > 1 || grp == 0, second_half = MB > 1 || grp == 1;   // (dlo, dhi were fetched in the prologue)
+            auto put = [&](int g, uint32_t bits, bool key) {
+                uint32_t w[8];
+                if (!key) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t b = (((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;   // bit i -> byte i
+                        w[k] = valid ? 0x20202020u + 0xC0u * b : 0u;                                     // 0 -> +32, 1 -> -32; no carries
+                    }
+                } else {
+                    w[0] = valid ? 1u : 0u;
+#pragma unroll
+                    for (int k = 1; k < 8; k++) w[k] = 0u;
+                }
+                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(DCOLS + mb * TC_ACOLS + 8 * g);
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            };
+            if (first_half) { put(0, dlo.x, false); put(1, dlo.y, false); put(2, dlo.z, false); put(3, dlo.w, false); }
+            if (second_half) { put(4, dhi.x, false); put(5, dhi.y, false); put(6, dhi.z, false); put(7, dhi.w, false); put(8, 0u, true); }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->fullA);
+        }
+        const int cbeg = MB > 1 ? 0 : grp * (TN / 2);   // 64 columns per warp and tile either way
+        static_assert((MB > 1 ? TN : TN / 2) == 64, "the epilogue reads 64 columns per warp and tile");
         for (int t = 0; t < NT; t++) {
             const int s = t & 1, ph = (t >> 1) & 1;
-            mbar_wait(&S->tfull[s], ph);
+            mbar_wait(&S->tfull[s][mb], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int col0 = t * TN;
-#pragma unroll 1
-            for (int c = cbeg; c < cend; c += 32) {
-                if (col0 + c >= pd.nt) break;   // warp-uniform
-                uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)((s * MB + mb) * TN + c);
+            // the warp's 64 columns of this tile with one tcgen05.ld (a load + wait per 32 columns cost ~85 cycles each)
+            uint32_t vv[64];
+            {
+                const uint32_t taddr = tmem + ((uint32_t)lane_base << 16) + (uint32_t)((s * MB + mb) * TN + cbeg);
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                    "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                    "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                    : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]),
+                      "=r"(vv[8]), "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15]),
+                      "=r"(vv[16]), "=r"(vv[17]), "=r"(vv[18]), "=r"(vv[19]), "=r"(vv[20]), "=r"(vv[21]), "=r"(vv[22]), "=r"(vv[23]),
+                      "=r"(vv[24]), "=r"(vv[25]), "=r"(vv[26]), "=r"(vv[27]), "=r"(vv[28]), "=r"(vv[29]), "=r"(vv[30]), "=r"(vv[31]),
+                      "=r"(vv[32]), "=r"(vv[33]), "=r"(vv[34]), "=r"(vv[35]), "=r"(vv[36]), "=r"(vv[37]), "=r"(vv[38]), "=r"(vv[39]),
+                      "=r"(vv[40]), "=r"(vv[41]), "=r"(vv[42]), "=r"(vv[43]), "=r"(vv[44]), "=r"(vv[45]), "=r"(vv[46]), "=r"(vv[47]),
+                      "=r"(vv[48]), "=r"(vv[49]), "=r"(vv[50]), "=r"(vv[51]), "=r"(vv[52]), "=r"(vv[53]), "=r"(vv[54]), "=r"(vv[55]),
+                      "=r"(vv[56]), "=r"(vv[57]), "=r"(vv[58]), "=r"(vv[59]), "=r"(vv[60]), "=r"(vv[61]), "=r"(vv[62]), "=r"(vv[63])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int c = cbeg + 32 * h;
+                if (col0 + c >= pd.nt) break;   // warp-uniform
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = vv[32 * h + j];
                 const int lim = pd.nt - (col0 + c);   // valid columns in this chunk
                 if (!SECOND && lim >= 32) {
                     // best-only, full chunk: the accumulators already are keys (dot * 32 + 31 - j: larger key = larger dot,
@@ -289,8 +370,21 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                     continue;
                 }
                 if (SECOND && lim >= 32) {
-                    // best + second, full chunk: same keys, reduced by a tree of (largest, second largest) pairs —
-                    // 2 ops per leaf pair, 3 per merge (max, min, max3): ~2.4 ALU instructions per element instead of ~6
+                    // best + second, full chunk.  First the chunk maximum alone (max3 tree, ~0.4 instructions per element): a
+                    // chunk whose largest dot does not exceed the row's running second best changes nothing, and after the
+                    // first few hundred columns that is almost every chunk (the running second is a record statistic), so
+                    // the pair tree below only runs when some row of the warp needs it.
+                    {
+                        int k[11];
+#pragma unroll
+                        for (int j = 0; j < 30; j += 3) k[j / 3] = __vimax3_s32((int)v[j], (int)v[j + 1], (int)v[j + 2]);
+                        k[10] = max((int)v[30], (int)v[31]);
+                        const int a0 = __vimax3_s32(k[0], k[1], k[2]), a1 = __vimax3_s32(k[3], k[4], k[5]), a2 = __vimax3_s32(k[6], k[7], k[8]);
+                        const int ck = max(__vimax3_s32(a0, a1, a2), max(k[9], k[10]));
+                        if (!__any_sync(0xffffffffu, (ck >> 5) > second)) continue;
+                    }
+                    // same keys, reduced by a tree of (largest, second largest) pairs — 2 ops per leaf pair, 3 per merge
+                    // (max, min, max3): ~2.4 ALU instructions per element instead of ~6
                     int hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
@@ -326,7 +420,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S->tempty[s]);
+            if (lane == 0) mbar_arrive(&S->tempty[s][mb]);
         }
         if (MB == 1 && grp == 1) { S->part_best[lane_base + lane] = best; S->part_second[lane_base + lane] = second; S->part_idx[lane_base + lane] = bidx; }
         if (MB > 1) {
@@ -342,7 +436,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
-    if (MB == 1 && warp >= 2 && warp < 6) {
+    if (MB == 1 && warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
         // merge the two column halves (lowest index wins ties) and write the row's result
         const int r = 32 * (warp & 3) + lane, row = q0 + r;
         const int b1 = S->part_best[r], s1 = S->part_second[r], i1 = S->part_idx[r];
