@@ -53,9 +53,9 @@
 __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid, const uint2 *lut)
 {
     uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
-    if (!valid) {
+    if (!valid) {   // rows past the train set: never read back (the epilogue masks their columns); keep the tile defined
 #pragma unroll
-        for (int c = 0; c < 18; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 16; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
         return;
     }
     const uint32_t w32[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -66,19 +66,24 @@ __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4
         *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
-    *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(31u - (uint32_t)(r & 31), 0, 0, 0);   // element 256: tie-break key (tiles start at multiples of 32)
-    *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
 }
-// one half of a train row (tiles of 64 rows: two expander threads per row): half 0 = descriptor bytes 0..15 (chunks 0..7)
-// and the key chunk 16, half 1 = bytes 16..31 (chunks 8..15) and the zero chunk 17
+// chunks 16 and 17 of row r (element 256 = tie-break key 31 - r % 32, elements 257..287 = 0) do not depend on the tile (tiles
+// start at multiples of 32 rows): written once per ring stage when the CTA starts
+__device__ __forceinline__ void write_key_chunks(uint8_t *tile, int r, bool key, bool zero)
+{
+    uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
+    if (key) *reinterpret_cast<uint4 *>(o + 16 * 128) = make_uint4(31u - (uint32_t)(r & 31), 0, 0, 0);
+    if (zero) *reinterpret_cast<uint4 *>(o + 17 * 128) = make_uint4(0, 0, 0, 0);
+}
+// one half of a train row (tiles of 64 rows: two expander threads per row): half 0 = descriptor bytes 0..15 (chunks 0..7),
+// half 1 = bytes 16..31 (chunks 8..15)
 __device__ __forceinline__ void expand_half_lut(uint8_t *tile, int r, int half, const uint4 d, bool valid, const uint2 *lut)
 {
     uint8_t *row = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
-    uint8_t *o = row + (size_t)half * 8 * 128, *ox = row + (size_t)(16 + half) * 128;
+    uint8_t *o = row + (size_t)half * 8 * 128;
     if (!valid) {
 #pragma unroll
         for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(ox) = make_uint4(0, 0, 0, 0);
         return;
     }
     const uint32_t w32[4] = {d.x, d.y, d.z, d.w};
@@ -89,7 +94,6 @@ __device__ __forceinline__ void expand_half_lut(uint8_t *tile, int r, int half, 
         *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
-    *reinterpret_cast<uint4 *>(ox) = make_uint4(half == 0 ? 31u - (uint32_t)(r & 31) : 0u, 0, 0, 0);   // element 256: tie-break key
 }
 
 // ---- PTX helpers
@@ -192,7 +196,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
         mbar_init(&S->fullA, 8);
         for (int s = 0; s < NSB; s++) { mbar_init(&S->full[s], TC_EXP_THREADS); mbar_init(&S->empty[s], MB); }   // one commit per issuer
         for (int s = 0; s < 2; s++)
-            for (int b = 0; b < MB; b++) { mbar_init(&S->tfull[s][b], 1); mbar_init(&S->tempty[s][b], 8 / MB); }
+            for (int b = 0; b < MB; b++) { mbar_init(&S->tfull[s][b], 1); mbar_init(&S->tempty[s][b], 4); }   // the four epilogue warps that read this accumulator
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {   // TMEM: 512 columns (accumulators + the query blocks)
@@ -241,6 +245,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
 
     if (warp >= TC_EXP_WARP0) {
         // ---- expanders: packed descriptors (global, read-only path) -> +-1 int8 rows in shared memory
+        for (int s = 0; s < NSB; s++) write_key_chunks(sB + s * TB_BYTES, r, PARTS == 1 || part == 0, PARTS == 1 || part == 1);
 #pragma unroll 1
         for (int t = eg; t < NT; t += 2) {
             const int s = t % NSB, ph = (t / NSB) & 1;
@@ -318,13 +323,17 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->fullA);
         }
-        const int cbeg = MB > 1 ? 0 : grp * (TN / 2);   // 64 columns per warp and tile either way
-        static_assert((MB > 1 ? TN : TN / 2) == 64, "the epilogue reads 64 columns per warp and tile");
-        for (int t = 0; t < NT; t++) {
+        // MB = 2: the four warps of block mb read every tile (64 columns); MB = 1: the two warp groups alternate tiles (group =
+        // TMEM stage) and read all 128 columns as two loads.  An accumulator is released as soon as it sits in registers.
+        for (int t = (MB == 1 ? grp : 0); t < NT; t += (MB == 1 ? 2 : 1)) {
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&S->tfull[s][mb], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int col0 = t * TN;
+            const int nh = (MB == 1 && col0 + 64 < pd.nt) ? 2 : 1;
+#pragma unroll 1
+            for (int half = 0; half < nh; half++) {
+            const int cbeg = 64 * half;
             // the warp's 64 columns of this tile with one tcgen05.ld (a load + wait per 32 columns cost ~85 cycles each)
             uint32_t vv[64];
             {
@@ -345,6 +354,11 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                       "=r"(vv[56]), "=r"(vv[57]), "=r"(vv[58]), "=r"(vv[59]), "=r"(vv[60]), "=r"(vv[61]), "=r"(vv[62]), "=r"(vv[63])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            if (half == nh - 1) {   // the values are in registers: the issuer may overwrite this accumulator
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S->tempty[s][mb]);
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -418,9 +432,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
                     }
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S->tempty[s][mb]);
+            }
         }
         if (MB == 1 && grp == 1) { S->part_best[lane_base + lane] = best; S->part_second[lane_base + lane] = second; S->part_idx[lane_base + lane] = bidx; }
         if (MB > 1) {
