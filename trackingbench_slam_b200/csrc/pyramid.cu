@@ -136,6 +136,20 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 #define PYR_BOXW 192
 #define PYR_FPC 8
 #define PYR_STAGES 3   // source boxes in flight (the register file limits the kernel to 3 CTAs/SM, shared memory has room)
+// hi32(a * b) + c
+__device__ __forceinline__ uint32_t pyr_madhi(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// lo | hi << 16 as a multiply-add (FMA pipe)
+__device__ __forceinline__ uint32_t pyr_pack16(uint32_t lo, uint32_t hi)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
 __device__ __forceinline__ uint32_t pyr_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pyr_tma_box(void *dst, const CUtensorMap *tm, int x, int y, int z, uint64_t *bar)
 {
@@ -181,7 +195,7 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
     // a*c0 + b*c1 = DP4A(pair, lo bytes) + 256 * DP4A(pair, hi bytes): shared memory sees 3 word loads instead of 8 byte
     // loads per row (the LSU data path, not the issue rate, bounds this kernel).
     int woff[3];               // stage offsets of the three words
-    uint32_t sel[4], clo[4], chi[4];
+    uint32_t sel01, sel23, cp[4];   // PRMT selectors for the tap pairs of columns (0,1) and (2,3); weights c0 | c1 << 16
     int wsh;
     {
         int4 xt[4];
@@ -194,13 +208,14 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
             const int x = min(4 * ((o_first >> 2) + j), 2 * PYR_BOXW - 4);
             woff[j] = x < PYR_BOXW ? x : box_bytes + x - PYR_BOXW;
         }
+        uint32_t ia[4], ib[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint32_t ia = (uint32_t)(xt[k].x - sx_lo - o_first), ib = (uint32_t)(xt[k].y - sx_lo - o_first);
-            sel[k] = ia | (ib << 4) | (ia << 8) | (ib << 12);
-            clo[k] = ((uint32_t)xt[k].z & 0xFF) | (((uint32_t)xt[k].w & 0xFF) << 8);
-            chi[k] = ((uint32_t)xt[k].z >> 8) | (((uint32_t)xt[k].w >> 8) << 8);
+            ia[k] = (uint32_t)(xt[k].x - sx_lo - o_first); ib[k] = (uint32_t)(xt[k].y - sx_lo - o_first);
+            cp[k] = ((uint32_t)xt[k].z & 0xFFFF) | ((uint32_t)xt[k].w << 16);
         }
+        sel01 = ia[0] | (ib[0] << 4) | (ia[1] << 8) | (ib[1] << 12);
+        sel23 = ia[2] | (ib[2] << 4) | (ia[3] << 8) | (ib[3] << 12);
     }
     // this thread's output rows (phase 2): table entries once per CTA
     const int dx0 = tx0 + cx;
@@ -222,13 +237,11 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
             const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + woff[0]), w1 = *reinterpret_cast<const uint32_t *>(row + woff[1]),
                            w2 = *reinterpret_cast<const uint32_t *>(row + woff[2]);
             const uint32_t lo = __funnelshift_r(w0, w1, wsh), hi = __funnelshift_r(w1, w2, wsh);
-            uint32_t h[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t pair = __byte_perm(lo, hi, sel[k]);            // (a, b, a, b)
-                h[k] = (__dp4a(pair, clo[k], 0u) + (__dp4a(pair, chi[k], 0u) << 8)) >> 4;
-            }
-            *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+            // a * c0 + b * c1 of one column is ONE dp2a (16-bit weights x 8-bit taps); a PRMT lines up the taps of two columns
+            const uint32_t p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);   // (a0, b0, a1, b1), (a2, b2, a3, b3)
+            const uint32_t h0 = __dp2a_lo(cp[0], p01, 0u) >> 4, h1 = __dp2a_hi(cp[1], p01, 0u) >> 4;
+            const uint32_t h2 = __dp2a_lo(cp[2], p23, 0u) >> 4, h3 = __dp2a_hi(cp[3], p23, 0u) >> 4;
+            *reinterpret_cast<uint2 *>(Hs + r * PYR_TW + cx) = make_uint2(pyr_pack16(h0, h1), pyr_pack16(h2, h3));
         }
         __syncthreads();                                   // H complete, stage s drained
         if (tid == 0 && f + PYR_STAGES < nf) {
@@ -246,12 +259,14 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
                 if (dy0 + kk > ty1) break;
                 const uint2 a = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] & 0xFFFF) * PYR_TW + cx);
                 const uint2 b = *reinterpret_cast<const uint2 *>(Hs + (yr[kk] >> 16) * PYR_TW + cx);
-                const int w0 = (int)(yc[kk] & 0xFFFF), w1 = (int)(yc[kk] >> 16);
-                const int h0[4] = {(int)(a.x & 0xFFFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16)};
-                const int h1[4] = {(int)(b.x & 0xFFFF), (int)(b.x >> 16), (int)(b.y & 0xFFFF), (int)(b.y >> 16)};
+                // (w * h) >> 16 = high word of (w << 16) * h: one multiply-high per tap on the FMA pipe (the kernel is bound by
+                // the integer ALU pipe), the second one adds the first and the rounding constant
+                const uint32_t W0 = yc[kk] << 16, W1 = yc[kk] & 0xFFFF0000u;
+                const uint32_t h0[4] = {a.x & 0xFFFFu, a.x >> 16, a.y & 0xFFFFu, a.y >> 16};
+                const uint32_t h1[4] = {b.x & 0xFFFFu, b.x >> 16, b.y & 0xFFFFu, b.y >> 16};
                 uint32_t v[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = (uint32_t)((((w0 * h0[k]) >> 16) + ((w1 * h1[k]) >> 16) + 2) >> 2);   // <= 255
+                for (int k = 0; k < 4; k++) v[k] = pyr_madhi(W1, h1[k], pyr_madhi(W0, h0[k], 2u)) >> 2;   // <= 255
                 const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
                 if (wordst) *reinterpret_cast<uint32_t *>(dp) = out;
                 else for (int k = 0; k < 4 && dx0 + k < dw; k++) dp[k] = (uint8_t)(out >> (8 * k));
