@@ -277,6 +277,128 @@ pyr_resize_linear_u8_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__re
     }
 }
 
+// ---- streaming variant (default): no H tile and no block barrier.  A thread owns 4 output columns x 8 output rows and walks
+// down its rows: the horizontal interpolation of a source row lives in 4 registers, the vertical taps of consecutive output
+// rows are (r, r+1) then (r+1, r+2) or (r+2, r+3), so the lower row of one output is reused as the upper row of the next and
+// every source row is interpolated once per 8-row group (1.2 rows per output row + one at the group's start).  Source boxes
+// arrive by TMA exactly as above; a stage is handed back through an mbarrier the eight warps arrive on, so the warps of a
+// CTA drift apart by up to PYR_STAGES frames instead of meeting at two barriers per frame.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+pyr_resize_linear_u8_stream(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, int dpitch, size_t dframe,
+                            int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames, int fpc)
+{
+    __shared__ alignas(8) uint64_t s_full[PYR_STAGES], s_empty[PYR_STAGES];
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+    const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
+    const int f0 = blockIdx.z * fpc, nf = min(n_frames, f0 + fpc) - f0;
+    const int box_bytes = (bh_max * PYR_BOXW + 127) & ~127;                       // one 192-wide box, 128-byte aligned
+    uint8_t *boxes = pyr_smem;                                                    // [PYR_STAGES][2 boxes][box_bytes]
+    const int sx_lo = __ldg(&xtab[tx0]).x & ~15;
+    const int sy_lo = __ldg(&ytab[ty0]).x;
+    auto fetch = [&](int s, int f) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
+        pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f, &s_full[s]);
+        pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < PYR_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_empty[s])), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < PYR_STAGES && s < nf; s++) fetch(s, f0 + s);
+    }
+    // this thread's 4 output columns: word offsets inside a stage, PRMT selectors of the tap pairs, weights c0 | c1 << 16
+    const int cx = threadIdx.x * 4;
+    int woff[3];
+    uint32_t sel01, sel23, cp[4];
+    int wsh;
+    {
+        int4 xt[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) xt[k] = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]);
+        const int o_first = xt[0].x - sx_lo;
+        wsh = 8 * (o_first & 3);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int x = min(4 * ((o_first >> 2) + j), 2 * PYR_BOXW - 4);
+            woff[j] = x < PYR_BOXW ? x : box_bytes + x - PYR_BOXW;
+        }
+        uint32_t ia[4], ib[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ia[k] = (uint32_t)(xt[k].x - sx_lo - o_first); ib[k] = (uint32_t)(xt[k].y - sx_lo - o_first);
+            cp[k] = ((uint32_t)xt[k].z & 0xFFFF) | ((uint32_t)xt[k].w << 16);
+        }
+        sel01 = ia[0] | (ib[0] << 4) | (ia[1] << 8) | (ib[1] << 12);
+        sel23 = ia[2] | (ib[2] << 4) | (ia[3] << 8) | (ib[3] << 12);
+    }
+    // this thread's output rows: source rows (relative to sy_lo, premultiplied by the box pitch) and weights, once per CTA
+    const int dx0 = tx0 + cx, dy0 = ty0 + threadIdx.y * (PYR_TH / 4);
+    // the tile's output rows: w0 (12 bits) | w1 << 12 | upper source row << 24 | (lower row = upper row + 1) << 31, once per CTA
+    __shared__ uint32_t s_yq[PYR_TH];
+    if (tid < PYR_TH) {
+        const int4 yt = __ldg(&ytab[min(ty0 + tid, dh - 1)]);
+        s_yq[tid] = ((uint32_t)yt.z & 0xFFF) | (((uint32_t)yt.w & 0xFFF) << 12) | ((uint32_t)(yt.x - sy_lo) << 24) | (yt.y != yt.x ? 0x80000000u : 0u);
+    }
+    const uint32_t *yq = s_yq + threadIdx.y * (PYR_TH / 4);
+    const bool active = dx0 <= tx1 && dy0 <= ty1;
+    __syncthreads();                                       // barriers initialised before anyone waits
+    for (int f = 0; f < nf; f++) {
+        const int s = f % PYR_STAGES;
+        const uint32_t ph = (uint32_t)((f / PYR_STAGES) & 1);
+        pyr_mbar_wait(&s_full[s], ph);
+        if (active) {
+            const uint8_t *stage = boxes + (size_t)(2 * s) * box_bytes;
+            // horizontal interpolation of source row r for the 4 columns: 3 word loads, a funnel shift to the first tap, one
+            // PRMT per column pair, one dp2a (16-bit weights x 8-bit taps) per column
+            auto hrow = [&](int r, uint32_t (&h)[4]) {
+                const uint8_t *row = stage + r * PYR_BOXW;
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + woff[0]), w1 = *reinterpret_cast<const uint32_t *>(row + woff[1]),
+                               w2 = *reinterpret_cast<const uint32_t *>(row + woff[2]);
+                const uint32_t lo = __funnelshift_r(w0, w1, wsh), hi = __funnelshift_r(w1, w2, wsh);
+                const uint32_t p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
+                h[0] = __dp2a_lo(cp[0], p01, 0u) >> 4; h[1] = __dp2a_hi(cp[1], p01, 0u) >> 4;
+                h[2] = __dp2a_lo(cp[2], p23, 0u) >> 4; h[3] = __dp2a_hi(cp[3], p23, 0u) >> 4;
+            };
+            uint8_t *dp = dst + (size_t)(f0 + f) * dframe + (size_t)dy0 * dpitch + dx0;   // advances by the pitch
+            // two row buffers; an output row needs source rows (r0, r1 = r0 or r0 + 1) and the next one starts at r1 or r1 + 1:
+            // the buffer that already holds r0 stays, the other one is refilled, and the WEIGHTS follow the buffers (the
+            // vertical blend is symmetric), so no register is copied
+            uint32_t hx[4], hy[4];
+            int rx = -1, ry = -1;                          // source rows held in hx / hy
+            const int nrows = min(PYR_TH / 4, ty1 - dy0 + 1);
+#pragma unroll 1
+            for (int kk = 0; kk < nrows; kk++) {
+                const uint32_t q = yq[kk];
+                const int r0 = (int)((q >> 24) & 0x7F), r1 = r0 + (int)(q >> 31);
+                const uint32_t W0 = (q & 0xFFFu) << 16, W1 = (q << 4) & 0x0FFF0000u;
+                uint32_t wx, wy;
+                if (ry == r0) { if (r1 != r0) { hrow(r1, hx); rx = r1; wx = W1; wy = W0; } else { wx = 0u; wy = W0 + W1; } }
+                else if (rx == r0) { if (r1 != r0) { hrow(r1, hy); ry = r1; wx = W0; wy = W1; } else { wx = W0 + W1; wy = 0u; } }
+                else { hrow(r0, hx); rx = r0; wx = W0; if (r1 != r0) { hrow(r1, hy); ry = r1; wy = W1; } else { wx = W0 + W1; wy = 0u; } }
+                // (w * h) >> 16 = high word of (w << 16) * h, one multiply-high per tap (FMA pipe)
+                uint32_t v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = (__umulhi(wx, hx[k]) + __umulhi(wy, hy[k]) + 2u) >> 2;   // <= 255
+                // the row pitch is a multiple of 64 bytes: a whole word fits even where fewer than 4 columns are inside the level
+                *reinterpret_cast<uint32_t *>(dp) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                dp += dpitch;
+            }
+        }
+        // hand the stage back: every warp arrives once; thread 0 refills it when all eight have
+        __syncwarp();
+        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pyr_s32(&s_empty[s])) : "memory");
+        if (tid == 0 && f + PYR_STAGES < nf) {
+            pyr_mbar_wait(&s_empty[s], ph);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fetch(s, f0 + f + PYR_STAGES);
+        }
+    }
+}
+
 // Host: shared-memory box (pitch, rows) needed by the worst tile of a level.
 void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
                    const std::vector<int32_t> &y1, int *bp, int *bh)
@@ -322,6 +444,16 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
     if (!area2 && tmap && use_tma && bp <= 2 * PYR_BOXW && bh <= 256) {
         const size_t box_bytes = ((size_t)bh * PYR_BOXW + 127) & ~(size_t)127;
         const size_t smem = 2 * PYR_STAGES * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
+        static const bool use_stream = !(getenv("TB_PYR_STREAM") && atoi(getenv("TB_PYR_STREAM")) == 0);   // A/B knob: 0 = H tile + barriers
+        if (use_stream) {
+            static const int fpc = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;   // frames per CTA (tuning knob)
+            dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, fpc)), block(64, 4);
+            static const int occ = getenv("TB_PYR_OCC") ? atoi(getenv("TB_PYR_OCC")) : 4;   // resident CTAs per SM the register budget allows (tuning knob)
+            if (occ >= 4) pyr_resize_linear_u8_stream<4><<<grid, block, 2 * PYR_STAGES * box_bytes, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+            else pyr_resize_linear_u8_stream<3><<<grid, block, 2 * PYR_STAGES * box_bytes, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+            TB_LAUNCH_CHECK(ctx);
+            return TB_OK;
+        }
         if (smem <= 200 * 1024) {
             static const int fpc = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;   // frames per CTA (tuning knob)
             dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, fpc)), block(64, 4);
@@ -347,6 +479,8 @@ void tb_pyramid_init_device()
 {
     cudaFuncSetAttribute(pyr_resize_linear_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(pyr_resize_linear_u8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pyr_resize_linear_u8_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pyr_resize_linear_u8_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 // tensor map over a level's frames for the TMA resize (box = PYR_BOXW x box_rows); false if the layout does not qualify
 bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows)
