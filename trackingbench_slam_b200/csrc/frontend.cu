@@ -145,6 +145,7 @@ struct tb_frontend {
     int box_pitch[TB_MAX_LEVELS] = {}, box_rows[TB_MAX_LEVELS] = {};   // K1 shared-memory source box
     CUtensorMap pyr_tmap[TB_MAX_LEVELS];                               // K1 TMA: tensor map over level l-1 (source of level l)
     bool has_tmap[TB_MAX_LEVELS] = {};
+    bool span8[TB_MAX_LEVELS] = {};                                    // K1: the 8-columns-per-thread kernel applies
     uint32_t *cand[TB_MAX_LEVELS] = {}, *kept[TB_MAX_LEVELS] = {};
     uint16_t *nid[TB_MAX_LEVELS] = {};
     int *n_cand = nullptr, *n_kept = nullptr, *n_kp = nullptr, *overflow = nullptr;
@@ -245,6 +246,7 @@ extern "C" int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *lw, 
             if ((rc = dev_alloc(fe, &fe->ytab[l], hy.size()))) break;
             cudaMemcpy(fe->xtab[l], hx.data(), hx.size() * sizeof(int4), cudaMemcpyHostToDevice);
             cudaMemcpy(fe->ytab[l], hy.data(), hy.size() * sizeof(int4), cudaMemcpyHostToDevice);
+            fe->span8[l] = tb_resize_span8_ok(tx, x1);
             if (!fe->area2[l] && tb_resize_span_ok(tx, x1))
                 fe->has_tmap[l] = tb_resize_tensor_map(&fe->pyr_tmap[l], fe->pyr[l - 1], lw[l - 1], lh[l - 1], B, fe->g[l - 1].pitch,
                                                        fe->g[l - 1].frame_stride, fe->box_rows[l]);
@@ -414,7 +416,7 @@ static int pyramid_enqueue(tb_frontend *fe, int n_frames)
         const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
         int rc = tb_launch_resize(fe->ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
                                   d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames, fe->box_pitch[l], fe->box_rows[l],
-                                  fe->has_tmap[l] ? &fe->pyr_tmap[l] : nullptr);
+                                  fe->has_tmap[l] ? &fe->pyr_tmap[l] : nullptr, fe->span8[l]);
         if (rc) return rc;
     }
     return TB_OK;

@@ -6,11 +6,12 @@ struct ResizeTab { int32_t ofs; int16_t c0, c1; };
 void tb_build_resize_tab(int sn, int dn, bool is_x, std::vector<ResizeTab> &tab, std::vector<int32_t> &ofs1);
 bool tb_resize_is_area2(int sw, int sh, int dw, int dh);
 bool tb_resize_span_ok(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1);
+bool tb_resize_span8_ok(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1);
 void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
                    const std::vector<int32_t> &y1, int *bp, int *bh);
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
                      size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh,
-                     const CUtensorMap *tmap);
+                     const CUtensorMap *tmap, bool span8);
 bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows);
 struct FastArgs {
     const uint8_t *img; int pitch; size_t frame_stride;

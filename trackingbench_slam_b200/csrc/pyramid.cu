@@ -399,6 +399,126 @@ pyr_resize_linear_u8_stream(const __grid_constant__ CUtensorMap tmap, uint8_t *_
     }
 }
 
+// ---- 8 columns per thread (default where the taps allow it): same streaming scheme with blockDim (32, 8) — a thread owns 8
+// output columns x 4 output rows.  Per-row bookkeeping (row table entry, buffer choice, store, loop) is paid once per 8 pixels
+// instead of once per 4: ncu showed the 4-column kernel issuing on 69 % of the cycles with ~94 instructions per 4-pixel row.
+// The taps of columns 0..3 lie in bytes [0, 8) and those of columns 4..7 in bytes [4, 12) of a 12-byte window that starts at
+// the thread's first tap (tb_resize_span8_ok checks this on the host).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+pyr_resize_linear_u8_stream8(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, int dpitch, size_t dframe,
+                             int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int bh_max, int n_frames, int fpc)
+{
+    __shared__ alignas(8) uint64_t s_full[PYR_STAGES], s_empty[PYR_STAGES];
+    __shared__ uint32_t s_yq[PYR_TH];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+    const int tx1 = min(tx0 + PYR_TW, dw) - 1, ty1 = min(ty0 + PYR_TH, dh) - 1;
+    const int f0 = blockIdx.z * fpc, nf = min(n_frames, f0 + fpc) - f0;
+    const int box_bytes = (bh_max * PYR_BOXW + 127) & ~127;
+    uint8_t *boxes = pyr_smem;                                                    // [PYR_STAGES][2 boxes][box_bytes]
+    const int sx_lo = __ldg(&xtab[tx0]).x & ~15;
+    const int sy_lo = __ldg(&ytab[ty0]).x;
+    auto fetch = [&](int s, int f) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(2 * bh_max * PYR_BOXW) : "memory");
+        pyr_tma_box(boxes + (size_t)(2 * s) * box_bytes, &tmap, sx_lo, sy_lo, f, &s_full[s]);
+        pyr_tma_box(boxes + (size_t)(2 * s + 1) * box_bytes, &tmap, sx_lo + PYR_BOXW, sy_lo, f, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < PYR_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_full[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_s32(&s_empty[s])), "r"(8));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < PYR_STAGES && s < nf; s++) fetch(s, f0 + s);
+    }
+    if (tid < PYR_TH) {   // the tile's output rows: w0 (12 bits) | w1 << 12 | upper source row << 24 | (lower row = upper + 1) << 31
+        const int4 yt = __ldg(&ytab[min(ty0 + tid, dh - 1)]);
+        s_yq[tid] = ((uint32_t)yt.z & 0xFFF) | (((uint32_t)yt.w & 0xFFF) << 12) | ((uint32_t)(yt.x - sy_lo) << 24) | (yt.y != yt.x ? 0x80000000u : 0u);
+    }
+    // this thread's 8 output columns: four word offsets inside a stage, PRMT selectors of the four tap pairs, weights c0 | c1 << 16
+    const int cx = threadIdx.x * 8;
+    int woff[4];
+    uint32_t sel[4], cp[8];
+    int wsh;
+    {
+        int4 xt[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) xt[k] = __ldg(&xtab[min(tx0 + cx + k, dw - 1)]);
+        const int o_first = xt[0].x - sx_lo;
+        wsh = 8 * (o_first & 3);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = min(4 * ((o_first >> 2) + j), 2 * PYR_BOXW - 4);
+            woff[j] = x < PYR_BOXW ? x : box_bytes + x - PYR_BOXW;
+        }
+        uint32_t ia[8], ib[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int base = o_first + (k < 4 ? 0 : 4);       // columns 4..7 select from the window's bytes 4..11
+            ia[k] = (uint32_t)(xt[k].x - sx_lo - base) & 7u; ib[k] = (uint32_t)(xt[k].y - sx_lo - base) & 7u;
+            cp[k] = ((uint32_t)xt[k].z & 0xFFFF) | ((uint32_t)xt[k].w << 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) sel[j] = ia[2 * j] | (ib[2 * j] << 4) | (ia[2 * j + 1] << 8) | (ib[2 * j + 1] << 12);
+    }
+    const int dx0 = tx0 + cx, dy0 = ty0 + threadIdx.y * (PYR_TH / 8);
+    const uint32_t *yq = s_yq + threadIdx.y * (PYR_TH / 8);
+    const bool active = dx0 <= tx1 && dy0 <= ty1;
+    const bool wide = dx0 + 4 <= tx1;                      // the second word holds at least one column of the level
+    __syncthreads();                                       // barriers and the row table initialised before anyone goes on
+    for (int f = 0; f < nf; f++) {
+        const int s = f % PYR_STAGES;
+        const uint32_t ph = (uint32_t)((f / PYR_STAGES) & 1);
+        pyr_mbar_wait(&s_full[s], ph);
+        if (active) {
+            const uint8_t *stage = boxes + (size_t)(2 * s) * box_bytes;
+            auto hrow = [&](int r, uint32_t (&h)[8]) {
+                const uint8_t *row = stage + r * PYR_BOXW;
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + woff[0]), w1 = *reinterpret_cast<const uint32_t *>(row + woff[1]),
+                               w2 = *reinterpret_cast<const uint32_t *>(row + woff[2]), w3 = *reinterpret_cast<const uint32_t *>(row + woff[3]);
+                const uint32_t b0 = __funnelshift_r(w0, w1, wsh), b1 = __funnelshift_r(w1, w2, wsh), b2 = __funnelshift_r(w2, w3, wsh);
+                const uint32_t p01 = __byte_perm(b0, b1, sel[0]), p23 = __byte_perm(b0, b1, sel[1]);
+                const uint32_t p45 = __byte_perm(b1, b2, sel[2]), p67 = __byte_perm(b1, b2, sel[3]);
+                h[0] = __dp2a_lo(cp[0], p01, 0u) >> 4; h[1] = __dp2a_hi(cp[1], p01, 0u) >> 4;
+                h[2] = __dp2a_lo(cp[2], p23, 0u) >> 4; h[3] = __dp2a_hi(cp[3], p23, 0u) >> 4;
+                h[4] = __dp2a_lo(cp[4], p45, 0u) >> 4; h[5] = __dp2a_hi(cp[5], p45, 0u) >> 4;
+                h[6] = __dp2a_lo(cp[6], p67, 0u) >> 4; h[7] = __dp2a_hi(cp[7], p67, 0u) >> 4;
+            };
+            uint8_t *dp = dst + (size_t)(f0 + f) * dframe + (size_t)dy0 * dpitch + dx0;   // advances by the pitch
+            uint32_t hx[8], hy[8];
+            int rx = -1, ry = -1;                          // source rows held in hx / hy
+            const int nrows = min(PYR_TH / 8, ty1 - dy0 + 1);
+#pragma unroll 1
+            for (int kk = 0; kk < nrows; kk++) {
+                const uint32_t q = yq[kk];
+                const int r0 = (int)((q >> 24) & 0x7F), r1 = r0 + (int)(q >> 31);
+                const uint32_t W0 = (q & 0xFFFu) << 16, W1 = (q << 4) & 0x0FFF0000u;
+                uint32_t wx, wy;
+                if (ry == r0) { if (r1 != r0) { hrow(r1, hx); rx = r1; wx = W1; wy = W0; } else { wx = 0u; wy = W0 + W1; } }
+                else if (rx == r0) { if (r1 != r0) { hrow(r1, hy); ry = r1; wx = W0; wy = W1; } else { wx = W0 + W1; wy = 0u; } }
+                else { hrow(r0, hx); rx = r0; wx = W0; if (r1 != r0) { hrow(r1, hy); ry = r1; wy = W1; } else { wx = W0 + W1; wy = 0u; } }
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = (__umulhi(wx, hx[k]) + __umulhi(wy, hy[k]) + 2u) >> 2;   // <= 255
+                const uint32_t o0 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                const uint32_t o1 = __byte_perm(__byte_perm(v[4], v[5], 0x0040), __byte_perm(v[6], v[7], 0x0040), 0x5410);
+                // the row pitch is a multiple of 64 bytes: whole words fit even where fewer columns are inside the level
+                if (wide) *reinterpret_cast<uint2 *>(dp) = make_uint2(o0, o1);
+                else *reinterpret_cast<uint32_t *>(dp) = o0;
+                dp += dpitch;
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pyr_s32(&s_empty[s])) : "memory");
+        if (tid == 0 && f + PYR_STAGES < nf) {
+            pyr_mbar_wait(&s_empty[s], ph);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fetch(s, f0 + f + PYR_STAGES);
+        }
+    }
+}
+
 // Host: shared-memory box (pitch, rows) needed by the worst tile of a level.
 void tb_resize_box(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1, const std::vector<ResizeTab> &ty,
                    const std::vector<int32_t> &y1, int *bp, int *bh)
@@ -422,6 +542,21 @@ bool tb_resize_span_ok(const std::vector<ResizeTab> &tx, const std::vector<int32
     return true;
 }
 
+// Host: the 8-column kernel needs the taps of columns 0..3 of every group of 8 inside bytes [0, 8) and those of columns 4..7
+// inside bytes [4, 12) of the window that starts at the group's first tap.
+bool tb_resize_span8_ok(const std::vector<ResizeTab> &tx, const std::vector<int32_t> &x1)
+{
+    const int dw = (int)tx.size();
+    for (int c = 0; c < dw; c += 8) {
+        const int last = std::min(c + 7, dw - 1), o = tx[c].ofs;
+        for (int k = c; k <= last; k++) {
+            const int lo = k - c < 4 ? 0 : 4;
+            if (tx[k].ofs - o < lo || x1[k] - o < lo || tx[k].ofs - o > lo + 7 || x1[k] - o > lo + 7) return false;
+        }
+    }
+    return true;
+}
+
 // Exact 2x: OpenCV switches INTER_LINEAR to INTER_AREA (2x2 mean with rounding).
 __global__ void __launch_bounds__(256)
 pyr_resize_area2_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
@@ -437,7 +572,7 @@ pyr_resize_area2_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 
 int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe, uint8_t *dst, int dpitch,
                      size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh,
-                     const CUtensorMap *tmap)
+                     const CUtensorMap *tmap, bool span8)
 {
     ProfScope prof__(ctx, "pyr_resize");
     static const bool use_tma = !(getenv("TB_PYR_TMA") && atoi(getenv("TB_PYR_TMA")) == 0);   // A/B knob: 0 forces the LDG-staged kernel
@@ -446,11 +581,22 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
         const size_t smem = 2 * PYR_STAGES * box_bytes + (size_t)bh * PYR_TW * sizeof(uint16_t);
         static const bool use_stream = !(getenv("TB_PYR_STREAM") && atoi(getenv("TB_PYR_STREAM")) == 0);   // A/B knob: 0 = H tile + barriers
         if (use_stream) {
-            static const int fpc = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;   // frames per CTA (tuning knob)
+            // frames per CTA: at most TB_PYR_FPC (8), fewer on the small levels so that a launch still has TB_PYR_WAVES (6) waves of
+            // 4 CTAs per SM (the last levels of a 1080p batch have ~30 tiles per frame)
+            static const int fpc_max = getenv("TB_PYR_FPC") ? std::max(1, atoi(getenv("TB_PYR_FPC"))) : PYR_FPC;
+            static const int waves = getenv("TB_PYR_WAVES") ? std::max(1, atoi(getenv("TB_PYR_WAVES"))) : 6;
+            const long tiles = (long)div_up(dw, PYR_TW) * div_up(dh, PYR_TH);
+            const int fpc = (int)std::min<long>(fpc_max, std::max<long>(1, tiles * n_frames / (148L * 4 * waves)));
             dim3 grid(div_up(dw, PYR_TW), div_up(dh, PYR_TH), div_up(n_frames, fpc)), block(64, 4);
             static const int occ = getenv("TB_PYR_OCC") ? atoi(getenv("TB_PYR_OCC")) : 4;   // resident CTAs per SM the register budget allows (tuning knob)
-            if (occ >= 4) pyr_resize_linear_u8_stream<4><<<grid, block, 2 * PYR_STAGES * box_bytes, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
-            else pyr_resize_linear_u8_stream<3><<<grid, block, 2 * PYR_STAGES * box_bytes, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+            static const bool want8 = !(getenv("TB_PYR_COLS") && atoi(getenv("TB_PYR_COLS")) == 4);   // A/B knob: 4 = four columns per thread
+            const size_t sm = 2 * PYR_STAGES * box_bytes;
+            if (want8 && span8) {
+                dim3 block8(32, 8);
+                if (occ >= 4) pyr_resize_linear_u8_stream8<4><<<grid, block8, sm, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+                else pyr_resize_linear_u8_stream8<3><<<grid, block8, sm, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+            } else if (occ >= 4) pyr_resize_linear_u8_stream<4><<<grid, block, sm, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
+            else pyr_resize_linear_u8_stream<3><<<grid, block, sm, ctx->stream>>>(*tmap, dst, dpitch, dframe, dw, dh, xtab, ytab, bh, n_frames, fpc);
             TB_LAUNCH_CHECK(ctx);
             return TB_OK;
         }
@@ -481,6 +627,8 @@ void tb_pyramid_init_device()
     cudaFuncSetAttribute(pyr_resize_linear_u8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(pyr_resize_linear_u8_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(pyr_resize_linear_u8_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pyr_resize_linear_u8_stream8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(pyr_resize_linear_u8_stream8<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 // tensor map over a level's frames for the TMA resize (box = PYR_BOXW x box_rows); false if the layout does not qualify
 bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows)
