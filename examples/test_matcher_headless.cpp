@@ -109,13 +109,20 @@ int main(int argc, char **argv)
         std::printf("undistort %llx %llx\n", fnv(rect.data, (size_t)rect.rows * rect.cols), fnv(un.data(), un.size() * sizeof(cv::Point2f)));
     }
 
-    // optical flow (LocalBA.cpp:54 calls searchByOPFlow(stereo_frame, current_frame, pts, true, true); reject is not built)
+    // optical flow; LocalBA.cpp:54 and test_vo.cpp:716 call searchByOPFlow(.., equalized = true, reject = true)
     for (int eq = 0; eq < 2; eq++) {
         std::vector<cv::Point2f> cur_points;
         matches = matcher_ptr->searchByOPFlow(frame2_ptr, frame1_ptr, cur_points, eq != 0, false);
         unsigned long long h = fnv(cur_points.data(), cur_points.size() * sizeof(cv::Point2f));
         for (const auto &m : matches) h = fnv(&m.queryIdx, sizeof m.queryIdx, h);
         std::printf("opflow%d %zu %llx\n", eq, matches.size(), h);
+    }
+    {
+        std::vector<cv::Point2f> cur_points;
+        matches = matcher_ptr->searchByOPFlow(frame2_ptr, frame1_ptr, cur_points, true, true);
+        unsigned long long h = fnv(cur_points.data(), cur_points.size() * sizeof(cv::Point2f));
+        for (const auto &m : matches) h = fnv(&m.queryIdx, sizeof m.queryIdx, h);
+        std::printf("opflow_reject %zu %llx\n", matches.size(), h);
     }
 
     // bag of words (test_vo.cpp:661-705 loads ORBvoc.txt and calls SetBow per keyframe); optional 4th argument

@@ -2,7 +2,7 @@
 // descriptor matchers on the hot path (searchByBF, searchByViolence, searchByProjection x2, searchByBow,
 // DescriptorDistance, ComputeThreeMaxima).  Public members, setters, method names and argument
 // meaning are the reference's; bodies (src/matchers/matcher.cpp:168-617,793-851) run on the GPU.
-// searchByOPFlow (matcher.cpp:724) runs its pyramidal LK on the GPU; its optional rejectWithF (RANSAC) is not built.
+// searchByOPFlow (matcher.cpp:724) runs its pyramidal LK and its rejectWithF (cv::findFundamentalMat RANSAC, :853-881) on the GPU.
 // searchByNN (approximate FLANN-LSH) and the direct-alignment methods are out of scope.
 #ifndef TRACKING_BENCH_MATCHER_H
 #define TRACKING_BENCH_MATCHER_H
@@ -124,12 +124,12 @@ public:
         return to_dmatch(out, n);
     }
     // matcher.cpp:724 — LK tracks of F2's keypoints into F1 (cv::calcOpticalFlowPyrLK, Size(21,21), 3 levels), status
-    // cleared outside the frame (:747-749); matches are {i, i}. reject=true (rejectWithF, RANSAC) is not on this path.
+    // cleared outside the frame (:747-749), then — reject = true, as every caller in the reference passes — rejectWithF
+    // (:751-755); matches are {i, i} for the tracks that are left.
     std::vector<cv::DMatch> searchByOPFlow(const std::shared_ptr<Frame> &F1, const std::shared_ptr<Frame> &F2, std::vector<cv::Point2f> &cur_points,
                                            bool equalized, bool reject, bool MapPointOnly = false)
     {
         (void)MapPointOnly;   // unused by the reference body as well
-        if (reject) throw std::invalid_argument("searchByOPFlow(reject=true): rejectWithF is not on the accelerated path");
         tb_ctx *ctx = tb_default_ctx();
         cv::Mat img1 = contiguous(equalized ? F1->Equalize() : F1->GetImage()), img2 = contiguous(F2->GetImage());
         const std::vector<cv::Point2f> prev = F2->GetCVKeys();
@@ -140,13 +140,29 @@ public:
         static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f must be two packed floats");
         if (n) tb_check(tb_lk_flow_host(ctx, &lk, img2.data, img1.data, img2.cols, img2.rows, img2.step, (const float *)prev.data(), n,
                                         (float *)cur_points.data(), status.data(), nullptr), ctx, "tb_lk_flow_host");
-        std::vector<cv::DMatch> matches;
         const int W = F1->GetCameraModel()->Width(), H = F1->GetCameraModel()->Height();
         for (int i = 0; i < n; i++) {
             const int xi = (int)cur_points[i].x, yi = (int)cur_points[i].y;
-            if (status[i] && xi >= 0 && xi < W && yi >= 0 && yi < H) { cv::DMatch m; m.queryIdx = i; m.trainIdx = i; matches.push_back(m); }
+            if (status[i] && !(xi >= 0 && xi < W && yi >= 0 && yi < H)) status[i] = 0;
         }
+        if (reject) rejectWithF(cur_points, prev, status);
+        std::vector<cv::DMatch> matches;
+        for (int i = 0; i < n; i++)
+            if (status[i]) { cv::DMatch m; m.queryIdx = i; m.trainIdx = i; matches.push_back(m); }
         return matches;
+    }
+    // matcher.cpp:853 — cv::findFundamentalMat(cur, last, FM_RANSAC, 1.0, 0.99) over the tracks with status != 0; outliers lose
+    // their status.  (The reference reads an empty mask when OpenCV returns none — fewer than 15 valid tracks run LMedS or
+    // nothing there; here status stays as it is.)
+    void rejectWithF(std::vector<cv::Point2f> &cur_pts, const std::vector<cv::Point2f> &last_pts, std::vector<uint8_t> &status)
+    {
+        tb_ctx *ctx = tb_default_ctx();
+        const int n = (int)std::min(cur_pts.size(), last_pts.size());
+        if (n == 0) return;
+        if (status.size() < (size_t)n) status.resize(n, 0);
+        const tb_ransac_params rp = {1.0f, 0.99f, 1000};
+        tb_check(tb_reject_with_f_host(ctx, &rp, (const float *)cur_pts.data(), (const float *)last_pts.data(), n, status.data(), nullptr, nullptr),
+                 ctx, "tb_reject_with_f_host");
     }
     // matcher.cpp:793
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b)

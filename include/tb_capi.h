@@ -328,7 +328,7 @@ int tb_frontend_stereo_match(tb_frontend *fe, const tb_stereo_params *p, int n_p
  * cv::Size(21,21), 3) call of Matcher::searchByOPFlow (src/matchers/matcher.cpp:745): OpenCV's fixed-point patches and
  * stop rules; the 2x2 sums are exact integers (OpenCV's SIMD build sums them in float lanes), so results agree with
  * OpenCV within a tolerance (tests/test_oracle_cv2.py) and with the oracle bit for bit. status = 1 where the track is
- * valid; err = OpenCV's mean absolute patch difference / 32. rejectWithF (RANSAC, matcher.cpp:751-755) is not included. */
+ * valid; err = OpenCV's mean absolute patch difference / 32. rejectWithF (RANSAC, matcher.cpp:751-755) is tb_reject_with_f_* below. */
 typedef struct {
     int32_t win;       /* reference: 21 (3..21) */
     int32_t max_level; /* reference: 3; at most 7 levels above level 0 are built (else TB_E_UNSUPPORTED) */
@@ -346,7 +346,8 @@ int tb_lk_flow_device(tb_ctx *ctx, const tb_lk_params *p, const void *prev_dptr,
                       const void *next_dptr, size_t next_pitch, size_t next_frame_stride, int n_next, int w, int h,
                       int n_pairs, const int32_t *prev_idx, const int32_t *next_idx, const void *pts_f32x2_dptr,
                       const void *counts_i32_dptr, int pts_cap, void *next_pts_f32x2_dptr, void *status_u8_dptr, void *err_f32_dptr);
-/* Matcher::searchByOPFlow(F1, F2, cur_points, equalized, reject=false) (matcher.cpp:724-768) over frames [0, n_frames) of
+/* Matcher::searchByOPFlow(F1, F2, cur_points, equalized, reject=false) (matcher.cpp:724-768; follow it with
+ * tb_frontend_reject_with_f for reject = true) over frames [0, n_frames) of
  * the frontend (level 0 resident, keypoints from the last extract): pair q tracks the keypoints of frame f2_frames[q] into
  * frame f1_frames[q] (CLAHE'd first when equalized), then clears status where IsInFrame(Vector2i(pt)) fails (:747-749).
  * The reference's match list is {i,i} for every status[i] != 0. Outputs on the device, [pair][tb_frontend_kp_capacity()]. */
@@ -354,13 +355,41 @@ int tb_frontend_search_by_opflow(tb_frontend *fe, const tb_lk_params *p, int n_f
                                  const int32_t *f2_frames, int equalized, void *next_pts_f32x2_dptr, void *status_u8_dptr,
                                  void *err_f32_dptr);
 
-/* LocalBA::AddMapPointsByStereo's live body (src/mapping/LocalBA.cpp:46-68) without rejectWithF: pair q tracks the keypoints of
+/* LocalBA::AddMapPointsByStereo's live body (src/mapping/LocalBA.cpp:46-68) without rejectWithF (run
+ * tb_frontend_reject_with_f on the returned tracks and drop the depths whose status it cleared): pair q tracks the keypoints of
  * frame current_frames[q] into frame stereo_frames[q] (searchByOPFlow(stereo, current, pts, equalized, ...), :54) and writes
  * depth_f32_dptr[q][i] = bf / |pts[i].x - kp[i].x| for every valid track, -1 elsewhere (:61-65). The tracks and their status
  * are returned as well ([pair][tb_frontend_kp_capacity()]) so that the caller can run the reference's RANSAC rejection. */
 int tb_frontend_stereo_depth_by_opflow(tb_frontend *fe, const tb_lk_params *p, float bf, int n_frames, int n_pairs,
                                        const int32_t *current_frames, const int32_t *stereo_frames, int equalized,
                                        void *depth_f32_dptr, void *next_pts_f32x2_dptr, void *status_u8_dptr);
+
+/* Matcher::rejectWithF (src/matchers/matcher.cpp:853-881), the step searchByOPFlow(reject = true) runs after the IsInFrame
+ * filter (:751-755; every reference call site passes reject = true): the tracks with status != 0 go through
+ * cv::findFundamentalMat(cur, last, cv::FM_RANSAC, 1.0, 0.99, mask) and the outliers' status is cleared.  OpenCV's RANSAC is
+ * reproduced iteration for iteration (cv::RNG((uint64)-1), getSubset with its collinearity test, the 7-point solver,
+ * solveCubic, the symmetric epipolar error rounded to float, RANSACUpdateNumIters): inlier masks identical to cv2 4.13 on
+ * every tested case.  Fewer than 15 tracks with status != 0 (OpenCV switches to LMedS below that) or n <= 8 (the reference
+ * does not call findFundamentalMat) leave status unchanged. */
+typedef struct {
+    float threshold;    /* reference: 1.0 (pixels) */
+    float confidence;   /* reference: 0.99 */
+    int32_t max_iters;  /* OpenCV default: 1000 */
+} tb_ransac_params;
+/* Host in/out, one pair: cur_xy / last_xy are n x 2 floats, status n bytes (updated in place); F9 (row-major 3x3, may be
+ * NULL) receives the best model, iterations (may be NULL) the number of RANSAC iterations OpenCV would have run. */
+int tb_reject_with_f_host(tb_ctx *ctx, const tb_ransac_params *p, const float *cur_xy, const float *last_xy, int n, uint8_t *status,
+                          double *F9, int *iterations);
+/* Device, batched: [pair][pts_cap] float2 points, [pair][pts_cap] status bytes (in/out), counts[pair] on the device;
+ * F_f64x9_dptr [pair][9] and iters_i32_dptr [pair] may be NULL.  One CTA per pair, no host wait. */
+int tb_reject_with_f_device(tb_ctx *ctx, const tb_ransac_params *p, int n_pairs, const void *cur_pts_f32x2_dptr,
+                            const void *last_pts_f32x2_dptr, const void *counts_i32_dptr, int pts_cap, void *status_u8_dptr,
+                            void *F_f64x9_dptr, void *iters_i32_dptr);
+/* The same behind tb_frontend_search_by_opflow / tb_frontend_stereo_depth_by_opflow: pair q's "last" points are the keypoints
+ * of frame f2_frames[q] (the frame the tracks started from), next_pts / status are that call's outputs
+ * ([pair][tb_frontend_kp_capacity()]). */
+int tb_frontend_reject_with_f(tb_frontend *fe, const tb_ransac_params *p, int n_pairs, const int32_t *f2_frames,
+                              const void *next_pts_f32x2_dptr, void *status_u8_dptr, void *F_f64x9_dptr, void *iters_i32_dptr);
 
 /* Matcher::searchByProjection(F1,F2) (matcher.cpp:405-531). F2's map points flattened:
  * mp_valid[i2] = (GetMapPoint(i2) != null && !isBad()), mp_xyz[3*i2], mp_desc[32*i2];

@@ -350,6 +350,17 @@ def lk_flow(params, prev, nxt, pts):
     return out, st, err
 
 
+def reject_with_f(cur_pts, last_pts, status, threshold=1.0, confidence=0.99, max_iters=1000):
+    """Matcher::rejectWithF (matcher.cpp:853-881): returns (status after the RANSAC rejection, F (3x3), iterations run)."""
+    cur = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2); last = np.ascontiguousarray(last_pts, np.float32).reshape(-1, 2)
+    st = np.ascontiguousarray(status, np.uint8).copy()
+    F = np.zeros(9, np.float64)
+    f = lib().tbo_reject_with_f
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    it = f(_p(cur), _p(last), len(cur), _p(st), threshold, confidence, max_iters, _p(F))
+    return st, F.reshape(3, 3), it
+
+
 def stereo_rowband(params, kL, dL, kR, dR, inv_sf, n_rows):
     """LocalBA.cpp:69-288 (block-commented ORB stereo matcher) -> (matches, depth[nL])."""
     kL, kR = np.ascontiguousarray(kL, KP_DTYPE), np.ascontiguousarray(kR, KP_DTYPE)

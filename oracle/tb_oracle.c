@@ -1532,3 +1532,218 @@ void tbo_undistort_points(float ffx, float ffy, float fcx, float fcy, const floa
         xy_out[2 * i + 1] = (float)(yy * ww);
     }
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Matcher::rejectWithF (matcher.cpp:853-881) -> cv::findFundamentalMat(FM_RANSAC, 1.0, 0.99): OpenCV 4.x restated
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t state; } tbo_rng;                       /* cv::RNG: multiply-with-carry */
+static unsigned rng_next(tbo_rng *r) { r->state = (uint64_t)(unsigned)r->state * 4164903690u + (unsigned)(r->state >> 32); return (unsigned)r->state; }
+static int rng_uniform(tbo_rng *r, int a, int b) { return a == b ? a : (int)(rng_next(r) % (unsigned)(b - a) + a); }
+
+/* haveCollinearPoints(m, 7): the last point against every pair of earlier ones */
+static int fm_collinear7(const float *p)
+{
+    const int i = 6;
+    for (int j = 0; j < i; j++) {
+        double dx1 = (double)p[2 * j] - p[2 * i], dy1 = (double)p[2 * j + 1] - p[2 * i + 1];
+        for (int k = 0; k < j; k++) {
+            double dx2 = (double)p[2 * k] - p[2 * i], dy2 = (double)p[2 * k + 1] - p[2 * i + 1];
+            if (fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return 1;
+        }
+    }
+    return 0;
+}
+/* RANSACPointSetRegistrator::getSubset (modelPoints = 7, maxAttempts = 10000) */
+static int fm_get_subset(const float *m1, const float *m2, int count, tbo_rng *rng, float *s1, float *s2)
+{
+    for (int it = 0; it < 10000; it++) {
+        int idx[7];
+        for (int i = 0; i < 7; i++) {
+            int v, dup;
+            do {
+                v = rng_uniform(rng, 0, count); dup = 0;
+                for (int k = 0; k < i; k++) dup |= idx[k] == v;
+            } while (dup);
+            idx[i] = v;
+            s1[2 * i] = m1[2 * v]; s1[2 * i + 1] = m1[2 * v + 1]; s2[2 * i] = m2[2 * v]; s2[2 * i + 1] = m2[2 * v + 1];
+        }
+        if (!fm_collinear7(s1) && !fm_collinear7(s2)) return 1;
+    }
+    return 0;
+}
+/* cv::solveCubic for c[0] x^3 + c[1] x^2 + c[2] x + c[3] */
+static int fm_solve_cubic(const double *c, double *x)
+{
+    double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+    if (a0 == 0) {
+        if (a1 == 0) { if (a2 == 0) return 0; x[0] = -a3 / a2; return 1; }
+        double d = a2 * a2 - 4 * a1 * a3;
+        if (d < 0) return 0;
+        d = sqrt(d);
+        double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (fabs(q1) > fabs(q2)) { x[0] = q1 / a1; x[1] = a3 / q1; } else { x[0] = q2 / a1; x[1] = a3 / q2; }
+        return d > 0 ? 2 : 1;
+    }
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+    double Q = (a1 * a1 - 3 * a2) * (1. / 9), R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    double Qcubed = Q * Q * Q, d = Qcubed - R * R;
+    if (d > 0) {
+        double theta = acos(R / sqrt(Qcubed)), sqrtQ = sqrt(Q), t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+        x[0] = t0 * cos(t1) - t2; x[1] = t0 * cos(t1 + (2. * 3.1415926535897932384626433832795 / 3)) - t2;
+        x[2] = t0 * cos(t1 + (4. * 3.1415926535897932384626433832795 / 3)) - t2;
+        return 3;
+    }
+    if (d == 0) {
+        if (R >= 0) { x[0] = -2 * pow(R, 1. / 3) - a1 / 3; x[1] = pow(R, 1. / 3) - a1 / 3; }
+        else { x[0] = 2 * pow(-R, 1. / 3) - a1 / 3; x[1] = -pow(-R, 1. / 3) - a1 / 3; }
+        return x[0] == x[1] ? 1 : 2;
+    }
+    d = sqrt(-d);
+    double e = pow(d + fabs(R), 1. / 3);
+    if (R > 0) e = -e;
+    x[0] = (e + Q / e) - a1 * (1. / 3);
+    return 1;
+}
+/* the two eigenvectors of the smallest eigenvalues of the symmetric 9x9 M (cyclic Jacobi) */
+static void fm_null2(double M[9][9], double *f1, double *f2)
+{
+    double V[9][9];
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 9; j++) V[i][j] = i == j;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int p = 0; p < 9; p++) for (int q = p + 1; q < 9; q++) off += M[p][q] * M[p][q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 9; p++) for (int q = p + 1; q < 9; q++) {
+            if (fabs(M[p][q]) < 1e-300) continue;
+            double theta = (M[q][q] - M[p][p]) / (2 * M[p][q]);
+            double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+            double c = 1 / sqrt(t * t + 1), s = t * c;
+            for (int k = 0; k < 9; k++) { double a = M[k][p], b = M[k][q]; M[k][p] = c * a - s * b; M[k][q] = s * a + c * b; }
+            for (int k = 0; k < 9; k++) { double a = M[p][k], b = M[q][k]; M[p][k] = c * a - s * b; M[q][k] = s * a + c * b; }
+            for (int k = 0; k < 9; k++) { double a = V[k][p], b = V[k][q]; V[k][p] = c * a - s * b; V[k][q] = s * a + c * b; }
+        }
+    }
+    int i1 = 0, i2 = -1;
+    for (int i = 1; i < 9; i++) if (M[i][i] < M[i1][i1]) i1 = i;
+    for (int i = 0; i < 9; i++) if (i != i1 && (i2 < 0 || M[i][i] < M[i2][i2])) i2 = i;
+    for (int k = 0; k < 9; k++) { f1[k] = V[k][i2]; f2[k] = V[k][i1]; }   /* OpenCV: f1 = 8th, f2 = 9th (smallest) right singular vector */
+}
+/* run7Point (fundam.cpp): up to 3 models, each 9 doubles */
+static int fm_run7(const float *m1, const float *m2, double *F)
+{
+    double c1x = 0, c1y = 0, c2x = 0, c2y = 0, scale1 = 0, scale2 = 0;
+    for (int i = 0; i < 7; i++) { c1x += m1[2 * i]; c1y += m1[2 * i + 1]; c2x += m2[2 * i]; c2y += m2[2 * i + 1]; }
+    const double t = 1. / 7;
+    c1x *= t; c1y *= t; c2x *= t; c2y *= t;
+    for (int i = 0; i < 7; i++) {
+        double dx = m1[2 * i] - c1x, dy = m1[2 * i + 1] - c1y; scale1 += sqrt(dx * dx + dy * dy);
+        dx = m2[2 * i] - c2x; dy = m2[2 * i + 1] - c2y; scale2 += sqrt(dx * dx + dy * dy);
+    }
+    scale1 *= t; scale2 *= t;
+    if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return 0;
+    scale1 = sqrt(2.) / scale1; scale2 = sqrt(2.) / scale2;
+    double A[7][9], M[9][9];
+    for (int i = 0; i < 7; i++) {
+        double x0 = (m1[2 * i] - c1x) * scale1, y0 = (m1[2 * i + 1] - c1y) * scale1;
+        double x1 = (m2[2 * i] - c2x) * scale2, y1 = (m2[2 * i + 1] - c2y) * scale2;
+        double r[9] = {x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1};
+        for (int k = 0; k < 9; k++) A[i][k] = r[k];
+    }
+    for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) { double s = 0; for (int i = 0; i < 7; i++) s += A[i][a] * A[i][b]; M[a][b] = s; }
+    double f1[9], f2[9], c[4], r[3] = {0, 0, 0};
+    fm_null2(M, f1, f2);
+    for (int i = 0; i < 9; i++) f1[i] -= f2[i];
+    double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+    c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+    c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) + f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+           f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) + f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+           f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+    t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+    c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) + f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+           f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) + f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+           f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+    c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+    const int n = fm_solve_cubic(c, r);
+    if (n < 1 || n > 3) return 0;
+    const double T1[9] = {scale1, 0, -scale1 * c1x, 0, scale1, -scale1 * c1y, 0, 0, 1};
+    const double T2[9] = {scale2, 0, -scale2 * c2x, 0, scale2, -scale2 * c2y, 0, 0, 1};
+    for (int k = 0; k < n; k++, F += 9) {
+        double lambda = r[k], mu = 1., s = f1[8] * r[k] + f2[8], G[9], H[9];
+        if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; G[8] = 1.; } else G[8] = 0.;
+        for (int i = 0; i < 8; i++) G[i] = f1[i] * lambda + f2[i] * mu;
+        /* F = T2^T * G * T1 */
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double v = 0; for (int m = 0; m < 3; m++) v += T2[m * 3 + a] * G[m * 3 + b]; H[a * 3 + b] = v; }
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double v = 0; for (int m = 0; m < 3; m++) v += H[a * 3 + m] * T1[m * 3 + b]; F[a * 3 + b] = v; }
+        if (fabs(F[8]) > FLT_EPSILON) { const double inv = 1. / F[8]; for (int i = 0; i < 9; i++) F[i] *= inv; }
+    }
+    return n;
+}
+/* FMEstimatorCallback::computeError + findInliers: err <= threshold^2 (float compare) */
+static int fm_inliers(const float *m1, const float *m2, int count, const double *F, float thr2, uint8_t *mask)
+{
+    int good = 0;
+    for (int i = 0; i < count; i++) {
+        const double x1 = m1[2 * i], y1 = m1[2 * i + 1], x2 = m2[2 * i], y2 = m2[2 * i + 1];
+        double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+        const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+        a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+        const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+        const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+        const float err = (float)(e1 > e2 ? e1 : e2);
+        const int in = err <= thr2;
+        if (mask) mask[i] = (uint8_t)in;
+        good += in;
+    }
+    return good;
+}
+static int fm_update_iters(double p, double ep, int model_points, int max_iters)
+{
+    p = p < 0 ? 0 : p > 1 ? 1 : p; ep = ep < 0 ? 0 : ep > 1 ? 1 : ep;
+    double num = 1. - p > DBL_MIN ? 1. - p : DBL_MIN, denom = 1. - pow(1. - ep, model_points);
+    if (denom < DBL_MIN) return 0;
+    num = log(num); denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)lrint(num / denom);
+}
+int tbo_reject_with_f(const float *cur_xy, const float *last_xy, int n, u8 *status, double threshold, double confidence,
+                      int max_iters, double *F9)
+{
+    if (n <= 8) return 0;                                         /* matcher.cpp:870: findFundamentalMat is not called */
+    int *id = (int *)malloc(sizeof(int) * (size_t)n), count = 0;
+    float *m1 = (float *)malloc(sizeof(float) * 2 * (size_t)n), *m2 = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+    for (int i = 0; i < n; i++) if (status[i]) {
+        id[count] = i; m1[2 * count] = cur_xy[2 * i]; m1[2 * count + 1] = cur_xy[2 * i + 1];
+        m2[2 * count] = last_xy[2 * i]; m2[2 * count + 1] = last_xy[2 * i + 1]; count++;
+    }
+    int iters = 0;
+    if (count >= 15) {                                            /* below that OpenCV runs LMedS (or nothing at all) */
+        if (threshold <= 0) threshold = 3;
+        if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+        u8 *mask = (u8 *)malloc((size_t)count);
+        tbo_rng rng = {0xffffffffffffffffull};
+        int niters = max_iters > 1 ? max_iters : 1, max_good = 0;
+        double best[9] = {0}, models[27];
+        const float thr2 = (float)(threshold * threshold);
+        for (iters = 0; iters < niters; iters++) {
+            float s1[14], s2[14];
+            if (!fm_get_subset(m1, m2, count, &rng, s1, s2)) break;
+            const int nm = fm_run7(s1, s2, models);
+            for (int k = 0; k < nm; k++) {
+                const int good = fm_inliers(m1, m2, count, models + 9 * k, thr2, NULL);
+                if (good > (max_good > 6 ? max_good : 6)) {
+                    memcpy(best, models + 9 * k, sizeof best);
+                    max_good = good;
+                    niters = fm_update_iters(confidence, (double)(count - good) / count, 7, niters);
+                }
+            }
+        }
+        if (max_good > 0) {
+            fm_inliers(m1, m2, count, best, thr2, mask);
+            for (int i = 0; i < count; i++) if (!mask[i]) status[id[i]] = 0;   /* matcher.cpp:874-880 */
+            if (F9) memcpy(F9, best, sizeof best);
+        }
+        free(mask);
+    }
+    free(id); free(m1); free(m2);
+    return iters;
+}

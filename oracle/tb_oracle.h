@@ -228,6 +228,18 @@ int tbo_fast_extract(const uint8_t *const *levels, const int *w, const int *h, c
                      const float *inv_sf, int nFeatures, float threshold, const uint8_t *occupied,
                      tbo_kp *out, int cap);
 
+/* Matcher::rejectWithF (src/matchers/matcher.cpp:853-881): the tracks with status != 0 go through
+ * cv::findFundamentalMat(cur, last, cv::FM_RANSAC, 1.0, 0.99, mask) and the outliers' status is cleared.  OpenCV is an
+ * un-vendored dependency: its RANSAC is restated here (calib3d fundam.cpp / ptsetreg.cpp, 4.x: RNG((uint64)-1), getSubset
+ * with the collinearity check, run7Point, solveCubic, the symmetric epipolar error in double rounded to float,
+ * RANSACUpdateNumIters) and pinned to cv2 4.13 by tests/test_oracle_cv2.py (inlier masks identical).  The two null vectors of
+ * the 7x9 system come from a Jacobi eigen-decomposition of A^T A instead of OpenCV's SVD: the models are the members of that
+ * pencil with det = 0, which do not depend on the basis.  Fewer than 15 valid tracks (OpenCV switches to LMedS below that)
+ * or n <= 8 (the reference does not call findFundamentalMat) leave status unchanged and return 0.
+ * Returns the number of RANSAC iterations run; F9 (may be NULL) receives the best model. */
+int tbo_reject_with_f(const float *cur_xy, const float *last_xy, int n, uint8_t *status, double threshold, double confidence,
+                      int max_iters, double *F9);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,15 @@ def test_headless_test_matcher(tmp_path, oracle, images):
         for i in idx:
             h = _fnv(np.int32(i).tobytes(), h)
         assert len(idx) > 300 and got['opflow%d' % eq] == [str(len(idx)), '%x' % h]
+        if eq:   # reject = true: Matcher::rejectWithF on the tracks that are left (matcher.cpp:751-755)
+            st2 = np.zeros(len(pts), np.uint8)
+            st2[idx] = 1
+            st3, _, it = oracle.reject_with_f(pts, np.stack([k1['x'], k1['y']], 1), st2)
+            idx3 = np.nonzero(st3)[0].astype(np.int32)
+            h = _fnv(pts.tobytes())
+            for i in idx3:
+                h = _fnv(np.int32(i).tobytes(), h)
+            assert it > 0 and 8 <= len(idx3) < len(idx) and got['opflow_reject'] == [str(len(idx3)), '%x' % h]
     # bag of words: Frame::SetBow (levelsup 4) + searchByBow, with and without MapPointOnly
     w1, n1, wt1 = oracle.bow_transform(voc, d1, 4)
     w2, n2, wt2 = oracle.bow_transform(voc, d2, 4)

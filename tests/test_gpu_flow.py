@@ -138,3 +138,81 @@ def test_frontend_stereo_depth_by_opflow(tb, ctx, oracle, images):
             assert good.sum() > 300
     finally:
         fe.close()
+
+
+def test_reject_with_f_host_entry(tb, ctx, oracle, images):
+    """Matcher::rejectWithF (matcher.cpp:853-881) through tb_reject_with_f_host: the kept tracks are exactly those the oracle
+    and the real cv2.findFundamentalMat(FM_RANSAC, 1.0, 0.99) keep (tolerance 0 on the masks), the same number of RANSAC
+    iterations is replayed, F agrees with the oracle to 1e-9 relative (CUDA's and glibc's acos / cos / pow differ in the last
+    bits; same algorithm otherwise)."""
+    from .test_oracle_cv2 import fm_cases, cv2_reject_with_f
+    for name, cur, last, st in fm_cases(images, seeds=range(16)):
+        es, eF, eit = oracle.reject_with_f(cur, last, st)
+        s, F, it = ctx.reject_with_f(cur, last, st)
+        assert np.array_equal(s, es), (name, int(s.sum()), int(es.sum()))
+        assert np.array_equal(s, cv2_reject_with_f(cur, last, st)), name
+        assert it == eit, (name, it, eit)
+        if eit:
+            assert np.abs(F - eF).max() <= 1e-9 * np.abs(eF).max(), name
+    s, F, it = ctx.reject_with_f(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.uint8))   # no tracks
+    assert len(s) == 0 and it == 0
+
+
+def test_reject_with_f_golden(tb, ctx):
+    import os
+    from .conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'reject_f.npz'))
+    for i in range(int(g['n_cases'])):
+        s, F, it = ctx.reject_with_f(g['cur%d' % i], g['last%d' % i], g['status_in%d' % i])
+        assert np.array_equal(s, g['status_out%d' % i]) and it == int(g['iters%d' % i]), i
+
+
+def test_reject_with_f_device_batched_and_frontend(tb, ctx, oracle, images):
+    """tb_reject_with_f_device on stacked pairs (one CTA per pair) and tb_frontend_reject_with_f behind
+    tb_frontend_search_by_opflow = Matcher::searchByOPFlow(F1, F2, pts, equalized, reject = true)."""
+    from .test_oracle_cv2 import fm_cases
+    cases = fm_cases(images, seeds=range(7))
+    cap = max(len(c[1]) for c in cases) + 5
+    P = len(cases)
+    cur = torch.zeros((P, cap, 2), dtype=torch.float32, device='cuda')
+    last = torch.zeros((P, cap, 2), dtype=torch.float32, device='cuda')
+    st = torch.ones((P, cap), dtype=torch.uint8, device='cuda')      # bytes past the count must stay untouched
+    cnt = torch.tensor([len(c[1]) for c in cases], dtype=torch.int32, device='cuda')
+    for i, (name, c, l, s) in enumerate(cases):
+        cur[i, :len(c)] = torch.from_numpy(c).cuda(); last[i, :len(c)] = torch.from_numpy(l).cuda(); st[i, :len(c)] = torch.from_numpy(s).cuda()
+    F = torch.zeros((P, 9), dtype=torch.float64, device='cuda')
+    it = torch.zeros(P, dtype=torch.int32, device='cuda')
+    ctx.reject_with_f_device(P, cur.data_ptr(), last.data_ptr(), cnt.data_ptr(), cap, st.data_ptr(), F.data_ptr(), it.data_ptr())
+    ctx.sync()
+    S, IT = st.cpu().numpy(), it.cpu().numpy()
+    for i, (name, c, l, s) in enumerate(cases):
+        es, eF, eit = oracle.reject_with_f(c, l, s)
+        assert np.array_equal(S[i, :len(c)], es) and (S[i, len(c):] == 1).all() and IT[i] == eit, name
+    # behind the frontend's flow entry
+    nl, sc, tgt, a, b = PARAM_SETS['B1000']
+    W, H = 1241, 376
+    frames = np.stack([images['left'], images['right']])
+    sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+    fe = tb.Frontend(ctx, lw, lh, max_batch=2, max_target=tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(2)
+        fe.extract(2, sf, tgt, a, b)
+        kps, desc, counts = fe.get_results_batch(2)
+        kc = fe.kp_cap
+        pairs = [(1, 0), (0, 1)]
+        pts = torch.zeros((2, kc, 2), dtype=torch.float32, device='cuda')
+        s2 = torch.zeros((2, kc), dtype=torch.uint8, device='cuda')
+        fe.search_by_opflow(tb.LKParams(), 2, [q[0] for q in pairs], [q[1] for q in pairs], 1, pts.data_ptr(), s2.data_ptr())
+        ctx.sync()
+        before = s2.cpu().numpy().copy()
+        fe.reject_with_f([q[1] for q in pairs], pts.data_ptr(), s2.data_ptr())
+        ctx.sync()
+        after, Pn = s2.cpu().numpy(), pts.cpu().numpy()
+        for i, (f1, f2) in enumerate(pairs):
+            n2 = counts[f2]
+            kp = np.stack([kps[f2, :n2]['x'], kps[f2, :n2]['y']], 1)
+            es, _, eit = oracle.reject_with_f(Pn[i, :n2], kp, before[i, :n2])
+            assert np.array_equal(after[i, :n2], es) and eit > 0 and es.sum() < before[i, :n2].sum(), i
+    finally:
+        fe.close()

@@ -200,3 +200,69 @@ def test_undistort_points_match_cv2(oracle, cam):
     else:
         ref = pts
     assert got.tobytes() == ref.tobytes()
+
+
+def fm_cases(images, seeds=range(12), max_n=2200):
+    """(name, cur_pts, last_pts, status) inputs of Matcher::rejectWithF: synthetic two-view tracks (pinhole camera, small
+    rotation + translation, 0.3 px noise, up to 45 % gross outliers, 10 % of the tracks already lost) and the real LK tracks
+    of the KITTI pair."""
+    cases = []
+    for seed in seeds:
+        rs = np.random.default_rng(seed)
+        n = int(rs.integers(15, max_n))
+        X = np.c_[rs.uniform(-5, 5, n), rs.uniform(-3, 3, n), rs.uniform(4, 30, n)]
+        K = np.array([[700, 0, 620], [0, 700, 188], [0, 0, 1.]])
+        Rm, _ = cv2.Rodrigues(rs.uniform(-0.05, 0.05, 3))
+        tv = rs.uniform(-0.5, 0.5, 3)
+        p1 = (K @ X.T).T
+        p1 = p1[:, :2] / p1[:, 2:]
+        p2 = (K @ ((Rm @ X.T).T + tv).T).T
+        p2 = p2[:, :2] / p2[:, 2:]
+        p1 += rs.normal(0, 0.3, p1.shape)
+        p2 += rs.normal(0, 0.3, p2.shape)
+        o = rs.choice(n, int(n * rs.uniform(0, 0.45)), replace=False)
+        p2[o] += rs.uniform(-40, 40, (len(o), 2))
+        st = (rs.random(n) >= 0.1).astype(np.uint8)
+        cases.append(('synthetic%d' % seed, p2.astype(np.float32), p1.astype(np.float32), st))
+    name, prev, nxt, pts = lk_inputs(images)[0]
+    n1, s1, _ = cv2.calcOpticalFlowPyrLK(prev, nxt, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+    cases.append(('kitti_lk', n1.reshape(-1, 2).astype(np.float32), pts, s1.ravel().astype(np.uint8)))
+    few = cases[0]
+    cases.append(('too_few', few[1][:40], few[2][:40], (np.arange(40) < 14).astype(np.uint8)))   # 14 valid tracks: OpenCV would run LMedS; unchanged
+    cases.append(('n8', few[1][:8], few[2][:8], np.ones(8, np.uint8)))                             # matcher.cpp:870: not called
+    return cases
+
+
+def cv2_reject_with_f(cur, last, status):
+    """Matcher::rejectWithF with the real OpenCV (matcher.cpp:853-881)."""
+    st = status.copy()
+    ids = np.flatnonzero(st)
+    if len(cur) > 8 and len(ids) >= 15:
+        F, mask = cv2.findFundamentalMat(cur[ids], last[ids], cv2.FM_RANSAC, 1.0, 0.99)
+        if mask is not None:
+            st[ids[mask.ravel() == 0]] = 0
+    return st
+
+
+def test_reject_with_f_matches_cv2(oracle, images):
+    """The restated RANSAC (cv::RNG, getSubset, 7-point solver, solveCubic, error, iteration update) keeps exactly the tracks
+    cv2.findFundamentalMat keeps — tolerance 0 on the masks; F agrees to 1e-6 relative (the null-space basis differs)."""
+    for name, cur, last, st in fm_cases(images, seeds=range(40)):
+        exp = cv2_reject_with_f(cur, last, st)
+        got, F, it = oracle.reject_with_f(cur, last, st)
+        assert np.array_equal(got, exp), (name, int(exp.sum()), int(got.sum()))
+        if name.startswith('synthetic') or name == 'kitti_lk':
+            assert 0 < it <= 1000 and got.sum() < st.sum() and got.sum() >= 8
+            Fc, _ = cv2.findFundamentalMat(cur[st > 0], last[st > 0], cv2.FM_RANSAC, 1.0, 0.99)
+            assert np.abs(F - Fc).max() <= 1e-6 * np.abs(Fc).max(), name
+        else:
+            assert it == 0 and np.array_equal(got, st)
+
+
+def test_reject_with_f_golden(oracle):
+    import os
+    from .conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'reject_f.npz'))
+    for i in range(int(g['n_cases'])):
+        got, F, it = oracle.reject_with_f(g['cur%d' % i], g['last%d' % i], g['status_in%d' % i])
+        assert np.array_equal(got, g['status_out%d' % i]) and it == int(g['iters%d' % i]), i

@@ -6,6 +6,6 @@ package only binds it (capi) and mirrors the reference's host-side classes for P
 (frontend).  There is no CPU fallback: importing capi without the built library raises.
 """
 from . import capi  # noqa: F401
-from .capi import (Context, Frontend, DeviceVocabulary, Undistorter, init_undistort_rectify_map, MatcherParams, StereoParams, LKParams, Pinhole, TbError, KP_DTYPE, MATCH_DTYPE,  # noqa: F401
+from .capi import (Context, Frontend, DeviceVocabulary, Undistorter, init_undistort_rectify_map, MatcherParams, StereoParams, LKParams, RansacParams, Pinhole, TbError, KP_DTYPE, MATCH_DTYPE,  # noqa: F401
                    pyramid_geometry, lib, TB_OK, TB_E_INVALID, TB_E_CUDA, TB_E_CAPACITY, TB_E_UNSUPPORTED, TB_E_NOMEM)
 from . import vocab  # noqa: F401

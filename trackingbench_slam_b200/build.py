@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtb_b200.so')
-SOURCES = ['frontend.cu', 'pyramid.cu', 'fast.cu', 'octree.cu', 'describe.cu', 'match.cu', 'match_tc.cu', 'window.cu', 'fastext.cu', 'ingest.cu', 'flow.cu']
+SOURCES = ['frontend.cu', 'pyramid.cu', 'fast.cu', 'octree.cu', 'describe.cu', 'match.cu', 'match_tc.cu', 'window.cu', 'fastext.cu', 'ingest.cu', 'flow.cu', 'fundam.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--fmad=false']
 

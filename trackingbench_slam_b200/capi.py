@@ -43,6 +43,7 @@ EXPORTS = [
     'tb_lk_flow_host', 'tb_lk_flow_device', 'tb_frontend_search_by_opflow',
     'tb_undistort_points', 'tb_undistort_points_device', 'tb_frontend_undistort_points',
     'tb_frontend_stereo_depth_by_opflow',
+    'tb_reject_with_f_host', 'tb_reject_with_f_device', 'tb_frontend_reject_with_f',
 ]
 
 
@@ -66,6 +67,14 @@ class LKParams(C.Structure):
 
     def __init__(self, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=1e-4):
         super().__init__(win, max_level, max_iter, eps, min_eig)
+
+
+class RansacParams(C.Structure):
+    """tb_ransac_params; defaults = the arguments of matcher.cpp:872 (cv::findFundamentalMat(.., FM_RANSAC, 1.0, 0.99, ..))."""
+    _fields_ = [('threshold', C.c_float), ('confidence', C.c_float), ('max_iters', C.c_int32)]
+
+    def __init__(self, threshold=1.0, confidence=0.99, max_iters=1000):
+        super().__init__(threshold, confidence, max_iters)
 
 
 class Pinhole(C.Structure):
@@ -243,6 +252,22 @@ class Context:
         self.check(lib().tb_lk_flow_host(self.h, C.byref(params), _vp(prev), _vp(nxt), w, h, C.c_size_t(prev.strides[0]), _vp(pts), len(pts),
                                          _vp(out), _vp(st), _vp(err)))
         return out, st, err
+
+    def reject_with_f(self, cur_pts, last_pts, status, params=None):
+        """Matcher::rejectWithF (matcher.cpp:853-881), host in/out -> (status after the rejection, F [3,3], iterations)."""
+        params = params or RansacParams()
+        cur = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+        last = np.ascontiguousarray(last_pts, np.float32).reshape(-1, 2)
+        st = np.ascontiguousarray(status, np.uint8).copy()
+        F = np.zeros(9, np.float64)
+        it = C.c_int()
+        self.check(lib().tb_reject_with_f_host(self.h, C.byref(params), _vp(cur), _vp(last), len(cur), _vp(st), _vp(F), C.byref(it)))
+        return st, F.reshape(3, 3), it.value
+
+    def reject_with_f_device(self, n_pairs, cur_dptr, last_dptr, counts_dptr, pts_cap, status_dptr, F_dptr=None, iters_dptr=None, params=None):
+        params = params or RansacParams()
+        self.check(lib().tb_reject_with_f_device(self.h, C.byref(params), int(n_pairs), _vp(cur_dptr), _vp(last_dptr), _vp(counts_dptr),
+                                                 int(pts_cap), _vp(status_dptr), _vp(F_dptr), _vp(iters_dptr)))
 
     def lk_flow_device(self, params, prev_dptr, prev_pitch, prev_frame_stride, n_prev, next_dptr, next_pitch, next_frame_stride, n_next, w, h,
                        prev_idx, next_idx, pts_dptr, counts_dptr, pts_cap, next_pts_dptr, status_dptr, err_dptr=None):
@@ -598,6 +623,17 @@ def _frontend_search_by_opflow(self, params, n_frames, f1_frames, f2_frames, equ
 
 
 Frontend.search_by_opflow = _frontend_search_by_opflow
+
+
+def _frontend_reject_with_f(self, f2_frames, next_pts_dptr, status_dptr, F_dptr=None, iters_dptr=None, params=None):
+    """rejectWithF behind search_by_opflow / stereo_depth_by_opflow: status is updated in place on the device."""
+    params = params or RansacParams()
+    f2 = np.ascontiguousarray(f2_frames, np.int32)
+    self.ctx.check(lib().tb_frontend_reject_with_f(self.h, C.byref(params), len(f2), _vp(f2), _vp(next_pts_dptr), _vp(status_dptr),
+                                                   _vp(F_dptr), _vp(iters_dptr)))
+
+
+Frontend.reject_with_f = _frontend_reject_with_f
 
 
 def _frontend_undistort_points(self, cam, n_frames, out_dptr):

@@ -80,6 +80,7 @@ struct tb_ctx {
     struct WinWs *wws = nullptr;     // batched windowed-matcher workspace (window.cu)
     struct IngestWs *iws = nullptr;  // CLAHE tile LUTs (ingest.cu)
     struct FlowWs *fws = nullptr;    // LK pyramids + pair descriptors (flow.cu)
+    struct RfWs *rfws = nullptr;     // rejectWithF: pair descriptors + compacted tracks (fundam.cu)
     int match_impl = 1;              // 1 = tcgen05 int8 (K8, the default), 0 = LOP3+POPC (K7)
     DevArena arena;                  // scratch of the host-facing entry points
     StageRing stage;                 // pinned staging of small host tables
@@ -107,6 +108,7 @@ void tb_match_tc_free(tb_ctx *ctx);
 void tb_window_ws_free(tb_ctx *ctx);
 void tb_ingest_ws_free(tb_ctx *ctx);
 void tb_flow_ws_free(tb_ctx *ctx);
+void tb_fund_ws_free(tb_ctx *ctx);
 
 static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "")
 {

@@ -41,7 +41,7 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
         delete c;
         return TB_E_CUDA;
     }
-    tb_fast_init_device(); tb_octree_init_device(); tb_pyramid_init_device(); tb_match_tc_init_device(); tb_describe_init_device();
+    tb_fast_init_device(); tb_fund_init_device(); tb_octree_init_device(); tb_pyramid_init_device(); tb_match_tc_init_device(); tb_describe_init_device();
     tb_window_init_device(); tb_flow_init_device();
     *out = c;
     return TB_OK;
@@ -55,6 +55,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     tb_window_ws_free(ctx);
     tb_ingest_ws_free(ctx);
     tb_flow_ws_free(ctx);
+    tb_fund_ws_free(ctx);
     ctx->arena.destroy();
     ctx->stage.destroy();
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -845,4 +846,24 @@ extern "C" int tb_frontend_search_by_projection(tb_frontend *fe, const tb_matche
     return tb_window_projection_batched(fe->ctx, p, cam, n_pairs, f1_frames, f2_frames, Tcw1, fe->B, fe->kps, fe->desc, fe->kp_cap, fe->n_kp,
                                         (const uint8_t *)f1_matched, (const uint8_t *)mp_valid, (const float *)mp_xyz, sf1, fe->L,
                                         fe->g[0].w, fe->g[0].h, (tb_match *)matches, capacity, (int *)counts);
+}
+
+// Matcher::rejectWithF behind the flow entries (matcher.cpp:751-755, :853-881): "last" points = keypoints of the frame the tracks
+// started from (cv::KeyPoint: pt first, 28-byte stride)
+extern "C" int tb_frontend_reject_with_f(tb_frontend *fe, const tb_ransac_params *p, int n_pairs, const int32_t *f2_frames,
+                                         const void *next_pts, void *status, void *F_out, void *iters_out)
+{
+    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
+    if (!fe || !p || n_pairs < 0 || (n_pairs && (!f2_frames || !next_pts || !status))) return TB_E_INVALID;
+    std::vector<RfPairHost> hp(n_pairs);
+    for (int i = 0; i < n_pairs; i++) {
+        const int f = f2_frames[i];
+        if (f < 0 || f >= fe->B) return tb_fail(fe->ctx, TB_E_INVALID, "tb_frontend_reject_with_f: frame index out of range");
+        hp[i].cur = (const float *)next_pts + 2 * (size_t)i * fe->kp_cap;
+        hp[i].last = (const uint8_t *)(fe->kps + (size_t)f * fe->kp_cap);
+        hp[i].last_stride = (int)sizeof(tb_keypoint);
+        hp[i].count = fe->n_kp + f;
+        hp[i].status = (uint8_t *)status + (size_t)i * fe->kp_cap;
+    }
+    return tb_reject_with_f_batched(fe->ctx, p, n_pairs, hp, fe->kp_cap, (double *)F_out, (int32_t *)iters_out);
 }

@@ -104,6 +104,12 @@ int tb_undistort_width(const tb_undistort *u);
 int tb_undistort_height(const tb_undistort *u);
 // per-device kernel attributes (dynamic shared memory opt-in); called by tb_ctx_create for its device
 void tb_fast_init_device();
+void tb_fund_init_device();
+// rejectWithF (fundam.cu): one frame pair = tracked points, the points they came from (float2 at last + i * last_stride),
+// their number (device) and the status bytes that are updated in place
+struct RfPairHost { const float *cur; const uint8_t *last; int last_stride; const int32_t *count; uint8_t *status; };
+int tb_reject_with_f_batched(tb_ctx *ctx, const tb_ransac_params *p, int n_pairs, const std::vector<RfPairHost> &hp, int pts_cap,
+                             double *F_out, int32_t *iters_out);
 void tb_octree_init_device();
 void tb_pyramid_init_device();
 void tb_match_tc_init_device();
