@@ -12,8 +12,8 @@
 //     compared with threshold^2 as OpenCV does);
 //   * one thread replays OpenCV's loop over the chunk: best-so-far model, RANSACUpdateNumIters, stop at niters.
 // One CTA per frame pair, no host round trip; the models of the iterations past the stopping point are simply dropped.
-// The null space comes from a Jacobi eigen-decomposition of A^T A instead of OpenCV's SVD: the candidate models are the
-// members of the pencil spanned by the two null vectors with det = 0, which do not depend on the basis.
+// The null space comes from a Gram-Schmidt orthogonalisation of the seven rows (in registers) instead of OpenCV's SVD: the
+// candidate models are the members of the pencil spanned by the two null vectors with det = 0, which do not depend on the basis.
 // Inlier masks are identical to cv2 4.13 on every case tested (tests/test_gpu_flow.py, tests/test_oracle_cv2.py).
 #include "common.cuh"
 #include "kernels.cuh"
@@ -101,39 +101,80 @@ __device__ __noinline__ int rf_run7(const float2 *m1, const float2 *m2, double *
     scale1 *= t; scale2 *= t;
     if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return 0;
     scale1 = sqrt(2.) / scale1; scale2 = sqrt(2.) / scale2;
-    // M = A^T A of the 7 x 9 system (m2[i], 1)^T F (m1[i], 1) = 0 on the normalised points
-    double M[9][9], V[9][9];
-    for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) { M[a][b] = 0; V[a][b] = a == b; }
+    // rows of the 7 x 9 system (m2[i], 1)^T F (m1[i], 1) = 0 on the normalised points, orthonormalised in registers (modified
+    // Gram-Schmidt, every row twice): all loops are unrolled and no array is indexed dynamically, so nothing lives in local
+    // memory (a Jacobi sweep over A^T A there cost milliseconds per round of 32 hypotheses)
+    double A[7][9];
+#pragma unroll
     for (int i = 0; i < 7; i++) {
         const double x0 = (m1[i].x - c1x) * scale1, y0 = (m1[i].y - c1y) * scale1;
         const double x1 = (m2[i].x - c2x) * scale2, y1 = (m2[i].y - c2y) * scale2;
-        const double r[9] = {x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1};
-        for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) M[a][b] += r[a] * r[b];
+        A[i][0] = x1 * x0; A[i][1] = x1 * y0; A[i][2] = x1; A[i][3] = y1 * x0; A[i][4] = y1 * y0; A[i][5] = y1; A[i][6] = x0; A[i][7] = y0; A[i][8] = 1;
     }
-    // cyclic Jacobi: the eigenvectors of the two smallest eigenvalues span the null space
-#pragma unroll 1
-    for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0;
-        for (int p = 0; p < 9; p++) for (int q = p + 1; q < 9; q++) off += M[p][q] * M[p][q];
-        if (off < 1e-300) break;
-#pragma unroll 1
-        for (int p = 0; p < 9; p++)
-#pragma unroll 1
-        for (int q = p + 1; q < 9; q++) {
-            if (fabs(M[p][q]) < 1e-300) continue;
-            const double theta = (M[q][q] - M[p][p]) / (2 * M[p][q]);
-            const double tt = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
-            const double c = 1 / sqrt(tt * tt + 1), s = tt * c;
-            for (int k = 0; k < 9; k++) { const double a = M[k][p], b = M[k][q]; M[k][p] = c * a - s * b; M[k][q] = s * a + c * b; }
-            for (int k = 0; k < 9; k++) { const double a = M[p][k], b = M[q][k]; M[p][k] = c * a - s * b; M[q][k] = s * a + c * b; }
-            for (int k = 0; k < 9; k++) { const double a = V[k][p], b = V[k][q]; V[k][p] = c * a - s * b; V[k][q] = s * a + c * b; }
-        }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++)
+#pragma unroll
+            for (int j = 0; j < i; j++) {
+                double d = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) d += A[j][k] * A[i][k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) A[i][k] -= d * A[j][k];
+            }
+        double nn = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) nn += A[i][k] * A[i][k];
+        const double inv = nn > 1e-280 ? 1. / sqrt(nn) : 0.;     // a dependent row drops out (the null space is then larger than 2)
+#pragma unroll
+        for (int k = 0; k < 9; k++) A[i][k] *= inv;
     }
-    int i1 = 0, i2 = -1;
-    for (int i = 1; i < 9; i++) if (M[i][i] < M[i1][i1]) i1 = i;
-    for (int i = 0; i < 9; i++) if (i != i1 && (i2 < 0 || M[i][i] < M[i2][i2])) i2 = i;
+    // two orthonormal vectors of the complement: project the unit vector that sticks out most, twice
     double f1[9], f2[9], c[4], r[3] = {0, 0, 0};
-    for (int k = 0; k < 9; k++) { f1[k] = V[k][i2]; f2[k] = V[k][i1]; }
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+        double res[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            double q = 1.;
+#pragma unroll
+            for (int i = 0; i < 7; i++) q -= A[i][k] * A[i][k];
+            if (which == 1) q -= f2[k] * f2[k];
+            res[k] = q;
+        }
+        int km = 0;
+        double best = res[0];
+#pragma unroll
+        for (int k = 1; k < 9; k++) if (res[k] > best) { best = res[k]; km = k; }
+        double v[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k] = k == km ? 1. : 0.;
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                double d = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) d += A[i][k] * v[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) v[k] -= d * A[i][k];
+            }
+            if (which == 1) {
+                double d = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) d += f2[k] * v[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) v[k] -= d * f2[k];
+            }
+        }
+        double nn = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) nn += v[k] * v[k];
+        const double inv = 1. / sqrt(nn);
+#pragma unroll
+        for (int k = 0; k < 9; k++) { if (which == 0) f2[k] = v[k] * inv; else f1[k] = v[k] * inv; }
+    }
     // det(lambda * f1 + (1 - lambda) * f2) = 0
     for (int i = 0; i < 9; i++) f1[i] -= f2[i];
     double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
@@ -183,7 +224,7 @@ __device__ __noinline__ int rf_update_iters(double p, double ep, int max_iters)
 
 extern __shared__ __align__(16) uint8_t rf_smem[];
 
-__global__ void __launch_bounds__(RF_THREADS, 2)
+__global__ void __launch_bounds__(RF_THREADS, 1)
 reject_with_f(const RfPair *__restrict__ pairs, float thr2, double confidence, int max_iters, int pts_cap, float2 *__restrict__ scratch_m,
               int32_t *__restrict__ scratch_id, double *__restrict__ F_out, int32_t *__restrict__ iters_out)
 {
