@@ -338,6 +338,21 @@ def extras_block(torch, dist, tb, local_rank, world, rank, a):
         ms = timed(ck, 10)
         out['kitti_size_stream'] = {'workload': 'synthetic 1241x376 frame stream, 2000 kpts/frame, extract + frame-to-frame match, batch 256',
                                     'ms_per_step': ms, 'frames_per_s': Bk * 1e3 / ms}
+        # ---- the same stream through Matcher::searchByOPFlow(F_{k+1}, F_k, pts, equalized = true, reject = true), the call of
+        #      test_vo.cpp:716 / LocalBA.cpp:54: CLAHE + pyramidal LK + IsInFrame filter + rejectWithF (RANSAC), 255 pairs per step
+        pts = torch.zeros((Bk - 1, cap, 2), dtype=torch.float32, device='cuda')
+        stt = torch.zeros((Bk - 1, cap), dtype=torch.uint8, device='cuda')
+        itr = torch.zeros(Bk - 1, dtype=torch.int32, device='cuda')
+        lkp = tb.LKParams()
+
+        def cf():
+            fe.search_by_opflow(lkp, Bk, tf, qf, 1, pts.data_ptr(), stt.data_ptr())
+            fe.reject_with_f(qf, pts.data_ptr(), stt.data_ptr(), None, itr.data_ptr())
+        ms = timed(cf, 10)
+        out['opflow_reject'] = {'workload': 'searchByOPFlow(equalized, reject = true) over the %d consecutive pairs of that stream: CLAHE + LK 21x21 / 3 levels + IsInFrame + rejectWithF' % (Bk - 1),
+                                'ms_per_step': ms, 'pairs_per_s': (Bk - 1) * 1e3 / ms, 'tracks_kept_per_pair': float(stt.float().sum().item() / (Bk - 1)),
+                                'mean_ransac_iterations': float(itr.float().mean().item())}
+        del pts, stt, itr
         fe.close()
         del m, c, dv, dx
     # ---- config 5: 4K, 8 streams x 4 frames, extract 2000 + projection-guided match to the previous frame of the stream;
