@@ -72,6 +72,29 @@ def test_knn2_vs_oracle(tb, ctx, oracle, nq, nt, impl):
     assert np.array_equal(idx.cpu().numpy(), io) and np.array_equal(best.cpu().numpy(), bo) and np.array_equal(second.cpu().numpy(), so)
 
 
+def test_knn2_sliced_train_set(tb, ctx, oracle):
+    """A query count that leaves the SMs half empty (25 000 rows = 196 CTAs, a rank's share of config 4 on 8 GPUs) makes the
+    tensor-core kNN-2 slice the train set and merge the partial results: same (argbest, best, second) as the oracle, with
+    duplicated train rows across the slice boundaries so that the lowest-index tie-break is exercised."""
+    nq, nt = 25000, 12288 + 37
+    rng = np.random.default_rng(3)
+    q, t = _rand_desc(rng, nq, nt)
+    t[4096:4096 + 50] = t[100:150]          # exact duplicates in a later slice: the earlier row must win
+    t[8200:8230] = t[4100:4130]
+    q[:300] = t[rng.integers(0, nt, 300)]   # queries with distance 0 somewhere
+    ctx.set_match_impl(1)
+    tq, tt = dev(q), dev(t)
+    idx = torch.empty(nq, dtype=torch.int32, device='cuda')
+    best = torch.empty_like(idx)
+    second = torch.empty_like(idx)
+    ctx.knn2_device(tq.data_ptr(), nq, tt.data_ptr(), nt, idx.data_ptr(), best.data_ptr(), second.data_ptr())
+    torch.cuda.synchronize()
+    ctx.set_match_impl(0)
+    io, bo, so = oracle.knn2(q, t)
+    so = np.where(so == np.iinfo(np.int32).max, 0x7fffffff, so)
+    assert np.array_equal(idx.cpu().numpy(), io) and np.array_equal(best.cpu().numpy(), bo) and np.array_equal(second.cpu().numpy(), so)
+
+
 def test_knn2_large_properties(tb, ctx):
     """Config-4 shaped data at 20k x 20k: planted pairs are found, result is invariant to a train permutation."""
     from trackingbench_slam_b200.synth import synth_descriptors

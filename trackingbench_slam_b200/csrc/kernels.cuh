@@ -70,7 +70,10 @@ struct PairDesc {
 };
 #define TB_TC_MIN_ROWS 256   // single-pair searchByBF takes the tensor-core kernel from this many rows on (one full 256-row CTA)
 int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_cap, int *best_idx, int *best_dist);
-int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pair, int nq, int *idx, int *best, int *second);
+int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pairs, int nq, int n_splits, int *idx, int *best, int *second);
+int tb_knn2_tc_splits(int nq, int nt, int num_sms);
+int tb_knn2_tc_merge(tb_ctx *ctx, const int *p_idx, const int *p_best, const int *p_second, int nq, int n_splits, int rows_per_split,
+                     int *idx, int *best, int *second);
 int tb_match_bf_batched(tb_ctx *ctx, int n_pairs, const int32_t *q_frames_host, const int32_t *t_frames_host, int n_frames_total,
                         const uint8_t *desc, size_t frame_stride, const int *counts, int kp_cap,
                         float ratio, float minTh, tb_match *matches, int capacity, int *out_counts);

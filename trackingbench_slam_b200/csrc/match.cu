@@ -229,8 +229,25 @@ extern "C" int tb_knn2_device(tb_ctx *ctx, const void *q, int nq, const void *t,
     if (rc) return rc;
     MatchWs &w = ws_of(ctx);
     PairDesc pd = {(const uint8_t *)q, (const uint8_t *)t, nq, nt};
+    if (ctx->match_impl == 1 && nt > 0) {
+        // the train set in slices where that fills the SMs better (config 4 sharded over 8 GPUs: 196 CTAs for 148 SMs)
+        static const int forced = getenv("TB_KNN_SPLITS") ? atoi(getenv("TB_KNN_SPLITS")) : 0;
+        const int S = forced > 0 ? std::min(forced, 8) : tb_knn2_tc_splits(nq, nt, ctx->num_sms);
+        if (S <= 1) {
+            if ((rc = tb_stage_upload(ctx, w.pairs, &pd, sizeof pd))) return rc;
+            return tb_knn2_tc(ctx, w.pairs, nq, 1, (int *)idx, (int *)best, (int *)second);
+        }
+        if ((rc = ws_reserve(ctx, 8, (size_t)S * nq))) return rc;
+        const int rows = (div_up(nt, S) + 127) & ~127;            // slices start at multiples of the tile height
+        PairDesc ps[8];
+        int used = 0;
+        for (int s = 0; s < S && s * rows < nt; s++, used++)
+            ps[s] = PairDesc{(const uint8_t *)q, (const uint8_t *)t + (size_t)s * rows * 32, nq, std::min(rows, nt - s * rows)};
+        if ((rc = tb_stage_upload(ctx, w.pairs, ps, sizeof(PairDesc) * used))) return rc;
+        if ((rc = tb_knn2_tc(ctx, w.pairs, nq, used, w.best_idx, w.best_dist, w.second))) return rc;
+        return tb_knn2_tc_merge(ctx, w.best_idx, w.best_dist, w.second, nq, used, rows, (int *)idx, (int *)best, (int *)second);
+    }
     if ((rc = tb_stage_upload(ctx, w.pairs, &pd, sizeof pd))) return rc;
-    if (ctx->match_impl == 1 && nt > 0) return tb_knn2_tc(ctx, w.pairs, nq, (int *)idx, (int *)best, (int *)second);
     dim3 grid(div_up(nq, KNN_THREADS), 1);
     ProfScope prof__(ctx, "hamming_knn");
     hamming_knn<true><<<grid, KNN_THREADS, 0, ctx->stream>>>(w.pairs, 0, (int *)idx, (int *)best, (int *)second);

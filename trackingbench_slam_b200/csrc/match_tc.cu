@@ -480,11 +480,47 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_ca
 }
 
 // best / second / argbest of nq query rows against nt train rows (tb_knn2_device with the tensor-core matcher);
-// d_pair = one PairDesc {q, t, nq, nt} already on the device
-int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pair, int nq, int *idx, int *best, int *second)
+// d_pairs = n_splits PairDesc {q, t + split offset, nq, rows of the split} already on the device: split s writes its partial
+// result to idx / best / second + s * nq (n_splits == 1: the final arrays)
+int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pairs, int nq, int n_splits, int *idx, int *best, int *second)
 {
     ProfScope prof__(ctx, "hamming_i8mma");
-    hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), 1), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pair, 0, idx, best, second);
+    hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), n_splits), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, nq, idx, best, second);
+    TB_LAUNCH_CHECK(ctx);
+    return TB_OK;
+}
+// How many slices of the train set make the launch fill whole waves of one 128-row CTA per SM: 25 000 query rows (a rank's
+// share of config 4 on 8 GPUs) are 196 CTAs = 1.3 waves on 148 SMs; three slices make it 3.97 waves of a third of the length.
+int tb_knn2_tc_splits(int nq, int nt, int num_sms)
+{
+    const int ctas = div_up(nq, TC_M);
+    int best_s = 1;
+    double best_cost = (double)div_up(ctas, num_sms);
+    for (int s = 2; s <= 8; s++) {
+        if (nt / s < 4096) break;
+        const double cost = (double)div_up(ctas * s, num_sms) / s;
+        if (cost < best_cost * 0.9) { best_cost = cost; best_s = s; }   // a slice more costs a query expansion per CTA and the merge
+    }
+    return best_s;
+}
+__global__ void knn2_merge_splits(const int *__restrict__ p_idx, const int *__restrict__ p_best, const int *__restrict__ p_second, int nq, int n_splits,
+                                  int rows_per_split, int *__restrict__ idx, int *__restrict__ best, int *__restrict__ second)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nq) return;
+    int bi = -1, bd = 0x7fffffff, sd = 0x7fffffff;
+    for (int s = 0; s < n_splits; s++) {                          // slices in index order: the earlier one wins ties
+        const int i = p_idx[(size_t)s * nq + r], d = p_best[(size_t)s * nq + r], d2 = p_second[(size_t)s * nq + r];
+        if (i < 0) continue;
+        if (d < bd) { sd = min(bd, d2); bd = d; bi = i + s * rows_per_split; }
+        else sd = min(sd, d);
+    }
+    idx[r] = bi; best[r] = bd; second[r] = sd;
+}
+int tb_knn2_tc_merge(tb_ctx *ctx, const int *p_idx, const int *p_best, const int *p_second, int nq, int n_splits, int rows_per_split,
+                     int *idx, int *best, int *second)
+{
+    knn2_merge_splits<<<div_up(nq, 256), 256, 0, ctx->stream>>>(p_idx, p_best, p_second, nq, n_splits, rows_per_split, idx, best, second);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
