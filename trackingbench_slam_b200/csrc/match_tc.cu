@@ -67,6 +67,25 @@ __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
 }
+// a quarter of a train row (tiles of 32 local rows: four expander threads per row): descriptor bytes 8 * part .. + 7 = chunks
+// 4 * part .. + 3
+__device__ __forceinline__ void expand_quarter_lut(uint8_t *tile, int r, int part, const uint2 d, bool valid, const uint2 *lut)
+{
+    uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16 + (size_t)part * 4 * 128;
+    if (!valid) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(o + c * 128) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint32_t w32[2] = {d.x, d.y};
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        const uint32_t x = w32[w];
+        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
+    }
+}
 // chunks 16 and 17 of row r (element 256 = tie-break key 31 - r % 32, elements 257..287 = 0) do not depend on the tile (tiles
 // start at multiples of 32 rows): written once per ring stage when the CTA starts
 __device__ __forceinline__ void write_key_chunks(uint8_t *tile, int r, bool key, bool zero)
@@ -152,6 +171,54 @@ __device__ __forceinline__ bool elect_one()
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// ---- CTA pair (cta_group::2): barrier of the leader CTA (rank 0 of the cluster) addressed from either CTA
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG> __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+    if (CG == 1) { mbar_arrive(bar); return; }
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(raddr) : "r"(smem_u32(bar)));
+    // default semantics (.release at CTA scope): a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR in front of every
+    // arrival (ncu: 19 % of the stall samples); the data the leader's MMAs read was already handed to the async proxy by
+    // fence.proxy.async, and TMEM reads are ordered by the tcgen05 fences
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// wait on a barrier that threads of the peer CTA arrive on as well
+template <int CG> __device__ __forceinline__ void mbar_wait_cg(uint64_t *bar, uint32_t parity)
+{
+    if (CG == 1) { mbar_wait(bar, parity); return; }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <int CG> __device__ __forceinline__ void tc_commit_cg(uint64_t *bar)
+{
+    if (CG == 1) { tc_commit(bar); return; }
+    // the arrival lands on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mma_i8_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // A operand from tensor memory (lane = row, 4 int8 per 32-bit column), B from shared memory
 __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -163,7 +230,7 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint
 }
 
 struct __align__(16) TcShared {
-    uint64_t fullA, full[TC_NSB_MAX], empty[TC_NSB_MAX], tfull[2][TC_MB_MAX], tempty[2][TC_MB_MAX];   // [TMEM stage][M block]
+    uint64_t fullA, full[TC_NSB_MAX], empty[TC_NSB_MAX], tfull[3][TC_MB_MAX], tempty[3][TC_MB_MAX];   // [TMEM stage][M block]
     uint32_t tmem_base;
     int part_best[TC_M], part_second[TC_M], part_idx[TC_M];   // MB = 1: partial results of the upper-half-column warps
 };
@@ -171,21 +238,33 @@ struct __align__(16) TcShared {
 #define TC_SMEM_BYTES (144 * 1024 + TC_LUT_BYTES + sizeof(TcShared) + 64)   // train ring: MB = 1: 4 x 36 KB; MB = 2: 6 x 18 KB; + table
 extern __shared__ __align__(1024) uint8_t tc_smem[];
 
-template <bool SECOND, int MB>
+// CG = 2: a CTA PAIR (cluster of two, cta_group::2) shares every train tile.  Each CTA keeps its own MB query blocks in its own
+// tensor memory and expands only HALF of the tile's rows into its own shared memory; the tcgen05.mma of the pair (issued by
+// the leader CTA's threads, M = 256) feeds both tensor cores with both halves, and each CTA's accumulators cover all TN
+// columns.  Per SM that halves the expansion work and the shared-memory reads of the train operand — the pipe that bound the
+// single-CTA kernel (84 % busy at a 69 % busy tensor pipe).  Barriers the peer CTA has to signal (query blocks written, tile
+// half expanded, accumulator read) live in the leader's shared memory and are reached with mapa + a cluster-scope arrive;
+// completion of the MMAs is multicast to both CTAs by tcgen05.commit.
+template <bool SECOND, int MB, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restrict__ best_idx, int *__restrict__ best_dist,
               int *__restrict__ second_dist)
 {
     const PairDesc pd = pairs[blockIdx.y];
     constexpr int TC_ROWS = TC_M * MB;
-    constexpr int TN = MB == 1 ? 128 : 64;             // train rows per tile
-    constexpr int TB_BYTES = TN * TC_KB;
+    constexpr int TN = MB == 1 ? 128 : 64;             // train rows per tile (columns of an accumulator)
+    constexpr int TL = TN / CG;                        // of which this CTA expands and holds TL
+    constexpr int TB_BYTES = TL * TC_KB;
     constexpr int NSB = MB == 1 ? 4 : 6;               // shared-memory stages of the train ring (the expanders run ahead of the MMAs)
-    constexpr int DCOLS = 2 * MB * TN;                 // TMEM: accumulators = 2 stages x MB blocks x TN columns, then MB query blocks
-    constexpr int PARTS = TC_EXP_THREADS / TN;         // expander threads per train row (1 or 2)
+    constexpr int TS = (MB == 1 && CG == 2) ? 3 : 2;   // accumulator stages: a pair's hand-shakes cross the SM boundary twice per tile
+                                                       // (tile expanded, accumulator read), a third stage hides that where TMEM has room
+    constexpr int DCOLS = TS * MB * TN;                // TMEM: accumulators = TS stages x MB blocks x TN columns, then MB query blocks
+    constexpr int PARTS = TC_EXP_THREADS / TL;         // expander threads per train row (1, 2 or 4)
     static_assert(DCOLS + MB * TC_ACOLS <= 512 && NSB <= TC_NSB_MAX && NSB * TB_BYTES <= 144 * 1024, "TMEM / shared-memory budget");
+    static_assert(PARTS == 1 || PARTS == 2 || PARTS == 4, "expander threads per row");
     const int q0 = blockIdx.x * TC_ROWS;
-    if (q0 >= pd.nq) return;
+    if ((int)(blockIdx.x / CG) * CG * TC_ROWS >= pd.nq) return;   // the whole pair has no query row (a lone CTA of a pair still expands its half)
+    const uint32_t rank = CG > 1 ? cluster_rank() : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *sB = tc_smem;                                  // NSB stages of TN rows
     uint2 *lut = reinterpret_cast<uint2 *>(tc_smem + NSB * TB_BYTES);
@@ -193,15 +272,21 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
     const int NT = (pd.nt + TN - 1) / TN;
 
     if (threadIdx.x == 0) {
-        mbar_init(&S->fullA, 8);
-        for (int s = 0; s < NSB; s++) { mbar_init(&S->full[s], TC_EXP_THREADS); mbar_init(&S->empty[s], MB); }   // one commit per issuer
-        for (int s = 0; s < 2; s++)
-            for (int b = 0; b < MB; b++) { mbar_init(&S->tfull[s][b], 1); mbar_init(&S->tempty[s][b], 4); }   // the four epilogue warps that read this accumulator
+        // fullA / full / tempty collect arrivals from both CTAs of a pair (only the leader's copies are used then)
+        mbar_init(&S->fullA, 8 * CG);
+        for (int s = 0; s < NSB; s++) { mbar_init(&S->full[s], (TC_EXP_THREADS / 32) * CG); mbar_init(&S->empty[s], MB); }   // one commit per issuer
+        for (int s = 0; s < TS; s++)
+            for (int b = 0; b < MB; b++) { mbar_init(&S->tfull[s][b], 1); mbar_init(&S->tempty[s][b], (8 / MB) * CG); }   // the epilogue warps that read this accumulator
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {   // TMEM: 512 columns (accumulators + the query blocks)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     // global loads that the roles need first are issued before the prologue's barrier (table build, TMEM allocation):
     // expanders: the descriptors of the first TC_PF train tiles; epilogue warps: their query row
@@ -209,16 +294,17 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
     const int eg = (warp - TC_EXP_WARP0) >> 2;            // expander group: tiles t = eg mod 2 (a tile's LDS -> STS chains leave the
                                                           // warp waiting most of the time; two groups keep two tiles in the works)
     const int et = threadIdx.x - 32 * TC_EXP_WARP0 - eg * TC_EXP_THREADS;
-    const int r = et & (TN - 1), part = et / TN;          // PARTS = 2: two expander threads share a row (16 descriptor bytes each)
+    const int r = et & (TL - 1), part = et / TL;          // PARTS = 2 / 4: two / four expander threads share a row (16 / 8 descriptor bytes each)
     const uint4 *tq = reinterpret_cast<const uint4 *>(pd.t);
     uint4 lo[TC_PF], hi[TC_PF];
 #pragma unroll
     for (int i = 0; i < TC_PF; i++) lo[i] = hi[i] = make_uint4(0, 0, 0, 0);
     auto fetch = [&](int t, uint4 &l, uint4 &h) {
-        const int row = t * TN + r;
+        const int row = t * TN + (int)rank * TL + r;      // this CTA's part of the tile
         if (t < NT && row < pd.nt) {
             if (PARTS == 1) { l = __ldg(tq + 2 * (size_t)row); h = __ldg(tq + 2 * (size_t)row + 1); }
-            else l = __ldg(tq + 2 * (size_t)row + part);
+            else if (PARTS == 2) l = __ldg(tq + 2 * (size_t)row + part);
+            else { const uint2 d = __ldg(reinterpret_cast<const uint2 *>(tq) + 4 * (size_t)row + part); l.x = d.x; l.y = d.y; }
         }
     };
     const int e_lane_base = 32 * (warp & 3), e_grp = (warp - TC_EPI_WARP0) >> 2, e_mb = MB > 1 ? e_grp : 0;
@@ -238,7 +324,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
         lut[i] = make_uint2(0x01010101u + 0xFEu * b0, 0x01010101u + 0xFEu * b1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CG == 1) __syncthreads(); else cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = S->tmem_base;
     int best = -1000, second = -1000, bidx = -1;   // running (max dot, second, arg) of an epilogue thread
@@ -251,39 +337,48 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
             const int s = t % NSB, ph = (t / NSB) & 1;
             mbar_wait(&S->empty[s], ph ^ 1);
             uint8_t *tile = sB + s * TB_BYTES;
-            if (PARTS == 1) expand_row_lut(tile, r, lo[0], hi[0], t * TN + r < pd.nt, lut + (lane & 15));
-            else expand_half_lut(tile, r, part, lo[0], t * TN + r < pd.nt, lut + (lane & 15));
+            const bool rv = t * TN + (int)rank * TL + r < pd.nt;
+            if (PARTS == 1) expand_row_lut(tile, r, lo[0], hi[0], rv, lut + (lane & 15));
+            else if (PARTS == 2) expand_half_lut(tile, r, part, lo[0], rv, lut + (lane & 15));
+            else expand_quarter_lut(tile, r, part, make_uint2(lo[0].x, lo[0].y), rv, lut + (lane & 15));
 #pragma unroll
             for (int i = 0; i + 1 < TC_PF; i++) { lo[i] = lo[i + 1]; hi[i] = hi[i + 1]; }
             fetch(t + 2 * TC_PF, lo[TC_PF - 1], hi[TC_PF - 1]);   // in flight while the next tiles are expanded
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
-            mbar_arrive(&S->full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader<CG>(&S->full[s]);            // one (for the peer CTA: remote) arrival per warp
         }
-    } else if (warp < 2 * MB) {
-        if (elect_one()) {
+    } else if (warp < (MB == 1 ? 1 : 2 * MB)) {
+        if (rank == 0 && elect_one()) {
             // ---- MMA issuers.  A single thread gets a tcgen05.mma out every ~120 cycles (ncu: the issuing warp never waits
             //      on a barrier; every instruction needs ~9 dependent uniform-datapath instructions of set-up), while an
             //      M128 x N x K32 int8 step runs N/2 cycles on the tensor pipe.  So the tiles are dealt to 2 * MB issuing
             //      threads: thread (block mbi, parity par) issues the nine K steps of block mbi for the tiles t = par mod 2
-            //      into TMEM stage par; accumulators of different threads are disjoint, so no ordering between them is needed.
+            //      into TMEM stage t mod TS; tiles of different threads use different accumulators or are ordered by tempty.
             // idesc = D s32 | A s8 | B s8 | K-major both | N = TN | M = 128
+            // (MB = 1: one thread issues every tile — with more than two accumulator stages a stage is no longer tied to a tile
+            // parity, and a parity wait is only safe for a waiter that sees every phase of its barrier)
             const int mbi = warp % MB, par = warp / MB;
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-            mbar_wait(&S->fullA, 0);
+            constexpr int TSTEP = MB == 1 ? 1 : 2;
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((TC_M * CG) >> 4) << 24);
+            mbar_wait_cg<CG>(&S->fullA, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int t = par; t < NT; t += 2) {
+            for (int t = par; t < NT; t += TSTEP) {
                 const int s = t % NSB, ph = (t / NSB) & 1;      // shared-memory stage
-                const int tph = (t >> 1) & 1;                   // phase of TMEM stage par
-                mbar_wait(&S->full[s], ph);
-                mbar_wait(&S->tempty[par][mbi], tph ^ 1);
+                const int ts = t % TS, tph = (t / TS) & 1;      // TMEM stage and its phase
+                mbar_wait_cg<CG>(&S->full[s], ph);
+                mbar_wait_cg<CG>(&S->tempty[ts][mbi], tph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t bdesc = make_desc(smem_u32(sB + s * TB_BYTES));
 #pragma unroll
-                for (int k = 0; k < TC_KB / 32; k++)   // K step = 32 int8 = 8 TMEM columns of A = two 16-byte core-matrix columns (256 B) of B
-                    mma_i8_ts(tmem + (uint32_t)((par * MB + mbi) * TN), tmem + (uint32_t)(DCOLS + mbi * TC_ACOLS + 8 * k),
-                              bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
-                tc_commit(&S->empty[s]);          // shared-memory stage reusable once the MMAs of every block retire
-                tc_commit(&S->tfull[par][mbi]);   // accumulator ready for the epilogue
+                for (int k = 0; k < TC_KB / 32; k++) {   // K step = 32 int8 = 8 TMEM columns of A = two 16-byte core-matrix columns (256 B) of B
+                    if (CG == 1) mma_i8_ts(tmem + (uint32_t)((ts * MB + mbi) * TN), tmem + (uint32_t)(DCOLS + mbi * TC_ACOLS + 8 * k),
+                                           bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                    else mma_i8_ts2(tmem + (uint32_t)((ts * MB + mbi) * TN), tmem + (uint32_t)(DCOLS + mbi * TC_ACOLS + 8 * k),
+                                    bdesc + (uint64_t)((k * 256) >> 4), idesc, k > 0 ? 1u : 0u);
+                }
+                tc_commit_cg<CG>(&S->empty[s]);          // shared-memory stage reusable once the MMAs of every block retire
+                tc_commit_cg<CG>(&S->tfull[ts][mbi]);   // accumulator ready for the epilogue
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
@@ -321,19 +416,19 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S->fullA);
+            if (lane == 0) mbar_arrive_leader<CG>(&S->fullA);
         }
-        // MB = 2: the four warps of block mb read every tile (64 columns); MB = 1: the two warp groups alternate tiles (group =
-        // TMEM stage) and read all 128 columns as two loads.  An accumulator is released as soon as it sits in registers.
-        for (int t = (MB == 1 ? grp : 0); t < NT; t += (MB == 1 ? 2 : 1)) {
-            const int s = t & 1, ph = (t >> 1) & 1;
+        // MB = 2: the four warps of block mb read every tile (64 columns); MB = 1: both warp groups read every tile, 64 of its 128
+        // columns each (merged at the end).  An accumulator is released as soon as it sits in registers.
+        for (int t = 0; t < NT; t++) {
+            const int s = t % TS, ph = (t / TS) & 1;
             mbar_wait(&S->tfull[s][mb], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int col0 = t * TN;
-            const int nh = (MB == 1 && col0 + 64 < pd.nt) ? 2 : 1;
-#pragma unroll 1
-            for (int half = 0; half < nh; half++) {
-            const int cbeg = 64 * half;
+            constexpr int nh = 1;
+            {
+            constexpr int half = 0;
+            const int cbeg = MB == 1 ? 64 * grp : 0;
             // the warp's 64 columns of this tile with one tcgen05.ld (a load + wait per 32 columns cost ~85 cycles each)
             uint32_t vv[64];
             {
@@ -358,7 +453,7 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
             if (half == nh - 1) {   // the values are in registers: the issuer may overwrite this accumulator
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S->tempty[s][mb]);
+                if (lane == 0) mbar_arrive_leader<CG>(&S->tempty[s][mb]);
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -446,8 +541,11 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (CG == 1) __syncthreads(); else cluster_sync_all();   // nobody leaves while the peer may still read this CTA's tile halves or signal its barriers
+    if (warp == 0) {
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
     if (MB == 1 && warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
         // merge the two column halves (lowest index wins ties) and write the row's result
         const int r = 32 * (warp & 3) + lane, row = q0 + r;
@@ -467,14 +565,37 @@ hamming_i8mma(const PairDesc *__restrict__ pairs, int out_stride, int *__restric
 }
 
 // ------------------------------------------------------------------------------------------ host side
-void tb_match_tc_free(tb_ctx *) {}   // the tensor-core matcher keeps no workspace of its own any more (operands are expanded in the kernel)
+void tb_match_tc_free(tb_ctx *) {}
+
+// CTA pairs (cta_group::2) are the default for the kNN-2 problem (one M block per CTA: halving the expansion per SM is what
+// it needs; 200k x 200k 7.5 -> 6.9 ms); the batched frame-pair matcher already shares every tile between two M blocks of one
+// CTA and is faster that way (0.40 ms against 0.51 ms as pairs).  TB_MATCH_CG = 1 / 2 forces one form for both (A/B).
+static int tc_cta_group(bool knn2)
+{
+    static const int cg = getenv("TB_MATCH_CG") ? atoi(getenv("TB_MATCH_CG")) : 0;
+    return cg == 1 ? 1 : cg == 2 ? 2 : knn2 ? 2 : 1;
+}
+template <typename K, typename... Args>
+static cudaError_t launch_pairs(K kernel, dim3 grid, size_t smem, cudaStream_t st, Args... args)
+{
+    grid.x = (grid.x + 1) & ~1u;                                  // whole pairs; a CTA without query rows still expands its half
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}   // the tensor-core matcher keeps no workspace of its own any more (operands are expanded in the kernel)
 
 // Fills best_idx/best_dist[2P][kp_cap] exactly like hamming_knn<false> does for the same pair table (match.cu: build_pairs).
 int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_cap, int *best_idx, int *best_dist)
 {
     ProfScope prof__(ctx, "hamming_i8mma");
     dim3 grid(div_up(kp_cap, TC_M * 2), 2 * n_pairs);
-    hamming_i8mma<false, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, kp_cap, best_idx, best_dist, nullptr);
+    if (tc_cta_group(false) == 2)   // pairs: one M block per CTA, 128-row tiles, three accumulator stages
+        launch_pairs(hamming_i8mma<false, 1, 2>, dim3(div_up(kp_cap, TC_M), 2 * n_pairs), TC_SMEM_BYTES, ctx->stream, d_pairs, kp_cap, best_idx, best_dist, (int *)nullptr);
+    else hamming_i8mma<false, 2, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, kp_cap, best_idx, best_dist, nullptr);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
@@ -485,7 +606,8 @@ int tb_match_knn_tc(tb_ctx *ctx, int n_pairs, const PairDesc *d_pairs, int kp_ca
 int tb_knn2_tc(tb_ctx *ctx, const PairDesc *d_pairs, int nq, int n_splits, int *idx, int *best, int *second)
 {
     ProfScope prof__(ctx, "hamming_i8mma");
-    hamming_i8mma<true, 1><<<dim3(div_up(nq, TC_M), n_splits), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, nq, idx, best, second);
+    if (tc_cta_group(true) == 2) launch_pairs(hamming_i8mma<true, 1, 2>, dim3(div_up(nq, TC_M), n_splits), TC_SMEM_BYTES, ctx->stream, d_pairs, nq, idx, best, second);
+    else hamming_i8mma<true, 1, 1><<<dim3(div_up(nq, TC_M), n_splits), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(d_pairs, nq, idx, best, second);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }
@@ -528,6 +650,8 @@ int tb_knn2_tc_merge(tb_ctx *ctx, const int *p_idx, const int *p_best, const int
 void tb_match_tc_init_device()
 {
     const int smem = (int)(TC_SMEM_BYTES);
-    cudaFuncSetAttribute(hamming_i8mma<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(hamming_i8mma<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(hamming_i8mma<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
