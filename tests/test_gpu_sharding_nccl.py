@@ -48,9 +48,10 @@ def _worker(rank, world, port, n, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
-def test_row_sharded_knn_two_gpus():
+@pytest.mark.parametrize('n', [4099, 4096])   # unequal shards (padded list gather) and equal shards (one all_gather_into_tensor)
+def test_row_sharded_knn_two_gpus(n):
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), 4099, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n, ret), nprocs=2, join=True)
     assert ret.get('ok') is True
