@@ -50,6 +50,10 @@ __device__ __forceinline__ short4 oct_child_box(short4 b, int c)
     return r;
 }
 
+// The key sweeps are bound by the latency of cand[k] (L2, one dependent load per iteration — ncu: 35 % of the stall samples sit
+// on its first use): every sweep fetches OCT_MLP candidates per thread before it touches the first one.
+#define OCT_MLP 4
+
 // In-place exclusive scan of a[0..n) (shared memory); returns the total. All threads must call.
 __device__ int block_excl_scan(int *a, int n)
 {
@@ -158,11 +162,19 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         S.box[0][i] = b; S.cnt[0][i] = 0;
     }
     __syncthreads();
-    for (int k = tid; k < n; k += OCT_THREADS) {
-        int ni = (int)__fdiv_rn((float)cand_x(cand[k]), a.hX);
-        ni = min(ni, a.nIni - 1); // (the reference would index out of bounds; cannot happen for x < W)
-        nid[k] = (uint16_t)ni;
-        atomicAdd(&S.cnt[0][ni], 1);
+    for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
+        uint32_t cc[OCT_MLP];
+#pragma unroll
+        for (int j = 0; j < OCT_MLP; j++) { const int k = k0 + j * OCT_THREADS; cc[j] = k < n ? __ldg(&cand[k]) : 0u; }
+#pragma unroll
+        for (int j = 0; j < OCT_MLP; j++) {
+            const int k = k0 + j * OCT_THREADS;
+            if (k >= n) break;
+            int ni = (int)__fdiv_rn((float)cand_x(cc[j]), a.hX);
+            ni = min(ni, a.nIni - 1); // (the reference would index out of bounds; cannot happen for x < W)
+            nid[k] = (uint16_t)ni;
+            atomicAdd(&S.cnt[0][ni], 1);
+        }
     }
     for (int e = tid; e < NE; e += OCT_THREADS) enid[e] = 0;
     __syncthreads();
@@ -191,11 +203,16 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         const int *cnt = S.cnt[cur];
         for (int i = tid; i < 4 * L0; i += OCT_THREADS) V[i] = 0;
         __syncthreads();
-        for (int k = tid; k < n; k += OCT_THREADS) {
-            int ni = nid[k];
-            if (cnt[ni] > 1) {
-                uint32_t c = cand[k];
-                atomicAdd(&V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))], 1);
+        for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
+            uint32_t cc[OCT_MLP];
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) { const int k = k0 + j * OCT_THREADS; cc[j] = k < n ? __ldg(&cand[k]) : 0u; }
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) {
+                const int k = k0 + j * OCT_THREADS;
+                if (k >= n) break;
+                const int ni = nid[k];
+                if (cnt[ni] > 1) atomicAdd(&V[4 * ni + oct_child(box[ni], (float)cand_x(cc[j]), (float)cand_y(cc[j]))], 1);
             }
         }
         __syncthreads();
@@ -293,19 +310,22 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         // ---- (C) remap keys, and vote for the next pass in the same sweep
         for (int i = tid; i < 4 * newL; i += OCT_THREADS) W[i] = 0;
         __syncthreads();
-        for (int k = tid; k < n; k += OCT_THREADS) {
-            const int ni = nid[k];
-            uint32_t c = 0;
-            bool have = false;
-            int nn;
-            if (S.aux2[ni] > 0) {
-                c = cand[k]; have = true;
-                nn = V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))];
-            } else nn = S.aux[ni];
-            nid[k] = (uint16_t)nn;
-            if (ncnt[nn] > 1) {
-                if (!have) c = cand[k];
-                atomicAdd(&W[4 * nn + oct_child(nbox[nn], (float)cand_x(c), (float)cand_y(c))], 1);
+        for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
+            uint32_t cc[OCT_MLP];
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) { const int k = k0 + j * OCT_THREADS; cc[j] = k < n ? __ldg(&cand[k]) : 0u; }
+#pragma unroll
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) {
+                const int k = k0 + j * OCT_THREADS;
+                if (k >= n) break;
+                const int ni = nid[k];
+                const uint32_t c = cc[j];
+                int nn;
+                if (S.aux2[ni] > 0) nn = V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))];
+                else nn = S.aux[ni];
+                nid[k] = (uint16_t)nn;
+                if (ncnt[nn] > 1) atomicAdd(&W[4 * nn + oct_child(nbox[nn], (float)cand_x(c), (float)cand_y(c))], 1);
             }
         }
         for (int e = tid; e < NE; e += OCT_THREADS) {
@@ -340,13 +360,21 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
     const int L = s_L;
     for (int i = tid; i < L; i += OCT_THREADS) { S.skey[i] = 0; S.aux2[i] = 1; }
     __syncthreads();
-    for (int k = tid; k < n; k += OCT_THREADS) {
-        uint32_t c = cand[k];
-        int x = cand_x(c), y = cand_y(c);
-        unsigned long long ord = ((unsigned long long)((y - 3) / a.hCell) << 32) | ((unsigned long long)((x - 3) / a.wCell) << 24) |
-                                 ((unsigned long long)y << 12) | (unsigned long long)x;
-        unsigned long long key = ((unsigned long long)cand_m(c) << 40) | (~ord & 0xFFFFFFFFFFull);
-        atomicMax(&S.skey[nid[k]], key);
+    for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
+        uint32_t cc[OCT_MLP];
+#pragma unroll
+        for (int j = 0; j < OCT_MLP; j++) { const int k = k0 + j * OCT_THREADS; cc[j] = k < n ? __ldg(&cand[k]) : 0u; }
+#pragma unroll
+        for (int j = 0; j < OCT_MLP; j++) {
+            const int k = k0 + j * OCT_THREADS;
+            if (k >= n) break;
+            const uint32_t c = cc[j];
+            int x = cand_x(c), y = cand_y(c);
+            unsigned long long ord = ((unsigned long long)((y - 3) / a.hCell) << 32) | ((unsigned long long)((x - 3) / a.wCell) << 24) |
+                                     ((unsigned long long)y << 12) | (unsigned long long)x;
+            unsigned long long key = ((unsigned long long)cand_m(c) << 40) | (~ord & 0xFFFFFFFFFFull);
+            atomicMax(&S.skey[nid[k]], key);
+        }
     }
     __syncthreads();
     // exit-key exclusion (:718-729): 20-px radius around the winner, per leaf
