@@ -648,6 +648,15 @@ def run_ours(a):
         pair_evals = 2.0 * float((counts[:-1].astype(np.float64) * counts[1:].astype(np.float64)).sum())
         hamming = {'kernel': mk, 'pair_evaluations_per_step': pair_evals,
                    'Gpairs_per_s': pair_evals / (table[mk]['ms'] * 1e-3) / 1e9 if mk in table and table[mk]['ms'] > 0 else None}
+        try:   # tensor roofline of the int8 matcher: 512 int8 ops per pair (K = 256) against the measured tcgen05 int8 peak
+            pk = json.load(open(os.path.join(ROOT, 'profiles', 'r02_int8_peak.json')))
+            if mk == 'hamming_i8mma' and hamming['Gpairs_per_s']:
+                ach = hamming['Gpairs_per_s'] * 512 / 1e6
+                hamming['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['int8_dense_Pop_per_s'], 'unit': 'Pop/s (int8, dense)',
+                                       'frac': ach / pk['int8_dense_Pop_per_s'], 'peak_source': 'measured: scripts/imma_probe.cu, profiles/r02_int8_peak.json',
+                                       'note': 'the kernel multiplies K = 288 (the tie-break key rides in a ninth K step): tensor-pipe occupancy is frac * 288/256'}
+        except Exception:
+            pass
         if a.profile_out:
             json.dump({'per_kernel': table, 'step_ms_profiled': tot}, open(a.profile_out, 'w'), indent=1)
 
