@@ -237,6 +237,11 @@ def config4_block(torch, dist, ctx, world, rank, n, steps=3):
                'planted_found': int((b[:n // 2] < 60).sum()), 'spot_check_exact': bool(np.array_equal(spot, b[:2000])),
                'cross_check': {'ms': cross_ms, 'mutual_matches': int(mutual.sum().item()),
                                'what': 'both directions sharded by rows + two gathers + idx21[idx12[q]] == q'}}
+        try:   # kernel time against the measured int8 tensor peak of the GPUs used (512 int8 ops per pair at K = 256)
+            pk = json.load(open(os.path.join(ROOT, 'profiles', 'r02_int8_peak.json')))['int8_dense_Pop_per_s']
+            out['kernel_frac_of_int8_peak'] = float(n) * n * 512 / (kms * 1e-3) / 1e15 / (pk * world)
+        except Exception:
+            pass
     del q, t
     return out
 
