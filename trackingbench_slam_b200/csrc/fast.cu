@@ -140,36 +140,87 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 }
 
 // Pipeline of one CTA (G cells of one cell row), every stage on dense lanes:
-//   0  stage the u8 tile (+3-px halo) with 8-byte loads
+//   0  stage the u8 tile (+3-px halo) with 16-byte loads
 //   then, at T = initTh for every cell and again at T = minTh only for the cells that produced no
 //   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792) — stages 1-4 are fused per
 //   warp (private survivor queue, no block barrier in between):
-//   1+2  SWAR prefilter, 8 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
+//   1+2  SWAR prefilter, 16 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
 //      (N,E,S,W at radius 3) both brighter than centre+T or both darker than centre-T; per 4 px and
 //      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
-//   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map
-//   5  NMS inside the cell interior, emission with one global atomic per pass
+//   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map,
+//      corner appended to the warp's own list (warp-uniform counter in a register: no atomics)
+//   5  NMS inside the cell interior by the warp that found the corner, survivors written straight to the
+//      candidate array (one global atomic per warp and round)
+// The tile pitch is a compile-time constant: queue and list entries are byte offsets into the tile, the m map has the
+// tile's pitch (plus a zero row above and below), so ring and neighbour reads are LDS with immediate offsets from one
+// register.
 __device__ uint2 g_bitpos[256];   // set-bit positions of a byte (one byte each, lowest first), filled by tb_fast_init_device
 #define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
+#define FAST_TP TB_FAST_TPITCH
 struct FastSmem {
-    uint8_t *tile, *sc, *cellOf, *need;
-    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), block corner list (a.list_cap entries)
-    uint32_t *stage;           // NMS survivors staged for the single global reservation (<= cap/4 + 1 entries)
+    uint8_t *tile, *scp, *colInfo, *need;   // scp[o] = m of the pixel at tile offset o (0 = not a corner)
+    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), per-warp corner lists (8 x capW entries)
 };
 
+// NMS of one corner (tile offset o) + emission bookkeeping; returns keep and the packed candidate
+__device__ __forceinline__ bool fast_nms_one(const FastArgs &a, const FastSmem &S, const int o, const int T, const int hEff,
+                                             const int xbase, const int cand_y0, int *s_has, uint32_t &val)
+{
+    constexpr int tp = FAST_TP;
+    const uint8_t *q = S.scp + o;
+    const int m = q[0];
+    const int trow = (int)__umulhi((uint32_t)o, 0xFFFFFFFFu / tp + 1u);   // o / tp (o < 65536)
+    const int col = o - trow * tp;
+    const int info = S.colInfo[col];          // cell | has-left-neighbour << 6 | has-right-neighbour << 7 (inside the cell's ROI)
+    const int lmask = (info & 0x40) ? 0xFF : 0, rmask = (info & 0x80) ? 0xFF : 0;
+    // OpenCV's buffer holds m-1 for corners and 0 elsewhere: keep iff m-1 > max(m2-1, 0) for every neighbour inside the
+    // cell's ROI interior, i.e. m > (largest in-range neighbour) and, if there is any neighbour, m > 1. Rows above and
+    // below the interior are zero rows of the map.
+    const int n0 = q[-tp - 1] & lmask, n1 = q[-tp], n2 = q[-tp + 1] & rmask;
+    const int n3 = q[-1] & lmask, n4 = q[1] & rmask;
+    const int n5 = q[tp - 1] & lmask, n6 = q[tp], n7 = q[tp + 1] & rmask;
+    const int mx = max3i(max3i(n0, n1, n2), max3i(n3, n4, n5), max(n6, n7));
+    bool keep = m > mx;
+    if (T < 1) keep = keep && (m > 1 || !(trow > 3 || trow + 1 < hEff + 3 || (info & 0xC0)));
+    if (keep) {
+        s_has[info & 63] = 1;
+        val = cand_pack(xbase + col, cand_y0 + trow, m);   // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
+    }
+    return keep;
+}
+
+__device__ __forceinline__ void fast_emit(const FastArgs &a, const int f, const bool keep, const uint32_t val)
+{
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int pos = base + __popc(bal & ((1u << lane) - 1));
+    if (keep) {
+        if (pos < a.cand_cap) a.cand[(size_t)f * a.cand_cap + pos] = val;
+        else atomicExch(a.overflow, 1);
+    }
+}
+
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
-                                          const int hEff, const int wEff, const int cs, const int ce, const int tp,
-                                          const int cand_x0, const int cand_y0, int *s_cnt, int *s_has, int *s_base,
+                                          const int hEff, const int wEff, const int cs, const int capW,
+                                          const int xbase, const int cand_y0, int *s_has, int *s_ovf,
                                           const int col_lo, const int col_hi)   // interior columns [col_lo, col_hi) to test
 {
+    constexpr int tp = FAST_TP;
     const int tid = threadIdx.x;
-    uint8_t *tile = S.tile, *sc = S.sc;
-    uint16_t *listB = S.listB;
-    // ---- stages 1-4, fused per warp (no block barrier, no block-wide list): every warp prefilters 256 pixels
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint8_t *tile = S.tile;
+    uint8_t *scp = S.scp;
+    uint16_t *myList = S.listB + warp * capW;
+    int nCorn = 0;                                      // warp-uniform: corners this warp found in this pass
+    const unsigned ltmask = (1u << lane) - 1;
+    // ---- stages 1-4, fused per warp (no block barrier, no block-wide list): every warp prefilters 512 pixels
     //      per iteration (need[] holds 0x80 for the bytes this pass must test), pushes the survivors into its own
     //      shared-memory queue and, whenever 32 are waiting, scores them on dense lanes.
     {
-        const int lane = tid & 31, warp = tid >> 5;
         uint16_t *q = S.queue + warp * FAST_QCAP;
         int qn = 0;                                     // warp-uniform queue fill
         const bool swar = T <= 127;                     // larger thresholds skip the byte-SIMD test: everything is scored
@@ -177,29 +228,31 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         const int g0 = (cs + col_lo) >> 4, nG = ((cs + col_hi + 15) >> 4) - g0;      // 16-pixel groups
         const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
         const int items = hEff * nG;
-        // score 32 (or, for the final flush, fewer) queued pixels; corners go to the block's corner list
-        auto score_batch = [&](int e, bool valid) {
+        // score 32 (or, for the final flush, fewer) queued pixels; corners go to the warp's corner list
+        auto score_batch = [&](int o, bool valid) {
             bool corner = false;
             if (valid) {
-                const int rr = e >> 10, cc = e & 1023;
-                const int m = fast9_score_packed(tile + (rr + 3) * tp + cs + cc, tp);
+                const int m = fast9_score_packed(tile + o, tp);
                 corner = m > T;
-                if (corner) sc[rr * a.scw + cc] = (uint8_t)m;
+                if (corner) scp[o] = (uint8_t)m;
             }
-            const int pos = warp_append1(corner, &s_cnt[2]);
-            if (corner && pos < a.list_cap) listB[pos] = (uint16_t)e;
+            const unsigned bal = __ballot_sync(0xffffffffu, corner);
+            const int pos = nCorn + __popc(bal & ltmask);
+            if (corner && pos < capW) myList[pos] = (uint16_t)o;
+            nCorn += __popc(bal);
         };
         for (int base = 0; base < items; base += 256) {
             const int it = base + tid;
             uint32_t c[4] = {0, 0, 0, 0};
-            int r = 0, o = 0;
+            int e0 = 0;
             if (it < items) {
-                r = fast_div(it, magic);
-                o = 16 * (it - r * nG + g0);
+                const int r = fast_div(it, magic);
+                const int o = 16 * (it - r * nG + g0);
+                e0 = (r + 3) * tp + o;                   // tile offset of the group's first pixel
                 const uint4 nd = *reinterpret_cast<const uint4 *>(S.need + o);
                 if (nd.x | nd.y | nd.z | nd.w) {
                     if (swar) {
-                        const uint8_t *row = tile + (r + 3) * tp + o;
+                        const uint8_t *row = tile + e0;
                         const uint4 cen = *reinterpret_cast<const uint4 *>(row);
                         const uint4 up = *reinterpret_cast<const uint4 *>(row - 3 * tp);
                         const uint4 dn = *reinterpret_cast<const uint4 *>(row + 3 * tp);
@@ -224,7 +277,6 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             if (total == 0) continue;                    // nothing in this warp's 512 pixels
             if (cnt) {
                 // set-bit positions of each flag byte from a 256-entry table (eight 3-bit positions per entry)
-                const int e0 = (r << 10) + (o - cs);   // o - cs < 0 only for bytes that need[] dropped
                 uint16_t *qp = q + qn + inc - cnt;
                 const uint32_t lo = m16 & 0xFF, hi = m16 >> 8;
                 const uint2 tl = __ldg(&g_bitpos[lo]), th = __ldg(&g_bitpos[hi]);   // eight byte-wide positions each (2 KB, L1 resident)
@@ -250,61 +302,35 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             __syncwarp();                                // queue reads above happen before the next pushes
         }
         if (qn > 0) score_batch(lane < qn ? q[lane] : 0, lane < qn);
+        if (nCorn > capW && lane == 0) *s_ovf = 1;
     }
     __syncthreads();
-    const int nc = s_cnt[2];
-    // ---- stage 5: NMS inside the cell interior; survivors are staged for the global write.
-    // The corner list holds a.list_cap entries (a quarter of the tile's pixels: the list of ALL pixels cost 15 KB of shared
-    // memory and two resident CTAs per SM). If a tile ever has more corners, the m map is scanned instead: slower, same result.
-    uint32_t *stage = S.stage;
-    const bool listed = nc <= a.list_cap;
-    const int n_iter = listed ? nc : hEff * a.scw;
-    for (int base = 0; base < n_iter; base += 256) {
-        const int i = base + tid;
-        bool keep = false;
-        uint32_t val = 0;
-        int rr = 0, cc = 0;
-        bool is_corner = false;
-        if (i < n_iter) {
-            if (listed) { const int e = listB[i]; rr = e >> 10; cc = e & 1023; is_corner = true; }
-            else {
+    // ---- stage 5: NMS inside the cell interior. Every warp walks its own corner list (capW entries: an eighth of a
+    // quarter of the tile's pixels). If a warp ever finds more corners, the whole block scans the m map instead: slower,
+    // same result.
+    if (*s_ovf == 0) {
+        for (int base = 0; base < nCorn; base += 32) {
+            const int i = base + lane;
+            bool keep = false;
+            uint32_t val = 0;
+            if (i < nCorn) keep = fast_nms_one(a, S, myList[i], T, hEff, xbase, cand_y0, s_has, val);
+            fast_emit(a, f, keep, val);
+        }
+    } else {
+        const int n_iter = hEff * tp;
+        for (int base = 0; base < n_iter; base += 256) {
+            const int i = base + tid;
+            bool keep = false;
+            uint32_t val = 0;
+            if (i < n_iter) {
                 // overflow path: pixel i of the m map; only columns this pass tested (pass 2 leaves pass-1 cells alone)
-                rr = i / a.scw; cc = i - rr * a.scw;
-                is_corner = cc < wEff && sc[i] != 0 && S.need[cs + cc] != 0;
+                const int o = i + 3 * tp;
+                const int col = i % tp;
+                if (col >= cs && col < cs + wEff && S.need[col] != 0 && scp[o] != 0)
+                    keep = fast_nms_one(a, S, o, T, hEff, xbase, cand_y0, s_has, val);
             }
+            fast_emit(a, f, keep, val);
         }
-        if (is_corner) {
-            const int m = sc[rr * a.scw + cc];
-            const int cell = S.cellOf[cc];
-            const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff); // [cl, chi) = this cell's interior columns
-            // OpenCV's buffer holds m-1 for corners and 0 elsewhere: keep iff m-1 > max(m2-1, 0) for every neighbour inside the
-            // cell's ROI interior, i.e. m > (largest in-range neighbour) and, if there is any neighbour, m > 1
-            const bool up = rr > 0, dn = rr + 1 < hEff, lf = cc > cl, rt = cc + 1 < chi;
-            const uint8_t *q = sc + rr * a.scw + cc;
-            const int n0 = (up && lf) ? q[-a.scw - 1] : 0, n1 = up ? q[-a.scw] : 0, n2 = (up && rt) ? q[-a.scw + 1] : 0;
-            const int n3 = lf ? q[-1] : 0, n4 = rt ? q[1] : 0;
-            const int n5 = (dn && lf) ? q[a.scw - 1] : 0, n6 = dn ? q[a.scw] : 0, n7 = (dn && rt) ? q[a.scw + 1] : 0;
-            const int mx = max3i(max3i(n0, n1, n2), max3i(n3, n4, n5), max(n6, n7));
-            keep = m > mx && (m > 1 || !(up || dn || lf || rt));
-            if (keep) {
-                s_has[cell] = 1;
-                // coordinates relative to (16,16): ROI-local (cc+3, rr+3) + cell offset
-                val = cand_pack(cand_x0 + cc + 3, cand_y0 + rr + 3, m);
-            }
-        }
-        const int pos = warp_append1(keep, &s_cnt[3]);
-        if (keep) stage[pos] = val;
-    }
-    __syncthreads();
-    // ---- emission: one global atomic for this pass
-    const int cnt = s_cnt[3];
-    if (cnt) {
-        if (tid == 0) *s_base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], cnt);
-        __syncthreads();
-        const int gbase = *s_base;
-        if (gbase + cnt > a.cand_cap) { if (tid == 0) atomicExch(a.overflow, 1); }
-        for (int i = tid; i < cnt; i += 256)
-            if (gbase + i < a.cand_cap) a.cand[(size_t)f * a.cand_cap + gbase + i] = stage[i];
     }
     __syncthreads();
 }
@@ -312,6 +338,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
 __global__ void __launch_bounds__(256)
 fast9_cells(FastArgs a)
 {
+    constexpr int tp = FAST_TP;
     const int tid = threadIdx.x;
     const int f = blockIdx.z;
     const int ci = blockIdx.y;          // cell row
@@ -325,24 +352,17 @@ fast9_cells(FastArgs a)
     const int ox = x0 - xa;
     const int cs = ox + 3, ce = cs + wEff;   // interior byte range inside a tile row
     const int rows = hEff + 6;
-    const int tp = a.tpitch;
-    const int cap = a.hCell * a.scw;
+    const int capW = a.list_cap >> 3;
 
     FastSmem S;
     S.tile = fast_smem;                                              // (hCell+6) * tp
-    S.sc = S.tile + (size_t)(a.hCell + 6) * tp;                      // hCell * scw : m map (0 = not a corner)
-    S.cellOf = S.sc + ((cap + 15) & ~15);                            // scw : cell index of an interior column
-    S.need = S.cellOf + ((a.scw + 15) & ~15);                        // tp : 0x80 where this pass tests the byte column
-    S.queue = reinterpret_cast<uint16_t *>(S.need + ((tp + 15) & ~15));
-    {   // queues and the NMS staging area share one region (see below): the larger of the two, 16-byte granular
-        const size_t qbytes = sizeof(uint16_t) * 8 * FAST_QCAP, sbytes = sizeof(uint32_t) * (((a.hCell + 1) / 2) * ((a.scw + 1) / 2) + 8);
-        S.listB = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.queue) + (((qbytes > sbytes ? qbytes : sbytes) + 15) & ~(size_t)15));
-    }
-    // the NMS survivors are staged where the per-warp queues were: the queues are dead once the fused stages 1-4 are over,
-    // and the staging area is read out (emission) before pass 2 fills the queues again. With the position table read
-    // through L1 instead of copied here, the CTA fits 5 to an SM.
-    S.stage = reinterpret_cast<uint32_t *>(S.queue);
-    __shared__ int s_cnt[4], s_base, s_again, s_lo, s_hi;
+    uint8_t *sc = S.tile + (size_t)(a.hCell + 6) * tp;               // (hCell+2) * tp : m map with a zero row above and below
+    S.scp = sc - 2 * tp;                                             // indexed by tile offset: interior row r is tile row r+3, map row r+1
+    S.colInfo = sc + (size_t)(a.hCell + 2) * tp;                     // tp : per tile column, cell | lf << 6 | rt << 7
+    S.need = S.colInfo + tp;                                         // tp : 0x80 where this pass tests the byte column
+    S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
+    S.listB = S.queue + 8 * FAST_QCAP;
+    __shared__ int s_ovf, s_mask;
     __shared__ int s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
@@ -380,42 +400,48 @@ fast9_cells(FastArgs a)
             }
         }
     }
-    for (int i = tid; i < (cap + 15) / 16; i += 256) reinterpret_cast<uint4 *>(S.sc)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (a.hCell + 2) * (tp / 16); i += 256) reinterpret_cast<uint4 *>(sc)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < tp; i += 256) {
-        S.need[i] = (i >= cs && i < ce) ? 0x80 : 0;
-        if (i < a.scw) S.cellOf[i] = (uint8_t)fast_div(i, a.magic_wcell);
+        const bool in = i >= cs && i < ce;
+        S.need[i] = in ? 0x80 : 0;
+        int info = 0;
+        if (in) {
+            const int cc = i - cs;
+            const int cell = fast_div(cc, a.magic_wcell);
+            const int cl = cell * a.wCell, chi = min(cl + a.wCell, wEff);   // [cl, chi) = this cell's interior columns
+            info = cell | (cc > cl ? 0x40 : 0) | (cc + 1 < chi ? 0x80 : 0);
+        }
+        S.colInfo[i] = (uint8_t)info;
     }
-    if (tid < 4) s_cnt[tid] = 0;
+    if (tid == 0) s_ovf = 0;
     if (tid < 64) s_has[tid] = 0;
     __syncthreads();
 
+    const int xbase = cj0 * a.wCell - cs + 3, cand_y0 = ci * a.hCell;   // candidate x = xbase + tile column, y = cand_y0 + tile row
     // pass 1: every cell at initTh (ORBextractor.cpp:785)
-    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base, 0, wEff);
+    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff);
     // pass 2: cells without a keypoint again at minTh (:788-792)
-    const int nCells = (wEff + a.wCell - 1) / a.wCell;
-    if (tid == 0) {
-        int first = -1, last = -1;
-        for (int c = 0; c < nCells; c++) if (!s_has[c]) { if (first < 0) first = c; last = c; }
-        s_again = first >= 0 && (a.minTh != a.initTh);
-        s_lo = first < 0 ? 0 : first * a.wCell;
-        s_hi = first < 0 ? 0 : min((last + 1) * a.wCell, wEff);
+    if (a.minTh == a.initTh) return;
+    const int nCells = (wEff + a.wCell - 1) / a.wCell;     // <= 32 (the host caps G)
+    if (tid < 32) {
+        const unsigned mk = __ballot_sync(0xffffffffu, tid < nCells && !s_has[tid]);
+        if (tid == 0) { s_mask = (int)mk; s_ovf = 0; }
     }
-    if (tid < 4) s_cnt[tid] = 0;
     __syncthreads();
-    if (!s_again) return;
-    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce && !s_has[S.cellOf[i - cs]]) ? 0x80 : 0;
+    const unsigned mk = (unsigned)s_mask;
+    if (mk == 0) return;
+    const int first = __ffs(mk) - 1, last = 31 - __clz(mk);
+    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
     __syncthreads();
-    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, ce, tp, cj0 * a.wCell, ci * a.hCell, s_cnt, s_has, &s_base, s_lo, s_hi);
+    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, first * a.wCell, min((last + 1) * a.wCell, wEff));
 }
 
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap)
 {
-    const int cap = hCell * scw;
-    // tile + m map + cellOf + need + per-warp queues + corner list (u16 per pixel) + survivor staging (NMS keeps at most
-    // ceil(h/2)*ceil(w/2) pixels of a tile)
-    return (size_t)(hCell + 6) * tpitch + ((cap + 15) & ~15) + ((scw + 15) & ~15) + ((tpitch + 15) & ~15) +
-           ((std::max(sizeof(uint16_t) * 8 * FAST_QCAP, sizeof(uint32_t) * (((hCell + 1) / 2) * ((scw + 1) / 2) + 8)) + 15) & ~(size_t)15) +
-           sizeof(uint16_t) * ((list_cap + 7) & ~7) + 64;
+    (void)scw;
+    // tile + m map (zero row above and below) + column info + need + per-warp queues + per-warp corner lists
+    return (size_t)(hCell + 6) * tpitch + (size_t)(hCell + 2) * tpitch + 2 * (size_t)tpitch +
+           sizeof(uint16_t) * 8 * FAST_QCAP + sizeof(uint16_t) * 8 * (size_t)(list_cap >> 3) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)

@@ -548,9 +548,10 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             a.img = fe->pyr[l]; a.pitch = g.pitch; a.frame_stride = g.frame_stride; a.w = g.w; a.h = g.h;
             a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
             static const int gpx = getenv("TB_FAST_GPX") ? atoi(getenv("TB_FAST_GPX")) : 256;   // tile width in pixels (tuning knob)
-            a.G = gpx / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun;
+            a.G = std::min(gpx, 256) / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun; if (a.G > 32) a.G = 32;
             a.scw = a.G * g.wCell;
-            a.tpitch = ((7 + a.scw + 6 + 15) & ~15) + 16;   // 8-byte aligned origin + halo + spare for the E-side read; multiple of 16 keeps every shared array 16-byte aligned
+            if (a.scw > 256 || (g.hCell + 6) * TB_FAST_TPITCH > 65535) return tb_fail(ctx, TB_E_UNSUPPORTED, "FAST cell larger than the tile");
+            a.tpitch = TB_FAST_TPITCH;   // 8-byte aligned origin + halo + spare for the E-side read; multiple of 16 keeps every shared array 16-byte aligned
             {
                 // full-width tile: x0 = 16 + k*G*wCell; when that is a multiple of 8 for every k the tile geometry is fixed
                 auto magic = [](int n) -> uint32_t { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; };

@@ -13,6 +13,9 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
                      size_t dframe, int dw, int dh, const int4 *xtab, const int4 *ytab, bool area2, int n_frames, int bp, int bh,
                      const CUtensorMap *tmap, bool span8);
 bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows);
+// tile pitch of fast9_cells in shared memory (compile-time: ring and neighbour reads use immediate offsets): 8-byte aligned
+// origin (<= 7) + up to 256 interior columns + 6 halo, rounded to 16, + 16 spare bytes for the E-side word of the prefilter
+#define TB_FAST_TPITCH 288
 struct FastArgs {
     const uint8_t *img; int pitch; size_t frame_stride;
     int w, h;
