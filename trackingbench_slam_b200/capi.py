@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtb_b200.so')
+LIB_PATH = os.environ.get('TB_LIB_PATH') or os.path.join(_HERE, 'libtb_b200.so')   # TB_LIB_PATH: developer knob (A/B builds)
 
 KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'),
                      ('response', '<f4'), ('octave', '<i4'), ('class_id', '<i4')])

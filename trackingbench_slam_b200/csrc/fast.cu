@@ -175,7 +175,7 @@ struct FastSmem {
 
 // NMS of one corner (tile offset o) + emission bookkeeping; returns keep and the packed candidate
 __device__ __forceinline__ bool fast_nms_one(const FastArgs &a, const FastSmem &S, const int o, const int T, const int hEff,
-                                             const int xbase, const int cand_y0, int *s_has, uint32_t &val)
+                                             const int xbase, const int cand_y0, uint8_t *s_has, uint32_t &val)
 {
     constexpr int tp = FAST_TP;
     const uint8_t *q = S.scp + o;
@@ -218,7 +218,7 @@ __device__ __forceinline__ void fast_emit(const FastArgs &a, const int f, const 
 template <bool UNS>
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
                                           const int hEff, const int wEff, const int cs, const int capW,
-                                          const int xbase, const int cand_y0, int *s_has, int *s_ovf,
+                                          const int xbase, const int cand_y0, uint8_t *s_has, int *s_ovf,
                                           const int col_lo, const int col_hi)   // interior columns [col_lo, col_hi) to test
 {
     constexpr int tp = FAST_TP;
@@ -347,7 +347,10 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef FAST_MINB
+#define FAST_MINB 6
+#endif
+__global__ void __launch_bounds__(256, FAST_MINB)
 fast9_cells(FastArgs a)
 {
     constexpr int tp = FAST_TP;
@@ -375,7 +378,7 @@ fast9_cells(FastArgs a)
     S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
     S.listB = S.queue + 8 * FAST_QCAP;
     __shared__ int s_ovf, s_mask;
-    __shared__ int s_has[64];
+    __shared__ uint8_t s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
     // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 16-byte words (xa is 8-byte aligned: the
@@ -388,7 +391,7 @@ fast9_cells(FastArgs a)
         const int total = rows * w16;
         for (int i0 = tid; i0 < total; i0 += 512) {
             uint4 v[2];
-            int dst[2], first[2];
+            int dst[2], first[2], last[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int i = i0 + 256 * k;
@@ -398,6 +401,7 @@ fast9_cells(FastArgs a)
                     v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(y0 + rr) * a.pitch + xa16) + ww);
                     dst[k] = rr * tp + 16 * ww;      // tile offset of this word if lead were 0
                     first[k] = ww == 0;
+                    last[k] = 16 * ww >= tp;       // second half of the word would land in the next tile row
                 }
             }
 #pragma unroll
@@ -407,7 +411,7 @@ fast9_cells(FastArgs a)
                     *reinterpret_cast<uint4 *>(S.tile + dst[k]) = v[k];
                 } else {   // tile origin sits 8 bytes into the 16-byte word: two 8-byte stores, drop what lies before the row
                     if (!first[k]) *reinterpret_cast<uint2 *>(S.tile + dst[k] - 8) = make_uint2(v[k].x, v[k].y);
-                    *reinterpret_cast<uint2 *>(S.tile + dst[k]) = make_uint2(v[k].z, v[k].w);
+                    if (!last[k]) *reinterpret_cast<uint2 *>(S.tile + dst[k]) = make_uint2(v[k].z, v[k].w);
                 }
             }
         }

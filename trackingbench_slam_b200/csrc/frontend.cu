@@ -568,11 +568,17 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
             a.overflow = fe->overflow;
             {
-                // a quarter of the tile's pixels (TB_FAST_LISTCAP overrides: tests force the overflow path with a tiny list)
                 static const int forced = getenv("TB_FAST_LISTCAP") ? atoi(getenv("TB_FAST_LISTCAP")) : 0;
-                a.list_cap = forced > 0 ? forced : std::max(256, (g.hCell * a.scw) / 4);
+                // per-warp corner lists: as long as six CTAs still fit an SM (227 KB / 6 - 1 KB reserved - static), never more
+                // than a warp's share of the tile could fill (TB_FAST_LISTCAP overrides: tests force the overflow path with a tiny list)
+                const int budget = 232448 / 6 - 1024 - 128;
+                const int base = (int)tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, 0);
+                static const int list_div = getenv("TB_FAST_LIST_DIV") ? atoi(getenv("TB_FAST_LIST_DIV")) : 0;   // developer knob: list = tile pixels / this
+                int cap = list_div > 0 ? (g.hCell * a.scw) / list_div : std::min(g.hCell * a.scw + 8 * 32, ((budget - base) / 16) * 8);
+                a.list_cap = forced > 0 ? forced : std::max(256, cap);
             }
-            size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, a.list_cap);
+            static const int smem_pad = getenv("TB_FAST_SMEM_PAD") ? atoi(getenv("TB_FAST_SMEM_PAD")) : 0;   // developer knob: fewer resident CTAs for A/B runs
+            size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, a.list_cap) + smem_pad;
             int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
             if (rc) return rc;
         }

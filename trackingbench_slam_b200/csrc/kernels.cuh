@@ -14,8 +14,11 @@ int tb_launch_resize(tb_ctx *ctx, const uint8_t *src, int spitch, size_t sframe,
                      const CUtensorMap *tmap, bool span8);
 bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int n_frames, int pitch, size_t frame_stride, int box_rows);
 // tile pitch of fast9_cells in shared memory (compile-time: ring and neighbour reads use immediate offsets): 8-byte aligned
-// origin (<= 7) + up to 256 interior columns + 6 halo, rounded to 16, + 16 spare bytes for the E-side word of the prefilter
-#define TB_FAST_TPITCH 288
+// origin (<= 7) + up to 256 interior columns + 6 halo, rounded to 16. The E-side word of the last prefilter group reads the
+// first bytes of the next row: those lanes belong to columns outside the interior and are masked.
+#ifndef TB_FAST_TPITCH
+#define TB_FAST_TPITCH 272
+#endif
 struct FastArgs {
     const uint8_t *img; int pitch; size_t frame_stride;
     int w, h;
