@@ -72,6 +72,13 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b)
     asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+// the same with the multiplier 1 read from a kernel argument: ptxas turns `mad x, 1, uniform` back into an ALU-pipe VIADD
+__device__ __forceinline__ uint32_t add_fma_pipe1(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
 // |ring - centre| > T per byte, result in bit 7 of each byte (T <= 127; K = (127-T)*0x01010101)
 __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t c, uint32_t K)
 {
@@ -85,7 +92,7 @@ __device__ __forceinline__ uint32_t byte_gt(uint32_t ring, uint32_t c, uint32_t 
     return (ring & ~c) | (~(ring ^ c) & t);                     // msb decides, else the low bits (ring != centre where used)
 }
 // compass test for one word of 4 centres: two ADJACENT compass pixels both brighter by > T or both darker by > T
-__device__ __forceinline__ uint32_t compass_signed(uint32_t n, uint32_t s_, uint32_t e, uint32_t w_, uint32_t c, uint32_t K)
+__device__ __forceinline__ uint32_t compass_signed(uint32_t n, uint32_t s_, uint32_t e, uint32_t w_, uint32_t c, uint32_t K, uint32_t)
 {
     const uint32_t clow = c & 0x7f7f7f7fu;
     const uint32_t aN = absdiff_gt(n, c, K), aS = absdiff_gt(s_, c, K), aE = absdiff_gt(e, c, K), aW = absdiff_gt(w_, c, K);
@@ -98,11 +105,11 @@ __device__ __forceinline__ uint32_t compass_signed(uint32_t n, uint32_t s_, uint
 // cheaper, weaker form of the compass test: some N/S pixel AND some E/W pixel differ from the centre by more than T (no
 // polarity). Lets through about a tenth more pixels than compass_signed at less than half the instructions: used where few
 // pixels survive anyway (high thresholds); the arc score decides exactly either way.
-__device__ __forceinline__ uint32_t compass_unsigned(uint32_t n, uint32_t s_, uint32_t e, uint32_t w_, uint32_t c, uint32_t K)
+__device__ __forceinline__ uint32_t compass_unsigned(uint32_t n, uint32_t s_, uint32_t e, uint32_t w_, uint32_t c, uint32_t K, uint32_t one)
 {
     const uint32_t dN = __vabsdiffu4(n, c), dS = __vabsdiffu4(s_, c), dE = __vabsdiffu4(e, c), dW = __vabsdiffu4(w_, c);
-    const uint32_t tN = add_fma_pipe(dN & 0x7f7f7f7fu, K), tS = add_fma_pipe(dS & 0x7f7f7f7fu, K);
-    const uint32_t tE = add_fma_pipe(dE & 0x7f7f7f7fu, K), tW = add_fma_pipe(dW & 0x7f7f7f7fu, K);
+    const uint32_t tN = add_fma_pipe1(dN & 0x7f7f7f7fu, K, one), tS = add_fma_pipe1(dS & 0x7f7f7f7fu, K, one);
+    const uint32_t tE = add_fma_pipe1(dE & 0x7f7f7f7fu, K, one), tW = add_fma_pipe1(dW & 0x7f7f7f7fu, K, one);
     return (tN | dN | tS | dS) & (tE | dE | tW | dW);
 }
 
@@ -166,6 +173,8 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 // tile's pitch (plus a zero row above and below), so ring and neighbour reads are LDS with immediate offsets from one
 // register.
 __device__ uint2 g_bitpos[256];   // set-bit positions of a byte (one byte each, lowest first), filled by tb_fast_init_device
+#define FAST_NT TB_FAST_NT   // threads per CTA
+#define FAST_NW (FAST_NT / 32)
 #define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
 #define FAST_TP TB_FAST_TPITCH
 struct FastSmem {
@@ -237,6 +246,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         int qn = 0;                                     // warp-uniform queue fill
         const bool swar = T <= 127;                     // larger thresholds skip the byte-SIMD test: everything is scored
         const uint32_t K = (uint32_t)(127 - (swar ? T : 0)) * 0x01010101u;
+        const uint32_t one = a.one;
         const int g0 = (cs + col_lo) >> 4, nG = ((cs + col_hi + 15) >> 4) - g0;      // 16-pixel groups
         const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
         const int items = hEff * nG;
@@ -253,7 +263,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             if (corner && pos < capW) myList[pos] = (uint16_t)o;
             nCorn += __popc(bal);
         };
-        for (int base = 0; base < items; base += 256) {
+        for (int base = 0; base < items; base += FAST_NT) {
             const int it = base + tid;
             uint32_t c[4] = {0, 0, 0, 0};
             int e0 = 0;
@@ -271,16 +281,17 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                         const uint32_t L = *reinterpret_cast<const uint32_t *>(row - 4);
                         const uint32_t R = *reinterpret_cast<const uint32_t *>(row + 16);
                         // west = pixel x-3, east = pixel x+3 of every byte lane
-                        c[0] = (UNS ? compass_unsigned : compass_signed)(dn.x, up.x, __byte_perm(cen.x, cen.y, 0x6543), __byte_perm(L, cen.x, 0x4321), cen.x, K) & nd.x;
-                        c[1] = (UNS ? compass_unsigned : compass_signed)(dn.y, up.y, __byte_perm(cen.y, cen.z, 0x6543), __byte_perm(cen.x, cen.y, 0x4321), cen.y, K) & nd.y;
-                        c[2] = (UNS ? compass_unsigned : compass_signed)(dn.z, up.z, __byte_perm(cen.z, cen.w, 0x6543), __byte_perm(cen.y, cen.z, 0x4321), cen.z, K) & nd.z;
-                        c[3] = (UNS ? compass_unsigned : compass_signed)(dn.w, up.w, __byte_perm(cen.w, R, 0x6543), __byte_perm(cen.z, cen.w, 0x4321), cen.w, K) & nd.w;
+                        c[0] = (UNS ? compass_unsigned : compass_signed)(dn.x, up.x, __byte_perm(cen.x, cen.y, 0x6543), __byte_perm(L, cen.x, 0x4321), cen.x, K, one) & nd.x;
+                        c[1] = (UNS ? compass_unsigned : compass_signed)(dn.y, up.y, __byte_perm(cen.y, cen.z, 0x6543), __byte_perm(cen.x, cen.y, 0x4321), cen.y, K, one) & nd.y;
+                        c[2] = (UNS ? compass_unsigned : compass_signed)(dn.z, up.z, __byte_perm(cen.z, cen.w, 0x6543), __byte_perm(cen.y, cen.z, 0x4321), cen.z, K, one) & nd.z;
+                        c[3] = (UNS ? compass_unsigned : compass_signed)(dn.w, up.w, __byte_perm(cen.w, R, 0x6543), __byte_perm(cen.z, cen.w, 0x4321), cen.w, K, one) & nd.w;
                     } else { c[0] = nd.x; c[1] = nd.y; c[2] = nd.z; c[3] = nd.w; }
                 }
             }
             // bit 7 of every byte -> one flag bit per pixel (the multiply moves bits 7,15,23,31 to 28..31 without carries)
-            const uint32_t m16 = ((c[0] & 0x80808080u) * 0x00204081u >> 28) | (((c[1] & 0x80808080u) * 0x00204081u >> 28) << 4) |
-                                 (((c[2] & 0x80808080u) * 0x00204081u >> 28) << 8) | (((c[3] & 0x80808080u) * 0x00204081u >> 28) << 12);
+            // (c[] only has bit 7 of each byte left: need[] holds 0x80 or 0)
+            const uint32_t m16 = (c[0] * 0x00204081u >> 28) | ((c[1] * 0x00204081u >> 28) << 4) |
+                                 ((c[2] * 0x00204081u >> 28) << 8) | ((c[3] * 0x00204081u >> 28) << 12);
             const int cnt = __popc(m16);
             int inc = cnt;                               // inclusive warp scan of the survivor counts
 #pragma unroll
@@ -330,7 +341,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         }
     } else {
         const int n_iter = hEff * tp;
-        for (int base = 0; base < n_iter; base += 256) {
+        for (int base = 0; base < n_iter; base += FAST_NT) {
             const int i = base + tid;
             bool keep = false;
             uint32_t val = 0;
@@ -347,10 +358,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     __syncthreads();
 }
 
-#ifndef FAST_MINB
-#define FAST_MINB 6
-#endif
-__global__ void __launch_bounds__(256, FAST_MINB)
+__global__ void __launch_bounds__(FAST_NT, TB_FAST_CTAS)
 fast9_cells(FastArgs a)
 {
     constexpr int tp = FAST_TP;
@@ -367,7 +375,7 @@ fast9_cells(FastArgs a)
     const int ox = x0 - xa;
     const int cs = ox + 3, ce = cs + wEff;   // interior byte range inside a tile row
     const int rows = hEff + 6;
-    const int capW = a.list_cap >> 3;
+    const int capW = a.list_cap / FAST_NW;
 
     FastSmem S;
     S.tile = fast_smem;                                              // (hCell+6) * tp
@@ -376,7 +384,7 @@ fast9_cells(FastArgs a)
     S.colInfo = sc + (size_t)(a.hCell + 2) * tp;                     // tp : per tile column, cell | lf << 6 | rt << 7
     S.need = S.colInfo + tp;                                         // tp : 0x80 where this pass tests the byte column
     S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
-    S.listB = S.queue + 8 * FAST_QCAP;
+    S.listB = S.queue + FAST_NW * FAST_QCAP;
     __shared__ int s_ovf, s_mask;
     __shared__ uint8_t s_has[64];
 
@@ -389,12 +397,12 @@ fast9_cells(FastArgs a)
         const int w16 = (lead + ox + wEff + 6 + 15) >> 4;
         const uint32_t magic16 = div_magic(w16);
         const int total = rows * w16;
-        for (int i0 = tid; i0 < total; i0 += 512) {
+        for (int i0 = tid; i0 < total; i0 += 2 * FAST_NT) {
             uint4 v[2];
             int dst[2], first[2], last[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const int i = i0 + 256 * k;
+                const int i = i0 + FAST_NT * k;
                 dst[k] = -1;
                 if (i < total) {
                     const int rr = fast_div(i, magic16), ww = i - rr * w16;
@@ -416,8 +424,8 @@ fast9_cells(FastArgs a)
             }
         }
     }
-    for (int i = tid; i < (a.hCell + 2) * (tp / 16); i += 256) reinterpret_cast<uint4 *>(sc)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < tp; i += 256) {
+    for (int i = tid; i < (a.hCell + 2) * (tp / 16); i += FAST_NT) reinterpret_cast<uint4 *>(sc)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < tp; i += FAST_NT) {
         const bool in = i >= cs && i < ce;
         S.need[i] = in ? 0x80 : 0;
         int info = 0;
@@ -430,7 +438,7 @@ fast9_cells(FastArgs a)
         S.colInfo[i] = (uint8_t)info;
     }
     if (tid == 0) s_ovf = 0;
-    if (tid < 64) s_has[tid] = 0;
+    for (int i = tid; i < 64; i += FAST_NT) s_has[i] = 0;
     __syncthreads();
 
     const int xbase = cj0 * a.wCell - cs + 3, cand_y0 = ci * a.hCell;   // candidate x = xbase + tile column, y = cand_y0 + tile row
@@ -448,7 +456,7 @@ fast9_cells(FastArgs a)
     const unsigned mk = (unsigned)s_mask;
     if (mk == 0) return;
     const int first = __ffs(mk) - 1, last = 31 - __clz(mk);
-    for (int i = tid; i < tp; i += 256) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
+    for (int i = tid; i < tp; i += FAST_NT) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
     __syncthreads();
     if (a.minTh >= a.unsignedTh) fast_pass<true>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, first * a.wCell, min((last + 1) * a.wCell, wEff));
     else fast_pass<false>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, first * a.wCell, min((last + 1) * a.wCell, wEff));
@@ -459,14 +467,14 @@ size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap)
     (void)scw;
     // tile + m map (zero row above and below) + column info + need + per-warp queues + per-warp corner lists
     return (size_t)(hCell + 6) * tpitch + (size_t)(hCell + 2) * tpitch + 2 * (size_t)tpitch +
-           sizeof(uint16_t) * 8 * FAST_QCAP + sizeof(uint16_t) * 8 * (size_t)(list_cap >> 3) + 64;
+           sizeof(uint16_t) * FAST_NW * FAST_QCAP + sizeof(uint16_t) * FAST_NW * (size_t)(list_cap / FAST_NW) + 64;
 }
 
 int tb_launch_fast(tb_ctx *ctx, const FastArgs &a, int nColsRun, int nRowsRun, int n_frames, size_t smem)
 {
     ProfScope prof__(ctx, "fast9_cells");
     dim3 grid(div_up(nColsRun, a.G), nRowsRun, n_frames);
-    fast9_cells<<<grid, 256, smem, ctx->stream>>>(a);
+    fast9_cells<<<grid, FAST_NT, smem, ctx->stream>>>(a);
     TB_LAUNCH_CHECK(ctx);
     return TB_OK;
 }

@@ -548,9 +548,9 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             a.img = fe->pyr[l]; a.pitch = g.pitch; a.frame_stride = g.frame_stride; a.w = g.w; a.h = g.h;
             a.nCols = g.nCols; a.nRows = g.nRows; a.wCell = g.wCell; a.hCell = g.hCell; a.maxBX = g.maxBX; a.maxBY = g.maxBY;
             static const int gpx = getenv("TB_FAST_GPX") ? atoi(getenv("TB_FAST_GPX")) : 256;   // tile width in pixels (tuning knob)
-            a.G = std::min(gpx, 256) / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun; if (a.G > 32) a.G = 32;
+            a.G = std::min(gpx, TB_FAST_TPITCH - 16) / g.wCell; if (a.G < 1) a.G = 1; if (a.G > g.nColsRun) a.G = g.nColsRun; if (a.G > 32) a.G = 32;
             a.scw = a.G * g.wCell;
-            if (a.scw > 256 || (g.hCell + 6) * TB_FAST_TPITCH > 65535) return tb_fail(ctx, TB_E_UNSUPPORTED, "FAST cell larger than the tile");
+            if (a.scw > TB_FAST_TPITCH - 16 || (g.hCell + 6) * TB_FAST_TPITCH > 65535) return tb_fail(ctx, TB_E_UNSUPPORTED, "FAST cell larger than the tile");
             a.tpitch = TB_FAST_TPITCH;   // 8-byte aligned origin + halo + spare for the E-side read; multiple of 16 keeps every shared array 16-byte aligned
             {
                 // full-width tile: x0 = 16 + k*G*wCell; when that is a multiple of 8 for every k the tile geometry is fixed
@@ -563,18 +563,19 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             }
             a.initTh = (int)initTh; a.minTh = (int)minTh;
             static const int unsTh = getenv("TB_FAST_UNSIGNED_TH") ? atoi(getenv("TB_FAST_UNSIGNED_TH")) : 12;
-            a.unsignedTh = unsTh;
+            a.unsignedTh = unsTh; a.one = 1;
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
             a.overflow = fe->overflow;
             {
                 static const int forced = getenv("TB_FAST_LISTCAP") ? atoi(getenv("TB_FAST_LISTCAP")) : 0;
-                // per-warp corner lists: as long as six CTAs still fit an SM (227 KB / 6 - 1 KB reserved - static), never more
+                // per-warp corner lists: as long as TB_FAST_CTAS CTAs still fit an SM (227 KB / CTAs - 1 KB reserved - static), never more
                 // than a warp's share of the tile could fill (TB_FAST_LISTCAP overrides: tests force the overflow path with a tiny list)
-                const int budget = 232448 / 6 - 1024 - 128;
+                const int nw = TB_FAST_NT / 32;
+                const int budget = 232448 / TB_FAST_CTAS - 1024 - 128;
                 const int base = (int)tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, 0);
                 static const int list_div = getenv("TB_FAST_LIST_DIV") ? atoi(getenv("TB_FAST_LIST_DIV")) : 0;   // developer knob: list = tile pixels / this
-                int cap = list_div > 0 ? (g.hCell * a.scw) / list_div : std::min(g.hCell * a.scw + 8 * 32, ((budget - base) / 16) * 8);
+                int cap = list_div > 0 ? (g.hCell * a.scw) / list_div : std::min(g.hCell * a.scw + nw * 32, ((budget - base) / (2 * nw)) * nw);
                 a.list_cap = forced > 0 ? forced : std::max(256, cap);
             }
             static const int smem_pad = getenv("TB_FAST_SMEM_PAD") ? atoi(getenv("TB_FAST_SMEM_PAD")) : 0;   // developer knob: fewer resident CTAs for A/B runs

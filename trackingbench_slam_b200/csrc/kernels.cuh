@@ -19,6 +19,13 @@ bool tb_resize_tensor_map(CUtensorMap *tm, const uint8_t *src, int w, int h, int
 #ifndef TB_FAST_TPITCH
 #define TB_FAST_TPITCH 272
 #endif
+#ifndef TB_FAST_NT
+#define TB_FAST_NT 128       // threads per fast9_cells CTA: four warps on a 256-pixel-wide tile (twice the pixels per warp of
+                             // eight warps amortise the per-warp fixed work: set-up, queue flush, NMS rounds)
+#endif
+#ifndef TB_FAST_CTAS
+#define TB_FAST_CTAS 8   // resident CTAs per SM the shared-memory layout and the register cap aim for
+#endif
 struct FastArgs {
     const uint8_t *img; int pitch; size_t frame_stride;
     int w, h;
@@ -27,6 +34,7 @@ struct FastArgs {
     int list_cap;      // entries of the per-tile corner list (more corners than that: the NMS scans the score map)
     uint32_t magic_groups, magic_w8, magic_wcell;   // 2^32/n rounded up for the full-width tile (0 when n == 1)
     int initTh, minTh;
+    uint32_t one;      // 1 (a multiplier ptxas cannot fold: keeps some adds on the FMA pipe)
     int unsignedTh;    // passes with a threshold >= this use the polarity-free compass prefilter (fewer instructions, a few more survivors)
     uint32_t *cand; int cand_cap;
     int *n_cand; int n_cand_stride;
