@@ -209,20 +209,36 @@ __device__ __forceinline__ bool fast_nms_one(const FastArgs &a, const FastSmem &
     return keep;
 }
 
-__device__ __forceinline__ void fast_emit(const FastArgs &a, const int f, const bool keep, const uint32_t val)
-{
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (bal == 0) return;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int pos = base + __popc(bal & ((1u << lane) - 1));
-    if (keep) {
-        if (pos < a.cand_cap) a.cand[(size_t)f * a.cand_cap + pos] = val;
-        else atomicExch(a.overflow, 1);
+// NMS survivors of a warp are collected in its (by then dead) survivor queue and written out with one global atomic per
+// warp and pass (the round trip of an atomic per NMS round showed up as the second largest stall of the kernel)
+#define FAST_STAGE_CAP (FAST_QCAP / 2)     // u32 entries that fit a warp's queue
+struct FastEmit {
+    uint32_t *stage; int n;                // warp-uniform fill
+    __device__ __forceinline__ void flush(const FastArgs &a, const int f)
+    {
+        if (n == 0) return;
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        __syncwarp();
+        if (lane == 0) base = atomicAdd(&a.n_cand[(size_t)f * a.n_cand_stride], n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < n; i += 32) {
+            if (base + i < a.cand_cap) a.cand[(size_t)f * a.cand_cap + base + i] = stage[i];
+            else atomicExch(a.overflow, 1);
+        }
+        __syncwarp();
+        n = 0;
     }
-}
+    __device__ __forceinline__ void push(const FastArgs &a, const int f, const bool keep, const uint32_t val)
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal == 0) return;
+        const int cnt = __popc(bal);
+        if (n + cnt > FAST_STAGE_CAP) flush(a, f);
+        if (keep) stage[n + __popc(bal & ((1u << (threadIdx.x & 31)) - 1))] = val;
+        n += cnt;
+    }
+};
 
 template <bool UNS>
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
@@ -331,13 +347,16 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
     // ---- stage 5: NMS inside the cell interior. Every warp walks its own corner list (capW entries: an eighth of a
     // quarter of the tile's pixels). If a warp ever finds more corners, the whole block scans the m map instead: slower,
     // same result.
+    FastEmit em;
+    em.stage = reinterpret_cast<uint32_t *>(S.queue + warp * FAST_QCAP);
+    em.n = 0;
     if (*s_ovf == 0) {
         for (int base = 0; base < nCorn; base += 32) {
             const int i = base + lane;
             bool keep = false;
             uint32_t val = 0;
             if (i < nCorn) keep = fast_nms_one(a, S, myList[i], T, hEff, xbase, cand_y0, s_has, val);
-            fast_emit(a, f, keep, val);
+            em.push(a, f, keep, val);
         }
     } else {
         const int n_iter = hEff * tp;
@@ -352,9 +371,10 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                 if (col >= cs && col < cs + wEff && S.need[col] != 0 && scp[o] != 0)
                     keep = fast_nms_one(a, S, o, T, hEff, xbase, cand_y0, s_has, val);
             }
-            fast_emit(a, f, keep, val);
+            em.push(a, f, keep, val);
         }
     }
+    em.flush(a, f);
     __syncthreads();
 }
 
@@ -389,40 +409,30 @@ fast9_cells(FastArgs a)
     __shared__ uint8_t s_has[64];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
-    // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) as 16-byte words (xa is 8-byte aligned: the
-    //      first word of a row is fetched as two 8-byte halves when xa is not 16-byte aligned)
+    // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) copied asynchronously (no registers, every copy of the thread
+    //      in flight at once): 16-byte units when the 8-byte aligned tile origin xa is 16-byte aligned, else 8-byte units.
+    //      The wait sits behind the zeroing and the column tables below.
     {
-        const int xa16 = xa & ~15;                     // 16-byte aligned start; tile byte 0 = image byte xa
-        const int lead = xa - xa16;                    // 0 or 8
-        const int w16 = (lead + ox + wEff + 6 + 15) >> 4;
-        const uint32_t magic16 = div_magic(w16);
-        const int total = rows * w16;
-        for (int i0 = tid; i0 < total; i0 += 2 * FAST_NT) {
-            uint4 v[2];
-            int dst[2], first[2], last[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int i = i0 + FAST_NT * k;
-                dst[k] = -1;
-                if (i < total) {
-                    const int rr = fast_div(i, magic16), ww = i - rr * w16;
-                    v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(y0 + rr) * a.pitch + xa16) + ww);
-                    dst[k] = rr * tp + 16 * ww;      // tile offset of this word if lead were 0
-                    first[k] = ww == 0;
-                    last[k] = 16 * ww >= tp;       // second half of the word would land in the next tile row
-                }
+        const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(S.tile);
+        const uint8_t *src0 = img + (size_t)y0 * a.pitch + xa;
+        if ((xa & 15) == 0) {
+            const int w16 = (ox + wEff + 6 + 15) >> 4;
+            const uint32_t magic16 = div_magic(w16);
+            const int total = rows * w16;
+            for (int i = tid; i < total; i += FAST_NT) {
+                const int rr = fast_div(i, magic16), ww = i - rr * w16;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(tile_s + rr * tp + 16 * ww), "l"(src0 + (size_t)rr * a.pitch + 16 * ww) : "memory");
             }
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                if (dst[k] < 0) continue;
-                if (lead == 0) {
-                    *reinterpret_cast<uint4 *>(S.tile + dst[k]) = v[k];
-                } else {   // tile origin sits 8 bytes into the 16-byte word: two 8-byte stores, drop what lies before the row
-                    if (!first[k]) *reinterpret_cast<uint2 *>(S.tile + dst[k] - 8) = make_uint2(v[k].x, v[k].y);
-                    if (!last[k]) *reinterpret_cast<uint2 *>(S.tile + dst[k]) = make_uint2(v[k].z, v[k].w);
-                }
+        } else {
+            const int w8 = (ox + wEff + 6 + 7) >> 3;
+            const uint32_t magic8 = div_magic(w8);
+            const int total = rows * w8;
+            for (int i = tid; i < total; i += FAST_NT) {
+                const int rr = fast_div(i, magic8), ww = i - rr * w8;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(tile_s + rr * tp + 8 * ww), "l"(src0 + (size_t)rr * a.pitch + 8 * ww) : "memory");
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int i = tid; i < (a.hCell + 2) * (tp / 16); i += FAST_NT) reinterpret_cast<uint4 *>(sc)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < tp; i += FAST_NT) {
@@ -439,6 +449,7 @@ fast9_cells(FastArgs a)
     }
     if (tid == 0) s_ovf = 0;
     for (int i = tid; i < 64; i += FAST_NT) s_has[i] = 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int xbase = cj0 * a.wCell - cs + 3, cand_y0 = ci * a.hCell;   // candidate x = xbase + tile column, y = cand_y0 + tile row
