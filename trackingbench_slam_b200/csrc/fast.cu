@@ -175,6 +175,7 @@ __device__ __forceinline__ int warp_append1(bool pred, int *counter)
 __device__ uint2 g_bitpos[256];   // set-bit positions of a byte (one byte each, lowest first), filled by tb_fast_init_device
 #define FAST_NT TB_FAST_NT   // threads per CTA
 #define FAST_NW (FAST_NT / 32)
+static_assert(TB_FAST_TPITCH % 16 == 0 && TB_FAST_TPITCH / 16 <= 32, "the pass-2 group list is built by one warp");
 #define FAST_QCAP 544   // per-warp survivor queue: up to 31 waiting + 512 new per iteration
 #define FAST_TP TB_FAST_TPITCH
 struct FastSmem {
@@ -244,7 +245,8 @@ template <bool UNS>
 __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, const int T, const int f,
                                           const int hEff, const int wEff, const int cs, const int capW,
                                           const int xbase, const int cand_y0, uint8_t *s_has, int *s_ovf,
-                                          const int col_lo, const int col_hi)   // interior columns [col_lo, col_hi) to test
+                                          const int col_lo, const int col_hi,   // interior columns [col_lo, col_hi) to test
+                                          const uint8_t *glist, const int n_glist)  // pass 2: the 16-pixel groups that touch a cell to redo
 {
     constexpr int tp = FAST_TP;
     const int tid = threadIdx.x;
@@ -263,8 +265,8 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         const bool swar = T <= 127;                     // larger thresholds skip the byte-SIMD test: everything is scored
         const uint32_t K = (uint32_t)(127 - (swar ? T : 0)) * 0x01010101u;
         const uint32_t one = a.one;
-        const int g0 = (cs + col_lo) >> 4, nG = ((cs + col_hi + 15) >> 4) - g0;      // 16-pixel groups
-        const uint32_t magic = (col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
+        const int g0 = (cs + col_lo) >> 4, nG = glist ? n_glist : ((cs + col_hi + 15) >> 4) - g0;      // 16-pixel groups
+        const uint32_t magic = (!glist && col_lo == 0 && col_hi == a.scw && a.magic_groups != 0xFFFFFFFFu) ? a.magic_groups : div_magic(nG);
         const int items = hEff * nG;
         // score 32 (or, for the final flush, fewer) queued pixels; corners go to the warp's corner list
         auto score_batch = [&](int o, bool valid) {
@@ -285,7 +287,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
             int e0 = 0;
             if (it < items) {
                 const int r = fast_div(it, magic);
-                const int o = 16 * (it - r * nG + g0);
+                const int o = 16 * (glist ? (int)glist[it - r * nG] : it - r * nG + g0);
                 e0 = (r + 3) * tp + o;                   // tile offset of the group's first pixel
                 const uint4 nd = *reinterpret_cast<const uint4 *>(S.need + o);
                 if (nd.x | nd.y | nd.z | nd.w) {
@@ -406,7 +408,7 @@ fast9_cells(FastArgs a)
     S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
     S.listB = S.queue + FAST_NW * FAST_QCAP;
     __shared__ int s_ovf, s_mask;
-    __shared__ uint8_t s_has[64];
+    __shared__ uint8_t s_has[64], s_glist[32];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
     // ---- stage 0: rows [y0, y0+rows), bytes [xa, x0+wEff+6) copied asynchronously (no registers, every copy of the thread
@@ -454,8 +456,8 @@ fast9_cells(FastArgs a)
 
     const int xbase = cj0 * a.wCell - cs + 3, cand_y0 = ci * a.hCell;   // candidate x = xbase + tile column, y = cand_y0 + tile row
     // pass 1: every cell at initTh (ORBextractor.cpp:785)
-    if (a.initTh >= a.unsignedTh) fast_pass<true>(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff);
-    else fast_pass<false>(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff);
+    if (a.initTh >= a.unsignedTh) fast_pass<true>(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, nullptr, 0);
+    else fast_pass<false>(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, nullptr, 0);
     // pass 2: cells without a keypoint again at minTh (:788-792)
     if (a.minTh == a.initTh) return;
     const int nCells = (wEff + a.wCell - 1) / a.wCell;     // <= 32 (the host caps G)
@@ -466,11 +468,20 @@ fast9_cells(FastArgs a)
     __syncthreads();
     const unsigned mk = (unsigned)s_mask;
     if (mk == 0) return;
-    const int first = __ffs(mk) - 1, last = 31 - __clz(mk);
     for (int i = tid; i < tp; i += FAST_NT) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
     __syncthreads();
-    if (a.minTh >= a.unsignedTh) fast_pass<true>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, first * a.wCell, min((last + 1) * a.wCell, wEff));
-    else fast_pass<false>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, first * a.wCell, min((last + 1) * a.wCell, wEff));
+    // the 16-pixel groups that hold a column to redo, in order (tp / 16 <= 32 groups: one warp's ballot)
+    if (tid < 32) {
+        bool any = false;
+        if (tid < tp / 16) { const uint4 nd = *reinterpret_cast<const uint4 *>(S.need + 16 * tid); any = (nd.x | nd.y | nd.z | nd.w) != 0; }
+        const unsigned gm = __ballot_sync(0xffffffffu, any);
+        if (any) s_glist[__popc(gm & ((1u << tid) - 1))] = (uint8_t)tid;
+        if (tid == 0) s_mask = __popc(gm);
+    }
+    __syncthreads();
+    const int n_glist = s_mask;
+    if (a.minTh >= a.unsignedTh) fast_pass<true>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist);
+    else fast_pass<false>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist);
 }
 
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap)
