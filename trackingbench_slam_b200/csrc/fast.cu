@@ -407,7 +407,7 @@ fast9_cells(FastArgs a)
     S.need = S.colInfo + tp;                                         // tp : 0x80 where this pass tests the byte column
     S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
     S.listB = S.queue + FAST_NW * FAST_QCAP;
-    __shared__ int s_ovf, s_mask;
+    __shared__ int s_ovf, s_mask, s_ng;
     __shared__ uint8_t s_has[64], s_glist[32];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
@@ -469,17 +469,21 @@ fast9_cells(FastArgs a)
     const unsigned mk = (unsigned)s_mask;
     if (mk == 0) return;
     for (int i = tid; i < tp; i += FAST_NT) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
-    __syncthreads();
-    // the 16-pixel groups that hold a column to redo, in order (tp / 16 <= 32 groups: one warp's ballot)
+    // the 16-pixel groups that hold a column to redo, in order (tp / 16 <= 32 groups: one warp's ballot): a group is
+    // needed when one of the cells between its first and its last interior column is in the mask
     if (tid < 32) {
         bool any = false;
-        if (tid < tp / 16) { const uint4 nd = *reinterpret_cast<const uint4 *>(S.need + 16 * tid); any = (nd.x | nd.y | nd.z | nd.w) != 0; }
+        const int lo = max(16 * tid, cs), hi = min(16 * tid + 15, ce - 1);
+        if (lo <= hi) {
+            const int c0 = S.colInfo[lo] & 63, c1 = S.colInfo[hi] & 63;
+            any = ((mk >> c0) & (0xFFFFFFFFu >> (31 - (c1 - c0)))) != 0;
+        }
         const unsigned gm = __ballot_sync(0xffffffffu, any);
         if (any) s_glist[__popc(gm & ((1u << tid) - 1))] = (uint8_t)tid;
-        if (tid == 0) s_mask = __popc(gm);
+        if (tid == 0) s_ng = __popc(gm);
     }
     __syncthreads();
-    const int n_glist = s_mask;
+    const int n_glist = s_ng;
     if (a.minTh >= a.unsignedTh) fast_pass<true>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist);
     else fast_pass<false>(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist);
 }
