@@ -646,7 +646,7 @@ def run_ours(a):
                 'launches_per_step': table[dom]['launches'], 'step_share': table[dom]['share'],
                 'whole_step': {'algorithmic_bytes': step_bytes, 'achieved': step_bytes / (ms / a.steps * 1e-3) / 1e9,
                                'frac': step_bytes / (ms / a.steps * 1e-3) / 1e9 / peak},
-                'note': 'fast9_cells is bound by instruction issue on the integer pipes (ncu: issue active 80 %, ALU pipe 69 %, DRAM 3 %), '
+                'note': 'fast9_cells is bound by instruction issue on the integer pipes (ncu: issue active 75 %, ALU pipe 71 %, DRAM 5 %), '
                         'not by HBM: profiles/r02_fast_ncu.md'}
         # Hamming throughput of the matcher kernel alone (both cross-check directions are evaluated)
         mk = 'hamming_i8mma' if a.match_impl == 'tc' else 'hamming_knn'
