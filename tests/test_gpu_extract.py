@@ -137,6 +137,30 @@ def test_edge_shapes_and_flat_images(tb, ctx, oracle, shape):
             fe.close()
 
 
+@pytest.mark.parametrize('width', [282, 283, 538, 539, 290, 547])
+def test_fast_tile_geometry_edges(tb, ctx, oracle, width):
+    """Widths that put the FAST tile at its limits: cells of 32 columns (a tile of eight is the full 256 interior columns of
+    the compile-time tile pitch), tile origins that are / are not 16-byte aligned (the tile is staged in 16- or 8-byte units),
+    ragged last tiles. Three frames so that the batch path runs too; textured and noisy content."""
+    from trackingbench_slam_b200.synth import synth_frame
+    h = 150
+    rng = np.random.default_rng(width)
+    frames = np.stack([synth_frame(width, width, h), rng.integers(0, 256, (h, width), dtype=np.uint8), synth_frame(7, width, h)])
+    nl, sc, tgt, a, b = 2, 0.9, 400, 20.0, 7.0
+    fe, sf = _frontend(tb, ctx, (h, width), nl, sc, 3, tgt)
+    try:
+        fe.upload_frames(0, frames)
+        fe.build_pyramid(3)
+        fe.extract(3, sf, tgt, a, b)
+        for f in range(3):
+            k, d = fe.get_results(f)
+            lv, _ = oracle.pyramid(frames[f], nl, sc)
+            ko, do, _ = oracle.orb_extract(lv, sf, tgt, a, b)
+            assert kp_bytes_equal(k, ko) and np.array_equal(d, do), (width, f)
+    finally:
+        fe.close()
+
+
 def test_pyramid_exact_half_scale(tb, ctx, oracle):
     """Frame(...,4,0.5) (test_projection.cpp:723): OpenCV switches to INTER_AREA on exact 2x."""
     img = np.random.default_rng(11).integers(0, 256, (480, 640), dtype=np.uint8)

@@ -21,7 +21,14 @@
 #include "kernels.cuh"
 #include <algorithm>
 
+#ifndef OCT_THREADS
 #define OCT_THREADS 512
+#endif
+#ifdef OCT_MINB
+#define OCT_BOUNDS __launch_bounds__(OCT_THREADS, OCT_MINB)
+#else
+#define OCT_BOUNDS __launch_bounds__(OCT_THREADS)
+#endif
 
 
 struct OctSmem {
@@ -113,7 +120,7 @@ struct OctArgsAll { OctArgs lv[TB_MAX_LEVELS]; int nid_cache_keys; };
 
 // grid = (frames, levels): all (frame, level) problems of a batch in ONE launch, so the short per-level
 // tails overlap instead of serialising eight launches that are each bounded by their slowest CTA.
-__global__ void __launch_bounds__(OCT_THREADS)
+__global__ void OCT_BOUNDS
 octree_distribute(const __grid_constant__ OctArgsAll all)
 {
     const OctArgs &a = all.lv[blockIdx.y];
