@@ -562,8 +562,7 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
                 a.magic_wcell = magic(g.wCell);
             }
             a.initTh = (int)initTh; a.minTh = (int)minTh;
-            static const int unsTh = getenv("TB_FAST_UNSIGNED_TH") ? atoi(getenv("TB_FAST_UNSIGNED_TH")) : 12;
-            a.unsignedTh = unsTh; a.one = 1;
+            a.one = 1;
             a.cand = fe->cand[l]; a.cand_cap = g.cand_cap;
             a.n_cand = fe->n_cand + l; a.n_cand_stride = L;
             a.overflow = fe->overflow;

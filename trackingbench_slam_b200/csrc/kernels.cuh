@@ -35,7 +35,6 @@ struct FastArgs {
     uint32_t magic_groups, magic_w8, magic_wcell;   // 2^32/n rounded up for the full-width tile (0 when n == 1)
     int initTh, minTh;
     uint32_t one;      // 1 (a multiplier ptxas cannot fold: keeps some adds on the FMA pipe)
-    int unsignedTh;    // passes with a threshold >= this use the polarity-free compass prefilter (fewer instructions, a few more survivors)
     uint32_t *cand; int cand_cap;
     int *n_cand; int n_cand_stride;
     int *overflow;
