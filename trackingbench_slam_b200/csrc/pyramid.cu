@@ -63,7 +63,9 @@ bool tb_resize_is_area2(int sw, int sh, int dw, int dh)
 // Every source byte is read from HBM once, every output byte written once; consecutive output rows share
 // their source rows through H instead of recomputing the horizontal interpolation.
 #define PYR_TW 256
+#ifndef PYR_TH
 #define PYR_TH 32
+#endif
 extern __shared__ __align__(128) uint8_t pyr_smem[];
 
 __global__ void __launch_bounds__(256)
@@ -135,7 +137,9 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 // are interpolated, so no thread issues a global load and the table entries are read once per CTA instead of once per frame.
 #define PYR_BOXW 192
 #define PYR_FPC 8
+#ifndef PYR_STAGES
 #define PYR_STAGES 3   // source boxes in flight (the register file limits the kernel to 3 CTAs/SM, shared memory has room)
+#endif
 // hi32(a * b) + c
 __device__ __forceinline__ uint32_t pyr_madhi(uint32_t a, uint32_t b, uint32_t c)
 {
