@@ -41,6 +41,15 @@ struct OctSmem {
     unsigned long long *skey; // [pow2(node_cap)] sort keys / best keys
 };
 
+// v / d for 0 <= v < 2^16 with magic = 2^32 / d rounded up (0 for d == 1)
+__device__ __forceinline__ int oct_div(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
+// keypoint coordinates are integers (the reference compares them as floats: same result, without four conversions per key)
+__device__ __forceinline__ int oct_child_i(short4 b, int x, int y)
+{
+    const int mx = b.x + ((b.y - b.x + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
+    const int my = b.z + ((b.w - b.z + 1) >> 1);   // UL.y + ceil((BR.y-UL.y)/2)
+    return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
 __device__ __forceinline__ int oct_child(short4 b, float x, float y)
 {
     const int mx = b.x + ((b.y - b.x + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
@@ -219,7 +228,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
                 const int k = k0 + j * OCT_THREADS;
                 if (k >= n) break;
                 const int ni = nid[k];
-                if (cnt[ni] > 1) atomicAdd(&V[4 * ni + oct_child(box[ni], (float)cand_x(cc[j]), (float)cand_y(cc[j]))], 1);
+                if (cnt[ni] > 1) atomicAdd(&V[4 * ni + oct_child_i(box[ni], cand_x(cc[j]), cand_y(cc[j]))], 1);
             }
         }
         __syncthreads();
@@ -329,10 +338,10 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
                 const int ni = nid[k];
                 const uint32_t c = cc[j];
                 int nn;
-                if (S.aux2[ni] > 0) nn = V[4 * ni + oct_child(box[ni], (float)cand_x(c), (float)cand_y(c))];
+                if (S.aux2[ni] > 0) nn = V[4 * ni + oct_child_i(box[ni], cand_x(c), cand_y(c))];
                 else nn = S.aux[ni];
                 nid[k] = (uint16_t)nn;
-                if (ncnt[nn] > 1) atomicAdd(&W[4 * nn + oct_child(nbox[nn], (float)cand_x(c), (float)cand_y(c))], 1);
+                if (ncnt[nn] > 1) atomicAdd(&W[4 * nn + oct_child_i(nbox[nn], cand_x(c), cand_y(c))], 1);
             }
         }
         for (int e = tid; e < NE; e += OCT_THREADS) {
@@ -365,6 +374,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
 
     // ---- best key per leaf (:700-716): max response, first in vKeys order
     const int L = s_L;
+    const uint32_t magic_h = a.hCell > 1 ? 0xFFFFFFFFu / (uint32_t)a.hCell + 1u : 0u, magic_w = a.wCell > 1 ? 0xFFFFFFFFu / (uint32_t)a.wCell + 1u : 0u;
     for (int i = tid; i < L; i += OCT_THREADS) { S.skey[i] = 0; S.aux2[i] = 1; }
     __syncthreads();
     for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
@@ -377,7 +387,8 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
             if (k >= n) break;
             const uint32_t c = cc[j];
             int x = cand_x(c), y = cand_y(c);
-            unsigned long long ord = ((unsigned long long)((y - 3) / a.hCell) << 32) | ((unsigned long long)((x - 3) / a.wCell) << 24) |
+            // (y - 3) / hCell and (x - 3) / wCell by multiply-high (exact: the dividends are below 4096, the cells a few dozen pixels)
+            unsigned long long ord = ((unsigned long long)oct_div(y - 3, magic_h) << 32) | ((unsigned long long)oct_div(x - 3, magic_w) << 24) |
                                      ((unsigned long long)y << 12) | (unsigned long long)x;
             unsigned long long key = ((unsigned long long)cand_m(c) << 40) | (~ord & 0xFFFFFFFFFFull);
             atomicMax(&S.skey[nid[k]], key);
