@@ -215,8 +215,9 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
     //      the pass before, which already has the key's coordinates in hand (one sweep over the keys per pass, not two)
     {
         const int L0 = s_L;
-        const short4 *box = S.box[cur];
-        const int *cnt = S.cnt[cur];
+        const short4 *box = cur ? S.box[1] : S.box[0];   // constant indices: a dynamically indexed pointer pair puts the whole
+        const int *cnt = cur ? S.cnt[1] : S.cnt[0];      // struct in local memory and every table access becomes a generic load
+
         for (int i = tid; i < 4 * L0; i += OCT_THREADS) V[i] = 0;
         __syncthreads();
         for (int k0 = tid; k0 < n; k0 += OCT_MLP * OCT_THREADS) {
@@ -235,8 +236,10 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
     }
     for (;;) {
         const int L = s_L;
-        short4 *box = S.box[cur], *nbox = S.box[cur ^ 1];
-        int *cnt = S.cnt[cur], *ncnt = S.cnt[cur ^ 1];
+        short4 *box = cur ? S.box[1] : S.box[0], *nbox = cur ? S.box[0] : S.box[1];
+        int *cnt = cur ? S.cnt[1] : S.cnt[0], *ncnt = cur ? S.cnt[0] : S.cnt[1];
+        // the node tables live in shared memory: say so, or every access is a generic load with 64-bit address arithmetic
+        // (the pointers come out of swaps and an indexed pair, which hides their address space from the compiler)
         // ---- (B) who splits, in which processing order
         // aux2[i] = number of non-empty children (0 for nodes that cannot split)
         for (int i = tid; i < L; i += OCT_THREADS) {
