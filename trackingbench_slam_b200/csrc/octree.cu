@@ -129,8 +129,11 @@ struct OctArgsAll { OctArgs lv[TB_MAX_LEVELS]; int nid_cache_keys; };
 
 // grid = (frames, levels): all (frame, level) problems of a batch in ONE launch, so the short per-level
 // tails overlap instead of serialising eight launches that are each bounded by their slowest CTA.
-__global__ void OCT_BOUNDS
-octree_distribute(const __grid_constant__ OctArgsAll all)
+// NIDS: the per-key node indices of this (frame, level) fit the launch's shared-memory key cache.  Two instantiations so that
+// the compiler knows the address space of nid[] in each (one pointer that is shared or global at run time is a generic
+// pointer: 64-bit address arithmetic and generic loads in every sweep).
+template <bool NIDS>
+__device__ __forceinline__ void octree_body(const OctArgsAll &all)
 {
     const OctArgs &a = all.lv[blockIdx.y];
     const int tid = threadIdx.x;
@@ -159,7 +162,7 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         S.aux2 = reinterpret_cast<int *>(p); p += sizeof(int) * NC;
         // every pass reads and rewrites nid[k] of all keys (27 k at level 0 of a 1080p frame): keep it in shared memory
         // instead of L2 when it fits the launch's key cache
-        if (n <= all.nid_cache_keys) nid = reinterpret_cast<uint16_t *>(p);
+        if (NIDS) nid = reinterpret_cast<uint16_t *>(p);
     }
     __shared__ int s_L, s_exp, s_cut;
 
@@ -426,6 +429,16 @@ octree_distribute(const __grid_constant__ OctArgsAll all)
         a.n_kept[(size_t)f * a.n_stride] = min(nk, a.kept_cap);
         if (nk > a.kept_cap) atomicExch(a.overflow, 3);
     }
+}
+
+__global__ void OCT_BOUNDS
+octree_distribute(const __grid_constant__ OctArgsAll all)
+{
+    const OctArgs &a = all.lv[blockIdx.y];
+    int n = a.n_cand[(size_t)blockIdx.x * a.n_stride];
+    if (n > a.cand_cap) n = a.cand_cap;
+    if (n <= all.nid_cache_keys) octree_body<true>(all);
+    else octree_body<false>(all);
 }
 
 size_t tb_octree_smem_bytes(int node_cap)
