@@ -68,7 +68,9 @@ __device__ __forceinline__ short4 oct_child_box(short4 b, int c)
 
 // The key sweeps are bound by the latency of cand[k] (L2, one dependent load per iteration — ncu: 35 % of the stall samples sit
 // on its first use): every sweep fetches OCT_MLP candidates per thread before it touches the first one.
+#ifndef OCT_MLP
 #define OCT_MLP 4
+#endif
 
 // In-place exclusive scan of a[0..n) (shared memory); returns the total. All threads must call.
 __device__ int block_excl_scan(int *a, int n)
@@ -230,9 +232,10 @@ __device__ __forceinline__ void octree_body(const OctArgsAll &all)
 #pragma unroll
             for (int j = 0; j < OCT_MLP; j++) {
                 const int k = k0 + j * OCT_THREADS;
-                if (k >= n) break;
-                const int ni = nid[k];
-                if (cnt[ni] > 1) atomicAdd(&V[4 * ni + oct_child_i(box[ni], cand_x(cc[j]), cand_y(cc[j]))], 1);
+                const bool valid = k < n;
+                const int ni = valid ? (int)nid[k] : 0;
+                const int ch = oct_child_i(box[ni], cand_x(cc[j]), cand_y(cc[j]));
+                if (valid && cnt[ni] > 1) atomicAdd(&V[4 * ni + ch], 1);
             }
         }
         __syncthreads();
@@ -336,18 +339,34 @@ __device__ __forceinline__ void octree_body(const OctArgsAll &all)
             uint32_t cc[OCT_MLP];
 #pragma unroll
             for (int j = 0; j < OCT_MLP; j++) { const int k = k0 + j * OCT_THREADS; cc[j] = k < n ? __ldg(&cand[k]) : 0u; }
-#pragma unroll
+            // branch-free and in stages (all loads of a stage for the OCT_MLP keys, then the next stage), so that the dependent
+            // chains (nid -> aux2/box -> V -> ncnt/nbox -> vote: shared-memory round trips) overlap instead of running one after
+            // the other; stores and votes come last because the compiler must assume they alias the tables. Keys past the end
+            // read node 0 and store nothing.
+            int ni[OCT_MLP], nn[OCT_MLP], px[OCT_MLP], py[OCT_MLP], a2[OCT_MLP], nc[OCT_MLP];
+            short4 bx[OCT_MLP];
+            bool valid[OCT_MLP];
 #pragma unroll
             for (int j = 0; j < OCT_MLP; j++) {
                 const int k = k0 + j * OCT_THREADS;
-                if (k >= n) break;
-                const int ni = nid[k];
-                const uint32_t c = cc[j];
-                int nn;
-                if (S.aux2[ni] > 0) nn = V[4 * ni + oct_child_i(box[ni], cand_x(c), cand_y(c))];
-                else nn = S.aux[ni];
-                nid[k] = (uint16_t)nn;
-                if (ncnt[nn] > 1) atomicAdd(&W[4 * nn + oct_child_i(nbox[nn], cand_x(c), cand_y(c))], 1);
+                valid[j] = k < n;
+                ni[j] = valid[j] ? (int)nid[k] : 0;
+                px[j] = cand_x(cc[j]); py[j] = cand_y(cc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) { a2[j] = S.aux2[ni[j]]; bx[j] = box[ni[j]]; }
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) {
+                const int *src = a2[j] > 0 ? &V[4 * ni[j] + oct_child_i(bx[j], px[j], py[j])] : &S.aux[ni[j]];
+                nn[j] = max(*src, 0);                 // (only a key past the end can meet an empty child's -1)
+            }
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) { nc[j] = ncnt[nn[j]]; bx[j] = nbox[nn[j]]; }
+#pragma unroll
+            for (int j = 0; j < OCT_MLP; j++) {
+                const int k = k0 + j * OCT_THREADS;
+                if (valid[j]) nid[k] = (uint16_t)nn[j];
+                if (valid[j] && nc[j] > 1) atomicAdd(&W[4 * nn[j] + oct_child_i(bx[j], px[j], py[j])], 1);
             }
         }
         for (int e = tid; e < NE; e += OCT_THREADS) {
