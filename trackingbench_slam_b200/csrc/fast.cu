@@ -12,11 +12,12 @@
 //  * Cell ROIs are [ini, ini+cell+6) with a 3-px untested border, so cell INTERIORS tile the level
 //    exactly with period (wCell, hCell); a cell is self-contained: tile = interior + 3-px ring halo.
 //  * A cell uses initTh if any NMS survivor has m > initTh, else minTh.
-// One CTA handles G consecutive cells of one cell row: the u8 tile (+halo) is staged once in
-// shared memory with 8-byte coalesced loads; a byte-SIMD prefilter and two exact tests thin the
-// pixels through compacted shared work lists so every expensive stage runs on dense lanes;
-// survivors are appended to the (frame, level) candidate array with one global atomic per CTA.  Candidate ORDER in memory is arbitrary: every consumer
-// derives the reference's order (cell row, cell col, y, x) from the coordinates themselves.
+// One CTA (four warps) handles G consecutive cells of one cell row: the u8 tile (+halo) is staged once in
+// shared memory by cp.async; a byte-SIMD prefilter thins the pixels into per-warp queues so that the exact
+// arc score runs on dense lanes; corners go to per-warp lists, the warp that found a corner does its NMS,
+// survivors are appended to the (frame, level) candidate array with one global atomic per warp and pass.
+// Candidate ORDER in memory is arbitrary: every consumer derives the reference's order (cell row, cell col,
+// y, x) from the coordinates themselves.
 #include "common.cuh"
 #include "kernels.cuh"
 #include <algorithm>
@@ -102,58 +103,18 @@ __device__ __forceinline__ uint32_t compass_unsigned(uint32_t n, uint32_t s_, ui
 __device__ __forceinline__ uint32_t div_magic(int n) { return n > 1 ? 0xFFFFFFFFu / (uint32_t)n + 1u : 0u; }
 __device__ __forceinline__ int fast_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
 
-// plain shared-memory atomic add: the callers already aggregate per warp, so bypass the compiler's own
-// warp-aggregation wrapper around atomicAdd
-__device__ __forceinline__ int atom_add_shared(int *addr, int v)
-{
-    int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
-    return old;
-}
-
-// warp-aggregated append of `cnt` (0..8) items per lane: returns this lane's first slot
-__device__ __forceinline__ int warp_reserve(int cnt, int *counter)
-{
-    const int lane = threadIdx.x & 31;
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
-    int base = 0;
-    if (total) {
-        if (lane == 31) base = atom_add_shared(counter, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-    }
-    return base + inc - cnt;
-}
-
-__device__ __forceinline__ int warp_append1(bool pred, int *counter)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned bal = __ballot_sync(0xffffffffu, pred);
-    int base = 0;
-    if (bal) {
-        if (lane == 0) base = atom_add_shared(counter, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-    }
-    return base + __popc(bal & ((1u << lane) - 1));
-}
-
 // Pipeline of one CTA (G cells of one cell row), every stage on dense lanes:
-//   0  stage the u8 tile (+3-px halo) with 16-byte loads
+//   0  stage the u8 tile (+3-px halo) by cp.async (16- or 8-byte units)
 //   then, at T = initTh for every cell and again at T = minTh only for the cells that produced no
 //   keypoint (the reference's two cv::FAST calls, ORBextractor.cpp:785-792) — stages 1-4 are fused per
 //   warp (private survivor queue, no block barrier in between):
 //   1+2  SWAR prefilter, 16 px per thread: a FAST-9 corner at T needs two ADJACENT compass pixels
-//      (N,E,S,W at radius 3) both brighter than centre+T or both darker than centre-T; per 4 px and
-//      compass pixel: VABSDIFF4 + 3 ops for |d| > T and 3 ops for the sign
+//      (N,E,S,W at radius 3) that differ from the centre by more than T; per 4 px and compass pixel:
+//      VABSDIFF4 + 3 ops for |d| > T (the polarity is left to the arc score)
 //   3+4  arc score m (both polarities packed in 16-bit lanes, VIMNMX3) of every survivor; corner <=> m > T -> m map,
 //      corner appended to the warp's own list (warp-uniform counter in a register: no atomics)
-//   5  NMS inside the cell interior by the warp that found the corner, survivors written straight to the
-//      candidate array (one global atomic per warp and round)
+//   5  NMS inside the cell interior by the warp that found the corner, survivors collected in the warp's (dead)
+//      queue and written to the candidate array with one global atomic per warp and pass
 // The tile pitch is a compile-time constant: queue and list entries are byte offsets into the tile, the m map has the
 // tile's pitch (plus a zero row above and below), so ring and neighbour reads are LDS with immediate offsets from one
 // register.
@@ -165,7 +126,7 @@ static_assert(TB_FAST_TPITCH % 16 == 0 && TB_FAST_TPITCH / 16 <= 32, "the pass-2
 #define FAST_TP TB_FAST_TPITCH
 struct FastSmem {
     uint8_t *tile, *scp, *colInfo, *need;   // scp[o] = m of the pixel at tile offset o (0 = not a corner)
-    uint16_t *queue, *listB;   // per-warp queues (8 x FAST_QCAP), per-warp corner lists (8 x capW entries)
+    uint16_t *queue, *listB;   // per-warp queues (FAST_NW x FAST_QCAP), per-warp corner lists (FAST_NW x capW entries)
 };
 
 // NMS of one corner (tile offset o) + emission bookkeeping; returns keep and the packed candidate
