@@ -94,3 +94,54 @@ def test_sharded_knn2_world1_and_cross_check(tb, oracle, impl):
                 assert np.array_equal(i12.cpu().numpy()[mu], bf['trainIdx']) and np.array_equal(b12.cpu().numpy()[mu].astype(np.float32), bf['distance'])
         finally:
             ctx.close()
+
+
+def test_side_stream_pyramid_is_joined_by_every_reader(tb, oracle):
+    """Batches of >= 32 frames build their pyramid on a side stream (FAST of level l only waits for level l). Everything
+    else has to wait for the whole pyramid: reading the levels right after build_pyramid, overwriting level 0 with the next
+    batch while the coarse levels may still be read from it, a second frontend on the same ctx in between."""
+    from trackingbench_slam_b200.synth import synth_stream
+    W, H, nl, sc, tgt = 640, 360, 6, 1.0 / 1.2, 500
+    batch = 36
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = tb.Context(0, stream.cuda_stream)
+        sf, lw, lh = tb.pyramid_geometry(W, H, nl, sc)
+        fe = tb.Frontend(ctx, lw, lh, max_batch=batch, max_target=tgt)
+        sf2, lw2, lh2 = tb.pyramid_geometry(320, 200, 3, 0.8)
+        fe2 = tb.Frontend(ctx, lw2, lh2, max_batch=batch, max_target=tgt)
+        try:
+            fa, fb = synth_stream(batch, W, H, seed0=5), synth_stream(batch, W, H, seed0=900)
+            small = synth_stream(batch, 320, 200, seed0=31)
+            # (1) levels read straight after the build
+            fe.upload_frames(0, fa)
+            fe.build_pyramid(batch)
+            for f in (0, batch - 1):
+                lv, _ = oracle.pyramid(fa[f], nl, sc)
+                for l in range(nl):
+                    assert np.array_equal(fe.download_level(f, l), lv[l]), ('levels after build', f, l)
+            # (2) the next batch overwrites level 0 right behind a build; a second frontend's build and extract in between
+            for rep in range(3):
+                fe.upload_frames(0, fa)
+                fe.build_pyramid(batch)
+                fe2.upload_frames(0, small)
+                fe2.build_pyramid(batch)
+                fe.upload_frames(0, fb)
+                fe.build_pyramid(batch)
+                fe2.extract(batch, sf2, tgt, 20.0, 7.0)
+                fe.extract(batch, sf, tgt, 20.0, 7.0)
+            ctx.sync()
+            kps, desc, counts = fe.get_results_batch(batch)
+            for f in (0, 17, batch - 1):
+                lv, sfo = oracle.pyramid(fb[f], nl, sc)
+                ko, do, _ = oracle.orb_extract(lv, sfo, tgt, 20.0, 7.0)
+                assert counts[f] == len(ko) and kps[f, :counts[f]].tobytes() == ko.tobytes() and np.array_equal(desc[f, :counts[f]], do), f
+            k2, d2, c2 = fe2.get_results_batch(batch)
+            for f in (0, batch - 1):
+                lv, sfo = oracle.pyramid(small[f], 3, 0.8)
+                ko, do, _ = oracle.orb_extract(lv, sfo, tgt, 20.0, 7.0)
+                assert c2[f] == len(ko) and k2[f, :c2[f]].tobytes() == ko.tobytes() and np.array_equal(d2[f, :c2[f]], do), ('second frontend', f)
+        finally:
+            fe.close()
+            fe2.close()
+            ctx.close()

@@ -72,6 +72,9 @@ struct tb_ctx {
     cudaStream_t side = nullptr, side2 = nullptr;   // side: Gaussian levels; side2: per-level octree launches behind FAST
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_lvl[TB_MAX_LEVELS] = {};
+    cudaEvent_t ev_pyr[TB_MAX_LEVELS] = {};   // level l of a pyramid built on the side stream is complete
+    bool pyr_pending = false;                 // the main stream has not yet waited for the levels built on the side stream
+    int pyr_last = 0;                         // index of the last ev_pyr recorded by that build
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -120,7 +123,19 @@ static inline int tb_fail(tb_ctx *ctx, int code, const char *fmt, const char *a 
 
 // every extern "C" entry point makes its ctx's device current first: two ctxs on different GPUs may share a host thread, and the
 // caller (e.g. torch) may have switched devices between calls
-#define TB_DEVICE_GUARD(c) do { const tb_ctx *c__ = (c); if (c__) cudaSetDevice(c__->device); } while (0)
+// ... and waits (on the ctx's main stream) for a pyramid that tb_frontend_build_pyramid is still building on the side stream:
+// only tb_frontend_extract lets its FAST launches wait level by level instead (TB_DEVICE_GUARD_NOJOIN)
+static inline void tb_device_guard(tb_ctx *c, bool join_pyramid)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (join_pyramid && c->pyr_pending) {
+        cudaStreamWaitEvent(c->stream, c->ev_pyr[c->pyr_last], 0);
+        c->pyr_pending = false;
+    }
+}
+#define TB_DEVICE_GUARD(c) tb_device_guard(const_cast<tb_ctx *>(static_cast<const tb_ctx *>(c)), true)
+#define TB_DEVICE_GUARD_NOJOIN(c) tb_device_guard(const_cast<tb_ctx *>(static_cast<const tb_ctx *>(c)), false)
 
 #define TB_CUDA(ctx, expr)                                                                    \
     do {                                                                                      \

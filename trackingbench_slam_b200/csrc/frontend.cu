@@ -31,6 +31,7 @@ extern "C" int tb_ctx_create(int device, void *stream, tb_ctx **out)
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     bool ev_ok = true;
     for (int l = 0; l < TB_MAX_LEVELS; l++) ev_ok = ev_ok && cudaEventCreateWithFlags(&c->ev_lvl[l], cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < TB_MAX_LEVELS; l++) ev_ok = ev_ok && cudaEventCreateWithFlags(&c->ev_pyr[l], cudaEventDisableTiming) == cudaSuccess;
     const int side_prio = getenv("TB_GAUSS_PRIO") ? (atoi(getenv("TB_GAUSS_PRIO")) > 0 ? prio_hi : prio_lo) : 0;   // tuning knob (default priority measured best)
     if (!ev_ok || cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_prio) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||   // its few CTAs go first
@@ -64,6 +65,7 @@ extern "C" void tb_ctx_destroy(tb_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     for (int l = 0; l < TB_MAX_LEVELS; l++) if (ctx->ev_lvl[l]) cudaEventDestroy(ctx->ev_lvl[l]);
+    for (int l = 0; l < TB_MAX_LEVELS; l++) if (ctx->ev_pyr[l]) cudaEventDestroy(ctx->ev_pyr[l]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -423,12 +425,38 @@ static int pyramid_enqueue(tb_frontend *fe, int n_frames)
     return TB_OK;
 }
 
+// Large batches: the level chain runs on the side stream and records an event per level; tb_frontend_extract lets FAST(l)
+// wait for level l only, so FAST of the fine levels overlaps the resizes of the coarse ones (both kernels are bound by
+// instruction issue on different pipes and by their launch tails: 6.16 -> 5.96 ms per 256-frame 1080p step). Every other
+// entry point waits for the whole pyramid first (TB_DEVICE_GUARD). TB_PYR_ASYNC=0 builds on the main stream.
+static int pyramid_enqueue_async(tb_frontend *fe, int n_frames)
+{
+    tb_ctx *ctx = fe->ctx;
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side;
+    int rc = TB_OK;
+    for (int l = 1; l < fe->L && rc == TB_OK; l++) {
+        const LevelGeom &s = fe->g[l - 1], &d = fe->g[l];
+        rc = tb_launch_resize(ctx, fe->pyr[l - 1], s.pitch, s.frame_stride, fe->pyr[l], d.pitch, d.frame_stride,
+                              d.w, d.h, fe->xtab[l], fe->ytab[l], fe->area2[l], n_frames, fe->box_pitch[l], fe->box_rows[l],
+                              fe->has_tmap[l] ? &fe->pyr_tmap[l] : nullptr, fe->span8[l]);
+        if (cudaEventRecord(ctx->ev_pyr[l], ctx->side) != cudaSuccess && rc == TB_OK) rc = TB_E_CUDA;
+    }
+    ctx->stream = main_stream;
+    if (fe->L > 1) { ctx->pyr_pending = true; ctx->pyr_last = fe->L - 1; }   // (also after a failed launch: what was enqueued is waited for)
+    return rc;
+}
+
 extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
 {
     TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || n_frames < 0 || n_frames > fe->B) return TB_E_INVALID;
     if (n_frames == 0) return TB_OK;
     tb_ctx *ctx = fe->ctx;
+    static const bool pyr_async = !(getenv("TB_PYR_ASYNC") && atoi(getenv("TB_PYR_ASYNC")) == 0);   // A/B knob: 0 = build on the main stream
+    if (pyr_async && !ctx->profiling && n_frames >= 32) return pyramid_enqueue_async(fe, n_frames);
     if (ctx->profiling || !graph_worthwhile(fe, n_frames)) return pyramid_enqueue(fe, n_frames);
     const bool same = fe->g_pyramid.n_frames == n_frames;
     fe->g_pyramid.n_frames = n_frames;
@@ -455,7 +483,7 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
 extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *sf, int target, float initTh, float minTh,
                                    const tb_keypoint *exit_kps, int n_exit)
 {
-    TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
+    TB_DEVICE_GUARD_NOJOIN(fe ? fe->ctx : nullptr);   // extract_enqueue waits for the pyramid level by level
     if (!fe || !sf || n_frames < 0 || n_frames > fe->B || target <= 0 || n_exit < 0) return TB_E_INVALID;
     tb_ctx *ctx = fe->ctx;
     if (target > fe->max_target) return tb_fail(ctx, TB_E_INVALID, "target exceeds the frontend's max_target");
@@ -483,6 +511,7 @@ extern "C" int tb_frontend_extract(tb_frontend *fe, int n_frames, const float *s
     }
     if (add_points || ctx->profiling || !graph_worthwhile(fe, n_frames))
         return extract_enqueue(fe, n_frames, sf, initTh, minTh, add_points, n_exit);
+    TB_DEVICE_GUARD(ctx);   // a replayed graph cannot wait level by level: join a pyramid that is still being built
     tb_frontend::GraphSlot &gs = fe->g_extract;
     bool same = gs.n_frames == n_frames && gs.target == target && gs.initTh == initTh && gs.minTh == minTh;
     for (int l = 0; l < L && same; l++) same = gs.sf[l] == sf[l];
@@ -579,6 +608,7 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             }
             static const int smem_pad = getenv("TB_FAST_SMEM_PAD") ? atoi(getenv("TB_FAST_SMEM_PAD")) : 0;   // developer knob: fewer resident CTAs for A/B runs
             size_t smem = tb_fast_smem_bytes(g.hCell, a.scw, a.tpitch, a.list_cap) + smem_pad;
+            if (ctx->pyr_pending && l >= 1 && l <= ctx->pyr_last) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pyr[l], 0));
             int rc = tb_launch_fast(ctx, a, g.nColsRun, g.nRowsRun, n_frames, smem);
             if (rc) return rc;
         }
@@ -597,6 +627,10 @@ static int extract_enqueue(tb_frontend *fe, int n_frames, const float *sf, float
             if (rc) return rc;
             if (desc_per_level) { rc = tb_launch_describe(ctx, d, fe->budget[l] + 4, n_frames, l, 1, os); if (rc) return rc; }
         }
+    }
+    if (ctx->pyr_pending) {   // every level has been waited for (levels without a FAST launch: wait for the last one)
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pyr[ctx->pyr_last], 0));
+        ctx->pyr_pending = false;
     }
     if (!per_level) {
         int rc = tb_launch_octree(ctx, oct, L, n_frames, ctx->stream);
