@@ -191,7 +191,8 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
                                           const int hEff, const int wEff, const int cs, const int capW,
                                           const int xbase, const int cand_y0, uint8_t *s_has, int *s_ovf,
                                           const int col_lo, const int col_hi,   // interior columns [col_lo, col_hi) to test
-                                          const uint8_t *glist, const int n_glist)  // pass 2: the 16-pixel groups that touch a cell to redo
+                                          const uint8_t *glist, const int n_glist,  // pass 2: the 16-pixel groups that touch a cell to redo
+                                          const bool last_pass)                     // nothing follows: no block barrier at the end
 {
     constexpr int tp = FAST_TP;
     const int tid = threadIdx.x;
@@ -322,7 +323,7 @@ __device__ __forceinline__ void fast_pass(const FastArgs &a, const FastSmem &S, 
         }
     }
     em.flush(a, f);
-    __syncthreads();
+    if (!last_pass) __syncthreads();
 }
 
 __global__ void __launch_bounds__(FAST_NT, TB_FAST_CTAS)
@@ -352,7 +353,7 @@ fast9_cells(FastArgs a)
     S.need = S.colInfo + tp;                                         // tp : 0x80 where this pass tests the byte column
     S.queue = reinterpret_cast<uint16_t *>(S.need + tp);
     S.listB = S.queue + FAST_NW * FAST_QCAP;
-    __shared__ int s_ovf, s_mask, s_ng;
+    __shared__ int s_ovf, s_ng;
     __shared__ uint8_t s_has[64], s_glist[32];
 
     const uint8_t *img = a.img + (size_t)f * a.frame_stride;
@@ -401,17 +402,14 @@ fast9_cells(FastArgs a)
 
     const int xbase = cj0 * a.wCell - cs + 3, cand_y0 = ci * a.hCell;   // candidate x = xbase + tile column, y = cand_y0 + tile row
     // pass 1: every cell at initTh (ORBextractor.cpp:785)
-    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, nullptr, 0);
+    fast_pass(a, S, a.initTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, nullptr, 0, a.minTh == a.initTh);
     // pass 2: cells without a keypoint again at minTh (:788-792)
     if (a.minTh == a.initTh) return;
     const int nCells = (wEff + a.wCell - 1) / a.wCell;     // <= 32 (the host caps G)
-    if (tid < 32) {
-        const unsigned mk = __ballot_sync(0xffffffffu, tid < nCells && !s_has[tid]);
-        if (tid == 0) { s_mask = (int)mk; s_ovf = 0; }
-    }
-    __syncthreads();
-    const unsigned mk = (unsigned)s_mask;
+    // (pass 1 ended with a block barrier: s_has is final; every warp forms the mask itself, no broadcast and no barrier)
+    const unsigned mk = __ballot_sync(0xffffffffu, (tid & 31) < nCells && !s_has[tid & 31]);
     if (mk == 0) return;
+    if (tid == 0) s_ovf = 0;
     for (int i = tid; i < tp; i += FAST_NT) S.need[i] = (i >= cs && i < ce && ((mk >> (S.colInfo[i] & 63)) & 1)) ? 0x80 : 0;
     // the 16-pixel groups that hold a column to redo, in order (tp / 16 <= 32 groups: one warp's ballot): a group is
     // needed when one of the cells between its first and its last interior column is in the mask
@@ -428,7 +426,7 @@ fast9_cells(FastArgs a)
     }
     __syncthreads();
     const int n_glist = s_ng;
-    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist);
+    fast_pass(a, S, a.minTh, f, hEff, wEff, cs, capW, xbase, cand_y0, s_has, &s_ovf, 0, wEff, s_glist, n_glist, true);
 }
 
 size_t tb_fast_smem_bytes(int hCell, int scw, int tpitch, int list_cap)
