@@ -137,6 +137,10 @@ pyr_resize_linear_u8(const uint8_t *__restrict__ src, int spitch, size_t sframe,
 // are interpolated, so no thread issues a global load and the table entries are read once per CTA instead of once per frame.
 #define PYR_BOXW 192
 #define PYR_FPC 8
+#ifndef PYR_ROW_UNROLL
+#define PYR_ROW_UNROLL 1   // row loop of the 8-column streaming kernel (2 and 4 measured: see profiles/r02_pyramid_ncu.md)
+#endif
+constexpr int kPyrRowUnroll = PYR_ROW_UNROLL;
 #ifndef PYR_STAGES
 #define PYR_STAGES 3   // source boxes in flight (the register file limits the kernel to 3 CTAs/SM, shared memory has room)
 #endif
@@ -493,7 +497,7 @@ pyr_resize_linear_u8_stream8(const __grid_constant__ CUtensorMap tmap, uint8_t *
             uint32_t hx[8], hy[8];
             int rx = -1, ry = -1;                          // source rows held in hx / hy
             const int nrows = min(PYR_TH / 8, ty1 - dy0 + 1);
-#pragma unroll 1
+#pragma unroll kPyrRowUnroll
             for (int kk = 0; kk < nrows; kk++) {
                 const uint32_t q = yq[kk];
                 const int r0 = (int)((q >> 24) & 0x7F), r1 = r0 + (int)(q >> 31);
