@@ -49,7 +49,26 @@
 // Layout of an expanded row r inside its tile: chunk c (16 bytes = 16 K elements) at (r/8)*TC_SBO + c*128 + (r%8)*16 — the
 // UMMA canonical K-major no-swizzle layout; the eight lanes of a quarter warp (consecutive rows) store 128 contiguous bytes.
 
-// train rows: two table look-ups per chunk (the arithmetic expansion cost ~21 integer instructions per chunk)
+// train rows: two table look-ups per chunk (the first arithmetic expansion cost ~21 integer instructions per chunk).
+// TC_EXPAND_ARITH: the byte -> 8 x (+-1) expansion without the table, 8 instructions per byte: bit i of a nibble is moved to the
+// most significant bit of byte i by ONE multiply (the partial products land on distinct bits, no carries), PRMT's sign-replicate
+// mode turns every byte into 0x00 / 0xFF, OR 0x01 makes that +1 / -1.  Takes the 16 KB of table reads per 64-row tile off the
+// shared-memory pipe and puts ~8 instructions per byte on the integer pipes — which the expander warps do not have to spare.
+#ifndef TC_EXPAND_ARITH
+#define TC_EXPAND_ARITH 0   // measured slower than the table (third session: 0.412 vs 0.401 ms batched, 7.45 vs 6.91 ms kNN-2)
+#endif
+__device__ __forceinline__ uint2 tc_expand_byte(uint32_t xw, int k)   // byte k of xw -> eight +-1 bytes
+{
+    const uint32_t b = k == 0 ? xw : __byte_perm(xw, 0u, 0x4440 + k);        // byte k in bits 0..7 (k = 0: the masks below suffice)
+    const uint32_t lo = (b & 0x0Fu) * 0x10204080u;                           // nibble bit i -> bit 8 i + 7
+    const uint32_t hi = (b & 0xF0u) * 0x01020408u;                           // bit 4 + i   -> bit 8 i + 7
+    return make_uint2(__byte_perm(lo, 0u, 0xBA98) | 0x01010101u, __byte_perm(hi, 0u, 0xBA98) | 0x01010101u);
+}
+#if TC_EXPAND_ARITH
+#define TC_EXPAND4(x, e0, e1, e2, e3) const uint2 e0 = tc_expand_byte(x, 0), e1 = tc_expand_byte(x, 1), e2 = tc_expand_byte(x, 2), e3 = tc_expand_byte(x, 3)
+#else
+#define TC_EXPAND4(x, e0, e1, e2, e3) const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16]
+#endif
 __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4 lo, const uint4 hi, bool valid, const uint2 *lut)
 {
     uint8_t *o = tile + (size_t)(r >> 3) * TC_SBO + (size_t)(r & 7) * 16;
@@ -62,7 +81,7 @@ __device__ __forceinline__ void expand_row_lut(uint8_t *tile, int r, const uint4
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const uint32_t x = w32[w];
-        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        TC_EXPAND4(x, e0, e1, e2, e3);
         *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
@@ -81,7 +100,7 @@ __device__ __forceinline__ void expand_quarter_lut(uint8_t *tile, int r, int par
 #pragma unroll
     for (int w = 0; w < 2; w++) {
         const uint32_t x = w32[w];
-        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        TC_EXPAND4(x, e0, e1, e2, e3);
         *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
@@ -109,7 +128,7 @@ __device__ __forceinline__ void expand_half_lut(uint8_t *tile, int r, int half, 
 #pragma unroll
     for (int w = 0; w < 4; w++) {
         const uint32_t x = w32[w];
-        const uint2 e0 = lut[(x & 0xFFu) * 16], e1 = lut[((x >> 8) & 0xFFu) * 16], e2 = lut[((x >> 16) & 0xFFu) * 16], e3 = lut[(x >> 24) * 16];
+        TC_EXPAND4(x, e0, e1, e2, e3);
         *reinterpret_cast<uint4 *>(o + (2 * w) * 128) = make_uint4(e0.x, e0.y, e1.x, e1.y);
         *reinterpret_cast<uint4 *>(o + (2 * w + 1) * 128) = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
