@@ -100,7 +100,10 @@ int tb_frontend_create(tb_ctx *ctx, int n_levels, const int32_t *level_w, const 
 void tb_frontend_destroy(tb_frontend *fe);
 int tb_frontend_kp_capacity(const tb_frontend *fe);
 
-/* Device layout of level `level`: frame f starts at base + f*frame_stride, rows are `pitch` apart. */
+/* Device layout of level `level`: frame f starts at base + f*frame_stride, rows are `pitch` apart.
+ * (Batches of >= 32 frames build levels >= 1 on a side stream of the ctx; every tb_* call orders itself behind that. Once a
+ * pointer to a level >= 1 has been handed out here, the frontend builds its pyramid on the ctx's own stream instead, so that
+ * the caller's kernels on that stream see complete levels.) */
 int tb_frontend_level_layout(const tb_frontend *fe, int level, int blurred, void **base_dptr,
                              size_t *pitch, size_t *frame_stride);
 /* H2D / D2H of one level of one frame (host row stride in bytes). */

@@ -157,6 +157,8 @@ struct tb_frontend {
     float2 *exit_xy = nullptr; int16_t *enid = nullptr; int exit_cap = 0;
     int budget[TB_MAX_LEVELS] = {};
     bool has_budget = false;
+    bool levels_exposed = false;   // a raw pointer to a level >= 1 was handed out (tb_frontend_level_layout): the pyramid is then
+                                   // always built on the main stream, so that a wait on the caller's stream covers it
     bool blur_valid = false;   // the dense blurred levels hold the Gaussian of the current pyramid (else made on demand)
     uint8_t *raw = nullptr; size_t raw_bytes = 0;   // staging for distorted frames (tb_frontend_upload_frames_undistort)
     // CUDA graphs of the launch sequences of small batches (the single-frame host entries are launch bound: ~50 launches
@@ -299,6 +301,7 @@ extern "C" int tb_frontend_level_layout(const tb_frontend *fe, int level, int bl
 {
     TB_DEVICE_GUARD(fe ? fe->ctx : nullptr);
     if (!fe || level < 0 || level >= fe->L) return TB_E_INVALID;
+    if (level >= 1) const_cast<tb_frontend *>(fe)->levels_exposed = true;
     if (base) *base = blurred ? fe->blur[level] : fe->pyr[level];
     if (pitch) *pitch = fe->g[level].pitch;
     if (frame_stride) *frame_stride = fe->g[level].frame_stride;
@@ -456,7 +459,7 @@ extern "C" int tb_frontend_build_pyramid(tb_frontend *fe, int n_frames)
     if (n_frames == 0) return TB_OK;
     tb_ctx *ctx = fe->ctx;
     static const bool pyr_async = !(getenv("TB_PYR_ASYNC") && atoi(getenv("TB_PYR_ASYNC")) == 0);   // A/B knob: 0 = build on the main stream
-    if (pyr_async && !ctx->profiling && n_frames >= 32) return pyramid_enqueue_async(fe, n_frames);
+    if (pyr_async && !ctx->profiling && n_frames >= 32 && !fe->levels_exposed) return pyramid_enqueue_async(fe, n_frames);
     if (ctx->profiling || !graph_worthwhile(fe, n_frames)) return pyramid_enqueue(fe, n_frames);
     const bool same = fe->g_pyramid.n_frames == n_frames;
     fe->g_pyramid.n_frames = n_frames;
