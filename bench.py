@@ -526,9 +526,11 @@ def run_ours(a):
     # measured 55.6 GB/s takes 9.55 ms, as long as the kernels) overlaps the kernels of the previous one.  The timed
     # region starts with an empty pipeline, so K steps cost about K uploads + one step of kernels + one readback.
     # TB_E2E_CHUNKS > 1 additionally splits a step into chunks of the batch (each chunk carries the first frame of the
-    # next one as its last frame so the k <-> k+1 matches across the boundary are still produced); measured slower
-    # (smaller launches are less efficient: 64-frame batches cost +15 % kernel time), so the default is 1.
-    NCH = max(1, min(int(os.environ.get('TB_E2E_CHUNKS', '1')), B // 16))
+    # next one as its last frame so the k <-> k+1 matches across the boundary are still produced).  Two chunks are the default
+    # since the kernels of a step (6 ms) fit well inside its upload (10 ms): the smaller launches cost kernel time that stays
+    # hidden, and only half a step of kernels is left behind the last upload (25.7 k against 25.4 k frames/s at 20 steps,
+    # 24.3 k against 23.1 k at 5; four chunks: 24.5 k).
+    NCH = max(1, min(int(os.environ.get('TB_E2E_CHUNKS', '2')), B // 16))
     NSLOT = int(os.environ.get('TB_E2E_SLOTS', '3'))
     bounds = [(c * B // NCH, (c + 1) * B // NCH) for c in range(NCH)]
     chunk_slots = []
