@@ -231,7 +231,7 @@ reject_with_f(const RfPair *__restrict__ pairs, float thr2, double confidence, i
     const RfPair pd = pairs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = min(*pd.count, pts_cap);
-    __shared__ int s_scan[RF_THREADS / 32], s_count, s_done, s_niters, s_iter, s_maxgood, s_nmodels[RF_CHUNK], s_good[RF_CHUNK * 3], s_nhyp;
+    __shared__ int s_scan[RF_THREADS / 32], s_done, s_niters, s_iter, s_maxgood, s_nmodels[RF_CHUNK], s_good[RF_CHUNK * 3], s_nhyp;
     __shared__ unsigned long long s_rng;
     __shared__ double s_best[9], s_models[RF_CHUNK * 27];
     __shared__ float2 s_sub[RF_CHUNK][14];   // the 7 + 7 points of every hypothesis of the chunk
